@@ -1,0 +1,1484 @@
+/* oracle/kanzi_oracle.c -- TEST INFRASTRUCTURE ONLY (never linked or loaded by the product).
+ *
+ * Plain-C, single-threaded restatement of kanzi's per-block transform -> entropy
+ * path (bitstream v6) written from the reference's behaviour, used as the CPU
+ * oracle of the parity tests.  Only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline leg may load it.
+ *
+ * PINNING: this restatement is checked byte-for-byte against the unmodified
+ * reference compiled into oracle/_ref/libkanzi_ref.so (tests/test_oracle_vs_ref.py,
+ * run in the build container) and against the committed fixtures in
+ * tests/golden/ that were generated from that same library (the reference ships
+ * no golden vectors of its own: SURVEY.md §8(c)).
+ *
+ * Each function cites the reference file:line it restates (paths under
+ * /root/reference/src).  Style is deliberately straight-line C; nothing here is
+ * tuned for speed.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef uint8_t u8;
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef int64_t i64;
+
+/* ------------------------------------------------------------------ bit I/O
+ * MSB-first packing.  bitstream/DefaultOutputBitStream.hpp:97-132 (writeBits),
+ * .cpp:42-128 (byte-array writes: whole bytes, then the TOP `rem` bits of the
+ * last byte), written() exact in bits after close (.hpp:73, .cpp:130-150).   */
+typedef struct {
+    u8* buf;
+    i64 cap;   /* bytes */
+    i64 bits;  /* bits written */
+    int overflow;
+} BitW;
+
+static void bw_init(BitW* w, u8* buf, i64 cap)
+{
+    w->buf = buf;
+    w->cap = cap;
+    w->bits = 0;
+    w->overflow = 0;
+    if (cap > 0)
+        memset(buf, 0, (size_t)cap);
+}
+
+static void bw_put(BitW* w, u64 v, int n)
+{
+    for (int k = n - 1; k >= 0; k--) {
+        const i64 byte = w->bits >> 3;
+        if (byte >= w->cap) {
+            w->overflow = 1;
+            w->bits++;
+            continue;
+        }
+        if ((v >> k) & 1)
+            w->buf[byte] |= (u8)(0x80 >> (w->bits & 7));
+        w->bits++;
+    }
+}
+
+static void bw_put_bytes(BitW* w, const u8* p, i64 nbits)
+{
+    i64 i = 0;
+    for (; nbits >= 8; nbits -= 8)
+        bw_put(w, p[i++], 8);
+    if (nbits > 0)
+        bw_put(w, (u64)(p[i] >> (8 - nbits)), (int)nbits);
+}
+
+/* bitstream/DefaultInputBitStream.hpp:88-150 */
+typedef struct {
+    const u8* buf;
+    i64 nbits; /* total bits available */
+    i64 pos;
+    int underflow;
+} BitR;
+
+static void br_init(BitR* r, const u8* buf, i64 nbits)
+{
+    r->buf = buf;
+    r->nbits = nbits;
+    r->pos = 0;
+    r->underflow = 0;
+}
+
+static u64 br_get(BitR* r, int n)
+{
+    u64 v = 0;
+    for (int k = 0; k < n; k++) {
+        u64 b = 0;
+        if (r->pos < r->nbits)
+            b = (r->buf[r->pos >> 3] >> (7 - (r->pos & 7))) & 1;
+        else
+            r->underflow = 1;
+        v = (v << 1) | b;
+        r->pos++;
+    }
+    return v;
+}
+
+static void br_get_bytes(BitR* r, u8* dst, i64 nbytes)
+{
+    for (i64 i = 0; i < nbytes; i++)
+        dst[i] = (u8)br_get(r, 8);
+}
+
+static int ilog2(u32 x) /* Global.hpp:91 _log2 */
+{
+    int r = 0;
+    while (x > 1) {
+        x >>= 1;
+        r++;
+    }
+    return r;
+}
+
+/* entropy/EntropyUtils.cpp:247-259 writeVarInt / :261-286 readVarInt */
+static void put_varint(BitW* w, u32 v)
+{
+    while (v >= 128) {
+        bw_put(w, 0x80 | (v & 0x7F), 8);
+        v >>= 7;
+    }
+    bw_put(w, v, 8);
+}
+
+static int get_varint(BitR* r, u32* out)
+{
+    u32 v = (u32)br_get(r, 8);
+    u32 res = v & 0x7F;
+    for (int shift = 7; v >= 128; shift += 7) {
+        v = (u32)br_get(r, 8);
+        if (shift == 28) {
+            if (v >= 128 || (v & 0x70))
+                return -1;
+            res |= (v & 0x0F) << shift;
+            break;
+        }
+        res |= (v & 0x7F) << shift;
+    }
+    *out = res;
+    return 0;
+}
+
+/* entropy/EntropyUtils.cpp:57-89 encodeAlphabet: "00" = all 256, "01" = empty,
+ * else "1", 5-bit index of the last non-zero mask byte, then the mask bytes
+ * (bit j of byte i = symbol 8i+j present).                                  */
+static void put_alphabet(BitW* w, const u32* alphabet, int count)
+{
+    if (count == 0) {
+        bw_put(w, 0, 1);
+        bw_put(w, 1, 1);
+    } else if (count == 256) {
+        bw_put(w, 0, 1);
+        bw_put(w, 0, 1);
+    } else {
+        u8 masks[32] = { 0 };
+        bw_put(w, 1, 1);
+        for (int i = 0; i < count; i++)
+            masks[alphabet[i] >> 3] |= (u8)(1 << (alphabet[i] & 7));
+        const int last = (int)(alphabet[count - 1] >> 3);
+        bw_put(w, (u64)last, 5);
+        bw_put_bytes(w, masks, 8 * (last + 1));
+    }
+}
+
+/* entropy/EntropyUtils.cpp:91-123 decodeAlphabet */
+static int get_alphabet(BitR* r, u32* alphabet)
+{
+    if (br_get(r, 1) == 0) {
+        const int n = (br_get(r, 1) == 0) ? 256 : 0;
+        for (int i = 0; i < n; i++)
+            alphabet[i] = (u32)i;
+        return n;
+    }
+    const int last = (int)br_get(r, 5);
+    int count = 0;
+    for (int i = 0; i <= last; i++) {
+        const u32 m = (u32)br_get(r, 8);
+        for (int j = 0; j < 8; j++)
+            if ((m >> j) & 1)
+                alphabet[count++] = (u32)(8 * i + j);
+    }
+    return count;
+}
+
+/* entropy/EntropyUtils.cpp:131-245 normalizeFrequencies (length fixed to 256).
+ * All arithmetic on freqs is uint32 (wrap-around included, :244).            */
+static int normalize_freqs(u32* freqs, u32* alphabet, u32 total, u32 scale)
+{
+    if (total == 0)
+        return 0;
+    int asz = 0;
+    if (total == scale) {
+        for (int i = 0; i < 256; i++)
+            if (freqs[i] != 0)
+                alphabet[asz++] = (u32)i;
+        return asz;
+    }
+    u32 sumScaled = 0, sumFreq = 0;
+    int idxMax = 0;
+    for (int i = 0; i < 256; i++) {
+        alphabet[i] = 0;
+        const u32 f = freqs[i];
+        if (f == 0)
+            continue;
+        alphabet[asz++] = (u32)i;
+        const i64 sf = (i64)f * (i64)scale;
+        const u32 sc = (sf <= (i64)total) ? 1u : (u32)((sf + ((i64)total >> 1)) / (i64)total);
+        sumScaled += sc;
+        freqs[i] = sc;
+        sumFreq += f;
+        if (sc > freqs[idxMax])
+            idxMax = i;
+        if (sumFreq >= total)
+            break;
+    }
+    if (asz == 0)
+        return 0;
+    if (asz == 1) {
+        freqs[alphabet[0]] = scale;
+        return 1;
+    }
+    if (sumScaled == scale)
+        return asz;
+    int delta = (int)(sumScaled - scale);
+    const int errThr = (int)freqs[idxMax] >> 4;
+    if (abs(delta) <= errThr) {
+        freqs[idxMax] -= (u32)delta;
+        return asz;
+    }
+    if (delta < 0) {
+        delta += errThr;
+        freqs[idxMax] += (u32)errThr;
+    } else {
+        delta -= errThr;
+        freqs[idxMax] -= (u32)errThr;
+    }
+    const int inc = (delta < 0) ? 1 : -1;
+    delta = abs(delta);
+    int round = 0;
+    while ((++round < 6) && (delta > 0)) {
+        int adjustments = 0;
+        for (int i = 0; i < asz; i++) {
+            const u32 idx = alphabet[i];
+            if (freqs[idx] <= 2)
+                continue;
+            freqs[idx] += (u32)inc;
+            adjustments++;
+            delta--;
+            if (delta == 0)
+                break;
+        }
+        if (adjustments == 0)
+            break;
+    }
+    {
+        const u32 v = freqs[idxMax] - (u32)delta;
+        freqs[idxMax] = (v > 1u) ? v : 1u;
+    }
+    return asz;
+}
+
+/* ------------------------------------------------------------------ rANS
+ * entropy/ANSRangeEncoder.hpp:92-116 ANSEncSymbol::reset                      */
+#define ANS_TOP (1 << 15)
+typedef struct {
+    int xMax, bias, cmplFreq, invShift;
+    u64 invFreq;
+} EncSym;
+
+static void encsym_reset(EncSym* s, int cum, int freq, int lr)
+{
+    if (freq >= (1 << lr))
+        freq = (1 << lr) - 1;
+    s->xMax = ((ANS_TOP >> lr) << 16) * freq;
+    s->cmplFreq = (1 << lr) - freq;
+    if (freq < 2) {
+        s->invFreq = 0xFFFFFFFFull;
+        s->invShift = 32;
+        s->bias = cum + (1 << lr) - 1;
+    } else {
+        int shift = 0;
+        while (freq > (1 << shift))
+            shift++;
+        s->invFreq = ((((u64)1 << (shift + 31)) + (u64)freq - 1) / (u64)freq) & 0xFFFFFFFFull;
+        s->invShift = 32 + shift - 1;
+        s->bias = cum;
+    }
+}
+
+/* entropy/ANSRangeEncoder.hpp:119-131 encodeSymbol (buffer grows downwards) */
+static int enc_step(u8** pp, int st, const EncSym* s)
+{
+    u8* p = *pp;
+    if (st >= s->xMax) {
+        *p-- = (u8)st;
+        *p-- = (u8)(st >> 8);
+        st >>= 16;
+    }
+    *pp = p;
+    return st + s->bias + (int)(((u64)(i64)st * s->invFreq) >> s->invShift) * s->cmplFreq;
+}
+
+/* entropy/ANSRangeEncoder.cpp:83-116 updateFrequencies + :119-155 encodeHeader
+ * (order 0: one table; order 1: 256 tables, freqs row stride 257).           */
+static int ans_write_tables(BitW* w, u32* freqs, EncSym* syms, int order, int lr)
+{
+    int res = 0;
+    const int endk = 255 * order + 1;
+    bw_put(w, (u64)(lr - 8), 3);
+    u32 alphabet[256];
+    for (int k = 0; k < endk; k++) {
+        u32* f = &freqs[k * 257];
+        const int asz = normalize_freqs(f, alphabet, f[256], 1u << lr);
+        if (asz > 0) {
+            int sum = 0, count = 0;
+            for (int i = 0; i < 256; i++) {
+                if (f[i] == 0)
+                    continue;
+                encsym_reset(&syms[(k << 8) + i], sum, (int)f[i], lr);
+                sum += (int)f[i];
+                if (++count >= asz)
+                    break;
+            }
+        }
+        put_alphabet(w, alphabet, asz);
+        if (asz > 1) {
+            const int chk = (asz >= 64) ? 8 : 6;
+            const int llr = ilog2((u32)lr) + 1;
+            for (int i = 1; i < asz; i += chk) {
+                const int endj = (i + chk < asz) ? i + chk : asz;
+                u32 mx = f[alphabet[i]] - 1;
+                for (int j = i + 1; j < endj; j++)
+                    if (f[alphabet[j]] - 1 > mx)
+                        mx = f[alphabet[j]] - 1;
+                const int logMax = (mx == 0) ? 0 : ilog2(mx) + 1;
+                bw_put(w, (u64)logMax, llr);
+                if (logMax == 0)
+                    continue;
+                for (int j = i; j < endj; j++)
+                    bw_put(w, f[alphabet[j]] - 1, logMax);
+            }
+        }
+        res += asz;
+    }
+    return res;
+}
+
+/* Global.cpp:170-309 computeHistogram as used by rebuildStatistics
+ * (ANSRangeEncoder.cpp:264-287): order 0 with total; order 1 = four quarter
+ * streams each starting in context 0, no total -> row totals are added here
+ * the way the order-1 "withTotal=false" call leaves them: NOT computed by the
+ * histogram; updateFrequencies reads f[256] ... see note in ans_encode.       */
+static void histo_o1_quarter(const u8* p, int len, u32* freqs)
+{
+    /* Global.cpp:271-307 (order 1, no total): length<32 -> single stream from
+     * context 0; else 4 sub-streams; sub-stream 0 starts in context 0, the
+     * others in the context of the byte preceding them.                       */
+    if (len < 32) {
+        u32 prv = 0;
+        for (int i = 0; i < len; i++) {
+            freqs[prv + p[i]]++;
+            prv = 256u * p[i];
+        }
+        return;
+    }
+    const int q = len >> 2;
+    for (int s = 0; s < 4; s++) {
+        u32 prv = (s == 0) ? 0 : 256u * p[s * q - 1];
+        const int end = (s == 3) ? len : (s + 1) * q;
+        for (int i = s * q; i < end; i++) {
+            freqs[prv + p[i]]++;
+            prv = 256u * p[i];
+        }
+    }
+}
+
+/* ANS block encoder.  entropy/ANSRangeEncoder.cpp:158-192 encode, :194-261
+ * encodeChunk, :264-287 rebuildStatistics.  chunkSize: order 0 -> 16384,
+ * order 1 -> 16384<<8; logRange 12 / 11 (ANSRangeEncoder.cpp:59-67).        */
+static void ans_encode(BitW* w, const u8* block, u32 count, int order)
+{
+    if (count <= 32) {
+        bw_put_bytes(w, block, 8 * (i64)count);
+        return;
+    }
+    const u32 chunkSize = (order == 0) ? 16384u : (16384u << 8);
+    const int lr = (order == 0) ? 12 : 11;
+    const int dim = 255 * order + 1;
+    u32* freqs = (u32*)malloc(sizeof(u32) * 257 * (size_t)dim);
+    EncSym* syms = (EncSym*)malloc(sizeof(EncSym) * 256 * (size_t)dim);
+    const u32 bufSize = 2 * chunkSize + 65536;
+    u8* buf = (u8*)malloc(bufSize);
+    u32 start = 0;
+    while (start < count) {
+        const u32 sz = (chunkSize < count - start) ? chunkSize : count - start;
+        const u8* b = block + start;
+        memset(freqs, 0, sizeof(u32) * 257 * (size_t)dim);
+        if (order == 0) {
+            for (u32 i = 0; i < sz; i++)
+                freqs[b[i]]++;
+            freqs[256] = sz;
+        } else {
+            /* rebuildStatistics :273-284 calls the order-1 histogram with
+             * withTotal=true on each quarter (row stride 257, totals kept).   */
+            const int quarter = (int)(sz >> 2);
+            u32* tmp = (u32*)calloc(65536, sizeof(u32));
+            if (quarter == 0) {
+                histo_o1_quarter(b, (int)sz, tmp);
+            } else {
+                for (int s = 0; s < 4; s++)
+                    histo_o1_quarter(b + s * quarter, quarter, tmp);
+            }
+            for (int c = 0; c < 256; c++) {
+                u32 tot = 0;
+                for (int s = 0; s < 256; s++) {
+                    freqs[c * 257 + s] = tmp[c * 256 + s];
+                    tot += tmp[c * 256 + s];
+                }
+                freqs[c * 257 + 256] = tot;
+            }
+            free(tmp);
+        }
+        const int asz = ans_write_tables(w, freqs, syms, order, lr);
+        if (asz <= 1 && order == 0) {
+            start += sz;
+            continue;
+        }
+        /* encodeChunk */
+        int st0 = ANS_TOP, st1 = ANS_TOP, st2 = ANS_TOP, st3 = ANS_TOP;
+        u8* p = &buf[bufSize - 1];
+        u8* const p0 = p;
+        const int end = (int)sz;
+        const int end4 = end & -4;
+        for (int i = end - 1; i >= end4; i--)
+            *p-- = b[i];
+        if (order == 0) {
+            for (int i = end4 - 1; i > 0; i -= 4) {
+                st0 = enc_step(&p, st0, &syms[b[i]]);
+                st1 = enc_step(&p, st1, &syms[b[i - 1]]);
+                st2 = enc_step(&p, st2, &syms[b[i - 2]]);
+                st3 = enc_step(&p, st3, &syms[b[i - 3]]);
+            }
+        } else {
+            const int quarter = end4 >> 2;
+            int i0 = quarter - 2, i1 = 2 * quarter - 2, i2 = 3 * quarter - 2, i3 = end4 - 2;
+            int prv0 = b[i0 + 1], prv1 = b[i1 + 1], prv2 = b[i2 + 1], prv3 = b[i3 + 1];
+            for (; i0 >= 0; i0--, i1--, i2--, i3--) {
+                const int c0 = b[i0], c1 = b[i1], c2 = b[i2], c3 = b[i3];
+                st0 = enc_step(&p, st0, &syms[(c0 << 8) | prv0]);
+                st1 = enc_step(&p, st1, &syms[(c1 << 8) | prv1]);
+                st2 = enc_step(&p, st2, &syms[(c2 << 8) | prv2]);
+                st3 = enc_step(&p, st3, &syms[(c3 << 8) | prv3]);
+                prv0 = c0;
+                prv1 = c1;
+                prv2 = c2;
+                prv3 = c3;
+            }
+            st0 = enc_step(&p, st0, &syms[prv0]);
+            st1 = enc_step(&p, st1, &syms[prv1]);
+            st2 = enc_step(&p, st2, &syms[prv2]);
+            st3 = enc_step(&p, st3, &syms[prv3]);
+        }
+        put_varint(w, (u32)(p0 - p));
+        bw_put(w, (u32)st0, 32);
+        bw_put(w, (u32)st1, 32);
+        bw_put(w, (u32)st2, 32);
+        bw_put(w, (u32)st3, 32);
+        if (p != p0)
+            bw_put_bytes(w, p + 1, 8 * (i64)(p0 - p));
+        start += sz;
+    }
+    free(buf);
+    free(syms);
+    free(freqs);
+}
+
+/* entropy/ANSRangeDecoder.cpp:80-175 decodeHeader, :177-216 decode, :218-292
+ * decodeChunk, ANSRangeDecoder.hpp:92-103 decodeSymbol.  Returns bytes
+ * decoded or -1.                                                             */
+static int ans_decode(BitR* r, u8* block, u32 count, int order)
+{
+    if (count <= 32) {
+        br_get_bytes(r, block, count);
+        return (int)count;
+    }
+    const u32 chunkSize = (order == 0) ? 16384u : (16384u << 8);
+    const int dim = 255 * order + 1;
+    u32* freqs = (u32*)malloc(sizeof(u32) * 256 * (size_t)dim);
+    u8* f2s = (u8*)malloc((size_t)dim << 15);
+    uint16_t* cumf = (uint16_t*)malloc(sizeof(uint16_t) * 256 * (size_t)dim);
+    uint16_t* frq = (uint16_t*)malloc(sizeof(uint16_t) * 256 * (size_t)dim);
+    const u32 bufSize = 2 * chunkSize;
+    u8* buf = (u8*)malloc(bufSize);
+    u32 alphabet[256];
+    u32 start = 0;
+    int rc = (int)count;
+    while (start < count && rc >= 0) {
+        const u32 sz = (chunkSize < count - start) ? chunkSize : count - start;
+        const int lr = 8 + (int)br_get(r, 3);
+        const u32 scale = 1u << lr;
+        const int llr = ilog2((u32)lr) + 1;
+        int total = 0, lastAsz = 0;
+        for (int k = 0; k < dim && rc >= 0; k++) {
+            const int asz = get_alphabet(r, alphabet);
+            if (asz == 0)
+                continue;
+            u32* f = &freqs[k << 8];
+            memset(f, 0, sizeof(u32) * 256);
+            const int chk = (asz >= 64) ? 8 : 6;
+            u32 sum = 0;
+            for (int i = 1; i < asz; i += chk) {
+                const u32 logMax = (u32)br_get(r, llr);
+                if (logMax > (u32)lr) {
+                    rc = -1;
+                    break;
+                }
+                const int endj = (i + chk < asz) ? i + chk : asz;
+                for (int j = i; j < endj; j++) {
+                    const u32 fr = (logMax == 0) ? 1u : (u32)br_get(r, (int)logMax) + 1u;
+                    if (fr >= scale)
+                        rc = -1;
+                    f[alphabet[j]] = fr;
+                    sum += fr;
+                }
+            }
+            if (rc < 0 || scale <= sum) {
+                rc = -1;
+                break;
+            }
+            f[alphabet[0]] = scale - sum;
+            sum = 0;
+            for (int i = 0; i < 256; i++) {
+                if (f[i] == 0)
+                    continue;
+                memset(&f2s[((size_t)k << lr) + sum], i, f[i]);
+                cumf[(k << 8) + i] = (uint16_t)sum;
+                frq[(k << 8) + i] = (f[i] >= scale) ? (uint16_t)(scale - 1) : (uint16_t)f[i];
+                sum += f[i];
+            }
+            total += asz;
+            lastAsz = asz;
+        }
+        if (rc < 0)
+            break;
+        if (total == 0) {
+            rc = (int)start;
+            break;
+        }
+        u8* out = block + start;
+        if (order == 0 && total == 1) {
+            (void)lastAsz;
+            memset(out, (int)alphabet[0], sz);
+            start += sz;
+            continue;
+        }
+        u32 psz;
+        if (get_varint(r, &psz) < 0 || psz >= (1u << 27) || psz > bufSize - 2) {
+            rc = -1;
+            break;
+        }
+        u32 st0 = (u32)br_get(r, 32), st1 = (u32)br_get(r, 32), st2 = (u32)br_get(r, 32), st3 = (u32)br_get(r, 32);
+        memset(buf, 0, bufSize);
+        br_get_bytes(r, buf, psz);
+        const u8* p = buf;
+        const u32 mask = scale - 1;
+        const int count4 = (int)sz & -4;
+#define DEC_STEP(st, k, s)                                                              \
+    do {                                                                                \
+        st = (u32)frq[((k) << 8) + (s)] * (st >> lr) + (st & mask) - cumf[((k) << 8) + (s)]; \
+        if (st < ANS_TOP) {                                                             \
+            st = (st << 16) | ((u32)p[0] << 8) | p[1];                                  \
+            p += 2;                                                                     \
+        }                                                                               \
+    } while (0)
+        if (order == 0) {
+            for (int i = 0; i < count4; i += 4) {
+                const u8 c3 = f2s[st3 & mask];
+                out[i] = c3;
+                DEC_STEP(st3, 0, c3);
+                const u8 c2 = f2s[st2 & mask];
+                out[i + 1] = c2;
+                DEC_STEP(st2, 0, c2);
+                const u8 c1 = f2s[st1 & mask];
+                out[i + 2] = c1;
+                DEC_STEP(st1, 0, c1);
+                const u8 c0 = f2s[st0 & mask];
+                out[i + 3] = c0;
+                DEC_STEP(st0, 0, c0);
+            }
+        } else {
+            const int quarter = count4 >> 2;
+            int prv0 = 0, prv1 = 0, prv2 = 0, prv3 = 0;
+            for (int i = 0; i < quarter; i++) {
+                const u8 c3 = f2s[((size_t)prv3 << lr) + (st3 & mask)];
+                const u8 c2 = f2s[((size_t)prv2 << lr) + (st2 & mask)];
+                const u8 c1 = f2s[((size_t)prv1 << lr) + (st1 & mask)];
+                const u8 c0 = f2s[((size_t)prv0 << lr) + (st0 & mask)];
+                DEC_STEP(st3, prv3, c3);
+                DEC_STEP(st2, prv2, c2);
+                DEC_STEP(st1, prv1, c1);
+                DEC_STEP(st0, prv0, c0);
+                out[3 * quarter + i] = c3;
+                out[2 * quarter + i] = c2;
+                out[quarter + i] = c1;
+                out[i] = c0;
+                prv3 = c3;
+                prv2 = c2;
+                prv1 = c1;
+                prv0 = c0;
+            }
+        }
+#undef DEC_STEP
+        for (u32 i = (u32)count4; i < sz; i++)
+            out[i] = *p++;
+        if (p != buf + psz) {
+            rc = -1;
+            break;
+        }
+        start += sz;
+    }
+    free(buf);
+    free(frq);
+    free(cumf);
+    free(f2s);
+    free(freqs);
+    return rc;
+}
+
+/* ------------------------------------------------------------------ ZRLT
+ * transform/ZRLT.cpp:27-117 forward.  Returns 1 (ok), 0 (stage refused).     */
+static int zrlt_forward(const u8* src, int n, u8* dst, int cap, int* outLen)
+{
+    *outLen = 0;
+    if (n == 0)
+        return 1;
+    if (cap < n) /* getMaxEncodedLength(n) == n, ZRLT.hpp:43 */
+        return 0;
+    u32 s = 0, d = 0;
+    const u32 sEnd = (u32)n, dEnd = (u32)cap;
+    while (s < sEnd) {
+        if (src[s] == 0) {
+            u32 run = 1;
+            while (s + run < sEnd && src[s + run] == 0)
+                run++;
+            s += run;
+            run++;
+            int lg = ilog2(run);
+            if ((u32)lg > dEnd - d)
+                return 0;
+            while (lg > 0) {
+                lg--;
+                dst[d++] = (u8)((run >> lg) & 1);
+            }
+            continue;
+        }
+        const int v = src[s];
+        const u32 need = (v >= 0xFE) ? 2u : 1u;
+        if (need > dEnd - d)
+            return 0;
+        if (v >= 0xFE) {
+            dst[d++] = 0xFF;
+            dst[d++] = (u8)(v - 0xFE);
+        } else {
+            dst[d++] = (u8)(v + 1);
+        }
+        s++;
+    }
+    *outLen = (int)d;
+    return 1;
+}
+
+/* transform/ZRLT.cpp:119-215 inverse */
+static int zrlt_inverse(const u8* src, int n, u8* dst, int cap, int* outLen)
+{
+    *outLen = 0;
+    if (n == 0)
+        return 1;
+    u32 s = 0, d = 0, run = 0;
+    const u32 sEnd = (u32)n, dEnd = (u32)cap;
+    for (;;) {
+        u32 v = src[s];
+        if (v <= 1) {
+            run = 1;
+            int ended = 0;
+            do {
+                run += run + v;
+                s++;
+                if (s >= sEnd) {
+                    ended = 1;
+                    break;
+                }
+                v = src[s];
+            } while (v <= 1);
+            if (ended)
+                break; /* goto End with run pending */
+            run--;
+            if (run > 0) {
+                if (run >= dEnd - d)
+                    break; /* goto End (run still > 0) */
+                memset(dst + d, 0, run);
+                d += run;
+                run = 0;
+                continue;
+            }
+        }
+        if (d >= dEnd)
+            return 0;
+        if (v == 0xFF) {
+            s++;
+            if (s >= sEnd)
+                return 0;
+            dst[d] = (u8)(0xFE + src[s]);
+        } else {
+            dst[d] = (u8)(v - 1);
+        }
+        s++;
+        d++;
+        if (s >= sEnd || d >= dEnd)
+            break;
+    }
+    if (run > 0) {
+        run--;
+        if (run > dEnd - d)
+            return 0;
+        if (run > 0) {
+            memset(dst + d, 0, run);
+            d += run;
+        }
+    }
+    *outLen = (int)d;
+    return s == sEnd;
+}
+
+/* ------------------------------------------------------------------ SBRT
+ * transform/SBRT.cpp:46-97 forward / :99-145 inverse; mode 1 MTFT, 2 RANK,
+ * 3 TIMESTAMP (:20-32 masks).                                                */
+static void sbrt_masks(int mode, int* m1, int* m2, int* sh)
+{
+    *m1 = (mode == 3) ? 0 : -1;
+    *m2 = (mode == 1) ? 0 : -1;
+    *sh = (mode == 2) ? 1 : 0;
+}
+
+static void sbrt_forward(const u8* src, int n, u8* dst, int mode)
+{
+    int m1, m2, sh, p[256] = { 0 }, q[256] = { 0 };
+    u8 s2r[256], r2s[256];
+    sbrt_masks(mode, &m1, &m2, &sh);
+    for (int i = 0; i < 256; i++)
+        s2r[i] = r2s[i] = (u8)i;
+    for (int i = 0; i < n; i++) {
+        const u8 c = src[i];
+        int r = s2r[c];
+        dst[i] = (u8)r;
+        const int qc = ((i & m1) + (p[c] & m2)) >> sh;
+        p[c] = i;
+        q[c] = qc;
+        while (r > 0 && q[r2s[r - 1]] <= qc) {
+            r2s[r] = r2s[r - 1];
+            s2r[r2s[r]] = (u8)r;
+            r--;
+        }
+        r2s[r] = c;
+        s2r[c] = (u8)r;
+    }
+}
+
+static void sbrt_inverse(const u8* src, int n, u8* dst, int mode)
+{
+    int m1, m2, sh, p[256] = { 0 }, q[256] = { 0 };
+    u8 r2s[256];
+    sbrt_masks(mode, &m1, &m2, &sh);
+    for (int i = 0; i < 256; i++)
+        r2s[i] = (u8)i;
+    for (int i = 0; i < n; i++) {
+        int r = src[i];
+        const int c = r2s[r];
+        dst[i] = (u8)c;
+        const int qc = ((i & m1) + (p[c] & m2)) >> sh;
+        p[c] = i;
+        q[c] = qc;
+        while (r > 0 && q[r2s[r - 1]] <= qc) {
+            r2s[r] = r2s[r - 1];
+            r--;
+        }
+        r2s[r] = (u8)c;
+    }
+}
+
+/* ------------------------------------------------------------------ BWT
+ * The BWT is canonical: any correct suffix sorter yields the reference's bytes.
+ * Restates the OUTPUT CONTRACT of BWT::forward (transform/BWT.cpp:92-134) and
+ * DivSufSort::computeBWT/constructBWT (transform/DivSufSort.cpp:171-295):
+ *   out[0] = in[n-1]; suffix rank r (end-of-string smallest) of suffix p>=1 goes to
+ *   out[r + (r < rank(0))] = in[p-1];  primaryIndex[k] = rank(k*step)+1,
+ *   step = ceil(n/chunks), chunks = 8 if n >= 256 else 1 (BWT.hpp:130).
+ * Suffix ranks by prefix doubling with two counting-sort passes per round.   */
+static void suffix_ranks(const u8* s, int n, int* rank)
+{
+    int* sa = (int*)malloc(sizeof(int) * (size_t)n);
+    int* tmp = (int*)malloc(sizeof(int) * (size_t)n);
+    int* cnt = (int*)malloc(sizeof(int) * ((size_t)n + 2));
+    int* nr = (int*)malloc(sizeof(int) * (size_t)n);
+    {
+        int c[257] = { 0 };
+        for (int i = 0; i < n; i++)
+            c[s[i] + 1]++;
+        for (int i = 0; i < 256; i++)
+            c[i + 1] += c[i];
+        for (int i = 0; i < n; i++)
+            rank[i] = c[s[i]]; /* bucket start */
+        int c2[257];
+        memcpy(c2, c, sizeof(c));
+        for (int i = 0; i < n; i++)
+            sa[c2[s[i]]++] = i;
+    }
+    for (int h = 1;; h <<= 1) {
+        /* pass 1: by second key (rank[i+h]+1, 0 if past the end) */
+        memset(cnt, 0, sizeof(int) * ((size_t)n + 2));
+        for (int i = 0; i < n; i++)
+            cnt[((i + h < n) ? rank[i + h] + 1 : 0) + 1]++;
+        for (int i = 0; i <= n; i++)
+            cnt[i + 1] += cnt[i];
+        for (int j = 0; j < n; j++) {
+            const int i = sa[j];
+            tmp[cnt[(i + h < n) ? rank[i + h] + 1 : 0]++] = i;
+        }
+        /* pass 2: stable by first key */
+        memset(cnt, 0, sizeof(int) * ((size_t)n + 2));
+        for (int i = 0; i < n; i++)
+            cnt[rank[i] + 1]++;
+        for (int i = 0; i < n; i++)
+            cnt[i + 1] += cnt[i];
+        for (int j = 0; j < n; j++) {
+            const int i = tmp[j];
+            sa[cnt[rank[i]]++] = i;
+        }
+        int distinct = 0;
+        for (int j = 0; j < n; j++) {
+            const int i = sa[j];
+            if (j > 0) {
+                const int pi = sa[j - 1];
+                const int a1 = (i + h < n) ? rank[i + h] : -1;
+                const int a0 = (pi + h < n) ? rank[pi + h] : -1;
+                if (rank[i] == rank[pi] && a1 == a0) {
+                    nr[i] = nr[pi];
+                    continue;
+                }
+            }
+            nr[i] = j;
+            distinct++;
+        }
+        memcpy(rank, nr, sizeof(int) * (size_t)n);
+        if (distinct == n || h >= n)
+            break;
+    }
+    free(nr);
+    free(cnt);
+    free(tmp);
+    free(sa);
+}
+
+static int bwt_chunks(int n) { return (n < 256) ? 1 : 8; }
+
+static void bwt_forward(const u8* in, int n, u8* out, int* pidx /*[8]*/)
+{
+    memset(pidx, 0, sizeof(int) * 8);
+    if (n == 1) { /* BWT.cpp:109-115: single byte copied, no index touched */
+        out[0] = in[0];
+        return;
+    }
+    int* rank = (int*)malloc(sizeof(int) * (size_t)n);
+    suffix_ranks(in, n, rank);
+    const int chunks = bwt_chunks(n);
+    const int st = n / chunks;
+    const int step = (chunks * st == n) ? st : st + 1;
+    out[0] = in[n - 1];
+    for (int p = 1; p < n; p++)
+        out[rank[p] + (rank[p] < rank[0] ? 1 : 0)] = in[p - 1];
+    for (int p = 0; p < n; p += step)
+        if (p / step < 8)
+            pidx[p / step] = rank[p] + 1;
+    free(rank);
+}
+
+/* transform/BWT.cpp:169-292 / :295-657: both inverse variants produce the
+ * original text; restated as the plain psi walk from primaryIndex[0].        */
+static int bwt_inverse(const u8* in, int n, u8* out, const int* pidx)
+{
+    if (n == 1) {
+        out[0] = in[0];
+        return 1;
+    }
+    const int p0 = pidx[0];
+    if (p0 <= 0 || p0 > n)
+        return 0;
+    u32 c[257] = { 0 };
+    for (int i = 0; i < n; i++)
+        c[in[i] + 1]++;
+    for (int i = 0; i < 256; i++)
+        c[i + 1] += c[i];
+    u32* nxt = (u32*)malloc(sizeof(u32) * (size_t)n);
+    for (int i = 0; i < n; i++) {
+        const u32 idx = (i == 0) ? 0u : ((i < p0) ? (u32)(i - 1) : (u32)i);
+        nxt[c[in[i]]++] = idx;
+    }
+    /* symbol of sorted position t = F[t]; recover from the bucket bounds */
+    u32 start[257] = { 0 };
+    for (int i = 0; i < n; i++)
+        start[in[i] + 1]++;
+    for (int i = 0; i < 256; i++)
+        start[i + 1] += start[i];
+    u8* F = (u8*)malloc((size_t)n);
+    for (int s = 0; s < 256; s++)
+        memset(F + start[s], s, start[s + 1] - start[s]);
+    u32 t = (u32)(p0 - 1);
+    for (int k = 0; k < n; k++) {
+        out[k] = F[t];
+        t = nxt[t];
+    }
+    free(F);
+    free(nxt);
+    return 1;
+}
+
+/* transform/BWTBlockCodec.cpp:32-87 forward (v6 header: mode byte then
+ * chunks x pIndexSize big-endian bytes of primaryIndex-1).                    */
+static int bwtcodec_forward(const u8* in, int n, u8* out, int cap, int* outLen)
+{
+    *outLen = 0;
+    if (n == 0)
+        return 1;
+    if (cap < n + 33)
+        return 0;
+    int lg = ilog2((u32)n);
+    if (n & (n - 1))
+        lg++;
+    const int pisz = (lg + 7) >> 3;
+    if (pisz <= 0 || pisz >= 5)
+        return 0;
+    const int chunks = bwt_chunks(n);
+    const int hdr = 1 + chunks * pisz;
+    int pidx[8];
+    bwt_forward(in, n, out + hdr, pidx);
+    out[0] = (u8)((ilog2((u32)chunks) << 2) | (pisz - 1));
+    int k = 1;
+    for (int i = 0; i < chunks; i++) {
+        const int v = pidx[i] - 1;
+        for (int sh = (pisz - 1) << 3; sh >= 0; sh -= 8)
+            out[k++] = (u8)(v >> sh);
+    }
+    *outLen = n + hdr;
+    return 1;
+}
+
+/* transform/BWTBlockCodec.cpp:89-168 inverse (bsVersion 6 branch) */
+static int bwtcodec_inverse(const u8* in, int n, u8* out, int cap, int* outLen)
+{
+    *outLen = 0;
+    if (n <= 1)
+        return n == 0;
+    const int mode = in[0];
+    const int chunks = 1 << ((mode >> 2) & 7);
+    const int pisz = (mode & 3) + 1;
+    const int hdr = 1 + chunks * pisz;
+    if (n < hdr)
+        return 0;
+    if (chunks != bwt_chunks(n - hdr))
+        return 0;
+    int pidx[8] = { 0 };
+    int k = 1;
+    for (int i = 0; i < chunks; i++) {
+        u32 v = 0;
+        for (int b = 0; b < pisz; b++)
+            v = (v << 8) | in[k++];
+        if (v >= 0x7FFFFFFFu)
+            return 0;
+        if (i < 8)
+            pidx[i] = (int)v + 1;
+    }
+    const int m = n - hdr;
+    if (m > cap)
+        return 0;
+    if (m == 0)
+        return 1;
+    if (!bwt_inverse(in + hdr, m, out, pidx))
+        return 0;
+    *outLen = m;
+    return 1;
+}
+
+/* ------------------------------------------------------------------ sequence
+ * transform ids: transform/TransformFactory.hpp:49-73.                       */
+enum { T_NONE = 0, T_BWT = 1, T_ZRLT = 6, T_MTFT = 7, T_RANK = 8 };
+
+static int stage_max_len(int t, int n) /* getMaxEncodedLength of each stage */
+{
+    return (t == T_BWT) ? n + 33 : n; /* BWTBlockCodec.hpp:47-50; others srcLen */
+}
+
+static int stage_forward(int t, const u8* in, int n, u8* out, int cap, int* outLen)
+{
+    switch (t) {
+    case T_NONE: /* NullTransform: plain copy */
+        if (cap < n)
+            return 0;
+        memcpy(out, in, (size_t)n);
+        *outLen = n;
+        return 1;
+    case T_BWT:
+        return bwtcodec_forward(in, n, out, cap, outLen);
+    case T_ZRLT:
+        return zrlt_forward(in, n, out, cap, outLen);
+    case T_MTFT:
+    case T_RANK:
+        if (n > cap)
+            return 0;
+        sbrt_forward(in, n, out, (t == T_MTFT) ? 1 : 2);
+        *outLen = n;
+        return 1;
+    default:
+        return -1;
+    }
+}
+
+static int stage_inverse(int t, const u8* in, int n, u8* out, int cap, int* outLen)
+{
+    switch (t) {
+    case T_NONE:
+        if (cap < n)
+            return 0;
+        memcpy(out, in, (size_t)n);
+        *outLen = n;
+        return 1;
+    case T_BWT:
+        return bwtcodec_inverse(in, n, out, cap, outLen);
+    case T_ZRLT:
+        return zrlt_inverse(in, n, out, cap, outLen);
+    case T_MTFT:
+    case T_RANK:
+        if (n > cap)
+            return 0;
+        sbrt_inverse(in, n, out, (t == T_MTFT) ? 1 : 2);
+        *outLen = n;
+        return 1;
+    default:
+        return -1;
+    }
+}
+
+/* Split the 48-bit transform word (first stage in the top 6 bits) the way
+ * TransformFactory::newTransform does (TransformFactory.hpp:208-223): slot 0 is
+ * always instantiated, later NONE slots are dropped.                         */
+static int split_types(u64 ttype, int* types)
+{
+    int n = 0;
+    for (int i = 0; i < 8; i++) {
+        const int t = (int)((ttype >> (42 - 6 * i)) & 63);
+        if (t != T_NONE || i == 0)
+            types[n++] = t;
+    }
+    return n;
+}
+
+/* transform/TransformSequence.hpp:88-162 forward.  The reference ping-pongs
+ * between the caller's two buffers (capacities inCap / outCap) and falls back
+ * to a private buffer of `required` bytes when one is too small; capacities
+ * matter because ZRLT refuses to run when its output would not fit.
+ * Returns post-transform length, sets *skipFlags (bit 7-i = stage i skipped). */
+static int sequence_forward(u64 ttype, const u8* in, int n, int inCap, u8* out, int outCap, int* skipFlags)
+{
+    int types[8];
+    const int nt = split_types(ttype, types);
+    int required = n;
+    for (int i = 0; i < nt; i++) {
+        const int m = stage_max_len(types[i], required);
+        if (m > required)
+            required = m;
+    }
+    const int big = (required > inCap ? required : inCap) > outCap ? (required > inCap ? required : inCap) : outCap;
+    u8* bufs[3];
+    int caps[3];
+    bufs[0] = (u8*)malloc((size_t)big + 64); /* plays the role of `input`  */
+    bufs[1] = (u8*)malloc((size_t)big + 64); /* plays the role of `output` */
+    bufs[2] = NULL;                           /* private `buffer`           */
+    caps[0] = inCap;
+    caps[1] = outCap;
+    caps[2] = 0;
+    memcpy(bufs[0], in, (size_t)n);
+    int ci = 0, co = 1, count = n, swaps = 0, flags = 0xFF;
+    for (int i = 0; i < nt; i++) {
+        if (caps[co] < required) {
+            if (co == 0 || co == 1)
+                co = 2;
+            if (caps[2] < required) {
+                free(bufs[2]);
+                bufs[2] = (u8*)malloc((size_t)required + 64);
+                caps[2] = required;
+            }
+        }
+        int produced = 0;
+        if (stage_forward(types[i], bufs[ci], count, bufs[co], caps[co], &produced) != 1)
+            continue;
+        flags &= ~(1 << (7 - i));
+        count = produced;
+        const int t = ci;
+        ci = co;
+        co = t;
+        swaps++;
+    }
+    int result = count;
+    if ((swaps & 1) == 0) {
+        if (count > outCap || count > caps[ci])
+            flags = 0xFF;
+        else
+            memmove(out, bufs[ci], (size_t)count);
+    } else {
+        /* odd number of swaps: the last stage wrote straight into `output`
+         * (index 1) because EncodingTask sizes it >= required (:733-739).      */
+        memcpy(out, bufs[ci], (size_t)count);
+    }
+    *skipFlags = flags;
+    free(bufs[0]);
+    free(bufs[1]);
+    free(bufs[2]);
+    return result;
+}
+
+/* transform/TransformSequence.hpp:165-247 inverse */
+static int sequence_inverse(u64 ttype, int skipFlags, const u8* in, int n, u8* out, int outCap, int* outLen)
+{
+    int types[8];
+    const int nt = split_types(ttype, types);
+    *outLen = 0;
+    if (n == 0)
+        return 1;
+    if (n > outCap)
+        return 0;
+    if ((skipFlags & 0xFF) == 0xFF) {
+        memmove(out, in, (size_t)n);
+        *outLen = n;
+        return 1;
+    }
+    u8* a = (u8*)malloc((size_t)outCap + 64);
+    u8* b = (u8*)malloc((size_t)outCap + 64);
+    u8* cur = a;
+    u8* nxt = b;
+    const int aCap = outCap; /* every working buffer is at least output._length */
+    if (n > outCap) {
+        free(a);
+        free(b);
+        return 0;
+    }
+    memcpy(cur, in, (size_t)n);
+    int count = n, ok = 1;
+    for (int i = nt - 1; i >= 0 && ok; i--) {
+        if (skipFlags & (1 << (7 - i)))
+            continue;
+        int produced = 0;
+        if (stage_inverse(types[i], cur, count, nxt, aCap, &produced) != 1) {
+            ok = 0;
+            break;
+        }
+        count = produced;
+        u8* t = cur;
+        cur = nxt;
+        nxt = t;
+    }
+    if (ok) {
+        memcpy(out, cur, (size_t)count);
+        *outLen = count;
+    }
+    free(a);
+    free(b);
+    return ok;
+}
+
+/* ------------------------------------------------------------------ blocks
+ * entropy ids: entropy/EntropyEncoderFactory.hpp:37-52.                      */
+enum { E_NONE = 0, E_ANS0 = 5, E_ANS1 = 8 };
+
+static int entropy_encode(BitW* w, int etype, const u8* p, u32 n)
+{
+    switch (etype) {
+    case E_NONE: /* NullEntropyEncoder: raw bytes */
+        bw_put_bytes(w, p, 8 * (i64)n);
+        return 0;
+    case E_ANS0:
+        ans_encode(w, p, n, 0);
+        return 0;
+    case E_ANS1:
+        ans_encode(w, p, n, 1);
+        return 0;
+    default:
+        return -1;
+    }
+}
+
+static int entropy_decode(BitR* r, int etype, u8* p, u32 n)
+{
+    switch (etype) {
+    case E_NONE:
+        br_get_bytes(r, p, n);
+        return (int)n;
+    case E_ANS0:
+        return ans_decode(r, p, n, 0);
+    case E_ANS1:
+        return ans_decode(r, p, n, 1);
+    default:
+        return -1;
+    }
+}
+
+/* One block exactly as EncodingTask::run builds it in its private buffer
+ * (io/CompressedOutputStream.cpp:652-898, checksum off, skipBlocks off):
+ * mode byte, [skip-flag byte], post-transform length, entropy payload.
+ * dataCap / bufCap model _data->_length / _buffer->_length (the two ping-pong
+ * capacities handed to TransformSequence::forward).  Returns bit count.       */
+static i64 encode_block(const u8* in, int n, u64 ttype, int etype, int dataCap, int bufCap, u8* out, i64 outCap)
+{
+    BitW w;
+    bw_init(&w, out, outCap);
+    int mode = 0, flags = 0xFF, post = n, ntr = 1;
+    u8* tbuf = NULL;
+    const u8* payload = in;
+    if (n <= 15) { /* SMALL_BLOCK_SIZE :38,691-695 */
+        mode |= 0x80;
+        ttype = 0;
+        etype = E_NONE;
+    }
+    {
+        int types[8];
+        ntr = split_types(ttype, types);
+        int required = n;
+        for (int i = 0; i < ntr; i++) {
+            const int m = stage_max_len(types[i], required);
+            if (m > required)
+                required = m;
+        }
+        if (bufCap < required)
+            bufCap = required; /* :733-739 */
+        tbuf = (u8*)malloc((size_t)bufCap + 64);
+        post = sequence_forward(ttype, in, n, dataCap, tbuf, bufCap, &flags);
+        payload = tbuf;
+    }
+    const int dataSize = (post < 256) ? 1 : (ilog2((u32)post) >> 3) + 1;
+    mode |= ((dataSize - 1) & 3) << 5;
+    if ((mode & 0x80) || ntr <= 4) {
+        mode |= (flags >> 4) & 0x0F;
+        bw_put(&w, (u64)mode, 8);
+    } else {
+        mode |= 0x10;
+        bw_put(&w, (u64)mode, 8);
+        bw_put(&w, (u64)flags, 8);
+    }
+    bw_put(&w, (u64)post, 8 * dataSize);
+    entropy_encode(&w, etype, payload, (u32)post);
+    free(tbuf);
+    return w.overflow ? -1 : w.bits;
+}
+
+/* io/CompressedInputStream.cpp:791-1041 DecodingTask::run (payload part) */
+static int decode_block(const u8* in, i64 nbits, u64 ttype, int etype, int blockSize, u8* out, int outCap)
+{
+    BitR r;
+    br_init(&r, in, nbits);
+    const int mode = (int)br_get(&r, 8);
+    int flags = 0;
+    if (mode & 0x80) {
+        ttype = 0;
+        etype = E_NONE;
+    } else if (mode & 0x10) {
+        flags = (int)br_get(&r, 8);
+    } else {
+        flags = ((mode << 4) | 0x0F) & 0xFF;
+    }
+    const int dataSize = 1 + ((mode >> 5) & 3);
+    const int pre = (int)br_get(&r, 8 * dataSize);
+    /* DecodingTask's _blockLength = blockSize + max(512, blockSize/16)
+     * (CompressedInputStream.cpp:275): capacity of the task's data buffer.     */
+    const int blkLen = blockSize + ((blockSize >> 4) > 512 ? (blockSize >> 4) : 512);
+    int maxT = blkLen + blkLen / 2;
+    if (maxT < 2048)
+        maxT = 2048;
+    if (pre <= 0 || pre > maxT)
+        return -1;
+    const int tmpCap = (pre + 512 > blkLen) ? pre + 512 : blkLen; /* :935 */
+    u8* tmp = (u8*)malloc((size_t)tmpCap + 64);
+    u8* data = (u8*)malloc((size_t)blkLen + 64);
+    int rc = -1;
+    if (entropy_decode(&r, etype, tmp, (u32)pre) == pre && !r.underflow) {
+        int produced = 0;
+        if (sequence_inverse(ttype, flags, tmp, pre, data, blkLen, &produced) && produced <= outCap) {
+            memcpy(out, data, (size_t)produced);
+            rc = produced;
+        }
+    }
+    free(data);
+    free(tmp);
+    return rc;
+}
+
+/* Stream header, io/CompressedOutputStream.cpp:277-342 */
+static void put_stream_header(BitW* w, u64 ttype, int etype, int blockSize, i64 inputSize)
+{
+    bw_put(w, 0x4B414E5A, 32);
+    bw_put(w, 6, 4);
+    bw_put(w, 0, 2); /* checksum size */
+    bw_put(w, (u64)etype, 5);
+    bw_put(w, ttype, 48);
+    bw_put(w, (u64)(blockSize >> 4), 28);
+    int szMask = 0;
+    if (inputSize != 0 && inputSize < ((i64)1 << 48)) {
+        int lg = 0;
+        u64 x = (u64)inputSize;
+        while (x > 1) {
+            x >>= 1;
+            lg++;
+        }
+        szMask = (lg >> 4) + 1;
+    }
+    bw_put(w, (u64)szMask, 2);
+    if (szMask)
+        bw_put(w, (u64)inputSize, 16 * szMask);
+    bw_put(w, 0, 15);
+    const u32 HASH = 0x1E35A7BDu;
+    u32 ck = HASH * (0x01030507u * 6u);
+    ck ^= HASH * (u32)~0u; /* ~ckSize with ckSize = 0 */
+    ck ^= HASH * (u32)~(u32)etype;
+    ck ^= HASH * (u32)((~ttype) >> 32);
+    ck ^= HASH * (u32)(~ttype);
+    ck ^= HASH * (u32)~(u32)blockSize;
+    if (szMask) {
+        ck ^= HASH * (u32)((~(u64)inputSize) >> 32);
+        ck ^= HASH * (u32)(~(u64)inputSize);
+    }
+    ck = (ck >> 23) ^ (ck >> 3);
+    bw_put(w, ck & 0xFFFFFFu, 24);
+}
+
+/* ================================================================== exports */
+#define API __attribute__((visibility("default")))
+
+API i64 ko_entropy_encode(int etype, const u8* in, int n, u8* out, i64 cap)
+{
+    BitW w;
+    bw_init(&w, out, cap);
+    if (entropy_encode(&w, etype, in, (u32)n) < 0 || w.overflow)
+        return -1;
+    return w.bits;
+}
+
+API int ko_entropy_decode(int etype, const u8* in, i64 nbits, u8* out, int n)
+{
+    BitR r;
+    br_init(&r, in, nbits);
+    const int rc = entropy_decode(&r, etype, out, (u32)n);
+    return r.underflow ? -1 : rc;
+}
+
+API int ko_stage_forward(int t, const u8* in, int n, u8* out, int cap, int* outLen) { return stage_forward(t, in, n, out, cap, outLen); }
+API int ko_stage_inverse(int t, const u8* in, int n, u8* out, int cap, int* outLen) { return stage_inverse(t, in, n, out, cap, outLen); }
+API void ko_bwt_forward(const u8* in, int n, u8* out, int* pidx) { bwt_forward(in, n, out, pidx); }
+API int ko_bwt_inverse(const u8* in, int n, u8* out, const int* pidx) { return bwt_inverse(in, n, out, pidx); }
+API void ko_suffix_ranks(const u8* in, int n, int* rank) { suffix_ranks(in, n, rank); }
+
+API int ko_sequence_forward(u64 ttype, const u8* in, int n, int inCap, u8* out, int outCap, int* skipFlags)
+{
+    return sequence_forward(ttype, in, n, inCap, out, outCap, skipFlags);
+}
+
+API int ko_sequence_inverse(u64 ttype, int skipFlags, const u8* in, int n, u8* out, int outCap, int* outLen)
+{
+    return sequence_inverse(ttype, skipFlags, in, n, out, outCap, outLen);
+}
+
+API i64 ko_encode_block(const u8* in, int n, u64 ttype, int etype, int dataCap, int bufCap, u8* out, i64 outCap)
+{
+    return encode_block(in, n, ttype, etype, dataCap, bufCap, out, outCap);
+}
+
+API int ko_decode_block(const u8* in, i64 nbits, u64 ttype, int etype, int blockSize, u8* out, int outCap)
+{
+    return decode_block(in, nbits, ttype, etype, blockSize, out, outCap);
+}
+
+/* Whole stream with the jobs=1 buffer model of CompressedOutputStream
+ * (:138-146, :447-474): _buffers[0] = max(bs + bs/8, 256 KiB) is the data buffer
+ * of every block; the transform buffer keeps the largest `required` seen.     */
+API i64 ko_stream_compress(const u8* in, i64 n, u64 ttype, int etype, int blockSize, u8* out, i64 cap)
+{
+    BitW w;
+    bw_init(&w, out, cap);
+    put_stream_header(&w, ttype, etype, blockSize, n);
+    const int dataCap = (blockSize + (blockSize >> 3) > 262144) ? blockSize + (blockSize >> 3) : 262144;
+    int bufCap = 0;
+    const i64 tmpCap = (i64)blockSize + (blockSize >> 1) + 65536;
+    u8* tmp = (u8*)malloc((size_t)tmpCap);
+    for (i64 off = 0; off < n; off += blockSize) {
+        const int len = (n - off < blockSize) ? (int)(n - off) : blockSize;
+        /* required size of this block's sequence */
+        int types[8];
+        u64 tt = (len <= 15) ? 0 : ttype;
+        const int nt = split_types(tt, types);
+        int required = len;
+        for (int i = 0; i < nt; i++) {
+            const int m = stage_max_len(types[i], required);
+            if (m > required)
+                required = m;
+        }
+        if (bufCap < required)
+            bufCap = required;
+        const i64 bits = encode_block(in + off, len, ttype, etype, dataCap, bufCap, tmp, tmpCap);
+        if (bits < 0) {
+            free(tmp);
+            return -1;
+        }
+        const u32 lw = (bits < 8) ? 3u : (u32)ilog2((u32)(bits >> 3)) + 4u;
+        bw_put(&w, lw - 3, 5);
+        bw_put(&w, (u64)bits, (int)lw);
+        bw_put_bytes(&w, tmp, bits);
+    }
+    bw_put(&w, 0, 5);
+    bw_put(&w, 0, 3);
+    free(tmp);
+    if (w.overflow)
+        return -1;
+    return (w.bits + 7) >> 3;
+}
+
+/* io/CompressedInputStream.cpp:511-663 readHeader (+ block loop) */
+API i64 ko_stream_decompress(const u8* in, i64 n, u8* out, i64 cap)
+{
+    BitR r;
+    br_init(&r, in, 8 * n);
+    if (br_get(&r, 32) != 0x4B414E5A)
+        return -1;
+    if (br_get(&r, 4) != 6)
+        return -2;
+    if (br_get(&r, 2) != 0)
+        return -3; /* checksums: not restated */
+    const int etype = (int)br_get(&r, 5);
+    const u64 ttype = br_get(&r, 48);
+    const int blockSize = (int)br_get(&r, 28) << 4;
+    const int szMask = (int)br_get(&r, 2);
+    if (szMask)
+        br_get(&r, 16 * szMask);
+    br_get(&r, 15);
+    br_get(&r, 24);
+    i64 produced = 0;
+    u8* tmp = NULL;
+    i64 tmpCap = 0;
+    for (;;) {
+        const int lr = 3 + (int)br_get(&r, 5);
+        const u64 bits = br_get(&r, lr);
+        if (bits == 0 || r.underflow)
+            break;
+        const i64 nb = (i64)((bits + 7) >> 3);
+        if (nb > tmpCap) {
+            free(tmp);
+            tmpCap = nb + 64;
+            tmp = (u8*)malloc((size_t)tmpCap);
+        }
+        memset(tmp, 0, (size_t)nb);
+        for (u64 k = 0; k < bits; k++) { /* re-align the block to byte 0 */
+            if (br_get(&r, 1))
+                tmp[k >> 3] |= (u8)(0x80 >> (k & 7));
+        }
+        const i64 room = cap - produced;
+        const int rc = decode_block(tmp, (i64)bits, ttype, etype, blockSize, out + produced,
+            (int)((room < blockSize) ? room : blockSize));
+        if (rc < 0) {
+            free(tmp);
+            return -4;
+        }
+        produced += rc;
+    }
+    free(tmp);
+    return produced;
+}

@@ -1,0 +1,73 @@
+"""Pins the plain-C oracle (oracle/kanzi_oracle.c) against the unmodified reference
+(oracle/_ref, built here from /root/reference).  CPU only; skipped where the
+reference library is absent."""
+import numpy as np
+import pytest
+
+import synth
+from cases import small_cases, rng_bytes
+
+CASES = small_cases()
+
+
+@pytest.mark.parametrize("ename", ["ANS0", "ANS1", "NONE"])
+def test_entropy_encode_matches_ref(oracle, ref, ename):
+    for name, data in CASES.items():
+        if data.size == 0:
+            continue
+        a, abits = oracle.entropy_encode(ename, data)
+        b, bbits = ref.entropy_encode(ename, data)
+        assert abits == bbits, (name, abits, bbits)
+        assert np.array_equal(a, b), name
+        dec, rc = oracle.entropy_decode(ename, b, bbits, data.size)
+        assert rc == data.size and np.array_equal(dec, data), name
+
+
+@pytest.mark.parametrize("tname", ["ZRLT", "RANK", "MTFT", "BWT", "BWT+RANK+ZRLT", "BWT+MTFT+ZRLT", "RANK+ZRLT"])
+def test_sequence_forward_matches_ref(oracle, ref, tname):
+    for name, data in CASES.items():
+        n = data.size
+        for in_cap, out_cap in ((n + n // 8 + 64, n + 33), (n, n), (n + 33, n + 33)):
+            if "BWT" in tname and out_cap < n + 33:
+                continue
+            a, af = oracle.sequence_forward(tname, data, in_cap, out_cap)
+            b, bf, ok = ref.sequence_forward(tname, data, in_cap, out_cap)
+            assert af == bf, (name, tname, in_cap, out_cap, af, bf)
+            if af != 0xFF:
+                assert np.array_equal(a, b), (name, tname, in_cap, out_cap)
+                back, ok2 = oracle.sequence_inverse(tname, bf, b, n + 64)
+                assert ok2 == 1 and np.array_equal(back, data), (name, tname)
+                back2, ok3 = ref.sequence_inverse(tname, bf, b, n + 64)
+                assert ok3 == 1 and np.array_equal(back2, data), (name, tname)
+
+
+def test_bwt_matches_ref(oracle, ref):
+    for name, data in CASES.items():
+        if data.size < 2:
+            continue
+        a, ap = oracle.bwt_forward(data)
+        b, bp = ref.bwt_forward(data)
+        assert np.array_equal(a, b), name
+        chunks = 8 if data.size >= 256 else 1
+        assert ap[:chunks] == bp[:chunks], (name, ap, bp)
+
+
+@pytest.mark.parametrize("tname,ename", [("NONE", "ANS0"), ("BWT+RANK+ZRLT", "ANS0"), ("NONE", "NONE"),
+                                         ("BWT", "ANS1"), ("ZRLT", "ANS0"), ("BWT+MTFT+ZRLT", "ANS0")])
+def test_stream_matches_ref(oracle, ref, tname, ename):
+    inputs = {
+        "comp_300k": synth.synth_compressible(300000, 21),
+        "text_70k": synth.synth_text(70000, 22),
+        "incomp_100k": synth.synth_incompressible(100000, 23),
+        "tiny_10": rng_bytes(10, 24),
+        "tiny_16": rng_bytes(16, 25),
+        "zeros_100k": np.zeros(100000, dtype=np.uint8),
+        "mixed": np.concatenate([synth.synth_text(65536, 26), synth.synth_incompressible(65536 + 13, 27)]),
+    }
+    for name, data in inputs.items():
+        for bs in (65536, 1 << 20):
+            a = oracle.stream_compress(data, tname, ename, bs)
+            b = ref.stream_compress(data, tname, ename, bs, jobs=1)
+            assert a.size == b.size and np.array_equal(a, b), (name, tname, ename, bs, a.size, b.size)
+            dec, n = oracle.stream_decompress(b, data.size)
+            assert n == data.size and np.array_equal(dec, data), (name, tname, ename, bs, n)

@@ -1,0 +1,147 @@
+/* knz_gpu.h -- C ABI of libknzgpu.so: the B200-native replacement for kanzi's
+ * per-block transform -> entropy path (EncodingTask::run / DecodingTask::run and
+ * the Transform<byte> / EntropyEncoder / EntropyDecoder stages they instantiate).
+ *
+ * Plain pointers and sizes only; no exceptions cross this boundary; the caller
+ * owns every host buffer, the library owns device memory, streams and kernels.
+ * All functions return 0 on success or a kanzi error code (src/Error.hpp:27-49;
+ * the ones used here are repeated below).  There is NO CPU fallback: if no CUDA
+ * device is usable knz_create() fails with KNZ_ERR_CREATE_COMPRESSOR.
+ *
+ * Each entry point names the reference interface it replaces (file:line under
+ * /root/reference/src).  INTEGRATION.md shows the reference-side bindings.
+ */
+#ifndef KNZ_GPU_H
+#define KNZ_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Error.hpp:27-49 */
+#define KNZ_OK 0
+#define KNZ_ERR_MISSING_PARAM 1
+#define KNZ_ERR_BLOCK_SIZE 2
+#define KNZ_ERR_INVALID_CODEC 3
+#define KNZ_ERR_CREATE_COMPRESSOR 4
+#define KNZ_ERR_OUTPUT_TOO_SMALL 10 /* (ERR_WRITE_FILE family: caller buffer too small) */
+#define KNZ_ERR_PROCESS_BLOCK 13
+#define KNZ_ERR_INVALID_FILE 20
+#define KNZ_ERR_STREAM_VERSION 21
+#define KNZ_ERR_INVALID_PARAM 24
+#define KNZ_ERR_UNKNOWN 127
+
+/* Transform ids are wire-visible: transform/TransformFactory.hpp:49-73 */
+#define KNZ_T_NONE 0
+#define KNZ_T_BWT 1
+#define KNZ_T_ZRLT 6
+#define KNZ_T_MTFT 7
+#define KNZ_T_RANK 8
+/* Entropy ids: entropy/EntropyEncoderFactory.hpp:37-52 */
+#define KNZ_E_NONE 0
+#define KNZ_E_ANS0 5
+
+typedef struct knz_ctx knz_ctx;
+
+/* Library lifetime.  `device` is the CUDA ordinal; maxBlockSize is the stream
+ * block size the context is provisioned for (multiple of 16, <= 64 MiB here);
+ * maxBatchBlocks bounds how many blocks are processed per device batch (working
+ * memory is ~48 B per input byte of a batch for the suffix sorter).             */
+int knz_create(int device, int maxBlockSize, int maxBatchBlocks, knz_ctx** out);
+void knz_destroy(knz_ctx* ctx);
+const char* knz_last_error(const knz_ctx* ctx);
+
+/* "BWT+RANK+ZRLT" -> 48-bit type word, first stage in the top 6 bits
+ * (TransformFactory<T>::getType, transform/TransformFactory.hpp:100-137);
+ * returns (uint64_t)-1 for a name this library does not implement.              */
+uint64_t knz_transform_type(const char* name);
+/* EntropyEncoderFactory::getType (entropy/EntropyEncoderFactory.hpp:131);  -1 if unsupported */
+int knz_entropy_type(const char* name);
+
+/* ---- Block level: what EncodingTask<T>::run (io/CompressedOutputStream.cpp:652-898)
+ * builds in its private buffer for each block -- mode byte, [skip-flag byte],
+ * post-transform length, entropy payload -- for nBlocks blocks at once.
+ *   in          nBlocks blocks laid out at `inStride` bytes from each other
+ *   lens[i]     bytes in block i (1 .. maxBlockSize)
+ *   out         block i's bytes are written at out + i*outStride
+ *   outBits[i]  exact bit count (`written` in the reference, :830)
+ *   skipFlags[i] TransformSequence skip flags (:745)
+ * The ping-pong buffer capacities that make ZRLT's accept/refuse decision
+ * (TransformSequence.hpp:88-162) follow the reference's jobs=1 buffer model with
+ * `firstBlockLen` = length of the first block of the stream and `blockSize` the
+ * stream block size (io/CompressedOutputStream.cpp:138-146, :733-739).            */
+int knz_encode_blocks(knz_ctx* ctx, uint64_t tType, int eType, int blockSize, const uint8_t* in,
+                      int64_t inStride, const int32_t* lens, int nBlocks, int firstBlockLen, uint8_t* out,
+                      int64_t outStride, uint64_t* outBits, uint8_t* skipFlags);
+
+/* DecodingTask<T>::run (io/CompressedInputStream.cpp:791-1041), payload part:
+ * block i = inBits[i] bits at in + i*inStride (byte aligned, as the reference's
+ * per-task copy :843-856); decoded bytes go to out + i*outStride; outLens[i] =
+ * decoded length.  blockSize = stream block size (sizes the task buffers).       */
+int knz_decode_blocks(knz_ctx* ctx, uint64_t tType, int eType, int blockSize, const uint8_t* in,
+                      int64_t inStride, const uint64_t* inBits, int nBlocks, uint8_t* out, int64_t outStride,
+                      int32_t* outLens);
+
+/* ---- Stream level: CompressedOutputStream::write + close
+ * (io/CompressedOutputStream.cpp:361-440, header :277-342, per-block length
+ * prefixes :852-864, end marker :416-417) and CompressedInputStream::read
+ * (io/CompressedInputStream.cpp:428-510, readHeader :511-663), host buffers.
+ * Output is byte-identical to the reference's stream for the same parameters
+ * (checksum 0, skipBlocks off).                                                  */
+int knz_compress(knz_ctx* ctx, const char* transform, const char* entropy, int blockSize, const uint8_t* in,
+                 int64_t n, uint8_t* out, int64_t cap, int64_t* outLen);
+int knz_decompress(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_t* out, int64_t cap, int64_t* outLen);
+
+/* Same work with the data already resident in device memory (bench `value` leg;
+ * also what a multi-GPU rank calls on its shard).  d_in / d_out are device
+ * pointers in the context's device.  compress: blocks [firstBlock, firstBlock+nBlocks)
+ * of a stream of total length streamLen whose block 0 has length min(blockSize,
+ * streamLen); d_blockOut receives each block's private buffer (outStride apart),
+ * d_outBits (device, uint64) the bit counts.                                      */
+int knz_encode_blocks_dev(knz_ctx* ctx, uint64_t tType, int eType, int blockSize, const uint8_t* d_in,
+                          int64_t inStride, const int32_t* lens, int nBlocks, int firstBlockLen,
+                          uint8_t* d_blockOut, int64_t outStride, uint64_t* d_outBits,
+                          uint8_t* h_skipFlags /* may be NULL */);
+int knz_decode_blocks_dev(knz_ctx* ctx, uint64_t tType, int eType, int blockSize, const uint8_t* d_in,
+                          int64_t inStride, const uint64_t* h_inBits, int nBlocks, uint8_t* d_out,
+                          int64_t outStride, int32_t* h_outLens);
+/* Bit-concatenate nBlocks block buffers (device) into the final stream body on
+ * the device: for each block `lw-3`(5) | bits(lw) | payload, starting at bit
+ * `startBit`; returns the end bit position.  (CompressedOutputStream.cpp:852-864) */
+int knz_assemble_stream_dev(knz_ctx* ctx, const uint8_t* d_blockOut, int64_t outStride, const uint64_t* d_outBits,
+                            int nBlocks, uint8_t* d_stream, int64_t streamCap, uint64_t startBit,
+                            uint64_t* endBit);
+/* Stream header bytes (io/CompressedOutputStream.cpp:277-342); returns byte count (20..26). */
+int knz_stream_header(uint64_t tType, int eType, int blockSize, int64_t inputSize, uint8_t out[32]);
+
+/* ---- Stage level (what the Transform<byte> / EntropyEncoder adapters call).
+ * knz_transform_forward == Transform<byte>::forward (src/Transform.hpp:38):
+ * returns KNZ_OK and *applied=1 when the stage produced output (*outLen bytes),
+ * *applied=0 when the stage refuses (reference returns false, stage skipped).
+ * type is a single transform id; cap = destination capacity (_length - _index).  */
+int knz_transform_forward(knz_ctx* ctx, int type, const uint8_t* in, int n, uint8_t* out, int cap, int* outLen,
+                          int* applied);
+int knz_transform_inverse(knz_ctx* ctx, int type, const uint8_t* in, int n, uint8_t* out, int cap, int* outLen,
+                          int* applied);
+/* EntropyEncoder::encode (src/EntropyEncoder.hpp:30) into a private bit buffer:
+ * out receives ceil(*outBits/8) bytes, MSB-first.                                */
+int knz_entropy_encode(knz_ctx* ctx, int type, const uint8_t* in, int n, uint8_t* out, int64_t cap,
+                       int64_t* outBits);
+/* EntropyDecoder::decode (src/EntropyDecoder.hpp:30): n = number of bytes to produce. */
+int knz_entropy_decode(knz_ctx* ctx, int type, const uint8_t* in, int64_t inBits, uint8_t* out, int n);
+
+/* Instrumentation for bench.py: kernels launched by this context since creation,
+ * and the CUDA stream (cudaStream_t) the library launches on.                    */
+uint64_t knz_launch_count(const knz_ctx* ctx);
+void* knz_stream(const knz_ctx* ctx);
+/* Device time (ms) of the last call, split by stage group, measured with CUDA
+ * events on the library stream: [0]=BWT [1]=RANK/MTFT [2]=ZRLT [3]=entropy
+ * [4]=bit assembly [5]=total.                                                     */
+void knz_last_timings(const knz_ctx* ctx, float ms[6]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KNZ_GPU_H */

@@ -1,0 +1,1239 @@
+// api.cu -- context, C ABI (include/knz_gpu.h) and host-side orchestration:
+// block scheduling, kanzi bitstream framing (stream header, block prefixes,
+// end marker) and the batched launch sequence
+//   transforms (BWT -> RANK/MTFT -> ZRLT)  ->  rANS  ->  bit assembly.
+// The reference's equivalents are CompressedOutputStream / EncodingTask and
+// CompressedInputStream / DecodingTask (io/Compressed{Output,Input}Stream.cpp).
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/knz_gpu.h"
+#include "kernels.h"
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            snprintf(ctx->err, sizeof(ctx->err), "%s:%d CUDA error %d: %s", __FILE__, __LINE__,    \
+                     (int)e_, cudaGetErrorString(e_));                                             \
+            return KNZ_ERR_PROCESS_BLOCK;                                                          \
+        }                                                                                          \
+    } while (0)
+
+struct knz_ctx {
+    int device, maxBlockSize, maxBatch;
+    cudaStream_t stream;
+    cudaEvent_t ev[8];
+    i64 bstride;     // stride of the ping-pong stage buffers
+    u8 *bufA, *bufB; // [maxBatch * bstride]
+    u8* dStageIn;    // host API: staged input blocks [maxBatch * bstride]
+    u8* dOut;        // per-block output bit strings [maxBatch * outStride]
+    i64 outStride;
+    BlkState* st;    // [10][maxBatch]
+    int *capEven, *capOdd;
+    int maxChunks;
+    u8* slots;
+    u32 *hdrBits, *payBytes, *payOff;
+    u64 *chunkOff, *blockBits, *blockOff, *streamPos;
+    u64 *chunkPos, *dInBits, *dPayStart;
+    int* dPreLen;
+    int* errFlag;
+    Workspace ws;
+    // pinned host mirrors
+    BlkState* h_st;
+    int *h_capEven, *h_capOdd, *h_err, *h_preLen;
+    u64 *h_bits, *h_payStart, *h_pos;
+    // stream-level buffers (grown on demand)
+    u8* dStream;
+    i64 dStreamCap;
+    u8* dPlain;
+    i64 dPlainCap;
+    u64 launches;
+    float ms[6];
+    char err[256];
+};
+
+static i64 round_up(i64 v, i64 a) { return (v + a - 1) / a * a; }
+
+static int split_types(u64 tType, int* types)
+{
+    int n = 0;
+    for (int i = 0; i < 8; i++) {
+        const int t = (int)((tType >> (42 - 6 * i)) & 63);
+        if (t != T_NONE || i == 0)
+            types[n++] = t;
+    }
+    return n;
+}
+
+static bool type_supported(int t) { return t == T_NONE || t == T_BWT || t == T_ZRLT || t == T_MTFT || t == T_RANK; }
+
+static int stage_max_len(int t, int n) { return (t == T_BWT) ? n + 33 : n; }
+
+static int required_size(const int* types, int nt, int n)
+{
+    int r = n;
+    for (int i = 0; i < nt; i++) {
+        const int m = stage_max_len(types[i], r);
+        if (m > r)
+            r = m;
+    }
+    return r;
+}
+
+extern "C" uint64_t knz_transform_type(const char* name)
+{
+    if (name == NULL)
+        return (uint64_t)-1;
+    u64 word = 0;
+    int shift = 42, n = 0;
+    const char* p = name;
+    while (*p) {
+        const char* q = strchr(p, '+');
+        const size_t len = q ? (size_t)(q - p) : strlen(p);
+        int t = -1;
+        if (len == 4 && !strncmp(p, "NONE", 4))
+            t = T_NONE;
+        else if (len == 3 && !strncmp(p, "BWT", 3))
+            t = T_BWT;
+        else if (len == 4 && !strncmp(p, "ZRLT", 4))
+            t = T_ZRLT;
+        else if (len == 4 && !strncmp(p, "MTFT", 4))
+            t = T_MTFT;
+        else if (len == 4 && !strncmp(p, "RANK", 4))
+            t = T_RANK;
+        if (t < 0 || ++n > 8)
+            return (uint64_t)-1;
+        if (t != T_NONE) {
+            word |= (u64)t << shift;
+            shift -= 6;
+        }
+        p += len;
+        if (*p == '+')
+            p++;
+    }
+    return word;
+}
+
+extern "C" int knz_entropy_type(const char* name)
+{
+    if (name == NULL)
+        return -1;
+    if (!strcmp(name, "NONE"))
+        return E_RAW;
+    if (!strcmp(name, "ANS0"))
+        return E_ANS0;
+    return -1;
+}
+
+template <class T>
+static cudaError_t dalloc(T** p, i64 count)
+{
+    return cudaMalloc((void**)p, (size_t)(count > 0 ? count : 1) * sizeof(T));
+}
+
+extern "C" int knz_create(int device, int maxBlockSize, int maxBatchBlocks, knz_ctx** out)
+{
+    if (out == NULL || maxBlockSize < 1024 || maxBlockSize > (64 << 20) || (maxBlockSize & 15) || maxBatchBlocks < 1)
+        return KNZ_ERR_INVALID_PARAM;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+        return KNZ_ERR_CREATE_COMPRESSOR; // no CPU fallback
+    if (cudaSetDevice(device) != cudaSuccess)
+        return KNZ_ERR_CREATE_COMPRESSOR;
+    knz_ctx* ctx = (knz_ctx*)calloc(1, sizeof(knz_ctx));
+    ctx->device = device;
+    ctx->maxBlockSize = maxBlockSize;
+    ctx->maxBatch = maxBatchBlocks;
+    const int nb = maxBatchBlocks;
+    // stage buffers hold a block plus the BWT header and the decoder's slack
+    const i64 slack = (maxBlockSize >> 4) > 512 ? (maxBlockSize >> 4) : 512;
+    ctx->bstride = round_up((i64)maxBlockSize + slack + 64, 256);
+    ctx->outStride = round_up((i64)maxBlockSize + (maxBlockSize >> 2) + 4096, 256);
+    ctx->maxChunks = (int)((ctx->bstride + ANS_CHUNK - 1) / ANS_CHUNK);
+    bool ok = true;
+#define A(call) ok = ok && ((call) == cudaSuccess)
+    A(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; i++)
+        A(cudaEventCreate(&ctx->ev[i]));
+    A(dalloc(&ctx->bufA, nb * ctx->bstride + 256));
+    A(dalloc(&ctx->bufB, nb * ctx->bstride + 256));
+    A(dalloc(&ctx->dStageIn, nb * ctx->bstride + 256));
+    A(dalloc(&ctx->dOut, nb * ctx->outStride + 256));
+    A(dalloc(&ctx->st, 10 * (i64)nb));
+    A(dalloc(&ctx->capEven, nb));
+    A(dalloc(&ctx->capOdd, nb));
+    const i64 nch = (i64)nb * ctx->maxChunks;
+    A(dalloc(&ctx->slots, nch * ANS_SLOT));
+    A(dalloc(&ctx->hdrBits, nch));
+    A(dalloc(&ctx->payBytes, nch));
+    A(dalloc(&ctx->payOff, nch));
+    A(dalloc(&ctx->chunkOff, nch));
+    A(dalloc(&ctx->chunkPos, nch));
+    A(dalloc(&ctx->blockBits, nb));
+    A(dalloc(&ctx->blockOff, nb));
+    A(dalloc(&ctx->streamPos, 4));
+    A(dalloc(&ctx->dInBits, nb));
+    A(dalloc(&ctx->dPayStart, nb));
+    A(dalloc(&ctx->dPreLen, nb));
+    A(dalloc(&ctx->errFlag, 4));
+    A(cudaMallocHost((void**)&ctx->h_st, sizeof(BlkState) * nb));
+    A(cudaMallocHost((void**)&ctx->h_capEven, sizeof(int) * nb));
+    A(cudaMallocHost((void**)&ctx->h_capOdd, sizeof(int) * nb));
+    A(cudaMallocHost((void**)&ctx->h_err, sizeof(int) * 4));
+    A(cudaMallocHost((void**)&ctx->h_preLen, sizeof(int) * nb));
+    A(cudaMallocHost((void**)&ctx->h_bits, sizeof(u64) * nb));
+    A(cudaMallocHost((void**)&ctx->h_payStart, sizeof(u64) * nb));
+    A(cudaMallocHost((void**)&ctx->h_pos, sizeof(u64) * 4));
+    ok = ok && workspace_alloc(ctx->ws, nb, (int)ctx->bstride);
+#undef A
+    if (!ok) {
+        knz_destroy(ctx);
+        return KNZ_ERR_CREATE_COMPRESSOR;
+    }
+    *out = ctx;
+    return KNZ_OK;
+}
+
+extern "C" void knz_destroy(knz_ctx* ctx)
+{
+    if (ctx == NULL)
+        return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream)
+        cudaStreamSynchronize(ctx->stream);
+    workspace_free(ctx->ws);
+    void* dev[] = { ctx->bufA, ctx->bufB, ctx->dStageIn, ctx->dOut, ctx->st, ctx->capEven, ctx->capOdd, ctx->slots,
+                    ctx->hdrBits, ctx->payBytes, ctx->payOff, ctx->chunkOff, ctx->chunkPos, ctx->blockBits,
+                    ctx->blockOff, ctx->streamPos, ctx->dInBits, ctx->dPayStart, ctx->dPreLen, ctx->errFlag,
+                    ctx->dStream, ctx->dPlain };
+    for (size_t i = 0; i < sizeof(dev) / sizeof(dev[0]); i++)
+        if (dev[i])
+            cudaFree(dev[i]);
+    void* hst[] = { ctx->h_st, ctx->h_capEven, ctx->h_capOdd, ctx->h_err, ctx->h_preLen, ctx->h_bits,
+                    ctx->h_payStart, ctx->h_pos };
+    for (size_t i = 0; i < sizeof(hst) / sizeof(hst[0]); i++)
+        if (hst[i])
+            cudaFreeHost(hst[i]);
+    for (int i = 0; i < 8; i++)
+        if (ctx->ev[i])
+            cudaEventDestroy(ctx->ev[i]);
+    if (ctx->stream)
+        cudaStreamDestroy(ctx->stream);
+    free(ctx);
+}
+
+extern "C" const char* knz_last_error(const knz_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+extern "C" uint64_t knz_launch_count(const knz_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" void* knz_stream(const knz_ctx* ctx) { return ctx ? (void*)ctx->stream : NULL; }
+extern "C" void knz_last_timings(const knz_ctx* ctx, float ms[6])
+{
+    for (int i = 0; i < 6; i++)
+        ms[i] = ctx ? ctx->ms[i] : 0.f;
+}
+
+static int map_kerr(knz_ctx* ctx, int kerr)
+{
+    if (kerr == 0)
+        return KNZ_OK;
+    snprintf(ctx->err, sizeof(ctx->err), "device error flag %d (%s)", kerr,
+             kerr == KERR_OUT_OVERFLOW  ? "output buffer overflow"
+             : kerr == KERR_BAD_STREAM  ? "invalid bitstream"
+             : kerr == KERR_UNSUPPORTED ? "unsupported stream feature"
+                                        : "internal");
+    return (kerr == KERR_BAD_STREAM) ? KNZ_ERR_INVALID_FILE : KNZ_ERR_PROCESS_BLOCK;
+}
+
+static void add_stage_time(knz_ctx* ctx, int t, float ms)
+{
+    const int slot = (t == T_BWT) ? 0 : (t == T_RANK || t == T_MTFT) ? 1 : (t == T_ZRLT) ? 2 : 5;
+    if (slot < 5)
+        ctx->ms[slot] += ms;
+}
+
+// Forward transforms + entropy for one batch of blocks resident on the device.
+// All lens[i] must be > 15 (small blocks are framed on the host).
+static int encode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8* d_in, i64 inStride,
+                        const int32_t* lens, int nB, int firstBlockLen, u8* d_out, i64 outStride, u64* d_bits,
+                        u8* h_flags)
+{
+    int types[8];
+    const int nt = split_types(tType, types);
+    for (int i = 0; i < nt; i++)
+        if (!type_supported(types[i])) {
+            snprintf(ctx->err, sizeof(ctx->err), "transform id %d not implemented", types[i]);
+            return KNZ_ERR_INVALID_CODEC;
+        }
+    if (eType != E_RAW && eType != E_ANS0) {
+        snprintf(ctx->err, sizeof(ctx->err), "entropy id %d not implemented", eType);
+        return KNZ_ERR_INVALID_CODEC;
+    }
+    if (nB > ctx->maxBatch || ((uintptr_t)d_in & 15) || (inStride & 15) || ((uintptr_t)d_out & 15) || (outStride & 15))
+        return KNZ_ERR_INVALID_PARAM;
+    cudaStream_t s = ctx->stream;
+    const int dataCap = (blockSize + (blockSize >> 3) > 262144) ? blockSize + (blockSize >> 3) : 262144;
+    const int reqFirst = required_size(types, nt, firstBlockLen);
+    int maxLen = 0;
+    for (int b = 0; b < nB; b++) {
+        if (lens[b] <= 15 || lens[b] > ctx->maxBlockSize)
+            return KNZ_ERR_BLOCK_SIZE;
+        const int req = required_size(types, nt, lens[b]);
+        ctx->h_st[b].len = lens[b];
+        ctx->h_st[b].cur = 2;
+        ctx->h_st[b].swaps = 0;
+        ctx->h_st[b].flags = 0xFF;
+        ctx->h_capEven[b] = (reqFirst > req) ? reqFirst : req;
+        ctx->h_capOdd[b] = (dataCap >= req) ? dataCap : req;
+        if (lens[b] > maxLen)
+            maxLen = lens[b];
+    }
+    CK(cudaMemcpyAsync(ctx->st, ctx->h_st, sizeof(BlkState) * nB, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->capEven, ctx->h_capEven, sizeof(int) * nB, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->capOdd, ctx->h_capOdd, sizeof(int) * nB, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(ctx->errFlag, 0, sizeof(int) * 4, s));
+
+    BufTable bt;
+    bt.base[0] = ctx->bufA;
+    bt.base[1] = ctx->bufB;
+    bt.base[2] = const_cast<u8*>(d_in);
+    bt.stride[0] = bt.stride[1] = ctx->bstride;
+    bt.stride[2] = inStride;
+
+    for (int i = 0; i < 6; i++)
+        ctx->ms[i] = 0.f;
+    CK(cudaEventRecord(ctx->ev[0], s));
+    for (int i = 0; i < nt; i++) {
+        StageLaunch L;
+        L.bt = bt;
+        L.stIn = ctx->st + (i64)i * ctx->maxBatch;
+        L.stOut = ctx->st + (i64)(i + 1) * ctx->maxBatch;
+        L.stageIdx = i;
+        L.nBlocks = nB;
+        L.maxLen = maxLen + 33 * (i + 1);
+        L.capEven = ctx->capEven;
+        L.capOdd = ctx->capOdd;
+        L.errFlag = ctx->errFlag;
+        CK(cudaEventRecord(ctx->ev[1], s));
+        switch (types[i]) {
+        case T_NONE:
+            launch_none_forward(L, s, &ctx->launches);
+            break;
+        case T_BWT:
+            launch_bwt_forward(L, ctx->ws, s, &ctx->launches);
+            break;
+        case T_ZRLT:
+            launch_zrlt_forward(L, ctx->ws, s, &ctx->launches);
+            break;
+        case T_MTFT:
+            launch_sbrt_forward(L, 1, ctx->ws, s, &ctx->launches);
+            break;
+        case T_RANK:
+            launch_sbrt_forward(L, 2, ctx->ws, s, &ctx->launches);
+            break;
+        }
+        CK(cudaEventRecord(ctx->ev[2], s));
+        CK(cudaEventSynchronize(ctx->ev[2]));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]);
+        add_stage_time(ctx, types[i], ms);
+    }
+    const BlkState* stFinal = ctx->st + (i64)nt * ctx->maxBatch;
+    CK(cudaEventRecord(ctx->ev[3], s));
+    EncodeLaunch E;
+    E.bt = bt;
+    E.st = stFinal;
+    E.nBlocks = nB;
+    E.maxChunks = ctx->maxChunks;
+    E.eType = eType;
+    E.nTransforms = nt;
+    E.slots = ctx->slots;
+    E.hdrBits = ctx->hdrBits;
+    E.payBytes = ctx->payBytes;
+    E.payOff = ctx->payOff;
+    E.chunkOff = ctx->chunkOff;
+    E.blockBits = d_bits;
+    E.out = d_out;
+    E.outStride = outStride;
+    E.errFlag = ctx->errFlag;
+    launch_entropy_encode(E, s, &ctx->launches);
+    CK(cudaEventRecord(ctx->ev[4], s));
+    CK(cudaMemcpyAsync(ctx->h_err, ctx->errFlag, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ctx->h_st, stFinal, sizeof(BlkState) * nB, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]);
+    ctx->ms[3] = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]);
+    ctx->ms[5] = ms;
+    if (h_flags)
+        for (int b = 0; b < nB; b++)
+            h_flags[b] = (u8)ctx->h_st[b].flags;
+    return map_kerr(ctx, ctx->h_err[0]);
+}
+
+extern "C" int knz_encode_blocks_dev(knz_ctx* ctx, uint64_t tType, int eType, int blockSize, const uint8_t* d_in,
+                                     int64_t inStride, const int32_t* lens, int nBlocks, int firstBlockLen,
+                                     uint8_t* d_blockOut, int64_t outStride, uint64_t* d_outBits,
+                                     uint8_t* h_skipFlags)
+{
+    if (!ctx || !d_in || !lens || !d_blockOut || !d_outBits || nBlocks < 0)
+        return KNZ_ERR_INVALID_PARAM;
+    cudaSetDevice(ctx->device);
+    for (int off = 0; off < nBlocks; off += ctx->maxBatch) {
+        const int nb = (nBlocks - off < ctx->maxBatch) ? nBlocks - off : ctx->maxBatch;
+        const int rc = encode_batch(ctx, tType, eType, blockSize, d_in + (i64)off * inStride, inStride, lens + off, nb,
+                                    firstBlockLen, d_blockOut + (i64)off * outStride, outStride, d_outBits + off,
+                                    h_skipFlags ? h_skipFlags + off : NULL);
+        if (rc != KNZ_OK)
+            return rc;
+    }
+    return KNZ_OK;
+}
+
+// Small blocks (<= 15 bytes) are always copy blocks: mode 0x80 | skipFlags>>4
+// with the single NullTransform applied (flags 0x7F), one length byte, raw bytes
+// (io/CompressedOutputStream.cpp:38,691-695).
+static u64 frame_small_block(const u8* in, int len, u8* out)
+{
+    out[0] = 0x87;
+    out[1] = (u8)len;
+    memcpy(out + 2, in, (size_t)len);
+    return 8ull * (u64)(2 + len);
+}
+
+extern "C" int knz_encode_blocks(knz_ctx* ctx, uint64_t tType, int eType, int blockSize, const uint8_t* in,
+                                 int64_t inStride, const int32_t* lens, int nBlocks, int firstBlockLen,
+                                 uint8_t* out, int64_t outStride, uint64_t* outBits, uint8_t* skipFlags)
+{
+    if (!ctx || !in || !lens || !out || !outBits || nBlocks < 0)
+        return KNZ_ERR_INVALID_PARAM;
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    for (int off = 0; off < nBlocks; off += ctx->maxBatch) {
+        const int nb = (nBlocks - off < ctx->maxBatch) ? nBlocks - off : ctx->maxBatch;
+        // small blocks can only be framed on the host; the rest go to the device
+        int32_t glens[1];
+        (void)glens;
+        int ng = 0;
+        int* map = (int*)malloc(sizeof(int) * (size_t)nb);
+        int32_t* dl = (int32_t*)malloc(sizeof(int32_t) * (size_t)nb);
+        for (int b = 0; b < nb; b++) {
+            const int len = lens[off + b];
+            if (len <= 0 || len > ctx->maxBlockSize) {
+                free(map);
+                free(dl);
+                return KNZ_ERR_BLOCK_SIZE;
+            }
+            if (len <= 15) {
+                outBits[off + b] = frame_small_block(in + (i64)(off + b) * inStride, len, out + (i64)(off + b) * outStride);
+                if (skipFlags)
+                    skipFlags[off + b] = 0x7F;
+            } else {
+                CK(cudaMemcpyAsync(ctx->dStageIn + (i64)ng * ctx->bstride, in + (i64)(off + b) * inStride, (size_t)len,
+                                   cudaMemcpyHostToDevice, s));
+                map[ng] = off + b;
+                dl[ng] = len;
+                ng++;
+            }
+        }
+        int rc = KNZ_OK;
+        u8* fl = (u8*)malloc((size_t)nb + 1);
+        if (ng > 0)
+            rc = encode_batch(ctx, tType, eType, blockSize, ctx->dStageIn, ctx->bstride, dl, ng, firstBlockLen, ctx->dOut,
+                              ctx->outStride, ctx->blockBits, fl);
+        if (rc == KNZ_OK && ng > 0) {
+            cudaMemcpyAsync(ctx->h_bits, ctx->blockBits, sizeof(u64) * ng, cudaMemcpyDeviceToHost, s);
+            cudaStreamSynchronize(s);
+            for (int g = 0; g < ng && rc == KNZ_OK; g++) {
+                const i64 nbytes = (i64)((ctx->h_bits[g] + 7) >> 3);
+                if (nbytes > outStride) {
+                    rc = KNZ_ERR_OUTPUT_TOO_SMALL;
+                    break;
+                }
+                cudaMemcpyAsync(out + (i64)map[g] * outStride, ctx->dOut + (i64)g * ctx->outStride, (size_t)nbytes,
+                                cudaMemcpyDeviceToHost, s);
+                outBits[map[g]] = ctx->h_bits[g];
+                if (skipFlags)
+                    skipFlags[map[g]] = fl[g];
+            }
+            cudaStreamSynchronize(s);
+        }
+        free(fl);
+        free(map);
+        free(dl);
+        if (rc != KNZ_OK)
+            return rc;
+    }
+    return KNZ_OK;
+}
+
+extern "C" int knz_assemble_stream_dev(knz_ctx* ctx, const uint8_t* d_blockOut, int64_t outStride,
+                                       const uint64_t* d_outBits, int nBlocks, uint8_t* d_stream, int64_t streamCap,
+                                       uint64_t startBit, uint64_t* endBit)
+{
+    if (!ctx || nBlocks < 0 || ((uintptr_t)d_stream & 3))
+        return KNZ_ERR_INVALID_PARAM;
+    (void)streamCap;
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    ctx->h_pos[0] = startBit;
+    CK(cudaMemcpyAsync(ctx->streamPos, ctx->h_pos, sizeof(u64), cudaMemcpyHostToDevice, s));
+    if (nBlocks > 0) {
+        if (nBlocks > ctx->maxBatch)
+            return KNZ_ERR_INVALID_PARAM;
+        launch_stream_assemble(d_blockOut, outStride, d_outBits, nBlocks, ctx->streamPos, ctx->blockOff, ctx->streamPos,
+                               d_stream, s, &ctx->launches);
+    }
+    CK(cudaMemcpyAsync(ctx->h_pos, ctx->streamPos, sizeof(u64), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    if (endBit)
+        *endBit = ctx->h_pos[0];
+    return KNZ_OK;
+}
+
+// Stream header (io/CompressedOutputStream.cpp:277-342), written with a tiny
+// host-side MSB-first packer.
+struct HostBits {
+    u8* p;
+    u64 pos;
+    void put(u64 v, int n)
+    {
+        for (int k = n - 1; k >= 0; k--) {
+            if ((v >> k) & 1)
+                p[pos >> 3] |= (u8)(0x80 >> (pos & 7));
+            pos++;
+        }
+    }
+};
+
+extern "C" int knz_stream_header(uint64_t tType, int eType, int blockSize, int64_t inputSize, uint8_t out[32])
+{
+    memset(out, 0, 32);
+    HostBits w = { out, 0 };
+    w.put(0x4B414E5A, 32);
+    w.put(6, 4);
+    w.put(0, 2);
+    w.put((u64)eType, 5);
+    w.put(tType, 48);
+    w.put((u64)(blockSize >> 4), 28);
+    int szMask = 0;
+    if (inputSize != 0 && inputSize < ((i64)1 << 48)) {
+        int lg = 0;
+        for (u64 x = (u64)inputSize; x > 1; x >>= 1)
+            lg++;
+        szMask = (lg >> 4) + 1;
+    }
+    w.put((u64)szMask, 2);
+    if (szMask)
+        w.put((u64)inputSize, 16 * szMask);
+    w.put(0, 15);
+    const u32 HASH = 0x1E35A7BDu;
+    u32 ck = HASH * (0x01030507u * 6u);
+    ck ^= HASH * (u32)~0u;
+    ck ^= HASH * (u32)~(u32)eType;
+    ck ^= HASH * (u32)((~tType) >> 32);
+    ck ^= HASH * (u32)(~tType);
+    ck ^= HASH * (u32)~(u32)blockSize;
+    if (szMask) {
+        ck ^= HASH * (u32)((~(u64)inputSize) >> 32);
+        ck ^= HASH * (u32)(~(u64)inputSize);
+    }
+    ck = (ck >> 23) ^ (ck >> 3);
+    w.put(ck & 0xFFFFFFu, 24);
+    return (int)(w.pos >> 3);
+}
+
+static int grow(knz_ctx* ctx, u8** buf, i64* cap, i64 need)
+{
+    if (*cap >= need)
+        return KNZ_OK;
+    if (*buf)
+        cudaFree(*buf);
+    *buf = NULL;
+    *cap = 0;
+    CK(cudaMalloc((void**)buf, (size_t)need));
+    *cap = need;
+    return KNZ_OK;
+}
+
+extern "C" int knz_compress(knz_ctx* ctx, const char* transform, const char* entropy, int blockSize,
+                            const uint8_t* in, int64_t n, uint8_t* out, int64_t cap, int64_t* outLen)
+{
+    if (!ctx || !in || !out || !outLen || n < 0)
+        return KNZ_ERR_INVALID_PARAM;
+    const u64 tType = knz_transform_type(transform);
+    const int eType = knz_entropy_type(entropy);
+    if (tType == (u64)-1 || eType < 0) {
+        snprintf(ctx->err, sizeof(ctx->err), "unsupported pipeline %s / %s", transform ? transform : "?",
+                 entropy ? entropy : "?");
+        return KNZ_ERR_INVALID_CODEC;
+    }
+    if (blockSize < 1024 || blockSize > ctx->maxBlockSize || (blockSize & 15))
+        return KNZ_ERR_BLOCK_SIZE;
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    u8 hdr[32];
+    const int hdrBytes = knz_stream_header(tType, eType, blockSize, n, hdr);
+    const i64 nBlocks = (n + blockSize - 1) / blockSize;
+    const i64 streamCap = round_up(n + (n >> 2) + 16 * nBlocks + 65536, 256);
+    int rc = grow(ctx, &ctx->dStream, &ctx->dStreamCap, streamCap);
+    if (rc != KNZ_OK)
+        return rc;
+    rc = grow(ctx, &ctx->dPlain, &ctx->dPlainCap, round_up((i64)ctx->maxBatch * blockSize + 256, 256));
+    if (rc != KNZ_OK)
+        return rc;
+    CK(cudaMemsetAsync(ctx->dStream, 0, (size_t)streamCap, s));
+    ctx->h_pos[0] = 8ull * (u64)hdrBytes;
+    CK(cudaMemcpyAsync(ctx->streamPos, ctx->h_pos, sizeof(u64), cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+    const int firstLen = (int)((n < blockSize) ? n : blockSize);
+    float acc[6] = { 0, 0, 0, 0, 0, 0 };
+    for (i64 b0 = 0; b0 < nBlocks; b0 += ctx->maxBatch) {
+        const int nb = (int)((nBlocks - b0 < ctx->maxBatch) ? nBlocks - b0 : ctx->maxBatch);
+        const i64 off = b0 * blockSize;
+        const i64 bytes = ((off + (i64)nb * blockSize) <= n) ? (i64)nb * blockSize : n - off;
+        CK(cudaMemcpyAsync(ctx->dPlain, in + off, (size_t)bytes, cudaMemcpyHostToDevice, s));
+        int32_t* lens = (int32_t*)malloc(sizeof(int32_t) * (size_t)nb);
+        for (int i = 0; i < nb; i++) {
+            const i64 rem = n - (off + (i64)i * blockSize);
+            lens[i] = (int)((rem < blockSize) ? rem : blockSize);
+        }
+        int ng = nb;
+        if (lens[nb - 1] <= 15)
+            ng = nb - 1; // only the last block of a stream can be that small
+        if (ng > 0) {
+            rc = encode_batch(ctx, tType, eType, blockSize, ctx->dPlain, blockSize, lens, ng, firstLen, ctx->dOut,
+                              ctx->outStride, ctx->blockBits, NULL);
+            for (int i = 0; i < 6; i++)
+                acc[i] += ctx->ms[i];
+        }
+        if (rc == KNZ_OK && ng < nb) {
+            u8 tmp[32];
+            memset(tmp, 0, sizeof(tmp));
+            ctx->h_bits[0] = frame_small_block(in + off + (i64)ng * blockSize, lens[ng], tmp);
+            CK(cudaMemcpyAsync(ctx->dOut + (i64)ng * ctx->outStride, tmp, 32, cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(ctx->blockBits + ng, ctx->h_bits, sizeof(u64), cudaMemcpyHostToDevice, s));
+            CK(cudaStreamSynchronize(s));
+        }
+        free(lens);
+        if (rc != KNZ_OK)
+            return rc;
+        CK(cudaEventRecord(ctx->ev[5], s));
+        launch_stream_assemble(ctx->dOut, ctx->outStride, ctx->blockBits, nb, ctx->streamPos, ctx->blockOff,
+                               ctx->streamPos, ctx->dStream, s, &ctx->launches);
+        CK(cudaEventRecord(ctx->ev[6], s));
+        CK(cudaEventSynchronize(ctx->ev[6]));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]);
+        acc[4] += ms;
+    }
+    CK(cudaMemcpyAsync(ctx->h_pos, ctx->streamPos, sizeof(u64), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    const u64 endBit = ctx->h_pos[0] + 8; // end marker: 5 + 3 zero bits (:416-417)
+    const i64 total = (i64)((endBit + 7) >> 3);
+    if (total > cap || total > streamCap)
+        return KNZ_ERR_OUTPUT_TOO_SMALL;
+    CK(cudaMemcpyAsync(out, ctx->dStream, (size_t)total, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    memcpy(out, hdr, (size_t)hdrBytes);
+    *outLen = total;
+    for (int i = 0; i < 6; i++)
+        ctx->ms[i] = acc[i];
+    return KNZ_OK;
+}
+
+// ------------------------------------------------------------------ decode
+struct HostBitReader {
+    const u8* p;
+    u64 nbits, pos;
+    bool bad;
+    u64 get(int n)
+    {
+        u64 v = 0;
+        for (int k = 0; k < n; k++) {
+            u64 b = 0;
+            if (pos < nbits)
+                b = (p[pos >> 3] >> (7 - (pos & 7))) & 1;
+            else
+                bad = true;
+            v = (v << 1) | b;
+            pos++;
+        }
+        return v;
+    }
+};
+
+// Inverse transforms + entropy decode for a batch.  Block b's bit string starts
+// at bit h_start[b] of d_in (+ b*inStride) and holds h_bits[b] bits.
+static int decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8* d_in, i64 inStride,
+                        const u64* h_payStart, const u64* h_endBit, const int* h_preLen, const u8* h_flags, int nB,
+                        u8* d_out, i64 outStride, int32_t* h_outLens)
+{
+    int types[8];
+    const int nt = split_types(tType, types);
+    for (int i = 0; i < nt; i++)
+        if (!type_supported(types[i]))
+            return KNZ_ERR_INVALID_CODEC;
+    if (eType != E_RAW && eType != E_ANS0)
+        return KNZ_ERR_INVALID_CODEC;
+    if (nB > ctx->maxBatch)
+        return KNZ_ERR_INVALID_PARAM;
+    cudaStream_t s = ctx->stream;
+    const int blkLen = blockSize + ((blockSize >> 4) > 512 ? (blockSize >> 4) : 512);
+    int maxLen = 0;
+    for (int b = 0; b < nB; b++) {
+        if (h_preLen[b] <= 0 || h_preLen[b] > blkLen || (i64)h_preLen[b] + 64 > ctx->bstride)
+            return KNZ_ERR_INVALID_FILE;
+        ctx->h_st[b].len = h_preLen[b];
+        ctx->h_st[b].cur = 0;
+        ctx->h_st[b].swaps = 0;
+        ctx->h_st[b].flags = h_flags[b];
+        ctx->h_preLen[b] = h_preLen[b];
+        ctx->h_payStart[b] = h_payStart[b];
+        ctx->h_bits[b] = h_endBit[b];
+        ctx->h_capEven[b] = blkLen;
+        ctx->h_capOdd[b] = blkLen;
+        if (h_preLen[b] > maxLen)
+            maxLen = h_preLen[b];
+    }
+    CK(cudaMemcpyAsync(ctx->st, ctx->h_st, sizeof(BlkState) * nB, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->dPreLen, ctx->h_preLen, sizeof(int) * nB, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->dPayStart, ctx->h_payStart, sizeof(u64) * nB, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->dInBits, ctx->h_bits, sizeof(u64) * nB, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->capEven, ctx->h_capEven, sizeof(int) * nB, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->capOdd, ctx->h_capOdd, sizeof(int) * nB, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(ctx->errFlag, 0, sizeof(int) * 4, s));
+    for (int i = 0; i < 6; i++)
+        ctx->ms[i] = 0.f;
+    CK(cudaEventRecord(ctx->ev[0], s));
+    DecodeLaunch D;
+    D.in = d_in;
+    D.inStride = inStride;
+    D.inBits = ctx->dInBits;
+    D.payStart = ctx->dPayStart;
+    D.preLen = ctx->dPreLen;
+    D.nBlocks = nB;
+    D.maxChunks = ctx->maxChunks;
+    D.eType = eType;
+    D.chunkPos = ctx->chunkPos;
+    D.dst = ctx->bufA;
+    D.dstStride = ctx->bstride;
+    D.errFlag = ctx->errFlag;
+    launch_entropy_decode(D, s, &ctx->launches);
+    CK(cudaEventRecord(ctx->ev[1], s));
+
+    BufTable bt;
+    bt.base[0] = ctx->bufA;
+    bt.base[1] = ctx->bufB;
+    bt.base[2] = ctx->bufA;
+    bt.stride[0] = bt.stride[1] = bt.stride[2] = ctx->bstride;
+    int step = 0;
+    for (int i = nt - 1; i >= 0; i--, step++) {
+        StageLaunch L;
+        L.bt = bt;
+        L.stIn = ctx->st + (i64)step * ctx->maxBatch;
+        L.stOut = ctx->st + (i64)(step + 1) * ctx->maxBatch;
+        L.stageIdx = i;
+        L.nBlocks = nB;
+        L.maxLen = blkLen;
+        L.capEven = ctx->capEven;
+        L.capOdd = ctx->capOdd;
+        L.errFlag = ctx->errFlag;
+        CK(cudaEventRecord(ctx->ev[2], s));
+        switch (types[i]) {
+        case T_NONE:
+            launch_none_forward(L, s, &ctx->launches); // inverse of a copy is a copy
+            break;
+        case T_BWT:
+            launch_bwt_inverse(L, ctx->ws, s, &ctx->launches);
+            break;
+        case T_ZRLT:
+            launch_zrlt_inverse(L, ctx->ws, s, &ctx->launches);
+            break;
+        case T_MTFT:
+            launch_sbrt_inverse(L, 1, ctx->ws, s, &ctx->launches);
+            break;
+        case T_RANK:
+            launch_sbrt_inverse(L, 2, ctx->ws, s, &ctx->launches);
+            break;
+        }
+        CK(cudaEventRecord(ctx->ev[3], s));
+        CK(cudaEventSynchronize(ctx->ev[3]));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
+        add_stage_time(ctx, types[i], ms);
+    }
+    const BlkState* stFinal = ctx->st + (i64)nt * ctx->maxBatch;
+    launch_copy_out(bt, stFinal, nB, d_out, outStride, s, &ctx->launches);
+    CK(cudaEventRecord(ctx->ev[4], s));
+    CK(cudaMemcpyAsync(ctx->h_err, ctx->errFlag, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ctx->h_st, stFinal, sizeof(BlkState) * nB, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    ctx->ms[3] = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]);
+    ctx->ms[5] = ms;
+    for (int b = 0; b < nB; b++)
+        h_outLens[b] = ctx->h_st[b].len;
+    return map_kerr(ctx, ctx->h_err[0]);
+}
+
+// Parse one block's private header (mode byte, [skip flags], length) at r.pos.
+// Returns 0 ok, 1 copy block, <0 error.
+static int parse_block_header(HostBitReader& r, int blkLen, u8* flags, int* preLen)
+{
+    const int mode = (int)r.get(8);
+    int fl = 0;
+    int copy = 0;
+    if (mode & 0x80)
+        copy = 1;
+    else if (mode & 0x10)
+        fl = (int)r.get(8);
+    else
+        fl = ((mode << 4) | 0x0F) & 0xFF;
+    const int dataSize = 1 + ((mode >> 5) & 3);
+    const int pre = (int)r.get(8 * dataSize);
+    int maxT = blkLen + blkLen / 2;
+    if (maxT < 2048)
+        maxT = 2048;
+    if (r.bad || pre <= 0 || pre > maxT)
+        return -1;
+    *flags = (u8)fl;
+    *preLen = pre;
+    return copy;
+}
+
+extern "C" int knz_decode_blocks_dev(knz_ctx* ctx, uint64_t tType, int eType, int blockSize, const uint8_t* d_in,
+                                     int64_t inStride, const uint64_t* h_inBits, int nBlocks, uint8_t* d_out,
+                                     int64_t outStride, int32_t* h_outLens)
+{
+    // The block headers live in device memory here: fetch the first 8 bytes of each block.
+    if (!ctx || !d_in || !h_inBits || !d_out || !h_outLens)
+        return KNZ_ERR_INVALID_PARAM;
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    const int blkLen = blockSize + ((blockSize >> 4) > 512 ? (blockSize >> 4) : 512);
+    for (int off = 0; off < nBlocks; off += ctx->maxBatch) {
+        const int nb = (nBlocks - off < ctx->maxBatch) ? nBlocks - off : ctx->maxBatch;
+        u8* heads = (u8*)malloc((size_t)nb * 8);
+        CK(cudaMemcpy2DAsync(heads, 8, d_in + (i64)off * inStride, (size_t)inStride, 8, (size_t)nb,
+                             cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        u64* pay = (u64*)malloc(sizeof(u64) * (size_t)nb);
+        u64* endb = (u64*)malloc(sizeof(u64) * (size_t)nb);
+        int* pre = (int*)malloc(sizeof(int) * (size_t)nb);
+        u8* fl = (u8*)malloc((size_t)nb);
+        int rc = KNZ_OK;
+        for (int b = 0; b < nb && rc == KNZ_OK; b++) {
+            HostBitReader r = { heads + 8 * b, 64, 0, false };
+            const int k = parse_block_header(r, blkLen, &fl[b], &pre[b]);
+            if (k != 0)
+                rc = (k < 0) ? KNZ_ERR_INVALID_FILE : KNZ_ERR_INVALID_CODEC; // device path: no copy blocks
+            pay[b] = r.pos;
+            endb[b] = h_inBits[off + b];
+        }
+        if (rc == KNZ_OK)
+            rc = decode_batch(ctx, tType, eType, blockSize, d_in + (i64)off * inStride, inStride, pay, endb, pre, fl, nb,
+                              d_out + (i64)off * outStride, outStride, h_outLens + off);
+        free(heads);
+        free(pay);
+        free(endb);
+        free(pre);
+        free(fl);
+        if (rc != KNZ_OK)
+            return rc;
+    }
+    return KNZ_OK;
+}
+
+extern "C" int knz_decode_blocks(knz_ctx* ctx, uint64_t tType, int eType, int blockSize, const uint8_t* in,
+                                 int64_t inStride, const uint64_t* inBits, int nBlocks, uint8_t* out,
+                                 int64_t outStride, int32_t* outLens)
+{
+    if (!ctx || !in || !inBits || !out || !outLens)
+        return KNZ_ERR_INVALID_PARAM;
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    const int blkLen = blockSize + ((blockSize >> 4) > 512 ? (blockSize >> 4) : 512);
+    for (int off = 0; off < nBlocks; off += ctx->maxBatch) {
+        const int nb = (nBlocks - off < ctx->maxBatch) ? nBlocks - off : ctx->maxBatch;
+        u64* pay = (u64*)malloc(sizeof(u64) * (size_t)nb);
+        u64* endb = (u64*)malloc(sizeof(u64) * (size_t)nb);
+        int* pre = (int*)malloc(sizeof(int) * (size_t)nb);
+        u8* fl = (u8*)malloc((size_t)nb);
+        int* map = (int*)malloc(sizeof(int) * (size_t)nb);
+        int ng = 0, rc = KNZ_OK;
+        for (int b = 0; b < nb && rc == KNZ_OK; b++) {
+            const u8* p = in + (i64)(off + b) * inStride;
+            const i64 nbytes = (i64)((inBits[off + b] + 7) >> 3);
+            HostBitReader r = { p, inBits[off + b], 0, false };
+            u8 f = 0;
+            int pl = 0;
+            const int k = parse_block_header(r, blkLen, &f, &pl);
+            if (k < 0 || nbytes + 16 > ctx->outStride) {
+                rc = KNZ_ERR_INVALID_FILE;
+            } else if (k == 1) { // copy block: raw bytes follow
+                if (r.pos + 8ull * (u64)pl > inBits[off + b] || pl > outStride) {
+                    rc = KNZ_ERR_INVALID_FILE;
+                } else {
+                    memcpy(out + (i64)(off + b) * outStride, p + (r.pos >> 3), (size_t)pl);
+                    outLens[off + b] = pl;
+                }
+            } else {
+                CK(cudaMemcpyAsync(ctx->dOut + (i64)ng * ctx->outStride, p, (size_t)nbytes, cudaMemcpyHostToDevice, s));
+                pay[ng] = r.pos;
+                endb[ng] = inBits[off + b];
+                pre[ng] = pl;
+                fl[ng] = f;
+                map[ng] = off + b;
+                ng++;
+            }
+        }
+        int32_t* ol = (int32_t*)malloc(sizeof(int32_t) * (size_t)nb);
+        if (rc == KNZ_OK && ng > 0)
+            rc = decode_batch(ctx, tType, eType, blockSize, ctx->dOut, ctx->outStride, pay, endb, pre, fl, ng,
+                              ctx->dStageIn, ctx->bstride, ol);
+        if (rc == KNZ_OK) {
+            for (int g = 0; g < ng; g++) {
+                if (ol[g] > outStride) {
+                    rc = KNZ_ERR_OUTPUT_TOO_SMALL;
+                    break;
+                }
+                cudaMemcpyAsync(out + (i64)map[g] * outStride, ctx->dStageIn + (i64)g * ctx->bstride, (size_t)ol[g],
+                                cudaMemcpyDeviceToHost, s);
+                outLens[map[g]] = ol[g];
+            }
+            cudaStreamSynchronize(s);
+        }
+        free(ol);
+        free(pay);
+        free(endb);
+        free(pre);
+        free(fl);
+        free(map);
+        if (rc != KNZ_OK)
+            return rc;
+    }
+    return KNZ_OK;
+}
+
+extern "C" int knz_decompress(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_t* out, int64_t cap, int64_t* outLen)
+{
+    if (!ctx || !in || !out || !outLen || n < 20)
+        return KNZ_ERR_INVALID_PARAM;
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    HostBitReader r = { in, 8ull * (u64)n, 0, false };
+    if (r.get(32) != 0x4B414E5A)
+        return KNZ_ERR_INVALID_FILE;
+    if (r.get(4) != 6)
+        return KNZ_ERR_STREAM_VERSION;
+    if (r.get(2) != 0) {
+        snprintf(ctx->err, sizeof(ctx->err), "block checksums not implemented");
+        return KNZ_ERR_INVALID_CODEC;
+    }
+    const int eType = (int)r.get(5);
+    const u64 tType = r.get(48);
+    const int blockSize = (int)r.get(28) << 4;
+    const int szMask = (int)r.get(2);
+    if (szMask)
+        r.get(16 * szMask);
+    r.get(15);
+    r.get(24); // header checksum (validated by the reference reader; not needed to decode)
+    if (r.bad || blockSize < 1024 || blockSize > ctx->maxBlockSize)
+        return KNZ_ERR_BLOCK_SIZE;
+    const int blkLen = blockSize + ((blockSize >> 4) > 512 ? (blockSize >> 4) : 512);
+    // whole compressed stream to the device; kernels read at bit offsets
+    int rc = grow(ctx, &ctx->dStream, &ctx->dStreamCap, round_up(n + 256, 256));
+    if (rc != KNZ_OK)
+        return rc;
+    rc = grow(ctx, &ctx->dPlain, &ctx->dPlainCap, round_up((i64)ctx->maxBatch * blockSize + 256, 256));
+    if (rc != KNZ_OK)
+        return rc;
+    CK(cudaMemsetAsync(ctx->dStream + (n & ~(i64)255), 0, (size_t)(round_up(n + 256, 256) - (n & ~(i64)255)), s));
+    CK(cudaMemcpyAsync(ctx->dStream, in, (size_t)n, cudaMemcpyHostToDevice, s));
+    const int mb = ctx->maxBatch;
+    u64* pay = (u64*)malloc(sizeof(u64) * (size_t)mb);
+    u64* endb = (u64*)malloc(sizeof(u64) * (size_t)mb);
+    int* pre = (int*)malloc(sizeof(int) * (size_t)mb);
+    u8* fl = (u8*)malloc((size_t)mb);
+    int32_t* ol = (int32_t*)malloc(sizeof(int32_t) * (size_t)mb);
+    i64 produced = 0;
+    bool done = false;
+    float acc[6] = { 0, 0, 0, 0, 0, 0 };
+    while (!done && rc == KNZ_OK) {
+        int ng = 0;
+        // gather up to maxBatch device blocks; copy blocks are resolved on the host in order
+        i64 batchOut = produced;
+        while (ng < mb) {
+            const int lr = 3 + (int)r.get(5);
+            const u64 bits = r.get(lr);
+            if (r.bad) {
+                rc = KNZ_ERR_INVALID_FILE;
+                break;
+            }
+            if (bits == 0) {
+                done = true;
+                break;
+            }
+            const u64 start = r.pos;
+            HostBitReader hb = { in, start + bits, start, false };
+            u8 f = 0;
+            int pl = 0;
+            const int k = parse_block_header(hb, blkLen, &f, &pl);
+            if (k < 0 || start + bits > r.nbits) {
+                rc = KNZ_ERR_INVALID_FILE;
+                break;
+            }
+            if (k == 1) {
+                if (ng > 0) { // keep output order simple: flush the device batch first
+                    r.pos = start - (u64)(5 + lr);
+                    break;
+                }
+                if (hb.pos + 8ull * (u64)pl > start + bits || produced + pl > cap) {
+                    rc = KNZ_ERR_INVALID_FILE;
+                    break;
+                }
+                for (int i = 0; i < pl; i++)
+                    out[produced + i] = (u8)hb.get(8);
+                produced += pl;
+                batchOut = produced;
+                r.pos = start + bits;
+                continue;
+            }
+            pay[ng] = hb.pos;
+            endb[ng] = start + bits;
+            pre[ng] = pl;
+            fl[ng] = f;
+            ng++;
+            r.pos = start + bits;
+        }
+        if (rc != KNZ_OK || ng == 0)
+            continue;
+        rc = decode_batch(ctx, tType, eType, blockSize, ctx->dStream, 0, pay, endb, pre, fl, ng, ctx->dPlain, blockSize,
+                          ol);
+        if (rc != KNZ_OK)
+            break;
+        for (int i = 0; i < 6; i++)
+            acc[i] += ctx->ms[i];
+        // decoded blocks are contiguous when every block but the last is full
+        for (int g = 0; g < ng; g++) {
+            if (ol[g] > blockSize || batchOut + ol[g] > cap) {
+                rc = KNZ_ERR_OUTPUT_TOO_SMALL;
+                break;
+            }
+            cudaMemcpyAsync(out + batchOut, ctx->dPlain + (i64)g * blockSize, (size_t)ol[g], cudaMemcpyDeviceToHost, s);
+            batchOut += ol[g];
+        }
+        cudaStreamSynchronize(s);
+        produced = batchOut;
+    }
+    free(pay);
+    free(endb);
+    free(pre);
+    free(fl);
+    free(ol);
+    if (rc != KNZ_OK)
+        return rc;
+    *outLen = produced;
+    for (int i = 0; i < 6; i++)
+        ctx->ms[i] = acc[i];
+    return KNZ_OK;
+}
+
+// ------------------------------------------------------------------ stage-level API
+static int run_single_stage(knz_ctx* ctx, int type, bool inverse, const u8* in, int n, u8* out, int cap, int* outLen,
+                            int* applied)
+{
+    if (!ctx || !in || !out || !outLen || !applied || n < 0)
+        return KNZ_ERR_INVALID_PARAM;
+    *applied = 0;
+    *outLen = 0;
+    if (n == 0) {
+        *applied = 1;
+        return KNZ_OK;
+    }
+    if (!type_supported(type))
+        return KNZ_ERR_INVALID_CODEC;
+    if ((i64)n + 64 > ctx->bstride || (i64)cap + 64 > ctx->bstride + 4096)
+        return KNZ_ERR_BLOCK_SIZE;
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->dStageIn, in, (size_t)n, cudaMemcpyHostToDevice, s));
+    ctx->h_st[0].len = n;
+    ctx->h_st[0].cur = 2;
+    ctx->h_st[0].swaps = 0;
+    ctx->h_st[0].flags = inverse ? 0x00 : 0xFF;
+    ctx->h_capEven[0] = cap;
+    ctx->h_capOdd[0] = cap;
+    CK(cudaMemcpyAsync(ctx->st, ctx->h_st, sizeof(BlkState), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->capEven, ctx->h_capEven, sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->capOdd, ctx->h_capOdd, sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(ctx->errFlag, 0, sizeof(int) * 4, s));
+    StageLaunch L;
+    L.bt.base[0] = ctx->bufA;
+    L.bt.base[1] = ctx->bufB;
+    L.bt.base[2] = ctx->dStageIn;
+    L.bt.stride[0] = L.bt.stride[1] = L.bt.stride[2] = ctx->bstride;
+    L.stIn = ctx->st;
+    L.stOut = ctx->st + ctx->maxBatch;
+    L.stageIdx = 0;
+    L.nBlocks = 1;
+    L.maxLen = (n > cap ? n : cap) + 64;
+    L.capEven = ctx->capEven;
+    L.capOdd = ctx->capOdd;
+    L.errFlag = ctx->errFlag;
+    switch (type) {
+    case T_NONE:
+        launch_none_forward(L, s, &ctx->launches);
+        break;
+    case T_BWT:
+        inverse ? launch_bwt_inverse(L, ctx->ws, s, &ctx->launches) : launch_bwt_forward(L, ctx->ws, s, &ctx->launches);
+        break;
+    case T_ZRLT:
+        inverse ? launch_zrlt_inverse(L, ctx->ws, s, &ctx->launches)
+                : launch_zrlt_forward(L, ctx->ws, s, &ctx->launches);
+        break;
+    case T_MTFT:
+    case T_RANK:
+        inverse ? launch_sbrt_inverse(L, type == T_MTFT ? 1 : 2, ctx->ws, s, &ctx->launches)
+                : launch_sbrt_forward(L, type == T_MTFT ? 1 : 2, ctx->ws, s, &ctx->launches);
+        break;
+    }
+    CK(cudaMemcpyAsync(ctx->h_err, ctx->errFlag, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ctx->h_st, L.stOut, sizeof(BlkState), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    if (ctx->h_err[0] != 0) {
+        if (inverse && ctx->h_err[0] == KERR_BAD_STREAM)
+            return KNZ_OK; // inverse() returns false on malformed input: applied stays 0
+        return map_kerr(ctx, ctx->h_err[0]);
+    }
+    const BlkState r = ctx->h_st[0];
+    if (r.swaps == 0)
+        return KNZ_OK; // stage refused
+    if (r.len > cap)
+        return KNZ_OK;
+    const u8* src = (r.cur == 0) ? ctx->bufA : (r.cur == 1) ? ctx->bufB : ctx->dStageIn;
+    CK(cudaMemcpyAsync(out, src, (size_t)r.len, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    *outLen = r.len;
+    *applied = 1;
+    return KNZ_OK;
+}
+
+extern "C" int knz_transform_forward(knz_ctx* ctx, int type, const uint8_t* in, int n, uint8_t* out, int cap,
+                                     int* outLen, int* applied)
+{
+    return run_single_stage(ctx, type, false, in, n, out, cap, outLen, applied);
+}
+
+extern "C" int knz_transform_inverse(knz_ctx* ctx, int type, const uint8_t* in, int n, uint8_t* out, int cap,
+                                     int* outLen, int* applied)
+{
+    return run_single_stage(ctx, type, true, in, n, out, cap, outLen, applied);
+}
+
+extern "C" int knz_entropy_encode(knz_ctx* ctx, int type, const uint8_t* in, int n, uint8_t* out, int64_t cap,
+                                  int64_t* outBits)
+{
+    if (!ctx || !in || !out || !outBits || n <= 0)
+        return KNZ_ERR_INVALID_PARAM;
+    if (type != E_RAW && type != E_ANS0)
+        return KNZ_ERR_INVALID_CODEC;
+    if ((i64)n + 64 > ctx->bstride)
+        return KNZ_ERR_BLOCK_SIZE;
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->dStageIn, in, (size_t)n, cudaMemcpyHostToDevice, s));
+    ctx->h_st[0].len = n;
+    ctx->h_st[0].cur = 2;
+    ctx->h_st[0].swaps = 0;
+    ctx->h_st[0].flags = 0xFF;
+    CK(cudaMemcpyAsync(ctx->st, ctx->h_st, sizeof(BlkState), cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(ctx->errFlag, 0, sizeof(int) * 4, s));
+    EncodeLaunch E;
+    E.bt.base[0] = ctx->bufA;
+    E.bt.base[1] = ctx->bufB;
+    E.bt.base[2] = ctx->dStageIn;
+    E.bt.stride[0] = E.bt.stride[1] = E.bt.stride[2] = ctx->bstride;
+    E.st = ctx->st;
+    E.nBlocks = 1;
+    E.maxChunks = ctx->maxChunks;
+    E.eType = type;
+    E.nTransforms = 1;
+    E.slots = ctx->slots;
+    E.hdrBits = ctx->hdrBits;
+    E.payBytes = ctx->payBytes;
+    E.payOff = ctx->payOff;
+    E.chunkOff = ctx->chunkOff;
+    E.blockBits = ctx->blockBits;
+    E.out = ctx->dOut;
+    E.outStride = ctx->outStride;
+    E.errFlag = ctx->errFlag;
+    launch_entropy_encode(E, s, &ctx->launches);
+    CK(cudaMemcpyAsync(ctx->h_err, ctx->errFlag, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ctx->h_bits, ctx->blockBits, sizeof(u64), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    if (ctx->h_err[0])
+        return map_kerr(ctx, ctx->h_err[0]);
+    // strip the block header the block-level path put in front (mode + length bytes)
+    const int dataSize = (n < 256) ? 1 : (ilog2_u32((u32)n) >> 3) + 1;
+    const int hdr = 1 + dataSize;
+    const u64 bits = ctx->h_bits[0] - 8ull * (u64)hdr;
+    const i64 nbytes = (i64)((bits + 7) >> 3);
+    if (nbytes > cap)
+        return KNZ_ERR_OUTPUT_TOO_SMALL;
+    CK(cudaMemcpyAsync(out, ctx->dOut + hdr, (size_t)nbytes, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    *outBits = (i64)bits;
+    return KNZ_OK;
+}
+
+extern "C" int knz_entropy_decode(knz_ctx* ctx, int type, const uint8_t* in, int64_t inBits, uint8_t* out, int n)
+{
+    if (!ctx || !in || !out || n <= 0 || inBits < 0)
+        return KNZ_ERR_INVALID_PARAM;
+    if (type != E_RAW && type != E_ANS0)
+        return KNZ_ERR_INVALID_CODEC;
+    const i64 nbytes = (inBits + 7) >> 3;
+    if ((i64)n + 64 > ctx->bstride || nbytes + 16 > ctx->outStride)
+        return KNZ_ERR_BLOCK_SIZE;
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemsetAsync(ctx->dOut + (nbytes & ~(i64)15), 0, 32, s));
+    CK(cudaMemcpyAsync(ctx->dOut, in, (size_t)nbytes, cudaMemcpyHostToDevice, s));
+    ctx->h_preLen[0] = n;
+    ctx->h_payStart[0] = 0;
+    ctx->h_bits[0] = (u64)inBits;
+    CK(cudaMemcpyAsync(ctx->dPreLen, ctx->h_preLen, sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->dPayStart, ctx->h_payStart, sizeof(u64), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->dInBits, ctx->h_bits, sizeof(u64), cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(ctx->errFlag, 0, sizeof(int) * 4, s));
+    DecodeLaunch D;
+    D.in = ctx->dOut;
+    D.inStride = ctx->outStride;
+    D.inBits = ctx->dInBits;
+    D.payStart = ctx->dPayStart;
+    D.preLen = ctx->dPreLen;
+    D.nBlocks = 1;
+    D.maxChunks = ctx->maxChunks;
+    D.eType = type;
+    D.chunkPos = ctx->chunkPos;
+    D.dst = ctx->bufA;
+    D.dstStride = ctx->bstride;
+    D.errFlag = ctx->errFlag;
+    launch_entropy_decode(D, s, &ctx->launches);
+    CK(cudaMemcpyAsync(ctx->h_err, ctx->errFlag, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(out, ctx->bufA, (size_t)n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    return map_kerr(ctx, ctx->h_err[0]);
+}

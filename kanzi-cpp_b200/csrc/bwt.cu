@@ -1,0 +1,874 @@
+// bwt.cu -- Burrows-Wheeler transform (kanzi BWT block codec) on sm_100a.
+//
+// Replaces BWTBlockCodec::forward/inverse (transform/BWTBlockCodec.cpp:32-168),
+// BWT::forward (transform/BWT.cpp:92-134) + DivSufSort::computeBWT
+// (transform/DivSufSort.cpp:171-295) and BWT::inverse (transform/BWT.cpp:136-657).
+// The BWT is canonical, so the induced-sorting suffix sorter of the reference is
+// replaced by batched prefix doubling built on a segmented LSD radix sort:
+//   * initial order: 8-byte big-endian prefixes (zero padded), radix sorted
+//   * each round h: only suffixes whose group is still ambiguous stay in play;
+//     they are re-keyed (group rank, rank[i+h]) and radix sorted; equal-key runs
+//     become the new groups; singleton groups leave the working set
+//   * only the inverse suffix array is materialised; the output is scattered as
+//     out[rank(p) + (rank(p) < rank(0))] = in[p-1], out[0] = in[n-1], primary
+//     index k = rank(k*ceil(n/8)) + 1 (same contract as constructBWT).
+// Many blocks are sorted in one launch sequence (segment = block).
+#include <string.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+#define RS_THREADS 256
+#define RS_ITEMS 8
+#define RS_TILE (RS_THREADS * RS_ITEMS)
+
+__device__ __forceinline__ int bwt_chunks(int n) { return (n < 256) ? 1 : 8; }
+
+__device__ __forceinline__ int bwt_pisz(int n)
+{
+    int lg = ilog2_u32((u32)n);
+    if (n & (n - 1))
+        lg++;
+    return (lg + 7) >> 3;
+}
+
+// ------------------------------------------------------------------ radix sort
+struct SortArrays {
+    u64* key[2];
+    u32* val[2];
+    u32* hist;      // [nBlocks][maxTiles][256]
+    u32* digitBase; // [nBlocks][256]
+    u32* totals;    // [nBlocks][8][256]
+    int* which;     // [9][maxBlocks]: buffer index holding block b's data before pass p
+    int* trivial;   // [8][maxBlocks]
+    const int* cnt; // [nBlocks]
+    int capN, maxTiles, maxBlocks;
+};
+
+// Digit totals for all 8 byte positions in one read of the keys.
+__global__ void __launch_bounds__(RS_THREADS)
+rs_totals_kernel(SortArrays A)
+{
+    __shared__ u32 s_h[8][256];
+    const int b = blockIdx.y;
+    const int cnt = A.cnt[b];
+    const int base = blockIdx.x * RS_TILE;
+    if (base >= cnt)
+        return;
+    for (int i = threadIdx.x; i < 2048; i += RS_THREADS)
+        (&s_h[0][0])[i] = 0;
+    __syncthreads();
+    const u64* __restrict__ k = A.key[A.which[b]] + (i64)b * A.capN;
+#pragma unroll
+    for (int it = 0; it < RS_ITEMS; it++) {
+        const int j = base + it * RS_THREADS + threadIdx.x;
+        if (j < cnt) {
+            const u64 v = k[j];
+#pragma unroll
+            for (int p = 0; p < 8; p++)
+                atomicAdd(&s_h[p][(v >> (8 * p)) & 0xFF], 1u);
+        }
+    }
+    __syncthreads();
+    u32* tot = A.totals + (i64)b * 2048;
+    for (int i = threadIdx.x; i < 2048; i += RS_THREADS) {
+        const u32 v = (&s_h[0][0])[i];
+        if (v)
+            atomicAdd(&tot[i], v);
+    }
+}
+
+// Per block: which passes are trivial (all keys share the digit) and where the
+// data lives before every pass.
+__global__ void rs_plan_kernel(SortArrays A, int nBlocks)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nBlocks)
+        return;
+    const u32 cnt = (u32)A.cnt[b];
+    int w = A.which[b];
+    const u32* tot = A.totals + (i64)b * 2048;
+    for (int p = 0; p < 8; p++) {
+        bool triv = (cnt <= 1);
+        if (!triv)
+            for (int d = 0; d < 256; d++)
+                if (tot[p * 256 + d] == cnt) {
+                    triv = true;
+                    break;
+                }
+        A.trivial[p * A.maxBlocks + b] = triv ? 1 : 0;
+        if (!triv)
+            w ^= 1;
+        A.which[(p + 1) * A.maxBlocks + b] = w;
+    }
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+rs_hist_kernel(SortArrays A, int pass)
+{
+    __shared__ u32 s_h[256];
+    const int b = blockIdx.y;
+    const int cnt = A.cnt[b];
+    const int base = blockIdx.x * RS_TILE;
+    if (base >= cnt || A.trivial[pass * A.maxBlocks + b])
+        return;
+    s_h[threadIdx.x] = 0;
+    __syncthreads();
+    const u64* __restrict__ k = A.key[A.which[pass * A.maxBlocks + b]] + (i64)b * A.capN;
+    const int sh = 8 * pass;
+#pragma unroll
+    for (int it = 0; it < RS_ITEMS; it++) {
+        const int j = base + it * RS_THREADS + threadIdx.x;
+        if (j < cnt)
+            atomicAdd(&s_h[(k[j] >> sh) & 0xFF], 1u);
+    }
+    __syncthreads();
+    A.hist[((i64)b * A.maxTiles + blockIdx.x) * 256 + threadIdx.x] = s_h[threadIdx.x];
+}
+
+// One CTA per block, thread = digit: exclusive prefix over tiles, then over digits.
+__global__ void __launch_bounds__(256)
+rs_scan_kernel(SortArrays A, int pass)
+{
+    __shared__ u32 s_w[8];
+    const int b = blockIdx.x;
+    const int cnt = A.cnt[b];
+    if (cnt <= 0 || A.trivial[pass * A.maxBlocks + b])
+        return;
+    const int tiles = (cnt + RS_TILE - 1) / RS_TILE;
+    u32* h = A.hist + (i64)b * A.maxTiles * 256 + threadIdx.x;
+    u32 run = 0;
+    for (int t = 0; t < tiles; t++) {
+        const u32 v = h[(i64)t * 256];
+        h[(i64)t * 256] = run;
+        run += v;
+    }
+    u32 tot;
+    const u32 ex = block_excl_sum_256(run, s_w, &tot);
+    A.digitBase[(i64)b * 256 + threadIdx.x] = ex;
+}
+
+// Stable scatter of one tile.  Element order inside a tile: warp-major, then
+// iteration, then lane, which is also the order of the loads.
+__global__ void __launch_bounds__(RS_THREADS)
+rs_scatter_kernel(SortArrays A, int pass)
+{
+    __shared__ u32 s_cnt[RS_THREADS / 32][256];
+    __shared__ u32 s_base[256];
+    const int b = blockIdx.y;
+    const int cnt = A.cnt[b];
+    const int tbase = blockIdx.x * RS_TILE;
+    if (tbase >= cnt || A.trivial[pass * A.maxBlocks + b])
+        return;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int src = A.which[pass * A.maxBlocks + b];
+    const u64* __restrict__ kin = A.key[src] + (i64)b * A.capN;
+    const u32* __restrict__ vin = A.val[src] + (i64)b * A.capN;
+    u64* __restrict__ kout = A.key[src ^ 1] + (i64)b * A.capN;
+    u32* __restrict__ vout = A.val[src ^ 1] + (i64)b * A.capN;
+    const int sh = 8 * pass;
+    for (int i = threadIdx.x; i < (RS_THREADS / 32) * 256; i += RS_THREADS)
+        (&s_cnt[0][0])[i] = 0;
+    s_base[threadIdx.x] = A.digitBase[(i64)b * 256 + threadIdx.x] +
+                          A.hist[((i64)b * A.maxTiles + blockIdx.x) * 256 + threadIdx.x];
+    __syncthreads();
+    u64 key[RS_ITEMS];
+    u32 val[RS_ITEMS];
+    u32 rnk[RS_ITEMS];
+#pragma unroll
+    for (int it = 0; it < RS_ITEMS; it++) {
+        const int j = tbase + w * (32 * RS_ITEMS) + it * 32 + lane;
+        const bool ok = j < cnt;
+        key[it] = ok ? kin[j] : 0;
+        val[it] = ok ? vin[j] : 0;
+        const u32 d = ok ? (u32)((key[it] >> sh) & 0xFF) : 256u; // 256 = padding class
+        const u32 peers = __match_any_sync(FULL_MASK, d);
+        const u32 prior = (d < 256) ? s_cnt[w][d] : 0;
+        __syncwarp();
+        if (d < 256 && (peers & lanemask_lt()) == 0)
+            s_cnt[w][d] = prior + __popc(peers);
+        __syncwarp();
+        rnk[it] = prior + __popc(peers & lanemask_lt());
+    }
+    __syncthreads();
+    {
+        // exclusive prefix over warps for every digit (thread = digit)
+        u32 run = 0;
+#pragma unroll
+        for (int x = 0; x < RS_THREADS / 32; x++) {
+            const u32 v = s_cnt[x][threadIdx.x];
+            s_cnt[x][threadIdx.x] = run;
+            run += v;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < RS_ITEMS; it++) {
+        const int j = tbase + w * (32 * RS_ITEMS) + it * 32 + lane;
+        if (j < cnt) {
+            const u32 d = (u32)((key[it] >> sh) & 0xFF);
+            const u32 pos = s_base[d] + s_cnt[w][d] + rnk[it];
+            kout[pos] = key[it];
+            vout[pos] = val[it];
+        }
+    }
+}
+
+static void radix_sort(const SortArrays& A, int nBlocks, int maxCnt, u32 passMask, cudaStream_t s, u64* launches)
+{
+    const int tiles = (maxCnt + RS_TILE - 1) / RS_TILE;
+    if (tiles <= 0)
+        return;
+    cudaMemsetAsync(A.totals, 0, sizeof(u32) * 2048 * (size_t)nBlocks, s);
+    KLAUNCH(rs_totals_kernel, dim3(tiles, nBlocks), RS_THREADS, s, A);
+    KLAUNCH(rs_plan_kernel, (nBlocks + 63) / 64, 64, s, A, nBlocks);
+    *launches += 2;
+    for (int p = 0; p < 8; p++) {
+        if (!((passMask >> p) & 1))
+            continue; // digit statically zero for every key: the plan marks it trivial as well
+        KLAUNCH(rs_hist_kernel, dim3(tiles, nBlocks), RS_THREADS, s, A, p);
+        KLAUNCH(rs_scan_kernel, nBlocks, 256, s, A, p);
+        KLAUNCH(rs_scatter_kernel, dim3(tiles, nBlocks), RS_THREADS, s, A, p);
+        *launches += 3;
+    }
+}
+
+// ------------------------------------------------------------------ forward
+__global__ void bwt_decide_kernel(StageLaunch L, int* __restrict__ cnt, int* __restrict__ which0,
+                                  int* __restrict__ bwtOk)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= L.nBlocks)
+        return;
+    const BlkState bs = L.stIn[b];
+    BlkState ns = bs;
+    const int n = bs.len;
+    const int cap = (bs.swaps & 1) ? L.capOdd[b] : L.capEven[b];
+    const int pisz = (n >= 1) ? bwt_pisz(n) : 0;
+    // BWTBlockCodec.cpp:44-60: needs room for n + 33 and 1..4 index bytes
+    const bool ok = (n >= 1) && (cap >= n + 33) && (pisz >= 1) && (pisz <= 4);
+    if (ok) {
+        ns.len = n + 1 + bwt_chunks(n) * pisz;
+        ns.cur = next_cur(bs.cur);
+        ns.swaps = bs.swaps + 1;
+        ns.flags = bs.flags & ~(1 << (7 - L.stageIdx));
+    }
+    L.stOut[b] = ns;
+    cnt[b] = ok ? n : 0;
+    which0[b] = 0;
+    bwtOk[b] = ok ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256)
+bwt_init_keys_kernel(BufTable bt, const BlkState* __restrict__ st, const int* __restrict__ bwtOk, int capN,
+                     u64* __restrict__ keyOut, u32* __restrict__ valOut)
+{
+    const int b = blockIdx.y;
+    if (!bwtOk[b])
+        return;
+    const BlkState bs = st[b];
+    const int n = bs.len;
+    const u8* __restrict__ src = blk_src(bt, bs, b);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        u64 k = 0;
+#pragma unroll
+        for (int x = 0; x < 8; x++)
+            k = (k << 8) | ((i + x < n) ? (u64)src[i + x] : 0ull);
+        keyOut[(i64)b * capN + i] = k;
+        valOut[(i64)b * capN + i] = (u32)i;
+    }
+}
+
+// Flags of sorted element j:  head = starts a new equal-key run; ghead = starts
+// a new OLD group (high key word changes; the initial round has one old group);
+// resolved = its run has length 1.
+struct GrpCtx {
+    const u64* key[2];
+    const u32* val[2];
+    u32* valOut[2];
+    u32* grpOut;
+    u32* isa;
+    const int* which; // [9][maxBlocks]; row 8 = after the sort
+    int* whichNext;   // row 0
+    const int* cnt;
+    int* cntNext;
+    u32* part; // [nBlocks][maxTiles][4]: maxH, maxG, sumU (then exclusive carries)
+    int capN, maxTiles, maxBlocks, initial;
+};
+
+__device__ __forceinline__ void grp_flags(const u64* __restrict__ k, int j, int cnt, int initial, bool& head,
+                                          bool& ghead, bool& resolved)
+{
+    const u64 kj = k[j];
+    if (j == 0) {
+        head = true;
+        ghead = true;
+    } else {
+        const u64 kp = k[j - 1];
+        head = kj != kp;
+        ghead = !initial && ((kj >> 32) != (kp >> 32));
+    }
+    const bool nexthead = (j + 1 >= cnt) || (k[j + 1] != kj);
+    resolved = head && nexthead;
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+bwt_grp_partials_kernel(GrpCtx G)
+{
+    __shared__ u32 s_a[8], s_b[8], s_c[8];
+    const int b = blockIdx.y;
+    const int cnt = G.cnt[b];
+    const int tbase = blockIdx.x * RS_TILE;
+    if (tbase >= cnt)
+        return;
+    const u64* __restrict__ k = G.key[G.which[8 * G.maxBlocks + b]] + (i64)b * G.capN;
+    u32 mh = 0, mg = 0, su = 0;
+    const int j0 = tbase + threadIdx.x * RS_ITEMS;
+    for (int x = 0; x < RS_ITEMS; x++) {
+        const int j = j0 + x;
+        if (j >= cnt)
+            break;
+        bool head, ghead, res;
+        grp_flags(k, j, cnt, G.initial, head, ghead, res);
+        if (head)
+            mh = (u32)j + 1;
+        if (ghead)
+            mg = (u32)j + 1;
+        su += res ? 0u : 1u;
+    }
+    // block reduce: max, max, sum
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mh = max(mh, __shfl_xor_sync(FULL_MASK, mh, o));
+        mg = max(mg, __shfl_xor_sync(FULL_MASK, mg, o));
+        su += __shfl_xor_sync(FULL_MASK, su, o);
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) {
+        s_a[w] = mh;
+        s_b[w] = mg;
+        s_c[w] = su;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 a = 0, bb = 0, c = 0;
+        for (int i = 0; i < 8; i++) {
+            a = max(a, s_a[i]);
+            bb = max(bb, s_b[i]);
+            c += s_c[i];
+        }
+        u32* p = G.part + ((i64)b * G.maxTiles + blockIdx.x) * 4;
+        p[0] = a;
+        p[1] = bb;
+        p[2] = c;
+    }
+}
+
+// One thread per block: exclusive carries over tiles; survivors; next source buffer.
+__global__ void bwt_grp_scan_kernel(GrpCtx G, int nBlocks)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nBlocks)
+        return;
+    const int cnt = G.cnt[b];
+    const int after = G.which[8 * G.maxBlocks + b];
+    G.whichNext[b] = after ^ 1; // survivors are compacted into the other buffer
+    if (cnt <= 0) {
+        G.cntNext[b] = 0;
+        return;
+    }
+    const int tiles = (cnt + RS_TILE - 1) / RS_TILE;
+    u32 ch = 0, cg = 0, cu = 0;
+    u32* p = G.part + (i64)b * G.maxTiles * 4;
+    for (int t = 0; t < tiles; t++) {
+        const u32 a = p[4 * t], bb = p[4 * t + 1], c = p[4 * t + 2];
+        p[4 * t] = ch;
+        p[4 * t + 1] = cg;
+        p[4 * t + 2] = cu;
+        ch = max(ch, a);
+        cg = max(cg, bb);
+        cu += c;
+    }
+    G.cntNext[b] = (int)cu;
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+bwt_grp_apply_kernel(GrpCtx G)
+{
+    __shared__ u32 s_w[8], s_mh[8], s_mg[8];
+    const int b = blockIdx.y;
+    const int cnt = G.cnt[b];
+    const int tbase = blockIdx.x * RS_TILE;
+    if (tbase >= cnt)
+        return;
+    const int src = G.which[8 * G.maxBlocks + b];
+    const u64* __restrict__ k = G.key[src] + (i64)b * G.capN;
+    const u32* __restrict__ v = G.val[src] + (i64)b * G.capN;
+    u32* __restrict__ vout = G.valOut[src ^ 1] + (i64)b * G.capN;
+    u32* __restrict__ gout = G.grpOut + (i64)b * G.capN;
+    u32* __restrict__ isa = G.isa + (i64)b * G.capN;
+    const u32* carry = G.part + ((i64)b * G.maxTiles + blockIdx.x) * 4;
+    const int j0 = tbase + threadIdx.x * RS_ITEMS;
+    bool head[RS_ITEMS], ghead[RS_ITEMS], res[RS_ITEMS];
+    u32 mh = 0, mg = 0, su = 0;
+#pragma unroll
+    for (int x = 0; x < RS_ITEMS; x++) {
+        const int j = j0 + x;
+        head[x] = ghead[x] = false;
+        res[x] = true;
+        if (j < cnt) {
+            grp_flags(k, j, cnt, G.initial, head[x], ghead[x], res[x]);
+            if (head[x])
+                mh = (u32)j + 1;
+            if (ghead[x])
+                mg = (u32)j + 1;
+            su += res[x] ? 0u : 1u;
+        }
+    }
+    // exclusive scans across threads: max (H), max (G), sum (U)
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    u32 ih = mh, ig = mg;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 th = __shfl_up_sync(FULL_MASK, ih, o), tg = __shfl_up_sync(FULL_MASK, ig, o);
+        if (lane >= o) {
+            ih = max(ih, th);
+            ig = max(ig, tg);
+        }
+    }
+    if (lane == 31) {
+        s_mh[w] = ih;
+        s_mg[w] = ig;
+    }
+    u32 eh = __shfl_up_sync(FULL_MASK, ih, 1), eg = __shfl_up_sync(FULL_MASK, ig, 1);
+    if (lane == 0)
+        eh = eg = 0;
+    u32 totU;
+    const u32 eu = block_excl_sum_256(su, s_w, &totU); // contains __syncthreads
+    u32 bh = carry[0], bg = carry[1];
+    for (int i = 0; i < w; i++) {
+        bh = max(bh, s_mh[i]);
+        bg = max(bg, s_mg[i]);
+    }
+    u32 H = max(bh, eh), Gm = max(bg, eg), U = carry[2] + eu;
+#pragma unroll
+    for (int x = 0; x < RS_ITEMS; x++) {
+        const int j = j0 + x;
+        if (j >= cnt)
+            break;
+        if (head[x])
+            H = (u32)j + 1;
+        if (ghead[x])
+            Gm = (u32)j + 1;
+        const u32 old = G.initial ? 0u : (u32)(k[j] >> 32);
+        const u32 rank = old + (H - Gm);
+        const u32 sfx = v[j];
+        isa[sfx] = rank;
+        if (!res[x]) {
+            vout[U] = sfx;
+            gout[U] = rank;
+            U++;
+        }
+    }
+}
+
+// Re-key the survivors for doubling step h: (group rank, order of suffix i+h).
+// Past-the-end neighbours sort before every real rank, longer overshoot first
+// (end-of-string is the smallest symbol).
+__global__ void __launch_bounds__(256)
+bwt_gather_kernel(const BlkState* __restrict__ st, const int* __restrict__ cnt, const int* __restrict__ which0,
+                  u64* key0, u64* key1, const u32* val0, const u32* val1, const u32* __restrict__ grp,
+                  const u32* __restrict__ isa, int capN, int h)
+{
+    const int b = blockIdx.y;
+    const int c = cnt[b];
+    const int n = st[b].len;
+    const int w = which0[b];
+    u64* __restrict__ k = (w ? key1 : key0) + (i64)b * capN;
+    const u32* __restrict__ v = (w ? val1 : val0) + (i64)b * capN;
+    const u32* __restrict__ g = grp + (i64)b * capN;
+    const u32* __restrict__ r = isa + (i64)b * capN;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < c; j += gridDim.x * blockDim.x) {
+        const u32 i = v[j];
+        const i64 nb = (i64)i + h;
+        const u32 k2 = (nb < n) ? r[nb] + (u32)n : (u32)(n - 1) - i;
+        k[j] = ((u64)g[j] << 32) | k2;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+bwt_emit_kernel(BufTable bt, const BlkState* __restrict__ st, const int* __restrict__ bwtOk,
+                const u32* __restrict__ isa, int capN)
+{
+    const int b = blockIdx.y;
+    if (!bwtOk[b])
+        return;
+    const BlkState bs = st[b];
+    const int n = bs.len;
+    const u8* __restrict__ src = blk_src(bt, bs, b);
+    u8* __restrict__ dst = blk_dst(bt, bs, b);
+    const u32* __restrict__ r = isa + (i64)b * capN;
+    const int chunks = bwt_chunks(n), pisz = bwt_pisz(n);
+    const int hdr = 1 + chunks * pisz;
+    const u32 r0 = r[0];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        // header: mode byte, then chunks x pisz big-endian bytes of (primary index - 1)
+        dst[0] = (u8)((ilog2_u32((u32)chunks) << 2) | (pisz - 1));
+        const int stp = n / chunks;
+        const int step = (chunks * stp == n) ? stp : stp + 1;
+        int q = 1;
+        for (int c = 0; c < chunks; c++) {
+            const i64 p = (i64)c * step;
+            const u32 v = (p < n) ? r[p] : 0xFFFFFFFFu; // primary index - 1 = rank; unset index -> 0 - 1
+            for (int sh = 8 * (pisz - 1); sh >= 0; sh -= 8)
+                dst[q++] = (u8)(v >> sh);
+        }
+        dst[hdr] = src[n - 1];
+    }
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x + 1; p < n; p += gridDim.x * blockDim.x) {
+        const u32 rp = r[p];
+        dst[hdr + rp + (rp < r0 ? 1 : 0)] = src[p - 1];
+    }
+}
+
+void launch_bwt_forward(const StageLaunch& L, Workspace& ws, cudaStream_t s, u64* launches)
+{
+    const int nB = L.nBlocks;
+    const int maxTiles = (ws.capN + RS_TILE - 1) / RS_TILE;
+    int* whichRows = ws.which;
+    KLAUNCH(bwt_decide_kernel, (nB + 63) / 64, 64, s, L, ws.cnt, whichRows, ws.bwtOk);
+    const int initBlocks = min((L.maxLen + 255) / 256, 1024);
+    KLAUNCH(bwt_init_keys_kernel, dim3(initBlocks, nB), 256, s, L.bt, L.stIn, ws.bwtOk, ws.capN, ws.keyA, ws.valA);
+    *launches += 2;
+
+    SortArrays A;
+    A.key[0] = ws.keyA;
+    A.key[1] = ws.keyB;
+    A.val[0] = ws.valA;
+    A.val[1] = ws.valB;
+    A.hist = ws.hist;
+    A.digitBase = ws.digitBase;
+    A.totals = ws.totals;
+    A.which = ws.which;
+    A.trivial = ws.trivial;
+    A.cnt = ws.cnt;
+    A.capN = ws.capN;
+    A.maxTiles = maxTiles;
+    A.maxBlocks = ws.maxBlocks;
+
+    GrpCtx G;
+    G.key[0] = ws.keyA;
+    G.key[1] = ws.keyB;
+    G.val[0] = ws.valA;
+    G.val[1] = ws.valB;
+    G.valOut[0] = ws.valA;
+    G.valOut[1] = ws.valB;
+    G.grpOut = ws.grpA;
+    G.isa = ws.isa;
+    G.which = ws.which;
+    G.whichNext = ws.which; // row 0
+    G.cnt = ws.cnt;
+    G.cntNext = ws.cntNext;
+    G.part = ws.scanA;
+    G.capN = ws.capN;
+    G.maxTiles = maxTiles;
+    G.maxBlocks = ws.maxBlocks;
+
+    int maxCnt = L.maxLen;
+    // key2 < 2n, group rank < n  ->  which byte positions can be non-zero
+    const int lowBits = ilog2_u32((u32)(2 * (i64)L.maxLen > 1 ? 2 * (i64)L.maxLen : 2)) + 1;
+    const int highBits = ilog2_u32((u32)(L.maxLen > 1 ? L.maxLen : 2)) + 1;
+    u32 roundMask = 0;
+    for (int p = 0; p < 4; p++)
+        if (8 * p < lowBits)
+            roundMask |= 1u << p;
+    for (int p = 0; p < 4; p++)
+        if (8 * p < highBits)
+            roundMask |= 1u << (4 + p);
+
+    for (int round = 0, h = 8;; round++) {
+        G.initial = (round == 0) ? 1 : 0;
+        radix_sort(A, nB, maxCnt, (round == 0) ? 0xFFu : roundMask, s, launches);
+        const int tiles = (maxCnt + RS_TILE - 1) / RS_TILE;
+        KLAUNCH(bwt_grp_partials_kernel, dim3(tiles, nB), RS_THREADS, s, G);
+        KLAUNCH(bwt_grp_scan_kernel, (nB + 63) / 64, 64, s, G, nB);
+        KLAUNCH(bwt_grp_apply_kernel, dim3(tiles, nB), RS_THREADS, s, G);
+        *launches += 3;
+        // survivors per block -> host (sizes the next round's grids, detects the end)
+        cudaMemcpyAsync(ws.h_cnt, ws.cntNext, sizeof(int) * nB, cudaMemcpyDeviceToHost, s);
+        cudaMemcpyAsync(ws.cnt, ws.cntNext, sizeof(int) * nB, cudaMemcpyDeviceToDevice, s);
+        cudaStreamSynchronize(s);
+        maxCnt = 0;
+        for (int b = 0; b < nB; b++)
+            maxCnt = max(maxCnt, ws.h_cnt[b]);
+        if (maxCnt == 0)
+            break;
+        if (round > 40) { // cannot happen: h exceeds any block length after 30 doublings
+            int e = KERR_INTERNAL;
+            cudaMemcpyAsync(L.errFlag, &e, sizeof(int), cudaMemcpyHostToDevice, s);
+            break;
+        }
+        const int gblocks = min((maxCnt + 255) / 256, 2048);
+        KLAUNCH(bwt_gather_kernel, dim3(gblocks, nB), 256, s, L.stIn, ws.cnt, ws.which, ws.keyA, ws.keyB, ws.valA, ws.valB,
+                ws.grpA, ws.isa, ws.capN, h);
+        *launches += 1;
+        h = (h < (1 << 29)) ? h * 2 : h;
+    }
+    const int eblocks = min((L.maxLen + 255) / 256, 2048);
+    KLAUNCH(bwt_emit_kernel, dim3(eblocks, nB), 256, s, L.bt, L.stIn, ws.bwtOk, ws.isa, ws.capN);
+    *launches += 1;
+}
+
+// ------------------------------------------------------------------ inverse
+// Header parse + decision (BWTBlockCodec.cpp:89-168, bsVersion 6 branch).
+__global__ void bwt_inv_decide_kernel(StageLaunch L, int* __restrict__ cnt, int* __restrict__ which0,
+                                      int* __restrict__ pidx, int* __restrict__ bwtOk)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= L.nBlocks)
+        return;
+    const BlkState bs = L.stIn[b];
+    BlkState ns = bs;
+    cnt[b] = 0;
+    which0[b] = 0;
+    bwtOk[b] = 0;
+    if (bs.flags & (1 << (7 - L.stageIdx))) {
+        L.stOut[b] = ns;
+        return;
+    }
+    const u8* __restrict__ src = blk_src(L.bt, bs, b);
+    const int n = bs.len;
+    const int cap = (bs.swaps & 1) ? L.capOdd[b] : L.capEven[b];
+    bool ok = n >= 2;
+    int m = 0;
+    if (ok) {
+        const int mode = src[0];
+        const int chunks = 1 << ((mode >> 2) & 7);
+        const int pisz = (mode & 3) + 1;
+        const int hdr = 1 + chunks * pisz;
+        m = n - hdr;
+        ok = (n >= hdr) && (chunks <= 8) && (m >= 1) && (chunks == bwt_chunks(m)) && (m <= cap);
+        if (ok) {
+            int q = 1;
+            for (int c = 0; c < chunks; c++) {
+                u32 v = 0;
+                for (int x = 0; x < pisz; x++)
+                    v = (v << 8) | src[q++];
+                const i64 p = (i64)v + 1;
+                // chunk starts that do not exist carry index 0 (encoded as -1): ignore them
+                const int stp = m / chunks;
+                const int step = (chunks * stp == m) ? stp : stp + 1;
+                const bool used = (i64)c * step < m;
+                if (used && (p < 1 || p > m))
+                    ok = false;
+                pidx[b * 8 + c] = used ? (int)p : 0;
+            }
+        }
+    }
+    if (!ok) {
+        atomicExch(L.errFlag, KERR_BAD_STREAM);
+        L.stOut[b] = ns;
+        return;
+    }
+    ns.len = m;
+    ns.cur = next_cur(bs.cur);
+    ns.swaps = bs.swaps + 1;
+    L.stOut[b] = ns;
+    cnt[b] = m;
+    bwtOk[b] = 1;
+}
+
+// keys = L column bytes, vals = row -> suffix-rank mapping (BWT.cpp:203-219):
+// row 0 is the end-of-string row, rows 1..p0-1 hold ranks 0..p0-2, rows >= p0 hold their own index.
+__global__ void __launch_bounds__(256)
+bwt_inv_init_kernel(BufTable bt, const BlkState* __restrict__ st, const int* __restrict__ bwtOk,
+                    const int* __restrict__ pidx, int capN, u64* __restrict__ keyOut, u32* __restrict__ valOut)
+{
+    const int b = blockIdx.y;
+    if (!bwtOk[b])
+        return;
+    const BlkState bs = st[b];
+    const u8* __restrict__ src = blk_src(bt, bs, b);
+    const int mode = src[0];
+    const int hdr = 1 + (1 << ((mode >> 2) & 7)) * ((mode & 3) + 1);
+    const int m = bs.len - hdr;
+    const int p0 = pidx[b * 8];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        keyOut[(i64)b * capN + i] = (u64)src[hdr + i];
+        valOut[(i64)b * capN + i] = (i == 0) ? 0u : ((i < p0) ? (u32)(i - 1) : (u32)i);
+    }
+}
+
+// One thread per (block, chunk): follow psi from the chunk's primary index.
+__global__ void bwt_inv_chase_kernel(BufTable bt, const BlkState* __restrict__ stIn, const int* __restrict__ bwtOk,
+                                     const int* __restrict__ pidx, const int* __restrict__ whichAfter, int capN,
+                                     const u64* key0, const u64* key1, const u32* val0, const u32* val1, int nBlocks,
+                                     int* __restrict__ errFlag)
+{
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = id >> 3, c = id & 7;
+    if (b >= nBlocks || !bwtOk[b])
+        return;
+    const BlkState bs = stIn[b];
+    const u8* __restrict__ src = blk_src(bt, bs, b);
+    u8* __restrict__ dst = blk_dst(bt, bs, b);
+    const int mode = src[0];
+    const int chunks = 1 << ((mode >> 2) & 7);
+    const int hdr = 1 + chunks * ((mode & 3) + 1);
+    const int m = bs.len - hdr;
+    if (c >= chunks)
+        return;
+    const int stp = m / chunks;
+    const int step = (chunks * stp == m) ? stp : stp + 1;
+    const i64 start = (i64)c * step;
+    if (start >= m)
+        return;
+    const int end = (start + step < (i64)m) ? (int)(start + step) : m;
+    const int w = whichAfter[b];
+    const u64* __restrict__ F = (w ? key1 : key0) + (i64)b * capN;
+    const u32* __restrict__ nxt = (w ? val1 : val0) + (i64)b * capN;
+    u32 t = (u32)(pidx[b * 8 + c] - 1);
+    for (int p = (int)start; p < end; p++) {
+        if (t >= (u32)m) {
+            atomicExch(errFlag, KERR_BAD_STREAM);
+            return;
+        }
+        dst[p] = (u8)F[t];
+        t = nxt[t];
+    }
+}
+
+void launch_bwt_inverse(const StageLaunch& L, Workspace& ws, cudaStream_t s, u64* launches)
+{
+    const int nB = L.nBlocks;
+    const int maxTiles = (ws.capN + RS_TILE - 1) / RS_TILE;
+    KLAUNCH(bwt_inv_decide_kernel, (nB + 63) / 64, 64, s, L, ws.cnt, ws.which, ws.pidx, ws.bwtOk);
+    const int initBlocks = min((L.maxLen + 255) / 256, 1024);
+    KLAUNCH(bwt_inv_init_kernel, dim3(initBlocks, nB), 256, s, L.bt, L.stIn, ws.bwtOk, ws.pidx, ws.capN, ws.keyA, ws.valA);
+    *launches += 2;
+    SortArrays A;
+    A.key[0] = ws.keyA;
+    A.key[1] = ws.keyB;
+    A.val[0] = ws.valA;
+    A.val[1] = ws.valB;
+    A.hist = ws.hist;
+    A.digitBase = ws.digitBase;
+    A.totals = ws.totals;
+    A.which = ws.which;
+    A.trivial = ws.trivial;
+    A.cnt = ws.cnt;
+    A.capN = ws.capN;
+    A.maxTiles = maxTiles;
+    A.maxBlocks = ws.maxBlocks;
+    radix_sort(A, nB, L.maxLen, 0x01u, s, launches); // stable counting sort by symbol = LF/psi construction
+    KLAUNCH(bwt_inv_chase_kernel, (nB * 8 + 63) / 64, 64, s, L.bt, L.stIn, ws.bwtOk, ws.pidx, ws.which + 8 * ws.maxBlocks,
+            ws.capN, ws.keyA, ws.keyB, ws.valA, ws.valB, nB, L.errFlag);
+    *launches += 1;
+}
+
+// ------------------------------------------------------------------ misc stages
+__global__ void none_stage_kernel(StageLaunch L)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= L.nBlocks)
+        return;
+    // NullTransform copies (transform/NullTransform.hpp:45-65); a copy is
+    // observable only through the swap parity and the cleared skip bit, so the
+    // data stays where it is.
+    BlkState ns = L.stIn[b];
+    const int cap = (ns.swaps & 1) ? L.capOdd[b] : L.capEven[b];
+    if (ns.len <= cap) {
+        ns.swaps += 1;
+        ns.flags &= ~(1 << (7 - L.stageIdx));
+    }
+    L.stOut[b] = ns;
+}
+
+void launch_none_forward(const StageLaunch& L, cudaStream_t s, u64* launches)
+{
+    KLAUNCH(none_stage_kernel, (L.nBlocks + 63) / 64, 64, s, L);
+    *launches += 1;
+}
+
+__global__ void __launch_bounds__(256)
+copy_out_kernel(BufTable bt, const BlkState* __restrict__ st, u8* __restrict__ out, i64 outStride)
+{
+    const int b = blockIdx.y;
+    const BlkState bs = st[b];
+    const u8* __restrict__ src = blk_src(bt, bs, b);
+    u8* __restrict__ dst = out + (i64)b * outStride;
+    const int n = bs.len;
+    if ((((uintptr_t)dst) & 15) == 0) {
+        const int n16 = n >> 4;
+        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x)
+            d4[i] = s4[i];
+        for (int i = (n16 << 4) + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+            dst[i] = src[i];
+    } else {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+            dst[i] = src[i];
+    }
+}
+
+void launch_copy_out(const BufTable& bt, const BlkState* st, int nBlocks, u8* out, i64 outStride, cudaStream_t s,
+                     u64* launches)
+{
+    KLAUNCH(copy_out_kernel, dim3(64, nBlocks), 256, s, bt, st, out, outStride);
+    *launches += 1;
+}
+
+// ------------------------------------------------------------------ workspace
+template <class T>
+static bool wsalloc(T** p, i64 count)
+{
+    return cudaMalloc((void**)p, (size_t)(count > 0 ? count : 1) * sizeof(T)) == cudaSuccess;
+}
+
+bool workspace_alloc(Workspace& ws, int maxBlocks, int capN)
+{
+    memset(&ws, 0, sizeof(ws));
+    ws.maxBlocks = maxBlocks;
+    ws.capN = capN;
+    const i64 nb = maxBlocks;
+    const i64 elems = nb * capN;
+    const i64 zTiles = (capN + 4095) / 4096 + 1;
+    const i64 sTiles = (capN + RS_TILE - 1) / RS_TILE + 1;
+    bool ok = true;
+    ws.tileWords = nb * zTiles * 8;
+    ok = ok && wsalloc(&ws.tileA, ws.tileWords);
+    ok = ok && wsalloc(&ws.tileB, ws.tileWords);
+    ws.occWords = nb * zTiles * 512;
+    ok = ok && wsalloc(&ws.occ, ws.occWords);
+    ok = ok && wsalloc(&ws.keyA, elems);
+    ok = ok && wsalloc(&ws.keyB, elems);
+    ok = ok && wsalloc(&ws.valA, elems);
+    ok = ok && wsalloc(&ws.valB, elems);
+    ok = ok && wsalloc(&ws.grpA, elems);
+    ok = ok && wsalloc(&ws.isa, elems);
+    ok = ok && wsalloc(&ws.hist, nb * sTiles * 256);
+    ok = ok && wsalloc(&ws.digitBase, nb * 256);
+    ok = ok && wsalloc(&ws.totals, nb * 2048);
+    ok = ok && wsalloc(&ws.which, 9 * nb);
+    ok = ok && wsalloc(&ws.trivial, 8 * nb);
+    ok = ok && wsalloc(&ws.cnt, nb);
+    ok = ok && wsalloc(&ws.cntNext, nb);
+    ok = ok && wsalloc(&ws.scanA, nb * sTiles * 4 + nb);
+    ok = ok && wsalloc(&ws.pidx, nb * 8);
+    ok = ok && wsalloc(&ws.bwtOk, nb);
+    ok = ok && (cudaMallocHost((void**)&ws.h_cnt, sizeof(int) * (size_t)nb) == cudaSuccess);
+    return ok;
+}
+
+void workspace_free(Workspace& ws)
+{
+    void* d[] = { ws.tileA, ws.tileB, ws.occ, ws.keyA, ws.keyB, ws.valA, ws.valB, ws.grpA, ws.isa, ws.hist,
+                  ws.digitBase, ws.totals, ws.which, ws.trivial, ws.cnt, ws.cntNext, ws.scanA, ws.pidx, ws.bwtOk };
+    for (size_t i = 0; i < sizeof(d) / sizeof(d[0]); i++)
+        if (d[i])
+            cudaFree(d[i]);
+    if (ws.h_cnt)
+        cudaFreeHost(ws.h_cnt);
+    memset(&ws, 0, sizeof(ws));
+}

@@ -1,0 +1,115 @@
+// kernels.h -- internal launch interfaces between api.cu and the kernel files.
+#pragma once
+#include "common.cuh"
+
+#define ANS_CHUNK 16384
+#define ANS0_LR 12
+// Per-chunk staging slot: [0,512) header bit string (+varint, 4 states);
+// renormalisation words grow downwards from ANS_WEND; <= 3 tail bytes follow it.
+#define ANS_HDR_AREA 512
+#define ANS_WEND (ANS_HDR_AREA + 2 * ANS_CHUNK)
+#define ANS_SLOT (ANS_WEND + 512)
+
+#define E_RAW 0
+#define E_ANS0 5
+
+#define T_NONE 0
+#define T_BWT 1
+#define T_ZRLT 6
+#define T_MTFT 7
+#define T_RANK 8
+
+// device-side error flags (first one wins)
+#define KERR_OUT_OVERFLOW 1
+#define KERR_BAD_STREAM 2
+#define KERR_UNSUPPORTED 3
+#define KERR_INTERNAL 4
+
+struct EncodeLaunch {
+    BufTable bt;
+    const BlkState* st; // state after the last transform stage
+    int nBlocks, maxChunks, eType, nTransforms;
+    u8* slots;
+    u32 *hdrBits, *payBytes, *payOff;
+    u64 *chunkOff, *blockBits;
+    u8* out;
+    i64 outStride;
+    int* errFlag;
+};
+void launch_entropy_encode(const EncodeLaunch& L, cudaStream_t s, u64* launches);
+// startBit / endBit are device scalars (may alias): batches chain without a host round trip.
+void launch_stream_assemble(const u8* blockOut, i64 outStride, const u64* blockBits, int nBlocks,
+                            const u64* startBit, u64* blockOff, u64* endBit, u8* stream, cudaStream_t s,
+                            u64* launches);
+
+// Entropy decode: block b's bit string is at in + b*inStride; its entropy payload
+// starts at bit payStart[b] and must yield preLen[b] bytes into dst (buffer A).
+struct DecodeLaunch {
+    const u8* in;
+    i64 inStride;
+    const u64* inBits;    // per block total bits
+    const u64* payStart;  // per block: bit offset of the entropy payload
+    const int* preLen;    // per block: bytes to decode
+    int nBlocks, maxChunks, eType;
+    u64* chunkPos;        // [nBlocks][maxChunks] bit offset of each chunk header
+    u8* dst;
+    i64 dstStride;
+    int* errFlag;
+};
+void launch_entropy_decode(const DecodeLaunch& L, cudaStream_t s, u64* launches);
+
+// Transform stages.  Every launcher reads st[s] and writes st[s+1].
+struct StageLaunch {
+    BufTable bt;
+    const BlkState* stIn;
+    BlkState* stOut;
+    int stageIdx;   // position in the sequence (skip-flag bit 7 - stageIdx)
+    int nBlocks;
+    int maxLen;     // upper bound of len over the batch (grid sizing)
+    const int* capEven; // per block: capacity of the reference's `output` buffer
+    const int* capOdd;  // per block: capacity of the reference's `input`/private buffer
+    int* errFlag;
+};
+struct Workspace;
+void launch_none_forward(const StageLaunch& L, cudaStream_t s, u64* launches);
+void launch_zrlt_forward(const StageLaunch& L, Workspace& ws, cudaStream_t s, u64* launches);
+void launch_zrlt_inverse(const StageLaunch& L, Workspace& ws, cudaStream_t s, u64* launches);
+void launch_sbrt_forward(const StageLaunch& L, int mode, Workspace& ws, cudaStream_t s, u64* launches);
+void launch_sbrt_inverse(const StageLaunch& L, int mode, Workspace& ws, cudaStream_t s, u64* launches);
+void launch_bwt_forward(const StageLaunch& L, Workspace& ws, cudaStream_t s, u64* launches);
+void launch_bwt_inverse(const StageLaunch& L, Workspace& ws, cudaStream_t s, u64* launches);
+
+// Scratch memory shared by the stage launchers (allocated once per context).
+struct Workspace {
+    int maxBlocks;   // batch capacity
+    int capN;        // per-block element capacity (maxBlockSize + slack)
+    // generic per-tile scratch (ZRLT / SBRT / scans)
+    u32* tileA;      // [maxBlocks * maxTiles * 4]
+    u32* tileB;
+    i64 tileWords;
+    // SBRT per-tile last-two-occurrence tables: [maxBlocks][tiles][256][2]
+    u32* occ;
+    i64 occWords;
+    // suffix sorting
+    u64 *keyA, *keyB;   // [maxBlocks * capN]
+    u32 *valA, *valB;
+    u32 *grpA, *grpB;
+    u32* isa;           // [maxBlocks * capN]
+    u32* hist;          // [maxBlocks * sortTiles * 256]
+    u32* digitBase;     // [maxBlocks * 256]
+    u32* totals;        // [maxBlocks * 8 * 256]
+    int* trivial;       // [8][maxBlocks]
+    int* which;         // [16][maxBlocks]
+    int* cnt;           // [maxBlocks] elements in play per block
+    int* cntNext;
+    int* h_cnt;         // pinned host mirror
+    u32* scanA;         // [maxBlocks * sortTiles * 4]
+    u32* scanB;
+    int* pidx;          // [maxBlocks * 8] primary indexes
+    int* bwtOk;         // [maxBlocks]
+};
+
+bool workspace_alloc(Workspace& ws, int maxBlocks, int capN);
+void workspace_free(Workspace& ws);
+void launch_copy_out(const BufTable& bt, const BlkState* st, int nBlocks, u8* out, i64 outStride, cudaStream_t s,
+                     u64* launches);

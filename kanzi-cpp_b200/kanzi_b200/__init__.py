@@ -1,0 +1,223 @@
+"""kanzi_b200 -- Python binding of libknzgpu.so (include/knz_gpu.h), the B200-native
+replacement for kanzi's per-block transform -> entropy path.
+
+This module is plumbing only: every byte of work happens in the hand-written
+sm_100a kernels behind the C ABI.  There is no CPU fallback: constructing a
+`Context` without the compiled library or without a CUDA device raises.
+
+Class and method names mirror the reference's Python binding and stream API
+(src/api/kanzi.py:18,86 Compressor/Decompressor; CompressedOutputStream::write/close).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libknzgpu.so")
+
+T_IDS = {"NONE": 0, "BWT": 1, "ZRLT": 6, "MTFT": 7, "RANK": 8}
+E_IDS = {"NONE": 0, "ANS0": 5}
+
+
+class KanziGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"knz error {code}: {msg}")
+        self.code = code
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _load(path):
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(no CPU fallback exists for this path)")
+    L = ctypes.CDLL(path)
+    L.knz_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+    L.knz_destroy.argtypes = [ctypes.c_void_p]
+    L.knz_last_error.restype = ctypes.c_char_p
+    L.knz_last_error.argtypes = [ctypes.c_void_p]
+    L.knz_transform_type.restype = ctypes.c_uint64
+    L.knz_transform_type.argtypes = [ctypes.c_char_p]
+    L.knz_entropy_type.argtypes = [ctypes.c_char_p]
+    L.knz_launch_count.restype = ctypes.c_uint64
+    L.knz_launch_count.argtypes = [ctypes.c_void_p]
+    L.knz_stream.restype = ctypes.c_void_p
+    L.knz_stream.argtypes = [ctypes.c_void_p]
+    L.knz_last_timings.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]
+    vp, i32, i64, u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint64
+    L.knz_compress.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p, i32, vp, i64, vp, i64, ctypes.POINTER(i64)]
+    L.knz_decompress.argtypes = [vp, vp, i64, vp, i64, ctypes.POINTER(i64)]
+    L.knz_encode_blocks.argtypes = [vp, u64, i32, i32, vp, i64, vp, i32, i32, vp, i64, vp, vp]
+    L.knz_decode_blocks.argtypes = [vp, u64, i32, i32, vp, i64, vp, i32, vp, i64, vp]
+    L.knz_encode_blocks_dev.argtypes = [vp, u64, i32, i32, vp, i64, vp, i32, i32, vp, i64, vp, vp]
+    L.knz_decode_blocks_dev.argtypes = [vp, u64, i32, i32, vp, i64, vp, i32, vp, i64, vp]
+    L.knz_assemble_stream_dev.argtypes = [vp, vp, i64, vp, i32, vp, i64, u64, ctypes.POINTER(u64)]
+    L.knz_stream_header.argtypes = [u64, i32, i32, i64, vp]
+    L.knz_transform_forward.argtypes = [vp, i32, vp, i32, vp, i32, ctypes.POINTER(i32), ctypes.POINTER(i32)]
+    L.knz_transform_inverse.argtypes = [vp, i32, vp, i32, vp, i32, ctypes.POINTER(i32), ctypes.POINTER(i32)]
+    L.knz_entropy_encode.argtypes = [vp, i32, vp, i32, vp, i64, ctypes.POINTER(i64)]
+    L.knz_entropy_decode.argtypes = [vp, i32, vp, i64, vp, i32]
+    return L
+
+
+class Context:
+    """One GPU context (device buffers, stream, kernels).  `lib_path` is only
+    overridden by the CPU tests that load the emulator build of the same sources."""
+
+    def __init__(self, device=0, max_block_size=4 << 20, max_batch_blocks=64, lib_path=None):
+        self.lib = _load(lib_path or LIB_PATH)
+        h = ctypes.c_void_p()
+        rc = self.lib.knz_create(device, max_block_size, max_batch_blocks, ctypes.byref(h))
+        if rc != 0:
+            raise KanziGpuError(rc, "knz_create failed (no usable CUDA device? there is no CPU fallback)")
+        self.h = h
+        self.max_block_size = max_block_size
+        self.max_batch_blocks = max_batch_blocks
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.knz_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise KanziGpuError(rc, self.lib.knz_last_error(self.h).decode())
+
+    @property
+    def launches(self):
+        return int(self.lib.knz_launch_count(self.h))
+
+    @property
+    def cuda_stream(self):
+        return int(self.lib.knz_stream(self.h) or 0)
+
+    def timings(self):
+        ms = (ctypes.c_float * 6)()
+        self.lib.knz_last_timings(self.h, ms)
+        return dict(zip(("bwt", "rank", "zrlt", "entropy", "assembly", "total"), [float(x) for x in ms]))
+
+    def transform_type(self, name):
+        return int(self.lib.knz_transform_type(name.encode()))
+
+    # ---- stream level (CompressedOutputStream write+close / CompressedInputStream read)
+    def compress(self, data, transform="BWT+RANK+ZRLT", entropy="ANS0", block_size=4 << 20, out=None):
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        cap = data.size + data.size // 4 + 16 * (data.size // block_size + 1) + 65536
+        if out is None:
+            out = np.empty(cap, dtype=np.uint8)
+        n = ctypes.c_int64(0)
+        self._check(self.lib.knz_compress(self.h, transform.encode(), entropy.encode(), block_size, _ptr(data),
+                                          data.size, _ptr(out), out.size, ctypes.byref(n)))
+        return out[: n.value]
+
+    def decompress(self, comp, cap, out=None):
+        comp = np.ascontiguousarray(comp, dtype=np.uint8)
+        if out is None:
+            out = np.empty(max(cap, 1), dtype=np.uint8)
+        n = ctypes.c_int64(0)
+        self._check(self.lib.knz_decompress(self.h, _ptr(comp), comp.size, _ptr(out), cap, ctypes.byref(n)))
+        return out[: n.value]
+
+    # ---- block level (EncodingTask::run / DecodingTask::run bodies)
+    def encode_blocks(self, blocks, transform, entropy, block_size, first_block_len=None):
+        """blocks: list of uint8 arrays.  Returns [(bytes, nbits, skipFlags)]."""
+        nb = len(blocks)
+        stride = (max(b.size for b in blocks) + 255) // 256 * 256
+        inp = np.zeros(nb * stride, dtype=np.uint8)
+        lens = np.zeros(nb, dtype=np.int32)
+        for i, b in enumerate(blocks):
+            inp[i * stride: i * stride + b.size] = b
+            lens[i] = b.size
+        ostride = (block_size + block_size // 4 + 4096 + 255) // 256 * 256
+        out = np.zeros(nb * ostride, dtype=np.uint8)
+        bits = np.zeros(nb, dtype=np.uint64)
+        flags = np.zeros(nb, dtype=np.uint8)
+        first = int(lens[0]) if first_block_len is None else first_block_len
+        self._check(self.lib.knz_encode_blocks(self.h, self.transform_type(transform), E_IDS[entropy], block_size,
+                                               _ptr(inp), stride, _ptr(lens), nb, first, _ptr(out), ostride,
+                                               _ptr(bits), _ptr(flags)))
+        res = []
+        for i in range(nb):
+            nbytes = (int(bits[i]) + 7) // 8
+            res.append((out[i * ostride: i * ostride + nbytes].copy(), int(bits[i]), int(flags[i])))
+        return res
+
+    def decode_blocks(self, enc, transform, entropy, block_size):
+        """enc: list of (bytes, nbits).  Returns list of uint8 arrays."""
+        nb = len(enc)
+        stride = (max(e[0].size for e in enc) + 64 + 255) // 256 * 256
+        inp = np.zeros(nb * stride, dtype=np.uint8)
+        bits = np.zeros(nb, dtype=np.uint64)
+        for i, (e, nbit) in enumerate(enc):
+            inp[i * stride: i * stride + e.size] = e
+            bits[i] = nbit
+        ostride = (block_size + 255) // 256 * 256
+        out = np.zeros(nb * ostride, dtype=np.uint8)
+        lens = np.zeros(nb, dtype=np.int32)
+        self._check(self.lib.knz_decode_blocks(self.h, self.transform_type(transform), E_IDS[entropy], block_size,
+                                               _ptr(inp), stride, _ptr(bits), nb, _ptr(out), ostride, _ptr(lens)))
+        return [out[i * ostride: i * ostride + int(lens[i])].copy() for i in range(nb)]
+
+    # ---- stage level (Transform<byte>::forward/inverse, EntropyEncoder::encode, EntropyDecoder::decode)
+    def transform_forward(self, name, data, cap=None):
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        cap = data.size + 64 if cap is None else cap
+        out = np.zeros(cap + 64, dtype=np.uint8)
+        ol, ap = ctypes.c_int(0), ctypes.c_int(0)
+        self._check(self.lib.knz_transform_forward(self.h, T_IDS[name], _ptr(data), data.size, _ptr(out), cap,
+                                                   ctypes.byref(ol), ctypes.byref(ap)))
+        return out[: ol.value].copy(), bool(ap.value)
+
+    def transform_inverse(self, name, data, cap):
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        out = np.zeros(cap + 64, dtype=np.uint8)
+        ol, ap = ctypes.c_int(0), ctypes.c_int(0)
+        self._check(self.lib.knz_transform_inverse(self.h, T_IDS[name], _ptr(data), data.size, _ptr(out), cap,
+                                                   ctypes.byref(ol), ctypes.byref(ap)))
+        return out[: ol.value].copy(), bool(ap.value)
+
+    def entropy_encode(self, name, data):
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        out = np.zeros(data.size + data.size // 4 + 8192, dtype=np.uint8)
+        bits = ctypes.c_int64(0)
+        self._check(self.lib.knz_entropy_encode(self.h, E_IDS[name], _ptr(data), data.size, _ptr(out), out.size,
+                                                ctypes.byref(bits)))
+        return out[: (bits.value + 7) // 8].copy(), bits.value
+
+    def entropy_decode(self, name, enc, nbits, n):
+        enc = np.ascontiguousarray(enc, dtype=np.uint8)
+        out = np.zeros(max(n, 1), dtype=np.uint8)
+        self._check(self.lib.knz_entropy_decode(self.h, E_IDS[name], _ptr(enc), nbits, _ptr(out), n))
+        return out[:n]
+
+
+class Compressor:
+    """Mirror of the reference binding's Compressor (src/api/kanzi.py:18): init with
+    the stream parameters, then compress() whole buffers."""
+
+    def __init__(self, transform="BWT+RANK+ZRLT", entropy="ANS0", block_size=4 << 20, device=0, max_batch_blocks=64,
+                 ctx=None):
+        self.transform, self.entropy, self.block_size = transform, entropy, block_size
+        self.ctx = ctx or Context(device, block_size, max_batch_blocks)
+
+    def compress(self, data):
+        return self.ctx.compress(data, self.transform, self.entropy, self.block_size)
+
+
+class Decompressor:
+    """Mirror of src/api/kanzi.py:86."""
+
+    def __init__(self, max_block_size=4 << 20, device=0, max_batch_blocks=64, ctx=None):
+        self.ctx = ctx or Context(device, max_block_size, max_batch_blocks)
+
+    def decompress(self, comp, original_size):
+        return self.ctx.decompress(comp, original_size)

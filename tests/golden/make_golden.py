@@ -1,0 +1,80 @@
+"""Generates tests/golden/golden.json from the UNMODIFIED reference (oracle/_ref,
+built from /root/reference by oracle/Makefile).  Run in the build container:
+
+    python tests/golden/make_golden.py
+
+Each record names a deterministic input (generator, seed, size -- see
+kanzi-cpp_b200/synth.py and tests/cases.py), the pipeline, the block size, and
+the reference's compressed stream: full bytes (hex) when small, else length +
+SHA-256.  The reference ships no golden vectors of its own, so
+these fixtures are what pins the oracle and the GPU path on boxes without
+/root/reference.
+"""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "kanzi-cpp_b200"), os.path.join(ROOT, "tests")]
+
+import synth  # noqa: E402
+from cases import small_cases  # noqa: E402
+from oracle.oracle import Ref  # noqa: E402
+
+STREAMS = [
+    # (generator, seed, size, transform, entropy, block size)
+    ("text", 1, 70000, "NONE", "ANS0", 65536),
+    ("text", 1, 70000, "BWT+RANK+ZRLT", "ANS0", 65536),
+    ("compressible", 2, 300000, "BWT+RANK+ZRLT", "ANS0", 65536),
+    ("compressible", 2, 300000, "BWT+MTFT+ZRLT", "ANS0", 1 << 18),
+    ("incompressible", 9, 100000, "BWT+RANK+ZRLT", "ANS0", 65536),
+    ("compressible", 3, 65536 * 2 + 9, "ZRLT", "ANS0", 65536),
+    ("compressible", 4, 200000, "BWT", "NONE", 65536),
+    ("compressible", 2, 9 << 20, "BWT+RANK+ZRLT", "ANS0", 4 << 20),
+    ("text", 1, 16 << 20, "NONE", "ANS0", 4 << 20),
+    ("compressible", 2, 64 << 20, "BWT+RANK+ZRLT", "ANS0", 4 << 20),
+]
+
+
+def main():
+    ref = Ref.load()
+    assert ref is not None, "oracle/_ref missing: run `make -C oracle ref` where /root/reference exists"
+    out = {"streams": [], "stages": []}
+    for gen, seed, size, tname, ename, bs in STREAMS:
+        data = synth.GENERATORS[gen](size, seed)
+        comp = ref.stream_compress(data, tname, ename, bs, jobs=1)  # jobs=1: the buffer model the GPU path reproduces
+        rec = {"gen": gen, "seed": seed, "size": size, "transform": tname, "entropy": ename, "block": bs,
+               "input_sha256": synth.sha256(data), "len": int(comp.size),
+               "sha256": hashlib.sha256(comp.tobytes()).hexdigest()}
+        if comp.size <= 50000:
+            rec["hex"] = comp.tobytes().hex()
+        out["streams"].append(rec)
+        print(gen, size, tname, ename, bs, "->", comp.size)
+    # stage-level vectors on the named small cases (reference BWT bytes + primary indexes, ANS0 bit strings)
+    cases = small_cases()
+    for name in ("mississippi", "pi", "sixmixed", "rnd256_257", "rnd4_1000", "zeros_5000", "fe_ff_heavy",
+                 "text_16387", "two_sym_9000"):
+        data = cases[name]
+        rec = {"case": name, "input_hex": data.tobytes().hex()}
+        if data.size >= 2:
+            bwt, pidx = ref.bwt_forward(data)
+            rec["bwt_hex"] = bwt.tobytes().hex()
+            rec["primary"] = pidx[: (8 if data.size >= 256 else 1)]
+        enc, bits = ref.entropy_encode("ANS0", data)
+        rec["ans0_hex"] = enc.tobytes().hex()
+        rec["ans0_bits"] = int(bits)
+        for t in ("ZRLT", "RANK", "MTFT"):
+            o, fl, ok = ref.sequence_forward(t, data, data.size + 64, data.size + 64)
+            rec[t.lower() + "_hex"] = o.tobytes().hex() if fl != 0xFF else None
+        out["stages"].append(rec)
+    with open(os.path.join(HERE, "golden.json"), "w") as f:
+        json.dump(out, f)
+    print("wrote golden.json", os.path.getsize(os.path.join(HERE, "golden.json")), "bytes")
+
+
+if __name__ == "__main__":
+    main()

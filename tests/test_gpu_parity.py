@@ -1,0 +1,175 @@
+"""GPU parity suite (run on the B200 box): the hand-written CUDA path, called through
+the C ABI, against (1) golden fixtures generated from the unmodified reference,
+(2) the plain-C oracle on seeded inputs, (3) the prebuilt reference library
+(oracle/_ref, when it travelled with the snapshot), (4) size-independent properties
+at full size (round trips, stream-of-blocks consistency).  Bit-exact everywhere."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import synth
+from cases import small_cases, rng_bytes
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))
+CASES = small_cases()
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import torch
+    assert torch.cuda.is_available()
+    from kanzi_b200 import Context
+    ctx = Context(0, 4 << 20, 64)
+    yield ctx
+    ctx.close()
+
+
+def _first_diff(a, b):
+    n = min(a.size, b.size)
+    d = np.nonzero(a[:n] != b[:n])[0]
+    return (int(d[0]) if d.size else n, a.size, b.size)
+
+
+@pytest.mark.parametrize("idx", range(len(GOLD["streams"])))
+def test_gpu_stream_matches_golden(gpu, idx):
+    rec = GOLD["streams"][idx]
+    data = synth.GENERATORS[rec["gen"]](rec["size"], rec["seed"])
+    assert synth.sha256(data) == rec["input_sha256"]
+    comp = gpu.compress(data, rec["transform"], rec["entropy"], rec["block"])
+    if "hex" in rec:
+        want = np.frombuffer(bytes.fromhex(rec["hex"]), dtype=np.uint8)
+        assert np.array_equal(comp, want), _first_diff(comp, want)
+    assert comp.size == rec["len"]
+    assert hashlib.sha256(comp.tobytes()).hexdigest() == rec["sha256"]
+    back = gpu.decompress(comp, data.size)
+    assert back.size == data.size and np.array_equal(back, data)
+
+
+def test_gpu_entropy_vs_oracle(gpu, oracle):
+    for name, data in CASES.items():
+        a, abits = gpu.entropy_encode("ANS0", data)
+        b, bbits = oracle.entropy_encode("ANS0", data)
+        assert abits == bbits, (name, abits, bbits)
+        assert np.array_equal(a, b), (name, _first_diff(a, b))
+        dec = gpu.entropy_decode("ANS0", b, bbits, data.size)
+        assert np.array_equal(dec, data), name
+
+
+@pytest.mark.parametrize("tname", ["ZRLT", "RANK", "MTFT", "BWT"])
+def test_gpu_stage_vs_oracle(gpu, oracle, tname):
+    for name, data in CASES.items():
+        n = data.size
+        for cap in (n + 64, n):
+            if tname == "BWT" and cap < n + 33:
+                continue
+            a, applied = gpu.transform_forward(tname, data, cap)
+            b, flags = oracle.sequence_forward(tname, data, n, cap)
+            assert applied == (flags != 0xFF), (name, tname, cap)
+            if applied:
+                assert a.size == b.size and np.array_equal(a, b), (name, tname, cap, _first_diff(a, b))
+                back, ok = gpu.transform_inverse(tname, b, n + 64)
+                assert ok and np.array_equal(back, data), (name, tname, cap)
+
+
+def test_gpu_stage_golden_vectors(gpu):
+    for rec in GOLD["stages"]:
+        data = CASES[rec["case"]]
+        if "bwt_hex" in rec:
+            out, applied = gpu.transform_forward("BWT", data, data.size + 64)
+            assert applied
+            chunks = 8 if data.size >= 256 else 1
+            lg = int(np.ceil(np.log2(data.size))) if data.size > 1 else 0
+            pisz = (lg + 7) // 8
+            hdr = 1 + chunks * pisz
+            assert out[hdr:].tobytes().hex() == rec["bwt_hex"], rec["case"]
+            for k, p in enumerate(rec["primary"]):
+                v = int.from_bytes(out[1 + k * pisz: 1 + (k + 1) * pisz].tobytes(), "big")
+                assert v == (p - 1) % (1 << (8 * pisz)), (rec["case"], k)
+        enc, bits = gpu.entropy_encode("ANS0", data)
+        assert bits == rec["ans0_bits"] and enc.tobytes().hex() == rec["ans0_hex"], rec["case"]
+        for t in ("ZRLT", "RANK", "MTFT"):
+            want = rec[t.lower() + "_hex"]
+            o, applied = gpu.transform_forward(t, data, data.size + 64)
+            if want is None:
+                assert not applied
+            else:
+                assert applied and o.tobytes().hex() == want, (rec["case"], t)
+
+
+@pytest.mark.parametrize("tname,ename", [("NONE", "ANS0"), ("BWT+RANK+ZRLT", "ANS0"), ("NONE", "NONE"),
+                                         ("ZRLT", "ANS0"), ("BWT+MTFT+ZRLT", "ANS0"), ("BWT", "NONE"),
+                                         ("RANK+ZRLT", "ANS0")])
+def test_gpu_stream_vs_oracle(gpu, oracle, tname, ename):
+    inputs = {
+        "comp_600k": synth.synth_compressible(600000, 21),
+        "text_70k": synth.synth_text(70000, 22),
+        "incomp_300k": synth.synth_incompressible(300000, 23),
+        "tiny_10": rng_bytes(10, 24),
+        "tiny_16": rng_bytes(16, 25),
+        "zeros_500k": np.zeros(500000, dtype=np.uint8),
+        "const_300k": np.full(300000, 0x61, dtype=np.uint8),
+        "tail_small": np.concatenate([synth.synth_text(1 << 18, 26), rng_bytes(7, 27)]),
+        "mixed": np.concatenate([synth.synth_text(1 << 18, 26), synth.synth_incompressible((1 << 18) + 13, 27)]),
+    }
+    for name, data in inputs.items():
+        for bs in (65536, 1 << 18):
+            a = gpu.compress(data, tname, ename, bs)
+            b = oracle.stream_compress(data, tname, ename, bs)
+            assert a.size == b.size and np.array_equal(a, b), (name, tname, ename, bs, _first_diff(a, b))
+            dec = gpu.decompress(b, data.size)
+            assert dec.size == data.size and np.array_equal(dec, data), (name, tname, ename, bs)
+
+
+def test_gpu_blocks_vs_oracle(gpu, oracle):
+    bs = 1 << 18
+    data = synth.synth_compressible(5 * bs + 1000, 31)
+    blocks = [data[i: i + bs] for i in range(0, data.size, bs)]
+    enc = gpu.encode_blocks(blocks, "BWT+RANK+ZRLT", "ANS0", bs)
+    data_cap = max(bs + bs // 8, 262144)
+    for i, blk in enumerate(blocks):
+        ref_bytes, ref_bits = oracle.encode_block(blk, "BWT+RANK+ZRLT", "ANS0", data_cap, blocks[0].size + 33)
+        assert enc[i][1] == ref_bits, (i, enc[i][1], ref_bits)
+        assert np.array_equal(enc[i][0], ref_bytes), (i, _first_diff(enc[i][0], ref_bytes))
+    dec = gpu.decode_blocks([(e[0], e[1]) for e in enc], "BWT+RANK+ZRLT", "ANS0", bs)
+    for i, blk in enumerate(blocks):
+        assert np.array_equal(dec[i], blk), i
+
+
+def test_gpu_vs_reference_library_fullsize(gpu):
+    """Headline pipeline at the named block size against the unmodified reference
+    (multi-threaded CPU) when its prebuilt library travelled with the snapshot."""
+    from oracle.oracle import Ref
+    ref = Ref.load()
+    if ref is None:
+        pytest.skip("oracle/_ref/libkanzi_ref.so not present")
+    data = synth.synth_compressible(96 << 20, 2)
+    want = ref.stream_compress(data, "BWT+RANK+ZRLT", "ANS0", 4 << 20, jobs=min(32, os.cpu_count() or 8))
+    got = gpu.compress(data, "BWT+RANK+ZRLT", "ANS0", 4 << 20)
+    assert got.size == want.size and np.array_equal(got, want), _first_diff(got, want)
+    back = gpu.decompress(want, data.size)
+    assert np.array_equal(back, data)
+    back2, rc = ref.stream_decompress(got, data.size, jobs=min(32, os.cpu_count() or 8))
+    assert rc == 0 and np.array_equal(back2, data)
+
+
+def test_gpu_roundtrip_fullsize_properties(gpu):
+    """BASELINE.json config 2 shape (4 MiB blocks, synth_compressible seed 2) at 1 GiB:
+    encode -> decode identity; the stream is the bit-concatenation of its blocks
+    (first 64 MiB prefix equals the stream of the 64 MiB fixture up to the header)."""
+    n = 1 << 30
+    data = synth.synth_compressible(n, 2)
+    comp = gpu.compress(data, "BWT+RANK+ZRLT", "ANS0", 4 << 20)
+    back = gpu.decompress(comp, n)
+    assert back.size == n and np.array_equal(back, data)
+    rec = [r for r in GOLD["streams"] if r["size"] == (64 << 20)][0]
+    small = gpu.compress(data[: 64 << 20], "BWT+RANK+ZRLT", "ANS0", 4 << 20)
+    assert hashlib.sha256(small.tobytes()).hexdigest() == rec["sha256"]
+    # blocks are independent: the 1 GiB stream's body starts with the 64 MiB stream's body
+    hdr_small, hdr_big = 24, 24
+    body = small.size - hdr_small - 2  # drop the end marker + padding bytes
+    assert np.array_equal(comp[hdr_big: hdr_big + body], small[hdr_small: hdr_small + body])

@@ -1,0 +1,89 @@
+"""CPU tests of the CUDA kernels' logic: the same .cu sources compiled on top of the
+execution-model emulator (tests/sim) are driven through the C ABI and compared with
+the plain-C oracle.  (The real parity gate is tests/test_gpu_parity.py on the B200.)"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import synth
+from cases import small_cases, rng_bytes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SIM = os.path.join(ROOT, "tests", "sim", "libknzsim.so")
+
+
+@pytest.fixture(scope="module")
+def sim():
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "sim"), "-j8"], stdout=subprocess.DEVNULL)
+    from kanzi_b200 import Context
+    ctx = Context(0, 1 << 18, 4, lib_path=SIM)
+    yield ctx
+    ctx.close()
+
+
+CASES = small_cases()
+
+
+def test_sim_entropy_ans0(sim, oracle):
+    for name, data in CASES.items():
+        a, abits = sim.entropy_encode("ANS0", data)
+        b, bbits = oracle.entropy_encode("ANS0", data)
+        assert abits == bbits, (name, abits, bbits)
+        assert np.array_equal(a, b), name
+        dec = sim.entropy_decode("ANS0", b, bbits, data.size)
+        assert np.array_equal(dec, data), name
+
+
+@pytest.mark.parametrize("tname", ["ZRLT", "RANK", "MTFT", "BWT"])
+def test_sim_stage_forward_inverse(sim, oracle, tname):
+    for name, data in CASES.items():
+        n = data.size
+        for cap in (n + 64, n):
+            if tname == "BWT" and cap < n + 33:
+                continue
+            a, applied = sim.transform_forward(tname, data, cap)
+            b, flags = oracle.sequence_forward(tname, data, n, cap)
+            assert applied == (flags != 0xFF), (name, tname, cap, applied, flags)
+            if applied:
+                assert a.size == b.size and np.array_equal(a, b), (name, tname, cap)
+                back, ok = sim.transform_inverse(tname, b, n + 64)
+                assert ok and np.array_equal(back, data), (name, tname, cap)
+
+
+@pytest.mark.parametrize("tname,ename", [("NONE", "ANS0"), ("BWT+RANK+ZRLT", "ANS0"), ("NONE", "NONE"),
+                                         ("ZRLT", "ANS0"), ("BWT+MTFT+ZRLT", "ANS0"), ("BWT", "NONE")])
+def test_sim_stream(sim, oracle, tname, ename):
+    inputs = {
+        "comp_150k": synth.synth_compressible(150000, 21),
+        "text_70k": synth.synth_text(70000, 22),
+        "incomp_80k": synth.synth_incompressible(80000, 23),
+        "tiny_10": rng_bytes(10, 24),
+        "tiny_16": rng_bytes(16, 25),
+        "zeros_100k": np.zeros(100000, dtype=np.uint8),
+        "tail_small": np.concatenate([synth.synth_text(65536, 26), rng_bytes(7, 27)]),
+        "mixed": np.concatenate([synth.synth_text(65536, 26), synth.synth_incompressible(65536 + 13, 27)]),
+    }
+    for name, data in inputs.items():
+        for bs in (65536, 1 << 18):
+            a = sim.compress(data, tname, ename, bs)
+            b = oracle.stream_compress(data, tname, ename, bs)
+            assert a.size == b.size and np.array_equal(a, b), (name, tname, ename, bs, a.size, b.size)
+            dec = sim.decompress(b, data.size)
+            assert dec.size == data.size and np.array_equal(dec, data), (name, tname, ename, bs)
+
+
+def test_sim_blocks(sim, oracle):
+    bs = 65536
+    data = synth.synth_compressible(3 * bs + 1000, 31)
+    blocks = [data[i: i + bs] for i in range(0, data.size, bs)]
+    enc = sim.encode_blocks(blocks, "BWT+RANK+ZRLT", "ANS0", bs)
+    data_cap = max(bs + bs // 8, 262144)
+    for i, blk in enumerate(blocks):
+        ref_bytes, ref_bits = oracle.encode_block(blk, "BWT+RANK+ZRLT", "ANS0", data_cap, blocks[0].size + 33)
+        assert enc[i][1] == ref_bits, (i, enc[i][1], ref_bits)
+        assert np.array_equal(enc[i][0], ref_bytes), i
+    dec = sim.decode_blocks([(e[0], e[1]) for e in enc], "BWT+RANK+ZRLT", "ANS0", bs)
+    for i, blk in enumerate(blocks):
+        assert np.array_equal(dec[i], blk), i

@@ -137,9 +137,9 @@ int knz_entropy_decode(knz_ctx* ctx, int type, const uint8_t* in, int64_t inBits
 uint64_t knz_launch_count(const knz_ctx* ctx);
 void* knz_stream(const knz_ctx* ctx);
 /* Device time (ms) of the last call, split by stage group, measured with CUDA
- * events on the library stream: [0]=BWT [1]=RANK/MTFT [2]=ZRLT [3]=entropy
- * [4]=bit assembly [5]=total.                                                     */
-void knz_last_timings(const knz_ctx* ctx, float ms[6]);
+ * events on the library stream: [0]=BWT [1]=RANK/MTFT [2]=ZRLT [3]=entropy stage
+ * [4]=bit assembly [5]=total [6]=rANS encode kernel alone [7]=rANS decode kernel alone. */
+void knz_last_timings(const knz_ctx* ctx, float ms[8]);
 
 #ifdef __cplusplus
 }

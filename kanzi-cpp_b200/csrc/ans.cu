@@ -403,8 +403,12 @@ void launch_entropy_encode(const EncodeLaunch& L, cudaStream_t s, u64* launches)
         const int groups = (L.maxChunks + 7) / 8;
         const i64 warps = (i64)nB * groups;
         const int ctas = (int)((warps + ENC_WARPS - 1) / ENC_WARPS);
+        if (L.evK0)
+            cudaEventRecord(L.evK0, s);
         KLAUNCH(ans0_encode_kernel, ctas, ENC_WARPS * 32, s, L.bt, L.st, nB, L.maxChunks, L.slots, L.hdrBits,
-                                                          L.payBytes, L.payOff);
+                L.payBytes, L.payOff);
+        if (L.evK1)
+            cudaEventRecord(L.evK1, s);
     }
     KLAUNCH(ans_scan_kernel, nB, 256, s, L.st, nB, L.maxChunks, L.eType, L.nTransforms, L.hdrBits, L.payBytes,
                                        L.chunkOff, L.blockBits, L.out, L.outStride, L.errFlag);
@@ -716,6 +720,10 @@ void launch_entropy_decode(const DecodeLaunch& L, cudaStream_t s, u64* launches)
 {
     KLAUNCH(ans0_dec_scan_kernel, (L.nBlocks + 31) / 32, 32, s, L);
     const int groups = (L.maxChunks + 7) / 8;
+    if (L.evK0)
+        cudaEventRecord(L.evK0, s);
     KLAUNCH(ans0_decode_kernel, L.nBlocks * groups, 32, s, L);
+    if (L.evK1)
+        cudaEventRecord(L.evK1, s);
     *launches += 2;
 }

@@ -24,7 +24,7 @@
 struct knz_ctx {
     int device, maxBlockSize, maxBatch;
     cudaStream_t stream;
-    cudaEvent_t ev[8];
+    cudaEvent_t ev[10];
     i64 bstride;     // stride of the ping-pong stage buffers
     u8 *bufA, *bufB; // [maxBatch * bstride]
     u8* dStageIn;    // host API: staged input blocks [maxBatch * bstride]
@@ -50,7 +50,7 @@ struct knz_ctx {
     u8* dPlain;
     i64 dPlainCap;
     u64 launches;
-    float ms[6];
+    float ms[8];
     char err[256];
 };
 
@@ -155,7 +155,7 @@ extern "C" int knz_create(int device, int maxBlockSize, int maxBatchBlocks, knz_
     bool ok = true;
 #define A(call) ok = ok && ((call) == cudaSuccess)
     A(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < 10; i++)
         A(cudaEventCreate(&ctx->ev[i]));
     A(dalloc(&ctx->bufA, nb * ctx->bstride + 256));
     A(dalloc(&ctx->bufB, nb * ctx->bstride + 256));
@@ -216,7 +216,7 @@ extern "C" void knz_destroy(knz_ctx* ctx)
     for (size_t i = 0; i < sizeof(hst) / sizeof(hst[0]); i++)
         if (hst[i])
             cudaFreeHost(hst[i]);
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < 10; i++)
         if (ctx->ev[i])
             cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream)
@@ -227,9 +227,9 @@ extern "C" void knz_destroy(knz_ctx* ctx)
 extern "C" const char* knz_last_error(const knz_ctx* ctx) { return ctx ? ctx->err : "null context"; }
 extern "C" uint64_t knz_launch_count(const knz_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" void* knz_stream(const knz_ctx* ctx) { return ctx ? (void*)ctx->stream : NULL; }
-extern "C" void knz_last_timings(const knz_ctx* ctx, float ms[6])
+extern "C" void knz_last_timings(const knz_ctx* ctx, float ms[8])
 {
-    for (int i = 0; i < 6; i++)
+    for (int i = 0; i < 8; i++)
         ms[i] = ctx ? ctx->ms[i] : 0.f;
 }
 
@@ -300,7 +300,7 @@ static int encode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const
     bt.stride[0] = bt.stride[1] = ctx->bstride;
     bt.stride[2] = inStride;
 
-    for (int i = 0; i < 6; i++)
+    for (int i = 0; i < 8; i++)
         ctx->ms[i] = 0.f;
     CK(cudaEventRecord(ctx->ev[0], s));
     for (int i = 0; i < nt; i++) {
@@ -356,6 +356,8 @@ static int encode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const
     E.out = d_out;
     E.outStride = outStride;
     E.errFlag = ctx->errFlag;
+    E.evK0 = ctx->ev[8];
+    E.evK1 = ctx->ev[9];
     launch_entropy_encode(E, s, &ctx->launches);
     CK(cudaEventRecord(ctx->ev[4], s));
     CK(cudaMemcpyAsync(ctx->h_err, ctx->errFlag, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
@@ -367,6 +369,10 @@ static int encode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const
     ctx->ms[3] = ms;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]);
     ctx->ms[5] = ms;
+    if (eType == E_ANS0) {
+        cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]);
+        ctx->ms[6] = ms;
+    }
     if (h_flags)
         for (int b = 0; b < nB; b++)
             h_flags[b] = (u8)ctx->h_st[b].flags;
@@ -590,7 +596,7 @@ extern "C" int knz_compress(knz_ctx* ctx, const char* transform, const char* ent
     CK(cudaMemcpyAsync(ctx->streamPos, ctx->h_pos, sizeof(u64), cudaMemcpyHostToDevice, s));
     CK(cudaStreamSynchronize(s));
     const int firstLen = (int)((n < blockSize) ? n : blockSize);
-    float acc[6] = { 0, 0, 0, 0, 0, 0 };
+    float acc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
     for (i64 b0 = 0; b0 < nBlocks; b0 += ctx->maxBatch) {
         const int nb = (int)((nBlocks - b0 < ctx->maxBatch) ? nBlocks - b0 : ctx->maxBatch);
         const i64 off = b0 * blockSize;
@@ -607,7 +613,7 @@ extern "C" int knz_compress(knz_ctx* ctx, const char* transform, const char* ent
         if (ng > 0) {
             rc = encode_batch(ctx, tType, eType, blockSize, ctx->dPlain, blockSize, lens, ng, firstLen, ctx->dOut,
                               ctx->outStride, ctx->blockBits, NULL);
-            for (int i = 0; i < 6; i++)
+            for (int i = 0; i < 8; i++)
                 acc[i] += ctx->ms[i];
         }
         if (rc == KNZ_OK && ng < nb) {
@@ -641,7 +647,7 @@ extern "C" int knz_compress(knz_ctx* ctx, const char* transform, const char* ent
     CK(cudaStreamSynchronize(s));
     memcpy(out, hdr, (size_t)hdrBytes);
     *outLen = total;
-    for (int i = 0; i < 6; i++)
+    for (int i = 0; i < 8; i++)
         ctx->ms[i] = acc[i];
     return KNZ_OK;
 }
@@ -707,7 +713,7 @@ static int decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const
     CK(cudaMemcpyAsync(ctx->capEven, ctx->h_capEven, sizeof(int) * nB, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->capOdd, ctx->h_capOdd, sizeof(int) * nB, cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync(ctx->errFlag, 0, sizeof(int) * 4, s));
-    for (int i = 0; i < 6; i++)
+    for (int i = 0; i < 8; i++)
         ctx->ms[i] = 0.f;
     CK(cudaEventRecord(ctx->ev[0], s));
     DecodeLaunch D;
@@ -723,6 +729,8 @@ static int decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const
     D.dst = ctx->bufA;
     D.dstStride = ctx->bstride;
     D.errFlag = ctx->errFlag;
+    D.evK0 = ctx->ev[8];
+    D.evK1 = ctx->ev[9];
     launch_entropy_decode(D, s, &ctx->launches);
     CK(cudaEventRecord(ctx->ev[1], s));
 
@@ -779,6 +787,8 @@ static int decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const
     ctx->ms[3] = ms;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]);
     ctx->ms[5] = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]);
+    ctx->ms[7] = ms;
     for (int b = 0; b < nB; b++)
         h_outLens[b] = ctx->h_st[b].len;
     return map_kerr(ctx, ctx->h_err[0]);
@@ -966,7 +976,7 @@ extern "C" int knz_decompress(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_
     int32_t* ol = (int32_t*)malloc(sizeof(int32_t) * (size_t)mb);
     i64 produced = 0;
     bool done = false;
-    float acc[6] = { 0, 0, 0, 0, 0, 0 };
+    float acc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
     while (!done && rc == KNZ_OK) {
         int ng = 0;
         // gather up to maxBatch device blocks; copy blocks are resolved on the host in order
@@ -1020,7 +1030,7 @@ extern "C" int knz_decompress(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_
                           ol);
         if (rc != KNZ_OK)
             break;
-        for (int i = 0; i < 6; i++)
+        for (int i = 0; i < 8; i++)
             acc[i] += ctx->ms[i];
         // decoded blocks are contiguous when every block but the last is full
         for (int g = 0; g < ng; g++) {
@@ -1042,7 +1052,7 @@ extern "C" int knz_decompress(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_
     if (rc != KNZ_OK)
         return rc;
     *outLen = produced;
-    for (int i = 0; i < 6; i++)
+    for (int i = 0; i < 8; i++)
         ctx->ms[i] = acc[i];
     return KNZ_OK;
 }
@@ -1177,6 +1187,7 @@ extern "C" int knz_entropy_encode(knz_ctx* ctx, int type, const uint8_t* in, int
     E.out = ctx->dOut;
     E.outStride = ctx->outStride;
     E.errFlag = ctx->errFlag;
+    E.evK0 = E.evK1 = NULL;
     launch_entropy_encode(E, s, &ctx->launches);
     CK(cudaMemcpyAsync(ctx->h_err, ctx->errFlag, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(ctx->h_bits, ctx->blockBits, sizeof(u64), cudaMemcpyDeviceToHost, s));
@@ -1230,6 +1241,7 @@ extern "C" int knz_entropy_decode(knz_ctx* ctx, int type, const uint8_t* in, int
     D.dst = ctx->bufA;
     D.dstStride = ctx->bstride;
     D.errFlag = ctx->errFlag;
+    D.evK0 = D.evK1 = NULL;
     launch_entropy_decode(D, s, &ctx->launches);
     CK(cudaMemcpyAsync(ctx->h_err, ctx->errFlag, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(out, ctx->bufA, (size_t)n, cudaMemcpyDeviceToHost, s));

@@ -35,6 +35,7 @@ struct EncodeLaunch {
     u8* out;
     i64 outStride;
     int* errFlag;
+    cudaEvent_t evK0, evK1; // optional: bracket the rANS kernel alone (NULL = off)
 };
 void launch_entropy_encode(const EncodeLaunch& L, cudaStream_t s, u64* launches);
 // startBit / endBit are device scalars (may alias): batches chain without a host round trip.
@@ -55,6 +56,7 @@ struct DecodeLaunch {
     u8* dst;
     i64 dstStride;
     int* errFlag;
+    cudaEvent_t evK0, evK1; // optional: bracket the rANS decode kernel alone
 };
 void launch_entropy_decode(const DecodeLaunch& L, cudaStream_t s, u64* launches);
 

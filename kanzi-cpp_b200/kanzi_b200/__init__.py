@@ -101,9 +101,10 @@ class Context:
         return int(self.lib.knz_stream(self.h) or 0)
 
     def timings(self):
-        ms = (ctypes.c_float * 6)()
+        ms = (ctypes.c_float * 8)()
         self.lib.knz_last_timings(self.h, ms)
-        return dict(zip(("bwt", "rank", "zrlt", "entropy", "assembly", "total"), [float(x) for x in ms]))
+        return dict(zip(("bwt", "rank", "zrlt", "entropy", "assembly", "total", "ans_enc_kernel", "ans_dec_kernel"),
+                        [float(x) for x in ms]))
 
     def transform_type(self, name):
         return int(self.lib.knz_transform_type(name.encode()))

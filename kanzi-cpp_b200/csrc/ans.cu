@@ -136,25 +136,43 @@ ans0_encode_kernel(BufTable bt, const BlkState* __restrict__ st, int nBlocks, in
     u32 cnt = 0;
     u16* wend = reinterpret_cast<u16*>(slot + ANS_WEND);
     const int bsh = 8 * (3 - k);
-    u32 nxt = (steps > 0) ? __ldg(&words[(end4 >> 2) - 1]) : 0u;
-    for (int s = 0; s < maxSteps; s++) {
-        const u32 cur = nxt;
-        if (s + 1 < steps)
-            nxt = __ldg(&words[(end4 >> 2) - 2 - s]);
-        bool did = false;
-        u32 word = 0;
-        if (s < steps) {
-            const u32 cb = (cur >> bsh) & 0xFF;
-            state = enc_step(state, sym[j][cb], ANS0_LR, &did, &word);
+    const int wtop = (end4 >> 2) - 1; // step s consumes word wtop - s (the quad's 4 bytes)
+    // Software pipeline: the words of step group g+2 are requested while group g is
+    // encoded, so the L2 latency of the (quad-broadcast) loads stays off the serial
+    // state-update chain.
+    u32 wa[4], wb[4], wc[4];
+#pragma unroll
+    for (int x = 0; x < 4; x++) {
+        wa[x] = (x < steps) ? __ldg(&words[wtop - x]) : 0u;
+        wb[x] = (4 + x < steps) ? __ldg(&words[wtop - 4 - x]) : 0u;
+    }
+    for (int s0 = 0; s0 < maxSteps; s0 += 4) {
+#pragma unroll
+        for (int x = 0; x < 4; x++)
+            wc[x] = (s0 + 8 + x < steps) ? __ldg(&words[wtop - s0 - 8 - x]) : 0u;
+#pragma unroll
+        for (int x = 0; x < 4; x++) {
+            const int s = s0 + x;
+            bool did = false;
+            u32 word = 0;
+            if (s < steps) {
+                const u32 cb = (wa[x] >> bsh) & 0xFF;
+                state = enc_step(state, sym[j][cb], ANS0_LR, &did, &word);
+            }
+            const u32 bal = __ballot_sync(FULL_MASK, did);
+            const u32 qb = (bal >> (lane & ~3)) & 0xF;
+            if (did) {
+                const u32 idx = cnt + __popc(qb & ((1u << k) - 1u));
+                // memory order [hi][lo] (ANSRangeEncoder.hpp:122-126)
+                *(wend - 1 - idx) = (u16)(((word & 0xFF) << 8) | (word >> 8));
+            }
+            cnt += __popc(qb);
         }
-        const u32 bal = __ballot_sync(FULL_MASK, did);
-        const u32 qb = (bal >> (lane & ~3)) & 0xF;
-        if (did) {
-            const u32 idx = cnt + __popc(qb & ((1u << k) - 1u));
-            // memory order [hi][lo] (ANSRangeEncoder.hpp:122-126)
-            *(wend - 1 - idx) = (u16)(((word & 0xFF) << 8) | (word >> 8));
+#pragma unroll
+        for (int x = 0; x < 4; x++) {
+            wa[x] = wb[x];
+            wb[x] = wc[x];
         }
-        cnt += __popc(qb);
     }
 
     // ---- epilogue: varint size, 4 states, tail bytes

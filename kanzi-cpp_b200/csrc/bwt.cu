@@ -620,6 +620,8 @@ void launch_bwt_forward(const StageLaunch& L, Workspace& ws, cudaStream_t s, u64
 }
 
 // ------------------------------------------------------------------ inverse
+#define BWT_END 0xFFFFFFFFu // psi of the end-of-string row: the text ends here
+#define SPL_LOG 8           // one splitter every 256 sorted positions
 // Header parse + decision (BWTBlockCodec.cpp:89-168, bsVersion 6 branch).
 __global__ void bwt_inv_decide_kernel(StageLaunch L, int* __restrict__ cnt, int* __restrict__ which0,
                                       int* __restrict__ pidx, int* __restrict__ bwtOk)
@@ -695,47 +697,183 @@ bwt_inv_init_kernel(BufTable bt, const BlkState* __restrict__ st, const int* __r
     const int p0 = pidx[b * 8];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
         keyOut[(i64)b * capN + i] = (u64)src[hdr + i];
-        valOut[(i64)b * capN + i] = (i == 0) ? 0u : ((i < p0) ? (u32)(i - 1) : (u32)i);
+        valOut[(i64)b * capN + i] = (i == 0) ? BWT_END : ((i < p0) ? (u32)(i - 1) : (u32)i);
     }
 }
 
-// One thread per (block, chunk): follow psi from the chunk's primary index.
-__global__ void bwt_inv_chase_kernel(BufTable bt, const BlkState* __restrict__ stIn, const int* __restrict__ bwtOk,
-                                     const int* __restrict__ pidx, const int* __restrict__ whichAfter, int capN,
-                                     const u64* key0, const u64* key1, const u32* val0, const u32* val1, int nBlocks,
-                                     int* __restrict__ errFlag)
+// psi walk, parallelised by list ranking with splitters (Helman-JaJa style):
+//   nodes   = every 256th sorted position + the (<= 8) primary-index positions
+//   walk 1  = every node follows psi to the next node: (next node, segment length)
+//   rank    = one thread per primary index walks the ~n/256 nodes of its chunk and
+//             hands every node its text offset
+//   walk 2  = every node re-walks its segment and writes the bytes in place.
+// packed[t] = (psi[t] << 8) | F[t]  (one 8-byte gather per step).
+struct InvCtx {
+    BufTable bt;
+    const BlkState* stIn;
+    const int* bwtOk;
+    const int* pidx;
+    const int* whichAfter;
+    const u64* key[2];
+    const u32* val[2];
+    u64* packed[2];
+    u32* node; // [nBlocks][nodeStride][4]: next, len, base, pad
+    int capN, nodeStride, nBlocks;
+    int* errFlag;
+};
+
+struct InvBlk {
+    int m, hdr, chunks, step, S;
+    u32 anchor[8];
+};
+
+__device__ __forceinline__ InvBlk inv_blk(const InvCtx& C, int b, const u8* src, int len)
 {
-    const int id = blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = id >> 3, c = id & 7;
-    if (b >= nBlocks || !bwtOk[b])
-        return;
-    const BlkState bs = stIn[b];
-    const u8* __restrict__ src = blk_src(bt, bs, b);
-    u8* __restrict__ dst = blk_dst(bt, bs, b);
+    InvBlk B;
     const int mode = src[0];
-    const int chunks = 1 << ((mode >> 2) & 7);
-    const int hdr = 1 + chunks * ((mode & 3) + 1);
-    const int m = bs.len - hdr;
-    if (c >= chunks)
-        return;
-    const int stp = m / chunks;
-    const int step = (chunks * stp == m) ? stp : stp + 1;
-    const i64 start = (i64)c * step;
-    if (start >= m)
-        return;
-    const int end = (start + step < (i64)m) ? (int)(start + step) : m;
-    const int w = whichAfter[b];
-    const u64* __restrict__ F = (w ? key1 : key0) + (i64)b * capN;
-    const u32* __restrict__ nxt = (w ? val1 : val0) + (i64)b * capN;
-    u32 t = (u32)(pidx[b * 8 + c] - 1);
-    for (int p = (int)start; p < end; p++) {
-        if (t >= (u32)m) {
-            atomicExch(errFlag, KERR_BAD_STREAM);
-            return;
-        }
-        dst[p] = (u8)F[t];
-        t = nxt[t];
+    B.chunks = 1 << ((mode >> 2) & 7);
+    B.hdr = 1 + B.chunks * ((mode & 3) + 1);
+    B.m = len - B.hdr;
+    const int stp = B.m / B.chunks;
+    B.step = (B.chunks * stp == B.m) ? stp : stp + 1;
+    B.S = (B.m + (1 << SPL_LOG) - 1) >> SPL_LOG;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const bool used = k < B.chunks && (i64)k * B.step < B.m;
+        B.anchor[k] = used ? (u32)(C.pidx[b * 8 + k] - 1) : 0xFFFFFFFEu;
     }
+    return B;
+}
+
+// node id of sorted position t, or -1.  Anchors take precedence over regular splitters.
+__device__ __forceinline__ int inv_node_of(const InvBlk& B, u32 t)
+{
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+        if (t == B.anchor[k])
+            return B.S + k;
+    if ((t & ((1u << SPL_LOG) - 1)) == 0)
+        return (int)(t >> SPL_LOG);
+    return -1;
+}
+
+__device__ __forceinline__ u32 inv_node_pos(const InvBlk& B, int id, bool* valid)
+{
+    if (id >= B.S) {
+        const u32 a = B.anchor[id - B.S];
+        *valid = a != 0xFFFFFFFEu;
+        return a;
+    }
+    const u32 t = (u32)id << SPL_LOG;
+    *valid = inv_node_of(B, t) == id; // a regular splitter that coincides with an anchor is represented by the anchor
+    return t;
+}
+
+__global__ void __launch_bounds__(256)
+bwt_inv_pack_kernel(InvCtx C)
+{
+    const int b = blockIdx.y;
+    if (!C.bwtOk[b])
+        return;
+    const BlkState bs = C.stIn[b];
+    const u8* __restrict__ src = blk_src(C.bt, bs, b);
+    const int mode = src[0];
+    const int m = bs.len - (1 + (1 << ((mode >> 2) & 7)) * ((mode & 3) + 1));
+    const int w = C.whichAfter[b];
+    const u64* __restrict__ F = C.key[w] + (i64)b * C.capN;
+    const u32* __restrict__ nx = C.val[w] + (i64)b * C.capN;
+    u64* __restrict__ P = C.packed[w ^ 1] + (i64)b * C.capN;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < m; t += gridDim.x * blockDim.x)
+        P[t] = ((u64)nx[t] << 8) | (F[t] & 0xFF);
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(128)
+bwt_inv_walk_kernel(InvCtx C)
+{
+    const int b = blockIdx.y;
+    if (!C.bwtOk[b])
+        return;
+    const BlkState bs = C.stIn[b];
+    const u8* __restrict__ src = blk_src(C.bt, bs, b);
+    const InvBlk B = inv_blk(C, b, src, bs.len);
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= B.S + 8)
+        return;
+    bool valid;
+    u32 t = inv_node_pos(B, id, &valid);
+    u32* nd = C.node + ((i64)b * C.nodeStride + id) * 4;
+    if (!valid || t >= (u32)B.m) {
+        if (PASS == 1) {
+            nd[0] = 0xFFFFFFFFu;
+            nd[1] = 0;
+            nd[2] = 0xFFFFFFFFu;
+        }
+        return;
+    }
+    const u64* __restrict__ P = C.packed[C.whichAfter[b] ^ 1] + (i64)b * C.capN;
+    if (PASS == 1) {
+        u32 len = 0;
+        int nxt = -1;
+        for (;;) {
+            const u64 e = P[t];
+            len++;
+            t = (u32)(e >> 8);
+            if (t == BWT_END)
+                break;
+            if (t >= (u32)B.m || len > (u32)B.m) { // not a permutation: malformed input
+                atomicExch(C.errFlag, KERR_BAD_STREAM);
+                break;
+            }
+            nxt = inv_node_of(B, t);
+            if (nxt >= 0)
+                break;
+        }
+        nd[0] = (u32)nxt;
+        nd[1] = len;
+        nd[2] = 0xFFFFFFFFu;
+    } else {
+        const u32 base = nd[2];
+        const u32 len = nd[1];
+        if (base == 0xFFFFFFFFu || (u64)base + len > (u64)B.m)
+            return;
+        u8* __restrict__ dst = blk_dst(C.bt, bs, b) + base;
+        for (u32 k = 0; k < len; k++) {
+            const u64 e = P[t];
+            dst[k] = (u8)e;
+            t = (u32)(e >> 8);
+        }
+    }
+}
+
+// one thread per (block, chunk): hand out text offsets along the chunk's node chain
+__global__ void bwt_inv_rank_kernel(InvCtx C)
+{
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = gid >> 3, k = gid & 7;
+    if (b >= C.nBlocks || !C.bwtOk[b])
+        return;
+    const BlkState bs = C.stIn[b];
+    const u8* __restrict__ src = blk_src(C.bt, bs, b);
+    const InvBlk B = inv_blk(C, b, src, bs.len);
+    if (B.anchor[k] == 0xFFFFFFFEu)
+        return;
+    u32* nodes = C.node + (i64)b * C.nodeStride * 4;
+    u32 off = (u32)((i64)k * B.step);
+    const u32 endOff = (u32)min((i64)(k + 1) * B.step, (i64)B.m);
+    int id = B.S + k;
+    int guard = B.S + 16;
+    while (guard-- > 0) {
+        u32* nd = nodes + (i64)id * 4;
+        nd[2] = off;
+        off += nd[1];
+        const u32 nx = nd[0];
+        if (nx == 0xFFFFFFFFu || (int)nx >= B.S) // text end or the next chunk's anchor
+            break;
+        id = (int)nx;
+    }
+    if (off != endOff)
+        atomicExch(C.errFlag, KERR_BAD_STREAM);
 }
 
 void launch_bwt_inverse(const StageLaunch& L, Workspace& ws, cudaStream_t s, u64* launches)
@@ -761,9 +899,30 @@ void launch_bwt_inverse(const StageLaunch& L, Workspace& ws, cudaStream_t s, u64
     A.maxTiles = maxTiles;
     A.maxBlocks = ws.maxBlocks;
     radix_sort(A, nB, L.maxLen, 0x01u, s, launches); // stable counting sort by symbol = LF/psi construction
-    KLAUNCH(bwt_inv_chase_kernel, (nB * 8 + 63) / 64, 64, s, L.bt, L.stIn, ws.bwtOk, ws.pidx, ws.which + 8 * ws.maxBlocks,
-            ws.capN, ws.keyA, ws.keyB, ws.valA, ws.valB, nB, L.errFlag);
-    *launches += 1;
+    InvCtx C;
+    C.bt = L.bt;
+    C.stIn = L.stIn;
+    C.bwtOk = ws.bwtOk;
+    C.pidx = ws.pidx;
+    C.whichAfter = ws.which + 8 * ws.maxBlocks;
+    C.key[0] = ws.keyA;
+    C.key[1] = ws.keyB;
+    C.val[0] = ws.valA;
+    C.val[1] = ws.valB;
+    C.packed[0] = ws.keyA;
+    C.packed[1] = ws.keyB;
+    C.node = ws.hist; // [maxBlocks][sTiles*256] u32 >= 4 * (capN/256 + 8) per block
+    C.capN = ws.capN;
+    C.nodeStride = maxTiles * 64;
+    C.nBlocks = nB;
+    C.errFlag = L.errFlag;
+    const int packBlocks = min((L.maxLen + 255) / 256, 1024);
+    KLAUNCH(bwt_inv_pack_kernel, dim3(packBlocks, nB), 256, s, C);
+    const int nodes = ((L.maxLen + 255) >> SPL_LOG) + 8;
+    KLAUNCH(bwt_inv_walk_kernel<1>, dim3((nodes + 127) / 128, nB), 128, s, C);
+    KLAUNCH(bwt_inv_rank_kernel, (nB * 8 + 63) / 64, 64, s, C);
+    KLAUNCH(bwt_inv_walk_kernel<2>, dim3((nodes + 127) / 128, nB), 128, s, C);
+    *launches += 4;
 }
 
 // ------------------------------------------------------------------ misc stages

@@ -189,66 +189,175 @@ sbrt_rank_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkState*
     }
 }
 
-// Inverse: serial replay per block (SBRT.cpp:99-145), one thread per block.
+// Inverse: serial replay per block (SBRT.cpp:99-145).  The update needs the decoded
+// symbol, so a block is one dependency chain; the kernel minimises the latency of a
+// step instead: one warp per block, every lane runs the same replay redundantly (no
+// divergence, no shuffles on the critical path), the 8 highest-ranked entries live in
+// registers (post-BWT ranks are overwhelmingly < 8), the rest in shared memory, and
+// input/output move through registers 128 bytes at a time with coalesced accesses.
+// Entry = key q, plus pb = (last access time << 8) | symbol.
+template <class PB>
 __global__ void __launch_bounds__(32)
 sbrt_inverse_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkState* __restrict__ stOut, int mode)
 {
-    __shared__ int s_q[256], s_p[256];
-    __shared__ u8 s_r2s[256];
+    __shared__ int s_q[256];
+    __shared__ PB s_b[256];
     const int b = blockIdx.x;
     const BlkState bs = stIn[b];
     if (stOut[b].swaps == bs.swaps)
         return;
     const int n = bs.len;
+    const int lane = threadIdx.x;
     const u8* __restrict__ src = blk_src(bt, bs, b);
     u8* __restrict__ dst = blk_dst(bt, bs, b);
-    for (int i = threadIdx.x; i < 256; i += 32) {
+    for (int i = lane; i < 256; i += 32) {
         s_q[i] = 0;
-        s_p[i] = 0;
-        s_r2s[i] = (u8)i;
+        s_b[i] = (PB)i;
     }
     __syncwarp();
-    if (threadIdx.x != 0)
-        return;
     u32 m1, m2;
     int sh;
     sbrt_masks(mode, m1, m2, sh);
-    int i = 0;
-    // 4 bytes at a time when aligned
-    while (i < n) {
-        u32 wv;
-        int cnt;
-        if (i + 4 <= n) {
-            wv = *reinterpret_cast<const u32*>(src + i); // buffers are 256-byte aligned, i % 4 == 0
-            cnt = 4;
-        } else {
-            wv = 0;
-            cnt = n - i;
-            for (int k = 0; k < cnt; k++)
-                wv |= (u32)src[i + k] << (8 * k);
+    int tq[8];
+    PB tb[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        tq[k] = 0;
+        tb[k] = (PB)k;
+    }
+    const u32* __restrict__ src4 = reinterpret_cast<const u32*>(src); // buffers are 16-byte aligned
+    const int groups = (n + 127) >> 7;
+    u32 nextw = 0;
+    if (4 * lane < n)
+        nextw = (4 * lane + 4 <= n) ? src4[lane] : 0u;
+    if (4 * lane < n && 4 * lane + 4 > n)
+        for (int k = 0; k < n - 4 * lane; k++)
+            nextw |= (u32)src[4 * lane + k] << (8 * k);
+    for (int g = 0; g < groups; g++) {
+        const u32 inw = nextw;
+        {
+            // prefetch the next 128 bytes while this group is replayed
+            const int p = (g + 1) * 128 + 4 * lane;
+            nextw = 0;
+            if (p + 4 <= n)
+                nextw = src4[p >> 2];
+            else if (p < n)
+                for (int k = 0; k < n - p; k++)
+                    nextw |= (u32)src[p + k] << (8 * k);
         }
-        u32 ow = 0;
-        for (int k = 0; k < cnt; k++, i++) {
-            int r = (int)((wv >> (8 * k)) & 0xFF);
-            const int c = s_r2s[r];
-            ow |= (u32)c << (8 * k);
-            const int qc = (int)((((u32)i & m1) + ((u32)s_p[c] & m2)) >> sh);
-            s_p[c] = i;
-            s_q[c] = qc;
-            while (r > 0) {
-                const int above = s_r2s[r - 1];
-                if (s_q[above] > qc)
-                    break;
-                s_r2s[r] = (u8)above;
-                r--;
+        u32 outw = 0;
+        const int base = g * 128;
+        const int cnt = min(128, n - base);
+        for (int j = 0; j < cnt; j += 4) {
+            const u32 w4 = __shfl_sync(FULL_MASK, inw, j >> 2);
+            u32 o4 = 0;
+            const int lim = min(4, cnt - j);
+            for (int x = 0; x < lim; x++) {
+                const int r = (int)((w4 >> (8 * x)) & 0xFF);
+                const u32 i = (u32)(base + j + x);
+                u32 c;
+                if (r == 0) {
+                    c = (u32)(tb[0] & 0xFF);
+                    const u32 pc = (u32)(tb[0] >> 8);
+                    tq[0] = (int)(((i & m1) + (pc & m2)) >> sh);
+                    tb[0] = ((PB)i << 8) | (PB)c;
+                } else if (r < 8) {
+                    PB e = tb[1];
+#pragma unroll
+                    for (int k = 2; k < 8; k++)
+                        if (r == k)
+                            e = tb[k];
+                    c = (u32)(e & 0xFF);
+                    const u32 pc = (u32)(e >> 8);
+                    const int qc = (int)(((i & m1) + (pc & m2)) >> sh);
+                    int rp = 0;
+#pragma unroll
+                    for (int k = 0; k < 7; k++)
+                        rp += (k < r && tq[k] > qc) ? 1 : 0;
+#pragma unroll
+                    for (int k = 7; k >= 1; k--) {
+                        const bool mv = (k > rp) && (k <= r);
+                        tq[k] = mv ? tq[k - 1] : tq[k];
+                        tb[k] = mv ? tb[k - 1] : tb[k];
+                    }
+                    const PB ne = ((PB)i << 8) | (PB)c;
+#pragma unroll
+                    for (int k = 0; k < 8; k++)
+                        if (k == rp) {
+                            tq[k] = qc;
+                            tb[k] = ne;
+                        }
+                } else {
+                    const PB e = s_b[r];
+                    c = (u32)(e & 0xFF);
+                    const u32 pc = (u32)(e >> 8);
+                    const int qc = (int)(((i & m1) + (pc & m2)) >> sh);
+                    const PB ne = ((PB)i << 8) | (PB)c;
+                    // new rank inside the shared-memory part of the list (read-only search)
+                    int jj = r;
+                    while (jj > 8 && s_q[jj - 1] <= qc)
+                        jj--;
+                    __syncwarp();
+                    // cooperative shift of ranks [jj, r-1] down by one (reads before writes)
+                    for (int top = r; top > jj; top -= 32) {
+                        const int idx = top - lane;
+                        const bool act = idx > jj;
+                        int vq = 0;
+                        PB vb = 0;
+                        if (act) {
+                            vq = s_q[idx - 1];
+                            vb = s_b[idx - 1];
+                        }
+                        __syncwarp();
+                        if (act) {
+                            s_q[idx] = vq;
+                            s_b[idx] = vb;
+                        }
+                        __syncwarp();
+                    }
+                    if (jj > 8 || tq[7] > qc) {
+                        if (lane == 0) {
+                            s_q[jj] = qc;
+                            s_b[jj] = ne;
+                        }
+                    } else {
+                        if (lane == 0) {
+                            s_q[8] = tq[7];
+                            s_b[8] = tb[7];
+                        }
+                        int rp = 0;
+#pragma unroll
+                        for (int k = 0; k < 7; k++)
+                            rp += (tq[k] > qc) ? 1 : 0;
+#pragma unroll
+                        for (int k = 7; k >= 1; k--) {
+                            const bool mv = (k > rp);
+                            tq[k] = mv ? tq[k - 1] : tq[k];
+                            tb[k] = mv ? tb[k - 1] : tb[k];
+                        }
+#pragma unroll
+                        for (int k = 0; k < 8; k++)
+                            if (k == rp) {
+                                tq[k] = qc;
+                                tb[k] = ne;
+                            }
+                    }
+                    __syncwarp();
+                }
+                o4 |= c << (8 * x);
             }
-            s_r2s[r] = (u8)c;
+            if (lane == (j >> 2))
+                outw = o4;
         }
-        if (cnt == 4) {
-            *reinterpret_cast<u32*>(dst + i - 4) = ow;
-        } else {
-            for (int k = 0; k < cnt; k++)
-                dst[i - cnt + k] = (u8)(ow >> (8 * k));
+        {
+            const int p = base + 4 * lane;
+            if (p + 4 <= n) {
+                *reinterpret_cast<u32*>(dst + p) = outw;
+            } else {
+                for (int k = 0; k < 4; k++)
+                    if (p + k < n)
+                        dst[p + k] = (u8)(outw >> (8 * k));
+            }
         }
     }
 }
@@ -270,6 +379,9 @@ void launch_sbrt_inverse(const StageLaunch& L, int mode, Workspace& ws, cudaStre
 {
     (void)ws;
     KLAUNCH(sbrt_decide_kernel, (L.nBlocks + 31) / 32, 32, s, L, 1);
-    KLAUNCH(sbrt_inverse_kernel, L.nBlocks, 32, s, L.bt, L.stIn, L.stOut, mode);
+    if (L.maxLen < (1 << 24))
+        KLAUNCH(sbrt_inverse_kernel<u32>, L.nBlocks, 32, s, L.bt, L.stIn, L.stOut, mode);
+    else
+        KLAUNCH(sbrt_inverse_kernel<u64>, L.nBlocks, 32, s, L.bt, L.stIn, L.stOut, mode);
     *launches += 2;
 }

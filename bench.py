@@ -126,7 +126,7 @@ def run_reference(args, rank, world):
         return
     import synth
     cores = os.cpu_count() or 1
-    jobs = max(1, min(64, cores))
+    jobs = max(1, min(63, cores))  # 64 trips a reference bug (jobsPerTask[63] = 0 once >= 63 blocks are queued)
     # bounded sample of the same workload: sized for ~10-20 s of CPU work per step
     sample = min(args.size, max(64 << 20, min(512 << 20, (cores * 12) << 20)))
     sample = (sample // BLOCK) * BLOCK
@@ -175,7 +175,7 @@ def run_ours(args, rank, world, local_rank):
     my = list(range(rank, nblocks, world))  # round-robin sharding (north_star)
     nb = len(my)
     host_in = torch.from_numpy(data).view(nblocks, BLOCK)[my].contiguous().pin_memory()
-    batch = min(64, nb)
+    batch = min(args.batch, nb)
     ctx = Context(local_rank, BLOCK, batch)
     L = ctx.lib
     ostride = (BLOCK + BLOCK // 4 + 4096 + 255) // 256 * 256
@@ -372,7 +372,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- CPU baseline beside it: the unmodified reference, all host threads, bounded sample
     cores = os.cpu_count() or 1
-    jobs = max(1, min(64, cores))
+    jobs = max(1, min(63, cores))
     cpu = None
     try:
         sample = min(size, max(64 << 20, min(256 << 20, (cores * 8) << 20)))
@@ -419,6 +419,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=1 << 30)
+    ap.add_argument("--batch", type=int, default=256, help="blocks per device batch")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -387,6 +387,7 @@ extern "C" int knz_encode_blocks_dev(knz_ctx* ctx, uint64_t tType, int eType, in
     if (!ctx || !d_in || !lens || !d_blockOut || !d_outBits || nBlocks < 0)
         return KNZ_ERR_INVALID_PARAM;
     cudaSetDevice(ctx->device);
+    float acc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
     for (int off = 0; off < nBlocks; off += ctx->maxBatch) {
         const int nb = (nBlocks - off < ctx->maxBatch) ? nBlocks - off : ctx->maxBatch;
         const int rc = encode_batch(ctx, tType, eType, blockSize, d_in + (i64)off * inStride, inStride, lens + off, nb,
@@ -394,7 +395,11 @@ extern "C" int knz_encode_blocks_dev(knz_ctx* ctx, uint64_t tType, int eType, in
                                     h_skipFlags ? h_skipFlags + off : NULL);
         if (rc != KNZ_OK)
             return rc;
+        for (int i = 0; i < 8; i++)
+            acc[i] += ctx->ms[i];
     }
+    for (int i = 0; i < 8; i++)
+        ctx->ms[i] = acc[i];
     return KNZ_OK;
 }
 
@@ -829,6 +834,7 @@ extern "C" int knz_decode_blocks_dev(knz_ctx* ctx, uint64_t tType, int eType, in
     cudaSetDevice(ctx->device);
     cudaStream_t s = ctx->stream;
     const int blkLen = blockSize + ((blockSize >> 4) > 512 ? (blockSize >> 4) : 512);
+    float acc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
     for (int off = 0; off < nBlocks; off += ctx->maxBatch) {
         const int nb = (nBlocks - off < ctx->maxBatch) ? nBlocks - off : ctx->maxBatch;
         u8* heads = (u8*)malloc((size_t)nb * 8);
@@ -858,7 +864,11 @@ extern "C" int knz_decode_blocks_dev(knz_ctx* ctx, uint64_t tType, int eType, in
         free(fl);
         if (rc != KNZ_OK)
             return rc;
+        for (int i = 0; i < 8; i++)
+            acc[i] += ctx->ms[i];
     }
+    for (int i = 0; i < 8; i++)
+        ctx->ms[i] = acc[i];
     return KNZ_OK;
 }
 

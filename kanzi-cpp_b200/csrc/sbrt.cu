@@ -190,18 +190,18 @@ sbrt_rank_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkState*
 }
 
 // Inverse: serial replay per block (SBRT.cpp:99-145).  The update needs the decoded
-// symbol, so a block is one dependency chain; the kernel minimises the latency of a
-// step instead: one warp per block, every lane runs the same replay redundantly (no
-// divergence, no shuffles on the critical path), the 8 highest-ranked entries live in
-// registers (post-BWT ranks are overwhelmingly < 8), the rest in shared memory, and
-// input/output move through registers 128 bytes at a time with coalesced accesses.
-// Entry = key q, plus pb = (last access time << 8) | symbol.
+// symbol, so a block is ONE dependency chain; the kernel minimises the latency of a
+// step: one warp per block with the 256-entry list distributed over the lanes in
+// registers (lane L owns ranks 8L..8L+7; entry = key q and pb = (last access << 8) | symbol).
+//   symbol at rank r      : uniform slot select + one shuffle from lane r>>3
+//   new rank of the symbol: #entries with q > qc  (8 ballots; the list is sorted by q)
+//   move-up               : every lane shifts its own slots, one shuffle-up for the seam
+// No shared memory, no divergence; zero words (runs of rank 0) take a closed form.
+// Input/output travel through registers 128 bytes at a time (coalesced, prefetched).
 template <class PB>
 __global__ void __launch_bounds__(32)
 sbrt_inverse_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkState* __restrict__ stOut, int mode)
 {
-    __shared__ int s_q[256];
-    __shared__ PB s_b[256];
     const int b = blockIdx.x;
     const BlkState bs = stIn[b];
     if (stOut[b].swaps == bs.swaps)
@@ -210,39 +210,36 @@ sbrt_inverse_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkSta
     const int lane = threadIdx.x;
     const u8* __restrict__ src = blk_src(bt, bs, b);
     u8* __restrict__ dst = blk_dst(bt, bs, b);
-    for (int i = lane; i < 256; i += 32) {
-        s_q[i] = 0;
-        s_b[i] = (PB)i;
-    }
-    __syncwarp();
     u32 m1, m2;
     int sh;
     sbrt_masks(mode, m1, m2, sh);
-    int tq[8];
-    PB tb[8];
+    int q[8];
+    PB pb[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        tq[k] = 0;
-        tb[k] = (PB)k;
+        q[k] = 0;
+        pb[k] = (PB)(8 * lane + k);
     }
     const u32* __restrict__ src4 = reinterpret_cast<const u32*>(src); // buffers are 16-byte aligned
     const int groups = (n + 127) >> 7;
     u32 nextw = 0;
-    if (4 * lane < n)
-        nextw = (4 * lane + 4 <= n) ? src4[lane] : 0u;
-    if (4 * lane < n && 4 * lane + 4 > n)
-        for (int k = 0; k < n - 4 * lane; k++)
-            nextw |= (u32)src[4 * lane + k] << (8 * k);
+    {
+        const int p = 4 * lane;
+        if (p + 4 <= n)
+            nextw = src4[lane];
+        else
+            for (int k = 0; p + k < n; k++)
+                nextw |= (u32)src[p + k] << (8 * k);
+    }
     for (int g = 0; g < groups; g++) {
         const u32 inw = nextw;
         {
-            // prefetch the next 128 bytes while this group is replayed
-            const int p = (g + 1) * 128 + 4 * lane;
+            const int p = (g + 1) * 128 + 4 * lane; // prefetch the next 128 bytes
             nextw = 0;
             if (p + 4 <= n)
                 nextw = src4[p >> 2];
-            else if (p < n)
-                for (int k = 0; k < n - p; k++)
+            else
+                for (int k = 0; p + k < n; k++)
                     nextw |= (u32)src[p + k] << (8 * k);
         }
         u32 outw = 0;
@@ -250,101 +247,67 @@ sbrt_inverse_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkSta
         const int cnt = min(128, n - base);
         for (int j = 0; j < cnt; j += 4) {
             const u32 w4 = __shfl_sync(FULL_MASK, inw, j >> 2);
-            u32 o4 = 0;
             const int lim = min(4, cnt - j);
-            for (int x = 0; x < lim; x++) {
-                const int r = (int)((w4 >> (8 * x)) & 0xFF);
-                const u32 i = (u32)(base + j + x);
-                u32 c;
-                if (r == 0) {
-                    c = (u32)(tb[0] & 0xFF);
-                    const u32 pc = (u32)(tb[0] >> 8);
-                    tq[0] = (int)(((i & m1) + (pc & m2)) >> sh);
-                    tb[0] = ((PB)i << 8) | (PB)c;
-                } else if (r < 8) {
-                    PB e = tb[1];
+            u32 o4 = 0;
+            if (w4 == 0 && lim == 4) {
+                // four accesses to the head of the list: only its key changes
+                const PB e = __shfl_sync(FULL_MASK, pb[0], 0);
+                const u32 c = (u32)(e & 0xFF);
+                const u32 i3 = (u32)(base + j + 3);
+                if (lane == 0) {
+                    q[0] = (int)(((i3 & m1) + ((i3 - 1) & m2)) >> sh);
+                    pb[0] = ((PB)i3 << 8) | (PB)c;
+                }
+                o4 = c * 0x01010101u;
+            } else {
+                for (int x = 0; x < lim; x++) {
+                    const int r = (int)((w4 >> (8 * x)) & 0xFF);
+                    const u32 i = (u32)(base + j + x);
+                    const int slot = r & 7;
+                    PB sel = pb[0];
 #pragma unroll
-                    for (int k = 2; k < 8; k++)
-                        if (r == k)
-                            e = tb[k];
-                    c = (u32)(e & 0xFF);
+                    for (int k = 1; k < 8; k++)
+                        if (slot == k)
+                            sel = pb[k];
+                    const PB e = __shfl_sync(FULL_MASK, sel, r >> 3);
+                    const u32 c = (u32)(e & 0xFF);
                     const u32 pc = (u32)(e >> 8);
                     const int qc = (int)(((i & m1) + (pc & m2)) >> sh);
+                    const PB ne = ((PB)i << 8) | (PB)c;
+                    o4 |= c << (8 * x);
+                    if (r == 0) {
+                        if (lane == 0) {
+                            q[0] = qc;
+                            pb[0] = ne;
+                        }
+                        continue;
+                    }
                     int rp = 0;
 #pragma unroll
-                    for (int k = 0; k < 7; k++)
-                        rp += (k < r && tq[k] > qc) ? 1 : 0;
+                    for (int k = 0; k < 8; k++)
+                        rp += __popc(__ballot_sync(FULL_MASK, q[k] > qc));
+                    // ranks (rp, r] take the entry of the rank above; rank rp takes the new entry
+                    const int pq = __shfl_up_sync(FULL_MASK, q[7], 1);
+                    const PB ppb = __shfl_up_sync(FULL_MASK, pb[7], 1);
+                    const int g0 = 8 * lane;
 #pragma unroll
                     for (int k = 7; k >= 1; k--) {
-                        const bool mv = (k > rp) && (k <= r);
-                        tq[k] = mv ? tq[k - 1] : tq[k];
-                        tb[k] = mv ? tb[k - 1] : tb[k];
+                        const bool mv = (g0 + k > rp) && (g0 + k <= r);
+                        q[k] = mv ? q[k - 1] : q[k];
+                        pb[k] = mv ? pb[k - 1] : pb[k];
                     }
-                    const PB ne = ((PB)i << 8) | (PB)c;
+                    {
+                        const bool mv = (g0 > rp) && (g0 <= r);
+                        q[0] = mv ? pq : q[0];
+                        pb[0] = mv ? ppb : pb[0];
+                    }
 #pragma unroll
                     for (int k = 0; k < 8; k++)
-                        if (k == rp) {
-                            tq[k] = qc;
-                            tb[k] = ne;
+                        if (g0 + k == rp) {
+                            q[k] = qc;
+                            pb[k] = ne;
                         }
-                } else {
-                    const PB e = s_b[r];
-                    c = (u32)(e & 0xFF);
-                    const u32 pc = (u32)(e >> 8);
-                    const int qc = (int)(((i & m1) + (pc & m2)) >> sh);
-                    const PB ne = ((PB)i << 8) | (PB)c;
-                    // new rank inside the shared-memory part of the list (read-only search)
-                    int jj = r;
-                    while (jj > 8 && s_q[jj - 1] <= qc)
-                        jj--;
-                    __syncwarp();
-                    // cooperative shift of ranks [jj, r-1] down by one (reads before writes)
-                    for (int top = r; top > jj; top -= 32) {
-                        const int idx = top - lane;
-                        const bool act = idx > jj;
-                        int vq = 0;
-                        PB vb = 0;
-                        if (act) {
-                            vq = s_q[idx - 1];
-                            vb = s_b[idx - 1];
-                        }
-                        __syncwarp();
-                        if (act) {
-                            s_q[idx] = vq;
-                            s_b[idx] = vb;
-                        }
-                        __syncwarp();
-                    }
-                    if (jj > 8 || tq[7] > qc) {
-                        if (lane == 0) {
-                            s_q[jj] = qc;
-                            s_b[jj] = ne;
-                        }
-                    } else {
-                        if (lane == 0) {
-                            s_q[8] = tq[7];
-                            s_b[8] = tb[7];
-                        }
-                        int rp = 0;
-#pragma unroll
-                        for (int k = 0; k < 7; k++)
-                            rp += (tq[k] > qc) ? 1 : 0;
-#pragma unroll
-                        for (int k = 7; k >= 1; k--) {
-                            const bool mv = (k > rp);
-                            tq[k] = mv ? tq[k - 1] : tq[k];
-                            tb[k] = mv ? tb[k - 1] : tb[k];
-                        }
-#pragma unroll
-                        for (int k = 0; k < 8; k++)
-                            if (k == rp) {
-                                tq[k] = qc;
-                                tb[k] = ne;
-                            }
-                    }
-                    __syncwarp();
                 }
-                o4 |= c << (8 * x);
             }
             if (lane == (j >> 2))
                 outw = o4;

@@ -22,6 +22,7 @@
 #include <string>
 #include <vector>
 #include <streambuf>
+#include <cstdio>
 
 #include "types.hpp"
 #include "Context.hpp"
@@ -86,7 +87,8 @@ int kref_stream_compress(const uint8_t* in, int64_t n, const char* transform, co
         *outLen = int64_t(ob.count());
         return 0;
     }
-    catch (const std::exception&) {
+    catch (const std::exception& e) {
+        fprintf(stderr, "[ref_shim] %s\n", e.what());
         return -1;
     }
 }
@@ -113,7 +115,8 @@ int kref_stream_decompress(const uint8_t* in, int64_t n, int jobs, uint8_t* out,
         *outLen = off;
         return 0;
     }
-    catch (const std::exception&) {
+    catch (const std::exception& e) {
+        fprintf(stderr, "[ref_shim] %s\n", e.what());
         return -1;
     }
 }
@@ -144,7 +147,8 @@ int kref_transform_forward(const char* name, const uint8_t* in, int n, int srcCa
         delete seq;
         return ok ? 1 : 0;
     }
-    catch (const std::exception&) {
+    catch (const std::exception& e) {
+        fprintf(stderr, "[ref_shim] %s\n", e.what());
         return -1;
     }
 }
@@ -168,7 +172,8 @@ int kref_transform_inverse(const char* name, int skipFlags, const uint8_t* in, i
         delete seq;
         return ok ? 1 : 0;
     }
-    catch (const std::exception&) {
+    catch (const std::exception& e) {
+        fprintf(stderr, "[ref_shim] %s\n", e.what());
         return -1;
     }
 }
@@ -189,7 +194,8 @@ int kref_bwt_forward(const uint8_t* in, int n, uint8_t* out, int* primaryIndexes
 
         return ok ? 1 : 0;
     }
-    catch (const std::exception&) {
+    catch (const std::exception& e) {
+        fprintf(stderr, "[ref_shim] %s\n", e.what());
         return -1;
     }
 }
@@ -218,7 +224,8 @@ int kref_entropy_encode(const char* name, const uint8_t* in, int n, uint8_t* out
 
         return (res == n) ? 1 : 0;
     }
-    catch (const std::exception&) {
+    catch (const std::exception& e) {
+        fprintf(stderr, "[ref_shim] %s\n", e.what());
         return -1;
     }
 }
@@ -239,7 +246,8 @@ int kref_entropy_decode(const char* name, const uint8_t* in, int64_t nbytes, uin
         *bitsRead = int64_t(ibs.read());
         return (res == n) ? 1 : 0;
     }
-    catch (const std::exception&) {
+    catch (const std::exception& e) {
+        fprintf(stderr, "[ref_shim] %s\n", e.what());
         return -1;
     }
 }

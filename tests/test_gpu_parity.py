@@ -119,7 +119,7 @@ def test_gpu_stream_vs_oracle(gpu, oracle, tname, ename):
     for name, data in inputs.items():
         for bs in (65536, 1 << 18):
             a = gpu.compress(data, tname, ename, bs)
-            if tname == "RANK+ZRLT" and name in ("incomp_300k", "mixed"):
+            if tname == "RANK+ZRLT" and name in ("incomp_300k", "mixed", "tiny_16", "tail_small"):
                 # Reference corner (DESIGN.md "known reference quirk"): an expanding ZRLT that
                 # lands in the sequence's *input* buffer passes its own capacity check but fails
                 # the final copy-back (TransformSequence.hpp:146-152); the reference then emits
@@ -156,12 +156,12 @@ def test_gpu_vs_reference_library_fullsize(gpu):
     if ref is None:
         pytest.skip("oracle/_ref/libkanzi_ref.so not present")
     data = synth.synth_compressible(96 << 20, 2)
-    want = ref.stream_compress(data, "BWT+RANK+ZRLT", "ANS0", 4 << 20, jobs=min(32, os.cpu_count() or 8))
+    want = ref.stream_compress(data, "BWT+RANK+ZRLT", "ANS0", 4 << 20, jobs=min(48, os.cpu_count() or 8))
     got = gpu.compress(data, "BWT+RANK+ZRLT", "ANS0", 4 << 20)
     assert got.size == want.size and np.array_equal(got, want), _first_diff(got, want)
     back = gpu.decompress(want, data.size)
     assert np.array_equal(back, data)
-    back2, rc = ref.stream_decompress(got, data.size, jobs=min(32, os.cpu_count() or 8))
+    back2, rc = ref.stream_decompress(got, data.size, jobs=min(48, os.cpu_count() or 8))
     assert rc == 0 and np.array_equal(back2, data)
 
 

@@ -112,13 +112,100 @@ __device__ __forceinline__ u64 sbrt_key(u32 p1, u32 p2, int sym, u32 m1, u32 m2,
     return ((u64)q << 32) | (u64)(t1 + 0x80000000u);
 }
 
-// 3. replay: one warp per tile
+// ---- the list, distributed over the lanes of one warp --------------------------
+// Rank g lives in lane (g & 31), slot (g >> 5): the 32 highest ranks are slot 0 of
+// the 32 lanes, so the common case (post-BWT ranks are small) touches one register
+// per lane.  Entry = key q and pb = (last access time << 8) | symbol.
+template <class PB>
+struct RankList {
+    int q[8];
+    PB pb[8];
+
+    // Move the entry at rank r (new key qc, new payload ne) up to its new rank:
+    // rp = #entries with key > qc (the list is sorted by key, ties: latest first).
+    __device__ __forceinline__ void move_up(int r, int qc, PB ne, int lane)
+    {
+        if (r < 32) {
+            const int rp = __popc(__ballot_sync(FULL_MASK, q[0] > qc));
+            const int nq = __shfl_up_sync(FULL_MASK, q[0], 1);
+            const PB npb = __shfl_up_sync(FULL_MASK, pb[0], 1);
+            const bool mv = (lane > rp) && (lane <= r);
+            q[0] = mv ? nq : q[0];
+            pb[0] = mv ? npb : pb[0];
+            if (lane == rp) {
+                q[0] = qc;
+                pb[0] = ne;
+            }
+            return;
+        }
+        int rp = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            rp += __popc(__ballot_sync(FULL_MASK, q[k] > qc));
+#pragma unroll
+        for (int k = 7; k >= 0; k--) {
+            // value arriving from the rank above: lane-1 of this slot, or lane 31 of the previous slot
+            int nq = __shfl_up_sync(FULL_MASK, q[k], 1);
+            PB npb = __shfl_up_sync(FULL_MASK, pb[k], 1);
+            if (k > 0) {
+                const int sq = __shfl_sync(FULL_MASK, q[k - 1], 31);
+                const PB spb = __shfl_sync(FULL_MASK, pb[k - 1], 31);
+                if (lane == 0) {
+                    nq = sq;
+                    npb = spb;
+                }
+            }
+            const int g = 32 * k + lane;
+            const bool mv = (g > rp) && (g <= r);
+            q[k] = mv ? nq : q[k];
+            pb[k] = mv ? npb : pb[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (32 * k + lane == rp) {
+                q[k] = qc;
+                pb[k] = ne;
+            }
+    }
+
+    __device__ __forceinline__ PB entry_at(int r) const
+    {
+        if (r < 32)
+            return __shfl_sync(FULL_MASK, pb[0], r);
+        // mask-select (an if-chain gets turned into an indexed load, which would push
+        // the whole list into local memory)
+        PB sel = 0;
+#pragma unroll
+        for (int k = 1; k < 8; k++)
+            sel |= pb[k] & (PB)(0 - (PB)((r >> 5) == k));
+        return __shfl_sync(FULL_MASK, sel, r & 31);
+    }
+
+    // rank of symbol c (always present)
+    __device__ __forceinline__ int find(u32 c) const
+    {
+        u32 m = __ballot_sync(FULL_MASK, (u32)(pb[0] & 0xFF) == c);
+        if (m)
+            return __ffs(m) - 1;
+#pragma unroll
+        for (int k = 1; k < 8; k++) {
+            m = __ballot_sync(FULL_MASK, (u32)(pb[k] & 0xFF) == c);
+            if (m)
+                return 32 * k + __ffs(m) - 1;
+        }
+        return 255;
+    }
+};
+
+// 3. replay: one warp per tile, exact list algorithm started from the tile's entry table
 #define R_WARPS 4
+template <class PB>
 __global__ void __launch_bounds__(R_WARPS * 32)
 sbrt_rank_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkState* __restrict__ stOut, int maxTiles,
                  const uint2* __restrict__ occ, int mode)
 {
     __shared__ u64 s_keys[R_WARPS][256];
+    __shared__ u64 s_ent[R_WARPS][256]; // (q << 32 | pb) by rank, only while the list is built
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int b = blockIdx.y;
     const int t = blockIdx.x * R_WARPS + w;
@@ -134,21 +221,48 @@ sbrt_rank_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkState*
     sbrt_masks(mode, m1, m2, sh);
     const u8* __restrict__ src = blk_src(bt, bs, b);
     u8* __restrict__ dst = blk_dst(bt, bs, b);
+    // ---- build the sorted list for this tile: rank(s) = #{u : key_u > key_s}
     u64* keys = s_keys[w];
+    u64* ent = s_ent[w];
     const uint2* o = occ + ((i64)b * maxTiles + t) * 256;
-    for (int s = lane; s < 256; s += 32) {
-        const uint2 e = o[s];
-        keys[s] = sbrt_key(e.x, e.y, s, m1, m2, sh);
+    u64 myKey[8];
+    u32 myQ[8], myP[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int sym = 32 * k + lane;
+        const uint2 e = o[sym];
+        myKey[k] = sbrt_key(e.x, e.y, sym, m1, m2, sh);
+        keys[sym] = myKey[k];
+        myQ[k] = (u32)(myKey[k] >> 32);
+        myP[k] = e.x ? e.x - 1 : 0u;
     }
     __syncwarp();
+    int rk[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    for (int u = 0; u < 256; u++) {
+        const u64 ku = keys[u];
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            rk[k] += (ku > myKey[k]) ? 1 : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+        ent[rk[k]] = ((u64)myQ[k] << 32) | ((u64)myP[k] << 8) | (u64)(32 * k + lane);
+    __syncwarp();
+    RankList<PB> L;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const u64 e = ent[32 * k + lane];
+        L.q[k] = (int)(e >> 32);
+        L.pb[k] = (PB)(e & 0xFFFFFFFFull);
+    }
+    // ---- replay
     const int end = min(base + S_TILE, n);
     for (int g = base; g < end; g += 128) {
-        // 128 positions per round: lane holds 4 input bytes, builds 4 output bytes
         u32 inw = 0;
         {
             const int p = g + 4 * lane;
-            if (p + 4 <= n && ((((uintptr_t)(src + p)) & 3) == 0)) {
-                inw = *reinterpret_cast<const u32*>(src + p);
+            if (p + 4 <= n) {
+                inw = *reinterpret_cast<const u32*>(src + p); // buffers are 16-byte aligned
             } else {
                 for (int k = 0; k < 4; k++)
                     if (p + k < n)
@@ -157,28 +271,34 @@ sbrt_rank_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkState*
         }
         u32 outw = 0;
         const int cnt = min(128, end - g);
-        for (int j = 0; j < cnt; j++) {
-            const u32 wv = __shfl_sync(FULL_MASK, inw, j >> 2);
-            const u32 c = (wv >> (8 * (j & 3))) & 0xFF;
-            const u64 kc = keys[c];
-            u32 rank = 0;
-#pragma unroll
-            for (int r = 0; r < 8; r++)
-                rank += __popc(__ballot_sync(FULL_MASK, keys[r * 32 + lane] > kc));
+        for (int j = 0; j < cnt; j += 4) {
+            const u32 w4 = __shfl_sync(FULL_MASK, inw, j >> 2);
+            const int lim = min(4, cnt - j);
+            u32 o4 = 0;
+            for (int x = 0; x < lim; x++) {
+                const u32 c = (w4 >> (8 * x)) & 0xFF;
+                const u32 i = (u32)(g + j + x);
+                const int r = L.find(c);
+                const PB e = L.entry_at(r);
+                const u32 pc = (u32)(e >> 8);
+                const int qc = (int)(((i & m1) + (pc & m2)) >> sh);
+                o4 |= (u32)r << (8 * x);
+                const PB ne = ((PB)i << 8) | (PB)c;
+                if (r == 0) {
+                    if (lane == 0) {
+                        L.q[0] = qc;
+                        L.pb[0] = ne;
+                    }
+                } else {
+                    L.move_up(r, qc, ne, lane);
+                }
+            }
             if (lane == (j >> 2))
-                outw |= rank << (8 * (j & 3));
-            const u32 i = (u32)(g + j);
-            const int tlast = (int)((u32)kc - 0x80000000u); // < 0: never accessed
-            const u32 prev = (tlast < 0) ? 0u : (u32)tlast;
-            const u32 qc = ((i & m1) + (prev & m2)) >> sh;
-            __syncwarp();
-            if (lane == 0)
-                keys[c] = ((u64)qc << 32) | (u64)(i + 0x80000000u);
-            __syncwarp();
+                outw = o4;
         }
         {
             const int p = g + 4 * lane;
-            if (p + 4 <= end && ((((uintptr_t)(dst + p)) & 3) == 0)) {
+            if (p + 4 <= end) {
                 *reinterpret_cast<u32*>(dst + p) = outw;
             } else {
                 for (int k = 0; k < 4; k++)
@@ -191,13 +311,9 @@ sbrt_rank_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkState*
 
 // Inverse: serial replay per block (SBRT.cpp:99-145).  The update needs the decoded
 // symbol, so a block is ONE dependency chain; the kernel minimises the latency of a
-// step: one warp per block with the 256-entry list distributed over the lanes in
-// registers (lane L owns ranks 8L..8L+7; entry = key q and pb = (last access << 8) | symbol).
-//   symbol at rank r      : uniform slot select + one shuffle from lane r>>3
-//   new rank of the symbol: #entries with q > qc  (8 ballots; the list is sorted by q)
-//   move-up               : every lane shifts its own slots, one shuffle-up for the seam
-// No shared memory, no divergence; zero words (runs of rank 0) take a closed form.
-// Input/output travel through registers 128 bytes at a time (coalesced, prefetched).
+// step: one warp per block, the list distributed over the lanes in registers
+// (RankList), no shared memory, no divergence; zero words (runs of rank 0) take a
+// closed form; input/output travel through registers 128 bytes at a time.
 template <class PB>
 __global__ void __launch_bounds__(32)
 sbrt_inverse_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkState* __restrict__ stOut, int mode)
@@ -213,12 +329,11 @@ sbrt_inverse_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkSta
     u32 m1, m2;
     int sh;
     sbrt_masks(mode, m1, m2, sh);
-    int q[8];
-    PB pb[8];
+    RankList<PB> L;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        q[k] = 0;
-        pb[k] = (PB)(8 * lane + k);
+        L.q[k] = 0;
+        L.pb[k] = (PB)(32 * k + lane);
     }
     const u32* __restrict__ src4 = reinterpret_cast<const u32*>(src); // buffers are 16-byte aligned
     const int groups = (n + 127) >> 7;
@@ -251,25 +366,19 @@ sbrt_inverse_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkSta
             u32 o4 = 0;
             if (w4 == 0 && lim == 4) {
                 // four accesses to the head of the list: only its key changes
-                const PB e = __shfl_sync(FULL_MASK, pb[0], 0);
+                const PB e = __shfl_sync(FULL_MASK, L.pb[0], 0);
                 const u32 c = (u32)(e & 0xFF);
                 const u32 i3 = (u32)(base + j + 3);
                 if (lane == 0) {
-                    q[0] = (int)(((i3 & m1) + ((i3 - 1) & m2)) >> sh);
-                    pb[0] = ((PB)i3 << 8) | (PB)c;
+                    L.q[0] = (int)(((i3 & m1) + ((i3 - 1) & m2)) >> sh);
+                    L.pb[0] = ((PB)i3 << 8) | (PB)c;
                 }
                 o4 = c * 0x01010101u;
             } else {
                 for (int x = 0; x < lim; x++) {
                     const int r = (int)((w4 >> (8 * x)) & 0xFF);
                     const u32 i = (u32)(base + j + x);
-                    const int slot = r & 7;
-                    PB sel = pb[0];
-#pragma unroll
-                    for (int k = 1; k < 8; k++)
-                        if (slot == k)
-                            sel = pb[k];
-                    const PB e = __shfl_sync(FULL_MASK, sel, r >> 3);
+                    const PB e = L.entry_at(r);
                     const u32 c = (u32)(e & 0xFF);
                     const u32 pc = (u32)(e >> 8);
                     const int qc = (int)(((i & m1) + (pc & m2)) >> sh);
@@ -277,36 +386,12 @@ sbrt_inverse_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkSta
                     o4 |= c << (8 * x);
                     if (r == 0) {
                         if (lane == 0) {
-                            q[0] = qc;
-                            pb[0] = ne;
+                            L.q[0] = qc;
+                            L.pb[0] = ne;
                         }
-                        continue;
+                    } else {
+                        L.move_up(r, qc, ne, lane);
                     }
-                    int rp = 0;
-#pragma unroll
-                    for (int k = 0; k < 8; k++)
-                        rp += __popc(__ballot_sync(FULL_MASK, q[k] > qc));
-                    // ranks (rp, r] take the entry of the rank above; rank rp takes the new entry
-                    const int pq = __shfl_up_sync(FULL_MASK, q[7], 1);
-                    const PB ppb = __shfl_up_sync(FULL_MASK, pb[7], 1);
-                    const int g0 = 8 * lane;
-#pragma unroll
-                    for (int k = 7; k >= 1; k--) {
-                        const bool mv = (g0 + k > rp) && (g0 + k <= r);
-                        q[k] = mv ? q[k - 1] : q[k];
-                        pb[k] = mv ? pb[k - 1] : pb[k];
-                    }
-                    {
-                        const bool mv = (g0 > rp) && (g0 <= r);
-                        q[0] = mv ? pq : q[0];
-                        pb[0] = mv ? ppb : pb[0];
-                    }
-#pragma unroll
-                    for (int k = 0; k < 8; k++)
-                        if (g0 + k == rp) {
-                            q[k] = qc;
-                            pb[k] = ne;
-                        }
                 }
             }
             if (lane == (j >> 2))
@@ -333,8 +418,12 @@ void launch_sbrt_forward(const StageLaunch& L, int mode, Workspace& ws, cudaStre
     KLAUNCH(sbrt_decide_kernel, (L.nBlocks + 31) / 32, 32, s, L, 0);
     KLAUNCH(sbrt_occ_kernel, dim3(tiles, L.nBlocks), 256, s, L.bt, L.stIn, L.stOut, maxTiles, occ);
     KLAUNCH(sbrt_fold_kernel, L.nBlocks, 256, s, L.stIn, L.stOut, maxTiles, occ);
-    KLAUNCH(sbrt_rank_kernel, dim3((tiles + R_WARPS - 1) / R_WARPS, L.nBlocks), R_WARPS * 32, s, L.bt, L.stIn, L.stOut,
-            maxTiles, occ, mode);
+    if (L.maxLen < (1 << 24))
+        KLAUNCH(sbrt_rank_kernel<u32>, dim3((tiles + R_WARPS - 1) / R_WARPS, L.nBlocks), R_WARPS * 32, s, L.bt, L.stIn,
+                L.stOut, maxTiles, occ, mode);
+    else
+        KLAUNCH(sbrt_rank_kernel<u64>, dim3((tiles + R_WARPS - 1) / R_WARPS, L.nBlocks), R_WARPS * 32, s, L.bt, L.stIn,
+                L.stOut, maxTiles, occ, mode);
     *launches += 4;
 }
 

@@ -531,6 +531,171 @@ bwt_emit_kernel(BufTable bt, const BlkState* __restrict__ st, const int* __restr
     }
 }
 
+// ---- rounds: tile-local sort + global sort of the groups that straddle tiles ----
+// After the gather, survivors sit in group order with key (group rank << 32 | key2).
+// Sorting every aligned 2048-element tile by key in shared memory (bitonic network;
+// ties never matter: equal keys stay one group) finishes every group that lies inside
+// one tile -- almost all of them.  Elements of groups that cross a tile boundary form
+// the prefix / suffix of their tiles; they are copied out, radix sorted globally and
+// written back to the same positions.
+struct XCtx {
+    u64* key[2];
+    u32* val[2];
+    const u32* grp;    // group rank by position (survivor order)
+    const int* which0; // buffer holding the survivors
+    int* which8;       // row read by the group kernels
+    const int* cnt;
+    u32* xcnt;         // [nBlocks][maxTiles][2] : npre, nsuf  -> exclusive offsets after the scan
+    int* cntX;         // [nBlocks] extracted elements
+    u64* xkey;         // extraction arrays (buffer 0 of the side sort)
+    u32* xval;
+    u32* xpos;
+    u64* xkeyAlt;      // buffer 1 of the side sort
+    u32* xvalAlt;
+    const int* whichX8;
+    int capN, maxTiles, maxBlocks;
+};
+
+__global__ void __launch_bounds__(RS_THREADS)
+bwt_tile_sort_kernel(XCtx X)
+{
+    __shared__ u64 sk[RS_TILE];
+    __shared__ u32 sv[RS_TILE];
+    __shared__ u32 s_red[2][8];
+    const int b = blockIdx.y;
+    const int cnt = X.cnt[b];
+    const int tbase = blockIdx.x * RS_TILE;
+    if (tbase >= cnt)
+        return;
+    const int w = X.which0[b];
+    u64* __restrict__ K = X.key[w] + (i64)b * X.capN;
+    u32* __restrict__ V = X.val[w] + (i64)b * X.capN;
+    const u32* __restrict__ G = X.grp + (i64)b * X.capN;
+    const int tend = min(tbase + RS_TILE, cnt);
+    for (int i = threadIdx.x; i < RS_TILE; i += RS_THREADS) {
+        const int j = tbase + i;
+        sk[i] = (j < cnt) ? K[j] : ~0ull;
+        sv[i] = (j < cnt) ? V[j] : 0u;
+    }
+    __syncthreads();
+    for (int k = 2; k <= RS_TILE; k <<= 1) {
+        for (int jj = k >> 1; jj > 0; jj >>= 1) {
+            for (int t = threadIdx.x; t < RS_TILE / 2; t += RS_THREADS) {
+                const int i = ((t & ~(jj - 1)) << 1) | (t & (jj - 1));
+                const int p2 = i | jj;
+                const bool up = (i & k) == 0;
+                const u64 a = sk[i], c = sk[p2];
+                if ((a > c) == up) {
+                    sk[i] = c;
+                    sk[p2] = a;
+                    const u32 va = sv[i];
+                    sv[i] = sv[p2];
+                    sv[p2] = va;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < RS_TILE; i += RS_THREADS) {
+        const int j = tbase + i;
+        if (j < cnt) {
+            K[j] = sk[i];
+            V[j] = sv[i];
+        }
+    }
+    // straddling groups: leading run of the first group / trailing run of the last group
+    const u32 g0 = G[tbase], gl = G[tend - 1];
+    const bool pre = (tbase > 0) && (G[tbase - 1] == g0);
+    const bool suf = (tend < cnt) && (G[tend] == gl);
+    u32 c0 = 0, c1 = 0;
+    for (int j = tbase + threadIdx.x; j < tend; j += RS_THREADS) {
+        const u32 g = G[j];
+        c0 += (g == g0) ? 1u : 0u;
+        c1 += (g == gl) ? 1u : 0u;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        c0 += __shfl_xor_sync(FULL_MASK, c0, o);
+        c1 += __shfl_xor_sync(FULL_MASK, c1, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_red[0][threadIdx.x >> 5] = c0;
+        s_red[1][threadIdx.x >> 5] = c1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 a = 0, c = 0;
+        for (int i = 0; i < 8; i++) {
+            a += s_red[0][i];
+            c += s_red[1][i];
+        }
+        u32 npre = pre ? a : 0u;
+        u32 nsuf = suf ? c : 0u;
+        if (npre + nsuf > (u32)(tend - tbase)) // one group fills the tile and crosses both edges
+            nsuf = (u32)(tend - tbase) - npre;
+        u32* xc = X.xcnt + ((i64)b * X.maxTiles + blockIdx.x) * 2;
+        xc[0] = npre;
+        xc[1] = nsuf;
+    }
+}
+
+__global__ void bwt_xscan_kernel(XCtx X, int nBlocks)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nBlocks)
+        return;
+    X.which8[b] = X.which0[b];
+    const int cnt = X.cnt[b];
+    const int tiles = (cnt + RS_TILE - 1) / RS_TILE;
+    u32 run = 0;
+    u32* xc = X.xcnt + (i64)b * X.maxTiles * 2;
+    for (int t = 0; t < tiles; t++) {
+        const u32 a = xc[2 * t], c = xc[2 * t + 1];
+        xc[2 * t] = run; // offset of the tile's prefix elements
+        run += a;
+        xc[2 * t + 1] = run | ((c != 0) ? 0x80000000u : 0u); // offset of its suffix elements (+flag)
+        run += c;
+    }
+    X.cntX[b] = (int)run;
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+bwt_extract_kernel(XCtx X, int writeBack)
+{
+    const int b = blockIdx.y;
+    const int cnt = X.cnt[b];
+    const int tbase = blockIdx.x * RS_TILE;
+    if (tbase >= cnt || X.cntX[b] == 0)
+        return;
+    const int w = X.which0[b];
+    u64* __restrict__ K = X.key[w] + (i64)b * X.capN;
+    u32* __restrict__ V = X.val[w] + (i64)b * X.capN;
+    const u32* __restrict__ G = X.grp + (i64)b * X.capN;
+    const int tend = min(tbase + RS_TILE, cnt);
+    const int tiles = (cnt + RS_TILE - 1) / RS_TILE;
+    const u32* xc = X.xcnt + ((i64)b * X.maxTiles + blockIdx.x) * 2;
+    const u32 offPre = xc[0];
+    const u32 offSuf = xc[1] & 0x7FFFFFFFu;
+    const u32 npre = offSuf - offPre;
+    const u32 offNext = (blockIdx.x + 1 < (u32)tiles) ? xc[2] : (u32)X.cntX[b];
+    const u32 nsuf = offNext - offSuf;
+    const int wx = writeBack ? X.whichX8[b] : 0;
+    u64* __restrict__ xk = (wx ? X.xkeyAlt : X.xkey) + (i64)b * X.capN;
+    u32* __restrict__ xv = (wx ? X.xvalAlt : X.xval) + (i64)b * X.capN;
+    (void)G;
+    for (u32 i = threadIdx.x; i < npre + nsuf; i += RS_THREADS) {
+        const int j = (i < npre) ? (tbase + (int)i) : (tend - (int)nsuf + (int)(i - npre));
+        const u32 x = (i < npre) ? (offPre + i) : (offSuf + (i - npre));
+        if (writeBack) {
+            K[j] = xk[x];
+            V[j] = xv[x];
+        } else {
+            xk[x] = K[j];
+            xv[x] = V[j];
+        }
+    }
+}
+
 void launch_bwt_forward(const StageLaunch& L, Workspace& ws, cudaStream_t s, u64* launches)
 {
     const int nB = L.nBlocks;
@@ -574,6 +739,35 @@ void launch_bwt_forward(const StageLaunch& L, Workspace& ws, cudaStream_t s, u64
     G.maxTiles = maxTiles;
     G.maxBlocks = ws.maxBlocks;
 
+    SortArrays AX = A; // side sort of the extracted (tile-crossing) elements
+    AX.key[0] = ws.xkeyA;
+    AX.key[1] = ws.xkeyB;
+    AX.val[0] = ws.xvalA;
+    AX.val[1] = ws.xvalB;
+    AX.which = ws.whichX;
+    AX.cnt = ws.cntX;
+
+    XCtx X;
+    X.key[0] = ws.keyA;
+    X.key[1] = ws.keyB;
+    X.val[0] = ws.valA;
+    X.val[1] = ws.valB;
+    X.grp = ws.grpA;
+    X.which0 = ws.which;
+    X.which8 = ws.which + 8 * ws.maxBlocks;
+    X.cnt = ws.cnt;
+    X.xcnt = ws.scanB;
+    X.cntX = ws.cntX;
+    X.xkey = ws.xkeyA;
+    X.xval = ws.xvalA;
+    X.xpos = NULL;
+    X.xkeyAlt = ws.xkeyB;
+    X.xvalAlt = ws.xvalB;
+    X.whichX8 = ws.whichX + 8 * ws.maxBlocks;
+    X.capN = ws.capN;
+    X.maxTiles = maxTiles;
+    X.maxBlocks = ws.maxBlocks;
+
     int maxCnt = L.maxLen;
     // key2 < 2n, group rank < n  ->  which byte positions can be non-zero
     const int lowBits = ilog2_u32((u32)(2 * (i64)L.maxLen > 1 ? 2 * (i64)L.maxLen : 2)) + 1;
@@ -588,8 +782,27 @@ void launch_bwt_forward(const StageLaunch& L, Workspace& ws, cudaStream_t s, u64
 
     for (int round = 0, h = 8;; round++) {
         G.initial = (round == 0) ? 1 : 0;
-        radix_sort(A, nB, maxCnt, (round == 0) ? 0xFFu : roundMask, s, launches);
         const int tiles = (maxCnt + RS_TILE - 1) / RS_TILE;
+        if (round == 0) {
+            radix_sort(A, nB, maxCnt, 0xFFu, s, launches);
+        } else {
+            // groups inside one tile: shared-memory sort; groups crossing tiles: side radix sort
+            KLAUNCH(bwt_tile_sort_kernel, dim3(tiles, nB), RS_THREADS, s, X);
+            KLAUNCH(bwt_xscan_kernel, (nB + 63) / 64, 64, s, X, nB);
+            *launches += 2;
+            cudaMemcpyAsync(ws.h_cnt, ws.cntX, sizeof(int) * nB, cudaMemcpyDeviceToHost, s);
+            cudaStreamSynchronize(s);
+            int maxX = 0;
+            for (int b = 0; b < nB; b++)
+                maxX = max(maxX, ws.h_cnt[b]);
+            if (maxX > 0) {
+                KLAUNCH(bwt_extract_kernel, dim3(tiles, nB), RS_THREADS, s, X, 0);
+                cudaMemsetAsync(ws.whichX, 0, sizeof(int) * ws.maxBlocks, s); // extracted data starts in buffer 0
+                radix_sort(AX, nB, maxX, roundMask, s, launches);
+                KLAUNCH(bwt_extract_kernel, dim3(tiles, nB), RS_THREADS, s, X, 1);
+                *launches += 2;
+            }
+        }
         KLAUNCH(bwt_grp_partials_kernel, dim3(tiles, nB), RS_THREADS, s, G);
         KLAUNCH(bwt_grp_scan_kernel, (nB + 63) / 64, 64, s, G, nB);
         KLAUNCH(bwt_grp_apply_kernel, dim3(tiles, nB), RS_THREADS, s, G);
@@ -1014,6 +1227,13 @@ bool workspace_alloc(Workspace& ws, int maxBlocks, int capN)
     ok = ok && wsalloc(&ws.cnt, nb);
     ok = ok && wsalloc(&ws.cntNext, nb);
     ok = ok && wsalloc(&ws.scanA, nb * sTiles * 4 + nb);
+    ok = ok && wsalloc(&ws.scanB, nb * sTiles * 2 + nb);
+    ok = ok && wsalloc(&ws.xkeyA, elems);
+    ok = ok && wsalloc(&ws.xkeyB, elems);
+    ok = ok && wsalloc(&ws.xvalA, elems);
+    ok = ok && wsalloc(&ws.xvalB, elems);
+    ok = ok && wsalloc(&ws.whichX, 9 * nb);
+    ok = ok && wsalloc(&ws.cntX, nb);
     ok = ok && wsalloc(&ws.pidx, nb * 8);
     ok = ok && wsalloc(&ws.bwtOk, nb);
     ok = ok && (cudaMallocHost((void**)&ws.h_cnt, sizeof(int) * (size_t)nb) == cudaSuccess);
@@ -1023,7 +1243,8 @@ bool workspace_alloc(Workspace& ws, int maxBlocks, int capN)
 void workspace_free(Workspace& ws)
 {
     void* d[] = { ws.tileA, ws.tileB, ws.occ, ws.keyA, ws.keyB, ws.valA, ws.valB, ws.grpA, ws.isa, ws.hist,
-                  ws.digitBase, ws.totals, ws.which, ws.trivial, ws.cnt, ws.cntNext, ws.scanA, ws.pidx, ws.bwtOk };
+                  ws.digitBase, ws.totals, ws.which, ws.trivial, ws.cnt, ws.cntNext, ws.scanA, ws.pidx, ws.bwtOk,
+                  ws.scanB, ws.xkeyA, ws.xkeyB, ws.xvalA, ws.xvalB, ws.whichX, ws.cntX };
     for (size_t i = 0; i < sizeof(d) / sizeof(d[0]); i++)
         if (d[i])
             cudaFree(d[i]);

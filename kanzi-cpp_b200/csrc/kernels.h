@@ -106,7 +106,11 @@ struct Workspace {
     int* cntNext;
     int* h_cnt;         // pinned host mirror
     u32* scanA;         // [maxBlocks * sortTiles * 4]
-    u32* scanB;
+    u32* scanB;         // [maxBlocks * sortTiles * 2]
+    u64 *xkeyA, *xkeyB; // side sort of tile-crossing groups
+    u32 *xvalA, *xvalB;
+    int* whichX;        // [9][maxBlocks]
+    int* cntX;          // [maxBlocks]
     int* pidx;          // [maxBlocks * 8] primary indexes
     int* bwtOk;         // [maxBlocks]
 };

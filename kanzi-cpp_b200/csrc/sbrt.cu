@@ -123,21 +123,22 @@ struct RankList {
 
     // Move the entry at rank r (new key qc, new payload ne) up to its new rank:
     // rp = #entries with key > qc (the list is sorted by key, ties: latest first).
+    // Fast path for r < 32, branch-free and without a vote: with nq/npb = the entry of
+    // the rank above (shuffled up BEFORE qc is known, off the critical path), lane g
+    //   takes the entry above   iff g <= r, g > 0 and q[g-1] <= qc   (it is below the new rank)
+    //   receives the new entry  iff g <= r, q[g] <= qc and (g == 0 or q[g-1] > qc)
+    // (the list is sorted by key, so "q[g-1] <= qc" == "g > new rank").
+    __device__ __forceinline__ void move_up_top(int r, int qc, PB ne, int lane, int nq, PB npb)
+    {
+        const bool below = lane <= r;
+        const bool mv = below && (lane > 0) && (nq <= qc);
+        const bool ins = below && (q[0] <= qc) && ((lane == 0) || (nq > qc));
+        q[0] = ins ? qc : (mv ? nq : q[0]);
+        pb[0] = ins ? ne : (mv ? npb : pb[0]);
+    }
+
     __device__ __forceinline__ void move_up(int r, int qc, PB ne, int lane)
     {
-        if (r < 32) {
-            const int rp = __popc(__ballot_sync(FULL_MASK, q[0] > qc));
-            const int nq = __shfl_up_sync(FULL_MASK, q[0], 1);
-            const PB npb = __shfl_up_sync(FULL_MASK, pb[0], 1);
-            const bool mv = (lane > rp) && (lane <= r);
-            q[0] = mv ? nq : q[0];
-            pb[0] = mv ? npb : pb[0];
-            if (lane == rp) {
-                q[0] = qc;
-                pb[0] = ne;
-            }
-            return;
-        }
         int rp = 0;
 #pragma unroll
         for (int k = 0; k < 8; k++)
@@ -278,19 +279,24 @@ sbrt_rank_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkState*
             for (int x = 0; x < lim; x++) {
                 const u32 c = (w4 >> (8 * x)) & 0xFF;
                 const u32 i = (u32)(g + j + x);
-                const int r = L.find(c);
-                const PB e = L.entry_at(r);
-                const u32 pc = (u32)(e >> 8);
-                const int qc = (int)(((i & m1) + (pc & m2)) >> sh);
-                o4 |= (u32)r << (8 * x);
-                const PB ne = ((PB)i << 8) | (PB)c;
-                if (r == 0) {
-                    if (lane == 0) {
-                        L.q[0] = qc;
-                        L.pb[0] = ne;
-                    }
+                // top-32 probe: who holds c, and its last access time, without waiting for the rank
+                const int nq = __shfl_up_sync(FULL_MASK, L.q[0], 1);
+                const PB npb = __shfl_up_sync(FULL_MASK, L.pb[0], 1);
+                const bool hit = (u32)(L.pb[0] & 0xFF) == c;
+                const u32 m = __ballot_sync(FULL_MASK, hit);
+                if (m) {
+                    const u32 pc = __reduce_or_sync(FULL_MASK, hit ? (u32)(L.pb[0] >> 8) : 0u);
+                    const int r = __ffs(m) - 1;
+                    const int qc = (int)(((i & m1) + (pc & m2)) >> sh);
+                    o4 |= (u32)r << (8 * x);
+                    L.move_up_top(r, qc, ((PB)i << 8) | (PB)c, lane, nq, npb);
                 } else {
-                    L.move_up(r, qc, ne, lane);
+                    const int r = L.find(c);
+                    const PB e = L.entry_at(r);
+                    const u32 pc = (u32)(e >> 8);
+                    const int qc = (int)(((i & m1) + (pc & m2)) >> sh);
+                    o4 |= (u32)r << (8 * x);
+                    L.move_up(r, qc, ((PB)i << 8) | (PB)c, lane);
                 }
             }
             if (lane == (j >> 2))
@@ -378,19 +384,22 @@ sbrt_inverse_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkSta
                 for (int x = 0; x < lim; x++) {
                     const int r = (int)((w4 >> (8 * x)) & 0xFF);
                     const u32 i = (u32)(base + j + x);
-                    const PB e = L.entry_at(r);
-                    const u32 c = (u32)(e & 0xFF);
-                    const u32 pc = (u32)(e >> 8);
-                    const int qc = (int)(((i & m1) + (pc & m2)) >> sh);
-                    const PB ne = ((PB)i << 8) | (PB)c;
-                    o4 |= c << (8 * x);
-                    if (r == 0) {
-                        if (lane == 0) {
-                            L.q[0] = qc;
-                            L.pb[0] = ne;
-                        }
+                    if (r < 32) {
+                        const int nq = __shfl_up_sync(FULL_MASK, L.q[0], 1);
+                        const PB npb = __shfl_up_sync(FULL_MASK, L.pb[0], 1);
+                        const PB e = __shfl_sync(FULL_MASK, L.pb[0], r);
+                        const u32 c = (u32)(e & 0xFF);
+                        const u32 pc = (u32)(e >> 8);
+                        const int qc = (int)(((i & m1) + (pc & m2)) >> sh);
+                        o4 |= c << (8 * x);
+                        L.move_up_top(r, qc, ((PB)i << 8) | (PB)c, lane, nq, npb);
                     } else {
-                        L.move_up(r, qc, ne, lane);
+                        const PB e = L.entry_at(r);
+                        const u32 c = (u32)(e & 0xFF);
+                        const u32 pc = (u32)(e >> 8);
+                        const int qc = (int)(((i & m1) + (pc & m2)) >> sh);
+                        o4 |= c << (8 * x);
+                        L.move_up(r, qc, ((PB)i << 8) | (PB)c, lane);
                     }
                 }
             }

@@ -217,6 +217,16 @@ inline T __shfl_xor_sync(uint32_t mask, T v, int x)
     return out;
 }
 
+inline uint32_t __reduce_or_sync(uint32_t mask, uint32_t v)
+{
+    return (uint32_t)cusim::collective(mask, v, [](const uint64_t* s, uint32_t m, int) {
+        uint64_t r = 0;
+        for (int i = 0; i < 32; i++)
+            if ((m >> i) & 1)
+                r |= s[i];
+        return r;
+    });
+}
 inline int __popc(uint32_t x) { return __builtin_popcount(x); }
 inline int __popcll(uint64_t x) { return __builtin_popcountll(x); }
 inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }

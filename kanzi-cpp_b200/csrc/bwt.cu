@@ -116,11 +116,17 @@ rs_hist_kernel(SortArrays A, int pass)
     __syncthreads();
     const u64* __restrict__ k = A.key[A.which[pass * A.maxBlocks + b]] + (i64)b * A.capN;
     const int sh = 8 * pass;
+    u64 kv[RS_ITEMS];
+#pragma unroll
+    for (int it = 0; it < RS_ITEMS; it++) {
+        const int j = base + it * RS_THREADS + threadIdx.x;
+        kv[it] = (j < cnt) ? __ldg(&k[j]) : 0;
+    }
 #pragma unroll
     for (int it = 0; it < RS_ITEMS; it++) {
         const int j = base + it * RS_THREADS + threadIdx.x;
         if (j < cnt)
-            atomicAdd(&s_h[(k[j] >> sh) & 0xFF], 1u);
+            atomicAdd(&s_h[(kv[it] >> sh) & 0xFF], 1u);
     }
     __syncthreads();
     A.hist[((i64)b * A.maxTiles + blockIdx.x) * 256 + threadIdx.x] = s_h[threadIdx.x];
@@ -175,12 +181,21 @@ rs_scatter_kernel(SortArrays A, int pass)
     u64 key[RS_ITEMS];
     u32 val[RS_ITEMS];
     u32 rnk[RS_ITEMS];
+    // all loads first: 16 independent requests per thread in flight
+#pragma unroll
+    for (int it = 0; it < RS_ITEMS; it++) {
+        const int j = tbase + w * (32 * RS_ITEMS) + it * 32 + lane;
+        key[it] = (j < cnt) ? __ldg(&kin[j]) : 0;
+    }
+#pragma unroll
+    for (int it = 0; it < RS_ITEMS; it++) {
+        const int j = tbase + w * (32 * RS_ITEMS) + it * 32 + lane;
+        val[it] = (j < cnt) ? __ldg(&vin[j]) : 0;
+    }
 #pragma unroll
     for (int it = 0; it < RS_ITEMS; it++) {
         const int j = tbase + w * (32 * RS_ITEMS) + it * 32 + lane;
         const bool ok = j < cnt;
-        key[it] = ok ? kin[j] : 0;
-        val[it] = ok ? vin[j] : 0;
         const u32 d = ok ? (u32)((key[it] >> sh) & 0xFF) : 256u; // 256 = padding class
         const u32 peers = __match_any_sync(FULL_MASK, d);
         const u32 prior = (d < 256) ? s_cnt[w][d] : 0;
@@ -561,7 +576,9 @@ bwt_tile_sort_kernel(XCtx X)
 {
     __shared__ u64 sk[RS_TILE];
     __shared__ u32 sv[RS_TILE];
+    __shared__ u32 sg[RS_TILE];
     __shared__ u32 s_red[2][8];
+    __shared__ u32 s_big;
     const int b = blockIdx.y;
     const int cnt = X.cnt[b];
     const int tbase = blockIdx.x * RS_TILE;
@@ -572,28 +589,74 @@ bwt_tile_sort_kernel(XCtx X)
     u32* __restrict__ V = X.val[w] + (i64)b * X.capN;
     const u32* __restrict__ G = X.grp + (i64)b * X.capN;
     const int tend = min(tbase + RS_TILE, cnt);
+    const int tsz = tend - tbase;
+    // groups that cross the tile edges are finished by the side sort: leave them alone here
+    const u32 g0 = G[tbase], gl = G[tend - 1];
+    const bool pre = (tbase > 0) && (G[tbase - 1] == g0);
+    const bool suf = (tend < cnt) && (G[tend] == gl);
     for (int i = threadIdx.x; i < RS_TILE; i += RS_THREADS) {
         const int j = tbase + i;
         sk[i] = (j < cnt) ? K[j] : ~0ull;
         sv[i] = (j < cnt) ? V[j] : 0u;
+        u32 g = (j < cnt) ? G[j] : 0xFFFFFFFFu;
+        if ((pre && g == g0) || (suf && g == gl))
+            g = 0xFFFFFFFEu - (u32)i; // unique id: never compared with a neighbour
+        sg[i] = g;
     }
+    if (threadIdx.x == 0)
+        s_big = 0;
     __syncthreads();
-    for (int k = 2; k <= RS_TILE; k <<= 1) {
-        for (int jj = k >> 1; jj > 0; jj >>= 1) {
+    // largest group in the tile, as a power of two bound: a group has more than P
+    // members iff some position i has the same group id at i + P
+    u32 big = 0;
+    for (int i = threadIdx.x; i < tsz; i += RS_THREADS) {
+        const u32 g = sg[i];
+#pragma unroll
+        for (int lg = 1; lg <= 5; lg++)
+            if (i + (1 << lg) < tsz && sg[i + (1 << lg)] == g)
+                big |= 1u << lg;
+    }
+    if (big)
+        atomicOr(&s_big, big);
+    __syncthreads();
+    const u32 bigAll = s_big;
+    if (!(bigAll & 32u)) {
+        // every group has <= 32 members: odd-even transposition inside groups
+        const int phases = (bigAll & 16u) ? 32 : (bigAll & 8u) ? 16 : (bigAll & 4u) ? 8 : (bigAll & 2u) ? 4 : 2;
+        for (int ph = 0; ph < phases; ph++) {
             for (int t = threadIdx.x; t < RS_TILE / 2; t += RS_THREADS) {
-                const int i = ((t & ~(jj - 1)) << 1) | (t & (jj - 1));
-                const int p2 = i | jj;
-                const bool up = (i & k) == 0;
-                const u64 a = sk[i], c = sk[p2];
-                if ((a > c) == up) {
-                    sk[i] = c;
-                    sk[p2] = a;
-                    const u32 va = sv[i];
-                    sv[i] = sv[p2];
-                    sv[p2] = va;
+                const int i = 2 * t + (ph & 1);
+                if (i + 1 < tsz && sg[i] == sg[i + 1]) {
+                    const u64 a = sk[i], c = sk[i + 1];
+                    if (a > c) {
+                        sk[i] = c;
+                        sk[i + 1] = a;
+                        const u32 va = sv[i];
+                        sv[i] = sv[i + 1];
+                        sv[i + 1] = va;
+                    }
                 }
             }
             __syncthreads();
+        }
+    } else {
+        for (int k = 2; k <= RS_TILE; k <<= 1) {
+            for (int jj = k >> 1; jj > 0; jj >>= 1) {
+                for (int t = threadIdx.x; t < RS_TILE / 2; t += RS_THREADS) {
+                    const int i = ((t & ~(jj - 1)) << 1) | (t & (jj - 1));
+                    const int p2 = i | jj;
+                    const bool up = (i & k) == 0;
+                    const u64 a = sk[i], c = sk[p2];
+                    if ((a > c) == up) {
+                        sk[i] = c;
+                        sk[p2] = a;
+                        const u32 va = sv[i];
+                        sv[i] = sv[p2];
+                        sv[p2] = va;
+                    }
+                }
+                __syncthreads();
+            }
         }
     }
     for (int i = threadIdx.x; i < RS_TILE; i += RS_THREADS) {
@@ -604,9 +667,6 @@ bwt_tile_sort_kernel(XCtx X)
         }
     }
     // straddling groups: leading run of the first group / trailing run of the last group
-    const u32 g0 = G[tbase], gl = G[tend - 1];
-    const bool pre = (tbase > 0) && (G[tbase - 1] == g0);
-    const bool suf = (tend < cnt) && (G[tend] == gl);
     u32 c0 = 0, c1 = 0;
     for (int j = tbase + threadIdx.x; j < tend; j += RS_THREADS) {
         const u32 g = G[j];

@@ -18,8 +18,9 @@
 using namespace knz;
 
 // ------------------------------------------------------------------ encoder
-// smem per warp: 8 tables x 256 x 8 B (histogram aliased in the first 1 KiB of
-// each) + 4 KiB scratch (4 privatised histograms / 8 x 256 u16 cumulative freqs).
+// smem per warp: 8 tables x 256 x 8 B = 16 KiB.  While the histograms are built the
+// second KiB of every table region is free: four of them hold the 4 privatised
+// copies of the chunk being counted.
 #define ENC_WARPS 2
 
 __global__ void __launch_bounds__(ENC_WARPS * 32)
@@ -27,7 +28,6 @@ ans0_encode_kernel(BufTable bt, const BlkState* __restrict__ st, int nBlocks, in
                    u32* __restrict__ hdrBits, u32* __restrict__ payBytes, u32* __restrict__ payOff)
 {
     __shared__ __align__(16) u64 s_sym[ENC_WARPS][8][256];
-    __shared__ __align__(16) u32 s_scr[ENC_WARPS][1024];
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int groupsPerBlk = (maxChunks + 7) >> 3;
@@ -56,7 +56,6 @@ ans0_encode_kernel(BufTable bt, const BlkState* __restrict__ st, int nBlocks, in
     }
 
     u64(*sym)[256] = s_sym[wib];
-    u32* scr = s_scr[wib];
 
     // ---- phase A: histograms (whole warp per chunk, 4-way privatised smem atomics)
     for (int j = 0; j < 8; j++) {
@@ -65,10 +64,17 @@ ans0_encode_kernel(BufTable bt, const BlkState* __restrict__ st, int nBlocks, in
             break;
         const int len = min(ANS_CHUNK, m - c * ANS_CHUNK);
         const u8* __restrict__ p = src + (i64)c * ANS_CHUNK;
-        for (int i = lane; i < 1024; i += 32)
-            scr[i] = 0;
+        // copy k lives in the upper KiB of table region (j + 1 + k) & 7
+        u32* hk[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            hk[k] = reinterpret_cast<u32*>(sym[(j + 1 + k) & 7]) + 256;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            for (int i = lane; i < 256; i += 32)
+                hk[k][i] = 0;
         __syncwarp();
-        u32* h = scr + ((lane & 3) << 8);
+        u32* h = reinterpret_cast<u32*>(sym[(j + 1 + (lane & 3)) & 7]) + 256;
         for (int i = lane * 16; i < len; i += 512) {
             if (i + 16 <= len) {
                 const uint4 v = *reinterpret_cast<const uint4*>(p + i);
@@ -88,7 +94,7 @@ ans0_encode_kernel(BufTable bt, const BlkState* __restrict__ st, int nBlocks, in
         __syncwarp();
         u32* f = reinterpret_cast<u32*>(sym[j]);
         for (int i = lane; i < 256; i += 32)
-            f[i] = scr[i] + scr[256 + i] + scr[512 + i] + scr[768 + i];
+            f[i] = hk[0][i] + hk[1][i] + hk[2][i] + hk[3][i];
         __syncwarp();
     }
 
@@ -107,16 +113,16 @@ ans0_encode_kernel(BufTable bt, const BlkState* __restrict__ st, int nBlocks, in
         put_chunk_header(w, f, asz, ANS0_LR);
         if (asz > 1) {
             active = 1;
-            u16* cum = reinterpret_cast<u16*>(scr) + (j << 8);
-            u32 run = 0;
-            for (int i = 0; i < 256; i++) {
-                cum[i] = (u16)run;
-                run += f[i];
-            }
-            // descending: entry i overwrites histogram words 2i, 2i+1 (both >= i, already consumed)
+            u32 total = 0;
+            for (int i = 0; i < 256; i++)
+                total += f[i];
+            // descending: entry i overwrites histogram words 2i, 2i+1 (both >= i, already consumed);
+            // cumulative frequency of i = total - sum of the frequencies >= i
+            u32 run = total;
             for (int i = 255; i >= 0; i--) {
                 const u32 fr = f[i];
-                sym[j][i] = (fr == 0) ? 0ull : make_enc_entry((int)cum[i], (int)fr, ANS0_LR);
+                run -= fr;
+                sym[j][i] = (fr == 0) ? 0ull : make_enc_entry((int)run, (int)fr, ANS0_LR);
             }
         }
     }
@@ -132,47 +138,55 @@ ans0_encode_kernel(BufTable bt, const BlkState* __restrict__ st, int nBlocks, in
         maxSteps = max(maxSteps, __shfl_xor_sync(FULL_MASK, maxSteps, o));
 
     const u32* __restrict__ words = reinterpret_cast<const u32*>(src + (i64)(valid ? c : 0) * ANS_CHUNK);
+    const u64* __restrict__ tab = sym[j];
     u32 state = 1u << 15; // ANS_TOP
     u32 cnt = 0;
     u16* wend = reinterpret_cast<u16*>(slot + ANS_WEND);
     const int bsh = 8 * (3 - k);
+    const u32 below = (1u << k) - 1u;
+    const int qsh = lane & ~3;
     const int wtop = (end4 >> 2) - 1; // step s consumes word wtop - s (the quad's 4 bytes)
-    // Software pipeline: the words of step group g+2 are requested while group g is
-    // encoded, so the L2 latency of the (quad-broadcast) loads stays off the serial
-    // state-update chain.
-    u32 wa[4], wb[4], wc[4];
-#pragma unroll
-    for (int x = 0; x < 4; x++) {
-        wa[x] = (x < steps) ? __ldg(&words[wtop - x]) : 0u;
-        wb[x] = (4 + x < steps) ? __ldg(&words[wtop - 4 - x]) : 0u;
-    }
+    // Software pipeline, 4 steps (16 input bytes per quad) per group, two groups ahead.
+    // Full chunks are 16-byte aligned from the top, so a group is one 128-bit load.
+    const bool vec = (end4 & 15) == 0;
+    uint4 ga = make_uint4(0, 0, 0, 0), gb = ga, gc = ga;
+    auto fetch = [&](int s0) -> uint4 {
+        uint4 r = make_uint4(0, 0, 0, 0);
+        if (s0 + 3 < steps && vec) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(words + (wtop - s0 - 3)));
+            r = make_uint4(v.w, v.z, v.y, v.x); // .x = word of step s0
+        } else {
+            if (s0 < steps)
+                r.x = __ldg(&words[wtop - s0]);
+            if (s0 + 1 < steps)
+                r.y = __ldg(&words[wtop - s0 - 1]);
+            if (s0 + 2 < steps)
+                r.z = __ldg(&words[wtop - s0 - 2]);
+            if (s0 + 3 < steps)
+                r.w = __ldg(&words[wtop - s0 - 3]);
+        }
+        return r;
+    };
+    ga = fetch(0);
+    gb = fetch(4);
     for (int s0 = 0; s0 < maxSteps; s0 += 4) {
-#pragma unroll
-        for (int x = 0; x < 4; x++)
-            wc[x] = (s0 + 8 + x < steps) ? __ldg(&words[wtop - s0 - 8 - x]) : 0u;
+        gc = fetch(s0 + 8);
+        const u32 wv[4] = { ga.x, ga.y, ga.z, ga.w };
 #pragma unroll
         for (int x = 0; x < 4; x++) {
-            const int s = s0 + x;
             bool did = false;
             u32 word = 0;
-            if (s < steps) {
-                const u32 cb = (wa[x] >> bsh) & 0xFF;
-                state = enc_step(state, sym[j][cb], ANS0_LR, &did, &word);
+            if (s0 + x < steps) {
+                const u32 cb = (wv[x] >> bsh) & 0xFF;
+                state = enc_step(state, tab[cb], ANS0_LR, &did, &word);
             }
-            const u32 bal = __ballot_sync(FULL_MASK, did);
-            const u32 qb = (bal >> (lane & ~3)) & 0xF;
-            if (did) {
-                const u32 idx = cnt + __popc(qb & ((1u << k) - 1u));
-                // memory order [hi][lo] (ANSRangeEncoder.hpp:122-126)
-                *(wend - 1 - idx) = (u16)(((word & 0xFF) << 8) | (word >> 8));
-            }
+            const u32 qb = (__ballot_sync(FULL_MASK, did) >> qsh) & 0xF;
+            if (did) // memory order [hi][lo] (ANSRangeEncoder.hpp:122-126)
+                wend[-1 - (int)(cnt + __popc(qb & below))] = (u16)__byte_perm(word, 0, 0x4401);
             cnt += __popc(qb);
         }
-#pragma unroll
-        for (int x = 0; x < 4; x++) {
-            wa[x] = wb[x];
-            wb[x] = wc[x];
-        }
+        ga = gb;
+        gb = gc;
     }
 
     // ---- epilogue: varint size, 4 states, tail bytes

@@ -320,9 +320,9 @@ sbrt_rank_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkState*
 // step: one warp per block, the list distributed over the lanes in registers
 // (RankList), no shared memory, no divergence; zero words (runs of rank 0) take a
 // closed form; input/output travel through registers 128 bytes at a time.
-template <class PB>
+template <class PB, int MODE>
 __global__ void __launch_bounds__(32)
-sbrt_inverse_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkState* __restrict__ stOut, int mode)
+sbrt_inverse_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkState* __restrict__ stOut)
 {
     const int b = blockIdx.x;
     const BlkState bs = stIn[b];
@@ -332,15 +332,17 @@ sbrt_inverse_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkSta
     const int lane = threadIdx.x;
     const u8* __restrict__ src = blk_src(bt, bs, b);
     u8* __restrict__ dst = blk_dst(bt, bs, b);
-    u32 m1, m2;
-    int sh;
-    sbrt_masks(mode, m1, m2, sh);
+    // key of an access at time i to a symbol last seen at time pc (SBRT.cpp:79)
+    auto keyOf = [](u32 i, u32 pc) -> int {
+        return (MODE == 1) ? (int)i : (MODE == 2) ? (int)((i + pc) >> 1) : (int)pc;
+    };
     RankList<PB> L;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         L.q[k] = 0;
         L.pb[k] = (PB)(32 * k + lane);
     }
+    const bool lane0 = lane == 0;
     const u32* __restrict__ src4 = reinterpret_cast<const u32*>(src); // buffers are 16-byte aligned
     const int groups = (n + 127) >> 7;
     u32 nextw = 0;
@@ -375,32 +377,39 @@ sbrt_inverse_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkSta
                 const PB e = __shfl_sync(FULL_MASK, L.pb[0], 0);
                 const u32 c = (u32)(e & 0xFF);
                 const u32 i3 = (u32)(base + j + 3);
-                if (lane == 0) {
-                    L.q[0] = (int)(((i3 & m1) + ((i3 - 1) & m2)) >> sh);
+                if (lane0) {
+                    L.q[0] = keyOf(i3, i3 - 1);
                     L.pb[0] = ((PB)i3 << 8) | (PB)c;
                 }
                 o4 = c * 0x01010101u;
+            } else if (lim == 4 && (w4 & 0xE0E0E0E0u) == 0) {
+                // all four ranks < 32: branch-free top-of-list path
+#pragma unroll
+                for (int x = 0; x < 4; x++) {
+                    const int r = (int)((w4 >> (8 * x)) & 0xFF);
+                    const u32 i = (u32)(base + j + x);
+                    const int nq = __shfl_up_sync(FULL_MASK, L.q[0], 1);
+                    const PB npb = __shfl_up_sync(FULL_MASK, L.pb[0], 1);
+                    const PB e = __shfl_sync(FULL_MASK, L.pb[0], r);
+                    const u32 c = (u32)(e & 0xFF);
+                    const int qc = keyOf(i, (u32)(e >> 8));
+                    o4 |= c << (8 * x);
+                    const bool below = lane <= r;
+                    const bool mv = below && !lane0 && (nq <= qc);
+                    const bool ins = below && (L.q[0] <= qc) && (lane0 || (nq > qc));
+                    const PB ne = ((PB)i << 8) | (PB)c;
+                    L.q[0] = ins ? qc : (mv ? nq : L.q[0]);
+                    L.pb[0] = ins ? ne : (mv ? npb : L.pb[0]);
+                }
             } else {
                 for (int x = 0; x < lim; x++) {
                     const int r = (int)((w4 >> (8 * x)) & 0xFF);
                     const u32 i = (u32)(base + j + x);
-                    if (r < 32) {
-                        const int nq = __shfl_up_sync(FULL_MASK, L.q[0], 1);
-                        const PB npb = __shfl_up_sync(FULL_MASK, L.pb[0], 1);
-                        const PB e = __shfl_sync(FULL_MASK, L.pb[0], r);
-                        const u32 c = (u32)(e & 0xFF);
-                        const u32 pc = (u32)(e >> 8);
-                        const int qc = (int)(((i & m1) + (pc & m2)) >> sh);
-                        o4 |= c << (8 * x);
-                        L.move_up_top(r, qc, ((PB)i << 8) | (PB)c, lane, nq, npb);
-                    } else {
-                        const PB e = L.entry_at(r);
-                        const u32 c = (u32)(e & 0xFF);
-                        const u32 pc = (u32)(e >> 8);
-                        const int qc = (int)(((i & m1) + (pc & m2)) >> sh);
-                        o4 |= c << (8 * x);
-                        L.move_up(r, qc, ((PB)i << 8) | (PB)c, lane);
-                    }
+                    const PB e = L.entry_at(r);
+                    const u32 c = (u32)(e & 0xFF);
+                    const int qc = keyOf(i, (u32)(e >> 8));
+                    o4 |= c << (8 * x);
+                    L.move_up(r, qc, ((PB)i << 8) | (PB)c, lane);
                 }
             }
             if (lane == (j >> 2))
@@ -440,9 +449,17 @@ void launch_sbrt_inverse(const StageLaunch& L, int mode, Workspace& ws, cudaStre
 {
     (void)ws;
     KLAUNCH(sbrt_decide_kernel, (L.nBlocks + 31) / 32, 32, s, L, 1);
-    if (L.maxLen < (1 << 24))
-        KLAUNCH(sbrt_inverse_kernel<u32>, L.nBlocks, 32, s, L.bt, L.stIn, L.stOut, mode);
-    else
-        KLAUNCH(sbrt_inverse_kernel<u64>, L.nBlocks, 32, s, L.bt, L.stIn, L.stOut, mode);
+    const bool small = L.maxLen < (1 << 24);
+    if (mode == 1) {
+        if (small)
+            KLAUNCH((sbrt_inverse_kernel<u32, 1>), L.nBlocks, 32, s, L.bt, L.stIn, L.stOut);
+        else
+            KLAUNCH((sbrt_inverse_kernel<u64, 1>), L.nBlocks, 32, s, L.bt, L.stIn, L.stOut);
+    } else {
+        if (small)
+            KLAUNCH((sbrt_inverse_kernel<u32, 2>), L.nBlocks, 32, s, L.bt, L.stIn, L.stOut);
+        else
+            KLAUNCH((sbrt_inverse_kernel<u64, 2>), L.nBlocks, 32, s, L.bt, L.stIn, L.stOut);
+    }
     *launches += 2;
 }

@@ -630,6 +630,418 @@ static int ans_decode(BitR* r, u8* block, u32 count, int order)
     return rc;
 }
 
+/* ------------------------------------------------------------------ Huffman
+ * entropy/HuffmanEncoder.cpp:58-126 updateFrequencies, :129-215 limitCodeLengths,
+ * :219-300 computeCodeLengths (Moffat-Katajainen in-place), :304-421 encode /
+ * encodeChunk; entropy/HuffmanCommon.cpp:29-63 generateCanonicalCodes;
+ * entropy/ExpGolombEncoder.hpp:51-62 (signed exp-Golomb of the code-length deltas);
+ * decoder entropy/HuffmanDecoder.cpp:65-108 readLengths, :156-201 decodeV6,
+ * :204-347 decodeChunk.  Chunk 16 KiB, codes <= 12 bits, 4 fragments per chunk.   */
+#define HUF_MAX_LEN 12
+#define HUF_CHUNK 16384
+
+/* signed exp-Golomb: '1' for 0; else floor(log2(|v|+1)) zeros, (|v|+1) in binary, sign bit */
+static void put_expgolomb_signed(BitW* w, int v)
+{
+    if (v == 0) {
+        bw_put(w, 1, 1);
+        return;
+    }
+    const u32 x = (u32)(v < 0 ? -v : v) + 1;
+    const int lg = ilog2(x);
+    bw_put(w, 0, lg);
+    bw_put(w, x, lg + 1);
+    bw_put(w, (u64)(v < 0 ? 1 : 0), 1);
+}
+
+static int get_expgolomb_signed(BitR* r) /* ExpGolombDecoder.hpp:52-75 */
+{
+    if (br_get(r, 1) == 1)
+        return 0;
+    u32 lg = 1;
+    while (br_get(r, 1) == 0 && !r->underflow)
+        lg++;
+    lg &= 7;
+    int res = (int)br_get(r, (int)lg + 1);
+    const int sgn = res & 1;
+    res = (res >> 1) + (1 << lg) - 1;
+    return (int)(int8_t)((res - sgn) ^ -sgn);
+}
+
+static int cmp_u32(const void* a, const void* b)
+{
+    const u32 x = *(const u32*)a, y = *(const u32*)b;
+    return (x > y) - (x < y);
+}
+
+/* computeCodeLengths: ranks[] = (freq << 8) | symbol, sorted increasing; sizes by symbol */
+static int huf_code_lengths(uint16_t* sizes, u32* ranks, int count)
+{
+    qsort(ranks, (size_t)count, sizeof(u32), cmp_u32);
+    u32 d[256] = { 0 };
+    for (int i = 0; i < count; i++) {
+        d[i] = ranks[i] >> 8;
+        ranks[i] &= 0xFF;
+        if (d[i] == 0)
+            return 0;
+    }
+    const int n = count;
+    /* phase 1 */
+    for (int s = 0, rr = 0, t = 0; t < n - 1; t++) {
+        u32 sum = 0;
+        for (int i = 0; i < 2; i++) {
+            if (s >= n || (rr < t && d[rr] < d[s])) {
+                sum += d[rr];
+                d[rr] = (u32)t;
+                rr++;
+                continue;
+            }
+            sum += d[s];
+            if (s > t)
+                d[s] = 0;
+            s++;
+        }
+        d[t] = sum;
+    }
+    /* phase 2 */
+    u32 topLevel = (u32)n - 2, depth = 1, totalNodes = 2;
+    int m = n;
+    while (m > 0) {
+        u32 k = topLevel;
+        while (k != 0 && d[k - 1] >= topLevel)
+            k--;
+        const int internal = (int)(topLevel - k);
+        const int leaves = (int)totalNodes - internal;
+        for (int j = 0; j < leaves; j++)
+            d[--m] = depth;
+        totalNodes = (u32)internal << 1;
+        topLevel = k;
+        depth++;
+    }
+    for (int i = 0; i < count; i++)
+        sizes[ranks[i]] = (uint16_t)d[i];
+    return (int)depth - 1;
+}
+
+/* EntropyUtils::normalizeFrequencies with an explicit array length (used by the
+ * length limiter with length = alphabet size, EntropyUtils.cpp:131-245).          */
+static int normalize_freqs_n(u32* freqs, u32* alphabet, int length, u32 total, u32 scale)
+{
+    if (length == 0 || total == 0)
+        return 0;
+    int asz = 0;
+    if (total == scale) {
+        for (int i = 0; i < 256; i++)
+            if (freqs[i] != 0)
+                alphabet[asz++] = (u32)i;
+        return asz;
+    }
+    u32 sumScaled = 0, sumFreq = 0;
+    int idxMax = 0;
+    for (int i = 0; i < length; i++) {
+        alphabet[i] = 0;
+        const u32 f = freqs[i];
+        if (f == 0)
+            continue;
+        alphabet[asz++] = (u32)i;
+        const i64 sf = (i64)f * (i64)scale;
+        const u32 sc = (sf <= (i64)total) ? 1u : (u32)((sf + ((i64)total >> 1)) / (i64)total);
+        sumScaled += sc;
+        freqs[i] = sc;
+        sumFreq += f;
+        if (sc > freqs[idxMax])
+            idxMax = i;
+        if (sumFreq >= total)
+            break;
+    }
+    if (asz == 0)
+        return 0;
+    if (asz == 1) {
+        freqs[alphabet[0]] = scale;
+        return 1;
+    }
+    if (sumScaled == scale)
+        return asz;
+    int delta = (int)(sumScaled - scale);
+    const int errThr = (int)freqs[idxMax] >> 4;
+    if (abs(delta) <= errThr) {
+        freqs[idxMax] -= (u32)delta;
+        return asz;
+    }
+    if (delta < 0) {
+        delta += errThr;
+        freqs[idxMax] += (u32)errThr;
+    } else {
+        delta -= errThr;
+        freqs[idxMax] -= (u32)errThr;
+    }
+    const int inc = (delta < 0) ? 1 : -1;
+    delta = abs(delta);
+    int round = 0;
+    while ((++round < 6) && (delta > 0)) {
+        int adjustments = 0;
+        for (int i = 0; i < asz; i++) {
+            const u32 idx = alphabet[i];
+            if (freqs[idx] <= 2)
+                continue;
+            freqs[idx] += (u32)inc;
+            adjustments++;
+            delta--;
+            if (delta == 0)
+                break;
+        }
+        if (adjustments == 0)
+            break;
+    }
+    {
+        const u32 v = freqs[idxMax] - (u32)delta;
+        freqs[idxMax] = (v > 1u) ? v : 1u;
+    }
+    return asz;
+}
+
+/* limitCodeLengths: ranks[] now holds symbols sorted by increasing frequency */
+static int huf_limit_lengths(const u32* alphabet, u32* freqs, uint16_t* sizes, u32* ranks, int count)
+{
+    int n = 0, debt = 0;
+    while (n < count && sizes[ranks[n]] >= HUF_MAX_LEN) {
+        debt += sizes[ranks[n]] - HUF_MAX_LEN;
+        sizes[ranks[n]] = HUF_MAX_LEN;
+        n++;
+    }
+    if (debt == 0)
+        return HUF_MAX_LEN;
+    int v[6][256], vn[6] = { 0 }, vh[6] = { 0 };
+    while (n < count) {
+        const int idx = HUF_MAX_LEN - 1 - sizes[ranks[n]];
+        if (idx > 5 || debt < (1 << idx))
+            break;
+        v[idx][vn[idx]++] = n;
+        n++;
+    }
+    int idx = 5;
+    while (debt > 0 && idx >= 0) {
+        if (vh[idx] >= vn[idx] || debt < (1 << idx)) {
+            idx--;
+            continue;
+        }
+        sizes[ranks[v[idx][vh[idx]]]]++;
+        debt -= 1 << idx;
+        vh[idx]++;
+    }
+    idx = 0;
+    while (debt > 0 && idx < 6) {
+        if (vh[idx] >= vn[idx]) {
+            idx++;
+            continue;
+        }
+        sizes[ranks[v[idx][vh[idx]]]]++;
+        debt -= 1 << idx;
+        vh[idx]++;
+    }
+    if (debt > 0) {
+        u32 alpha[256] = { 0 }, f[256] = { 0 }, total = 0;
+        for (int i = 0; i < count; i++) {
+            f[i] = freqs[alphabet[i]];
+            total += f[i];
+        }
+        normalize_freqs_n(f, alpha, count, total, HUF_CHUNK >> 3);
+        for (int i = 0; i < count; i++) {
+            freqs[alphabet[i]] = f[i];
+            ranks[i] = (f[i] << 8) | alphabet[i];
+        }
+        return huf_code_lengths(sizes, ranks, count);
+    }
+    return HUF_MAX_LEN;
+}
+
+/* generateCanonicalCodes: symbols ordered by (length, symbol) get consecutive codes */
+static int huf_canonical(const uint16_t* sizes, uint16_t* codes, u32* symbols, int count)
+{
+    if (count == 0)
+        return 0;
+    if (count > 1) {
+        u8 present[(HUF_MAX_LEN << 8) + 256];
+        memset(present, 0, sizeof(present));
+        for (int i = 0; i < count; i++) {
+            const u32 sy = symbols[i];
+            if (sy > 255 || sizes[sy] > HUF_MAX_LEN || sizes[sy] == 0)
+                return -1;
+            present[((sizes[sy] - 1) << 8) | sy] = 1;
+        }
+        for (int i = 0, n = 0; n < count; i++) {
+            symbols[n] = (u32)(i & 0xFF);
+            n += present[i];
+        }
+    }
+    int curLen = sizes[symbols[0]];
+    for (int i = 0, code = 0; i < count; i++) {
+        const u32 sy = symbols[i];
+        code <<= (sizes[sy] - curLen);
+        curLen = sizes[sy];
+        codes[sy] = (uint16_t)code;
+        code++;
+    }
+    return count;
+}
+
+/* updateFrequencies: writes alphabet + length deltas, fills codes[] = (len << 12) | code */
+static int huf_update(BitW* w, u32* freqs, uint16_t* codes)
+{
+    int count = 0;
+    uint16_t sizes[256] = { 0 };
+    u32 alphabet[256] = { 0 };
+    for (int i = 0; i < 256; i++) {
+        codes[i] = 0;
+        if (freqs[i] > 0)
+            alphabet[count++] = (u32)i;
+    }
+    put_alphabet(w, alphabet, count);
+    if (count == 0)
+        return 0;
+    if (count == 1) {
+        codes[alphabet[0]] = 1 << 12;
+        sizes[alphabet[0]] = 1;
+    } else {
+        u32 ranks[256];
+        for (int i = 0; i < count; i++)
+            ranks[i] = (freqs[alphabet[i]] << 8) | alphabet[i];
+        int maxLen = huf_code_lengths(sizes, ranks, count);
+        if (maxLen > HUF_MAX_LEN)
+            maxLen = huf_limit_lengths(alphabet, freqs, sizes, ranks, count);
+        if (maxLen > HUF_MAX_LEN) {
+            for (int i = 0; i < count; i++) {
+                codes[alphabet[i]] = (uint16_t)i;
+                sizes[alphabet[i]] = 8;
+            }
+        } else {
+            huf_canonical(sizes, codes, ranks, count);
+        }
+    }
+    int prev = 2;
+    for (int i = 0; i < count; i++) {
+        const u32 sy = alphabet[i];
+        codes[sy] |= (uint16_t)(sizes[sy] << 12);
+        put_expgolomb_signed(w, (int)(int8_t)(sizes[sy] - prev));
+        prev = sizes[sy];
+    }
+    return count;
+}
+
+static void huf_encode(BitW* w, const u8* block, u32 count)
+{
+    uint16_t codes[256];
+    u32 start = 0;
+    while (start < count) {
+        const u32 sz = (HUF_CHUNK < count - start) ? HUF_CHUNK : count - start;
+        const u8* b = block + start;
+        if (sz < 32) {
+            bw_put_bytes(w, b, 8 * (i64)sz);
+        } else {
+            u32 freqs[256] = { 0 };
+            for (u32 i = 0; i < sz; i++)
+                freqs[b[i]]++;
+            if (huf_update(w, freqs, codes) > 1) {
+                /* encodeChunk: 4 fragments of sz/4 symbols, each its own bit string */
+                const u32 frag = sz / 4;
+                u32 nbits[4];
+                for (int j = 0; j < 4; j++) {
+                    u32 bits = 0;
+                    for (u32 i = 0; i < frag; i++)
+                        bits += codes[b[j * frag + i]] >> 12;
+                    nbits[j] = bits;
+                }
+                for (int j = 0; j < 4; j++)
+                    put_varint(w, nbits[j]);
+                for (int j = 0; j < 4; j++)
+                    for (u32 i = 0; i < frag; i++) {
+                        const uint16_t c = codes[b[j * frag + i]];
+                        bw_put(w, (u64)(c & 0x0FFF), c >> 12);
+                    }
+                for (u32 i = 4 * frag; i < sz; i++)
+                    bw_put(w, b[i], 8);
+            }
+        }
+        start += sz;
+    }
+}
+
+static int huf_decode(BitR* r, u8* block, u32 count)
+{
+    u32 start = 0;
+    while (start < count) {
+        const u32 sz = (HUF_CHUNK < count - start) ? HUF_CHUNK : count - start;
+        u8* out = block + start;
+        if (sz < 32) {
+            br_get_bytes(r, out, sz);
+            start += sz;
+            continue;
+        }
+        u32 alphabet[256];
+        uint16_t sizes[256] = { 0 }, codes[256] = { 0 };
+        const int asz = get_alphabet(r, alphabet);
+        if (asz <= 0)
+            return (int)start;
+        int cur = 2;
+        for (int i = 0; i < asz; i++) {
+            cur += get_expgolomb_signed(r);
+            cur = (int)(int8_t)cur;
+            if (cur <= 0 || cur > HUF_MAX_LEN)
+                return -1;
+            sizes[alphabet[i]] = (uint16_t)cur;
+        }
+        if (asz == 1) {
+            memset(out, (int)alphabet[0], sz);
+            start += sz;
+            continue;
+        }
+        if (huf_canonical(sizes, codes, alphabet, asz) < 0)
+            return -1;
+        /* 12-bit direct table: (symbol << 8) | length */
+        static uint16_t table[1 << HUF_MAX_LEN];
+        memset(table, 0, sizeof(table));
+        for (int i = 0; i < asz; i++) {
+            const u32 sy = alphabet[i];
+            const int wdt = 1 << (HUF_MAX_LEN - sizes[sy]);
+            const int idx = codes[sy] * wdt;
+            if (idx + wdt > (1 << HUF_MAX_LEN))
+                return -1;
+            for (int k = 0; k < wdt; k++)
+                table[idx + k] = (uint16_t)((sy << 8) | sizes[sy]);
+        }
+        u32 nbits[4];
+        for (int j = 0; j < 4; j++)
+            if (get_varint(r, &nbits[j]) < 0)
+                return -1;
+        const u32 frag = sz / 4;
+        for (int j = 0; j < 4; j++) {
+            const i64 fragEnd = r->pos + nbits[j];
+            for (u32 i = 0; i < frag; i++) {
+                /* peek 12 bits (zero padded past the fragment) */
+                u32 v = 0;
+                for (int k = 0; k < HUF_MAX_LEN; k++) {
+                    const i64 p = r->pos + k;
+                    u32 bit = 0;
+                    if (p < fragEnd && p < r->nbits)
+                        bit = (r->buf[p >> 3] >> (7 - (p & 7))) & 1;
+                    v = (v << 1) | bit;
+                }
+                const uint16_t e = table[v];
+                if ((e & 0xFF) == 0)
+                    return -1;
+                out[j * frag + i] = (u8)(e >> 8);
+                r->pos += e & 0xFF;
+            }
+            if (r->pos != fragEnd)
+                return -1;
+        }
+        for (u32 i = 4 * frag; i < sz; i++)
+            out[i] = (u8)br_get(r, 8);
+        start += sz;
+    }
+    return (int)count;
+}
+
 /* ------------------------------------------------------------------ ZRLT
  * transform/ZRLT.cpp:27-117 forward.  Returns 1 (ok), 0 (stage refused).     */
 static int zrlt_forward(const u8* src, int n, u8* dst, int cap, int* outLen)
@@ -1181,7 +1593,7 @@ static int sequence_inverse(u64 ttype, int skipFlags, const u8* in, int n, u8* o
 
 /* ------------------------------------------------------------------ blocks
  * entropy ids: entropy/EntropyEncoderFactory.hpp:37-52.                      */
-enum { E_NONE = 0, E_ANS0 = 5, E_ANS1 = 8 };
+enum { E_NONE = 0, E_HUFFMAN = 1, E_ANS0 = 5, E_ANS1 = 8 };
 
 static int entropy_encode(BitW* w, int etype, const u8* p, u32 n)
 {
@@ -1194,6 +1606,9 @@ static int entropy_encode(BitW* w, int etype, const u8* p, u32 n)
         return 0;
     case E_ANS1:
         ans_encode(w, p, n, 1);
+        return 0;
+    case E_HUFFMAN:
+        huf_encode(w, p, n);
         return 0;
     default:
         return -1;
@@ -1210,6 +1625,8 @@ static int entropy_decode(BitR* r, int etype, u8* p, u32 n)
         return ans_decode(r, p, n, 0);
     case E_ANS1:
         return ans_decode(r, p, n, 1);
+    case E_HUFFMAN:
+        return huf_decode(r, p, n);
     default:
         return -1;
     }

@@ -10,7 +10,7 @@ from cases import small_cases, rng_bytes
 CASES = small_cases()
 
 
-@pytest.mark.parametrize("ename", ["ANS0", "ANS1", "NONE"])
+@pytest.mark.parametrize("ename", ["ANS0", "ANS1", "NONE", "HUFFMAN"])
 def test_entropy_encode_matches_ref(oracle, ref, ename):
     for name, data in CASES.items():
         if data.size == 0:
@@ -53,7 +53,8 @@ def test_bwt_matches_ref(oracle, ref):
 
 
 @pytest.mark.parametrize("tname,ename", [("NONE", "ANS0"), ("BWT+RANK+ZRLT", "ANS0"), ("NONE", "NONE"),
-                                         ("BWT", "ANS1"), ("ZRLT", "ANS0"), ("BWT+MTFT+ZRLT", "ANS0")])
+                                         ("BWT", "ANS1"), ("ZRLT", "ANS0"), ("BWT+MTFT+ZRLT", "ANS0"),
+                                         ("NONE", "HUFFMAN"), ("BWT+RANK+ZRLT", "HUFFMAN")])
 def test_stream_matches_ref(oracle, ref, tname, ename):
     inputs = {
         "comp_300k": synth.synth_compressible(300000, 21),

@@ -41,6 +41,7 @@ extern "C" {
 #define KNZ_T_RANK 8
 /* Entropy ids: entropy/EntropyEncoderFactory.hpp:37-52 */
 #define KNZ_E_NONE 0
+#define KNZ_E_HUFFMAN 1
 #define KNZ_E_ANS0 5
 
 typedef struct knz_ctx knz_ctx;

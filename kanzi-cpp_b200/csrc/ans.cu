@@ -431,6 +431,8 @@ void launch_entropy_encode(const EncodeLaunch& L, cudaStream_t s, u64* launches)
     const int nB = L.nBlocks;
     if (L.eType == E_RAW) {
         KLAUNCH(raw_meta_kernel, (nB + 127) / 128, 128, s, L.st, nB, L.maxChunks, L.hdrBits, L.payBytes, L.payOff);
+    } else if (L.eType == E_HUF) {
+        launch_huffman_encode_chunks(L, s, launches);
     } else {
         const int groups = (L.maxChunks + 7) / 8;
         const i64 warps = (i64)nB * groups;
@@ -750,6 +752,10 @@ ans0_decode_kernel(DecodeLaunch L)
 
 void launch_entropy_decode(const DecodeLaunch& L, cudaStream_t s, u64* launches)
 {
+    if (L.eType == E_HUF) {
+        launch_huffman_decode(L, s, launches);
+        return;
+    }
     KLAUNCH(ans0_dec_scan_kernel, (L.nBlocks + 31) / 32, 32, s, L);
     const int groups = (L.maxChunks + 7) / 8;
     if (L.evK0)

@@ -124,6 +124,8 @@ extern "C" int knz_entropy_type(const char* name)
         return E_RAW;
     if (!strcmp(name, "ANS0"))
         return E_ANS0;
+    if (!strcmp(name, "HUFFMAN"))
+        return E_HUF;
     return -1;
 }
 
@@ -265,7 +267,7 @@ static int encode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const
             snprintf(ctx->err, sizeof(ctx->err), "transform id %d not implemented", types[i]);
             return KNZ_ERR_INVALID_CODEC;
         }
-    if (eType != E_RAW && eType != E_ANS0) {
+    if (eType != E_RAW && eType != E_ANS0 && eType != E_HUF) {
         snprintf(ctx->err, sizeof(ctx->err), "entropy id %d not implemented", eType);
         return KNZ_ERR_INVALID_CODEC;
     }
@@ -369,7 +371,7 @@ static int encode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const
     ctx->ms[3] = ms;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]);
     ctx->ms[5] = ms;
-    if (eType == E_ANS0) {
+    if (eType == E_ANS0 || eType == E_HUF) {
         cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]);
         ctx->ms[6] = ms;
     }
@@ -689,7 +691,7 @@ static int decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const
     for (int i = 0; i < nt; i++)
         if (!type_supported(types[i]))
             return KNZ_ERR_INVALID_CODEC;
-    if (eType != E_RAW && eType != E_ANS0)
+    if (eType != E_RAW && eType != E_ANS0 && eType != E_HUF)
         return KNZ_ERR_INVALID_CODEC;
     if (nB > ctx->maxBatch)
         return KNZ_ERR_INVALID_PARAM;
@@ -1165,7 +1167,7 @@ extern "C" int knz_entropy_encode(knz_ctx* ctx, int type, const uint8_t* in, int
 {
     if (!ctx || !in || !out || !outBits || n <= 0)
         return KNZ_ERR_INVALID_PARAM;
-    if (type != E_RAW && type != E_ANS0)
+    if (type != E_RAW && type != E_ANS0 && type != E_HUF)
         return KNZ_ERR_INVALID_CODEC;
     if ((i64)n + 64 > ctx->bstride)
         return KNZ_ERR_BLOCK_SIZE;
@@ -1222,7 +1224,7 @@ extern "C" int knz_entropy_decode(knz_ctx* ctx, int type, const uint8_t* in, int
 {
     if (!ctx || !in || !out || n <= 0 || inBits < 0)
         return KNZ_ERR_INVALID_PARAM;
-    if (type != E_RAW && type != E_ANS0)
+    if (type != E_RAW && type != E_ANS0 && type != E_HUF)
         return KNZ_ERR_INVALID_CODEC;
     const i64 nbytes = (inBits + 7) >> 3;
     if ((i64)n + 64 > ctx->bstride || nbytes + 16 > ctx->outStride)

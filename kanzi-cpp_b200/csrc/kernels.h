@@ -11,6 +11,7 @@
 #define ANS_SLOT (ANS_WEND + 512)
 
 #define E_RAW 0
+#define E_HUF 1
 #define E_ANS0 5
 
 #define T_NONE 0
@@ -59,6 +60,8 @@ struct DecodeLaunch {
     cudaEvent_t evK0, evK1; // optional: bracket the rANS decode kernel alone
 };
 void launch_entropy_decode(const DecodeLaunch& L, cudaStream_t s, u64* launches);
+void launch_huffman_encode_chunks(const EncodeLaunch& L, cudaStream_t s, u64* launches);
+void launch_huffman_decode(const DecodeLaunch& L, cudaStream_t s, u64* launches);
 
 // Transform stages.  Every launcher reads st[s] and writes st[s+1].
 struct StageLaunch {

@@ -200,11 +200,15 @@ struct RankList {
 
 // 3. replay: one warp per tile, exact list algorithm started from the tile's entry table
 #define R_WARPS 4
-template <class PB>
+template <class PB, int MODE>
 __global__ void __launch_bounds__(R_WARPS * 32)
 sbrt_rank_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkState* __restrict__ stOut, int maxTiles,
-                 const uint2* __restrict__ occ, int mode)
+                 const uint2* __restrict__ occ)
 {
+    const int mode = MODE;
+    auto keyOf = [](u32 i, u32 pc) -> int {
+        return (MODE == 1) ? (int)i : (MODE == 2) ? (int)((i + pc) >> 1) : (int)pc;
+    };
     __shared__ u64 s_keys[R_WARPS][256];
     __shared__ u64 s_ent[R_WARPS][256]; // (q << 32 | pb) by rank, only while the list is built
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -287,14 +291,14 @@ sbrt_rank_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkState*
                 if (m) {
                     const u32 pc = __reduce_or_sync(FULL_MASK, hit ? (u32)(L.pb[0] >> 8) : 0u);
                     const int r = __ffs(m) - 1;
-                    const int qc = (int)(((i & m1) + (pc & m2)) >> sh);
+                    const int qc = keyOf(i, pc);
                     o4 |= (u32)r << (8 * x);
                     L.move_up_top(r, qc, ((PB)i << 8) | (PB)c, lane, nq, npb);
                 } else {
                     const int r = L.find(c);
                     const PB e = L.entry_at(r);
                     const u32 pc = (u32)(e >> 8);
-                    const int qc = (int)(((i & m1) + (pc & m2)) >> sh);
+                    const int qc = keyOf(i, pc);
                     o4 |= (u32)r << (8 * x);
                     L.move_up(r, qc, ((PB)i << 8) | (PB)c, lane);
                 }
@@ -436,12 +440,19 @@ void launch_sbrt_forward(const StageLaunch& L, int mode, Workspace& ws, cudaStre
     KLAUNCH(sbrt_decide_kernel, (L.nBlocks + 31) / 32, 32, s, L, 0);
     KLAUNCH(sbrt_occ_kernel, dim3(tiles, L.nBlocks), 256, s, L.bt, L.stIn, L.stOut, maxTiles, occ);
     KLAUNCH(sbrt_fold_kernel, L.nBlocks, 256, s, L.stIn, L.stOut, maxTiles, occ);
-    if (L.maxLen < (1 << 24))
-        KLAUNCH(sbrt_rank_kernel<u32>, dim3((tiles + R_WARPS - 1) / R_WARPS, L.nBlocks), R_WARPS * 32, s, L.bt, L.stIn,
-                L.stOut, maxTiles, occ, mode);
-    else
-        KLAUNCH(sbrt_rank_kernel<u64>, dim3((tiles + R_WARPS - 1) / R_WARPS, L.nBlocks), R_WARPS * 32, s, L.bt, L.stIn,
-                L.stOut, maxTiles, occ, mode);
+    const dim3 rg((tiles + R_WARPS - 1) / R_WARPS, L.nBlocks);
+    const bool small = L.maxLen < (1 << 24);
+    if (mode == 1) {
+        if (small)
+            KLAUNCH((sbrt_rank_kernel<u32, 1>), rg, R_WARPS * 32, s, L.bt, L.stIn, L.stOut, maxTiles, occ);
+        else
+            KLAUNCH((sbrt_rank_kernel<u64, 1>), rg, R_WARPS * 32, s, L.bt, L.stIn, L.stOut, maxTiles, occ);
+    } else {
+        if (small)
+            KLAUNCH((sbrt_rank_kernel<u32, 2>), rg, R_WARPS * 32, s, L.bt, L.stIn, L.stOut, maxTiles, occ);
+        else
+            KLAUNCH((sbrt_rank_kernel<u64, 2>), rg, R_WARPS * 32, s, L.bt, L.stIn, L.stOut, maxTiles, occ);
+    }
     *launches += 4;
 }
 

@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "libknzgpu.so")
 
 T_IDS = {"NONE": 0, "BWT": 1, "ZRLT": 6, "MTFT": 7, "RANK": 8}
-E_IDS = {"NONE": 0, "ANS0": 5}
+E_IDS = {"NONE": 0, "HUFFMAN": 1, "ANS0": 5}
 
 
 class KanziGpuError(RuntimeError):

@@ -36,6 +36,8 @@ STREAMS = [
     ("compressible", 4, 200000, "BWT", "NONE", 65536),
     ("compressible", 2, 9 << 20, "BWT+RANK+ZRLT", "ANS0", 4 << 20),
     ("text", 1, 16 << 20, "NONE", "ANS0", 4 << 20),
+    ("text", 1, 16 << 20, "NONE", "HUFFMAN", 4 << 20),  # BASELINE.json configs[0]
+    ("compressible", 5, 200000, "BWT+RANK+ZRLT", "HUFFMAN", 65536),
     ("compressible", 2, 64 << 20, "BWT+RANK+ZRLT", "ANS0", 4 << 20),
 ]
 

@@ -26,13 +26,14 @@ def sim():
 CASES = small_cases()
 
 
-def test_sim_entropy_ans0(sim, oracle):
+@pytest.mark.parametrize("ename", ["ANS0", "HUFFMAN"])
+def test_sim_entropy(sim, oracle, ename):
     for name, data in CASES.items():
-        a, abits = sim.entropy_encode("ANS0", data)
-        b, bbits = oracle.entropy_encode("ANS0", data)
+        a, abits = sim.entropy_encode(ename, data)
+        b, bbits = oracle.entropy_encode(ename, data)
         assert abits == bbits, (name, abits, bbits)
         assert np.array_equal(a, b), name
-        dec = sim.entropy_decode("ANS0", b, bbits, data.size)
+        dec = sim.entropy_decode(ename, b, bbits, data.size)
         assert np.array_equal(dec, data), name
 
 
@@ -53,7 +54,8 @@ def test_sim_stage_forward_inverse(sim, oracle, tname):
 
 
 @pytest.mark.parametrize("tname,ename", [("NONE", "ANS0"), ("BWT+RANK+ZRLT", "ANS0"), ("NONE", "NONE"),
-                                         ("ZRLT", "ANS0"), ("BWT+MTFT+ZRLT", "ANS0"), ("BWT", "NONE")])
+                                         ("ZRLT", "ANS0"), ("BWT+MTFT+ZRLT", "ANS0"), ("BWT", "NONE"),
+                                         ("NONE", "HUFFMAN"), ("BWT+RANK+ZRLT", "HUFFMAN")])
 def test_sim_stream(sim, oracle, tname, ename):
     inputs = {
         "comp_150k": synth.synth_compressible(150000, 21),

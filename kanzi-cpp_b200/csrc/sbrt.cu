@@ -284,11 +284,17 @@ sbrt_rank_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkState*
                 const u32 c = (w4 >> (8 * x)) & 0xFF;
                 const u32 i = (u32)(g + j + x);
                 // top-32 probe: who holds c, and its last access time, without waiting for the rank
-                const int nq = __shfl_up_sync(FULL_MASK, L.q[0], 1);
-                const PB npb = __shfl_up_sync(FULL_MASK, L.pb[0], 1);
                 const bool hit = (u32)(L.pb[0] & 0xFF) == c;
                 const u32 m = __ballot_sync(FULL_MASK, hit);
-                if (m) {
+                if (m & 1u) {
+                    // c is the head of the list: rank 0, only the head's key changes
+                    if (lane == 0) {
+                        L.q[0] = keyOf(i, (u32)(L.pb[0] >> 8));
+                        L.pb[0] = ((PB)i << 8) | (PB)c;
+                    }
+                } else if (m) {
+                    const int nq = __shfl_up_sync(FULL_MASK, L.q[0], 1);
+                    const PB npb = __shfl_up_sync(FULL_MASK, L.pb[0], 1);
                     const u32 pc = __reduce_or_sync(FULL_MASK, hit ? (u32)(L.pb[0] >> 8) : 0u);
                     const int r = __ffs(m) - 1;
                     const int qc = keyOf(i, pc);

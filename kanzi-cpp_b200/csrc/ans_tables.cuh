@@ -71,8 +71,10 @@ KNZ_HD int log2_floor(u32 x) // x >= 1
 }
 
 // Scale the 256 counts in f[] (sum = total > 0) to sum `scale`; returns the
-// alphabet size.  f[] is updated in place.
-KNZ_HD int normalize_counts(u32* f, u32 total, u32 scale)
+// alphabet size.  f[] is updated in place.  `Arr` is anything indexable by symbol
+// (a plain u32* or the lane-rotated view the encoder keeps in shared memory).
+template <class Arr>
+KNZ_HD int normalize_counts(Arr f, u32 total, u32 scale)
 {
     int asz = 0;
     if (total == scale) {
@@ -145,7 +147,8 @@ KNZ_HD int normalize_counts(u32* f, u32 total, u32 scale)
 
 // Emit the order-0 chunk header for normalised freqs f[] (alphabet size asz):
 // logRange-8 (3 bits), alphabet, then freq groups.
-KNZ_HD void put_chunk_header(BitSink& w, const u32* f, int asz, int lr)
+template <class Arr>
+KNZ_HD void put_chunk_header(BitSink& w, Arr f, int asz, int lr)
 {
     w.put((u32)(lr - 8), 3);
     if (asz == 256) {

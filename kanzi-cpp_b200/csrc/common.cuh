@@ -6,6 +6,8 @@
 #else
 #include <cuda_runtime.h>
 #define KLAUNCH(kernel, grid, block, stream, ...) kernel<<<grid, block, 0, stream>>>(__VA_ARGS__)
+#define KLAUNCH_DYN(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#define KNZ_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
 
 typedef uint8_t u8;

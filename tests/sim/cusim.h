@@ -343,3 +343,8 @@ inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
 inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return 0; }
 
 #define KLAUNCH(kernel, grid, block, stream, ...) cusim::launch(grid, block, [&]() { kernel(__VA_ARGS__); })
+#define KLAUNCH_DYN(kernel, grid, block, smem, stream, ...) cusim::launch(grid, block, [&]() { kernel(__VA_ARGS__); })
+#define KNZ_DYN_SMEM(name) static __attribute__((aligned(16))) unsigned char name[232 * 1024]
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <class F>
+inline cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }

@@ -365,6 +365,22 @@ def run_ours(args, rank, world, local_rank):
         "encode_pipeline": rl(my_bytes + comp_share, e_ms["total"]),
         "decode_pipeline": rl(my_bytes + comp_share, d_ms["total"]),
     }
+    # entropy kernels alone on the raw workload (BASELINE config 4 shape: -t NONE -e {ANS0,HUFFMAN}, 4 MiB blocks)
+    try:
+        for ename in ("ANS0", "HUFFMAN"):
+            et2 = E_IDS[ename]
+            tt0 = ctx.transform_type("NONE")
+            sharded.encode_shard(ctx, tt0, et2, BLOCK, d_in, lens, BLOCK, d_blk, d_bits)
+            sharded.encode_shard(ctx, tt0, et2, BLOCK, d_in, lens, BLOCK, d_blk, d_bits)
+            t4 = ctx.timings()
+            e4 = int((d_bits.sum().item() + 7) // 8)
+            sharded.decode_shard(ctx, tt0, et2, BLOCK, d_blk, d_bits.cpu().numpy().astype(np.uint64), d_dec)
+            t4d = ctx.timings()
+            assert bool((d_dec == d_in).all().item())
+            stages[f"{ename.lower()}_encode_kernel_config4"] = rl(my_bytes + e4, t4["ans_enc_kernel"])
+            stages[f"{ename.lower()}_decode_kernel_config4"] = rl(my_bytes + e4, t4d["ans_dec_kernel"])
+    except Exception as ex:
+        stages["config4_error"] = str(ex)
     dominant = dict(stages["bwt_forward"] or {})
     dominant["kernel"] = ("bwt_forward stage (segmented radix-sort prefix doubling: rs_scatter/rs_hist/"
                           "bwt_grp_* kernels), dominant share of the encode pass")

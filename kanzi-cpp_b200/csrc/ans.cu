@@ -26,7 +26,6 @@ using namespace knz;
 // same region first.  Symbol s lives at slot (s + lane) & 255 of the lane's region:
 // skewed data makes every lane look up the same symbol at the same time, and the
 // rotation turns that 32-way bank conflict into a conflict-free access.
-// Renormalisation words are packed 4 at a time into one aligned 8-byte store.
 struct RotArr { // lane-rotated view of a 256-entry u32 array
     u32* p;
     int rot;
@@ -73,8 +72,12 @@ ans0_encode_kernel(BufTable bt, const BlkState* __restrict__ st, int nBlocks, in
     u32* hw = reinterpret_cast<u32*>(tab);                 // histogram view (first KiB)
     const RotArr f = { hw, lane };
 
-    // ---- phase A: private histogram (plain read-modify-write, no atomics)
-    for (int i = 0; i < 256; i++)
+    // ---- phase A: private histogram (plain read-modify-write, no atomics).  Two
+    // sub-histograms (the two KiB of the lane's region) keep two independent
+    // read-modify-write chains in flight; equal neighbouring bytes are merged first.
+    u32* __restrict__ hA = hw;
+    u32* __restrict__ hB = hw + 256;
+    for (int i = 0; i < 512; i++)
         hw[i] = 0;
     {
         int i = 0;
@@ -83,14 +86,20 @@ ans0_encode_kernel(BufTable bt, const BlkState* __restrict__ st, int nBlocks, in
             const u32 w[4] = { v.x, v.y, v.z, v.w };
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                f[w[q] & 0xFF]++;
-                f[(w[q] >> 8) & 0xFF]++;
-                f[(w[q] >> 16) & 0xFF]++;
-                f[w[q] >> 24]++;
+                const u32 b0 = w[q] & 0xFF, b1 = (w[q] >> 8) & 0xFF, b2 = (w[q] >> 16) & 0xFF, b3 = w[q] >> 24;
+                const u32 e01 = (b0 == b1) ? 1u : 0u, e23 = (b2 == b3) ? 1u : 0u;
+                hA[(b0 + lane) & 255] += 1 + e01;
+                hB[(b2 + lane) & 255] += 1 + e23;
+                if (!e01)
+                    hA[(b1 + lane) & 255] += 1;
+                if (!e23)
+                    hB[(b3 + lane) & 255] += 1;
             }
         }
         for (; i < len; i++)
-            f[p[i]]++;
+            hA[(p[i] + lane) & 255] += 1;
+        for (int k = 0; k < 256; k++)
+            hA[k] += hB[k];
     }
 
     // ---- phase B: normalise, header, table (same lane)
@@ -126,25 +135,21 @@ ans0_encode_kernel(BufTable bt, const BlkState* __restrict__ st, int nBlocks, in
     const int steps = end4 >> 2;
     const u32* __restrict__ words = reinterpret_cast<const u32*>(p);
     u32 s0 = 1u << 15, s1 = 1u << 15, s2 = 1u << 15, s3 = 1u << 15; // ANS_TOP
-    u32 cnt = 0;   // words emitted
-    u64 ebuf = 0;  // up to 4 pending words, oldest in the top bits
-    u64* wend8 = reinterpret_cast<u64*>(slot + ANS_WEND);
+    u32 cnt = 0; // words emitted
     const int wtop = steps - 1;
     const bool vec = (end4 & 15) == 0;
 
-#define KNZ_ENC_ONE(ST, BYTE)                                                            \
+    u16* wend = reinterpret_cast<u16*>(slot + ANS_WEND);
+    // One state update, emission deferred: EM = 1 when a 16-bit word leaves the state.
+#define KNZ_ENC_ONE(ST, BYTE, EM, WORD)                                                  \
     do {                                                                                 \
         const u64 e_ = tab[((BYTE) + lane) & 255];                                       \
         const u32 hi_ = (u32)(e_ >> 32), inv_ = (u32)e_;                                 \
         const u32 fr_ = hi_ & 0xFFF;                                                     \
-        u32 x_ = ST;                                                                     \
-        if (x_ >= (fr_ << (31 - ANS0_LR))) {                                             \
-            ebuf = (ebuf << 16) | (u64)__byte_perm(x_, 0, 0x4401);                       \
-            cnt++;                                                                       \
-            if ((cnt & 3) == 0)                                                          \
-                wend8[-(int)(cnt >> 2)] = ebuf;                                          \
-            x_ >>= 16;                                                                   \
-        }                                                                                \
+        const u32 x0_ = ST;                                                              \
+        EM = (x0_ >= (fr_ << (31 - ANS0_LR))) ? 1u : 0u;                                 \
+        WORD = __byte_perm(x0_, 0, 0x4401);                                              \
+        const u32 x_ = EM ? (x0_ >> 16) : x0_;                                           \
         const u32 q_ = __umulhi(x_, inv_) >> (hi_ >> 25);                                \
         ST = x_ + ((hi_ >> 12) & 0x1FFF) + q_ * ((1u << ANS0_LR) - fr_);                 \
     } while (0)
@@ -176,26 +181,29 @@ ans0_encode_kernel(BufTable bt, const BlkState* __restrict__ st, int nBlocks, in
         for (int x = 0; x < 4; x++) {
             if (4 * g + x < steps) {
                 const u32 wd = wv[x];
-                KNZ_ENC_ONE(s0, wd >> 24);
-                KNZ_ENC_ONE(s1, (wd >> 16) & 0xFF);
-                KNZ_ENC_ONE(s2, (wd >> 8) & 0xFF);
-                KNZ_ENC_ONE(s3, wd & 0xFF);
+                u32 e0, e1, e2, e3, w0, w1, w2, w3;
+                // four independent chains ...
+                KNZ_ENC_ONE(s0, wd >> 24, e0, w0);
+                KNZ_ENC_ONE(s1, (wd >> 16) & 0xFF, e1, w1);
+                KNZ_ENC_ONE(s2, (wd >> 8) & 0xFF, e2, w2);
+                KNZ_ENC_ONE(s3, wd & 0xFF, e3, w3);
+                // ... then the ordered emission (st0, st1, st2, st3): only `cnt` is carried
+                const u32 i1 = cnt + e0, i2 = i1 + e1, i3 = i2 + e2;
+                if (e0)
+                    wend[-1 - (int)cnt] = (u16)w0;
+                if (e1)
+                    wend[-1 - (int)i1] = (u16)w1;
+                if (e2)
+                    wend[-1 - (int)i2] = (u16)w2;
+                if (e3)
+                    wend[-1 - (int)i3] = (u16)w3;
+                cnt = i3 + e3;
             }
         }
         ga = gb;
         gb = gc;
     }
 #undef KNZ_ENC_ONE
-    // pending words (1..3): word k sits at byte offset -2(k+1) from the end
-    {
-        const u32 r = cnt & 3;
-        u16* wend = reinterpret_cast<u16*>(slot + ANS_WEND);
-        for (u32 t = 0; t < r; t++) {
-            const u32 k = cnt - r + t;
-            wend[-1 - (int)k] = (u16)(ebuf >> (16 * (r - 1 - t)));
-        }
-    }
-
     // ---- epilogue: varint size, 4 states, tail bytes
     const int tail = len & 3;
     u32 P = 2 * cnt + (u32)tail;

@@ -18,31 +18,24 @@
 using namespace knz;
 
 // ------------------------------------------------------------------ encoder
-// One LANE per 16 KiB chunk (32 chunks per warp), all four rANS states of a chunk in
-// that lane's registers: the states are independent chains (ILP 4), the emission
-// order inside a step is plain program order, so the hot loop has no ballot, no
-// shuffle and no cross-lane dependency at all.  Each lane owns a 2 KiB table in
-// shared memory (64 KiB per warp, 3 warps per SM); the histogram is counted into the
-// same region first.  Symbol s lives at slot (s + lane) & 255 of the lane's region:
-// skewed data makes every lane look up the same symbol at the same time, and the
-// rotation turns that 32-way bank conflict into a conflict-free access.
-struct RotArr { // lane-rotated view of a 256-entry u32 array
-    u32* p;
-    int rot;
-    __device__ __forceinline__ u32& operator[](int i) const { return p[(i + rot) & 255]; }
-};
+// smem per warp: 8 tables x 256 x 8 B = 16 KiB.  While the histograms are built the
+// second KiB of every table region is free: four of them hold the 4 privatised
+// copies of the chunk being counted.
+#define ENC_WARPS 2
 
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(ENC_WARPS * 32)
 ans0_encode_kernel(BufTable bt, const BlkState* __restrict__ st, int nBlocks, int maxChunks, u8* __restrict__ slots,
                    u32* __restrict__ hdrBits, u32* __restrict__ payBytes, u32* __restrict__ payOff)
 {
-    KNZ_DYN_SMEM(s_raw);
-    const int lane = threadIdx.x;
-    const int groupsPerBlk = (maxChunks + 31) >> 5;
-    const int b = blockIdx.x / groupsPerBlk;
+    __shared__ __align__(16) u64 s_sym[ENC_WARPS][8][256];
+
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int groupsPerBlk = (maxChunks + 7) >> 3;
+    const int gw = blockIdx.x * ENC_WARPS + wib;
+    const int b = gw / groupsPerBlk;
     if (b >= nBlocks)
         return;
-    const int c0 = (blockIdx.x - b * groupsPerBlk) << 5;
+    const int c0 = (gw - b * groupsPerBlk) << 3;
     const BlkState bs = st[b];
     const int m = bs.len;
     const u8* __restrict__ src = blk_src(bt, bs, b);
@@ -61,167 +54,171 @@ ans0_encode_kernel(BufTable bt, const BlkState* __restrict__ st, int nBlocks, in
         }
         return;
     }
-    const int c = c0 + lane;
-    if (c >= nChunks)
-        return; // no collectives below: lanes are fully independent
-    const int len = min(ANS_CHUNK, m - c * ANS_CHUNK);
-    const u8* __restrict__ p = src + (i64)c * ANS_CHUNK;
-    const i64 ci = (i64)b * maxChunks + c;
-    u8* slot = slots + ci * ANS_SLOT;
-    u64* tab = reinterpret_cast<u64*>(s_raw) + lane * 256; // this lane's 2 KiB
-    u32* hw = reinterpret_cast<u32*>(tab);                 // histogram view (first KiB)
-    const RotArr f = { hw, lane };
 
-    // ---- phase A: private histogram (plain read-modify-write, no atomics).  Two
-    // sub-histograms (the two KiB of the lane's region) keep two independent
-    // read-modify-write chains in flight; equal neighbouring bytes are merged first.
-    u32* __restrict__ hA = hw;
-    u32* __restrict__ hB = hw + 256;
-    for (int i = 0; i < 512; i++)
-        hw[i] = 0;
-    {
-        int i = 0;
-        for (; i + 16 <= len; i += 16) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(p + i));
-            const u32 w[4] = { v.x, v.y, v.z, v.w };
+    u64(*sym)[256] = s_sym[wib];
+
+    // ---- phase A: histograms (whole warp per chunk, 4-way privatised smem atomics)
+    for (int j = 0; j < 8; j++) {
+        const int c = c0 + j;
+        if (c >= nChunks)
+            break;
+        const int len = min(ANS_CHUNK, m - c * ANS_CHUNK);
+        const u8* __restrict__ p = src + (i64)c * ANS_CHUNK;
+        // copy k lives in the upper KiB of table region (j + 1 + k) & 7
+        u32* hk[4];
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const u32 b0 = w[q] & 0xFF, b1 = (w[q] >> 8) & 0xFF, b2 = (w[q] >> 16) & 0xFF, b3 = w[q] >> 24;
-                const u32 e01 = (b0 == b1) ? 1u : 0u, e23 = (b2 == b3) ? 1u : 0u;
-                hA[(b0 + lane) & 255] += 1 + e01;
-                hB[(b2 + lane) & 255] += 1 + e23;
-                if (!e01)
-                    hA[(b1 + lane) & 255] += 1;
-                if (!e23)
-                    hB[(b3 + lane) & 255] += 1;
+        for (int k = 0; k < 4; k++)
+            hk[k] = reinterpret_cast<u32*>(sym[(j + 1 + k) & 7]) + 256;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            for (int i = lane; i < 256; i += 32)
+                hk[k][i] = 0;
+        __syncwarp();
+        u32* h = reinterpret_cast<u32*>(sym[(j + 1 + (lane & 3)) & 7]) + 256;
+        for (int i = lane * 16; i < len; i += 512) {
+            if (i + 16 <= len) {
+                const uint4 v = *reinterpret_cast<const uint4*>(p + i);
+                const u32 w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    atomicAdd(&h[w[q] & 0xFF], 1u);
+                    atomicAdd(&h[(w[q] >> 8) & 0xFF], 1u);
+                    atomicAdd(&h[(w[q] >> 16) & 0xFF], 1u);
+                    atomicAdd(&h[w[q] >> 24], 1u);
+                }
+            } else {
+                for (int t = i; t < len; t++)
+                    atomicAdd(&h[p[t]], 1u);
             }
         }
-        for (; i < len; i++)
-            hA[(p[i] + lane) & 255] += 1;
-        for (int k = 0; k < 256; k++)
-            hA[k] += hB[k];
+        __syncwarp();
+        u32* f = reinterpret_cast<u32*>(sym[j]);
+        for (int i = lane; i < 256; i += 32)
+            f[i] = hk[0][i] + hk[1][i] + hk[2][i] + hk[3][i];
+        __syncwarp();
     }
 
-    // ---- phase B: normalise, header, table (same lane)
+    // ---- phase B: one lane per chunk: normalise, header, tables
+    const int j = lane >> 2, k = lane & 3;
+    const int c = c0 + j;
+    const bool valid = c < nChunks;
+    const int len = valid ? min(ANS_CHUNK, m - c * ANS_CHUNK) : 0;
+    u8* slot = slots + ((i64)b * maxChunks + (valid ? c : 0)) * ANS_SLOT;
     BitSink w;
     w.init(slot);
-    const int asz = normalize_counts(f, (u32)len, 1u << ANS0_LR);
-    put_chunk_header(w, f, asz, ANS0_LR);
-    if (asz <= 1) { // header only (ANSRangeEncoder.cpp:182-185)
-        w.finish();
-        hdrBits[ci] = w.total;
-        payBytes[ci] = 0;
-        payOff[ci] = (u32)ANS_WEND;
-        return;
-    }
-    {
-        // cumulative frequencies in natural symbol order, parked in the upper halves
-        u32 run = 0;
-        for (int i = 0; i < 256; i++) {
-            const u32 fr = f[i];
-            f[i] = fr | (run << 16);
-            run += fr;
-        }
-        // entries by descending SLOT: slot k overwrites histogram words 2k, 2k+1 (>= k, consumed)
-        for (int k = 255; k >= 0; k--) {
-            const u32 v = hw[k];
-            const u32 fr = v & 0xFFFF;
-            tab[k] = (fr == 0) ? 0ull : make_enc_entry((int)(v >> 16), (int)fr, ANS0_LR);
+    int active = 0;
+    if (valid && k == 0) {
+        u32* f = reinterpret_cast<u32*>(sym[j]);
+        const int asz = normalize_counts(f, (u32)len, 1u << ANS0_LR);
+        put_chunk_header(w, f, asz, ANS0_LR);
+        if (asz > 1) {
+            active = 1;
+            u32 total = 0;
+            for (int i = 0; i < 256; i++)
+                total += f[i];
+            // descending: entry i overwrites histogram words 2i, 2i+1 (both >= i, already consumed);
+            // cumulative frequency of i = total - sum of the frequencies >= i
+            u32 run = total;
+            for (int i = 255; i >= 0; i--) {
+                const u32 fr = f[i];
+                run -= fr;
+                sym[j][i] = (fr == 0) ? 0ull : make_enc_entry((int)run, (int)fr, ANS0_LR);
+            }
         }
     }
+    __syncwarp();
+    active = __shfl_sync(FULL_MASK, active, lane & ~3);
 
-    // ---- phase C: the four interleaved states, sequentially in this lane
+    // ---- phase C: interleaved rANS, lane k of quad j owns state k
     const int end4 = len & ~3;
-    const int steps = end4 >> 2;
-    const u32* __restrict__ words = reinterpret_cast<const u32*>(p);
-    u32 s0 = 1u << 15, s1 = 1u << 15, s2 = 1u << 15, s3 = 1u << 15; // ANS_TOP
-    u32 cnt = 0; // words emitted
-    const int wtop = steps - 1;
-    const bool vec = (end4 & 15) == 0;
+    const int steps = active ? (end4 >> 2) : 0;
+    int maxSteps = steps;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        maxSteps = max(maxSteps, __shfl_xor_sync(FULL_MASK, maxSteps, o));
 
+    const u32* __restrict__ words = reinterpret_cast<const u32*>(src + (i64)(valid ? c : 0) * ANS_CHUNK);
+    const u64* __restrict__ tab = sym[j];
+    u32 state = 1u << 15; // ANS_TOP
+    u32 cnt = 0;
     u16* wend = reinterpret_cast<u16*>(slot + ANS_WEND);
-    // One state update, emission deferred: EM = 1 when a 16-bit word leaves the state.
-#define KNZ_ENC_ONE(ST, BYTE, EM, WORD)                                                  \
-    do {                                                                                 \
-        const u64 e_ = tab[((BYTE) + lane) & 255];                                       \
-        const u32 hi_ = (u32)(e_ >> 32), inv_ = (u32)e_;                                 \
-        const u32 fr_ = hi_ & 0xFFF;                                                     \
-        const u32 x0_ = ST;                                                              \
-        EM = (x0_ >= (fr_ << (31 - ANS0_LR))) ? 1u : 0u;                                 \
-        WORD = __byte_perm(x0_, 0, 0x4401);                                              \
-        const u32 x_ = EM ? (x0_ >> 16) : x0_;                                           \
-        const u32 q_ = __umulhi(x_, inv_) >> (hi_ >> 25);                                \
-        ST = x_ + ((hi_ >> 12) & 0x1FFF) + q_ * ((1u << ANS0_LR) - fr_);                 \
-    } while (0)
-
-    auto fetch = [&](int g) -> uint4 { // the 4 words of steps 4g .. 4g+3 (x = first step)
+    const int bsh = 8 * (3 - k);
+    const u32 below = (1u << k) - 1u;
+    const int qsh = lane & ~3;
+    const int wtop = (end4 >> 2) - 1; // step s consumes word wtop - s (the quad's 4 bytes)
+    // Software pipeline, 4 steps (16 input bytes per quad) per group, two groups ahead.
+    // Full chunks are 16-byte aligned from the top, so a group is one 128-bit load.
+    const bool vec = (end4 & 15) == 0;
+    uint4 ga = make_uint4(0, 0, 0, 0), gb = ga, gc = ga;
+    auto fetch = [&](int s0) -> uint4 {
         uint4 r = make_uint4(0, 0, 0, 0);
-        const int sA = 4 * g;
-        if (sA + 3 < steps && vec) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(words + (wtop - sA - 3)));
-            r = make_uint4(v.w, v.z, v.y, v.x);
+        if (s0 + 3 < steps && vec) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(words + (wtop - s0 - 3)));
+            r = make_uint4(v.w, v.z, v.y, v.x); // .x = word of step s0
         } else {
-            if (sA < steps)
-                r.x = __ldg(&words[wtop - sA]);
-            if (sA + 1 < steps)
-                r.y = __ldg(&words[wtop - sA - 1]);
-            if (sA + 2 < steps)
-                r.z = __ldg(&words[wtop - sA - 2]);
-            if (sA + 3 < steps)
-                r.w = __ldg(&words[wtop - sA - 3]);
+            if (s0 < steps)
+                r.x = __ldg(&words[wtop - s0]);
+            if (s0 + 1 < steps)
+                r.y = __ldg(&words[wtop - s0 - 1]);
+            if (s0 + 2 < steps)
+                r.z = __ldg(&words[wtop - s0 - 2]);
+            if (s0 + 3 < steps)
+                r.w = __ldg(&words[wtop - s0 - 3]);
         }
         return r;
     };
-    uint4 ga = fetch(0), gb = fetch(1);
-    const int ngroups = (steps + 3) >> 2;
-    for (int g = 0; g < ngroups; g++) {
-        const uint4 gc = fetch(g + 2);
+    ga = fetch(0);
+    gb = fetch(4);
+    for (int s0 = 0; s0 < maxSteps; s0 += 4) {
+        gc = fetch(s0 + 8);
         const u32 wv[4] = { ga.x, ga.y, ga.z, ga.w };
 #pragma unroll
         for (int x = 0; x < 4; x++) {
-            if (4 * g + x < steps) {
-                const u32 wd = wv[x];
-                u32 e0, e1, e2, e3, w0, w1, w2, w3;
-                // four independent chains ...
-                KNZ_ENC_ONE(s0, wd >> 24, e0, w0);
-                KNZ_ENC_ONE(s1, (wd >> 16) & 0xFF, e1, w1);
-                KNZ_ENC_ONE(s2, (wd >> 8) & 0xFF, e2, w2);
-                KNZ_ENC_ONE(s3, wd & 0xFF, e3, w3);
-                // ... then the ordered emission (st0, st1, st2, st3): only `cnt` is carried
-                const u32 i1 = cnt + e0, i2 = i1 + e1, i3 = i2 + e2;
-                if (e0)
-                    wend[-1 - (int)cnt] = (u16)w0;
-                if (e1)
-                    wend[-1 - (int)i1] = (u16)w1;
-                if (e2)
-                    wend[-1 - (int)i2] = (u16)w2;
-                if (e3)
-                    wend[-1 - (int)i3] = (u16)w3;
-                cnt = i3 + e3;
+            bool did = false;
+            u32 word = 0;
+            if (s0 + x < steps) {
+                const u32 cb = (wv[x] >> bsh) & 0xFF;
+                state = enc_step(state, tab[cb], ANS0_LR, &did, &word);
             }
+            const u32 qb = (__ballot_sync(FULL_MASK, did) >> qsh) & 0xF;
+            if (did) // memory order [hi][lo] (ANSRangeEncoder.hpp:122-126)
+                wend[-1 - (int)(cnt + __popc(qb & below))] = (u16)__byte_perm(word, 0, 0x4401);
+            cnt += __popc(qb);
         }
         ga = gb;
         gb = gc;
     }
-#undef KNZ_ENC_ONE
+
     // ---- epilogue: varint size, 4 states, tail bytes
-    const int tail = len & 3;
-    u32 P = 2 * cnt + (u32)tail;
-    payBytes[ci] = P;
-    payOff[ci] = (u32)(ANS_WEND - 2 * cnt);
-    while (P >= 128) { // EntropyUtils.cpp:247-259
-        w.put(0x80 | (P & 0x7F), 8);
-        P >>= 7;
+    const u32 s1 = __shfl_sync(FULL_MASK, state, (lane & ~3) + 1);
+    const u32 s2 = __shfl_sync(FULL_MASK, state, (lane & ~3) + 2);
+    const u32 s3 = __shfl_sync(FULL_MASK, state, (lane & ~3) + 3);
+    if (valid && k == 0) {
+        const i64 ci = (i64)b * maxChunks + c;
+        if (active) {
+            const int tail = len & 3;
+            u32 P = 2 * cnt + (u32)tail;
+            payBytes[ci] = P;
+            payOff[ci] = (u32)(ANS_WEND - 2 * cnt);
+            while (P >= 128) { // EntropyUtils.cpp:247-259
+                w.put(0x80 | (P & 0x7F), 8);
+                P >>= 7;
+            }
+            w.put(P, 8);
+            w.put(state, 32);
+            w.put(s1, 32);
+            w.put(s2, 32);
+            w.put(s3, 32);
+            const u8* p = src + (i64)c * ANS_CHUNK;
+            for (int t = 0; t < tail; t++)
+                slot[ANS_WEND + t] = p[end4 + t];
+        } else {
+            payBytes[ci] = 0;
+            payOff[ci] = (u32)ANS_WEND;
+        }
+        w.finish();
+        hdrBits[ci] = w.total;
     }
-    w.put(P, 8);
-    w.put(s0, 32);
-    w.put(s1, 32);
-    w.put(s2, 32);
-    w.put(s3, 32);
-    for (int t = 0; t < tail; t++)
-        slot[ANS_WEND + t] = p[end4 + t];
-    w.finish();
-    hdrBits[ci] = w.total;
 }
 
 // Raw "entropy" (NullEntropyEncoder): one pseudo-chunk per block = the bytes themselves.
@@ -437,16 +434,13 @@ void launch_entropy_encode(const EncodeLaunch& L, cudaStream_t s, u64* launches)
     } else if (L.eType == E_HUF) {
         launch_huffman_encode_chunks(L, s, launches);
     } else {
-        const int groups = (L.maxChunks + 31) / 32;
-        static bool attrSet = false;
-        if (!attrSet) {
-            cudaFuncSetAttribute(ans0_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
-            attrSet = true;
-        }
+        const int groups = (L.maxChunks + 7) / 8;
+        const i64 warps = (i64)nB * groups;
+        const int ctas = (int)((warps + ENC_WARPS - 1) / ENC_WARPS);
         if (L.evK0)
             cudaEventRecord(L.evK0, s);
-        KLAUNCH_DYN(ans0_encode_kernel, nB * groups, 32, 65536, s, L.bt, L.st, nB, L.maxChunks, L.slots, L.hdrBits,
-                    L.payBytes, L.payOff);
+        KLAUNCH(ans0_encode_kernel, ctas, ENC_WARPS * 32, s, L.bt, L.st, nB, L.maxChunks, L.slots, L.hdrBits,
+                L.payBytes, L.payOff);
         if (L.evK1)
             cudaEventRecord(L.evK1, s);
     }

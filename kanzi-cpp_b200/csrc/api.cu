@@ -24,6 +24,8 @@
 struct knz_ctx {
     int device, maxBlockSize, maxBatch;
     cudaStream_t stream;
+    cudaStream_t copyStream; // host<->device staging of the stream-level API (overlaps with compute)
+    cudaEvent_t evCopy[2], evDone[2];
     cudaEvent_t ev[10];
     i64 bstride;     // stride of the ping-pong stage buffers
     u8 *bufA, *bufB; // [maxBatch * bstride]
@@ -49,6 +51,8 @@ struct knz_ctx {
     i64 dStreamCap;
     u8* dPlain;
     i64 dPlainCap;
+    u8* dPlain2;
+    i64 dPlain2Cap;
     u64 launches;
     float ms[8];
     char err[256];
@@ -157,6 +161,11 @@ extern "C" int knz_create(int device, int maxBlockSize, int maxBatchBlocks, knz_
     bool ok = true;
 #define A(call) ok = ok && ((call) == cudaSuccess)
     A(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    A(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        A(cudaEventCreate(&ctx->evCopy[i]));
+        A(cudaEventCreate(&ctx->evDone[i]));
+    }
     for (int i = 0; i < 10; i++)
         A(cudaEventCreate(&ctx->ev[i]));
     A(dalloc(&ctx->bufA, nb * ctx->bstride + 256));
@@ -209,7 +218,7 @@ extern "C" void knz_destroy(knz_ctx* ctx)
     void* dev[] = { ctx->bufA, ctx->bufB, ctx->dStageIn, ctx->dOut, ctx->st, ctx->capEven, ctx->capOdd, ctx->slots,
                     ctx->hdrBits, ctx->payBytes, ctx->payOff, ctx->chunkOff, ctx->chunkPos, ctx->blockBits,
                     ctx->blockOff, ctx->streamPos, ctx->dInBits, ctx->dPayStart, ctx->dPreLen, ctx->errFlag,
-                    ctx->dStream, ctx->dPlain };
+                    ctx->dStream, ctx->dPlain, ctx->dPlain2 };
     for (size_t i = 0; i < sizeof(dev) / sizeof(dev[0]); i++)
         if (dev[i])
             cudaFree(dev[i]);
@@ -221,6 +230,14 @@ extern "C" void knz_destroy(knz_ctx* ctx)
     for (int i = 0; i < 10; i++)
         if (ctx->ev[i])
             cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->evCopy[i])
+            cudaEventDestroy(ctx->evCopy[i]);
+        if (ctx->evDone[i])
+            cudaEventDestroy(ctx->evDone[i]);
+    }
+    if (ctx->copyStream)
+        cudaStreamDestroy(ctx->copyStream);
     if (ctx->stream)
         cudaStreamDestroy(ctx->stream);
     free(ctx);
@@ -595,20 +612,42 @@ extern "C" int knz_compress(knz_ctx* ctx, const char* transform, const char* ent
     int rc = grow(ctx, &ctx->dStream, &ctx->dStreamCap, streamCap);
     if (rc != KNZ_OK)
         return rc;
-    rc = grow(ctx, &ctx->dPlain, &ctx->dPlainCap, round_up((i64)ctx->maxBatch * blockSize + 256, 256));
+    // Encode in sub-batches of <= 64 blocks: the pinned-host -> device copy of sub-batch
+    // i+1 runs on the copy stream while sub-batch i is being encoded.
+    const int eb = (ctx->maxBatch < 64) ? ctx->maxBatch : 64;
+    const i64 plainBytes = round_up((i64)eb * blockSize + 256, 256);
+    rc = grow(ctx, &ctx->dPlain, &ctx->dPlainCap, plainBytes);
     if (rc != KNZ_OK)
         return rc;
+    rc = grow(ctx, &ctx->dPlain2, &ctx->dPlain2Cap, plainBytes);
+    if (rc != KNZ_OK)
+        return rc;
+    u8* plain[2] = { ctx->dPlain, ctx->dPlain2 };
     CK(cudaMemsetAsync(ctx->dStream, 0, (size_t)streamCap, s));
     ctx->h_pos[0] = 8ull * (u64)hdrBytes;
     CK(cudaMemcpyAsync(ctx->streamPos, ctx->h_pos, sizeof(u64), cudaMemcpyHostToDevice, s));
     CK(cudaStreamSynchronize(s));
     const int firstLen = (int)((n < blockSize) ? n : blockSize);
     float acc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
-    for (i64 b0 = 0; b0 < nBlocks; b0 += ctx->maxBatch) {
-        const int nb = (int)((nBlocks - b0 < ctx->maxBatch) ? nBlocks - b0 : ctx->maxBatch);
+    auto issueCopy = [&](i64 b0, int slot) -> cudaError_t {
+        const int nb = (int)((nBlocks - b0 < eb) ? nBlocks - b0 : eb);
         const i64 off = b0 * blockSize;
         const i64 bytes = ((off + (i64)nb * blockSize) <= n) ? (i64)nb * blockSize : n - off;
-        CK(cudaMemcpyAsync(ctx->dPlain, in + off, (size_t)bytes, cudaMemcpyHostToDevice, s));
+        cudaError_t e = cudaMemcpyAsync(plain[slot], in + off, (size_t)bytes, cudaMemcpyHostToDevice, ctx->copyStream);
+        if (e == cudaSuccess)
+            e = cudaEventRecord(ctx->evCopy[slot], ctx->copyStream);
+        return e;
+    };
+    if (nBlocks > 0)
+        CK(issueCopy(0, 0));
+    int slot = 0;
+    for (i64 b0 = 0; b0 < nBlocks; b0 += eb, slot ^= 1) {
+        const int nb = (int)((nBlocks - b0 < eb) ? nBlocks - b0 : eb);
+        const i64 off = b0 * blockSize;
+        // the other staging buffer is free: encode_batch of the previous sub-batch has completed
+        if (b0 + eb < nBlocks)
+            CK(issueCopy(b0 + eb, slot ^ 1));
+        CK(cudaStreamWaitEvent(s, ctx->evCopy[slot], 0));
         int32_t* lens = (int32_t*)malloc(sizeof(int32_t) * (size_t)nb);
         for (int i = 0; i < nb; i++) {
             const i64 rem = n - (off + (i64)i * blockSize);
@@ -618,7 +657,7 @@ extern "C" int knz_compress(knz_ctx* ctx, const char* transform, const char* ent
         if (lens[nb - 1] <= 15)
             ng = nb - 1; // only the last block of a stream can be that small
         if (ng > 0) {
-            rc = encode_batch(ctx, tType, eType, blockSize, ctx->dPlain, blockSize, lens, ng, firstLen, ctx->dOut,
+            rc = encode_batch(ctx, tType, eType, blockSize, plain[slot], blockSize, lens, ng, firstLen, ctx->dOut,
                               ctx->outStride, ctx->blockBits, NULL);
             for (int i = 0; i < 8; i++)
                 acc[i] += ctx->ms[i];

@@ -340,6 +340,7 @@ inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = nullptr; return 0; }
 inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
 inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return 0; }
 inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return 0; }
 
 #define KLAUNCH(kernel, grid, block, stream, ...) cusim::launch(grid, block, [&]() { kernel(__VA_ARGS__); })

@@ -992,6 +992,8 @@ struct InvCtx {
     u64* packed[2];
     u32* node; // [nBlocks][nodeStride][4]: next, len, base, pad
     int capN, nodeStride, nBlocks;
+    int b0;     // first block of the group a walk launch covers (L2-sized groups)
+    int narrow; // 1: packed entries are 32-bit ((psi << 8) | F, blocks < 16 MiB), else 64-bit
     int* errFlag;
 };
 
@@ -1056,16 +1058,22 @@ bwt_inv_pack_kernel(InvCtx C)
     const u64* __restrict__ F = C.key[w] + (i64)b * C.capN;
     const u32* __restrict__ nx = C.val[w] + (i64)b * C.capN;
     u64* __restrict__ P = C.packed[w ^ 1] + (i64)b * C.capN;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < m; t += gridDim.x * blockDim.x)
-        P[t] = ((u64)nx[t] << 8) | (F[t] & 0xFF);
+    u32* __restrict__ P32 = reinterpret_cast<u32*>(P);
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < m; t += gridDim.x * blockDim.x) {
+        const u32 nxv = nx[t];
+        if (C.narrow) // psi < 2^24; the end marker keeps its all-ones pattern in 24 bits
+            P32[t] = (nxv << 8) | (u32)(F[t] & 0xFF);
+        else
+            P[t] = ((u64)nxv << 8) | (F[t] & 0xFF);
+    }
 }
 
 template <int PASS>
 __global__ void __launch_bounds__(128)
 bwt_inv_walk_kernel(InvCtx C)
 {
-    const int b = blockIdx.y;
-    if (!C.bwtOk[b])
+    const int b = C.b0 + blockIdx.y;
+    if (b >= C.nBlocks || !C.bwtOk[b])
         return;
     const BlkState bs = C.stIn[b];
     const u8* __restrict__ src = blk_src(C.bt, bs, b);
@@ -1085,13 +1093,29 @@ bwt_inv_walk_kernel(InvCtx C)
         return;
     }
     const u64* __restrict__ P = C.packed[C.whichAfter[b] ^ 1] + (i64)b * C.capN;
+    const u32* __restrict__ P32 = reinterpret_cast<const u32*>(P);
+    const bool narrow = C.narrow != 0;
+    // entry t -> (symbol, next position); BWT_END when the text ends here
+    auto entry = [&](u32 t, u32& nxt) -> u32 {
+        if (narrow) {
+            const u32 e = P32[t];
+            nxt = e >> 8;
+            if (nxt == 0x00FFFFFFu)
+                nxt = BWT_END;
+            return e & 0xFF;
+        }
+        const u64 e = P[t];
+        nxt = (u32)(e >> 8);
+        return (u32)(e & 0xFF);
+    };
     if (PASS == 1) {
         u32 len = 0;
         int nxt = -1;
         for (;;) {
-            const u64 e = P[t];
+            u32 nx;
+            entry(t, nx);
             len++;
-            t = (u32)(e >> 8);
+            t = nx;
             if (t == BWT_END)
                 break;
             if (t >= (u32)B.m || len > (u32)B.m) { // not a permutation: malformed input
@@ -1112,9 +1136,9 @@ bwt_inv_walk_kernel(InvCtx C)
             return;
         u8* __restrict__ dst = blk_dst(C.bt, bs, b) + base;
         for (u32 k = 0; k < len; k++) {
-            const u64 e = P[t];
-            dst[k] = (u8)e;
-            t = (u32)(e >> 8);
+            u32 nx;
+            dst[k] = (u8)entry(t, nx);
+            t = nx;
         }
     }
 }
@@ -1188,14 +1212,30 @@ void launch_bwt_inverse(const StageLaunch& L, Workspace& ws, cudaStream_t s, u64
     C.capN = ws.capN;
     C.nodeStride = maxTiles * 64;
     C.nBlocks = nB;
+    C.b0 = 0;
+    C.narrow = (L.maxLen < (1 << 24) - 1) ? 1 : 0;
     C.errFlag = L.errFlag;
     const int packBlocks = min((L.maxLen + 255) / 256, 1024);
     KLAUNCH(bwt_inv_pack_kernel, dim3(packBlocks, nB), 256, s, C);
     const int nodes = ((L.maxLen + 255) >> SPL_LOG) + 8;
-    KLAUNCH(bwt_inv_walk_kernel<1>, dim3((nodes + 127) / 128, nB), 128, s, C);
+    // Walk a few blocks at a time so that their packed psi arrays stay resident in the
+    // 126 MB L2: every 32-byte sector is then fetched from HBM once instead of once per
+    // element it holds.
+    const i64 perBlock = (i64)L.maxLen * (C.narrow ? 4 : 8);
+    int grp = (int)((96ll << 20) / (perBlock > 0 ? perBlock : 1));
+    grp = grp < 1 ? 1 : (grp > nB ? nB : grp);
+    for (int g0 = 0; g0 < nB; g0 += grp) {
+        C.b0 = g0;
+        KLAUNCH(bwt_inv_walk_kernel<1>, dim3((nodes + 127) / 128, min(grp, nB - g0)), 128, s, C);
+        *launches += 1;
+    }
     KLAUNCH(bwt_inv_rank_kernel, (nB * 8 + 63) / 64, 64, s, C);
-    KLAUNCH(bwt_inv_walk_kernel<2>, dim3((nodes + 127) / 128, nB), 128, s, C);
-    *launches += 4;
+    *launches += 1;
+    for (int g0 = 0; g0 < nB; g0 += grp) {
+        C.b0 = g0;
+        KLAUNCH(bwt_inv_walk_kernel<2>, dim3((nodes + 127) / 128, min(grp, nB - g0)), 128, s, C);
+        *launches += 1;
+    }
 }
 
 // ------------------------------------------------------------------ misc stages

@@ -1150,6 +1150,7 @@ static int run_single_stage(knz_ctx* ctx, int type, bool inverse, const u8* in, 
     L.capEven = ctx->capEven;
     L.capOdd = ctx->capOdd;
     L.errFlag = ctx->errFlag;
+    CK(cudaEventRecord(ctx->ev[1], s));
     switch (type) {
     case T_NONE:
         launch_none_forward(L, s, &ctx->launches);
@@ -1167,10 +1168,19 @@ static int run_single_stage(knz_ctx* ctx, int type, bool inverse, const u8* in, 
                 : launch_sbrt_forward(L, type == T_MTFT ? 1 : 2, ctx->ws, s, &ctx->launches);
         break;
     }
+    CK(cudaEventRecord(ctx->ev[2], s));
     CK(cudaMemcpyAsync(ctx->h_err, ctx->errFlag, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(ctx->h_st, L.stOut, sizeof(BlkState), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
+    {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]);
+        for (int k = 0; k < 8; k++)
+            ctx->ms[k] = 0.f;
+        add_stage_time(ctx, type, ms);
+        ctx->ms[5] = ms;
+    }
     if (ctx->h_err[0] != 0) {
         if (inverse && ctx->h_err[0] == KERR_BAD_STREAM)
             return KNZ_OK; // inverse() returns false on malformed input: applied stays 0

@@ -14,6 +14,7 @@
 //     index k = rank(k*ceil(n/8)) + 1 (same contract as constructBWT).
 // Many blocks are sorted in one launch sequence (segment = block).
 #include <string.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -1218,11 +1219,19 @@ void launch_bwt_inverse(const StageLaunch& L, Workspace& ws, cudaStream_t s, u64
     const int packBlocks = min((L.maxLen + 255) / 256, 1024);
     KLAUNCH(bwt_inv_pack_kernel, dim3(packBlocks, nB), 256, s, C);
     const int nodes = ((L.maxLen + 255) >> SPL_LOG) + 8;
-    // Walk a few blocks at a time so that their packed psi arrays stay resident in the
-    // 126 MB L2: every 32-byte sector is then fetched from HBM once instead of once per
-    // element it holds.
-    const i64 perBlock = (i64)L.maxLen * (C.narrow ? 4 : 8);
-    int grp = (int)((96ll << 20) / (perBlock > 0 ? perBlock : 1));
+    // The walks are latency-bound pointer chases: they want every resident thread slot
+    // busy, which matters more than keeping the packed arrays inside L2 (measured: groups
+    // of 6 blocks = 96 MB halve the throughput).  KNZ_INV_GROUP overrides for experiments.
+    int grp = nB;
+    {
+        static int envGrp = -1;
+        if (envGrp < 0) {
+            const char* e = getenv("KNZ_INV_GROUP");
+            envGrp = e ? atoi(e) : 0;
+        }
+        if (envGrp > 0)
+            grp = envGrp;
+    }
     grp = grp < 1 ? 1 : (grp > nB ? nB : grp);
     for (int g0 = 0; g0 < nB; g0 += grp) {
         C.b0 = g0;

@@ -13,6 +13,8 @@
 //      comparisons of a step are 8 ballots.
 // The inverse needs the decoded symbol to update the list, so it is a serial
 // replay per block (one thread per block, list in shared memory).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -438,6 +440,200 @@ sbrt_inverse_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkSta
     }
 }
 
+// ---- inverse, latency-optimised (blocks < 2^24 bytes) --------------------------------
+// Measured on B200 with one warp per SM sub-partition (tools/microbench/lat*.cu):
+// SHFL.IDX 33 cycles, SHFL.UP 26, +4.5 per extra shuffle in flight, ALU op 4.4,
+// ballot+popc 15, a TAKEN branch 15-25.  A step of sbrt_inverse_kernel costs 98 cycles
+// (three dependent predicate hops after the shuffle); this kernel's step costs ~68:
+//   * keys are kept as Y & ~1 with Y = i + p (RANK mode): (a >> 1) <= (Y >> 1)  <=>
+//     (a & ~1) <= Y, so the shift leaves the critical path and both selects hang off ONE
+//     compare level:  lane g <= r with K[g] <= Y takes (K[g-1] <= Y ? entry g-1 : new entry)
+//   * a word of four ranks < 32 is straight-line code; the only taken branch per word is
+//     the loop back-edge
+//   * runs of zero words (rank 0 repeated: only the head's key/time change) are folded in
+//     closed form from a ballot mask of the 32 input words of a 128-byte group.
+template <int MODE>
+struct InvList {
+    u32 dK[8], dP[8]; // rank g in lane g & 31, slot g >> 5;  dP = (last access time << 8) | symbol
+
+    static __device__ __forceinline__ u32 key_raw(u32 i, u32 p)
+    {
+        return (MODE == 1) ? i : (MODE == 2) ? i + p : p;
+    }
+    static __device__ __forceinline__ u32 key_store(u32 y) { return (MODE == 2) ? (y & ~1u) : y; }
+
+    // r < 32, branch-free
+    __device__ __forceinline__ u32 step_top(int r, u32 i, int lane)
+    {
+        const u32 e = __shfl_sync(FULL_MASK, dP[0], r);
+        u32 nK = __shfl_up_sync(FULL_MASK, dK[0], 1);
+        const u32 nP = __shfl_up_sync(FULL_MASK, dP[0], 1);
+        if (lane == 0)
+            nK = 0xFFFFFFFFu;
+        const u32 c = e & 0xFF;
+        const u32 y = key_raw(i, e >> 8);
+        const u32 yn = key_store(y);
+        const u32 ne = (i << 8) | c;
+        if (lane <= r && dK[0] <= y) {
+            const bool up = nK <= y;
+            dK[0] = up ? nK : yn;
+            dP[0] = up ? nP : ne;
+        }
+        return c;
+    }
+
+    // any r: generic 8-slot update
+    __device__ __forceinline__ u32 step_deep(int r, u32 i, int lane)
+    {
+        u32 sel = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            sel |= dP[k] & (0u - (u32)((r >> 5) == k));
+        const u32 e = __shfl_sync(FULL_MASK, sel, r & 31);
+        const u32 c = e & 0xFF;
+        const u32 y = key_raw(i, e >> 8);
+        const u32 yn = key_store(y);
+        const u32 ne = (i << 8) | c;
+        int rp = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            rp += __popc(__ballot_sync(FULL_MASK, dK[k] > y));
+#pragma unroll
+        for (int k = 7; k >= 0; k--) {
+            u32 nK = __shfl_up_sync(FULL_MASK, dK[k], 1);
+            u32 nP = __shfl_up_sync(FULL_MASK, dP[k], 1);
+            if (k > 0) {
+                const u32 sK = __shfl_sync(FULL_MASK, dK[k - 1], 31);
+                const u32 sP = __shfl_sync(FULL_MASK, dP[k - 1], 31);
+                if (lane == 0) {
+                    nK = sK;
+                    nP = sP;
+                }
+            }
+            const int g = 32 * k + lane;
+            const bool mv = (g > rp) && (g <= r);
+            const bool ins = g == rp;
+            dK[k] = ins ? yn : (mv ? nK : dK[k]);
+            dP[k] = ins ? ne : (mv ? nP : dP[k]);
+        }
+        return c;
+    }
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(32)
+sbrt_inverse_fast_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkState* __restrict__ stOut)
+{
+    const int b = blockIdx.x;
+    const BlkState bs = stIn[b];
+    if (stOut[b].swaps == bs.swaps)
+        return;
+    const int n = bs.len;
+    const int lane = threadIdx.x;
+    const u8* __restrict__ src = blk_src(bt, bs, b);
+    u8* __restrict__ dst = blk_dst(bt, bs, b);
+    InvList<MODE> L;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        L.dK[k] = 0;
+        L.dP[k] = (u32)(32 * k + lane);
+    }
+    const u32* __restrict__ src4 = reinterpret_cast<const u32*>(src); // buffers are 16-byte aligned
+    const int groups = (n + 127) >> 7;
+    u32 nextw = 0;
+    {
+        const int p = 4 * lane;
+        if (p + 4 <= n)
+            nextw = src4[lane];
+        else
+            for (int k = 0; p + k < n; k++)
+                nextw |= (u32)src[p + k] << (8 * k);
+    }
+    for (int g = 0; g < groups; g++) {
+        const u32 inw = nextw;
+        {
+            const int p = (g + 1) * 128 + 4 * lane; // prefetch the next 128 bytes
+            nextw = 0;
+            if (p + 4 <= n)
+                nextw = src4[p >> 2];
+            else
+                for (int k = 0; p + k < n; k++)
+                    nextw |= (u32)src[p + k] << (8 * k);
+        }
+        u32 outw = 0;
+        const int base = g * 128;
+        const int cnt = min(128, n - base);
+        const int fullWords = cnt >> 2;
+        u32 zm = __ballot_sync(FULL_MASK, inw == 0);                     // words of four zero ranks
+        const u32 dm = __ballot_sync(FULL_MASK, (inw & 0xE0E0E0E0u) != 0); // words holding a rank >= 32
+        if (fullWords < 32)
+            zm &= (1u << fullWords) - 1u;
+        int j = 0;
+        u32 w4 = __shfl_sync(FULL_MASK, inw, 0);
+        while (j < fullWords) {
+            const u32 zrest = zm >> j;
+            if (zrest & 1u) {
+                // zr consecutive zero words = 4*zr accesses to the head: only its key and
+                // last access time change (the previous access was one position earlier)
+                const int zr = (zrest == 0xFFFFFFFFu) ? 32 : (__ffs((int)~zrest) - 1);
+                const u32 i3 = (u32)(base + 4 * (j + zr) - 1);
+                const u32 c = __shfl_sync(FULL_MASK, L.dP[0], 0) & 0xFF;
+                if (lane == 0) {
+                    L.dK[0] = InvList<MODE>::key_store(InvList<MODE>::key_raw(i3, i3 - 1));
+                    L.dP[0] = (i3 << 8) | c;
+                }
+                if (lane >= j && lane < j + zr)
+                    outw = c * 0x01010101u;
+                j += zr;
+                w4 = __shfl_sync(FULL_MASK, inw, j & 31);
+                continue;
+            }
+            const u32 w4n = __shfl_sync(FULL_MASK, inw, (j + 1) & 31);
+            const u32 i0 = (u32)(base + 4 * j);
+            u32 o4;
+            if (!((dm >> j) & 1u)) {
+                o4 = L.step_top((int)(w4 & 0xFF), i0, lane);
+                o4 |= L.step_top((int)((w4 >> 8) & 0xFF), i0 + 1, lane) << 8;
+                o4 |= L.step_top((int)((w4 >> 16) & 0xFF), i0 + 2, lane) << 16;
+                o4 |= L.step_top((int)(w4 >> 24), i0 + 3, lane) << 24;
+            } else {
+                o4 = 0;
+#pragma unroll 1
+                for (int x = 0; x < 4; x++) {
+                    const int r = (int)((w4 >> (8 * x)) & 0xFF);
+                    const u32 c = (r < 32) ? L.step_top(r, i0 + x, lane) : L.step_deep(r, i0 + x, lane);
+                    o4 |= c << (8 * x);
+                }
+            }
+            if (lane == j)
+                outw = o4;
+            j++;
+            w4 = w4n;
+        }
+        if (cnt & 3) { // ragged tail of the block
+            w4 = __shfl_sync(FULL_MASK, inw, fullWords & 31);
+            u32 o4 = 0;
+            for (int x = 0; x < (cnt & 3); x++) {
+                const int r = (int)((w4 >> (8 * x)) & 0xFF);
+                const u32 c = L.step_deep(r, (u32)(base + 4 * fullWords + x), lane);
+                o4 |= c << (8 * x);
+            }
+            if (lane == fullWords)
+                outw = o4;
+        }
+        {
+            const int p = base + 4 * lane;
+            if (p + 4 <= n) {
+                *reinterpret_cast<u32*>(dst + p) = outw;
+            } else {
+                for (int k = 0; k < 4; k++)
+                    if (p + k < n)
+                        dst[p + k] = (u8)(outw >> (8 * k));
+            }
+        }
+    }
+}
+
 void launch_sbrt_forward(const StageLaunch& L, int mode, Workspace& ws, cudaStream_t s, u64* launches)
 {
     const int maxTiles = (ws.capN + S_TILE - 1) / S_TILE;
@@ -467,14 +663,27 @@ void launch_sbrt_inverse(const StageLaunch& L, int mode, Workspace& ws, cudaStre
     (void)ws;
     KLAUNCH(sbrt_decide_kernel, (L.nBlocks + 31) / 32, 32, s, L, 1);
     const bool small = L.maxLen < (1 << 24);
+    static int variant = -1; // KNZ_SBRT_INV=0 selects the plain distributed-list kernel (experiments)
+    if (variant < 0) {
+        const char* e = getenv("KNZ_SBRT_INV");
+        variant = e ? atoi(e) : 1;
+    }
+    if (small && variant == 0) {
+        if (mode == 1)
+            KLAUNCH((sbrt_inverse_kernel<u32, 1>), L.nBlocks, 32, s, L.bt, L.stIn, L.stOut);
+        else
+            KLAUNCH((sbrt_inverse_kernel<u32, 2>), L.nBlocks, 32, s, L.bt, L.stIn, L.stOut);
+        *launches += 2;
+        return;
+    }
     if (mode == 1) {
         if (small)
-            KLAUNCH((sbrt_inverse_kernel<u32, 1>), L.nBlocks, 32, s, L.bt, L.stIn, L.stOut);
+            KLAUNCH((sbrt_inverse_fast_kernel<1>), L.nBlocks, 32, s, L.bt, L.stIn, L.stOut);
         else
             KLAUNCH((sbrt_inverse_kernel<u64, 1>), L.nBlocks, 32, s, L.bt, L.stIn, L.stOut);
     } else {
         if (small)
-            KLAUNCH((sbrt_inverse_kernel<u32, 2>), L.nBlocks, 32, s, L.bt, L.stIn, L.stOut);
+            KLAUNCH((sbrt_inverse_fast_kernel<2>), L.nBlocks, 32, s, L.bt, L.stIn, L.stOut);
         else
             KLAUNCH((sbrt_inverse_kernel<u64, 2>), L.nBlocks, 32, s, L.bt, L.stIn, L.stOut);
     }

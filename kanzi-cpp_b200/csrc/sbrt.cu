@@ -452,6 +452,26 @@ sbrt_inverse_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkSta
 //     the loop back-edge
 //   * runs of zero words (rank 0 repeated: only the head's key/time change) are folded in
 //     closed form from a ballot mask of the 32 input words of a 128-byte group.
+// Shuffles in program order: the indexed one (33 cycles, on the critical path) is issued
+// before the two up-shuffles instead of behind them.
+#ifndef KNZ_SIM
+__device__ __forceinline__ u32 shfl_idx_ordered(u32 v, int l)
+{
+    u32 r;
+    asm volatile("shfl.sync.idx.b32 %0, %1, %2, 0x1f, 0xffffffff;" : "=r"(r) : "r"(v), "r"(l));
+    return r;
+}
+__device__ __forceinline__ u32 shfl_up1_ordered(u32 v)
+{
+    u32 r;
+    asm volatile("shfl.sync.up.b32 %0, %1, 1, 0x0, 0xffffffff;" : "=r"(r) : "r"(v));
+    return r;
+}
+#else
+__device__ __forceinline__ u32 shfl_idx_ordered(u32 v, int l) { return __shfl_sync(FULL_MASK, v, l); }
+__device__ __forceinline__ u32 shfl_up1_ordered(u32 v) { return __shfl_up_sync(FULL_MASK, v, 1); }
+#endif
+
 template <int MODE>
 struct InvList {
     u32 dK[8], dP[8]; // rank g in lane g & 31, slot g >> 5;  dP = (last access time << 8) | symbol
@@ -465,9 +485,9 @@ struct InvList {
     // r < 32, branch-free
     __device__ __forceinline__ u32 step_top(int r, u32 i, int lane)
     {
-        const u32 e = __shfl_sync(FULL_MASK, dP[0], r);
-        u32 nK = __shfl_up_sync(FULL_MASK, dK[0], 1);
-        const u32 nP = __shfl_up_sync(FULL_MASK, dP[0], 1);
+        const u32 e = shfl_idx_ordered(dP[0], r);
+        u32 nK = shfl_up1_ordered(dK[0]);
+        const u32 nP = shfl_up1_ordered(dP[0]);
         if (lane == 0)
             nK = 0xFFFFFFFFu;
         const u32 c = e & 0xFF;
@@ -566,8 +586,19 @@ sbrt_inverse_fast_kernel(BufTable bt, const BlkState* __restrict__ stIn, const B
         const int fullWords = cnt >> 2;
         u32 zm = __ballot_sync(FULL_MASK, inw == 0);                     // words of four zero ranks
         const u32 dm = __ballot_sync(FULL_MASK, (inw & 0xE0E0E0E0u) != 0); // words holding a rank >= 32
-        if (fullWords < 32)
-            zm &= (1u << fullWords) - 1u;
+        const u32 valid = (fullWords < 32) ? ((1u << fullWords) - 1u) : 0xFFFFFFFFu;
+        zm &= valid;
+        const u32 notfast = zm | dm | ~valid;
+        // four ranks < 32, straight line
+        auto word = [&](u32 w, int jj) {
+            const u32 i0 = (u32)(base + 4 * jj);
+            u32 o4 = L.step_top((int)(w & 0xFF), i0, lane);
+            o4 |= L.step_top((int)((w >> 8) & 0xFF), i0 + 1, lane) << 8;
+            o4 |= L.step_top((int)((w >> 16) & 0xFF), i0 + 2, lane) << 16;
+            o4 |= L.step_top((int)(w >> 24), i0 + 3, lane) << 24;
+            if (lane == jj)
+                outw = o4;
+        };
         int j = 0;
         u32 w4 = __shfl_sync(FULL_MASK, inw, 0);
         while (j < fullWords) {
@@ -588,27 +619,41 @@ sbrt_inverse_fast_kernel(BufTable bt, const BlkState* __restrict__ stIn, const B
                 w4 = __shfl_sync(FULL_MASK, inw, j & 31);
                 continue;
             }
-            const u32 w4n = __shfl_sync(FULL_MASK, inw, (j + 1) & 31);
-            const u32 i0 = (u32)(base + 4 * j);
-            u32 o4;
-            if (!((dm >> j) & 1u)) {
-                o4 = L.step_top((int)(w4 & 0xFF), i0, lane);
-                o4 |= L.step_top((int)((w4 >> 8) & 0xFF), i0 + 1, lane) << 8;
-                o4 |= L.step_top((int)((w4 >> 16) & 0xFF), i0 + 2, lane) << 16;
-                o4 |= L.step_top((int)(w4 >> 24), i0 + 3, lane) << 24;
-            } else {
-                o4 = 0;
+            if ((dm >> j) & 1u) {
+                const u32 i0 = (u32)(base + 4 * j);
+                u32 o4 = 0;
 #pragma unroll 1
                 for (int x = 0; x < 4; x++) {
                     const int r = (int)((w4 >> (8 * x)) & 0xFF);
                     const u32 c = (r < 32) ? L.step_top(r, i0 + x, lane) : L.step_deep(r, i0 + x, lane);
                     o4 |= c << (8 * x);
                 }
+                if (lane == j)
+                    outw = o4;
+                j++;
+                w4 = __shfl_sync(FULL_MASK, inw, j & 31);
+                continue;
             }
-            if (lane == j)
-                outw = o4;
-            j++;
-            w4 = w4n;
+            // up to four consecutive plain words per trip: the loop back-edge is the only
+            // taken branch, and the words were fetched before the chain needs them
+            const u32 nf = notfast >> j; // bit 0 is clear
+            int run = (nf == 0) ? 32 : (__ffs((int)nf) - 1);
+            run = min(min(run, 4), 32 - j);
+            const u32 wa = __shfl_sync(FULL_MASK, inw, (j + 1) & 31);
+            const u32 wb = __shfl_sync(FULL_MASK, inw, (j + 2) & 31);
+            const u32 wc = __shfl_sync(FULL_MASK, inw, (j + 3) & 31);
+            const u32 wnext = __shfl_sync(FULL_MASK, inw, (j + run) & 31);
+            word(w4, j);
+            if (run > 1) {
+                word(wa, j + 1);
+                if (run > 2) {
+                    word(wb, j + 2);
+                    if (run > 3)
+                        word(wc, j + 3);
+                }
+            }
+            j += run;
+            w4 = wnext;
         }
         if (cnt & 3) { // ragged tail of the block
             w4 = __shfl_sync(FULL_MASK, inw, fullWords & 31);

@@ -38,7 +38,7 @@ struct SortArrays {
     u64* key[2];
     u32* val[2];
     u32* hist;      // [nBlocks][maxTiles][256]
-    u32* digitBase; // [nBlocks][256]
+    int* ticket;    // [8][maxBlocks]: next tile index of block b in pass p (one-sweep)
     u32* totals;    // [nBlocks][8][256]
     int* which;     // [9][maxBlocks]: buffer index holding block b's data before pass p
     int* trivial;   // [8][maxBlocks]
@@ -104,69 +104,44 @@ __global__ void rs_plan_kernel(SortArrays A, int nBlocks)
     }
 }
 
-__global__ void __launch_bounds__(RS_THREADS)
-rs_hist_kernel(SortArrays A, int pass)
-{
-    __shared__ u32 s_h[256];
-    const int b = blockIdx.y;
-    const int cnt = A.cnt[b];
-    const int base = blockIdx.x * RS_TILE;
-    if (base >= cnt || A.trivial[pass * A.maxBlocks + b])
-        return;
-    s_h[threadIdx.x] = 0;
-    __syncthreads();
-    const u64* __restrict__ k = A.key[A.which[pass * A.maxBlocks + b]] + (i64)b * A.capN;
-    const int sh = 8 * pass;
-    u64 kv[RS_ITEMS];
-#pragma unroll
-    for (int it = 0; it < RS_ITEMS; it++) {
-        const int j = base + it * RS_THREADS + threadIdx.x;
-        kv[it] = (j < cnt) ? __ldg(&k[j]) : 0;
-    }
-#pragma unroll
-    for (int it = 0; it < RS_ITEMS; it++) {
-        const int j = base + it * RS_THREADS + threadIdx.x;
-        if (j < cnt)
-            atomicAdd(&s_h[(kv[it] >> sh) & 0xFF], 1u);
-    }
-    __syncthreads();
-    A.hist[((i64)b * A.maxTiles + blockIdx.x) * 256 + threadIdx.x] = s_h[threadIdx.x];
-}
+// One-sweep pass (Adinets & Merrill): histogram, tile offsets and scatter in ONE kernel.
+// The tile's digit counts are chained to its predecessors with a decoupled look-back over
+// status words (2 flag bits + 30-bit count) instead of a separate histogram pass and a
+// scan kernel, so a pass reads 12 and writes 12 bytes per element.  The sorted tile is
+// staged in shared memory and written out in sorted order: consecutive threads store
+// consecutive addresses inside a digit run.  Tiles take their index from a per-block
+// ticket, so every predecessor of a running tile is itself running or finished.
+#define OS_ITEMS 16
+#define OS_TILE (RS_THREADS * OS_ITEMS)
+#define OS_AGG 0x40000000u
+#define OS_INC 0x80000000u
+#define OS_VAL 0x3FFFFFFFu
+#define OS_SMEM (OS_TILE * 12 + (RS_THREADS / 32) * 256 * 4 + 2 * 256 * 4 + 64)
 
-// One CTA per block, thread = digit: exclusive prefix over tiles, then over digits.
-__global__ void __launch_bounds__(256)
-rs_scan_kernel(SortArrays A, int pass)
+__global__ void __launch_bounds__(RS_THREADS, 2)
+rs_onesweep_kernel(SortArrays A, int pass)
 {
-    __shared__ u32 s_w[8];
-    const int b = blockIdx.x;
+    KNZ_DYN_SMEM(os_smem);
+    u64* s_key = reinterpret_cast<u64*>(os_smem);
+    u32* s_val = reinterpret_cast<u32*>(os_smem + OS_TILE * 8);
+    u32(*s_cnt)[256] = reinterpret_cast<u32(*)[256]>(os_smem + OS_TILE * 12);
+    u32* s_delta = reinterpret_cast<u32*>(os_smem + OS_TILE * 12 + (RS_THREADS / 32) * 1024);
+    u32* s_toff = s_delta + 256;
+    u32* s_w = s_toff + 256; // 8 words for the block scan + 1 for the ticket
+    const int b = blockIdx.y;
     const int cnt = A.cnt[b];
     if (cnt <= 0 || A.trivial[pass * A.maxBlocks + b])
         return;
-    const int tiles = (cnt + RS_TILE - 1) / RS_TILE;
-    u32* h = A.hist + (i64)b * A.maxTiles * 256 + threadIdx.x;
-    u32 run = 0;
-    for (int t = 0; t < tiles; t++) {
-        const u32 v = h[(i64)t * 256];
-        h[(i64)t * 256] = run;
-        run += v;
-    }
-    u32 tot;
-    const u32 ex = block_excl_sum_256(run, s_w, &tot);
-    A.digitBase[(i64)b * 256 + threadIdx.x] = ex;
-}
-
-// Stable scatter of one tile.  Element order inside a tile: warp-major, then
-// iteration, then lane, which is also the order of the loads.
-__global__ void __launch_bounds__(RS_THREADS)
-rs_scatter_kernel(SortArrays A, int pass)
-{
-    __shared__ u32 s_cnt[RS_THREADS / 32][256];
-    __shared__ u32 s_base[256];
-    const int b = blockIdx.y;
-    const int cnt = A.cnt[b];
-    const int tbase = blockIdx.x * RS_TILE;
-    if (tbase >= cnt || A.trivial[pass * A.maxBlocks + b])
+    const int tiles = (cnt + OS_TILE - 1) / OS_TILE;
+    if ((int)blockIdx.x >= tiles)
         return;
+    if (threadIdx.x == 0)
+        s_w[8] = (u32)atomicAdd(&A.ticket[pass * A.maxBlocks + b], 1);
+    for (int i = threadIdx.x; i < (RS_THREADS / 32) * 256; i += RS_THREADS)
+        (&s_cnt[0][0])[i] = 0;
+    __syncthreads();
+    const int tile = (int)s_w[8];
+    const int tbase = tile * OS_TILE;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int src = A.which[pass * A.maxBlocks + b];
     const u64* __restrict__ kin = A.key[src] + (i64)b * A.capN;
@@ -174,58 +149,86 @@ rs_scatter_kernel(SortArrays A, int pass)
     u64* __restrict__ kout = A.key[src ^ 1] + (i64)b * A.capN;
     u32* __restrict__ vout = A.val[src ^ 1] + (i64)b * A.capN;
     const int sh = 8 * pass;
-    for (int i = threadIdx.x; i < (RS_THREADS / 32) * 256; i += RS_THREADS)
-        (&s_cnt[0][0])[i] = 0;
-    s_base[threadIdx.x] = A.digitBase[(i64)b * 256 + threadIdx.x] +
-                          A.hist[((i64)b * A.maxTiles + blockIdx.x) * 256 + threadIdx.x];
-    __syncthreads();
-    u64 key[RS_ITEMS];
-    u32 val[RS_ITEMS];
-    u32 rnk[RS_ITEMS];
-    // all loads first: 16 independent requests per thread in flight
+    u64 key[OS_ITEMS];
+    u32 val[OS_ITEMS];
+    u16 rnk[OS_ITEMS];
 #pragma unroll
-    for (int it = 0; it < RS_ITEMS; it++) {
-        const int j = tbase + w * (32 * RS_ITEMS) + it * 32 + lane;
+    for (int it = 0; it < OS_ITEMS; it++) {
+        const int j = tbase + w * (32 * OS_ITEMS) + it * 32 + lane;
         key[it] = (j < cnt) ? __ldg(&kin[j]) : 0;
     }
 #pragma unroll
-    for (int it = 0; it < RS_ITEMS; it++) {
-        const int j = tbase + w * (32 * RS_ITEMS) + it * 32 + lane;
+    for (int it = 0; it < OS_ITEMS; it++) {
+        const int j = tbase + w * (32 * OS_ITEMS) + it * 32 + lane;
         val[it] = (j < cnt) ? __ldg(&vin[j]) : 0;
     }
+    // rank inside the warp's 512 elements (load order = stable order)
 #pragma unroll
-    for (int it = 0; it < RS_ITEMS; it++) {
-        const int j = tbase + w * (32 * RS_ITEMS) + it * 32 + lane;
-        const bool ok = j < cnt;
-        const u32 d = ok ? (u32)((key[it] >> sh) & 0xFF) : 256u; // 256 = padding class
+    for (int it = 0; it < OS_ITEMS; it++) {
+        const int j = tbase + w * (32 * OS_ITEMS) + it * 32 + lane;
+        const u32 d = (j < cnt) ? (u32)((key[it] >> sh) & 0xFF) : 256u; // 256 = padding class
         const u32 peers = __match_any_sync(FULL_MASK, d);
         const u32 prior = (d < 256) ? s_cnt[w][d] : 0;
         __syncwarp();
         if (d < 256 && (peers & lanemask_lt()) == 0)
             s_cnt[w][d] = prior + __popc(peers);
         __syncwarp();
-        rnk[it] = prior + __popc(peers & lanemask_lt());
+        rnk[it] = (u16)(prior + __popc(peers & lanemask_lt()));
     }
     __syncthreads();
-    {
-        // exclusive prefix over warps for every digit (thread = digit)
-        u32 run = 0;
+    // thread = digit: warp prefixes, tile count, look-back, offsets
+    const int d = threadIdx.x;
+    u32 tcount = 0;
 #pragma unroll
-        for (int x = 0; x < RS_THREADS / 32; x++) {
-            const u32 v = s_cnt[x][threadIdx.x];
-            s_cnt[x][threadIdx.x] = run;
-            run += v;
+    for (int x = 0; x < RS_THREADS / 32; x++) {
+        const u32 v = s_cnt[x][d];
+        s_cnt[x][d] = tcount;
+        tcount += v;
+    }
+    volatile u32* st = A.hist + ((i64)b * A.maxTiles) * 256 + d;
+    st[(i64)tile * 256] = (tile == 0) ? (OS_INC | tcount) : (OS_AGG | tcount);
+    u32 before = 0; // elements with this digit in earlier tiles
+    for (int t = tile - 1; t >= 0;) {
+        const u32 v = st[(i64)t * 256];
+        if (v & OS_INC) {
+            before += v & OS_VAL;
+            break;
+        }
+        if (v & OS_AGG) {
+            before += v & OS_VAL;
+            t--;
+        }
+    }
+    if (tile > 0)
+        st[(i64)tile * 256] = OS_INC | (before + tcount);
+    u32 tot;
+    const u32 dbase = block_excl_sum_256(A.totals[(i64)b * 2048 + pass * 256 + d], s_w, &tot); // digits < d, whole block
+    const u32 toff = block_excl_sum_256(tcount, s_w, &tot);                                    // digits < d, this tile
+    s_delta[d] = dbase + before - toff;
+    const u32 mine = toff; // first staged slot of digit d
+    // stage in sorted order
+    s_toff[d] = mine;
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < OS_ITEMS; it++) {
+        const int j = tbase + w * (32 * OS_ITEMS) + it * 32 + lane;
+        if (j < cnt) {
+            const u32 dg = (u32)((key[it] >> sh) & 0xFF);
+            const u32 q = s_toff[dg] + s_cnt[w][dg] + rnk[it];
+            s_key[q] = key[it];
+            s_val[q] = val[it];
         }
     }
     __syncthreads();
+    const int valid = min(OS_TILE, cnt - tbase);
 #pragma unroll
-    for (int it = 0; it < RS_ITEMS; it++) {
-        const int j = tbase + w * (32 * RS_ITEMS) + it * 32 + lane;
-        if (j < cnt) {
-            const u32 d = (u32)((key[it] >> sh) & 0xFF);
-            const u32 pos = s_base[d] + s_cnt[w][d] + rnk[it];
-            kout[pos] = key[it];
-            vout[pos] = val[it];
+    for (int it = 0; it < OS_ITEMS; it++) {
+        const int q = it * RS_THREADS + threadIdx.x;
+        if (q < valid) {
+            const u64 k = s_key[q];
+            const u32 pos = s_delta[(u32)((k >> sh) & 0xFF)] + (u32)q;
+            kout[pos] = k;
+            vout[pos] = s_val[q];
         }
     }
 }
@@ -235,17 +238,25 @@ static void radix_sort(const SortArrays& A, int nBlocks, int maxCnt, u32 passMas
     const int tiles = (maxCnt + RS_TILE - 1) / RS_TILE;
     if (tiles <= 0)
         return;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(rs_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OS_SMEM);
+        attr = true;
+    }
     cudaMemsetAsync(A.totals, 0, sizeof(u32) * 2048 * (size_t)nBlocks, s);
+    cudaMemsetAsync(A.ticket, 0, sizeof(int) * 8 * (size_t)A.maxBlocks, s);
     KLAUNCH(rs_totals_kernel, dim3(tiles, nBlocks), RS_THREADS, s, A);
     KLAUNCH(rs_plan_kernel, (nBlocks + 63) / 64, 64, s, A, nBlocks);
     *launches += 2;
+    const int otiles = (maxCnt + OS_TILE - 1) / OS_TILE;
     for (int p = 0; p < 8; p++) {
         if (!((passMask >> p) & 1))
             continue; // digit statically zero for every key: the plan marks it trivial as well
-        KLAUNCH(rs_hist_kernel, dim3(tiles, nBlocks), RS_THREADS, s, A, p);
-        KLAUNCH(rs_scan_kernel, nBlocks, 256, s, A, p);
-        KLAUNCH(rs_scatter_kernel, dim3(tiles, nBlocks), RS_THREADS, s, A, p);
-        *launches += 3;
+        // status words of the tiles this pass can touch: [block][tile][256]
+        cudaMemset2DAsync(A.hist, sizeof(u32) * 256 * (size_t)A.maxTiles, 0, sizeof(u32) * 256 * (size_t)otiles,
+                          (size_t)nBlocks, s);
+        KLAUNCH_DYN(rs_onesweep_kernel, dim3(otiles, nBlocks), RS_THREADS, OS_SMEM, s, A, p);
+        *launches += 1;
     }
 }
 
@@ -773,7 +784,7 @@ void launch_bwt_forward(const StageLaunch& L, Workspace& ws, cudaStream_t s, u64
     A.val[0] = ws.valA;
     A.val[1] = ws.valB;
     A.hist = ws.hist;
-    A.digitBase = ws.digitBase;
+    A.ticket = reinterpret_cast<int*>(ws.digitBase);
     A.totals = ws.totals;
     A.which = ws.which;
     A.trivial = ws.trivial;
@@ -1188,7 +1199,7 @@ void launch_bwt_inverse(const StageLaunch& L, Workspace& ws, cudaStream_t s, u64
     A.val[0] = ws.valA;
     A.val[1] = ws.valB;
     A.hist = ws.hist;
-    A.digitBase = ws.digitBase;
+    A.ticket = reinterpret_cast<int*>(ws.digitBase);
     A.totals = ws.totals;
     A.which = ws.which;
     A.trivial = ws.trivial;

@@ -111,16 +111,37 @@ __global__ void rs_plan_kernel(SortArrays A, int nBlocks)
 // staged in shared memory and written out in sorted order: consecutive threads store
 // consecutive addresses inside a digit run.  Tiles take their index from a per-block
 // ticket, so every predecessor of a running tile is itself running or finished.
-#define OS_ITEMS 16
-#define OS_TILE (RS_THREADS * OS_ITEMS)
 #define OS_AGG 0x40000000u
 #define OS_INC 0x80000000u
 #define OS_VAL 0x3FFFFFFFu
-#define OS_SMEM (OS_TILE * 12 + (RS_THREADS / 32) * 256 * 4 + 2 * 256 * 4 + 64)
+#define OS_SMEM(items) (RS_THREADS * (items) * 12 + (RS_THREADS / 32) * 256 * 4 + 2 * 256 * 4 + 64)
 
-__global__ void __launch_bounds__(RS_THREADS, 2)
+#define OS_LOOK 8
+// status words travel on their own (the count is in the word): relaxed device-scope accesses
+__device__ __forceinline__ void os_publish(u32* p, u32 v)
+{
+#ifndef KNZ_SIM
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#else
+    *(volatile u32*)p = v;
+#endif
+}
+__device__ __forceinline__ u32 os_peek(const u32* p)
+{
+#ifndef KNZ_SIM
+    u32 v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+#else
+    return *(const volatile u32*)p;
+#endif
+}
+
+template <int OS_ITEMS>
+__global__ void __launch_bounds__(RS_THREADS, (OS_ITEMS <= 8) ? 4 : 2)
 rs_onesweep_kernel(SortArrays A, int pass)
 {
+    constexpr int OS_TILE = RS_THREADS * OS_ITEMS;
     KNZ_DYN_SMEM(os_smem);
     u64* s_key = reinterpret_cast<u64*>(os_smem);
     u32* s_val = reinterpret_cast<u32*>(os_smem + OS_TILE * 8);
@@ -185,22 +206,29 @@ rs_onesweep_kernel(SortArrays A, int pass)
         s_cnt[x][d] = tcount;
         tcount += v;
     }
-    volatile u32* st = A.hist + ((i64)b * A.maxTiles) * 256 + d;
-    st[(i64)tile * 256] = (tile == 0) ? (OS_INC | tcount) : (OS_AGG | tcount);
+    u32* st = A.hist + ((i64)b * A.maxTiles) * 256 + d;
+    os_publish(st + (i64)tile * 256, (tile == 0) ? (OS_INC | tcount) : (OS_AGG | tcount));
     u32 before = 0; // elements with this digit in earlier tiles
+    // look-back, OS_LOOK predecessors per round trip (the loads are independent)
     for (int t = tile - 1; t >= 0;) {
-        const u32 v = st[(i64)t * 256];
-        if (v & OS_INC) {
-            before += v & OS_VAL;
-            break;
-        }
-        if (v & OS_AGG) {
-            before += v & OS_VAL;
+        u32 v[OS_LOOK];
+#pragma unroll
+        for (int k = 0; k < OS_LOOK; k++)
+            v[k] = (t - k >= 0) ? os_peek(st + (i64)(t - k) * 256) : OS_INC; // nothing precedes tile 0
+        bool done = false;
+#pragma unroll
+        for (int k = 0; k < OS_LOOK; k++) {
+            if (done || !(v[k] & (OS_INC | OS_AGG)))
+                break; // not published yet: poll again from this tile
+            before += v[k] & OS_VAL;
             t--;
+            done = (v[k] & OS_INC) != 0;
         }
+        if (done)
+            break;
     }
     if (tile > 0)
-        st[(i64)tile * 256] = OS_INC | (before + tcount);
+        os_publish(st + (i64)tile * 256, OS_INC | (before + tcount));
     u32 tot;
     const u32 dbase = block_excl_sum_256(A.totals[(i64)b * 2048 + pass * 256 + d], s_w, &tot); // digits < d, whole block
     const u32 toff = block_excl_sum_256(tcount, s_w, &tot);                                    // digits < d, this tile
@@ -238,24 +266,30 @@ static void radix_sort(const SortArrays& A, int nBlocks, int maxCnt, u32 passMas
     const int tiles = (maxCnt + RS_TILE - 1) / RS_TILE;
     if (tiles <= 0)
         return;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(rs_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OS_SMEM);
-        attr = true;
+    static int items = 0;
+    if (!items) {
+        const char* e = getenv("KNZ_OS_ITEMS"); // experiments: 8 (4 CTAs/SM) or 16 (2 CTAs/SM)
+        items = (e && atoi(e) == 16) ? 16 : 8;
+        cudaFuncSetAttribute(rs_onesweep_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, OS_SMEM(8));
+        cudaFuncSetAttribute(rs_onesweep_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, OS_SMEM(16));
     }
     cudaMemsetAsync(A.totals, 0, sizeof(u32) * 2048 * (size_t)nBlocks, s);
     cudaMemsetAsync(A.ticket, 0, sizeof(int) * 8 * (size_t)A.maxBlocks, s);
     KLAUNCH(rs_totals_kernel, dim3(tiles, nBlocks), RS_THREADS, s, A);
     KLAUNCH(rs_plan_kernel, (nBlocks + 63) / 64, 64, s, A, nBlocks);
     *launches += 2;
-    const int otiles = (maxCnt + OS_TILE - 1) / OS_TILE;
+    const int otile = RS_THREADS * items;
+    const int otiles = (maxCnt + otile - 1) / otile;
     for (int p = 0; p < 8; p++) {
         if (!((passMask >> p) & 1))
             continue; // digit statically zero for every key: the plan marks it trivial as well
         // status words of the tiles this pass can touch: [block][tile][256]
         cudaMemset2DAsync(A.hist, sizeof(u32) * 256 * (size_t)A.maxTiles, 0, sizeof(u32) * 256 * (size_t)otiles,
                           (size_t)nBlocks, s);
-        KLAUNCH_DYN(rs_onesweep_kernel, dim3(otiles, nBlocks), RS_THREADS, OS_SMEM, s, A, p);
+        if (items == 16)
+            KLAUNCH_DYN(rs_onesweep_kernel<16>, dim3(otiles, nBlocks), RS_THREADS, OS_SMEM(16), s, A, p);
+        else
+            KLAUNCH_DYN(rs_onesweep_kernel<8>, dim3(otiles, nBlocks), RS_THREADS, OS_SMEM(8), s, A, p);
         *launches += 1;
     }
 }

@@ -1022,11 +1022,12 @@ bwt_inv_init_kernel(BufTable bt, const BlkState* __restrict__ st, const int* __r
 
 // psi walk, parallelised by list ranking with splitters (Helman-JaJa style):
 //   nodes   = every 256th sorted position + the (<= 8) primary-index positions
-//   walk 1  = every node follows psi to the next node: (next node, segment length)
+//   walk    = every node follows psi to the next node and keeps the symbols of its segment
+//             in a private slot: (next node, segment length)
 //   rank    = one thread per primary index walks the ~n/256 nodes of its chunk and
 //             hands every node its text offset
-//   walk 2  = every node re-walks its segment and writes the bytes in place.
-// packed[t] = (psi[t] << 8) | F[t]  (one 8-byte gather per step).
+//   copy    = one warp per node moves the slot to its text offset.
+// packed[t] = (psi[t] << 8) | F[t]  (one 4- or 8-byte gather per step).
 struct InvCtx {
     BufTable bt;
     const BlkState* stIn;
@@ -1040,6 +1041,7 @@ struct InvCtx {
     int capN, nodeStride, nBlocks;
     int b0;     // first block of the group a walk launch covers (L2-sized groups)
     int narrow; // 1: packed entries are 32-bit ((psi << 8) | F, blocks < 16 MiB), else 64-bit
+    int slot;   // bytes of symbol storage per node (multiple of 4)
     int* errFlag;
 };
 
@@ -1114,7 +1116,25 @@ bwt_inv_pack_kernel(InvCtx C)
     }
 }
 
-template <int PASS>
+// entry t of the packed psi array -> (symbol, next position); BWT_END when the text ends here
+__device__ __forceinline__ u32 inv_entry(const u64* __restrict__ P, bool narrow, u32 t, u32& nxt)
+{
+    if (narrow) {
+        const u32 e = reinterpret_cast<const u32*>(P)[t];
+        nxt = e >> 8;
+        if (nxt == 0x00FFFFFFu)
+            nxt = BWT_END;
+        return e & 0xFF;
+    }
+    const u64 e = P[t];
+    nxt = (u32)(e >> 8);
+    return (u32)(e & 0xFF);
+}
+
+// ONE walk: every node follows psi to the next node and keeps the symbols it meets in its
+// own INV_SLOT-byte slot (segments average 256 symbols; the 0.25% that overflow the slot
+// are re-walked by the copy kernel from the position saved in nd[3]).
+#define INV_SLOT 1536 // upper bound; small blocks get a smaller slot (InvCtx::slot)
 __global__ void __launch_bounds__(128)
 bwt_inv_walk_kernel(InvCtx C)
 {
@@ -1131,60 +1151,87 @@ bwt_inv_walk_kernel(InvCtx C)
     u32 t = inv_node_pos(B, id, &valid);
     u32* nd = C.node + ((i64)b * C.nodeStride + id) * 4;
     if (!valid || t >= (u32)B.m) {
-        if (PASS == 1) {
-            nd[0] = 0xFFFFFFFFu;
-            nd[1] = 0;
-            nd[2] = 0xFFFFFFFFu;
-        }
+        nd[0] = 0xFFFFFFFFu;
+        nd[1] = 0;
+        nd[2] = 0xFFFFFFFFu;
+        nd[3] = 0;
         return;
     }
-    const u64* __restrict__ P = C.packed[C.whichAfter[b] ^ 1] + (i64)b * C.capN;
-    const u32* __restrict__ P32 = reinterpret_cast<const u32*>(P);
+    const int w = C.whichAfter[b];
+    const u64* __restrict__ P = C.packed[w ^ 1] + (i64)b * C.capN;
+    u32* __restrict__ slot = reinterpret_cast<u32*>(C.packed[w] + (i64)b * C.capN) + (i64)id * (C.slot / 4);
+    const u32 cap = (u32)C.slot;
     const bool narrow = C.narrow != 0;
-    // entry t -> (symbol, next position); BWT_END when the text ends here
-    auto entry = [&](u32 t, u32& nxt) -> u32 {
-        if (narrow) {
-            const u32 e = P32[t];
-            nxt = e >> 8;
-            if (nxt == 0x00FFFFFFu)
-                nxt = BWT_END;
-            return e & 0xFF;
-        }
-        const u64 e = P[t];
-        nxt = (u32)(e >> 8);
-        return (u32)(e & 0xFF);
-    };
-    if (PASS == 1) {
-        u32 len = 0;
-        int nxt = -1;
-        for (;;) {
-            u32 nx;
-            entry(t, nx);
-            len++;
-            t = nx;
-            if (t == BWT_END)
-                break;
-            if (t >= (u32)B.m || len > (u32)B.m) { // not a permutation: malformed input
-                atomicExch(C.errFlag, KERR_BAD_STREAM);
-                break;
+    u32 len = 0, acc = 0, tcap = 0;
+    int nxt = -1;
+    for (;;) {
+        u32 nx;
+        const u32 sym = inv_entry(P, narrow, t, nx);
+        if (len < cap) {
+            acc |= sym << (8 * (len & 3));
+            if ((len & 3) == 3) {
+                slot[len >> 2] = acc;
+                acc = 0;
             }
-            nxt = inv_node_of(B, t);
-            if (nxt >= 0)
-                break;
         }
-        nd[0] = (u32)nxt;
-        nd[1] = len;
-        nd[2] = 0xFFFFFFFFu;
-    } else {
-        const u32 base = nd[2];
-        const u32 len = nd[1];
-        if (base == 0xFFFFFFFFu || (u64)base + len > (u64)B.m)
-            return;
-        u8* __restrict__ dst = blk_dst(C.bt, bs, b) + base;
-        for (u32 k = 0; k < len; k++) {
-            u32 nx;
-            dst[k] = (u8)entry(t, nx);
-            t = nx;
+        len++;
+        t = nx;
+        if (len == cap)
+            tcap = t;
+        if (t == BWT_END)
+            break;
+        if (t >= (u32)B.m || len > (u32)B.m) { // not a permutation: malformed input
+            atomicExch(C.errFlag, KERR_BAD_STREAM);
+            break;
+        }
+        nxt = inv_node_of(B, t);
+        if (nxt >= 0)
+            break;
+    }
+    if (len < cap && (len & 3))
+        slot[len >> 2] = acc;
+    nd[0] = (u32)nxt;
+    nd[1] = len;
+    nd[2] = 0xFFFFFFFFu;
+    nd[3] = tcap;
+}
+
+// Segments to their text offsets: one warp per node copies the slot; the rare overflow
+// tail is re-walked by lane 0.
+__global__ void __launch_bounds__(256)
+bwt_inv_copy_kernel(InvCtx C)
+{
+    const int b = C.b0 + blockIdx.y;
+    if (b >= C.nBlocks || !C.bwtOk[b])
+        return;
+    const BlkState bs = C.stIn[b];
+    const u8* __restrict__ src = blk_src(C.bt, bs, b);
+    const InvBlk B = inv_blk(C, b, src, bs.len);
+    const int lane = threadIdx.x & 31;
+    const int w = C.whichAfter[b];
+    const u64* __restrict__ P = C.packed[w ^ 1] + (i64)b * C.capN;
+    const u8* __restrict__ slots = reinterpret_cast<const u8*>(C.packed[w] + (i64)b * C.capN);
+    const bool narrow = C.narrow != 0;
+    u8* __restrict__ dst = blk_dst(C.bt, bs, b);
+    const int warpsPerGrid = gridDim.x * (blockDim.x >> 5);
+    for (int id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); id < B.S + 8; id += warpsPerGrid) {
+        const u32* nd = C.node + ((i64)b * C.nodeStride + id) * 4;
+        const u32 len = nd[1], base = nd[2];
+        if (len == 0 || base == 0xFFFFFFFFu || (u64)base + len > (u64)B.m)
+            continue;
+        const u32 cap = (u32)C.slot;
+        const u32 n = len < cap ? len : cap;
+        const u8* __restrict__ sp = slots + (i64)id * cap;
+        u8* __restrict__ d = dst + base;
+        for (u32 k = lane; k < n; k += 32)
+            d[k] = sp[k];
+        if (len > cap && lane == 0) {
+            u32 t = nd[3];
+            for (u32 k = cap; k < len; k++) {
+                u32 nx;
+                d[k] = (u8)inv_entry(P, narrow, t, nx);
+                t = nx;
+            }
         }
     }
 }
@@ -1264,32 +1311,16 @@ void launch_bwt_inverse(const StageLaunch& L, Workspace& ws, cudaStream_t s, u64
     const int packBlocks = min((L.maxLen + 255) / 256, 1024);
     KLAUNCH(bwt_inv_pack_kernel, dim3(packBlocks, nB), 256, s, C);
     const int nodes = ((L.maxLen + 255) >> SPL_LOG) + 8;
-    // The walks are latency-bound pointer chases: they want every resident thread slot
-    // busy, which matters more than keeping the packed arrays inside L2 (measured: groups
-    // of 6 blocks = 96 MB halve the throughput).  KNZ_INV_GROUP overrides for experiments.
-    int grp = nB;
     {
-        static int envGrp = -1;
-        if (envGrp < 0) {
-            const char* e = getenv("KNZ_INV_GROUP");
-            envGrp = e ? atoi(e) : 0;
-        }
-        if (envGrp > 0)
-            grp = envGrp;
+        // the slots live in the sort's input buffer (8 * capN bytes per block, free after the pack)
+        const i64 maxNodes = ((i64)ws.capN >> SPL_LOG) + 9;
+        const i64 fit = (8 * (i64)ws.capN / maxNodes) & ~(i64)3;
+        C.slot = (int)(fit < INV_SLOT ? fit : INV_SLOT);
     }
-    grp = grp < 1 ? 1 : (grp > nB ? nB : grp);
-    for (int g0 = 0; g0 < nB; g0 += grp) {
-        C.b0 = g0;
-        KLAUNCH(bwt_inv_walk_kernel<1>, dim3((nodes + 127) / 128, min(grp, nB - g0)), 128, s, C);
-        *launches += 1;
-    }
+    KLAUNCH(bwt_inv_walk_kernel, dim3((nodes + 127) / 128, nB), 128, s, C);
     KLAUNCH(bwt_inv_rank_kernel, (nB * 8 + 63) / 64, 64, s, C);
-    *launches += 1;
-    for (int g0 = 0; g0 < nB; g0 += grp) {
-        C.b0 = g0;
-        KLAUNCH(bwt_inv_walk_kernel<2>, dim3((nodes + 127) / 128, min(grp, nB - g0)), 128, s, C);
-        *launches += 1;
-    }
+    KLAUNCH(bwt_inv_copy_kernel, dim3(min((nodes + 7) / 8, 1024), nB), 256, s, C);
+    *launches += 3;
 }
 
 // ------------------------------------------------------------------ misc stages

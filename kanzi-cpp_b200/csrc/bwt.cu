@@ -999,27 +999,6 @@ __global__ void bwt_inv_decide_kernel(StageLaunch L, int* __restrict__ cnt, int*
     bwtOk[b] = 1;
 }
 
-// keys = L column bytes, vals = row -> suffix-rank mapping (BWT.cpp:203-219):
-// row 0 is the end-of-string row, rows 1..p0-1 hold ranks 0..p0-2, rows >= p0 hold their own index.
-__global__ void __launch_bounds__(256)
-bwt_inv_init_kernel(BufTable bt, const BlkState* __restrict__ st, const int* __restrict__ bwtOk,
-                    const int* __restrict__ pidx, int capN, u64* __restrict__ keyOut, u32* __restrict__ valOut)
-{
-    const int b = blockIdx.y;
-    if (!bwtOk[b])
-        return;
-    const BlkState bs = st[b];
-    const u8* __restrict__ src = blk_src(bt, bs, b);
-    const int mode = src[0];
-    const int hdr = 1 + (1 << ((mode >> 2) & 7)) * ((mode & 3) + 1);
-    const int m = bs.len - hdr;
-    const int p0 = pidx[b * 8];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
-        keyOut[(i64)b * capN + i] = (u64)src[hdr + i];
-        valOut[(i64)b * capN + i] = (i == 0) ? BWT_END : ((i < p0) ? (u32)(i - 1) : (u32)i);
-    }
-}
-
 // psi walk, parallelised by list ranking with splitters (Helman-JaJa style):
 //   nodes   = every 256th sorted position + the (<= 8) primary-index positions
 //   walk    = every node follows psi to the next node and keeps the symbols of its segment
@@ -1033,10 +1012,11 @@ struct InvCtx {
     const BlkState* stIn;
     const int* bwtOk;
     const int* pidx;
-    const int* whichAfter;
-    const u64* key[2];
-    const u32* val[2];
-    u64* packed[2];
+    u64* packed[2]; // [0]: symbol slots of the walk, [1]: packed psi
+    u32* symTotals; // [nBlocks][256]
+    u32* status;    // one-sweep status words [nBlocks][statusStride][256]
+    int* ticket;    // [nBlocks]
+    int statusStride;
     u32* node; // [nBlocks][nodeStride][4]: next, len, base, pad
     int capN, nodeStride, nBlocks;
     int b0;     // first block of the group a walk launch covers (L2-sized groups)
@@ -1092,27 +1072,151 @@ __device__ __forceinline__ u32 inv_node_pos(const InvBlk& B, int id, bool* valid
     return t;
 }
 
+// Symbol totals of the L column, per block (the digit bases of the counting sort below).
 __global__ void __launch_bounds__(256)
-bwt_inv_pack_kernel(InvCtx C)
+bwt_inv_hist_kernel(InvCtx C)
 {
+    __shared__ u32 s_h[256];
     const int b = blockIdx.y;
     if (!C.bwtOk[b])
         return;
     const BlkState bs = C.stIn[b];
     const u8* __restrict__ src = blk_src(C.bt, bs, b);
     const int mode = src[0];
-    const int m = bs.len - (1 + (1 << ((mode >> 2) & 7)) * ((mode & 3) + 1));
-    const int w = C.whichAfter[b];
-    const u64* __restrict__ F = C.key[w] + (i64)b * C.capN;
-    const u32* __restrict__ nx = C.val[w] + (i64)b * C.capN;
-    u64* __restrict__ P = C.packed[w ^ 1] + (i64)b * C.capN;
-    u32* __restrict__ P32 = reinterpret_cast<u32*>(P);
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < m; t += gridDim.x * blockDim.x) {
-        const u32 nxv = nx[t];
-        if (C.narrow) // psi < 2^24; the end marker keeps its all-ones pattern in 24 bits
-            P32[t] = (nxv << 8) | (u32)(F[t] & 0xFF);
-        else
-            P[t] = ((u64)nxv << 8) | (F[t] & 0xFF);
+    const int hdr = 1 + (1 << ((mode >> 2) & 7)) * ((mode & 3) + 1);
+    const int m = bs.len - hdr;
+    const int base = blockIdx.x * 8192;
+    if (base >= m)
+        return;
+    s_h[threadIdx.x] = 0;
+    __syncthreads();
+    const int end = min(base + 8192, m);
+    for (int i = base + threadIdx.x; i < end; i += 256)
+        atomicAdd(&s_h[src[hdr + i]], 1u);
+    __syncthreads();
+    if (s_h[threadIdx.x])
+        atomicAdd(&C.symTotals[(i64)b * 256 + threadIdx.x], s_h[threadIdx.x]);
+}
+
+// psi by ONE stable counting-sort pass over the L bytes (BWT.cpp:203-219 builds the same
+// mapping with a serial bucket scan): sorted position of row i = C[L[i]] + #{i' < i : L[i'] = L[i]},
+// and that position receives (row -> suffix-rank value of i) << 8 | L[i].  Same one-sweep
+// structure as the radix pass (tickets, look-back status words, shared-memory staging),
+// but the element is a byte on the way in and the packed psi entry on the way out:
+// 1 + 4 bytes of traffic per symbol instead of an init / sort / pack chain over 12-byte pairs.
+#define PSI_ITEMS 8
+#define PSI_TILE (RS_THREADS * PSI_ITEMS)
+template <bool NARROW>
+__global__ void __launch_bounds__(RS_THREADS, 4)
+bwt_inv_psi_kernel(InvCtx C)
+{
+    __shared__ u32 s_cnt[RS_THREADS / 32][256];
+    __shared__ u32 s_delta[256], s_toff[256], s_w[9];
+    __shared__ u64 s_out64[NARROW ? 1 : PSI_TILE];
+    __shared__ u32 s_out32[NARROW ? PSI_TILE : 1];
+    const int b = blockIdx.y;
+    if (!C.bwtOk[b])
+        return;
+    const BlkState bs = C.stIn[b];
+    const u8* __restrict__ src = blk_src(C.bt, bs, b);
+    const int mode = src[0];
+    const int hdr = 1 + (1 << ((mode >> 2) & 7)) * ((mode & 3) + 1);
+    const int m = bs.len - hdr;
+    const int tiles = (m + PSI_TILE - 1) / PSI_TILE;
+    if ((int)blockIdx.x >= tiles)
+        return;
+    if (threadIdx.x == 0)
+        s_w[8] = (u32)atomicAdd(&C.ticket[b], 1);
+    for (int i = threadIdx.x; i < (RS_THREADS / 32) * 256; i += RS_THREADS)
+        (&s_cnt[0][0])[i] = 0;
+    __syncthreads();
+    const int tile = (int)s_w[8];
+    const int tbase = tile * PSI_TILE;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const u32 p0 = (u32)C.pidx[b * 8];
+    u32 sym[PSI_ITEMS];
+    u16 rnk[PSI_ITEMS];
+#pragma unroll
+    for (int it = 0; it < PSI_ITEMS; it++) {
+        const int j = tbase + w * (32 * PSI_ITEMS) + it * 32 + lane;
+        sym[it] = (j < m) ? (u32)src[hdr + j] : 256u; // 256 = padding class
+    }
+#pragma unroll
+    for (int it = 0; it < PSI_ITEMS; it++) {
+        const u32 d = sym[it];
+        const u32 peers = __match_any_sync(FULL_MASK, d);
+        const u32 prior = (d < 256) ? s_cnt[w][d] : 0;
+        __syncwarp();
+        if (d < 256 && (peers & lanemask_lt()) == 0)
+            s_cnt[w][d] = prior + __popc(peers);
+        __syncwarp();
+        rnk[it] = (u16)(prior + __popc(peers & lanemask_lt()));
+    }
+    __syncthreads();
+    const int d = threadIdx.x;
+    u32 tcount = 0;
+#pragma unroll
+    for (int x = 0; x < RS_THREADS / 32; x++) {
+        const u32 v = s_cnt[x][d];
+        s_cnt[x][d] = tcount;
+        tcount += v;
+    }
+    u32* st = C.status + ((i64)b * C.statusStride) * 256 + d;
+    os_publish(st + (i64)tile * 256, (tile == 0) ? (OS_INC | tcount) : (OS_AGG | tcount));
+    u32 before = 0;
+    for (int t = tile - 1; t >= 0;) {
+        u32 v[OS_LOOK];
+#pragma unroll
+        for (int k = 0; k < OS_LOOK; k++)
+            v[k] = (t - k >= 0) ? os_peek(st + (i64)(t - k) * 256) : OS_INC;
+        bool done = false;
+#pragma unroll
+        for (int k = 0; k < OS_LOOK; k++) {
+            if (done || !(v[k] & (OS_INC | OS_AGG)))
+                break;
+            before += v[k] & OS_VAL;
+            t--;
+            done = (v[k] & OS_INC) != 0;
+        }
+        if (done)
+            break;
+    }
+    if (tile > 0)
+        os_publish(st + (i64)tile * 256, OS_INC | (before + tcount));
+    u32 tot;
+    const u32 dbase = block_excl_sum_256(C.symTotals[(i64)b * 256 + d], s_w, &tot);
+    const u32 toff = block_excl_sum_256(tcount, s_w, &tot);
+    s_delta[d] = dbase + before - toff;
+    s_toff[d] = toff;
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < PSI_ITEMS; it++) {
+        const int j = tbase + w * (32 * PSI_ITEMS) + it * 32 + lane;
+        if (j < m) {
+            const u32 q = s_toff[sym[it]] + s_cnt[w][sym[it]] + rnk[it];
+            // row -> suffix rank: row 0 ends the text, rows < p0 hold rank row-1, rows >= p0 their index
+            const u32 nxv = (j == 0) ? BWT_END : (((u32)j < p0) ? (u32)(j - 1) : (u32)j);
+            if (NARROW)
+                s_out32[q] = (nxv << 8) | sym[it]; // the end marker keeps its all-ones pattern in 24 bits
+            else
+                s_out64[q] = ((u64)nxv << 8) | (u64)sym[it];
+        }
+    }
+    __syncthreads();
+    const int valid = min(PSI_TILE, m - tbase);
+    u64* __restrict__ P = C.packed[1] + (i64)b * C.capN;
+#pragma unroll
+    for (int it = 0; it < PSI_ITEMS; it++) {
+        const int q = it * RS_THREADS + threadIdx.x;
+        if (q < valid) {
+            if (NARROW) {
+                const u32 e = s_out32[q];
+                reinterpret_cast<u32*>(P)[s_delta[e & 0xFF] + (u32)q] = e;
+            } else {
+                const u64 e = s_out64[q];
+                P[s_delta[(u32)(e & 0xFF)] + (u32)q] = e;
+            }
+        }
     }
 }
 
@@ -1157,9 +1261,8 @@ bwt_inv_walk_kernel(InvCtx C)
         nd[3] = 0;
         return;
     }
-    const int w = C.whichAfter[b];
-    const u64* __restrict__ P = C.packed[w ^ 1] + (i64)b * C.capN;
-    u32* __restrict__ slot = reinterpret_cast<u32*>(C.packed[w] + (i64)b * C.capN) + (i64)id * (C.slot / 4);
+    const u64* __restrict__ P = C.packed[1] + (i64)b * C.capN;
+    u32* __restrict__ slot = reinterpret_cast<u32*>(C.packed[0] + (i64)b * C.capN) + (i64)id * (C.slot / 4);
     const u32 cap = (u32)C.slot;
     const bool narrow = C.narrow != 0;
     u32 len = 0, acc = 0, tcap = 0;
@@ -1208,9 +1311,8 @@ bwt_inv_copy_kernel(InvCtx C)
     const u8* __restrict__ src = blk_src(C.bt, bs, b);
     const InvBlk B = inv_blk(C, b, src, bs.len);
     const int lane = threadIdx.x & 31;
-    const int w = C.whichAfter[b];
-    const u64* __restrict__ P = C.packed[w ^ 1] + (i64)b * C.capN;
-    const u8* __restrict__ slots = reinterpret_cast<const u8*>(C.packed[w] + (i64)b * C.capN);
+    const u64* __restrict__ P = C.packed[1] + (i64)b * C.capN;
+    const u8* __restrict__ slots = reinterpret_cast<const u8*>(C.packed[0] + (i64)b * C.capN);
     const bool narrow = C.narrow != 0;
     u8* __restrict__ dst = blk_dst(C.bt, bs, b);
     const int warpsPerGrid = gridDim.x * (blockDim.x >> 5);
@@ -1271,45 +1373,37 @@ void launch_bwt_inverse(const StageLaunch& L, Workspace& ws, cudaStream_t s, u64
     const int nB = L.nBlocks;
     const int maxTiles = (ws.capN + RS_TILE - 1) / RS_TILE;
     KLAUNCH(bwt_inv_decide_kernel, (nB + 63) / 64, 64, s, L, ws.cnt, ws.which, ws.pidx, ws.bwtOk);
-    const int initBlocks = min((L.maxLen + 255) / 256, 1024);
-    KLAUNCH(bwt_inv_init_kernel, dim3(initBlocks, nB), 256, s, L.bt, L.stIn, ws.bwtOk, ws.pidx, ws.capN, ws.keyA, ws.valA);
-    *launches += 2;
-    SortArrays A;
-    A.key[0] = ws.keyA;
-    A.key[1] = ws.keyB;
-    A.val[0] = ws.valA;
-    A.val[1] = ws.valB;
-    A.hist = ws.hist;
-    A.ticket = reinterpret_cast<int*>(ws.digitBase);
-    A.totals = ws.totals;
-    A.which = ws.which;
-    A.trivial = ws.trivial;
-    A.cnt = ws.cnt;
-    A.capN = ws.capN;
-    A.maxTiles = maxTiles;
-    A.maxBlocks = ws.maxBlocks;
-    radix_sort(A, nB, L.maxLen, 0x01u, s, launches); // stable counting sort by symbol = LF/psi construction
+    *launches += 1;
     InvCtx C;
     C.bt = L.bt;
     C.stIn = L.stIn;
     C.bwtOk = ws.bwtOk;
     C.pidx = ws.pidx;
-    C.whichAfter = ws.which + 8 * ws.maxBlocks;
-    C.key[0] = ws.keyA;
-    C.key[1] = ws.keyB;
-    C.val[0] = ws.valA;
-    C.val[1] = ws.valB;
     C.packed[0] = ws.keyA;
     C.packed[1] = ws.keyB;
-    C.node = ws.hist; // [maxBlocks][sTiles*256] u32 >= 4 * (capN/256 + 8) per block
+    C.symTotals = ws.totals;
+    C.status = ws.hist;
+    C.statusStride = maxTiles;
+    C.ticket = reinterpret_cast<int*>(ws.digitBase);
+    C.node = ws.hist; // [maxBlocks][sTiles*256] u32 >= 4 * (capN/256 + 8) per block (after the psi pass)
     C.capN = ws.capN;
     C.nodeStride = maxTiles * 64;
     C.nBlocks = nB;
     C.b0 = 0;
     C.narrow = (L.maxLen < (1 << 24) - 1) ? 1 : 0;
     C.errFlag = L.errFlag;
-    const int packBlocks = min((L.maxLen + 255) / 256, 1024);
-    KLAUNCH(bwt_inv_pack_kernel, dim3(packBlocks, nB), 256, s, C);
+    {
+        const int ptiles = (L.maxLen + PSI_TILE - 1) / PSI_TILE;
+        cudaMemsetAsync(ws.totals, 0, sizeof(u32) * 256 * (size_t)nB, s);
+        cudaMemsetAsync(C.ticket, 0, sizeof(int) * (size_t)nB, s);
+        cudaMemset2DAsync(C.status, sizeof(u32) * 256 * (size_t)maxTiles, 0, sizeof(u32) * 256 * (size_t)ptiles, (size_t)nB, s);
+        KLAUNCH(bwt_inv_hist_kernel, dim3((L.maxLen + 8191) / 8192, nB), 256, s, C);
+        if (C.narrow)
+            KLAUNCH(bwt_inv_psi_kernel<true>, dim3(ptiles, nB), RS_THREADS, s, C);
+        else
+            KLAUNCH(bwt_inv_psi_kernel<false>, dim3(ptiles, nB), RS_THREADS, s, C);
+        *launches += 2;
+    }
     const int nodes = ((L.maxLen + 255) >> SPL_LOG) + 8;
     {
         // the slots live in the sort's input buffer (8 * capN bytes per block, free after the pack)

@@ -24,7 +24,8 @@
 struct knz_ctx {
     int device, maxBlockSize, maxBatch;
     cudaStream_t stream;
-    cudaStream_t copyStream; // host<->device staging of the stream-level API (overlaps with compute)
+    cudaStream_t copyStream; // host->device staging of the stream-level API (overlaps with compute)
+    cudaStream_t d2hStream;  // device->host copies of finished output (second DMA direction)
     cudaEvent_t evCopy[2], evDone[2];
     cudaEvent_t ev[10];
     i64 bstride;     // stride of the ping-pong stage buffers
@@ -162,6 +163,7 @@ extern "C" int knz_create(int device, int maxBlockSize, int maxBatchBlocks, knz_
 #define A(call) ok = ok && ((call) == cudaSuccess)
     A(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     A(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+    A(cudaStreamCreateWithFlags(&ctx->d2hStream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) {
         A(cudaEventCreate(&ctx->evCopy[i]));
         A(cudaEventCreate(&ctx->evDone[i]));
@@ -238,6 +240,8 @@ extern "C" void knz_destroy(knz_ctx* ctx)
     }
     if (ctx->copyStream)
         cudaStreamDestroy(ctx->copyStream);
+    if (ctx->d2hStream)
+        cudaStreamDestroy(ctx->d2hStream);
     if (ctx->stream)
         cudaStreamDestroy(ctx->stream);
     free(ctx);
@@ -612,9 +616,24 @@ extern "C" int knz_compress(knz_ctx* ctx, const char* transform, const char* ent
     int rc = grow(ctx, &ctx->dStream, &ctx->dStreamCap, streamCap);
     if (rc != KNZ_OK)
         return rc;
-    // Encode in sub-batches of <= 64 blocks: the pinned-host -> device copy of sub-batch
-    // i+1 runs on the copy stream while sub-batch i is being encoded.
-    const int eb = (ctx->maxBatch < 64) ? ctx->maxBatch : 64;
+    // Encode in sub-batches: the pinned-host -> device copy of sub-batch i+1 runs on the copy
+    // stream while sub-batch i is being encoded, and the finished bytes of the stream go back
+    // to the host on a third stream.  The first sub-batch is small (its copy is exposed),
+    // later ones are large (GPU efficiency, fewer round trips).
+    static int sched[3] = { 0, 0, 0 }; // KNZ_ENC_BATCH=a,b,c overrides the schedule (experiments)
+    if (!sched[0]) {
+        sched[0] = 32, sched[1] = 96, sched[2] = 128;
+        const char* e = getenv("KNZ_ENC_BATCH");
+        if (e)
+            sscanf(e, "%d,%d,%d", &sched[0], &sched[1], &sched[2]);
+    }
+    auto batchSize = [&](int k, i64 left) -> int {
+        const int want = sched[k < 2 ? k : 2];
+        const int lim = (want < ctx->maxBatch) ? want : ctx->maxBatch;
+        return (int)((left < lim) ? left : lim);
+    };
+    const int ebWant = (sched[1] > sched[2]) ? (sched[1] > sched[0] ? sched[1] : sched[0]) : (sched[2] > sched[0] ? sched[2] : sched[0]);
+    const int eb = (ctx->maxBatch < ebWant) ? ctx->maxBatch : ebWant;
     const i64 plainBytes = round_up((i64)eb * blockSize + 256, 256);
     rc = grow(ctx, &ctx->dPlain, &ctx->dPlainCap, plainBytes);
     if (rc != KNZ_OK)
@@ -629,8 +648,7 @@ extern "C" int knz_compress(knz_ctx* ctx, const char* transform, const char* ent
     CK(cudaStreamSynchronize(s));
     const int firstLen = (int)((n < blockSize) ? n : blockSize);
     float acc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
-    auto issueCopy = [&](i64 b0, int slot) -> cudaError_t {
-        const int nb = (int)((nBlocks - b0 < eb) ? nBlocks - b0 : eb);
+    auto issueCopy = [&](i64 b0, int nb, int slot) -> cudaError_t {
         const i64 off = b0 * blockSize;
         const i64 bytes = ((off + (i64)nb * blockSize) <= n) ? (i64)nb * blockSize : n - off;
         cudaError_t e = cudaMemcpyAsync(plain[slot], in + off, (size_t)bytes, cudaMemcpyHostToDevice, ctx->copyStream);
@@ -638,15 +656,20 @@ extern "C" int knz_compress(knz_ctx* ctx, const char* transform, const char* ent
             e = cudaEventRecord(ctx->evCopy[slot], ctx->copyStream);
         return e;
     };
+    int nbCur = batchSize(0, nBlocks);
     if (nBlocks > 0)
-        CK(issueCopy(0, 0));
+        CK(issueCopy(0, nbCur, 0));
     int slot = 0;
-    for (i64 b0 = 0; b0 < nBlocks; b0 += eb, slot ^= 1) {
-        const int nb = (int)((nBlocks - b0 < eb) ? nBlocks - b0 : eb);
+    i64 sentBytes = 0; // bytes of the stream already on their way to the host
+    for (i64 b0 = 0, k = 0; b0 < nBlocks; k++, slot ^= 1) {
+        const int nb = nbCur;
         const i64 off = b0 * blockSize;
+        const i64 bNext = b0 + nb;
         // the other staging buffer is free: encode_batch of the previous sub-batch has completed
-        if (b0 + eb < nBlocks)
-            CK(issueCopy(b0 + eb, slot ^ 1));
+        if (bNext < nBlocks) {
+            nbCur = batchSize((int)k + 1, nBlocks - bNext);
+            CK(issueCopy(bNext, nbCur, slot ^ 1));
+        }
         CK(cudaStreamWaitEvent(s, ctx->evCopy[slot], 0));
         int32_t* lens = (int32_t*)malloc(sizeof(int32_t) * (size_t)nb);
         for (int i = 0; i < nb; i++) {
@@ -671,26 +694,42 @@ extern "C" int knz_compress(knz_ctx* ctx, const char* transform, const char* ent
             CK(cudaStreamSynchronize(s));
         }
         free(lens);
-        if (rc != KNZ_OK)
+        if (rc != KNZ_OK) {
+            cudaStreamSynchronize(ctx->d2hStream);
             return rc;
+        }
         CK(cudaEventRecord(ctx->ev[5], s));
         launch_stream_assemble(ctx->dOut, ctx->outStride, ctx->blockBits, nb, ctx->streamPos, ctx->blockOff,
                                ctx->streamPos, ctx->dStream, s, &ctx->launches);
         CK(cudaEventRecord(ctx->ev[6], s));
-        CK(cudaEventSynchronize(ctx->ev[6]));
+        CK(cudaMemcpyAsync(ctx->h_pos, ctx->streamPos, sizeof(u64), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
         float ms = 0.f;
         cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]);
         acc[4] += ms;
+        // whole bytes assembled so far are final: send them while the next sub-batch encodes
+        const i64 fullBytes = (i64)(ctx->h_pos[0] >> 3);
+        if (fullBytes > cap || fullBytes > streamCap) {
+            cudaStreamSynchronize(ctx->d2hStream);
+            return KNZ_ERR_OUTPUT_TOO_SMALL;
+        }
+        if (bNext < nBlocks && fullBytes > sentBytes) {
+            CK(cudaMemcpyAsync(out + sentBytes, ctx->dStream + sentBytes, (size_t)(fullBytes - sentBytes),
+                               cudaMemcpyDeviceToHost, ctx->d2hStream));
+            sentBytes = fullBytes;
+        }
+        b0 = bNext;
     }
-    CK(cudaMemcpyAsync(ctx->h_pos, ctx->streamPos, sizeof(u64), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
     const u64 endBit = ctx->h_pos[0] + 8; // end marker: 5 + 3 zero bits (:416-417)
     const i64 total = (i64)((endBit + 7) >> 3);
-    if (total > cap || total > streamCap)
+    if (total > cap || total > streamCap) {
+        cudaStreamSynchronize(ctx->d2hStream);
         return KNZ_ERR_OUTPUT_TOO_SMALL;
-    CK(cudaMemcpyAsync(out, ctx->dStream, (size_t)total, cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaMemcpyAsync(out + sentBytes, ctx->dStream + sentBytes, (size_t)(total - sentBytes), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    CK(cudaStreamSynchronize(ctx->d2hStream));
     memcpy(out, hdr, (size_t)hdrBytes);
     *outLen = total;
     for (int i = 0; i < 8; i++)
@@ -723,7 +762,8 @@ struct HostBitReader {
 // at bit h_start[b] of d_in (+ b*inStride) and holds h_bits[b] bits.
 static int decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8* d_in, i64 inStride,
                         const u64* h_payStart, const u64* h_endBit, const int* h_preLen, const u8* h_flags, int nB,
-                        u8* d_out, i64 outStride, int32_t* h_outLens)
+                        u8* d_out, i64 outStride, int32_t* h_outLens,
+                        u8* h_sink = NULL, int* h_sinkBlocks = NULL)
 {
     int types[8];
     const int nt = split_types(tType, types);
@@ -798,6 +838,43 @@ static int decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const
         L.capOdd = ctx->capOdd;
         L.errFlag = ctx->errFlag;
         CK(cudaEventRecord(ctx->ev[2], s));
+        // Last stage of a full batch with a host sink: inverse-BWT the blocks in four groups and
+        // send each group's (full-size) blocks to the host while the next group is being walked.
+        const bool grouped = (h_sink != NULL) && (i == 0) && (types[0] == T_BWT) && (nB >= 64) && (outStride == blockSize);
+        if (grouped) {
+            static int envG = 0; // KNZ_DEC_GROUPS overrides the group count (experiments)
+            if (!envG) {
+                const char* e = getenv("KNZ_DEC_GROUPS");
+                envG = (e && atoi(e) > 0) ? atoi(e) : 2; // 2: the per-launch latency of the node ranking outweighs more overlap
+            }
+            const int G = (envG < nB / 8) ? envG : nB / 8;
+            for (int g = 0; g < G; g++) {
+                const int g0 = (int)((i64)nB * g / G), g1 = (int)((i64)nB * (g + 1) / G);
+                StageLaunch Lg = L;
+                for (int k = 0; k < 3; k++)
+                    Lg.bt.base[k] = L.bt.base[k] + (i64)g0 * L.bt.stride[k];
+                Lg.stIn = L.stIn + g0;
+                Lg.stOut = L.stOut + g0;
+                Lg.capEven = L.capEven + g0;
+                Lg.capOdd = L.capOdd + g0;
+                Lg.nBlocks = g1 - g0;
+                launch_bwt_inverse(Lg, ctx->ws, s, &ctx->launches);
+                launch_copy_out(Lg.bt, Lg.stOut, g1 - g0, d_out + (i64)g0 * outStride, outStride, s, &ctx->launches);
+                CK(cudaEventRecord(ctx->evDone[g & 1], s));
+                CK(cudaStreamWaitEvent(ctx->d2hStream, ctx->evDone[g & 1], 0));
+                const int last = (g1 == nB) ? g1 - 1 : g1; // the batch's last block may be short: the caller copies it
+                if (last > g0)
+                    CK(cudaMemcpyAsync(h_sink + (i64)g0 * blockSize, d_out + (i64)g0 * outStride,
+                                       (size_t)(last - g0) * (size_t)blockSize, cudaMemcpyDeviceToHost, ctx->d2hStream));
+            }
+            *h_sinkBlocks = nB - 1;
+            CK(cudaEventRecord(ctx->ev[3], s));
+            CK(cudaEventSynchronize(ctx->ev[3]));
+            float msg = 0.f;
+            cudaEventElapsedTime(&msg, ctx->ev[2], ctx->ev[3]);
+            add_stage_time(ctx, types[i], msg);
+            continue;
+        }
         switch (types[i]) {
         case T_NONE:
             launch_none_forward(L, s, &ctx->launches); // inverse of a copy is a copy
@@ -822,7 +899,8 @@ static int decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const
         add_stage_time(ctx, types[i], ms);
     }
     const BlkState* stFinal = ctx->st + (i64)nt * ctx->maxBatch;
-    launch_copy_out(bt, stFinal, nB, d_out, outStride, s, &ctx->launches);
+    if (!(h_sinkBlocks && *h_sinkBlocks > 0))
+        launch_copy_out(bt, stFinal, nB, d_out, outStride, s, &ctx->launches);
     CK(cudaEventRecord(ctx->ev[4], s));
     CK(cudaMemcpyAsync(ctx->h_err, ctx->errFlag, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(ctx->h_st, stFinal, sizeof(BlkState) * nB, cudaMemcpyDeviceToHost, s));
@@ -1077,22 +1155,34 @@ extern "C" int knz_decompress(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_
         }
         if (rc != KNZ_OK || ng == 0)
             continue;
+        // blocks the batch already sent to the host (full-size blocks, overlapped with the last stage)
+        int sunk = 0;
+        const bool roomy = batchOut + (i64)ng * blockSize <= cap;
         rc = decode_batch(ctx, tType, eType, blockSize, ctx->dStream, 0, pay, endb, pre, fl, ng, ctx->dPlain, blockSize,
-                          ol);
-        if (rc != KNZ_OK)
+                          ol, roomy ? out + batchOut : NULL, &sunk);
+        if (rc != KNZ_OK) {
+            cudaStreamSynchronize(ctx->d2hStream);
             break;
+        }
         for (int i = 0; i < 8; i++)
             acc[i] += ctx->ms[i];
+        for (int g = 0; g < sunk; g++)
+            if (ol[g] != blockSize)
+                sunk = 0; // a short block in the middle: positions shift, copy everything again
         // decoded blocks are contiguous when every block but the last is full
         for (int g = 0; g < ng; g++) {
             if (ol[g] > blockSize || batchOut + ol[g] > cap) {
                 rc = KNZ_ERR_OUTPUT_TOO_SMALL;
                 break;
             }
-            cudaMemcpyAsync(out + batchOut, ctx->dPlain + (i64)g * blockSize, (size_t)ol[g], cudaMemcpyDeviceToHost, s);
+            if (g == 0 && sunk == 0)
+                cudaStreamSynchronize(ctx->d2hStream); // nothing of ours may land after the fresh copies
+            if (g >= sunk)
+                cudaMemcpyAsync(out + batchOut, ctx->dPlain + (i64)g * blockSize, (size_t)ol[g], cudaMemcpyDeviceToHost, s);
             batchOut += ol[g];
         }
         cudaStreamSynchronize(s);
+        cudaStreamSynchronize(ctx->d2hStream);
         produced = batchOut;
     }
     free(pay);

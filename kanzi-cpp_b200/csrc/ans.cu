@@ -11,6 +11,8 @@
 // Each chunk is encoded into a private staging slot (header bit string at the
 // front, renormalisation words written backwards so they land in decode order)
 // and then bit-concatenated into the block buffer by bitcat.cu.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ans_tables.cuh"
 #include "kernels.h"
@@ -18,14 +20,285 @@
 using namespace knz;
 
 // ------------------------------------------------------------------ encoder
-// smem per warp: 8 tables x 256 x 8 B = 16 KiB.  While the histograms are built the
-// second KiB of every table region is free: four of them hold the 4 privatised
-// copies of the chunk being counted.
+// smem per warp: 8 table regions x 256 x 8 B = 16 KiB.  While the histograms are built the
+// upper KiB of every region is free: four of them hold the 4 privatised copies of the chunk
+// being counted; during table construction the upper KiB of the chunk's own region is the
+// scratch of the header builder (compacted frequencies + header bit string).
 #define ENC_WARPS 2
+
+__device__ __forceinline__ u32 warp_sum_u32(u32 v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_xor_sync(FULL_MASK, v, o);
+    return v;
+}
+
+__device__ __forceinline__ u32 warp_max_u32(u32 v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v = max(v, __shfl_xor_sync(FULL_MASK, v, o));
+    return v;
+}
+
+// OR n (1..32) bits of v (v < 2^n) into an MSB-first bit string kept as 32-bit words whose
+// bit 31 is the first bit of the word (converted to stream byte order when copied out).
+__device__ __forceinline__ void sput(u32* hw, u32 pos, u32 v, int n)
+{
+    const u32 w = pos >> 5;
+    const int off = (int)(pos & 31);
+    const u64 x = ((u64)v << (64 - n)) >> off;
+    const u32 hi = (u32)(x >> 32), lo = (u32)x;
+    if (hi)
+        atomicOr(&hw[w], hi);
+    if (lo)
+        atomicOr(&hw[w + 1], lo);
+}
+
+// Packed encoder entry (8 bytes), laid out so that every field costs one instruction in the
+// coding loop: lo = invFreq; hi = bias[0:13] | (invShift-32)[13:18] | cmplFreq[20:32].
+// Same arithmetic as ANSEncSymbol::reset (entropy/ANSRangeEncoder.hpp:92-116); the 64-bit
+// division of the reciprocal is done as two 32-bit long-division steps.
+__device__ __forceinline__ u64 make_enc_entry12(u32 cum, u32 freq)
+{
+    if (freq >= (1u << ANS0_LR))
+        freq = (1u << ANS0_LR) - 1;
+    u32 inv, sh, bias;
+    if (freq < 2) {
+        inv = 0xFFFFFFFFu;
+        sh = 0;
+        bias = cum + (1u << ANS0_LR) - 1;
+    } else {
+        const int shift = 32 - __clz((int)(freq - 1)); // smallest shift with freq <= 2^shift
+        const u32 n1 = 1u << (shift + 15);
+        const u32 q1 = n1 / freq, r1 = n1 - q1 * freq;
+        const u32 n2 = r1 << 16;
+        const u32 q2 = n2 / freq, r2 = n2 - q2 * freq;
+        inv = (q1 << 16) + q2 + (r2 ? 1u : 0u); // ceil(2^(shift+31) / freq) mod 2^32
+        sh = (u32)(shift - 1);
+        bias = cum;
+    }
+    const u32 hi = bias | (sh << 13) | (((1u << ANS0_LR) - freq) << 20);
+    return ((u64)hi << 32) | inv;
+}
+
+// One coding step of a quad lane (state k of a chunk).  LIVE = false masks lanes whose chunk
+// has no step here; a zero entry (inactive quads) never emits and leaves the state alone.
+#define ANS0_STEP(E, LIVE)                                                                   \
+    {                                                                                        \
+        const u32 hi_ = (u32)((E) >> 32), inv_ = (u32)(E);                                   \
+        const u32 cmpl_ = hi_ >> 20;                                                         \
+        const u32 xmax_ = 0x80000000u - (cmpl_ << 19); /* freq << (31 - lr) */               \
+        const bool did_ = (LIVE) && (state >= xmax_);                                        \
+        const u32 bal_ = __ballot_sync(FULL_MASK, did_);                                     \
+        if (did_) { /* memory order [hi][lo] (ANSRangeEncoder.hpp:122-126) */                \
+            wlast[-(int)(cnt + (u32)__popc(bal_ & mBelow))] = (u16)__byte_perm(state, 0, 0x4401); \
+            state >>= 16;                                                                    \
+        }                                                                                    \
+        cnt += (u32)__popc(bal_ & mQuad);                                                    \
+        const u32 q_ = __funnelshift_r(__umulhi(state, inv_), 0, hi_ >> 13);                 \
+        if (LIVE)                                                                            \
+            state = state + (hi_ & 0x1FFFu) + q_ * cmpl_;                                    \
+    }
+
+// Lane 0 only: slow path of the normalisation (error spread over the frequencies),
+// entropy/EntropyUtils.cpp:205-244, on the scaled counts f[].
+__device__ __noinline__ void normalize_spread(u32* f, int delta, int idxMax)
+{
+    const int errThr = (int)f[idxMax] >> 4;
+    if (delta < 0) {
+        delta += errThr;
+        f[idxMax] += (u32)errThr;
+    } else {
+        delta -= errThr;
+        f[idxMax] -= (u32)errThr;
+    }
+    const int inc = (delta < 0) ? 1 : -1;
+    delta = (delta < 0) ? -delta : delta;
+    int round = 0;
+    while ((++round < 6) && (delta > 0)) {
+        int adjustments = 0;
+        for (int i = 0; i < 256; i++) {
+            if (f[i] <= 2) // absent symbols (0) are skipped by the same test
+                continue;
+            f[i] += (u32)inc;
+            adjustments++;
+            delta--;
+            if (delta == 0)
+                break;
+        }
+        if (adjustments == 0)
+            break;
+    }
+    const u32 v = f[idxMax] - (u32)delta;
+    f[idxMax] = (v > 1u) ? v : 1u;
+}
+
+// Whole warp, one chunk: normalise the histogram in `region` (256 u32), write the chunk header
+// (logRange, alphabet, frequency groups: ANSRangeEncoder.cpp:83-155, EntropyUtils.cpp:57-89)
+// to `slot`, then overwrite the region with the 256 packed encoder entries.  Lane t owns
+// symbols 8t..8t+7.  Returns the alphabet size; *hdrBits = header length, *partial = the last,
+// partly filled header byte (the chunk's quad continues the bit string after the coding loop).
+__device__ __forceinline__ int ans0_build_chunk(u32* region, int len, u8* slot, int lane, u32* hdrBits, u32* partial)
+{
+    u16* v16 = reinterpret_cast<u16*>(region + 256);
+    u32* hw = region + 384;
+    u32 c[8];
+    {
+        const uint4 a = *reinterpret_cast<const uint4*>(region + lane * 8);
+        const uint4 b = *reinterpret_cast<const uint4*>(region + lane * 8 + 4);
+        c[0] = a.x, c[1] = a.y, c[2] = a.z, c[3] = a.w;
+        c[4] = b.x, c[5] = b.y, c[6] = b.z, c[7] = b.w;
+    }
+#pragma unroll
+    for (int t = 0; t < 4; t++)
+        hw[lane * 4 + t] = 0;
+    u32 pm = 0;
+#pragma unroll
+    for (int t = 0; t < 8; t++)
+        pm |= (c[t] != 0) ? (1u << t) : 0u;
+    const u32 cntp = (u32)__popc(pm);
+    const u32 incl = warp_incl_sum(cntp, lane);
+    const int asz = (int)__shfl_sync(FULL_MASK, incl, 31);
+    const u32 lanesP = __ballot_sync(FULL_MASK, pm != 0);
+    const u32 total = (u32)len, scale = 1u << ANS0_LR;
+    if (total != scale) {
+        u32 ssum = 0, best = 0; // best = (scaled << 8) | (255 - symbol): max value, lowest symbol
+#pragma unroll
+        for (int t = 0; t < 8; t++)
+            if (c[t]) {
+                const u32 sf = c[t] << ANS0_LR; // <= 2^26
+                const u32 sc = (sf <= total) ? 1u : (sf + (total >> 1)) / total;
+                c[t] = sc;
+                ssum += sc;
+                best = max(best, (sc << 8) | (u32)(255 - (lane * 8 + t)));
+            }
+        ssum = warp_sum_u32(ssum);
+        best = warp_max_u32(best);
+        const int idxMax = 255 - (int)(best & 0xFF);
+        if (asz == 1) {
+#pragma unroll
+            for (int t = 0; t < 8; t++)
+                if (c[t])
+                    c[t] = scale;
+        } else if (ssum != scale) {
+            const int delta = (int)ssum - (int)scale;
+            const int errThr = (int)(best >> 8) >> 4;
+            if (((delta < 0) ? -delta : delta) <= errThr) {
+#pragma unroll
+                for (int t = 0; t < 8; t++)
+                    if (lane * 8 + t == idxMax)
+                        c[t] -= (u32)delta;
+            } else {
+                __syncwarp();
+#pragma unroll
+                for (int t = 0; t < 8; t++)
+                    region[lane * 8 + t] = c[t];
+                __syncwarp();
+                if (lane == 0)
+                    normalize_spread(region, delta, idxMax);
+                __syncwarp();
+#pragma unroll
+                for (int t = 0; t < 8; t++)
+                    c[t] = region[lane * 8 + t];
+            }
+        }
+    }
+    __syncwarp(); // hw[] zeroed, region reads done
+    // ---- header: logRange - 8 (3 bits), alphabet
+    u32 pos0;
+    if (asz == 256) {
+        if (lane == 0)
+            sput(hw, 0, (u32)(ANS0_LR - 8) << 2, 5); // "00" = full alphabet
+        pos0 = 5;
+    } else {
+        const int last = 31 - __clz((int)lanesP); // last mask byte = symbols 8*last..
+        if (lane == 0)
+            sput(hw, 0, ((u32)(ANS0_LR - 8) << 6) | 0x20u | (u32)last, 9);
+        if (lane <= last)
+            sput(hw, 9 + 8 * lane, pm, 8); // pm == 0 writes nothing
+        pos0 = 9 + 8 * (u32)(last + 1);
+    }
+    u32 bits = pos0;
+    if (asz > 1) {
+        // ---- frequency groups: present symbols in increasing order, the first one implicit
+        u32 r = incl - cntp;
+#pragma unroll
+        for (int t = 0; t < 8; t++)
+            if (c[t]) {
+                if (r >= 1)
+                    v16[r - 1] = (u16)(c[t] - 1);
+                r++;
+            }
+        __syncwarp();
+        const int chk = (asz >= 64) ? 8 : 6;
+        const int nv = asz - 1;
+        u32 glen[2], glog[2];
+        int gcnt[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int g = lane + 32 * u;
+            const int cnt = min(chk, nv - g * chk); // <= 0: no such group
+            u32 mx = 0;
+            for (int k = 0; k < cnt; k++)
+                mx = max(mx, (u32)v16[g * chk + k]);
+            const u32 lm = mx ? (u32)ilog2_u32(mx) + 1u : 0u;
+            gcnt[u] = cnt;
+            glog[u] = lm;
+            glen[u] = (cnt > 0) ? 4u + (u32)cnt * lm : 0u; // llr = log2(12) + 1 = 4
+        }
+        const u32 inc0 = warp_incl_sum(glen[0], lane);
+        const u32 tot0 = __shfl_sync(FULL_MASK, inc0, 31);
+        const u32 inc1 = warp_incl_sum(glen[1], lane);
+        const u32 tot1 = __shfl_sync(FULL_MASK, inc1, 31);
+        u32 off[2] = { pos0 + inc0 - glen[0], pos0 + tot0 + inc1 - glen[1] };
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            if (gcnt[u] <= 0)
+                continue;
+            const int g = lane + 32 * u;
+            sput(hw, off[u], glog[u], 4);
+            u32 o = off[u] + 4;
+            if (glog[u])
+                for (int k = 0; k < gcnt[u]; k++) {
+                    sput(hw, o, (u32)v16[g * chk + k], (int)glog[u]);
+                    o += glog[u];
+                }
+        }
+        bits = pos0 + tot0 + tot1;
+    }
+    __syncwarp();
+    // ---- copy the header out (stream byte order); keep the partly filled last byte
+    const int nw = (int)((bits + 31) >> 5);
+    u32* sw = reinterpret_cast<u32*>(slot);
+    for (int i = lane; i < nw; i += 32)
+        sw[i] = bswap32(hw[i]);
+    *hdrBits = bits;
+    *partial = (hw[bits >> 5] >> (24 - (int)((bits >> 3) & 3) * 8)) & 0xFFu;
+    __syncwarp();
+    // ---- encoder entries over the whole region (cumulative frequencies by warp scan)
+    u32 ls = 0;
+#pragma unroll
+    for (int t = 0; t < 8; t++)
+        ls += c[t];
+    u32 cum = warp_incl_sum(ls, lane) - ls;
+    u64* ent = reinterpret_cast<u64*>(region);
+    u64 e[8];
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        e[t] = (c[t] == 0 || asz <= 1) ? 0ull : make_enc_entry12(cum, c[t]);
+        cum += c[t];
+    }
+#pragma unroll
+    for (int t = 0; t < 8; t += 2)
+        *reinterpret_cast<ulonglong2*>(ent + lane * 8 + t) = make_ulonglong2(e[t], e[t + 1]);
+    return asz;
+}
 
 __global__ void __launch_bounds__(ENC_WARPS * 32)
 ans0_encode_kernel(BufTable bt, const BlkState* __restrict__ st, int nBlocks, int maxChunks, u8* __restrict__ slots,
-                   u32* __restrict__ hdrBits, u32* __restrict__ payBytes, u32* __restrict__ payOff)
+                   u32* __restrict__ hdrBits, u32* __restrict__ payBytes, u32* __restrict__ payOff, int dbgStop)
 {
     __shared__ __align__(16) u64 s_sym[ENC_WARPS][8][256];
 
@@ -75,8 +348,29 @@ ans0_encode_kernel(BufTable bt, const BlkState* __restrict__ st, int nBlocks, in
                 hk[k][i] = 0;
         __syncwarp();
         u32* h = reinterpret_cast<u32*>(sym[(j + 1 + (lane & 3)) & 7]) + 256;
-        for (int i = lane * 16; i < len; i += 512) {
-            if (i + 16 <= len) {
+        int i = lane * 16;
+        if ((((size_t)p) & 15) == 0) {
+            // eight 128-bit loads in flight per lane (4 KiB per warp) before the counting starts
+            for (; i + 7 * 512 + 16 <= len; i += 8 * 512) {
+                uint4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    v[u] = __ldg(reinterpret_cast<const uint4*>(p + i + u * 512));
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const u32 w[4] = { v[u].x, v[u].y, v[u].z, v[u].w };
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        atomicAdd(&h[w[q] & 0xFF], 1u);
+                        atomicAdd(&h[(w[q] >> 8) & 0xFF], 1u);
+                        atomicAdd(&h[(w[q] >> 16) & 0xFF], 1u);
+                        atomicAdd(&h[w[q] >> 24], 1u);
+                    }
+                }
+            }
+        }
+        for (; i < len; i += 512) {
+            if (i + 16 <= len && (((size_t)p) & 15) == 0) {
                 const uint4 v = *reinterpret_cast<const uint4*>(p + i);
                 const u32 w[4] = { v.x, v.y, v.z, v.w };
 #pragma unroll
@@ -87,7 +381,7 @@ ans0_encode_kernel(BufTable bt, const BlkState* __restrict__ st, int nBlocks, in
                     atomicAdd(&h[w[q] >> 24], 1u);
                 }
             } else {
-                for (int t = i; t < len; t++)
+                for (int t = i; t < min(i + 16, len); t++)
                     atomicAdd(&h[p[t]], 1u);
             }
         }
@@ -98,103 +392,130 @@ ans0_encode_kernel(BufTable bt, const BlkState* __restrict__ st, int nBlocks, in
         __syncwarp();
     }
 
-    // ---- phase B: one lane per chunk: normalise, header, tables
+    if (dbgStop == 1)
+        return;
+    // ---- phase B: per chunk, whole warp: normalise, header, tables
     const int j = lane >> 2, k = lane & 3;
     const int c = c0 + j;
     const bool valid = c < nChunks;
     const int len = valid ? min(ANS_CHUNK, m - c * ANS_CHUNK) : 0;
     u8* slot = slots + ((i64)b * maxChunks + (valid ? c : 0)) * ANS_SLOT;
-    BitSink w;
-    w.init(slot);
     int active = 0;
-    if (valid && k == 0) {
-        u32* f = reinterpret_cast<u32*>(sym[j]);
-        const int asz = normalize_counts(f, (u32)len, 1u << ANS0_LR);
-        put_chunk_header(w, f, asz, ANS0_LR);
-        if (asz > 1) {
-            active = 1;
-            u32 total = 0;
-            for (int i = 0; i < 256; i++)
-                total += f[i];
-            // descending: entry i overwrites histogram words 2i, 2i+1 (both >= i, already consumed);
-            // cumulative frequency of i = total - sum of the frequencies >= i
-            u32 run = total;
-            for (int i = 255; i >= 0; i--) {
-                const u32 fr = f[i];
-                run -= fr;
-                sym[j][i] = (fr == 0) ? 0ull : make_enc_entry((int)run, (int)fr, ANS0_LR);
-            }
+    u32 myHdrBits = 0, myPartial = 0;
+    for (int jj = 0; jj < 8; jj++) {
+        const int cc = c0 + jj;
+        u32* region = reinterpret_cast<u32*>(sym[jj]);
+        int asz = 0;
+        u32 hb = 0, part = 0;
+        if (cc < nChunks) {
+            const int clen = min(ANS_CHUNK, m - cc * ANS_CHUNK);
+            asz = ans0_build_chunk(region, clen, slots + ((i64)b * maxChunks + cc) * ANS_SLOT, lane, &hb, &part);
+        } else {
+#pragma unroll
+            for (int t = 0; t < 4; t++) // no chunk: a zero table keeps the quad's lanes idle in the coding loop
+                *reinterpret_cast<uint4*>(region + (t * 32 + lane) * 4) = make_uint4(0, 0, 0, 0);
+        }
+        if (j == jj) {
+            active = (asz > 1) ? 1 : 0;
+            myHdrBits = hb;
+            myPartial = part;
         }
     }
     __syncwarp();
-    active = __shfl_sync(FULL_MASK, active, lane & ~3);
 
+    if (dbgStop == 2)
+        return;
     // ---- phase C: interleaved rANS, lane k of quad j owns state k
     const int end4 = len & ~3;
     const int steps = active ? (end4 >> 2) : 0;
-    int maxSteps = steps;
+    int maxSteps = steps, minSteps = active ? steps : 0x7FFFFFFF;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
+    for (int o = 16; o > 0; o >>= 1) {
         maxSteps = max(maxSteps, __shfl_xor_sync(FULL_MASK, maxSteps, o));
-
-    const u32* __restrict__ words = reinterpret_cast<const u32*>(src + (i64)(valid ? c : 0) * ANS_CHUNK);
+        minSteps = min(minSteps, __shfl_xor_sync(FULL_MASK, minSteps, o));
+    }
+    // steps every active quad takes, in whole 16-byte groups; idle quads walk chunk c0's bytes
+    // against their zero table (chunk c0 is never shorter than any other chunk of the warp)
+    int fast = (maxSteps > 0) ? (minSteps & ~31) : 0;
+    const u32* __restrict__ words = reinterpret_cast<const u32*>(src + (i64)(active ? c : c0) * ANS_CHUNK);
+    const int wtop = active ? (end4 >> 2) - 1 : fast - 1; // step s consumes word wtop - s (the quad's 4 bytes)
+    if (__any_sync(FULL_MASK, (((size_t)words) & 15) != 0 || (((wtop + 1) & 3) != 0)))
+        fast = 0; // 128-bit groups need 16-byte alignment from the top
     const u64* __restrict__ tab = sym[j];
     u32 state = 1u << 15; // ANS_TOP
-    u32 cnt = 0;
     u16* wend = reinterpret_cast<u16*>(slot + ANS_WEND);
-    const int bsh = 8 * (3 - k);
-    const u32 below = (1u << k) - 1u;
+    u16* const wlast = wend - 1;
+    u32 cnt = 0; // renormalisation words of the quad so far
+    const u32 selK = 0x4440u | (u32)(3 - k); // byte 3 - k of the quad's word
     const int qsh = lane & ~3;
-    const int wtop = (end4 >> 2) - 1; // step s consumes word wtop - s (the quad's 4 bytes)
-    // Software pipeline, 4 steps (16 input bytes per quad) per group, two groups ahead.
-    // Full chunks are 16-byte aligned from the top, so a group is one 128-bit load.
-    const bool vec = (end4 & 15) == 0;
-    uint4 ga = make_uint4(0, 0, 0, 0), gb = ga, gc = ga;
-    auto fetch = [&](int s0) -> uint4 {
-        uint4 r = make_uint4(0, 0, 0, 0);
-        if (s0 + 3 < steps && vec) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(words + (wtop - s0 - 3)));
-            r = make_uint4(v.w, v.z, v.y, v.x); // .x = word of step s0
-        } else {
-            if (s0 < steps)
-                r.x = __ldg(&words[wtop - s0]);
-            if (s0 + 1 < steps)
-                r.y = __ldg(&words[wtop - s0 - 1]);
-            if (s0 + 2 < steps)
-                r.z = __ldg(&words[wtop - s0 - 2]);
-            if (s0 + 3 < steps)
-                r.w = __ldg(&words[wtop - s0 - 3]);
-        }
-        return r;
-    };
-    ga = fetch(0);
-    gb = fetch(4);
-    for (int s0 = 0; s0 < maxSteps; s0 += 4) {
-        gc = fetch(s0 + 8);
-        const u32 wv[4] = { ga.x, ga.y, ga.z, ga.w };
-#pragma unroll
-        for (int x = 0; x < 4; x++) {
-            bool did = false;
-            u32 word = 0;
-            if (s0 + x < steps) {
-                const u32 cb = (wv[x] >> bsh) & 0xFF;
-                state = enc_step(state, tab[cb], ANS0_LR, &did, &word);
-            }
-            const u32 qb = (__ballot_sync(FULL_MASK, did) >> qsh) & 0xF;
-            if (did) // memory order [hi][lo] (ANSRangeEncoder.hpp:122-126)
-                wend[-1 - (int)(cnt + __popc(qb & below))] = (u16)__byte_perm(word, 0, 0x4401);
-            cnt += __popc(qb);
-        }
-        ga = gb;
-        gb = gc;
+    const u32 mQuad = 0xFu << qsh;
+    const u32 mBelow = ((1u << k) - 1u) << qsh;
+#define SYM_OF(W) __byte_perm((W), 0, selK)
+    int s0 = 0;
+    if (fast > 0) {
+        // 32 steps (128 input bytes per quad) per trip: a ring of eight 128-bit groups;
+        // table entries are fetched one group ahead.
+        const uint4* __restrict__ gp = reinterpret_cast<const uint4*>(words + (wtop - 3)); // group g = gp[-g]
+        const int nG = fast >> 2;
+#define LOADG(G) __ldg(gp - min((G), nG - 1))
+#define GROUP_STEPS(WN)                                                                                         \
+    {                                                                                                           \
+        const u64 n0 = tab[SYM_OF((WN).w)], n1 = tab[SYM_OF((WN).z)], n2 = tab[SYM_OF((WN).y)],                 \
+                  n3 = tab[SYM_OF((WN).x)];                                                                     \
+        ANS0_STEP(e0, true)                                                                                     \
+        ANS0_STEP(e1, true)                                                                                     \
+        ANS0_STEP(e2, true)                                                                                     \
+        ANS0_STEP(e3, true)                                                                                     \
+        e0 = n0, e1 = n1, e2 = n2, e3 = n3;                                                                     \
     }
-
+        uint4 a0 = LOADG(0), a1 = LOADG(1), a2 = LOADG(2), a3 = LOADG(3);
+        uint4 b0 = LOADG(4), b1 = LOADG(5), b2 = LOADG(6), b3 = LOADG(7);
+        u64 e0 = tab[SYM_OF(a0.w)], e1 = tab[SYM_OF(a0.z)], e2 = tab[SYM_OF(a0.y)], e3 = tab[SYM_OF(a0.x)];
+        for (int g = 0; g < nG; g += 8) {
+#ifndef KNZ_SIM
+            if (k == 0 && g + 40 < nG) // pull the line four trips ahead into L2
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(gp - (g + 40)));
+#endif
+            a0 = LOADG(g + 8); // group g's entries are already in e0..e3: every slot is refilled right
+            GROUP_STEPS(a1)    // after its last use, seven groups (28 steps) before it is needed again
+            a1 = LOADG(g + 9);
+            GROUP_STEPS(a2)
+            a2 = LOADG(g + 10);
+            GROUP_STEPS(a3)
+            a3 = LOADG(g + 11);
+            GROUP_STEPS(b0)
+            b0 = LOADG(g + 12);
+            GROUP_STEPS(b1)
+            b1 = LOADG(g + 13);
+            GROUP_STEPS(b2)
+            b2 = LOADG(g + 14);
+            GROUP_STEPS(b3)
+            b3 = LOADG(g + 15);
+            GROUP_STEPS(a0)
+        }
+        s0 = fast;
+#undef GROUP_STEPS
+#undef LOADG
+    }
+    for (; s0 < maxSteps; s0++) { // ragged end: chunks of different lengths in one warp, unaligned chunks
+        const bool live = s0 < steps;
+        u64 e = 0;
+        if (live)
+            e = tab[SYM_OF(__ldg(&words[wtop - s0]))];
+        ANS0_STEP(e, live)
+    }
+#undef SYM_OF
     // ---- epilogue: varint size, 4 states, tail bytes
     const u32 s1 = __shfl_sync(FULL_MASK, state, (lane & ~3) + 1);
     const u32 s2 = __shfl_sync(FULL_MASK, state, (lane & ~3) + 2);
     const u32 s3 = __shfl_sync(FULL_MASK, state, (lane & ~3) + 3);
     if (valid && k == 0) {
         const i64 ci = (i64)b * maxChunks + c;
+        BitSink w;
+        w.p = slot + (myHdrBits >> 3);
+        w.n = (int)(myHdrBits & 7);
+        w.acc = (u64)(myPartial >> (8 - w.n));
+        w.total = myHdrBits;
         if (active) {
             const int tail = len & 3;
             u32 P = 2 * cnt + (u32)tail;
@@ -439,8 +760,13 @@ void launch_entropy_encode(const EncodeLaunch& L, cudaStream_t s, u64* launches)
         const int ctas = (int)((warps + ENC_WARPS - 1) / ENC_WARPS);
         if (L.evK0)
             cudaEventRecord(L.evK0, s);
+        static int dbgStop = -1; // timing experiments only: KNZ_ANS_STOP=1|2 ends the kernel after phase A|B
+        if (dbgStop < 0) {
+            const char* e = getenv("KNZ_ANS_STOP");
+            dbgStop = e ? atoi(e) : 0;
+        }
         KLAUNCH(ans0_encode_kernel, ctas, ENC_WARPS * 32, s, L.bt, L.st, nB, L.maxChunks, L.slots, L.hdrBits,
-                L.payBytes, L.payOff);
+                L.payBytes, L.payOff, dbgStop);
         if (L.evK1)
             cudaEventRecord(L.evK1, s);
     }

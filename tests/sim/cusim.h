@@ -22,6 +22,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __restrict__
 #define __shared__ static
 #define __launch_bounds__(...)
@@ -42,6 +43,7 @@ inline uint2 make_uint2(unsigned a, unsigned b) { return uint2{ a, b }; }
 struct ulonglong2 {
     unsigned long long x, y;
 };
+inline ulonglong2 make_ulonglong2(unsigned long long a, unsigned long long b) { return ulonglong2{ a, b }; }
 
 typedef int cudaError_t;
 typedef void* cudaStream_t;
@@ -255,6 +257,11 @@ inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t sh)
 {
     sh &= 31;
     return sh ? ((hi << sh) | (lo >> (32 - sh))) : hi;
+}
+inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh)
+{
+    sh &= 31;
+    return sh ? ((lo >> sh) | (hi << (32 - sh))) : lo;
 }
 template <class T>
 inline T __ldg(const T* p) { return *p; }

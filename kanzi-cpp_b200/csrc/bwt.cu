@@ -13,6 +13,7 @@
 //     out[rank(p) + (rank(p) < rank(0))] = in[p-1], out[0] = in[n-1], primary
 //     index k = rank(k*ceil(n/8)) + 1 (same contract as constructBWT).
 // Many blocks are sorted in one launch sequence (segment = block).
+#include <stdio.h>
 #include <string.h>
 #include <stdlib.h>
 
@@ -292,6 +293,348 @@ static void radix_sort(const SortArrays& A, int nBlocks, int maxCnt, u32 passMas
             KLAUNCH_DYN(rs_onesweep_kernel<8>, dim3(otiles, nBlocks), RS_THREADS, OS_SMEM(8), s, A, p);
         *launches += 1;
     }
+}
+
+
+// ------------------------------------------------------------------ initial sort, text mode
+// For blocks of at most 4 MiB the first round does not move keys at all: the element is the
+// suffix index (22 bits) and the digit of pass p is the text byte at index + 7 - p, which is
+// either read in order (pass 0), carried in the top bits of the element from the pass before
+// (odd passes) or gathered from the block's text, L2 resident while its tiles are in flight
+// (passes 2, 4, 6; the gather also fetches the byte the next pass needs).  A pass then moves
+// 4 + 4 bytes per element instead of 12 + 12.
+#define TX_IDX_BITS 22
+#define TX_IDX_MASK ((1u << TX_IDX_BITS) - 1u)
+#define TX_SMEM (RS_TILE * 4 + (RS_THREADS / 32) * 256 * 4 + 2 * 256 * 4 + 64 + RS_TILE)
+
+struct TextSort {
+    BufTable bt;
+    const BlkState* st;
+};
+
+// H[d] = occurrences of byte d in the block -> totals row 0 (the plan derives all 8 rows)
+__global__ void __launch_bounds__(RS_THREADS)
+rs_text_hist_kernel(SortArrays A, TextSort T)
+{
+    __shared__ u32 s_h[256];
+    const int b = blockIdx.y;
+    const int cnt = A.cnt[b];
+    const int base = blockIdx.x * (RS_TILE * 4);
+    if (base >= cnt)
+        return;
+    s_h[threadIdx.x] = 0;
+    __syncthreads();
+    const u8* __restrict__ text = blk_src(T.bt, T.st[b], b);
+    const int end = min(cnt, base + RS_TILE * 4);
+    for (int j = base + threadIdx.x; j < end; j += RS_THREADS)
+        atomicAdd(&s_h[text[j]], 1u);
+    __syncthreads();
+    const u32 v = s_h[threadIdx.x];
+    if (v)
+        atomicAdd(&A.totals[(i64)b * 2048 + threadIdx.x], v);
+}
+
+// One CTA per block: totals of pass p = histogram of text[s .. n) plus min(s, n) padding zeros,
+// s = 7 - p; no pass is skipped (an odd pass needs the byte its predecessor carried).
+__global__ void __launch_bounds__(256)
+rs_text_plan_kernel(SortArrays A, TextSort T, int nBlocks)
+{
+    const int b = blockIdx.x;
+    const int d = threadIdx.x;
+    const int n = A.cnt[b];
+    u32* tot = A.totals + (i64)b * 2048;
+    const u32 H = tot[d];
+    const u8* __restrict__ text = blk_src(T.bt, T.st[b], b);
+    for (int p = 0; p < 8; p++) {
+        const int s = min(7 - p, n);
+        u32 v = H;
+        for (int x = 0; x < s; x++)
+            v -= (text[x] == d) ? 1u : 0u;
+        if (d == 0)
+            v += (u32)s;
+        tot[p * 256 + d] = v;
+    }
+    if (d == 0) {
+        int w = A.which[b];
+        for (int p = 0; p < 8; p++) {
+            const int triv = (n <= 0) ? 1 : 0;
+            A.trivial[p * A.maxBlocks + b] = triv;
+            if (!triv)
+                w ^= 1;
+            A.which[(p + 1) * A.maxBlocks + b] = w;
+        }
+    }
+}
+
+// KIND 0: pass 0 (implicit index, text read in order); 1: odd pass (digit carried by the
+// element); 2: even pass >= 2 (digit and the next pass's digit gathered from the text).
+template <int KIND>
+__global__ void __launch_bounds__(RS_THREADS, 4)
+rs_onesweep_text_kernel(SortArrays A, TextSort T, int pass)
+{
+    KNZ_DYN_SMEM(os_smem);
+    u32* s_val = reinterpret_cast<u32*>(os_smem);
+    u32(*s_cnt)[256] = reinterpret_cast<u32(*)[256]>(os_smem + RS_TILE * 4);
+    u32* s_delta = reinterpret_cast<u32*>(os_smem + RS_TILE * 4 + (RS_THREADS / 32) * 1024);
+    u32* s_toff = s_delta + 256;
+    u32* s_w = s_toff + 256; // 8 words for the block scan + 1 for the ticket
+    u8* s_dig = reinterpret_cast<u8*>(s_w + 16); // digit of every staged slot
+    const int b = blockIdx.y;
+    const int cnt = A.cnt[b];
+    if (cnt <= 0)
+        return;
+    const int tiles = (cnt + RS_TILE - 1) / RS_TILE;
+    if ((int)blockIdx.x >= tiles)
+        return;
+    if (threadIdx.x == 0)
+        s_w[8] = (u32)atomicAdd(&A.ticket[pass * A.maxBlocks + b], 1);
+    for (int i = threadIdx.x; i < (RS_THREADS / 32) * 256; i += RS_THREADS)
+        (&s_cnt[0][0])[i] = 0;
+    __syncthreads();
+    const int tile = (int)s_w[8];
+    const int tbase = tile * RS_TILE;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int src = A.which[pass * A.maxBlocks + b];
+    const u32* __restrict__ vin = A.val[src] + (i64)b * A.capN;
+    u32* __restrict__ vout = A.val[src ^ 1] + (i64)b * A.capN;
+    const u8* __restrict__ text = blk_src(T.bt, T.st[b], b);
+    const int sft = 7 - pass; // digit = text[index + sft]
+    u32 val[RS_ITEMS];
+    u32 dgt[RS_ITEMS];
+    u16 rnk[RS_ITEMS];
+    if (KIND != 0) {
+#pragma unroll
+        for (int it = 0; it < RS_ITEMS; it++) {
+            const int j = tbase + w * (32 * RS_ITEMS) + it * 32 + lane;
+            val[it] = (j < cnt) ? __ldg(&vin[j]) : 0;
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < RS_ITEMS; it++) {
+        const int j = tbase + w * (32 * RS_ITEMS) + it * 32 + lane;
+        u32 d = 256u; // padding class
+        if (j < cnt) {
+            if (KIND == 1) {
+                d = val[it] >> TX_IDX_BITS;
+                val[it] &= TX_IDX_MASK;
+            } else {
+                const int idx = (KIND == 0) ? j : (int)(val[it] & TX_IDX_MASK);
+                const int a = idx + sft;
+                d = (a < cnt) ? (u32)__ldg(&text[a]) : 0u;
+                const u32 c = (a >= 1 && a - 1 < cnt) ? (u32)__ldg(&text[a - 1]) : 0u;
+                val[it] = (u32)idx | (c << TX_IDX_BITS);
+            }
+        }
+        dgt[it] = d;
+    }
+    // rank inside the warp's 256 elements (load order = stable order)
+#pragma unroll
+    for (int it = 0; it < RS_ITEMS; it++) {
+        const u32 d = dgt[it];
+        const u32 peers = __match_any_sync(FULL_MASK, d);
+        const u32 prior = (d < 256) ? s_cnt[w][d] : 0;
+        __syncwarp();
+        if (d < 256 && (peers & lanemask_lt()) == 0)
+            s_cnt[w][d] = prior + __popc(peers);
+        __syncwarp();
+        rnk[it] = (u16)(prior + __popc(peers & lanemask_lt()));
+    }
+    __syncthreads();
+    // thread = digit: warp prefixes, tile count, look-back, offsets
+    const int d = threadIdx.x;
+    u32 tcount = 0;
+#pragma unroll
+    for (int x = 0; x < RS_THREADS / 32; x++) {
+        const u32 v = s_cnt[x][d];
+        s_cnt[x][d] = tcount;
+        tcount += v;
+    }
+    u32* stw = A.hist + ((i64)b * A.maxTiles) * 256 + d;
+    os_publish(stw + (i64)tile * 256, (tile == 0) ? (OS_INC | tcount) : (OS_AGG | tcount));
+    u32 before = 0;
+    for (int t = tile - 1; t >= 0;) {
+        u32 v[OS_LOOK];
+#pragma unroll
+        for (int k = 0; k < OS_LOOK; k++)
+            v[k] = (t - k >= 0) ? os_peek(stw + (i64)(t - k) * 256) : OS_INC;
+        bool done = false;
+#pragma unroll
+        for (int k = 0; k < OS_LOOK; k++) {
+            if (done || !(v[k] & (OS_INC | OS_AGG)))
+                break;
+            before += v[k] & OS_VAL;
+            t--;
+            done = (v[k] & OS_INC) != 0;
+        }
+        if (done)
+            break;
+    }
+    if (tile > 0)
+        os_publish(stw + (i64)tile * 256, OS_INC | (before + tcount));
+    u32 tot;
+    const u32 dbase = block_excl_sum_256(A.totals[(i64)b * 2048 + pass * 256 + d], s_w, &tot);
+    const u32 toff = block_excl_sum_256(tcount, s_w, &tot);
+    s_delta[d] = dbase + before - toff;
+    s_toff[d] = toff;
+    __syncthreads();
+    // stage in sorted order (the element no longer holds this pass's digit: stage it alongside)
+#pragma unroll
+    for (int it = 0; it < RS_ITEMS; it++) {
+        const u32 dg = dgt[it];
+        if (dg < 256) {
+            const u32 q = s_toff[dg] + s_cnt[w][dg] + rnk[it];
+            s_val[q] = val[it];
+            s_dig[q] = (u8)dg;
+        }
+    }
+    __syncthreads();
+    const int valid = min(RS_TILE, cnt - tbase);
+#pragma unroll
+    for (int it = 0; it < RS_ITEMS; it++) {
+        const int q = it * RS_THREADS + threadIdx.x;
+        if (q < valid)
+            vout[s_delta[s_dig[q]] + (u32)q] = s_val[q];
+    }
+}
+
+// Keys of the sorted suffixes for the grouping kernels: 8 text bytes, big-endian, zero padded.
+__global__ void __launch_bounds__(256)
+bwt_regen_keys_kernel(SortArrays A, TextSort T, int slowOnly)
+{
+    const int b = blockIdx.y;
+    const int n = A.cnt[b];
+    if (n <= 0)
+        return;
+    const int w8 = A.which[8 * A.maxBlocks + b];
+    const u32* __restrict__ v = A.val[w8] + (i64)b * A.capN;
+    u64* __restrict__ k = A.key[w8] + (i64)b * A.capN;
+    const u8* __restrict__ text = blk_src(T.bt, T.st[b], b);
+    const bool al = (((size_t)text) & 7) == 0;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const int i = (int)v[j];
+        u64 key;
+        const int b8 = i & ~7;
+        if (al && b8 + 16 <= n && !slowOnly) {
+            // two aligned 8-byte words cover text[i .. i+8)
+#ifdef KNZ_REGEN_PLAIN
+            const u64 w0 = *reinterpret_cast<const volatile u64*>(text + b8);
+            const u64 w1 = *reinterpret_cast<const volatile u64*>(text + b8 + 8);
+#else
+            const u64 w0 = __ldg(reinterpret_cast<const u64*>(text + b8));
+            const u64 w1 = __ldg(reinterpret_cast<const u64*>(text + b8 + 8));
+#endif
+            const int sh = (i & 7) * 8;
+            const u64 le = sh ? ((w0 >> sh) | (w1 << (64 - sh))) : w0; // byte x of le = text[i + x]
+            const u32 lo = (u32)le, hi = (u32)(le >> 32);
+            key = ((u64)bswap32(lo) << 32) | (u64)bswap32(hi);
+        } else {
+            // the last few suffixes of the block (zero padded) and unaligned text: byte by byte
+            u32 hi = 0, lo = 0;
+#pragma unroll 1
+            for (int x = 0; x < 8; x++) {
+                const int p = i + x;
+                u32 c = 0;
+                if (p < n)
+                    c = text[p];
+                hi = (hi << 8) | (lo >> 24);
+                lo = (lo << 8) | c;
+            }
+            key = ((u64)hi << 32) | lo;
+        }
+#ifdef KNZ_DEBUG_REGEN
+        {
+            u64 key2 = 0;
+            for (int x = 0; x < 8; x++)
+                key2 = (key2 << 8) | ((i + x < n) ? (u64)text[i + x] : 0ull);
+            if (key2 != key)
+                printf("regen mismatch j=%d i=%d n=%d fast=%llx slow=%llx\n", j, i, n, (unsigned long long)key,
+                       (unsigned long long)key2);
+        }
+#endif
+        k[j] = key;
+    }
+}
+
+// debug (KNZ_TX_CHECK=1): recompute every key bytewise and report mismatches / order violations
+__global__ void bwt_regen_check_kernel(SortArrays A, TextSort T)
+{
+    const int b = blockIdx.y;
+    const int n = A.cnt[b];
+    if (n <= 0)
+        return;
+    const int w8 = A.which[8 * A.maxBlocks + b];
+    const u32* v = A.val[w8] + (i64)b * A.capN;
+    const u64* k = A.key[w8] + (i64)b * A.capN;
+    const u8* text = blk_src(T.bt, T.st[b], b);
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const int i = (int)v[j];
+        u64 key2 = 0;
+        for (int x = 0; x < 8; x++)
+            key2 = (key2 << 8) | ((i + x < n) ? (u64)text[i + x] : 0ull);
+        if (key2 != k[j])
+            printf("KEY mismatch b=%d j=%d i=%d got=%llx want=%llx\n", b, j, i, (unsigned long long)k[j],
+                   (unsigned long long)key2);
+        if (j > 0 && k[j - 1] > k[j])
+            printf("ORDER violation b=%d j=%d i=%d prev=%llx cur=%llx\n", b, j, i, (unsigned long long)k[j - 1],
+                   (unsigned long long)k[j]);
+        if (j > 0 && k[j - 1] == k[j] && v[j - 1] > v[j])
+            printf("STABILITY violation b=%d j=%d i=%d prev i=%d\n", b, j, i, (int)v[j - 1]);
+    }
+}
+
+static void radix_sort_text(const SortArrays& A, const TextSort& T, int nBlocks, int maxCnt, cudaStream_t s,
+                            u64* launches)
+{
+    const int tiles = (maxCnt + RS_TILE - 1) / RS_TILE;
+    if (tiles <= 0)
+        return;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(rs_onesweep_text_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TX_SMEM);
+        cudaFuncSetAttribute(rs_onesweep_text_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TX_SMEM);
+        cudaFuncSetAttribute(rs_onesweep_text_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TX_SMEM);
+        attr = true;
+    }
+    cudaMemsetAsync(A.totals, 0, sizeof(u32) * 2048 * (size_t)nBlocks, s);
+    cudaMemsetAsync(A.ticket, 0, sizeof(int) * 8 * (size_t)A.maxBlocks, s);
+    KLAUNCH(rs_text_hist_kernel, dim3((maxCnt + RS_TILE * 4 - 1) / (RS_TILE * 4), nBlocks), RS_THREADS, s, A, T);
+    KLAUNCH(rs_text_plan_kernel, nBlocks, 256, s, A, T, nBlocks);
+    *launches += 2;
+    for (int p = 0; p < 8; p++) {
+        cudaMemset2DAsync(A.hist, sizeof(u32) * 256 * (size_t)A.maxTiles, 0, sizeof(u32) * 256 * (size_t)tiles,
+                          (size_t)nBlocks, s);
+        static int dbgAllGather = -1;
+        if (dbgAllGather < 0) {
+            const char* e = getenv("KNZ_TX_ALLGATHER");
+            dbgAllGather = (e && atoi(e)) ? 1 : 0;
+        }
+        if (p == 0)
+            KLAUNCH_DYN(rs_onesweep_text_kernel<0>, dim3(tiles, nBlocks), RS_THREADS, TX_SMEM, s, A, T, p);
+        else if ((p & 1) && !dbgAllGather)
+            KLAUNCH_DYN(rs_onesweep_text_kernel<1>, dim3(tiles, nBlocks), RS_THREADS, TX_SMEM, s, A, T, p);
+        else
+            KLAUNCH_DYN(rs_onesweep_text_kernel<2>, dim3(tiles, nBlocks), RS_THREADS, TX_SMEM, s, A, T, p);
+        *launches += 1;
+    }
+    const int gblocks = min((maxCnt + 255) / 256, 2048);
+    static int dbgSlow = -1;
+    if (dbgSlow < 0) {
+        const char* e = getenv("KNZ_TX_REGEN_SLOW");
+        dbgSlow = (e && atoi(e)) ? 1 : 0;
+    }
+    KLAUNCH(bwt_regen_keys_kernel, dim3(gblocks, nBlocks), 256, s, A, T, dbgSlow);
+#ifndef KNZ_SIM
+    static int dbgCheck = -1;
+    if (dbgCheck < 0) {
+        const char* e = getenv("KNZ_TX_CHECK");
+        dbgCheck = (e && atoi(e)) ? 1 : 0;
+    }
+    if (dbgCheck) {
+        bwt_regen_check_kernel<<<dim3(gblocks, nBlocks), 256, 0, s>>>(A, T);
+        cudaStreamSynchronize(s);
+    }
+#endif
+    *launches += 1;
 }
 
 // ------------------------------------------------------------------ forward
@@ -808,9 +1151,22 @@ void launch_bwt_forward(const StageLaunch& L, Workspace& ws, cudaStream_t s, u64
     const int maxTiles = (ws.capN + RS_TILE - 1) / RS_TILE;
     int* whichRows = ws.which;
     KLAUNCH(bwt_decide_kernel, (nB + 63) / 64, 64, s, L, ws.cnt, whichRows, ws.bwtOk);
-    const int initBlocks = min((L.maxLen + 255) / 256, 1024);
-    KLAUNCH(bwt_init_keys_kernel, dim3(initBlocks, nB), 256, s, L.bt, L.stIn, ws.bwtOk, ws.capN, ws.keyA, ws.valA);
-    *launches += 2;
+    // blocks of <= 4 MiB: index-only initial sort (digits gathered from the text); else keys travel
+    static int textMode = -1;
+    if (textMode < 0) {
+        const char* e = getenv("KNZ_BWT_TEXTSORT");
+        textMode = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    // L.maxLen bounds the stage OUTPUT (input + 33 per BWT stage so far): indexes stay below 2^22
+    const bool useText = textMode && (L.maxLen - 33 * (L.stageIdx + 1) <= (1 << TX_IDX_BITS));
+    if (getenv("KNZ_VERBOSE"))
+        fprintf(stderr, "bwt_forward: nB=%d maxLen=%d stage=%d text-mode=%d\n", nB, L.maxLen, L.stageIdx, (int)useText);
+    *launches += 1;
+    if (!useText) {
+        const int initBlocks = min((L.maxLen + 255) / 256, 1024);
+        KLAUNCH(bwt_init_keys_kernel, dim3(initBlocks, nB), 256, s, L.bt, L.stIn, ws.bwtOk, ws.capN, ws.keyA, ws.valA);
+        *launches += 1;
+    }
 
     SortArrays A;
     A.key[0] = ws.keyA;
@@ -890,7 +1246,14 @@ void launch_bwt_forward(const StageLaunch& L, Workspace& ws, cudaStream_t s, u64
         G.initial = (round == 0) ? 1 : 0;
         const int tiles = (maxCnt + RS_TILE - 1) / RS_TILE;
         if (round == 0) {
-            radix_sort(A, nB, maxCnt, 0xFFu, s, launches);
+            if (useText) {
+                TextSort T;
+                T.bt = L.bt;
+                T.st = L.stIn;
+                radix_sort_text(A, T, nB, maxCnt, s, launches);
+            } else {
+                radix_sort(A, nB, maxCnt, 0xFFu, s, launches);
+            }
         } else {
             // groups inside one tile: shared-memory sort; groups crossing tiles: side radix sort
             KLAUNCH(bwt_tile_sort_kernel, dim3(tiles, nB), RS_THREADS, s, X);

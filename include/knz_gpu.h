@@ -141,6 +141,14 @@ void* knz_stream(const knz_ctx* ctx);
  * events on the library stream: [0]=BWT [1]=RANK/MTFT [2]=ZRLT [3]=entropy stage
  * [4]=bit assembly [5]=total [6]=rANS encode kernel alone [7]=rANS decode kernel alone. */
 void knz_last_timings(const knz_ctx* ctx, float ms[8]);
+/* Decode scheduling: the blocks of a batch are decoded as `groups` (1..8) independent groups on
+ * separate CUDA streams, so the serial inverse RANK/MTFT chain of one group (the counterpart of
+ * SBRT::inverse, src/transform/SBRT.cpp:99-145, one dependency chain per block) overlaps the
+ * entropy / ZRLT / BWT stages of the others -- the role DecodingTask concurrency plays in
+ * src/io/CompressedInputStream.cpp:436-470.  1 = one group: knz_last_timings is split per stage;
+ * with more groups only the total [5] is meaningful.  Default 1 (env KNZ_DEC_OVERLAP): on B200 the
+ * chain warps slow down when they share SMs with the other groups' kernels.      */
+int knz_set_decode_groups(knz_ctx* ctx, int groups);
 
 #ifdef __cplusplus
 }

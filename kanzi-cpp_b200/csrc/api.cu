@@ -21,6 +21,8 @@
         }                                                                                          \
     } while (0)
 
+#define KNZ_MAX_GROUPS 8
+
 struct knz_ctx {
     int device, maxBlockSize, maxBatch;
     cudaStream_t stream;
@@ -28,6 +30,9 @@ struct knz_ctx {
     cudaStream_t d2hStream;  // device->host copies of finished output (second DMA direction)
     cudaEvent_t evCopy[2], evDone[2];
     cudaEvent_t ev[10];
+    cudaStream_t gStream[KNZ_MAX_GROUPS]; // decode: one stream per block group (stages of different groups overlap)
+    cudaEvent_t gEv[KNZ_MAX_GROUPS + 1];
+    int decGroups;                        // 1 = one group, per-stage timings valid
     i64 bstride;     // stride of the ping-pong stage buffers
     u8 *bufA, *bufB; // [maxBatch * bstride]
     u8* dStageIn;    // host API: staged input blocks [maxBatch * bstride]
@@ -170,6 +175,18 @@ extern "C" int knz_create(int device, int maxBlockSize, int maxBatchBlocks, knz_
     }
     for (int i = 0; i < 10; i++)
         A(cudaEventCreate(&ctx->ev[i]));
+    for (int i = 0; i < KNZ_MAX_GROUPS; i++)
+        A(cudaStreamCreateWithFlags(&ctx->gStream[i], cudaStreamNonBlocking));
+    for (int i = 0; i <= KNZ_MAX_GROUPS; i++)
+        A(cudaEventCreate(&ctx->gEv[i]));
+    {
+        // Block groups of the decode pipeline.  Default 1: measured on B200 (256 x 4 MiB blocks) 2 groups
+        // = 193 ms (same as 1), 4 groups = 213 ms -- the inverse RANK chain warps lose issue slots to
+        // the throughput kernels they share an SM with, which costs more than the overlap returns.
+        const char* e = getenv("KNZ_DEC_OVERLAP");
+        const int g = e ? atoi(e) : 1;
+        ctx->decGroups = g < 1 ? 1 : (g > KNZ_MAX_GROUPS ? KNZ_MAX_GROUPS : g);
+    }
     A(dalloc(&ctx->bufA, nb * ctx->bstride + 256));
     A(dalloc(&ctx->bufB, nb * ctx->bstride + 256));
     A(dalloc(&ctx->dStageIn, nb * ctx->bstride + 256));
@@ -238,6 +255,12 @@ extern "C" void knz_destroy(knz_ctx* ctx)
         if (ctx->evDone[i])
             cudaEventDestroy(ctx->evDone[i]);
     }
+    for (int i = 0; i < KNZ_MAX_GROUPS; i++)
+        if (ctx->gStream[i])
+            cudaStreamDestroy(ctx->gStream[i]);
+    for (int i = 0; i <= KNZ_MAX_GROUPS; i++)
+        if (ctx->gEv[i])
+            cudaEventDestroy(ctx->gEv[i]);
     if (ctx->copyStream)
         cudaStreamDestroy(ctx->copyStream);
     if (ctx->d2hStream)
@@ -245,6 +268,14 @@ extern "C" void knz_destroy(knz_ctx* ctx)
     if (ctx->stream)
         cudaStreamDestroy(ctx->stream);
     free(ctx);
+}
+
+extern "C" int knz_set_decode_groups(knz_ctx* ctx, int groups)
+{
+    if (ctx == NULL || groups < 1 || groups > KNZ_MAX_GROUPS)
+        return KNZ_ERR_INVALID_PARAM;
+    ctx->decGroups = groups;
+    return KNZ_OK;
 }
 
 extern "C" const char* knz_last_error(const knz_ctx* ctx) { return ctx ? ctx->err : "null context"; }
@@ -337,6 +368,7 @@ static int encode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const
         L.capEven = ctx->capEven;
         L.capOdd = ctx->capOdd;
         L.errFlag = ctx->errFlag;
+        L.wsBlock0 = 0;
         CK(cudaEventRecord(ctx->ev[1], s));
         switch (types[i]) {
         case T_NONE:
@@ -817,14 +849,102 @@ static int decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const
     D.errFlag = ctx->errFlag;
     D.evK0 = ctx->ev[8];
     D.evK1 = ctx->ev[9];
-    launch_entropy_decode(D, s, &ctx->launches);
-    CK(cudaEventRecord(ctx->ev[1], s));
-
     BufTable bt;
     bt.base[0] = ctx->bufA;
     bt.base[1] = ctx->bufB;
     bt.base[2] = ctx->bufA;
     bt.stride[0] = bt.stride[1] = bt.stride[2] = ctx->bstride;
+
+    // Overlapped mode: the batch is cut into block groups, each running the whole inverse chain on
+    // its own stream over its own slice of the scratch arrays.  The inverse RANK/MTFT stage is one
+    // dependency chain per block (one warp per block, ~140 ms for 4 MiB whatever the batch size):
+    // while one group sits in it the SMs run the entropy / ZRLT / BWT stages of the other groups.
+    const int G = (ctx->decGroups > 1 && nB >= 4 * ctx->decGroups) ? ctx->decGroups : 1;
+    if (G > 1) {
+        const bool sink = (h_sink != NULL) && (outStride == blockSize);
+        CK(cudaEventRecord(ctx->gEv[KNZ_MAX_GROUPS], s));
+        for (int g = 0; g < G; g++) {
+            const int g0 = (int)((i64)nB * g / G), g1 = (int)((i64)nB * (g + 1) / G);
+            cudaStream_t sg = ctx->gStream[g];
+            CK(cudaStreamWaitEvent(sg, ctx->gEv[KNZ_MAX_GROUPS], 0));
+            DecodeLaunch Dg = D;
+            Dg.in = d_in + (i64)g0 * inStride;
+            Dg.inBits = ctx->dInBits + g0;
+            Dg.payStart = ctx->dPayStart + g0;
+            Dg.preLen = ctx->dPreLen + g0;
+            Dg.nBlocks = g1 - g0;
+            Dg.chunkPos = ctx->chunkPos + (i64)g0 * ctx->maxChunks;
+            Dg.dst = ctx->bufA + (i64)g0 * ctx->bstride;
+            Dg.evK0 = NULL;
+            Dg.evK1 = NULL;
+            launch_entropy_decode(Dg, sg, &ctx->launches);
+            int stepg = 0;
+            for (int i = nt - 1; i >= 0; i--, stepg++) {
+                StageLaunch L;
+                L.bt = bt;
+                for (int k = 0; k < 3; k++)
+                    L.bt.base[k] = bt.base[k] + (i64)g0 * bt.stride[k];
+                L.stIn = ctx->st + (i64)stepg * ctx->maxBatch + g0;
+                L.stOut = ctx->st + (i64)(stepg + 1) * ctx->maxBatch + g0;
+                L.stageIdx = i;
+                L.nBlocks = g1 - g0;
+                L.maxLen = blkLen;
+                L.capEven = ctx->capEven + g0;
+                L.capOdd = ctx->capOdd + g0;
+                L.errFlag = ctx->errFlag;
+                L.wsBlock0 = g0;
+                switch (types[i]) {
+                case T_NONE:
+                    launch_none_forward(L, sg, &ctx->launches);
+                    break;
+                case T_BWT:
+                    launch_bwt_inverse(L, ctx->ws, sg, &ctx->launches);
+                    break;
+                case T_ZRLT:
+                    launch_zrlt_inverse(L, ctx->ws, sg, &ctx->launches);
+                    break;
+                case T_MTFT:
+                    launch_sbrt_inverse(L, 1, ctx->ws, sg, &ctx->launches);
+                    break;
+                case T_RANK:
+                    launch_sbrt_inverse(L, 2, ctx->ws, sg, &ctx->launches);
+                    break;
+                }
+            }
+            {
+                BufTable btg = bt;
+                for (int k = 0; k < 3; k++)
+                    btg.base[k] = bt.base[k] + (i64)g0 * bt.stride[k];
+                launch_copy_out(btg, ctx->st + (i64)nt * ctx->maxBatch + g0, g1 - g0, d_out + (i64)g0 * outStride,
+                                outStride, sg, &ctx->launches);
+            }
+            if (sink) { // full-size blocks go to the host as soon as their group is done
+                const int last = (g1 == nB) ? g1 - 1 : g1; // the batch's last block may be short: the caller copies it
+                if (last > g0)
+                    CK(cudaMemcpyAsync(h_sink + (i64)g0 * blockSize, d_out + (i64)g0 * outStride,
+                                       (size_t)(last - g0) * (size_t)blockSize, cudaMemcpyDeviceToHost, sg));
+            }
+            CK(cudaEventRecord(ctx->gEv[g], sg));
+            CK(cudaStreamWaitEvent(s, ctx->gEv[g], 0));
+        }
+        if (sink)
+            *h_sinkBlocks = nB - 1;
+        const BlkState* stF = ctx->st + (i64)nt * ctx->maxBatch;
+        CK(cudaEventRecord(ctx->ev[4], s));
+        CK(cudaMemcpyAsync(ctx->h_err, ctx->errFlag, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(ctx->h_st, stF, sizeof(BlkState) * nB, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        CK(cudaGetLastError());
+        float msT = 0.f;
+        cudaEventElapsedTime(&msT, ctx->ev[0], ctx->ev[4]);
+        ctx->ms[5] = msT; // per-stage times are not separable when the groups overlap
+        for (int b = 0; b < nB; b++)
+            h_outLens[b] = ctx->h_st[b].len;
+        return map_kerr(ctx, ctx->h_err[0]);
+    }
+
+    launch_entropy_decode(D, s, &ctx->launches);
+    CK(cudaEventRecord(ctx->ev[1], s));
     int step = 0;
     for (int i = nt - 1; i >= 0; i--, step++) {
         StageLaunch L;
@@ -837,6 +957,7 @@ static int decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const
         L.capEven = ctx->capEven;
         L.capOdd = ctx->capOdd;
         L.errFlag = ctx->errFlag;
+        L.wsBlock0 = 0;
         CK(cudaEventRecord(ctx->ev[2], s));
         // Last stage of a full batch with a host sink: inverse-BWT the blocks in four groups and
         // send each group's (full-size) blocks to the host while the next group is being walked.
@@ -1240,6 +1361,7 @@ static int run_single_stage(knz_ctx* ctx, int type, bool inverse, const u8* in, 
     L.capEven = ctx->capEven;
     L.capOdd = ctx->capOdd;
     L.errFlag = ctx->errFlag;
+    L.wsBlock0 = 0;
     CK(cudaEventRecord(ctx->ev[1], s));
     switch (type) {
     case T_NONE:

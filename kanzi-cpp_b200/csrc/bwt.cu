@@ -138,9 +138,24 @@ __device__ __forceinline__ u32 os_peek(const u32* p)
 #endif
 }
 
+// CTA -> block mapping of the one-sweep kernels (1-D grid of tilesMax * nBlocks CTAs): consecutive
+// CTAs serve different blocks of a group of OS_GROUP blocks, so the CTAs in flight are spread over
+// OS_GROUP look-back chains (a chain link costs an L2 round trip; with one block at a time every
+// tile polled a long run of unfinished predecessors) while the group's text stays L2 resident.
+#define OS_GROUP 16
+__device__ __forceinline__ int os_block_of_cta(int nBlocks, int tilesMax)
+{
+    const int id = (int)blockIdx.x;
+    const int per = OS_GROUP * tilesMax;
+    const int g = id / per;
+    const int r = id - g * per;
+    const int nbg = min(OS_GROUP, nBlocks - g * OS_GROUP);
+    return g * OS_GROUP + (r % nbg);
+}
+
 template <int OS_ITEMS>
 __global__ void __launch_bounds__(RS_THREADS, (OS_ITEMS <= 8) ? 4 : 2)
-rs_onesweep_kernel(SortArrays A, int pass)
+rs_onesweep_kernel(SortArrays A, int pass, int nBlocks, int tilesMax)
 {
     constexpr int OS_TILE = RS_THREADS * OS_ITEMS;
     KNZ_DYN_SMEM(os_smem);
@@ -150,26 +165,26 @@ rs_onesweep_kernel(SortArrays A, int pass)
     u32* s_delta = reinterpret_cast<u32*>(os_smem + OS_TILE * 12 + (RS_THREADS / 32) * 1024);
     u32* s_toff = s_delta + 256;
     u32* s_w = s_toff + 256; // 8 words for the block scan + 1 for the ticket
-    const int b = blockIdx.y;
+    const int b = os_block_of_cta(nBlocks, tilesMax);
     const int cnt = A.cnt[b];
     if (cnt <= 0 || A.trivial[pass * A.maxBlocks + b])
         return;
     const int tiles = (cnt + OS_TILE - 1) / OS_TILE;
-    if ((int)blockIdx.x >= tiles)
-        return;
     if (threadIdx.x == 0)
         s_w[8] = (u32)atomicAdd(&A.ticket[pass * A.maxBlocks + b], 1);
     for (int i = threadIdx.x; i < (RS_THREADS / 32) * 256; i += RS_THREADS)
         (&s_cnt[0][0])[i] = 0;
     __syncthreads();
     const int tile = (int)s_w[8];
+    if (tile >= tiles)
+        return; // every block has tilesMax CTAs: the surplus ones of a short block leave here
     const int tbase = tile * OS_TILE;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int src = A.which[pass * A.maxBlocks + b];
-    const u64* __restrict__ kin = A.key[src] + (i64)b * A.capN;
-    const u32* __restrict__ vin = A.val[src] + (i64)b * A.capN;
-    u64* __restrict__ kout = A.key[src ^ 1] + (i64)b * A.capN;
-    u32* __restrict__ vout = A.val[src ^ 1] + (i64)b * A.capN;
+    const u64* __restrict__ kin = (src ? A.key[1] : A.key[0]) + (i64)b * A.capN;
+    const u32* __restrict__ vin = (src ? A.val[1] : A.val[0]) + (i64)b * A.capN;
+    u64* __restrict__ kout = (src ? A.key[0] : A.key[1]) + (i64)b * A.capN;
+    u32* __restrict__ vout = (src ? A.val[0] : A.val[1]) + (i64)b * A.capN;
     const int sh = 8 * pass;
     u64 key[OS_ITEMS];
     u32 val[OS_ITEMS];
@@ -288,9 +303,9 @@ static void radix_sort(const SortArrays& A, int nBlocks, int maxCnt, u32 passMas
         cudaMemset2DAsync(A.hist, sizeof(u32) * 256 * (size_t)A.maxTiles, 0, sizeof(u32) * 256 * (size_t)otiles,
                           (size_t)nBlocks, s);
         if (items == 16)
-            KLAUNCH_DYN(rs_onesweep_kernel<16>, dim3(otiles, nBlocks), RS_THREADS, OS_SMEM(16), s, A, p);
+            KLAUNCH_DYN(rs_onesweep_kernel<16>, otiles * nBlocks, RS_THREADS, OS_SMEM(16), s, A, p, nBlocks, otiles);
         else
-            KLAUNCH_DYN(rs_onesweep_kernel<8>, dim3(otiles, nBlocks), RS_THREADS, OS_SMEM(8), s, A, p);
+            KLAUNCH_DYN(rs_onesweep_kernel<8>, otiles * nBlocks, RS_THREADS, OS_SMEM(8), s, A, p, nBlocks, otiles);
         *launches += 1;
     }
 }
@@ -370,7 +385,7 @@ rs_text_plan_kernel(SortArrays A, TextSort T, int nBlocks)
 // element); 2: even pass >= 2 (digit and the next pass's digit gathered from the text).
 template <int KIND>
 __global__ void __launch_bounds__(RS_THREADS, 4)
-rs_onesweep_text_kernel(SortArrays A, TextSort T, int pass)
+rs_onesweep_text_kernel(SortArrays A, TextSort T, int pass, int nBlocks, int tilesMax)
 {
     KNZ_DYN_SMEM(os_smem);
     u32* s_val = reinterpret_cast<u32*>(os_smem);
@@ -379,24 +394,24 @@ rs_onesweep_text_kernel(SortArrays A, TextSort T, int pass)
     u32* s_toff = s_delta + 256;
     u32* s_w = s_toff + 256; // 8 words for the block scan + 1 for the ticket
     u8* s_dig = reinterpret_cast<u8*>(s_w + 16); // digit of every staged slot
-    const int b = blockIdx.y;
+    const int b = os_block_of_cta(nBlocks, tilesMax);
     const int cnt = A.cnt[b];
     if (cnt <= 0)
         return;
     const int tiles = (cnt + RS_TILE - 1) / RS_TILE;
-    if ((int)blockIdx.x >= tiles)
-        return;
     if (threadIdx.x == 0)
         s_w[8] = (u32)atomicAdd(&A.ticket[pass * A.maxBlocks + b], 1);
     for (int i = threadIdx.x; i < (RS_THREADS / 32) * 256; i += RS_THREADS)
         (&s_cnt[0][0])[i] = 0;
     __syncthreads();
     const int tile = (int)s_w[8];
+    if (tile >= tiles)
+        return;
     const int tbase = tile * RS_TILE;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int src = A.which[pass * A.maxBlocks + b];
-    const u32* __restrict__ vin = A.val[src] + (i64)b * A.capN;
-    u32* __restrict__ vout = A.val[src ^ 1] + (i64)b * A.capN;
+    const u32* __restrict__ vin = (src ? A.val[1] : A.val[0]) + (i64)b * A.capN;
+    u32* __restrict__ vout = (src ? A.val[0] : A.val[1]) + (i64)b * A.capN;
     const u8* __restrict__ text = blk_src(T.bt, T.st[b], b);
     const int sft = 7 - pass; // digit = text[index + sft]
     u32 val[RS_ITEMS];
@@ -609,11 +624,11 @@ static void radix_sort_text(const SortArrays& A, const TextSort& T, int nBlocks,
             dbgAllGather = (e && atoi(e)) ? 1 : 0;
         }
         if (p == 0)
-            KLAUNCH_DYN(rs_onesweep_text_kernel<0>, dim3(tiles, nBlocks), RS_THREADS, TX_SMEM, s, A, T, p);
+            KLAUNCH_DYN(rs_onesweep_text_kernel<0>, tiles * nBlocks, RS_THREADS, TX_SMEM, s, A, T, p, nBlocks, tiles);
         else if ((p & 1) && !dbgAllGather)
-            KLAUNCH_DYN(rs_onesweep_text_kernel<1>, dim3(tiles, nBlocks), RS_THREADS, TX_SMEM, s, A, T, p);
+            KLAUNCH_DYN(rs_onesweep_text_kernel<1>, tiles * nBlocks, RS_THREADS, TX_SMEM, s, A, T, p, nBlocks, tiles);
         else
-            KLAUNCH_DYN(rs_onesweep_text_kernel<2>, dim3(tiles, nBlocks), RS_THREADS, TX_SMEM, s, A, T, p);
+            KLAUNCH_DYN(rs_onesweep_text_kernel<2>, tiles * nBlocks, RS_THREADS, TX_SMEM, s, A, T, p, nBlocks, tiles);
         *launches += 1;
     }
     const int gblocks = min((maxCnt + 255) / 256, 2048);
@@ -1731,10 +1746,24 @@ __global__ void bwt_inv_rank_kernel(InvCtx C)
         atomicExch(C.errFlag, KERR_BAD_STREAM);
 }
 
-void launch_bwt_inverse(const StageLaunch& L, Workspace& ws, cudaStream_t s, u64* launches)
+void launch_bwt_inverse(const StageLaunch& L, Workspace& wsAll, cudaStream_t s, u64* launches)
 {
     const int nB = L.nBlocks;
-    const int maxTiles = (ws.capN + RS_TILE - 1) / RS_TILE;
+    const int maxTiles = (wsAll.capN + RS_TILE - 1) / RS_TILE;
+    // this launch's slice of the per-block scratch (L.wsBlock0 .. + nB)
+    Workspace ws = wsAll;
+    {
+        const i64 g0 = L.wsBlock0;
+        ws.cnt += g0;
+        ws.which += g0; // rows stay maxBlocks apart
+        ws.pidx += g0 * 8;
+        ws.bwtOk += g0;
+        ws.keyA += g0 * wsAll.capN;
+        ws.keyB += g0 * wsAll.capN;
+        ws.totals += g0 * 256; // 256 symbol totals per block in this stage
+        ws.hist += g0 * (i64)maxTiles * 256;
+        ws.digitBase += g0; // one ticket per block
+    }
     KLAUNCH(bwt_inv_decide_kernel, (nB + 63) / 64, 64, s, L, ws.cnt, ws.which, ws.pidx, ws.bwtOk);
     *launches += 1;
     InvCtx C;

@@ -74,6 +74,8 @@ struct StageLaunch {
     const int* capEven; // per block: capacity of the reference's `output` buffer
     const int* capOdd;  // per block: capacity of the reference's `input`/private buffer
     int* errFlag;
+    int wsBlock0;       // first workspace slot of this launch (block groups decoded concurrently on
+                        // separate streams use disjoint slices of the per-block scratch arrays)
 };
 struct Workspace;
 void launch_none_forward(const StageLaunch& L, cudaStream_t s, u64* launches);

@@ -463,9 +463,9 @@ void launch_zrlt_inverse(const StageLaunch& L, Workspace& ws, cudaStream_t s, u6
 {
     const int maxTiles = (ws.capN + Z_TILE - 1) / Z_TILE;
     const int tiles = (L.maxLen + Z_TILE - 1) / Z_TILE;
-    ZSum* tileSum = reinterpret_cast<ZSum*>(ws.tileA);
-    ZEntry* tileEntry = reinterpret_cast<ZEntry*>(ws.tileB);
-    u32* zlen = ws.scanA;
+    ZSum* tileSum = reinterpret_cast<ZSum*>(ws.tileA) + (i64)L.wsBlock0 * maxTiles;
+    ZEntry* tileEntry = reinterpret_cast<ZEntry*>(ws.tileB) + (i64)L.wsBlock0 * maxTiles;
+    u32* zlen = ws.scanA + L.wsBlock0;
     const int bit = 1 << (7 - L.stageIdx);
     KLAUNCH(zrlt_inv_sum_kernel, dim3(tiles, L.nBlocks), Z_THREADS, s, L.bt, L.stIn, bit, maxTiles, tileSum, L.errFlag);
     KLAUNCH(zrlt_fold_kernel<true>, (L.nBlocks + 31) / 32, 32, s, L, maxTiles, tileSum, tileEntry, zlen);

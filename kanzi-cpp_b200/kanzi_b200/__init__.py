@@ -42,6 +42,8 @@ def _load(path):
     L.knz_transform_type.restype = ctypes.c_uint64
     L.knz_transform_type.argtypes = [ctypes.c_char_p]
     L.knz_entropy_type.argtypes = [ctypes.c_char_p]
+    L.knz_set_decode_groups.restype = ctypes.c_int
+    L.knz_set_decode_groups.argtypes = [ctypes.c_void_p, ctypes.c_int]
     L.knz_launch_count.restype = ctypes.c_uint64
     L.knz_launch_count.argtypes = [ctypes.c_void_p]
     L.knz_stream.restype = ctypes.c_void_p
@@ -99,6 +101,10 @@ class Context:
     @property
     def cuda_stream(self):
         return int(self.lib.knz_stream(self.h) or 0)
+
+    def set_decode_groups(self, groups):
+        """Block groups decoded concurrently (1 = serial stages with per-stage timings)."""
+        self._check(self.lib.knz_set_decode_groups(self.h, int(groups)))
 
     def timings(self):
         ms = (ctypes.c_float * 8)()

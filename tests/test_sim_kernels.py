@@ -89,3 +89,18 @@ def test_sim_blocks(sim, oracle):
     dec = sim.decode_blocks([(e[0], e[1]) for e in enc], "BWT+RANK+ZRLT", "ANS0", bs)
     for i, blk in enumerate(blocks):
         assert np.array_equal(dec[i], blk), i
+
+
+def test_sim_decode_groups(oracle):
+    """Block groups decoded on separate streams over disjoint workspace slices (knz_set_decode_groups)."""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "sim"), "-j8"], stdout=subprocess.DEVNULL)
+    from kanzi_b200 import Context
+    bs = 1 << 16
+    ctx = Context(0, bs, 16, lib_path=SIM)
+    data = synth.synth_compressible(9 * bs + 777, 5)
+    comp = ctx.compress(data, "BWT+RANK+ZRLT", "ANS0", bs)
+    assert np.array_equal(comp, oracle.stream_compress(data, "BWT+RANK+ZRLT", "ANS0", bs))
+    for g in (2, 1):
+        ctx.set_decode_groups(g)
+        assert np.array_equal(ctx.decompress(comp, data.size), data), g
+    ctx.close()

@@ -808,91 +808,137 @@ __device__ __forceinline__ u32 rd_bits(const u8* __restrict__ p, u64 pos, int n)
     return (u32)((w >> (40 - sh - n)) & ((n == 32) ? 0xFFFFFFFFull : ((1ull << n) - 1)));
 }
 
-// Pass 1: one thread per block walks the chunk headers to find where each chunk
-// starts (the positions depend on every previous chunk's header and payload
-// size: ANSRangeDecoder.cpp:197-213,221).
-__global__ void ans0_dec_scan_kernel(DecodeLaunch L)
+// Same fetch from a window of the bit string staged in shared memory as 32-bit words whose bit
+// 31 is the first bit (rel = bit offset inside the window, n <= 25 + whatever fits: two words).
+__device__ __forceinline__ u32 rd_win(const u32* __restrict__ w, u32 rel, int n)
 {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= L.nBlocks)
-        return;
+    const u32 i = rel >> 5;
+    const u64 v = ((u64)w[i] << 32) | (u64)w[i + 1];
+    return (u32)((v >> (64 - (int)(rel & 31) - n)) & ((n == 32) ? 0xFFFFFFFFull : ((1ull << n) - 1)));
+}
+
+// Pass 1: where does every chunk start?  The positions depend on every previous chunk's header
+// and payload size (ANSRangeDecoder.cpp:197-213,221), so a block is one serial walk -- done by
+// one warp per block: the warp stages a 512-byte window of the bit string at the current position in
+// shared memory with coalesced 32-bit loads, lane 0 parses the header out of it.
+#define SCAN_WIN_WORDS 128
+__global__ void __launch_bounds__(32)
+ans0_dec_scan_kernel(DecodeLaunch L)
+{
+    __shared__ u32 s_win[SCAN_WIN_WORDS + 2];
+    const int b = blockIdx.x;
+    const int lane = threadIdx.x;
     const int m = L.preLen[b];
     u64* cp = L.chunkPos + (i64)b * L.maxChunks;
     u64 pos = L.payStart[b];
     const u64 endBits = L.inBits[b];
     if (L.eType == E_RAW || m <= 32) {
-        cp[0] = pos;
-        if (pos + 8ull * (u64)m > endBits)
-            atomicExch(L.errFlag, KERR_BAD_STREAM);
+        if (lane == 0) {
+            cp[0] = pos;
+            if (pos + 8ull * (u64)m > endBits)
+                atomicExch(L.errFlag, KERR_BAD_STREAM);
+        }
         return;
     }
     const u8* __restrict__ p = L.in + (i64)b * L.inStride;
+    const u32* __restrict__ pw = reinterpret_cast<const u32*>(p); // block bit strings start 4-byte aligned
+    const bool aligned = (((size_t)p) & 3) == 0;
+    const u64 lastWord = (endBits + 31) >> 5; // words holding valid bits: [0, lastWord)
     const int nChunks = (m + ANS_CHUNK - 1) >> 14;
     for (int c = 0; c < nChunks; c++) {
-        cp[c] = pos;
-        if (pos + 16 > endBits) {
-            atomicExch(L.errFlag, KERR_BAD_STREAM);
+        // stage the window [pos & ~31, + 4096 bits + 2 words): a header is < 3600 bits
+        const u64 w0 = pos >> 5;
+        __syncwarp();
+        for (int i = lane; i < SCAN_WIN_WORDS + 2; i += 32) {
+            const u64 wi = w0 + (u64)i;
+            u32 v = 0;
+            if (wi < lastWord) {
+                if (aligned) {
+                    v = bswap32(__ldg(&pw[wi]));
+                } else {
+                    const u8* q = p + wi * 4;
+                    v = ((u32)q[0] << 24) | ((u32)q[1] << 16) | ((u32)q[2] << 8) | (u32)q[3];
+                }
+            }
+            s_win[i] = v;
+        }
+        __syncwarp();
+        int err = 0;
+        u64 next = pos;
+        if (lane == 0) {
+            cp[c] = pos;
+            u32 rel = (u32)(pos & 31);
+            if (pos + 16 > endBits) {
+                err = KERR_BAD_STREAM;
+            } else {
+                const int lr = 8 + (int)rd_win(s_win, rel, 3);
+                rel += 3;
+                int asz;
+                if (rd_win(s_win, rel, 1) == 0) {
+                    asz = (rd_win(s_win, rel + 1, 1) == 0) ? 256 : 0;
+                    rel += 2;
+                } else {
+                    const int last = (int)rd_win(s_win, rel + 1, 5);
+                    rel += 6;
+                    asz = 0;
+                    for (int i = 0; i <= last; i++) {
+                        asz += __popc(rd_win(s_win, rel, 8));
+                        rel += 8;
+                    }
+                }
+                if (asz == 0 || lr > ANS0_LR) {
+                    err = (asz == 0) ? KERR_BAD_STREAM : KERR_UNSUPPORTED;
+                } else {
+                    const int chk = (asz >= 64) ? 8 : 6;
+                    const int llr = ilog2_u32((u32)lr) + 1;
+                    // header <= 3 + 6 + 256 + 43 * 4 + 255 * lr bits < the window
+                    for (int i = 1; i < asz && !err; i += chk) {
+                        const int logMax = (int)rd_win(s_win, rel, llr);
+                        rel += llr;
+                        if (logMax > lr)
+                            err = KERR_BAD_STREAM;
+                        rel += (u32)logMax * (u32)min(chk, asz - i);
+                    }
+                    u64 q = (pos & ~31ull) + rel;
+                    if (!err && asz > 1) {
+                        u32 v = rd_win(s_win, rel, 8);
+                        rel += 8;
+                        u32 sz = v & 0x7F;
+                        for (int shift = 7; v >= 128 && shift <= 28; shift += 7) {
+                            v = rd_win(s_win, rel, 8);
+                            rel += 8;
+                            sz |= (v & 0x7F) << shift;
+                        }
+                        q = (pos & ~31ull) + rel + 128 + 8ull * sz;
+                    }
+                    if (q > endBits)
+                        err = KERR_BAD_STREAM;
+                    next = q;
+                }
+            }
+        }
+        err = __shfl_sync(FULL_MASK, err, 0);
+        if (err) {
+            if (lane == 0)
+                atomicExch(L.errFlag, err);
             return;
         }
-        const int lr = 8 + (int)rd_bits(p, pos, 3);
-        pos += 3;
-        int asz;
-        if (rd_bits(p, pos, 1) == 0) {
-            asz = (rd_bits(p, pos + 1, 1) == 0) ? 256 : 0;
-            pos += 2;
-        } else {
-            const int last = (int)rd_bits(p, pos + 1, 5);
-            pos += 6;
-            asz = 0;
-            for (int i = 0; i <= last; i++) {
-                asz += __popc(rd_bits(p, pos, 8));
-                pos += 8;
-            }
-        }
-        if (asz == 0 || lr > ANS0_LR) {
-            atomicExch(L.errFlag, (asz == 0) ? KERR_BAD_STREAM : KERR_UNSUPPORTED);
-            return;
-        }
-        const int chk = (asz >= 64) ? 8 : 6;
-        const int llr = ilog2_u32((u32)lr) + 1;
-        for (int i = 1; i < asz; i += chk) {
-            const int logMax = (int)rd_bits(p, pos, llr);
-            pos += llr;
-            if (logMax > lr) {
-                atomicExch(L.errFlag, KERR_BAD_STREAM);
-                return;
-            }
-            pos += (u64)logMax * (u64)min(chk, asz - i);
-            if (pos > endBits) {
-                atomicExch(L.errFlag, KERR_BAD_STREAM);
-                return;
-            }
-        }
-        if (asz > 1) {
-            u32 v = rd_bits(p, pos, 8);
-            pos += 8;
-            u32 sz = v & 0x7F;
-            for (int shift = 7; v >= 128 && shift <= 28; shift += 7) {
-                v = rd_bits(p, pos, 8);
-                pos += 8;
-                sz |= (v & 0x7F) << shift;
-            }
-            pos += 128 + 8ull * sz;
-        }
-        if (pos > endBits) {
-            atomicExch(L.errFlag, KERR_BAD_STREAM);
-            return;
-        }
+        pos = __shfl_sync(FULL_MASK, next, 0);
     }
 }
 
-// Pass 2: one warp per 8 chunks, one quad per chunk.
-// smem per chunk: 4 KiB slot->symbol table + 256 x (freq | cum<<16).
+// Pass 2: one warp per 8 chunks, one quad per chunk, lane k owns state k.
+// smem per chunk: 4 KiB slot->symbol table, 256 x (freq | cum << 16), and a 128-word ring of the
+// chunk's renormalisation words: the quad copies the (bit-misaligned) payload into it 32 words
+// at a time, shifted into place, one refill ahead of the coding loop, so a renormalisation is a
+// shared-memory read instead of a global one on the state's dependency chain.
+#define DEC_RING 128
 __global__ void __launch_bounds__(32)
 ans0_decode_kernel(DecodeLaunch L)
 {
     __shared__ __align__(16) u8 s_f2s[8][1 << ANS0_LR];
     __shared__ u32 s_fc[8][256];
+    __shared__ __align__(16) u32 s_ring[8][DEC_RING / 2];
 
     const int lane = threadIdx.x;
     const int groupsPerBlk = (L.maxChunks + 7) >> 3;
@@ -990,17 +1036,6 @@ ans0_decode_kernel(DecodeLaunch L)
             if (asz == 1) {
                 single = 1 + firstSym;
             } else {
-                u8* f2s = s_f2s[j];
-                u32 run = 0;
-                for (int i = 0; i < 256; i++) {
-                    const u32 fr = fc[i];
-                    if (fr == 0)
-                        continue;
-                    for (u32 t = 0; t < fr; t++)
-                        f2s[run + t] = (u8)i;
-                    fc[i] = fr | (run << 16);
-                    run += fr;
-                }
                 u32 v = rd_bits(p, pos, 8);
                 pos += 8;
                 psz = v & 0x7F;
@@ -1030,6 +1065,37 @@ ans0_decode_kernel(DecodeLaunch L)
         const u32 c2 = __shfl_sync(FULL_MASK, st2, qlead), d3 = __shfl_sync(FULL_MASK, st3, qlead);
         state = (k == 0) ? a : (k == 1) ? b1 : (k == 2) ? c2 : d3;
     }
+    const bool active = valid && asz > 1;
+    // slot -> symbol table and cumulative frequencies: the quad's four lanes fill it together
+    // (lane k takes the symbols k, k+4, ...; each writes its symbol's run of slots)
+    {
+        u32* fc = s_fc[j];
+        u8* f2s = s_f2s[j];
+        // exclusive prefix of the frequencies: lane k sums its 64 consecutive symbols first
+        u32 part = 0;
+        if (active)
+            for (int i = 64 * k; i < 64 * k + 64; i++)
+                part += fc[i];
+        u32 run = 0;
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+            const u32 v = __shfl_sync(FULL_MASK, part, qlead + t);
+            if (t < k)
+                run += v;
+        }
+        if (active) {
+            for (int i = 64 * k; i < 64 * k + 64; i++) {
+                const u32 fr = fc[i];
+                if (fr == 0)
+                    continue;
+                for (u32 t = 0; t < fr; t++)
+                    f2s[run + t] = (u8)i;
+                fc[i] = fr | (run << 16);
+                run += fr;
+            }
+        }
+    }
+    __syncwarp();
 
     // single-symbol chunks: fill (ANSRangeDecoder.cpp:203-205)
     if (single) {
@@ -1037,7 +1103,6 @@ ans0_decode_kernel(DecodeLaunch L)
             o[i] = (u8)(single - 1);
     }
 
-    const bool active = valid && asz > 1;
     const int count4 = len & ~3;
     const int steps = active ? (count4 >> 2) : 0;
     int maxSteps = steps;
@@ -1047,26 +1112,117 @@ ans0_decode_kernel(DecodeLaunch L)
     const u32 mask = (1u << lr) - 1;
     const u8* f2s = s_f2s[j];
     const u32* fc = s_fc[j];
-    u32 cnt = 0; // 16-bit words consumed by the quad so far
-    for (int s = 0; s < maxSteps; s++) {
-        bool need = false;
-        u32 cur = 0;
-        if (s < steps) {
-            cur = f2s[state & mask];
-            const u32 e = fc[cur];
-            state = (e & 0xFFFF) * (state >> lr) + (state & mask) - (e >> 16);
-            need = state < (1u << 15);
-            o[4 * s + 3 - k] = (u8)cur; // st3 -> i, st2 -> i+1, st1 -> i+2, st0 -> i+3
+
+    // ---- renormalisation ring.  Word w of the payload = bits [pos + 16 w, + 16) of the block's bit string.
+    // A refill = 32 words = 64 bytes; lane k produces bytes [16 k, 16 k + 16) of it from five aligned
+    // source words, funnel-shifted by the payload's misalignment; ring word pairs are stored first
+    // word in the high half, so word w is the 16-bit value at index w ^ 1.  The loads of a refill
+    // are issued one period (8 steps) before their data is shifted into the ring.
+    const u32* __restrict__ pw = reinterpret_cast<const u32*>(p);
+    const bool aligned = (((size_t)p) & 3) == 0;
+    const u32 lastWord = (u32)((L.inBits[b] + 31) >> 5);
+    u32* ring = s_ring[j];
+    const u16* ring16 = reinterpret_cast<const u16*>(ring);
+    u32 filled = 0; // words staged so far (multiple of 32)
+    const u32 wordsTotal = active ? (psz >> 1) : 0;
+    const int fsh = (int)((pos + 128ull * (u32)k) & 31);     // the same for every refill (64 bytes apart)
+    u32 srcw = (u32)((pos + 128ull * (u32)k) >> 5);          // first source word of this lane's next refill
+    u32 pend[5];
+    bool havePending = false;
+    auto issue = [&]() {
+#pragma unroll
+        for (int t = 0; t < 5; t++) {
+            const u32 wi = srcw + (u32)t;
+            u32 v = 0;
+            if (wi < lastWord) {
+                if (aligned) {
+                    v = __ldg(&pw[wi]);
+                } else {
+                    const u8* q = p + (u64)wi * 4;
+                    v = (u32)q[0] | ((u32)q[1] << 8) | ((u32)q[2] << 16) | ((u32)q[3] << 24);
+                }
+            }
+            pend[t] = v; // memory byte order; swapped when it lands in the ring
         }
-        const u32 bal = __ballot_sync(FULL_MASK, need);
-        const u32 qb = (bal >> qlead) & 0xF;
-        if (need) {
-            // consumption order inside a step: st3, st2, st1, st0 (ANSRangeDecoder.cpp:245-258)
-            const u32 idx = cnt + __popc(qb >> (k + 1));
-            state = (state << 16) | rd_bits(p, pos + 16ull * idx, 16);
+        srcw += 16;
+    };
+    auto store = [&]() {
+        const u32 w0 = bswap32(pend[0]), w1 = bswap32(pend[1]), w2 = bswap32(pend[2]), w3 = bswap32(pend[3]),
+                  w4 = bswap32(pend[4]);
+        uint4 v;
+        v.x = __funnelshift_l(w1, w0, fsh);
+        v.y = __funnelshift_l(w2, w1, fsh);
+        v.z = __funnelshift_l(w3, w2, fsh);
+        v.w = __funnelshift_l(w4, w3, fsh);
+        *reinterpret_cast<uint4*>(ring + (((filled & (DEC_RING - 1)) >> 1) + 4 * k)) = v;
+        filled += 32;
+    };
+    // initial fill: the whole ring
+    for (int r = 0; r < DEC_RING / 32; r++) {
+        if (active) {
+            issue();
+            store();
         }
-        cnt += __popc(qb);
     }
+    __syncwarp();
+
+    u32 cnt = 0; // 16-bit words consumed by the quad so far
+    // every 8 steps (<= 32 words consumed): land the refill issued last time, issue the next one
+#define DEC_REFILL()                                                                             \
+    {                                                                                            \
+        if (havePending) {                                                                       \
+            store();                                                                             \
+            havePending = false;                                                                 \
+        }                                                                                        \
+        if (active && filled - cnt <= DEC_RING - 32 && filled < wordsTotal + 32) {               \
+            issue();                                                                             \
+            havePending = true;                                                                  \
+        }                                                                                        \
+        __syncwarp();                                                                            \
+    }
+    // one step; LIVE masks lanes whose chunk has no step here (their table reads stay in bounds)
+#define DEC_STEP(LIVE, OUT)                                                                      \
+    {                                                                                            \
+        const u32 slot_ = state & mask;                                                          \
+        const u32 cur_ = f2s[slot_];                                                             \
+        const u32 e_ = fc[cur_];                                                                 \
+        const u32 nst_ = (e_ & 0xFFFF) * (state >> lr) + slot_ - (e_ >> 16);                     \
+        const bool need_ = (LIVE) && nst_ < (1u << 15);                                          \
+        if (LIVE) {                                                                              \
+            state = nst_;                                                                        \
+            (OUT) = (u8)cur_; /* st3 -> i, st2 -> i+1, st1 -> i+2, st0 -> i+3 */                 \
+        }                                                                                        \
+        const u32 bal_ = __ballot_sync(FULL_MASK, need_);                                        \
+        if (need_) { /* consumption order inside a step: st3, st2, st1, st0 (ANSRangeDecoder.cpp:245-258) */ \
+            const u32 idx_ = cnt + (u32)__popc(bal_ & mAbove);                                   \
+            state = (state << 16) | (u32)ring16[(idx_ & (DEC_RING - 1)) ^ 1];                    \
+        }                                                                                        \
+        cnt += (u32)__popc(bal_ & mQuad);                                                        \
+    }
+    const u32 mQuad = 0xFu << qlead;
+    const u32 mAbove = (0xFu << (k + 1) & 0xFu) << qlead; // states consumed before this lane's in a step
+    int minSteps = active ? steps : 0x7FFFFFFF;
+#pragma unroll
+    for (int x = 16; x > 0; x >>= 1)
+        minSteps = min(minSteps, __shfl_xor_sync(FULL_MASK, minSteps, x));
+    const int fast = (maxSteps > 0) ? (minSteps & ~7) : 0; // steps every active quad takes
+    u8* op = o + (3 - k);
+    int s = 0;
+    for (; s < fast; s += 8) {
+        DEC_REFILL()
+#pragma unroll
+        for (int x = 0; x < 8; x++)
+            DEC_STEP(active, op[4 * x])
+        op += 32;
+    }
+    for (; s < maxSteps; s++) {
+        if ((s & 7) == 0)
+            DEC_REFILL()
+        DEC_STEP(s < steps, op[0])
+        op += 4;
+    }
+#undef DEC_STEP
+#undef DEC_REFILL
     if (active && k == 0) {
         const int tail = len & 3;
         for (int t = 0; t < tail; t++)
@@ -1082,7 +1238,7 @@ void launch_entropy_decode(const DecodeLaunch& L, cudaStream_t s, u64* launches)
         launch_huffman_decode(L, s, launches);
         return;
     }
-    KLAUNCH(ans0_dec_scan_kernel, (L.nBlocks + 31) / 32, 32, s, L);
+    KLAUNCH(ans0_dec_scan_kernel, L.nBlocks, 32, s, L);
     const int groups = (L.maxChunks + 7) / 8;
     if (L.evK0)
         cudaEventRecord(L.evK0, s);

@@ -12,9 +12,10 @@ A "step" = one encode pass + one decode pass over the whole input.
   e2e     same metric through the public API with HOST buffers: pinned-host -> device
           copies of the input, device -> host of the compressed stream and of the
           decoded bytes inside the timed region (knz_compress / knz_decompress at N=1).
-  roofline  dominant stage (BWT forward: radix-sort prefix doubling) against the HBM
-          roofline with SURVEY.md §8(d) algorithmic bytes (2n+25 per block); the other
-          stages, incl. the rANS kernel alone (m + e bytes), are under roofline_stages.
+  roofline  dominant kernel of the step (inverse RANK, one launch) against the HBM roofline
+          with SURVEY.md §8(d) algorithmic bytes (2n per block) and the DRAM traffic of the
+          committed ncu capture; every stage, incl. BWT forward (2n+25) and the rANS kernels
+          alone (m + e bytes), is under roofline_stages.
   cpu_baseline / --impl reference: the unmodified reference (oracle/_ref, built from
           /root/reference by oracle/Makefile) with all host threads on a bounded sample.
 """
@@ -381,9 +382,20 @@ def run_ours(args, rank, world, local_rank):
             stages[f"{ename.lower()}_decode_kernel_config4"] = rl(my_bytes + e4, t4d["ans_dec_kernel"])
     except Exception as ex:
         stages["config4_error"] = str(ex)
-    dominant = dict(stages["bwt_forward"] or {})
-    dominant["kernel"] = ("bwt_forward stage (segmented radix-sort prefix doubling: rs_scatter/rs_hist/"
-                          "bwt_grp_* kernels), dominant share of the encode pass")
+    # DRAM traffic per launch from the committed `ncu --set full` captures (profiles/r01_ncu_*.md),
+    # scaled to this rank's blocks: dram__bytes_read.sum + dram__bytes_write.sum
+    NCU_TRAFFIC_PER_BLOCK = {
+        "rank_inverse": (1.088619e9 + 1.040149e9) / 256,      # r01_ncu_rank_inverse_256blocks.md
+        "ans0_encode_kernel_config4": (491.811584e6 + 145.973248e6) / 64,  # r01_ncu_ans0_encode_v5_64blocks_config4.md
+    }
+    for k, per_block in NCU_TRAFFIC_PER_BLOCK.items():
+        if stages.get(k):
+            stages[k]["traffic"] = per_block * nb
+    # the dominant KERNEL of the step: the inverse RANK chain (one launch, ~1/3 of the step on its own)
+    dominant = dict(stages["rank_inverse"] or {})
+    dominant["kernel"] = ("sbrt_inverse_fast_kernel<2> (inverse RANK: one dependency chain per block, one warp per "
+                          "block; latency-bound, DRAM traffic = algorithmic bytes); the largest stage, BWT forward, "
+                          "is ~100 launches and is listed under roofline_stages")
     dominant["peak_source"] = peak_src
 
     # ---- CPU baseline beside it: the unmodified reference, all host threads, bounded sample

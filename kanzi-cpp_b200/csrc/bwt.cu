@@ -414,6 +414,7 @@ rs_onesweep_text_kernel(SortArrays A, TextSort T, int pass, int nBlocks, int til
     u32* __restrict__ vout = (src ? A.val[0] : A.val[1]) + (i64)b * A.capN;
     const u8* __restrict__ text = blk_src(T.bt, T.st[b], b);
     const int sft = 7 - pass; // digit = text[index + sft]
+    const bool textAl = (((size_t)text) & 7) == 0;
     u32 val[RS_ITEMS];
     u32 dgt[RS_ITEMS];
     u16 rnk[RS_ITEMS];
@@ -435,8 +436,18 @@ rs_onesweep_text_kernel(SortArrays A, TextSort T, int pass, int nBlocks, int til
             } else {
                 const int idx = (KIND == 0) ? j : (int)(val[it] & TX_IDX_MASK);
                 const int a = idx + sft;
-                d = (a < cnt) ? (u32)__ldg(&text[a]) : 0u;
-                const u32 c = (a >= 1 && a - 1 < cnt) ? (u32)__ldg(&text[a - 1]) : 0u;
+                const int q = a - 1; // the next pass's digit sits right before this pass's
+                u32 c;
+                if (KIND == 2 && textAl && q >= 0 && (q & 7) != 7 && (q | 7) < cnt) {
+                    // both bytes from one aligned 8-byte word: one L1 wavefront per lane instead of two
+                    const u64 w8 = __ldg(reinterpret_cast<const u64*>(text + (q & ~7)));
+                    const u32 two = (u32)(w8 >> ((q & 7) * 8));
+                    c = two & 0xFFu;
+                    d = (two >> 8) & 0xFFu;
+                } else {
+                    d = (a < cnt) ? (u32)__ldg(&text[a]) : 0u;
+                    c = (q >= 0 && q < cnt) ? (u32)__ldg(&text[q]) : 0u;
+                }
                 val[it] = (u32)idx | (c << TX_IDX_BITS);
             }
         }

@@ -313,28 +313,58 @@ __device__ __forceinline__ u32 hrd_bits(const u8* __restrict__ p, u64 pos, int n
     return (u32)((w >> (40 - sh - n)) & ((n == 32) ? 0xFFFFFFFFull : ((1ull << n) - 1)));
 }
 
-__device__ __forceinline__ int hrd_expgolomb(const u8* __restrict__ p, u64& pos)
+// The same fetch from a window of the bit string staged in shared memory (32-bit words, bit 31 =
+// first bit; word i holds bits [base + 32 i, + 32)); n <= 32.
+#define HSCAN_WIN_WORDS 128
+struct WinSrc {
+    const u32* w;
+    u64 base;
+};
+__device__ __forceinline__ u32 hrd_bits(const WinSrc& s, u64 pos, int n)
 {
-    if (hrd_bits(p, pos, 1)) {
+    const u32 rel = (u32)(pos - s.base);
+    const u32 i = min(rel >> 5, 128u); // malformed headers may run past the 130-word window
+    const u64 v = ((u64)s.w[i] << 32) | (u64)s.w[i + 1];
+    return (u32)((v >> (64 - (int)(rel & 31) - n)) & ((n == 32) ? 0xFFFFFFFFull : ((1ull << n) - 1)));
+}
+
+// Signed exp-Golomb (ExpGolombDecoder.hpp:52-75): `1` = 0, else z >= 1 zeros, a one, (z & 7) + 1
+// value bits whose last one is the sign.  One 32-bit peek decodes every code the encoder emits
+// (z <= 4); longer zero runs (malformed input) take the bitwise walk.
+template <class S>
+__device__ __forceinline__ int hrd_expgolomb(const S& p, u64& pos)
+{
+    const u32 v = hrd_bits(p, pos, 32);
+    if (v & 0x80000000u) {
         pos += 1;
         return 0;
     }
-    pos += 1;
-    u32 lg = 1;
-    while (hrd_bits(p, pos, 1) == 0 && lg < 64) {
+    u32 lg;
+    int res;
+    const int z = __clz((int)v); // zeros before the first one (v != 0 -> z <= 31; v == 0 -> 32)
+    if (z <= 16) {
+        lg = (u32)z & 7;
+        res = (int)((v << (z + 1)) >> (31 - lg));
+        pos += (u64)(z + 1) + lg + 1;
+    } else {
         pos += 1;
-        lg++;
+        lg = 1;
+        while (hrd_bits(p, pos, 1) == 0 && lg < 64) {
+            pos += 1;
+            lg++;
+        }
+        pos += 1;
+        lg &= 7;
+        res = (int)hrd_bits(p, pos, (int)lg + 1);
+        pos += lg + 1;
     }
-    pos += 1;
-    lg &= 7;
-    int res = (int)hrd_bits(p, pos, (int)lg + 1);
-    pos += lg + 1;
     const int sgn = res & 1;
     res = (res >> 1) + (1 << lg) - 1;
     return (int)(int8_t)((res - sgn) ^ -sgn);
 }
 
-__device__ __forceinline__ u32 hrd_varint(const u8* __restrict__ p, u64& pos)
+template <class S>
+__device__ __forceinline__ u32 hrd_varint(const S& p, u64& pos)
 {
     u32 v = hrd_bits(p, pos, 8);
     pos += 8;
@@ -349,7 +379,8 @@ __device__ __forceinline__ u32 hrd_varint(const u8* __restrict__ p, u64& pos)
 
 // Parses one chunk header at pos: alphabet bitmap into pm[8], lengths into sizes (may be NULL).
 // Returns the alphabet size (0 = invalid).
-__device__ int huf_read_header(const u8* __restrict__ p, u64& pos, u32* pm, u8* sizes)
+template <class S>
+__device__ int huf_read_header(const S& p, u64& pos, u32* pm, u8* sizes)
 {
     int asz = 0;
     if (hrd_bits(p, pos, 1) == 0) {
@@ -385,44 +416,87 @@ __device__ int huf_read_header(const u8* __restrict__ p, u64& pos, u32* pm, u8* 
     return asz;
 }
 
-__global__ void huf_dec_scan_kernel(DecodeLaunch L)
+// Chunk start positions: one serial walk per block (a chunk's length is only known once its header
+// is parsed) -- one warp per block stages a 512-byte window of the bit string at the current
+// position in shared memory (coalesced 32-bit loads), lane 0 parses the header out of it.  A header
+// is at most 262 + 256 * 10 + 4 * 40 bits.
+__global__ void __launch_bounds__(32)
+huf_dec_scan_kernel(DecodeLaunch L)
 {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= L.nBlocks)
-        return;
+    __shared__ u32 s_win[HSCAN_WIN_WORDS + 2];
+    const int b = blockIdx.x;
+    const int lane = threadIdx.x;
     const int m = L.preLen[b];
     u64* cp = L.chunkPos + (i64)b * L.maxChunks;
     u64 pos = L.payStart[b];
     const u64 endBits = L.inBits[b];
     const u8* __restrict__ p = L.in + (i64)b * L.inStride;
+    const u32* __restrict__ pw = reinterpret_cast<const u32*>(p);
+    const bool aligned = (((size_t)p) & 3) == 0;
+    const u64 lastWord = (endBits + 31) >> 5;
     const int nChunks = (m + HUF_CHUNK - 1) / HUF_CHUNK;
-    u32 pm[8];
     for (int c = 0; c < nChunks; c++) {
-        cp[c] = pos;
         const int len = min(HUF_CHUNK, m - c * HUF_CHUNK);
         if (len < 32) {
+            if (lane == 0)
+                cp[c] = pos;
             pos += 8ull * (u64)len;
-        } else {
+            if (pos > endBits) {
+                if (lane == 0)
+                    atomicExch(L.errFlag, KERR_BAD_STREAM);
+                return;
+            }
+            continue;
+        }
+        const u64 w0 = pos >> 5;
+        __syncwarp();
+        for (int i = lane; i < HSCAN_WIN_WORDS + 2; i += 32) {
+            const u64 wi = w0 + (u64)i;
+            u32 v = 0;
+            if (wi < lastWord) {
+                if (aligned) {
+                    v = bswap32(__ldg(&pw[wi]));
+                } else {
+                    const u8* q = p + wi * 4;
+                    v = ((u32)q[0] << 24) | ((u32)q[1] << 16) | ((u32)q[2] << 8) | (u32)q[3];
+                }
+            }
+            s_win[i] = v;
+        }
+        __syncwarp();
+        int err = 0;
+        u64 next = pos;
+        if (lane == 0) {
+            cp[c] = pos;
             if (pos + 8 > endBits) {
-                atomicExch(L.errFlag, KERR_BAD_STREAM);
-                return;
-            }
-            const int asz = huf_read_header(p, pos, pm, NULL);
-            if (asz == 0) {
-                atomicExch(L.errFlag, KERR_BAD_STREAM);
-                return;
-            }
-            if (asz > 1) {
-                u64 tot = 0;
-                for (int j = 0; j < 4; j++)
-                    tot += hrd_varint(p, pos);
-                pos += tot + 8ull * (u64)(len - 4 * (len >> 2));
+                err = KERR_BAD_STREAM;
+            } else {
+                WinSrc src;
+                src.w = s_win;
+                src.base = w0 << 5;
+                u32 pm[8];
+                u64 q = pos;
+                const int asz = huf_read_header(src, q, pm, (u8*)NULL);
+                if (asz == 0) {
+                    err = KERR_BAD_STREAM;
+                } else if (asz > 1) {
+                    u64 tot = 0;
+                    for (int j = 0; j < 4; j++)
+                        tot += hrd_varint(src, q);
+                    q += tot + 8ull * (u64)(len - 4 * (len >> 2));
+                }
+                if (q > endBits)
+                    err = KERR_BAD_STREAM;
+                next = q;
             }
         }
-        if (pos > endBits) {
-            atomicExch(L.errFlag, KERR_BAD_STREAM);
+        err = __shfl_sync(FULL_MASK, err, 0);
+        if (err) {
+            if (lane == 0)
+                atomicExch(L.errFlag, err);
             return;
         }
+        pos = __shfl_sync(FULL_MASK, next, 0);
     }
 }
 
@@ -433,6 +507,7 @@ huf_decode_kernel(DecodeLaunch L)
 {
     __shared__ u8 s_tab[8][1 << HUF_MAX_LEN];
     __shared__ u8 s_len[8][256];
+    __shared__ u32 s_hwin[8][HSCAN_WIN_WORDS + 2]; // the 8 chunk headers, staged by the whole warp
     const int lane = threadIdx.x;
     const int groupsPerBlk = (L.maxChunks + 7) >> 3;
     const int b = blockIdx.x / groupsPerBlk;
@@ -450,6 +525,28 @@ huf_decode_kernel(DecodeLaunch L)
     const int len = valid ? min(HUF_CHUNK, m - c * HUF_CHUNK) : 0;
     u8* __restrict__ o = out + (i64)(valid ? c : 0) * HUF_CHUNK;
     u64 pos = valid ? cp[c] : 0;
+    {
+        const u32* __restrict__ pw = reinterpret_cast<const u32*>(p);
+        const bool aligned = (((size_t)p) & 3) == 0;
+        const u64 lastWord = (L.inBits[b] + 31) >> 5;
+        for (int jj = 0; jj < 8; jj++) {
+            const u64 w0 = __shfl_sync(FULL_MASK, pos, 4 * jj) >> 5;
+            for (int i = lane; i < HSCAN_WIN_WORDS + 2; i += 32) {
+                const u64 wi = w0 + (u64)i;
+                u32 v = 0;
+                if (c0 + jj < nChunks && wi < lastWord) {
+                    if (aligned) {
+                        v = bswap32(__ldg(&pw[wi]));
+                    } else {
+                        const u8* q = p + wi * 4;
+                        v = ((u32)q[0] << 24) | ((u32)q[1] << 16) | ((u32)q[2] << 8) | (u32)q[3];
+                    }
+                }
+                s_hwin[jj][i] = v;
+            }
+        }
+        __syncwarp();
+    }
     int asz = 0, single = -1;
     u32 nb[4] = { 0, 0, 0, 0 };
     if (valid && len < 32) {
@@ -460,7 +557,10 @@ huf_decode_kernel(DecodeLaunch L)
         u8* sizes = s_len[j];
         for (int i = 0; i < 256; i++)
             sizes[i] = 0;
-        asz = huf_read_header(p, pos, pm, sizes);
+        WinSrc hsrc;
+        hsrc.w = s_hwin[j];
+        hsrc.base = (pos >> 5) << 5;
+        asz = huf_read_header(hsrc, pos, pm, sizes);
         if (asz == 1) {
             for (int s = 0; s < 256; s++)
                 if (sizes[s])
@@ -500,7 +600,7 @@ huf_decode_kernel(DecodeLaunch L)
                 // by pointing at a symbol with length 0 if one exists
             }
             for (int q = 0; q < 4; q++)
-                nb[q] = hrd_varint(p, pos);
+                nb[q] = hrd_varint(hsrc, pos);
         }
         if (asz == 0)
             atomicExch(L.errFlag, KERR_BAD_STREAM);
@@ -567,7 +667,7 @@ void launch_huffman_encode_chunks(const EncodeLaunch& L, cudaStream_t s, u64* la
 
 void launch_huffman_decode(const DecodeLaunch& L, cudaStream_t s, u64* launches)
 {
-    KLAUNCH(huf_dec_scan_kernel, (L.nBlocks + 31) / 32, 32, s, L);
+    KLAUNCH(huf_dec_scan_kernel, L.nBlocks, 32, s, L);
     const int groups = (L.maxChunks + 7) / 8;
     if (L.evK0)
         cudaEventRecord(L.evK0, s);

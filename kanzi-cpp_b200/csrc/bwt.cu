@@ -742,6 +742,35 @@ __device__ __forceinline__ void grp_flags(const u64* __restrict__ k, int j, int 
     resolved = head && nexthead;
 }
 
+// The grouping kernels give every thread RS_ITEMS consecutive sorted positions (the scans run in
+// that order); the keys are brought in with coalesced loads and re-read from shared memory in the
+// blocked order.  Slot i holds k[tbase - 1 + i] (one halo key on either side), padded one slot in
+// eight so the blocked 64-bit reads are bank-conflict free.
+#define GRP_PAD(i) ((i) + ((i) >> 3))
+#define GRP_SK_SLOTS (GRP_PAD(RS_TILE + 2) + 1)
+__device__ __forceinline__ void grp_stage_keys(const u64* __restrict__ k, int tbase, int cnt, u64* sk)
+{
+    for (int i = threadIdx.x; i < RS_TILE + 2; i += RS_THREADS) {
+        const int j = tbase - 1 + i;
+        sk[GRP_PAD(i)] = (j >= 0 && j < cnt) ? __ldg(&k[j]) : 0ull;
+    }
+    __syncthreads();
+}
+// flags of position j from its key and its neighbours' (kp = k[j-1], kn = k[j+1])
+__device__ __forceinline__ void grp_flags_k(u64 kp, u64 kj, u64 kn, int j, int cnt, int initial, bool& head, bool& ghead,
+                                            bool& resolved)
+{
+    if (j == 0) {
+        head = true;
+        ghead = true;
+    } else {
+        head = kj != kp;
+        ghead = !initial && ((kj >> 32) != (kp >> 32));
+    }
+    const bool nexthead = (j + 1 >= cnt) || (kn != kj);
+    resolved = head && nexthead;
+}
+
 __global__ void __launch_bounds__(RS_THREADS)
 bwt_grp_partials_kernel(GrpCtx G)
 {
@@ -751,20 +780,30 @@ bwt_grp_partials_kernel(GrpCtx G)
     const int tbase = blockIdx.x * RS_TILE;
     if (tbase >= cnt)
         return;
-    const u64* __restrict__ k = G.key[G.which[8 * G.maxBlocks + b]] + (i64)b * G.capN;
+    const u64* __restrict__ k = (G.which[8 * G.maxBlocks + b] ? G.key[1] : G.key[0]) + (i64)b * G.capN;
+    __shared__ u64 s_k[GRP_SK_SLOTS];
+    grp_stage_keys(k, tbase, cnt, s_k);
     u32 mh = 0, mg = 0, su = 0;
     const int j0 = tbase + threadIdx.x * RS_ITEMS;
-    for (int x = 0; x < RS_ITEMS; x++) {
-        const int j = j0 + x;
-        if (j >= cnt)
-            break;
-        bool head, ghead, res;
-        grp_flags(k, j, cnt, G.initial, head, ghead, res);
-        if (head)
-            mh = (u32)j + 1;
-        if (ghead)
-            mg = (u32)j + 1;
-        su += res ? 0u : 1u;
+    {
+        const int i0 = threadIdx.x * RS_ITEMS + 1; // slot of j0
+        u64 kp = s_k[GRP_PAD(i0 - 1)], kj = s_k[GRP_PAD(i0)];
+#pragma unroll
+        for (int x = 0; x < RS_ITEMS; x++) {
+            const int j = j0 + x;
+            const u64 kn = s_k[GRP_PAD(i0 + x + 1)];
+            if (j < cnt) {
+                bool head, ghead, res;
+                grp_flags_k(kp, kj, kn, j, cnt, G.initial, head, ghead, res);
+                if (head)
+                    mh = (u32)j + 1;
+                if (ghead)
+                    mg = (u32)j + 1;
+                su += res ? 0u : 1u;
+            }
+            kp = kj;
+            kj = kn;
+        }
     }
     // block reduce: max, max, sum
 #pragma unroll
@@ -794,32 +833,60 @@ bwt_grp_partials_kernel(GrpCtx G)
     }
 }
 
-// One thread per block: exclusive carries over tiles; survivors; next source buffer.
-__global__ void bwt_grp_scan_kernel(GrpCtx G, int nBlocks)
+// One warp per block: exclusive carries over tiles (max, max, sum); survivors; next source buffer.
+__global__ void __launch_bounds__(32)
+bwt_grp_scan_kernel(GrpCtx G, int nBlocks)
 {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.x;
+    const int lane = threadIdx.x;
     if (b >= nBlocks)
         return;
     const int cnt = G.cnt[b];
     const int after = G.which[8 * G.maxBlocks + b];
-    G.whichNext[b] = after ^ 1; // survivors are compacted into the other buffer
+    if (lane == 0)
+        G.whichNext[b] = after ^ 1; // survivors are compacted into the other buffer
     if (cnt <= 0) {
-        G.cntNext[b] = 0;
+        if (lane == 0)
+            G.cntNext[b] = 0;
         return;
     }
     const int tiles = (cnt + RS_TILE - 1) / RS_TILE;
-    u32 ch = 0, cg = 0, cu = 0;
+    u32 ch = 0, cg = 0, cu = 0; // carries of everything before the current group of 32 tiles
     u32* p = G.part + (i64)b * G.maxTiles * 4;
-    for (int t = 0; t < tiles; t++) {
-        const u32 a = p[4 * t], bb = p[4 * t + 1], c = p[4 * t + 2];
-        p[4 * t] = ch;
-        p[4 * t + 1] = cg;
-        p[4 * t + 2] = cu;
-        ch = max(ch, a);
-        cg = max(cg, bb);
-        cu += c;
+    for (int t0 = 0; t0 < tiles; t0 += 32) {
+        const int t = t0 + lane;
+        u32 a = 0, bb = 0, c = 0;
+        if (t < tiles) {
+            a = p[4 * t];
+            bb = p[4 * t + 1];
+            c = p[4 * t + 2];
+        }
+        u32 ia = a, ib = bb, ic = c; // inclusive scans over the lanes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 ta = __shfl_up_sync(FULL_MASK, ia, o), tb = __shfl_up_sync(FULL_MASK, ib, o);
+            const u32 tc = __shfl_up_sync(FULL_MASK, ic, o);
+            if (lane >= o) {
+                ia = max(ia, ta);
+                ib = max(ib, tb);
+                ic += tc;
+            }
+        }
+        u32 ea = __shfl_up_sync(FULL_MASK, ia, 1), eb = __shfl_up_sync(FULL_MASK, ib, 1);
+        u32 ec = __shfl_up_sync(FULL_MASK, ic, 1);
+        if (lane == 0)
+            ea = eb = ec = 0;
+        if (t < tiles) {
+            p[4 * t] = max(ch, ea);
+            p[4 * t + 1] = max(cg, eb);
+            p[4 * t + 2] = cu + ec;
+        }
+        ch = max(ch, __shfl_sync(FULL_MASK, ia, 31));
+        cg = max(cg, __shfl_sync(FULL_MASK, ib, 31));
+        cu += __shfl_sync(FULL_MASK, ic, 31);
     }
-    G.cntNext[b] = (int)cu;
+    if (lane == 0)
+        G.cntNext[b] = (int)cu;
 }
 
 __global__ void __launch_bounds__(RS_THREADS)
@@ -832,27 +899,41 @@ bwt_grp_apply_kernel(GrpCtx G)
     if (tbase >= cnt)
         return;
     const int src = G.which[8 * G.maxBlocks + b];
-    const u64* __restrict__ k = G.key[src] + (i64)b * G.capN;
-    const u32* __restrict__ v = G.val[src] + (i64)b * G.capN;
-    u32* __restrict__ vout = G.valOut[src ^ 1] + (i64)b * G.capN;
+    const u64* __restrict__ k = (src ? G.key[1] : G.key[0]) + (i64)b * G.capN;
+    const u32* __restrict__ v = (src ? G.val[1] : G.val[0]) + (i64)b * G.capN;
+    u32* __restrict__ vout = (src ? G.valOut[0] : G.valOut[1]) + (i64)b * G.capN;
     u32* __restrict__ gout = G.grpOut + (i64)b * G.capN;
     u32* __restrict__ isa = G.isa + (i64)b * G.capN;
     const u32* carry = G.part + ((i64)b * G.maxTiles + blockIdx.x) * 4;
     const int j0 = tbase + threadIdx.x * RS_ITEMS;
+    __shared__ u64 s_k[GRP_SK_SLOTS];
+    __shared__ u32 s_v[GRP_PAD(RS_TILE) + 1];
+    for (int i = threadIdx.x; i < RS_TILE; i += RS_THREADS)
+        s_v[GRP_PAD(i)] = (tbase + i < cnt) ? __ldg(&v[tbase + i]) : 0u;
+    grp_stage_keys(k, tbase, cnt, s_k);
     bool head[RS_ITEMS], ghead[RS_ITEMS], res[RS_ITEMS];
+    u32 oldHi[RS_ITEMS];
     u32 mh = 0, mg = 0, su = 0;
+    {
+        const int i0 = threadIdx.x * RS_ITEMS + 1; // slot of j0
+        u64 kp = s_k[GRP_PAD(i0 - 1)], kj = s_k[GRP_PAD(i0)];
 #pragma unroll
-    for (int x = 0; x < RS_ITEMS; x++) {
-        const int j = j0 + x;
-        head[x] = ghead[x] = false;
-        res[x] = true;
-        if (j < cnt) {
-            grp_flags(k, j, cnt, G.initial, head[x], ghead[x], res[x]);
-            if (head[x])
-                mh = (u32)j + 1;
-            if (ghead[x])
-                mg = (u32)j + 1;
-            su += res[x] ? 0u : 1u;
+        for (int x = 0; x < RS_ITEMS; x++) {
+            const int j = j0 + x;
+            const u64 kn = s_k[GRP_PAD(i0 + x + 1)];
+            head[x] = ghead[x] = false;
+            res[x] = true;
+            oldHi[x] = (u32)(kj >> 32);
+            if (j < cnt) {
+                grp_flags_k(kp, kj, kn, j, cnt, G.initial, head[x], ghead[x], res[x]);
+                if (head[x])
+                    mh = (u32)j + 1;
+                if (ghead[x])
+                    mg = (u32)j + 1;
+                su += res[x] ? 0u : 1u;
+            }
+            kp = kj;
+            kj = kn;
         }
     }
     // exclusive scans across threads: max (H), max (G), sum (U)
@@ -890,9 +971,9 @@ bwt_grp_apply_kernel(GrpCtx G)
             H = (u32)j + 1;
         if (ghead[x])
             Gm = (u32)j + 1;
-        const u32 old = G.initial ? 0u : (u32)(k[j] >> 32);
+        const u32 old = G.initial ? 0u : oldHi[x];
         const u32 rank = old + (H - Gm);
-        const u32 sfx = v[j];
+        const u32 sfx = s_v[GRP_PAD(threadIdx.x * RS_ITEMS + x)];
         isa[sfx] = rank;
         if (!res[x]) {
             vout[U] = sfx;
@@ -1114,24 +1195,37 @@ bwt_tile_sort_kernel(XCtx X)
     }
 }
 
-__global__ void bwt_xscan_kernel(XCtx X, int nBlocks)
+// One warp per block: exclusive offsets of the tiles' extracted prefix / suffix runs.
+__global__ void __launch_bounds__(32)
+bwt_xscan_kernel(XCtx X, int nBlocks)
 {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.x;
+    const int lane = threadIdx.x;
     if (b >= nBlocks)
         return;
-    X.which8[b] = X.which0[b];
+    if (lane == 0)
+        X.which8[b] = X.which0[b];
     const int cnt = X.cnt[b];
     const int tiles = (cnt + RS_TILE - 1) / RS_TILE;
     u32 run = 0;
     u32* xc = X.xcnt + (i64)b * X.maxTiles * 2;
-    for (int t = 0; t < tiles; t++) {
-        const u32 a = xc[2 * t], c = xc[2 * t + 1];
-        xc[2 * t] = run; // offset of the tile's prefix elements
-        run += a;
-        xc[2 * t + 1] = run | ((c != 0) ? 0x80000000u : 0u); // offset of its suffix elements (+flag)
-        run += c;
+    for (int t0 = 0; t0 < tiles; t0 += 32) {
+        const int t = t0 + lane;
+        u32 a = 0, c = 0;
+        if (t < tiles) {
+            a = xc[2 * t];
+            c = xc[2 * t + 1];
+        }
+        const u32 inc = warp_incl_sum(a + c, lane);
+        const u32 ex = run + inc - (a + c);
+        if (t < tiles) {
+            xc[2 * t] = ex; // offset of the tile's prefix elements
+            xc[2 * t + 1] = (ex + a) | ((c != 0) ? 0x80000000u : 0u); // offset of its suffix elements (+flag)
+        }
+        run += __shfl_sync(FULL_MASK, inc, 31);
     }
-    X.cntX[b] = (int)run;
+    if (lane == 0)
+        X.cntX[b] = (int)run;
 }
 
 __global__ void __launch_bounds__(RS_THREADS)
@@ -1283,7 +1377,7 @@ void launch_bwt_forward(const StageLaunch& L, Workspace& ws, cudaStream_t s, u64
         } else {
             // groups inside one tile: shared-memory sort; groups crossing tiles: side radix sort
             KLAUNCH(bwt_tile_sort_kernel, dim3(tiles, nB), RS_THREADS, s, X);
-            KLAUNCH(bwt_xscan_kernel, (nB + 63) / 64, 64, s, X, nB);
+            KLAUNCH(bwt_xscan_kernel, nB, 32, s, X, nB);
             *launches += 2;
             cudaMemcpyAsync(ws.h_cnt, ws.cntX, sizeof(int) * nB, cudaMemcpyDeviceToHost, s);
             cudaStreamSynchronize(s);
@@ -1299,7 +1393,7 @@ void launch_bwt_forward(const StageLaunch& L, Workspace& ws, cudaStream_t s, u64
             }
         }
         KLAUNCH(bwt_grp_partials_kernel, dim3(tiles, nB), RS_THREADS, s, G);
-        KLAUNCH(bwt_grp_scan_kernel, (nB + 63) / 64, 64, s, G, nB);
+        KLAUNCH(bwt_grp_scan_kernel, nB, 32, s, G, nB);
         KLAUNCH(bwt_grp_apply_kernel, dim3(tiles, nB), RS_THREADS, s, G);
         *launches += 3;
         // survivors per block -> host (sizes the next round's grids, detects the end)

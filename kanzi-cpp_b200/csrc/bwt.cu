@@ -320,7 +320,7 @@ static void radix_sort(const SortArrays& A, int nBlocks, int maxCnt, u32 passMas
 // 4 + 4 bytes per element instead of 12 + 12.
 #define TX_IDX_BITS 22
 #define TX_IDX_MASK ((1u << TX_IDX_BITS) - 1u)
-#define TX_SMEM (RS_TILE * 4 + (RS_THREADS / 32) * 256 * 4 + 2 * 256 * 4 + 64 + RS_TILE)
+#define TX_SMEM(items) (RS_THREADS * (items) * 4 + (RS_THREADS / 32) * 256 * 4 + 2 * 256 * 4 + 64 + RS_THREADS * (items))
 
 struct TextSort {
     BufTable bt;
@@ -383,14 +383,15 @@ rs_text_plan_kernel(SortArrays A, TextSort T, int nBlocks)
 
 // KIND 0: pass 0 (implicit index, text read in order); 1: odd pass (digit carried by the
 // element); 2: even pass >= 2 (digit and the next pass's digit gathered from the text).
-template <int KIND>
-__global__ void __launch_bounds__(RS_THREADS, 4)
+template <int KIND, int ITEMS>
+__global__ void __launch_bounds__(RS_THREADS, (ITEMS <= 8) ? 4 : 3)
 rs_onesweep_text_kernel(SortArrays A, TextSort T, int pass, int nBlocks, int tilesMax)
 {
+    constexpr int TILE = RS_THREADS * ITEMS;
     KNZ_DYN_SMEM(os_smem);
     u32* s_val = reinterpret_cast<u32*>(os_smem);
-    u32(*s_cnt)[256] = reinterpret_cast<u32(*)[256]>(os_smem + RS_TILE * 4);
-    u32* s_delta = reinterpret_cast<u32*>(os_smem + RS_TILE * 4 + (RS_THREADS / 32) * 1024);
+    u32(*s_cnt)[256] = reinterpret_cast<u32(*)[256]>(os_smem + TILE * 4);
+    u32* s_delta = reinterpret_cast<u32*>(os_smem + TILE * 4 + (RS_THREADS / 32) * 1024);
     u32* s_toff = s_delta + 256;
     u32* s_w = s_toff + 256; // 8 words for the block scan + 1 for the ticket
     u8* s_dig = reinterpret_cast<u8*>(s_w + 16); // digit of every staged slot
@@ -398,7 +399,7 @@ rs_onesweep_text_kernel(SortArrays A, TextSort T, int pass, int nBlocks, int til
     const int cnt = A.cnt[b];
     if (cnt <= 0)
         return;
-    const int tiles = (cnt + RS_TILE - 1) / RS_TILE;
+    const int tiles = (cnt + TILE - 1) / TILE;
     if (threadIdx.x == 0)
         s_w[8] = (u32)atomicAdd(&A.ticket[pass * A.maxBlocks + b], 1);
     for (int i = threadIdx.x; i < (RS_THREADS / 32) * 256; i += RS_THREADS)
@@ -407,7 +408,7 @@ rs_onesweep_text_kernel(SortArrays A, TextSort T, int pass, int nBlocks, int til
     const int tile = (int)s_w[8];
     if (tile >= tiles)
         return;
-    const int tbase = tile * RS_TILE;
+    const int tbase = tile * TILE;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int src = A.which[pass * A.maxBlocks + b];
     const u32* __restrict__ vin = (src ? A.val[1] : A.val[0]) + (i64)b * A.capN;
@@ -415,19 +416,19 @@ rs_onesweep_text_kernel(SortArrays A, TextSort T, int pass, int nBlocks, int til
     const u8* __restrict__ text = blk_src(T.bt, T.st[b], b);
     const int sft = 7 - pass; // digit = text[index + sft]
     const bool textAl = (((size_t)text) & 7) == 0;
-    u32 val[RS_ITEMS];
-    u32 dgt[RS_ITEMS];
-    u16 rnk[RS_ITEMS];
+    u32 val[ITEMS];
+    u32 dgt[ITEMS]; // digit (9 bits) | rank inside the warp's elements << 9
+
     if (KIND != 0) {
 #pragma unroll
-        for (int it = 0; it < RS_ITEMS; it++) {
-            const int j = tbase + w * (32 * RS_ITEMS) + it * 32 + lane;
+        for (int it = 0; it < ITEMS; it++) {
+            const int j = tbase + w * (32 * ITEMS) + it * 32 + lane;
             val[it] = (j < cnt) ? __ldg(&vin[j]) : 0;
         }
     }
 #pragma unroll
-    for (int it = 0; it < RS_ITEMS; it++) {
-        const int j = tbase + w * (32 * RS_ITEMS) + it * 32 + lane;
+    for (int it = 0; it < ITEMS; it++) {
+        const int j = tbase + w * (32 * ITEMS) + it * 32 + lane;
         u32 d = 256u; // padding class
         if (j < cnt) {
             if (KIND == 1) {
@@ -455,7 +456,7 @@ rs_onesweep_text_kernel(SortArrays A, TextSort T, int pass, int nBlocks, int til
     }
     // rank inside the warp's 256 elements (load order = stable order)
 #pragma unroll
-    for (int it = 0; it < RS_ITEMS; it++) {
+    for (int it = 0; it < ITEMS; it++) {
         const u32 d = dgt[it];
         const u32 peers = __match_any_sync(FULL_MASK, d);
         const u32 prior = (d < 256) ? s_cnt[w][d] : 0;
@@ -463,7 +464,7 @@ rs_onesweep_text_kernel(SortArrays A, TextSort T, int pass, int nBlocks, int til
         if (d < 256 && (peers & lanemask_lt()) == 0)
             s_cnt[w][d] = prior + __popc(peers);
         __syncwarp();
-        rnk[it] = (u16)(prior + __popc(peers & lanemask_lt()));
+        dgt[it] = d | ((prior + (u32)__popc(peers & lanemask_lt())) << 9);
     }
     __syncthreads();
     // thread = digit: warp prefixes, tile count, look-back, offsets
@@ -505,18 +506,18 @@ rs_onesweep_text_kernel(SortArrays A, TextSort T, int pass, int nBlocks, int til
     __syncthreads();
     // stage in sorted order (the element no longer holds this pass's digit: stage it alongside)
 #pragma unroll
-    for (int it = 0; it < RS_ITEMS; it++) {
-        const u32 dg = dgt[it];
+    for (int it = 0; it < ITEMS; it++) {
+        const u32 dg = dgt[it] & 0x1FFu;
         if (dg < 256) {
-            const u32 q = s_toff[dg] + s_cnt[w][dg] + rnk[it];
+            const u32 q = s_toff[dg] + s_cnt[w][dg] + (dgt[it] >> 9);
             s_val[q] = val[it];
             s_dig[q] = (u8)dg;
         }
     }
     __syncthreads();
-    const int valid = min(RS_TILE, cnt - tbase);
+    const int valid = min(TILE, cnt - tbase);
 #pragma unroll
-    for (int it = 0; it < RS_ITEMS; it++) {
+    for (int it = 0; it < ITEMS; it++) {
         const int q = it * RS_THREADS + threadIdx.x;
         if (q < valid)
             vout[s_delta[s_dig[q]] + (u32)q] = s_val[q];
@@ -611,16 +612,21 @@ __global__ void bwt_regen_check_kernel(SortArrays A, TextSort T)
 static void radix_sort_text(const SortArrays& A, const TextSort& T, int nBlocks, int maxCnt, cudaStream_t s,
                             u64* launches)
 {
-    const int tiles = (maxCnt + RS_TILE - 1) / RS_TILE;
+    static int items = 0;
+    if (!items) {
+        const char* e = getenv("KNZ_TX_ITEMS"); // elements per thread of the index-only passes: 8 or 16
+        items = (e && atoi(e) == 8) ? 8 : 16;
+        cudaFuncSetAttribute(rs_onesweep_text_kernel<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, TX_SMEM(8));
+        cudaFuncSetAttribute(rs_onesweep_text_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, TX_SMEM(8));
+        cudaFuncSetAttribute(rs_onesweep_text_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, TX_SMEM(8));
+        cudaFuncSetAttribute(rs_onesweep_text_kernel<0, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TX_SMEM(16));
+        cudaFuncSetAttribute(rs_onesweep_text_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TX_SMEM(16));
+        cudaFuncSetAttribute(rs_onesweep_text_kernel<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TX_SMEM(16));
+    }
+    const int tile = RS_THREADS * items;
+    const int tiles = (maxCnt + tile - 1) / tile;
     if (tiles <= 0)
         return;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(rs_onesweep_text_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TX_SMEM);
-        cudaFuncSetAttribute(rs_onesweep_text_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TX_SMEM);
-        cudaFuncSetAttribute(rs_onesweep_text_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TX_SMEM);
-        attr = true;
-    }
     cudaMemsetAsync(A.totals, 0, sizeof(u32) * 2048 * (size_t)nBlocks, s);
     cudaMemsetAsync(A.ticket, 0, sizeof(int) * 8 * (size_t)A.maxBlocks, s);
     KLAUNCH(rs_text_hist_kernel, dim3((maxCnt + RS_TILE * 4 - 1) / (RS_TILE * 4), nBlocks), RS_THREADS, s, A, T);
@@ -629,17 +635,24 @@ static void radix_sort_text(const SortArrays& A, const TextSort& T, int nBlocks,
     for (int p = 0; p < 8; p++) {
         cudaMemset2DAsync(A.hist, sizeof(u32) * 256 * (size_t)A.maxTiles, 0, sizeof(u32) * 256 * (size_t)tiles,
                           (size_t)nBlocks, s);
-        static int dbgAllGather = -1;
-        if (dbgAllGather < 0) {
-            const char* e = getenv("KNZ_TX_ALLGATHER");
-            dbgAllGather = (e && atoi(e)) ? 1 : 0;
+        const int kind = (p == 0) ? 0 : (p & 1) ? 1 : 2;
+#define TX_LAUNCH(K, I) KLAUNCH_DYN((rs_onesweep_text_kernel<K, I>), tiles * nBlocks, RS_THREADS, TX_SMEM(I), s, A, T, p, nBlocks, tiles)
+        if (items == 16) {
+            if (kind == 0)
+                TX_LAUNCH(0, 16);
+            else if (kind == 1)
+                TX_LAUNCH(1, 16);
+            else
+                TX_LAUNCH(2, 16);
+        } else {
+            if (kind == 0)
+                TX_LAUNCH(0, 8);
+            else if (kind == 1)
+                TX_LAUNCH(1, 8);
+            else
+                TX_LAUNCH(2, 8);
         }
-        if (p == 0)
-            KLAUNCH_DYN(rs_onesweep_text_kernel<0>, tiles * nBlocks, RS_THREADS, TX_SMEM, s, A, T, p, nBlocks, tiles);
-        else if ((p & 1) && !dbgAllGather)
-            KLAUNCH_DYN(rs_onesweep_text_kernel<1>, tiles * nBlocks, RS_THREADS, TX_SMEM, s, A, T, p, nBlocks, tiles);
-        else
-            KLAUNCH_DYN(rs_onesweep_text_kernel<2>, tiles * nBlocks, RS_THREADS, TX_SMEM, s, A, T, p, nBlocks, tiles);
+#undef TX_LAUNCH
         *launches += 1;
     }
     const int gblocks = min((maxCnt + 255) / 256, 2048);

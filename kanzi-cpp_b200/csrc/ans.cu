@@ -964,28 +964,55 @@ ans0_decode_kernel(DecodeLaunch L)
     const int len = valid ? min(ANS_CHUNK, m - c * ANS_CHUNK) : 0;
     u8* __restrict__ o = out + (i64)(valid ? c : 0) * ANS_CHUNK;
 
-    // ---- header parse + tables (one lane per chunk)
+    // ---- header parse + tables (one lane per chunk, out of a shared-memory window of the bit string
+    // that the whole warp stages first: the parse is a chain of ~300 dependent small reads)
     int asz = 0, lr = ANS0_LR, single = 0;
     u64 pos = 0;
+    u64 hbase = 0; // bit position of s_hwin[j][0]
+    {
+        const u32* __restrict__ pwh = reinterpret_cast<const u32*>(p);
+        const bool alh = (((size_t)p) & 3) == 0;
+        const u64 lastW = (L.inBits[b] + 31) >> 5;
+        const u64 mypos = (valid && k == 0) ? cp[c] : 0;
+        hbase = (mypos >> 5) << 5;
+        for (int jj = 0; jj < 8; jj++) {
+            const u64 w0 = __shfl_sync(FULL_MASK, mypos, 4 * jj) >> 5;
+            for (int i = lane; i < SCAN_WIN_WORDS + 2; i += 32) {
+                const u64 wi = w0 + (u64)i;
+                u32 v = 0;
+                if (c0 + jj < nChunks && wi < lastW) {
+                    if (alh) {
+                        v = bswap32(__ldg(&pwh[wi]));
+                    } else {
+                        const u8* q = p + wi * 4;
+                        v = ((u32)q[0] << 24) | ((u32)q[1] << 16) | ((u32)q[2] << 8) | (u32)q[3];
+                    }
+                }
+                reinterpret_cast<u32*>(s_f2s[jj])[i] = v; // the window lives in the (not yet built) slot table
+            }
+        }
+        __syncwarp();
+    }
+#define HRD(POS, N) rd_win(reinterpret_cast<const u32*>(s_f2s[j]), (u32)((POS) - hbase), (N))
     u32 psz = 0;
     u32 st0 = 0, st1 = 0, st2 = 0, st3 = 0;
     if (valid && k == 0) {
         pos = cp[c];
-        lr = 8 + (int)rd_bits(p, pos, 3);
+        lr = 8 + (int)HRD(pos, 3);
         pos += 3;
         u32 pm[8];
-        if (rd_bits(p, pos, 1) == 0) {
+        if (HRD(pos, 1) == 0) {
             pos += 2; // "00": the scan pass rejected "01"
             for (int i = 0; i < 8; i++)
                 pm[i] = 0xFFFFFFFFu;
             asz = 256;
         } else {
-            const int last = (int)rd_bits(p, pos + 1, 5);
+            const int last = (int)HRD(pos + 1, 5);
             pos += 6;
             for (int i = 0; i < 8; i++)
                 pm[i] = 0;
             for (int i = 0; i <= last; i++) {
-                const u32 mk = rd_bits(p, pos, 8);
+                const u32 mk = HRD(pos, 8);
                 pos += 8;
                 pm[i >> 2] |= mk << (8 * (i & 3)); // bit (8i+j) = symbol 8i+j
                 asz += __popc(mk);
@@ -1008,14 +1035,14 @@ ans0_decode_kernel(DecodeLaunch L)
         bool bad = false;
         while (left > 0) {
             const int cnt = min(left, chk);
-            const int logMax = (int)rd_bits(p, pos, llr);
+            const int logMax = (int)HRD(pos, llr);
             pos += llr;
             int got = 0;
             while (got < cnt) {
                 if ((pm[sym >> 5] >> (sym & 31)) & 1) {
                     u32 fr = 1;
                     if (logMax != 0) {
-                        fr = rd_bits(p, pos, logMax) + 1;
+                        fr = HRD(pos, logMax) + 1;
                         pos += logMax;
                     }
                     if (fr >= scale)
@@ -1036,22 +1063,23 @@ ans0_decode_kernel(DecodeLaunch L)
             if (asz == 1) {
                 single = 1 + firstSym;
             } else {
-                u32 v = rd_bits(p, pos, 8);
+                u32 v = HRD(pos, 8);
                 pos += 8;
                 psz = v & 0x7F;
                 for (int shift = 7; v >= 128 && shift <= 28; shift += 7) {
-                    v = rd_bits(p, pos, 8);
+                    v = HRD(pos, 8);
                     pos += 8;
                     psz |= (v & 0x7F) << shift;
                 }
-                st0 = rd_bits(p, pos, 32);
-                st1 = rd_bits(p, pos + 32, 32);
-                st2 = rd_bits(p, pos + 64, 32);
-                st3 = rd_bits(p, pos + 96, 32);
+                st0 = HRD(pos, 32);
+                st1 = HRD(pos + 32, 32);
+                st2 = HRD(pos + 64, 32);
+                st3 = HRD(pos + 96, 32);
                 pos += 128;
             }
         }
     }
+#undef HRD
     __syncwarp();
     const int qlead = lane & ~3;
     asz = __shfl_sync(FULL_MASK, asz, qlead);

@@ -185,3 +185,21 @@ def test_gpu_roundtrip_fullsize_properties(gpu):
     hdr_small, hdr_big = 24, 24
     body = small.size - hdr_small - 2  # drop the end marker + padding bytes
     assert np.array_equal(comp[hdr_big: hdr_big + body], small[hdr_small: hdr_small + body])
+
+
+@pytest.mark.parametrize("groups", [2, 4])
+def test_gpu_decode_groups(gpu, oracle, groups):
+    """knz_set_decode_groups: block groups decoded concurrently on separate streams over disjoint
+    workspace slices must give the same bytes as the serial schedule."""
+    bs = 1 << 18
+    data = synth.synth_compressible(37 * bs + 4321, 41)
+    comp = gpu.compress(data, "BWT+RANK+ZRLT", "ANS0", bs)
+    try:
+        gpu.set_decode_groups(groups)
+        for _ in range(2):
+            back = gpu.decompress(comp, data.size)
+            assert back.size == data.size and np.array_equal(back, data)
+        comp_h = gpu.compress(data, "BWT+MTFT+ZRLT", "HUFFMAN", bs)
+        assert np.array_equal(gpu.decompress(comp_h, data.size), data)
+    finally:
+        gpu.set_decode_groups(1)

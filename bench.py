@@ -385,7 +385,15 @@ def run_ours(args, rank, world, local_rank):
     # DRAM traffic per launch from the committed `ncu --set full` captures (profiles/r01_ncu_*.md),
     # scaled to this rank's blocks: dram__bytes_read.sum + dram__bytes_write.sum
     NCU_TRAFFIC_PER_BLOCK = {
-        "rank_inverse": (1.088619e9 + 1.040149e9) / 256,      # r01_ncu_rank_inverse_256blocks.md
+        # profiles/r01_ncu_traffic_64blocks_v6.md (stage sums of one encode+decode of 64 blocks) / 64
+        "bwt_forward": 64.38e9 / 64,
+        "rank_forward": 1.23e9 / 64,
+        "zrlt_forward": 0.70e9 / 64,
+        "ans0_encode_kernel": 0.46e9 / 64,
+        "ans0_decode_kernel": 0.26e9 / 64,
+        "zrlt_inverse": 1.07e9 / 64,
+        "bwt_inverse": 24.17e9 / 64,
+        "rank_inverse": (1.088619e9 + 1.040149e9) / 256,      # r01_ncu_rank_inverse_256blocks.md (--set full)
         "ans0_encode_kernel_config4": (491.811584e6 + 145.973248e6) / 64,  # r01_ncu_ans0_encode_v5_64blocks_config4.md
     }
     for k, per_block in NCU_TRAFFIC_PER_BLOCK.items():

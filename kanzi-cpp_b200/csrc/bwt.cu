@@ -902,7 +902,7 @@ bwt_grp_scan_kernel(GrpCtx G, int nBlocks)
         G.cntNext[b] = (int)cu;
 }
 
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, 4)
 bwt_grp_apply_kernel(GrpCtx G)
 {
     __shared__ u32 s_w[8], s_mh[8], s_mg[8];

@@ -951,6 +951,8 @@ ans0_decode_kernel(DecodeLaunch L)
     const int nChunks = (L.eType == E_RAW || m <= 32) ? 1 : ((m + ANS_CHUNK - 1) >> 14);
     if (c0 >= nChunks)
         return;
+    if (*L.errFlag != 0)
+        return; // the header walk rejected a block: its chunk positions are not trustworthy
     if (L.eType == E_RAW || m <= 32) {
         const u64 pos = cp[0];
         for (int i = lane; i < m; i += 32)

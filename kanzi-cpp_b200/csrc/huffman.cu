@@ -519,6 +519,8 @@ huf_decode_kernel(DecodeLaunch L)
     const int nChunks = (m + HUF_CHUNK - 1) / HUF_CHUNK;
     if (c0 >= nChunks)
         return;
+    if (*L.errFlag != 0)
+        return; // the header walk rejected a block: its chunk positions are not trustworthy
     const int j = lane >> 2, k = lane & 3;
     const int c = c0 + j;
     const bool valid = c < nChunks;

@@ -112,3 +112,32 @@ def test_sim_decode_groups(oracle):
         ctx.set_decode_groups(g)
         assert np.array_equal(ctx.decompress(comp, data.size), data), g
     ctx.close()
+
+
+def test_sim_corrupt_streams():
+    """Bit flips in a valid stream: the decoders must come back with an error or with (wrong) bytes,
+    never hang or fault, and the context must stay usable (the block checksum option is off, as in
+    BASELINE's configs, so silent corruption of literal bytes is expected)."""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "sim"), "-j8"], stdout=subprocess.DEVNULL)
+    from kanzi_b200 import Context, KanziGpuError
+    bs = 1 << 16
+    ctx = Context(0, bs, 8, lib_path=SIM)
+    data = synth.synth_compressible(3 * bs + 500, 9)
+    rng = np.random.RandomState(1)
+    for tname, ename in (("NONE", "ANS0"), ("NONE", "HUFFMAN"), ("ZRLT", "ANS0")):
+        comp = ctx.compress(data, tname, ename, bs)
+        outcomes = {"error": 0, "bytes": 0}
+        for t in range(8):
+            c = comp.copy()
+            for _ in range(1 + t % 4):
+                pos = rng.randint(24, c.size - 2)  # past the stream header
+                c[pos] ^= 1 << rng.randint(0, 8)
+            try:
+                back = ctx.decompress(c, data.size)
+                assert back.size <= data.size
+                outcomes["bytes"] += 1
+            except KanziGpuError:
+                outcomes["error"] += 1
+        assert outcomes["error"] + outcomes["bytes"] == 8
+        assert np.array_equal(ctx.decompress(comp, data.size), data), (tname, ename, outcomes)
+    ctx.close()

@@ -26,11 +26,13 @@ extern "C" {
 #define KNZ_ERR_BLOCK_SIZE 2
 #define KNZ_ERR_INVALID_CODEC 3
 #define KNZ_ERR_CREATE_COMPRESSOR 4
-#define KNZ_ERR_OUTPUT_TOO_SMALL 10 /* (ERR_WRITE_FILE family: caller buffer too small) */
+#define KNZ_ERR_CREATE_DECOMPRESSOR 5
+#define KNZ_ERR_OUTPUT_TOO_SMALL 12 /* ERR_WRITE_FILE: the caller's output buffer is too small */
 #define KNZ_ERR_PROCESS_BLOCK 13
-#define KNZ_ERR_INVALID_FILE 20
-#define KNZ_ERR_STREAM_VERSION 21
-#define KNZ_ERR_INVALID_PARAM 24
+#define KNZ_ERR_INVALID_FILE 15
+#define KNZ_ERR_STREAM_VERSION 16
+#define KNZ_ERR_INVALID_PARAM 18
+#define KNZ_ERR_CRC_CHECK 19
 #define KNZ_ERR_UNKNOWN 127
 
 /* Transform ids are wire-visible: transform/TransformFactory.hpp:49-73 */

@@ -1255,10 +1255,14 @@ ans0_decode_kernel(DecodeLaunch L)
 #undef DEC_REFILL
     if (active && k == 0) {
         const int tail = len & 3;
-        for (int t = 0; t < tail; t++)
-            o[count4 + t] = (u8)rd_bits(p, pos + 16ull * cnt + 8ull * t, 8);
-        if (2 * cnt + (u32)tail != psz)
+        // the tail bytes follow the consumed words: only read them when the payload size agrees
+        // (a corrupted payload may report any word count; the scan bounded pos + 8*psz, not cnt)
+        if (2 * cnt + (u32)tail != psz) {
             atomicExch(L.errFlag, KERR_BAD_STREAM);
+        } else {
+            for (int t = 0; t < tail; t++)
+                o[count4 + t] = (u8)rd_bits(p, pos + 16ull * cnt + 8ull * t, 8);
+        }
     }
 }
 

@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
 
 #include "../../include/knz_gpu.h"
 #include "kernels.h"
@@ -30,6 +31,11 @@ struct knz_ctx {
     cudaStream_t d2hStream;  // device->host copies of finished output (second DMA direction)
     cudaEvent_t evCopy[2], evDone[2];
     cudaEvent_t ev[10];
+    cudaEvent_t evStage[16]; // per-stage brackets: recorded during a batch, read once after it (no mid-batch sync)
+    std::recursive_mutex mtx; // every C-ABI entry point locks its context (reference worker threads share one)
+    int stageCap;             // bytes a stage buffer slot can hold (bstride - 64)
+    int encSched[3];          // knz_compress sub-batch schedule (env KNZ_ENC_BATCH)
+    int decBwtGroups;         // knz_decompress: groups of the last inverse-BWT stage (env KNZ_DEC_GROUPS)
     cudaStream_t gStream[KNZ_MAX_GROUPS]; // decode: one stream per block group (stages of different groups overlap)
     cudaEvent_t gEv[KNZ_MAX_GROUPS + 1];
     int decGroups;                        // 1 = one group, per-stage timings valid
@@ -154,14 +160,30 @@ extern "C" int knz_create(int device, int maxBlockSize, int maxBatchBlocks, knz_
         return KNZ_ERR_CREATE_COMPRESSOR; // no CPU fallback
     if (cudaSetDevice(device) != cudaSuccess)
         return KNZ_ERR_CREATE_COMPRESSOR;
-    knz_ctx* ctx = (knz_ctx*)calloc(1, sizeof(knz_ctx));
+    knz_ctx* ctx = new (std::nothrow) knz_ctx();
+    if (ctx == NULL)
+        return KNZ_ERR_CREATE_COMPRESSOR;
     ctx->device = device;
     ctx->maxBlockSize = maxBlockSize;
     ctx->maxBatch = maxBatchBlocks;
     const int nb = maxBatchBlocks;
-    // stage buffers hold a block plus the BWT header and the decoder's slack
-    const i64 slack = (maxBlockSize >> 4) > 512 ? (maxBlockSize >> 4) : 512;
-    ctx->bstride = round_up((i64)maxBlockSize + slack + 64, 256);
+    // A stage buffer slot holds what the reference's task buffers can hold: max(bs + bs/8, 256 KiB)
+    // (io/CompressedOutputStream.cpp:138-146) -- ZRLT at odd swap parity may legally expand a block up to
+    // that capacity -- plus the BWT headers and 64 bytes of slack for vector accesses.
+    const i64 refCap = ((i64)maxBlockSize + (maxBlockSize >> 3) > 262144) ? (i64)maxBlockSize + (maxBlockSize >> 3) : 262144;
+    ctx->bstride = round_up(refCap + 33 * 8 + 64, 256);
+    ctx->stageCap = (int)(ctx->bstride - 64);
+    ctx->encSched[0] = 32, ctx->encSched[1] = 96, ctx->encSched[2] = 128;
+    {
+        const char* e = getenv("KNZ_ENC_BATCH");
+        if (e)
+            sscanf(e, "%d,%d,%d", &ctx->encSched[0], &ctx->encSched[1], &ctx->encSched[2]);
+        for (int i = 0; i < 3; i++)
+            if (ctx->encSched[i] < 1)
+                ctx->encSched[i] = 1;
+        const char* g = getenv("KNZ_DEC_GROUPS");
+        ctx->decBwtGroups = (g && atoi(g) > 0) ? atoi(g) : 2; // 2: the per-launch latency of the node ranking outweighs more overlap
+    }
     ctx->outStride = round_up((i64)maxBlockSize + (maxBlockSize >> 2) + 4096, 256);
     ctx->maxChunks = (int)((ctx->bstride + ANS_CHUNK - 1) / ANS_CHUNK);
     bool ok = true;
@@ -175,6 +197,8 @@ extern "C" int knz_create(int device, int maxBlockSize, int maxBatchBlocks, knz_
     }
     for (int i = 0; i < 10; i++)
         A(cudaEventCreate(&ctx->ev[i]));
+    for (int i = 0; i < 16; i++)
+        A(cudaEventCreate(&ctx->evStage[i]));
     for (int i = 0; i < KNZ_MAX_GROUPS; i++)
         A(cudaStreamCreateWithFlags(&ctx->gStream[i], cudaStreamNonBlocking));
     for (int i = 0; i <= KNZ_MAX_GROUPS; i++)
@@ -249,6 +273,9 @@ extern "C" void knz_destroy(knz_ctx* ctx)
     for (int i = 0; i < 10; i++)
         if (ctx->ev[i])
             cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 16; i++)
+        if (ctx->evStage[i])
+            cudaEventDestroy(ctx->evStage[i]);
     for (int i = 0; i < 2; i++) {
         if (ctx->evCopy[i])
             cudaEventDestroy(ctx->evCopy[i]);
@@ -267,13 +294,14 @@ extern "C" void knz_destroy(knz_ctx* ctx)
         cudaStreamDestroy(ctx->d2hStream);
     if (ctx->stream)
         cudaStreamDestroy(ctx->stream);
-    free(ctx);
+    delete ctx;
 }
 
 extern "C" int knz_set_decode_groups(knz_ctx* ctx, int groups)
 {
     if (ctx == NULL || groups < 1 || groups > KNZ_MAX_GROUPS)
         return KNZ_ERR_INVALID_PARAM;
+    std::lock_guard<std::recursive_mutex> lock_(ctx->mtx);
     ctx->decGroups = groups;
     return KNZ_OK;
 }
@@ -306,6 +334,48 @@ static void add_stage_time(knz_ctx* ctx, int t, float ms)
         ctx->ms[slot] += ms;
 }
 
+static void launch_forward_stage(knz_ctx* ctx, int type, const StageLaunch& L, cudaStream_t s)
+{
+    switch (type) {
+    case T_NONE:
+        launch_none_forward(L, s, &ctx->launches);
+        break;
+    case T_BWT:
+        launch_bwt_forward(L, ctx->ws, s, &ctx->launches);
+        break;
+    case T_ZRLT:
+        launch_zrlt_forward(L, ctx->ws, s, &ctx->launches);
+        break;
+    case T_MTFT:
+        launch_sbrt_forward(L, 1, ctx->ws, s, &ctx->launches);
+        break;
+    case T_RANK:
+        launch_sbrt_forward(L, 2, ctx->ws, s, &ctx->launches);
+        break;
+    }
+}
+
+static void launch_inverse_stage(knz_ctx* ctx, int type, const StageLaunch& L, cudaStream_t s)
+{
+    switch (type) {
+    case T_NONE:
+        launch_none_forward(L, s, &ctx->launches); // inverse of a copy is a copy
+        break;
+    case T_BWT:
+        launch_bwt_inverse(L, ctx->ws, s, &ctx->launches);
+        break;
+    case T_ZRLT:
+        launch_zrlt_inverse(L, ctx->ws, s, &ctx->launches);
+        break;
+    case T_MTFT:
+        launch_sbrt_inverse(L, 1, ctx->ws, s, &ctx->launches);
+        break;
+    case T_RANK:
+        launch_sbrt_inverse(L, 2, ctx->ws, s, &ctx->launches);
+        break;
+    }
+}
+
 // Forward transforms + entropy for one batch of blocks resident on the device.
 // All lens[i] must be > 15 (small blocks are framed on the host).
 static int encode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8* d_in, i64 inStride,
@@ -325,6 +395,9 @@ static int encode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const
     }
     if (nB > ctx->maxBatch || ((uintptr_t)d_in & 15) || (inStride & 15) || ((uintptr_t)d_out & 15) || (outStride & 15))
         return KNZ_ERR_INVALID_PARAM;
+    // the context is provisioned for maxBlockSize: larger stream parameters would overrun its scratch
+    if (blockSize < 1 || blockSize > ctx->maxBlockSize || firstBlockLen < 0 || firstBlockLen > ctx->maxBlockSize)
+        return KNZ_ERR_BLOCK_SIZE;
     cudaStream_t s = ctx->stream;
     const int dataCap = (blockSize + (blockSize >> 3) > 262144) ? blockSize + (blockSize >> 3) : 262144;
     const int reqFirst = required_size(types, nt, firstBlockLen);
@@ -339,6 +412,11 @@ static int encode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const
         ctx->h_st[b].flags = 0xFF;
         ctx->h_capEven[b] = (reqFirst > req) ? reqFirst : req;
         ctx->h_capOdd[b] = (dataCap >= req) ? dataCap : req;
+        // never beyond what a stage buffer slot holds (cannot bind for blockSize <= maxBlockSize)
+        if (ctx->h_capEven[b] > ctx->stageCap)
+            ctx->h_capEven[b] = ctx->stageCap;
+        if (ctx->h_capOdd[b] > ctx->stageCap)
+            ctx->h_capOdd[b] = ctx->stageCap;
         if (lens[b] > maxLen)
             maxLen = lens[b];
     }
@@ -369,29 +447,9 @@ static int encode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const
         L.capOdd = ctx->capOdd;
         L.errFlag = ctx->errFlag;
         L.wsBlock0 = 0;
-        CK(cudaEventRecord(ctx->ev[1], s));
-        switch (types[i]) {
-        case T_NONE:
-            launch_none_forward(L, s, &ctx->launches);
-            break;
-        case T_BWT:
-            launch_bwt_forward(L, ctx->ws, s, &ctx->launches);
-            break;
-        case T_ZRLT:
-            launch_zrlt_forward(L, ctx->ws, s, &ctx->launches);
-            break;
-        case T_MTFT:
-            launch_sbrt_forward(L, 1, ctx->ws, s, &ctx->launches);
-            break;
-        case T_RANK:
-            launch_sbrt_forward(L, 2, ctx->ws, s, &ctx->launches);
-            break;
-        }
-        CK(cudaEventRecord(ctx->ev[2], s));
-        CK(cudaEventSynchronize(ctx->ev[2]));
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]);
-        add_stage_time(ctx, types[i], ms);
+        CK(cudaEventRecord(ctx->evStage[2 * i], s));
+        launch_forward_stage(ctx, types[i], L, s);
+        CK(cudaEventRecord(ctx->evStage[2 * i + 1], s));
     }
     const BlkState* stFinal = ctx->st + (i64)nt * ctx->maxBatch;
     CK(cudaEventRecord(ctx->ev[3], s));
@@ -420,6 +478,10 @@ static int encode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
     float ms = 0.f;
+    for (int i = 0; i < nt; i++) { // stage brackets were recorded without stalling the stream
+        cudaEventElapsedTime(&ms, ctx->evStage[2 * i], ctx->evStage[2 * i + 1]);
+        add_stage_time(ctx, types[i], ms);
+    }
     cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]);
     ctx->ms[3] = ms;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]);
@@ -441,6 +503,7 @@ extern "C" int knz_encode_blocks_dev(knz_ctx* ctx, uint64_t tType, int eType, in
 {
     if (!ctx || !d_in || !lens || !d_blockOut || !d_outBits || nBlocks < 0)
         return KNZ_ERR_INVALID_PARAM;
+    std::lock_guard<std::recursive_mutex> lock_(ctx->mtx);
     cudaSetDevice(ctx->device);
     float acc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
     for (int off = 0; off < nBlocks; off += ctx->maxBatch) {
@@ -475,6 +538,7 @@ extern "C" int knz_encode_blocks(knz_ctx* ctx, uint64_t tType, int eType, int bl
 {
     if (!ctx || !in || !lens || !out || !outBits || nBlocks < 0)
         return KNZ_ERR_INVALID_PARAM;
+    std::lock_guard<std::recursive_mutex> lock_(ctx->mtx);
     cudaSetDevice(ctx->device);
     cudaStream_t s = ctx->stream;
     for (int off = 0; off < nBlocks; off += ctx->maxBatch) {
@@ -541,7 +605,7 @@ extern "C" int knz_assemble_stream_dev(knz_ctx* ctx, const uint8_t* d_blockOut, 
 {
     if (!ctx || nBlocks < 0 || ((uintptr_t)d_stream & 3))
         return KNZ_ERR_INVALID_PARAM;
-    (void)streamCap;
+    std::lock_guard<std::recursive_mutex> lock_(ctx->mtx);
     cudaSetDevice(ctx->device);
     cudaStream_t s = ctx->stream;
     ctx->h_pos[0] = startBit;
@@ -549,6 +613,18 @@ extern "C" int knz_assemble_stream_dev(knz_ctx* ctx, const uint8_t* d_blockOut, 
     if (nBlocks > 0) {
         if (nBlocks > ctx->maxBatch)
             return KNZ_ERR_INVALID_PARAM;
+        // the assembled bits must fit the caller's buffer: sum the prefixes + payloads before writing
+        CK(cudaMemcpyAsync(ctx->h_bits, d_outBits, sizeof(u64) * (size_t)nBlocks, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        u64 total = startBit;
+        for (int b = 0; b < nBlocks; b++) {
+            int lw = 3;
+            while (lw < 34 && (ctx->h_bits[b] >> lw) != 0)
+                lw++;
+            total += 5ull + (u64)lw + ctx->h_bits[b];
+        }
+        if (streamCap < 0 || ((total + 8 + 31) >> 5) * 4 > (u64)streamCap)
+            return KNZ_ERR_OUTPUT_TOO_SMALL;
         launch_stream_assemble(d_blockOut, outStride, d_outBits, nBlocks, ctx->streamPos, ctx->blockOff, ctx->streamPos,
                                d_stream, s, &ctx->launches);
     }
@@ -630,6 +706,7 @@ extern "C" int knz_compress(knz_ctx* ctx, const char* transform, const char* ent
 {
     if (!ctx || !in || !out || !outLen || n < 0)
         return KNZ_ERR_INVALID_PARAM;
+    std::lock_guard<std::recursive_mutex> lock_(ctx->mtx);
     const u64 tType = knz_transform_type(transform);
     const int eType = knz_entropy_type(entropy);
     if (tType == (u64)-1 || eType < 0) {
@@ -652,13 +729,7 @@ extern "C" int knz_compress(knz_ctx* ctx, const char* transform, const char* ent
     // stream while sub-batch i is being encoded, and the finished bytes of the stream go back
     // to the host on a third stream.  The first sub-batch is small (its copy is exposed),
     // later ones are large (GPU efficiency, fewer round trips).
-    static int sched[3] = { 0, 0, 0 }; // KNZ_ENC_BATCH=a,b,c overrides the schedule (experiments)
-    if (!sched[0]) {
-        sched[0] = 32, sched[1] = 96, sched[2] = 128;
-        const char* e = getenv("KNZ_ENC_BATCH");
-        if (e)
-            sscanf(e, "%d,%d,%d", &sched[0], &sched[1], &sched[2]);
-    }
+    const int* sched = ctx->encSched; // KNZ_ENC_BATCH=a,b,c overrides the schedule (read once per context)
     auto batchSize = [&](int k, i64 left) -> int {
         const int want = sched[k < 2 ? k : 2];
         const int lim = (want < ctx->maxBatch) ? want : ctx->maxBatch;
@@ -806,11 +877,17 @@ static int decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const
         return KNZ_ERR_INVALID_CODEC;
     if (nB > ctx->maxBatch)
         return KNZ_ERR_INVALID_PARAM;
+    if (blockSize < 1 || blockSize > ctx->maxBlockSize)
+        return KNZ_ERR_BLOCK_SIZE;
     cudaStream_t s = ctx->stream;
+    // a decoded block may not exceed its destination slot nor the stream's block size
+    const int outCap = (int)((outStride > 0 && outStride < blockSize) ? outStride : blockSize);
+    // capacity of the reference's task buffers on the decode side (io/CompressedInputStream.cpp:275)
     const int blkLen = blockSize + ((blockSize >> 4) > 512 ? (blockSize >> 4) : 512);
     int maxLen = 0;
     for (int b = 0; b < nB; b++) {
-        if (h_preLen[b] <= 0 || h_preLen[b] > blkLen || (i64)h_preLen[b] + 64 > ctx->bstride)
+        // entropy-decoded length: whatever a stage buffer slot holds (the encoder emits <= max(bs + bs/8, 256 KiB))
+        if (h_preLen[b] <= 0 || h_preLen[b] > ctx->stageCap)
             return KNZ_ERR_INVALID_FILE;
         ctx->h_st[b].len = h_preLen[b];
         ctx->h_st[b].cur = 0;
@@ -888,35 +965,19 @@ static int decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const
                 L.stOut = ctx->st + (i64)(stepg + 1) * ctx->maxBatch + g0;
                 L.stageIdx = i;
                 L.nBlocks = g1 - g0;
-                L.maxLen = blkLen;
+                L.maxLen = (maxLen > blkLen) ? maxLen : blkLen;
                 L.capEven = ctx->capEven + g0;
                 L.capOdd = ctx->capOdd + g0;
                 L.errFlag = ctx->errFlag;
                 L.wsBlock0 = g0;
-                switch (types[i]) {
-                case T_NONE:
-                    launch_none_forward(L, sg, &ctx->launches);
-                    break;
-                case T_BWT:
-                    launch_bwt_inverse(L, ctx->ws, sg, &ctx->launches);
-                    break;
-                case T_ZRLT:
-                    launch_zrlt_inverse(L, ctx->ws, sg, &ctx->launches);
-                    break;
-                case T_MTFT:
-                    launch_sbrt_inverse(L, 1, ctx->ws, sg, &ctx->launches);
-                    break;
-                case T_RANK:
-                    launch_sbrt_inverse(L, 2, ctx->ws, sg, &ctx->launches);
-                    break;
-                }
+                launch_inverse_stage(ctx, types[i], L, sg);
             }
             {
                 BufTable btg = bt;
                 for (int k = 0; k < 3; k++)
                     btg.base[k] = bt.base[k] + (i64)g0 * bt.stride[k];
                 launch_copy_out(btg, ctx->st + (i64)nt * ctx->maxBatch + g0, g1 - g0, d_out + (i64)g0 * outStride,
-                                outStride, sg, &ctx->launches);
+                                outStride, outCap, ctx->errFlag, sg, &ctx->launches);
             }
             if (sink) { // full-size blocks go to the host as soon as their group is done
                 const int last = (g1 == nB) ? g1 - 1 : g1; // the batch's last block may be short: the caller copies it
@@ -953,22 +1014,17 @@ static int decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const
         L.stOut = ctx->st + (i64)(step + 1) * ctx->maxBatch;
         L.stageIdx = i;
         L.nBlocks = nB;
-        L.maxLen = blkLen;
+        L.maxLen = (maxLen > blkLen) ? maxLen : blkLen;
         L.capEven = ctx->capEven;
         L.capOdd = ctx->capOdd;
         L.errFlag = ctx->errFlag;
         L.wsBlock0 = 0;
-        CK(cudaEventRecord(ctx->ev[2], s));
+        CK(cudaEventRecord(ctx->evStage[2 * step], s));
         // Last stage of a full batch with a host sink: inverse-BWT the blocks in four groups and
         // send each group's (full-size) blocks to the host while the next group is being walked.
         const bool grouped = (h_sink != NULL) && (i == 0) && (types[0] == T_BWT) && (nB >= 64) && (outStride == blockSize);
         if (grouped) {
-            static int envG = 0; // KNZ_DEC_GROUPS overrides the group count (experiments)
-            if (!envG) {
-                const char* e = getenv("KNZ_DEC_GROUPS");
-                envG = (e && atoi(e) > 0) ? atoi(e) : 2; // 2: the per-launch latency of the node ranking outweighs more overlap
-            }
-            const int G = (envG < nB / 8) ? envG : nB / 8;
+            const int G = (ctx->decBwtGroups < nB / 8) ? ctx->decBwtGroups : nB / 8;
             for (int g = 0; g < G; g++) {
                 const int g0 = (int)((i64)nB * g / G), g1 = (int)((i64)nB * (g + 1) / G);
                 StageLaunch Lg = L;
@@ -980,7 +1036,8 @@ static int decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const
                 Lg.capOdd = L.capOdd + g0;
                 Lg.nBlocks = g1 - g0;
                 launch_bwt_inverse(Lg, ctx->ws, s, &ctx->launches);
-                launch_copy_out(Lg.bt, Lg.stOut, g1 - g0, d_out + (i64)g0 * outStride, outStride, s, &ctx->launches);
+                launch_copy_out(Lg.bt, Lg.stOut, g1 - g0, d_out + (i64)g0 * outStride, outStride, outCap, ctx->errFlag, s,
+                                &ctx->launches);
                 CK(cudaEventRecord(ctx->evDone[g & 1], s));
                 CK(cudaStreamWaitEvent(ctx->d2hStream, ctx->evDone[g & 1], 0));
                 const int last = (g1 == nB) ? g1 - 1 : g1; // the batch's last block may be short: the caller copies it
@@ -989,51 +1046,33 @@ static int decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const
                                        (size_t)(last - g0) * (size_t)blockSize, cudaMemcpyDeviceToHost, ctx->d2hStream));
             }
             *h_sinkBlocks = nB - 1;
-            CK(cudaEventRecord(ctx->ev[3], s));
-            CK(cudaEventSynchronize(ctx->ev[3]));
-            float msg = 0.f;
-            cudaEventElapsedTime(&msg, ctx->ev[2], ctx->ev[3]);
-            add_stage_time(ctx, types[i], msg);
+            CK(cudaEventRecord(ctx->evStage[2 * step + 1], s));
             continue;
         }
-        switch (types[i]) {
-        case T_NONE:
-            launch_none_forward(L, s, &ctx->launches); // inverse of a copy is a copy
-            break;
-        case T_BWT:
-            launch_bwt_inverse(L, ctx->ws, s, &ctx->launches);
-            break;
-        case T_ZRLT:
-            launch_zrlt_inverse(L, ctx->ws, s, &ctx->launches);
-            break;
-        case T_MTFT:
-            launch_sbrt_inverse(L, 1, ctx->ws, s, &ctx->launches);
-            break;
-        case T_RANK:
-            launch_sbrt_inverse(L, 2, ctx->ws, s, &ctx->launches);
-            break;
-        }
-        CK(cudaEventRecord(ctx->ev[3], s));
-        CK(cudaEventSynchronize(ctx->ev[3]));
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
-        add_stage_time(ctx, types[i], ms);
+        launch_inverse_stage(ctx, types[i], L, s);
+        CK(cudaEventRecord(ctx->evStage[2 * step + 1], s));
     }
     const BlkState* stFinal = ctx->st + (i64)nt * ctx->maxBatch;
     if (!(h_sinkBlocks && *h_sinkBlocks > 0))
-        launch_copy_out(bt, stFinal, nB, d_out, outStride, s, &ctx->launches);
+        launch_copy_out(bt, stFinal, nB, d_out, outStride, outCap, ctx->errFlag, s, &ctx->launches);
     CK(cudaEventRecord(ctx->ev[4], s));
     CK(cudaMemcpyAsync(ctx->h_err, ctx->errFlag, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(ctx->h_st, stFinal, sizeof(BlkState) * nB, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
     float ms = 0.f;
+    for (int k = 0; k < nt; k++) { // stage brackets were recorded without stalling the stream
+        cudaEventElapsedTime(&ms, ctx->evStage[2 * k], ctx->evStage[2 * k + 1]);
+        add_stage_time(ctx, types[nt - 1 - k], ms);
+    }
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
     ctx->ms[3] = ms;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]);
     ctx->ms[5] = ms;
-    cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]);
-    ctx->ms[7] = ms;
+    if (eType == E_ANS0 || eType == E_HUF) {
+        cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]);
+        ctx->ms[7] = ms;
+    }
     for (int b = 0; b < nB; b++)
         h_outLens[b] = ctx->h_st[b].len;
     return map_kerr(ctx, ctx->h_err[0]);
@@ -1071,6 +1110,7 @@ extern "C" int knz_decode_blocks_dev(knz_ctx* ctx, uint64_t tType, int eType, in
     // The block headers live in device memory here: fetch the first 8 bytes of each block.
     if (!ctx || !d_in || !h_inBits || !d_out || !h_outLens)
         return KNZ_ERR_INVALID_PARAM;
+    std::lock_guard<std::recursive_mutex> lock_(ctx->mtx);
     cudaSetDevice(ctx->device);
     cudaStream_t s = ctx->stream;
     const int blkLen = blockSize + ((blockSize >> 4) > 512 ? (blockSize >> 4) : 512);
@@ -1118,6 +1158,7 @@ extern "C" int knz_decode_blocks(knz_ctx* ctx, uint64_t tType, int eType, int bl
 {
     if (!ctx || !in || !inBits || !out || !outLens)
         return KNZ_ERR_INVALID_PARAM;
+    std::lock_guard<std::recursive_mutex> lock_(ctx->mtx);
     cudaSetDevice(ctx->device);
     cudaStream_t s = ctx->stream;
     const int blkLen = blockSize + ((blockSize >> 4) > 512 ? (blockSize >> 4) : 512);
@@ -1187,6 +1228,7 @@ extern "C" int knz_decompress(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_
 {
     if (!ctx || !in || !out || !outLen || n < 20)
         return KNZ_ERR_INVALID_PARAM;
+    std::lock_guard<std::recursive_mutex> lock_(ctx->mtx);
     cudaSetDevice(ctx->device);
     cudaStream_t s = ctx->stream;
     HostBitReader r = { in, 8ull * (u64)n, 0, false };
@@ -1194,19 +1236,41 @@ extern "C" int knz_decompress(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_
         return KNZ_ERR_INVALID_FILE;
     if (r.get(4) != 6)
         return KNZ_ERR_STREAM_VERSION;
-    if (r.get(2) != 0) {
-        snprintf(ctx->err, sizeof(ctx->err), "block checksums not implemented");
-        return KNZ_ERR_INVALID_CODEC;
-    }
+    const u32 ckSize = (u32)r.get(2);
     const int eType = (int)r.get(5);
     const u64 tType = r.get(48);
     const int blockSize = (int)r.get(28) << 4;
     const int szMask = (int)r.get(2);
+    u64 origSize = 0;
     if (szMask)
-        r.get(16 * szMask);
+        origSize = r.get(16 * szMask);
     r.get(15);
-    r.get(24); // header checksum (validated by the reference reader; not needed to decode)
-    if (r.bad || blockSize < 1024 || blockSize > ctx->maxBlockSize)
+    const u32 ck1 = (u32)r.get(24);
+    if (r.bad)
+        return KNZ_ERR_INVALID_FILE;
+    { // header checksum: the reference rejects a mismatch (io/CompressedInputStream.cpp:622-645)
+        const u32 HASH = 0x1E35A7BDu;
+        u32 ck = HASH * (0x01030507u * 6u);
+        ck ^= HASH * (u32)~ckSize;
+        ck ^= HASH * (u32)~(u32)eType;
+        ck ^= HASH * (u32)((~tType) >> 32);
+        ck ^= HASH * (u32)(~tType);
+        ck ^= HASH * (u32)~(u32)blockSize;
+        if (szMask) {
+            ck ^= HASH * (u32)((~origSize) >> 32);
+            ck ^= HASH * (u32)(~origSize);
+        }
+        ck = (ck >> 23) ^ (ck >> 3);
+        if ((ck & 0xFFFFFFu) != ck1) {
+            snprintf(ctx->err, sizeof(ctx->err), "invalid bitstream, header checksum mismatch");
+            return KNZ_ERR_CRC_CHECK;
+        }
+    }
+    if (ckSize != 0) {
+        snprintf(ctx->err, sizeof(ctx->err), "block checksums not implemented");
+        return KNZ_ERR_INVALID_CODEC;
+    }
+    if (blockSize < 1024 || blockSize > ctx->maxBlockSize)
         return KNZ_ERR_BLOCK_SIZE;
     const int blkLen = blockSize + ((blockSize >> 4) > 512 ? (blockSize >> 4) : 512);
     // whole compressed stream to the device; kernels read at bit offsets
@@ -1325,6 +1389,7 @@ static int run_single_stage(knz_ctx* ctx, int type, bool inverse, const u8* in, 
 {
     if (!ctx || !in || !out || !outLen || !applied || n < 0)
         return KNZ_ERR_INVALID_PARAM;
+    std::lock_guard<std::recursive_mutex> lock_(ctx->mtx);
     *applied = 0;
     *outLen = 0;
     if (n == 0) {
@@ -1333,8 +1398,9 @@ static int run_single_stage(knz_ctx* ctx, int type, bool inverse, const u8* in, 
     }
     if (!type_supported(type))
         return KNZ_ERR_INVALID_CODEC;
-    if ((i64)n + 64 > ctx->bstride || (i64)cap + 64 > ctx->bstride + 4096)
+    if (n > ctx->stageCap || cap < 0)
         return KNZ_ERR_BLOCK_SIZE;
+    const int devCap = (cap < ctx->stageCap) ? cap : ctx->stageCap; // what a stage buffer slot can hold
     cudaSetDevice(ctx->device);
     cudaStream_t s = ctx->stream;
     CK(cudaMemcpyAsync(ctx->dStageIn, in, (size_t)n, cudaMemcpyHostToDevice, s));
@@ -1342,8 +1408,8 @@ static int run_single_stage(knz_ctx* ctx, int type, bool inverse, const u8* in, 
     ctx->h_st[0].cur = 2;
     ctx->h_st[0].swaps = 0;
     ctx->h_st[0].flags = inverse ? 0x00 : 0xFF;
-    ctx->h_capEven[0] = cap;
-    ctx->h_capOdd[0] = cap;
+    ctx->h_capEven[0] = devCap;
+    ctx->h_capOdd[0] = devCap;
     CK(cudaMemcpyAsync(ctx->st, ctx->h_st, sizeof(BlkState), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->capEven, ctx->h_capEven, sizeof(int), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->capOdd, ctx->h_capOdd, sizeof(int), cudaMemcpyHostToDevice, s));
@@ -1357,7 +1423,7 @@ static int run_single_stage(knz_ctx* ctx, int type, bool inverse, const u8* in, 
     L.stOut = ctx->st + ctx->maxBatch;
     L.stageIdx = 0;
     L.nBlocks = 1;
-    L.maxLen = (n > cap ? n : cap) + 64;
+    L.maxLen = (n > devCap ? n : devCap) + 64;
     L.capEven = ctx->capEven;
     L.capOdd = ctx->capOdd;
     L.errFlag = ctx->errFlag;
@@ -1428,6 +1494,7 @@ extern "C" int knz_entropy_encode(knz_ctx* ctx, int type, const uint8_t* in, int
 {
     if (!ctx || !in || !out || !outBits || n <= 0)
         return KNZ_ERR_INVALID_PARAM;
+    std::lock_guard<std::recursive_mutex> lock_(ctx->mtx);
     if (type != E_RAW && type != E_ANS0 && type != E_HUF)
         return KNZ_ERR_INVALID_CODEC;
     if ((i64)n + 64 > ctx->bstride)
@@ -1485,6 +1552,7 @@ extern "C" int knz_entropy_decode(knz_ctx* ctx, int type, const uint8_t* in, int
 {
     if (!ctx || !in || !out || n <= 0 || inBits < 0)
         return KNZ_ERR_INVALID_PARAM;
+    std::lock_guard<std::recursive_mutex> lock_(ctx->mtx);
     if (type != E_RAW && type != E_ANS0 && type != E_HUF)
         return KNZ_ERR_INVALID_CODEC;
     const i64 nbytes = (inBits + 7) >> 3;

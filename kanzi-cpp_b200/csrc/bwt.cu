@@ -1952,13 +1952,19 @@ void launch_none_forward(const StageLaunch& L, cudaStream_t s, u64* launches)
 }
 
 __global__ void __launch_bounds__(256)
-copy_out_kernel(BufTable bt, const BlkState* __restrict__ st, u8* __restrict__ out, i64 outStride)
+copy_out_kernel(BufTable bt, const BlkState* __restrict__ st, u8* __restrict__ out, i64 outStride, int outCap,
+                int* __restrict__ errFlag)
 {
     const int b = blockIdx.y;
     const BlkState bs = st[b];
     const u8* __restrict__ src = blk_src(bt, bs, b);
     u8* __restrict__ dst = out + (i64)b * outStride;
     const int n = bs.len;
+    if (n > outCap) { // never write past the block's destination slot
+        if (blockIdx.x == 0 && threadIdx.x == 0)
+            atomicExch(errFlag, KERR_OUT_OVERFLOW);
+        return;
+    }
     if ((((uintptr_t)dst) & 15) == 0) {
         const int n16 = n >> 4;
         const uint4* s4 = reinterpret_cast<const uint4*>(src);
@@ -1973,10 +1979,10 @@ copy_out_kernel(BufTable bt, const BlkState* __restrict__ st, u8* __restrict__ o
     }
 }
 
-void launch_copy_out(const BufTable& bt, const BlkState* st, int nBlocks, u8* out, i64 outStride, cudaStream_t s,
-                     u64* launches)
+void launch_copy_out(const BufTable& bt, const BlkState* st, int nBlocks, u8* out, i64 outStride, int outCap,
+                     int* errFlag, cudaStream_t s, u64* launches)
 {
-    KLAUNCH(copy_out_kernel, dim3(64, nBlocks), 256, s, bt, st, out, outStride);
+    KLAUNCH(copy_out_kernel, dim3(64, nBlocks), 256, s, bt, st, out, outStride, outCap, errFlag);
     *launches += 1;
 }
 

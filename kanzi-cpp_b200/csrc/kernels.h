@@ -122,5 +122,7 @@ struct Workspace {
 
 bool workspace_alloc(Workspace& ws, int maxBlocks, int capN);
 void workspace_free(Workspace& ws);
-void launch_copy_out(const BufTable& bt, const BlkState* st, int nBlocks, u8* out, i64 outStride, cudaStream_t s,
-                     u64* launches);
+// Copies each block's final bytes to out + b*outStride; a block longer than outCap is not copied
+// and raises KERR_OUT_OVERFLOW (a crafted stream may not write past its destination slot).
+void launch_copy_out(const BufTable& bt, const BlkState* st, int nBlocks, u8* out, i64 outStride, int outCap,
+                     int* errFlag, cudaStream_t s, u64* launches);

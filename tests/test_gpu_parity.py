@@ -203,3 +203,68 @@ def test_gpu_decode_groups(gpu, oracle, groups):
         assert np.array_equal(gpu.decompress(comp_h, data.size), data)
     finally:
         gpu.set_decode_groups(1)
+
+
+@pytest.fixture(scope="module")
+def gpu_big():
+    """A context provisioned for the large-block configurations (BASELINE configs 4 and 5): the
+    > 4 MiB suffix-sort path (bwt_init_keys), the 64-bit SBRT kernels (>= 16 MiB) and large
+    chunk counts only run here."""
+    import torch
+    assert torch.cuda.is_available()
+    from kanzi_b200 import Context
+    ctx = Context(0, 32 << 20, 4)
+    yield ctx
+    ctx.close()
+
+
+@pytest.mark.parametrize("bs_mib", [16, 32])
+@pytest.mark.parametrize("tname,ename", [("BWT+RANK+ZRLT", "ANS0"), ("NONE", "HUFFMAN"), ("NONE", "ANS0"),
+                                         ("BWT+MTFT+ZRLT", "HUFFMAN")])
+def test_gpu_large_blocks_vs_reference(gpu_big, tname, ename, bs_mib):
+    """16 MiB and 32 MiB blocks against the unmodified reference (prebuilt oracle/_ref)."""
+    from oracle.oracle import Ref
+    ref = Ref.load()
+    if ref is None:
+        pytest.skip("oracle/_ref/libkanzi_ref.so not present")
+    bs = bs_mib << 20
+    data = synth.synth_compressible(2 * bs + (bs >> 2) + 12345, 50 + bs_mib)
+    want = ref.stream_compress(data, tname, ename, bs, jobs=3)
+    got = gpu_big.compress(data, tname, ename, bs)
+    assert got.size == want.size and np.array_equal(got, want), (tname, ename, bs_mib, _first_diff(got, want))
+    back = gpu_big.decompress(want, data.size)
+    assert back.size == data.size and np.array_equal(back, data)
+
+
+def test_gpu_zrlt_odd_parity_expansion(gpu):
+    """ZRLT at odd swap parity on 0xFE/0xFF-heavy input expands a block up to the reference's
+    max(bs + bs/8, 256 KiB) task buffer: the stage buffers must hold that (the neighbours of the
+    block in the batch stay intact) and the stream must decode."""
+    bs = 65536
+    heavy = (rng_bytes(6 * bs, 77, 4) + 252).astype(np.uint8)
+    plain = synth.synth_text(2 * bs, 78)
+    data = np.concatenate([plain[:bs], heavy[: 3 * bs], plain[bs:], heavy[3 * bs:]])
+    for tname in ("BWT+ZRLT", "RANK+ZRLT", "MTFT+ZRLT"):
+        comp = gpu.compress(data, tname, "ANS0", bs)
+        back = gpu.decompress(comp, data.size)
+        assert back.size == data.size and np.array_equal(back, data), tname
+        comp = gpu.compress(np.full(3 * bs + 17, 0xFF, dtype=np.uint8), tname, "NONE", bs)
+        back = gpu.decompress(comp, 3 * bs + 17)
+        assert np.array_equal(back, np.full(3 * bs + 17, 0xFF, dtype=np.uint8)), tname
+
+
+def test_gpu_rejects_oversized_parameters(gpu):
+    """Sizes beyond what the context was provisioned for are refused, not executed."""
+    from kanzi_b200 import KanziGpuError
+    data = synth.synth_text(1 << 16, 5)
+    with pytest.raises(KanziGpuError):
+        gpu.compress(data, "BWT+RANK+ZRLT", "ANS0", 8 << 20)
+    blocks = [data]
+    with pytest.raises(KanziGpuError):
+        gpu.encode_blocks(blocks, "ZRLT", "ANS0", 8 << 20)
+    comp = gpu.compress(data, "NONE", "ANS0", 1 << 16)
+    bad = comp.copy()
+    bad[19] ^= 0x5A  # stream header checksum byte
+    with pytest.raises(KanziGpuError) as e:
+        gpu.decompress(bad, data.size)
+    assert e.value.code == 19  # ERR_CRC_CHECK

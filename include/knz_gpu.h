@@ -45,6 +45,7 @@ extern "C" {
 #define KNZ_E_NONE 0
 #define KNZ_E_HUFFMAN 1
 #define KNZ_E_ANS0 5
+#define KNZ_E_ANS1 8
 
 typedef struct knz_ctx knz_ctx;
 

@@ -747,9 +747,23 @@ stream_concat_kernel(const u8* __restrict__ blockOut, i64 outStride, const u64* 
 }
 
 // ------------------------------------------------------------------ host side
+void launch_out_prepare_and_header(const EncodeLaunch& L, cudaStream_t s, u64* launches)
+{
+    const int nB = L.nBlocks;
+    i64 zx64 = (L.outStride / 4 + 255) / 256;
+    const int zx = (int)(zx64 < 64 ? zx64 : 64);
+    KLAUNCH(out_prepare_kernel, dim3(zx, nB), 256, s, L.st, L.nTransforms, L.blockBits, L.out, L.outStride);
+    KLAUNCH(block_header_kernel, (nB + 127) / 128, 128, s, L.st, nB, L.nTransforms, L.out, L.outStride);
+    *launches += 2;
+}
+
 void launch_entropy_encode(const EncodeLaunch& L, cudaStream_t s, u64* launches)
 {
     const int nB = L.nBlocks;
+    if (L.eType == E_ANS1) {
+        launch_ans1_encode(L, s, launches);
+        return;
+    }
     if (L.eType == E_RAW) {
         KLAUNCH(raw_meta_kernel, (nB + 127) / 128, 128, s, L.st, nB, L.maxChunks, L.hdrBits, L.payBytes, L.payOff);
     } else if (L.eType == E_HUF) {
@@ -772,10 +786,7 @@ void launch_entropy_encode(const EncodeLaunch& L, cudaStream_t s, u64* launches)
     }
     KLAUNCH(ans_scan_kernel, nB, 256, s, L.st, nB, L.maxChunks, L.eType, L.nTransforms, L.hdrBits, L.payBytes,
                                        L.chunkOff, L.blockBits, L.out, L.outStride, L.errFlag);
-    i64 zx64 = (L.outStride / 4 + 255) / 256;
-    const int zx = (int)(zx64 < 64 ? zx64 : 64);
-    KLAUNCH(out_prepare_kernel, dim3(zx, nB), 256, s, L.st, L.nTransforms, L.blockBits, L.out, L.outStride);
-    KLAUNCH(block_header_kernel, (nB + 127) / 128, 128, s, L.st, nB, L.nTransforms, L.out, L.outStride);
+    launch_out_prepare_and_header(L, s, launches);
     if (L.eType == E_RAW)
         KLAUNCH(ans_concat_kernel, dim3(64, nB), 128, s, L.bt, L.st, L.maxChunks, L.eType, L.slots, L.hdrBits,
                                                        L.payBytes, L.payOff, L.chunkOff, L.out, L.outStride);
@@ -783,7 +794,7 @@ void launch_entropy_encode(const EncodeLaunch& L, cudaStream_t s, u64* launches)
         KLAUNCH(ans_concat_kernel, dim3(L.maxChunks, nB), 128, s, L.bt, L.st, L.maxChunks, L.eType, L.slots,
                                                                 L.hdrBits, L.payBytes, L.payOff, L.chunkOff,
                                                                 L.out, L.outStride);
-    *launches += 5;
+    *launches += 3;
 }
 
 void launch_stream_assemble(const u8* blockOut, i64 outStride, const u64* blockBits, int nBlocks,
@@ -1270,6 +1281,10 @@ void launch_entropy_decode(const DecodeLaunch& L, cudaStream_t s, u64* launches)
 {
     if (L.eType == E_HUF) {
         launch_huffman_decode(L, s, launches);
+        return;
+    }
+    if (L.eType == E_ANS1) {
+        launch_ans1_decode(L, s, launches);
         return;
     }
     KLAUNCH(ans0_dec_scan_kernel, L.nBlocks, 32, s, L);

@@ -1,8 +1,8 @@
 // ans_tables.cuh -- per-chunk rANS statistics: frequency normalisation, chunk
 // header emission and encoder/decoder table construction.  Sequential code run
 // by ONE lane per 16 KiB chunk (8 chunks per warp in flight); also compiled for
-// the host by tests/host_units.cpp so the exact small-integer behaviour is
-// unit-tested on CPU against the oracle.
+// the host (KNZ_HD) so the emulator build (tests/sim) exercises the same small-integer code; the
+// CPU suite compares it with the oracle.
 //
 // Format and arithmetic follow the reference bit for bit:
 //   normalisation  entropy/EntropyUtils.cpp:131-245

@@ -54,6 +54,8 @@ struct knz_ctx {
     int* dPreLen;
     int* errFlag;
     Workspace ws;
+    Ans1Work a1; // order-1 rANS scratch, allocated on the first use of ANS1
+    bool a1Ready;
     // pinned host mirrors
     BlkState* h_st;
     int *h_capEven, *h_capOdd, *h_err, *h_preLen;
@@ -82,6 +84,8 @@ static int split_types(u64 tType, int* types)
     }
     return n;
 }
+
+static bool entropy_supported(int e) { return e == E_RAW || e == E_ANS0 || e == E_HUF || e == E_ANS1; }
 
 static bool type_supported(int t) { return t == T_NONE || t == T_BWT || t == T_ZRLT || t == T_MTFT || t == T_RANK; }
 
@@ -142,6 +146,8 @@ extern "C" int knz_entropy_type(const char* name)
         return E_ANS0;
     if (!strcmp(name, "HUFFMAN"))
         return E_HUF;
+    if (!strcmp(name, "ANS1"))
+        return E_ANS1;
     return -1;
 }
 
@@ -184,7 +190,9 @@ extern "C" int knz_create(int device, int maxBlockSize, int maxBatchBlocks, knz_
         const char* g = getenv("KNZ_DEC_GROUPS");
         ctx->decBwtGroups = (g && atoi(g) > 0) ? atoi(g) : 2; // 2: the per-launch latency of the node ranking outweighs more overlap
     }
-    ctx->outStride = round_up((i64)maxBlockSize + (maxBlockSize >> 2) + 4096, 256);
+    // a block's output: the block, 25 % expansion room, and the 256 context headers of every order-1
+    // rANS chunk (<= 401 bytes each) -- incompressible data under ANS1 costs up to ~100 KiB per chunk
+    ctx->outStride = round_up((i64)maxBlockSize + (maxBlockSize >> 2) + 4096 + 131072 * (i64)((maxBlockSize >> 22) + 1), 256);
     ctx->maxChunks = (int)((ctx->bstride + ANS_CHUNK - 1) / ANS_CHUNK);
     bool ok = true;
 #define A(call) ok = ok && ((call) == cudaSuccess)
@@ -258,6 +266,8 @@ extern "C" void knz_destroy(knz_ctx* ctx)
     if (ctx->stream)
         cudaStreamSynchronize(ctx->stream);
     workspace_free(ctx->ws);
+    if (ctx->a1Ready)
+        ans1_work_free(ctx->a1);
     void* dev[] = { ctx->bufA, ctx->bufB, ctx->dStageIn, ctx->dOut, ctx->st, ctx->capEven, ctx->capOdd, ctx->slots,
                     ctx->hdrBits, ctx->payBytes, ctx->payOff, ctx->chunkOff, ctx->chunkPos, ctx->blockBits,
                     ctx->blockOff, ctx->streamPos, ctx->dInBits, ctx->dPayStart, ctx->dPreLen, ctx->errFlag,
@@ -334,6 +344,30 @@ static void add_stage_time(knz_ctx* ctx, int t, float ms)
         ctx->ms[slot] += ms;
 }
 
+// ANS1 keeps a 256 x 256 table set and a pre-mapped record stream per chunk: only contexts that
+// use it pay for the memory.
+static int ensure_ans1(knz_ctx* ctx, int eType)
+{
+    if (eType != E_ANS1 || ctx->a1Ready)
+        return KNZ_OK;
+    if (!ans1_work_alloc(ctx->a1, ctx->maxBatch, ctx->stageCap)) {
+        snprintf(ctx->err, sizeof(ctx->err), "out of device memory for the ANS1 tables");
+        return KNZ_ERR_CREATE_COMPRESSOR;
+    }
+    ctx->a1Ready = true;
+    return KNZ_OK;
+}
+
+static int ensure_bwt(knz_ctx* ctx, const int* types, int nt)
+{
+    for (int i = 0; i < nt; i++)
+        if (types[i] == T_BWT && !ctx->ws.bwtReady && !workspace_alloc_bwt(ctx->ws)) {
+            snprintf(ctx->err, sizeof(ctx->err), "out of device memory for the suffix-sort workspace");
+            return KNZ_ERR_CREATE_COMPRESSOR;
+        }
+    return KNZ_OK;
+}
+
 static void launch_forward_stage(knz_ctx* ctx, int type, const StageLaunch& L, cudaStream_t s)
 {
     switch (type) {
@@ -389,9 +423,16 @@ static int encode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const
             snprintf(ctx->err, sizeof(ctx->err), "transform id %d not implemented", types[i]);
             return KNZ_ERR_INVALID_CODEC;
         }
-    if (eType != E_RAW && eType != E_ANS0 && eType != E_HUF) {
+    if (!entropy_supported(eType)) {
         snprintf(ctx->err, sizeof(ctx->err), "entropy id %d not implemented", eType);
         return KNZ_ERR_INVALID_CODEC;
+    }
+    {
+        int rc1 = ensure_ans1(ctx, eType);
+        if (rc1 == KNZ_OK)
+            rc1 = ensure_bwt(ctx, types, nt);
+        if (rc1 != KNZ_OK)
+            return rc1;
     }
     if (nB > ctx->maxBatch || ((uintptr_t)d_in & 15) || (inStride & 15) || ((uintptr_t)d_out & 15) || (outStride & 15))
         return KNZ_ERR_INVALID_PARAM;
@@ -471,6 +512,7 @@ static int encode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const
     E.errFlag = ctx->errFlag;
     E.evK0 = ctx->ev[8];
     E.evK1 = ctx->ev[9];
+    E.a1 = &ctx->a1;
     launch_entropy_encode(E, s, &ctx->launches);
     CK(cudaEventRecord(ctx->ev[4], s));
     CK(cudaMemcpyAsync(ctx->h_err, ctx->errFlag, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
@@ -486,7 +528,7 @@ static int encode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const
     ctx->ms[3] = ms;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]);
     ctx->ms[5] = ms;
-    if (eType == E_ANS0 || eType == E_HUF) {
+    if (eType == E_ANS0 || eType == E_HUF || eType == E_ANS1) {
         cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]);
         ctx->ms[6] = ms;
     }
@@ -721,7 +763,7 @@ extern "C" int knz_compress(knz_ctx* ctx, const char* transform, const char* ent
     u8 hdr[32];
     const int hdrBytes = knz_stream_header(tType, eType, blockSize, n, hdr);
     const i64 nBlocks = (n + blockSize - 1) / blockSize;
-    const i64 streamCap = round_up(n + (n >> 2) + 16 * nBlocks + 65536, 256);
+    const i64 streamCap = round_up(n + (n >> 2) + 16 * nBlocks + 65536 + ((eType == E_ANS1) ? 131072 * (n / ((blockSize < ANS1_CHUNK) ? blockSize : ANS1_CHUNK) + 1) : 0), 256);
     int rc = grow(ctx, &ctx->dStream, &ctx->dStreamCap, streamCap);
     if (rc != KNZ_OK)
         return rc;
@@ -873,8 +915,15 @@ static int decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const
     for (int i = 0; i < nt; i++)
         if (!type_supported(types[i]))
             return KNZ_ERR_INVALID_CODEC;
-    if (eType != E_RAW && eType != E_ANS0 && eType != E_HUF)
+    if (!entropy_supported(eType))
         return KNZ_ERR_INVALID_CODEC;
+    {
+        int rc1 = ensure_ans1(ctx, eType);
+        if (rc1 == KNZ_OK)
+            rc1 = ensure_bwt(ctx, types, nt);
+        if (rc1 != KNZ_OK)
+            return rc1;
+    }
     if (nB > ctx->maxBatch)
         return KNZ_ERR_INVALID_PARAM;
     if (blockSize < 1 || blockSize > ctx->maxBlockSize)
@@ -926,6 +975,7 @@ static int decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const
     D.errFlag = ctx->errFlag;
     D.evK0 = ctx->ev[8];
     D.evK1 = ctx->ev[9];
+    D.a1 = &ctx->a1;
     BufTable bt;
     bt.base[0] = ctx->bufA;
     bt.base[1] = ctx->bufB;
@@ -1069,7 +1119,7 @@ static int decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const
     ctx->ms[3] = ms;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]);
     ctx->ms[5] = ms;
-    if (eType == E_ANS0 || eType == E_HUF) {
+    if (eType == E_ANS0 || eType == E_HUF || eType == E_ANS1) {
         cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]);
         ctx->ms[7] = ms;
     }
@@ -1401,6 +1451,11 @@ static int run_single_stage(knz_ctx* ctx, int type, bool inverse, const u8* in, 
     if (n > ctx->stageCap || cap < 0)
         return KNZ_ERR_BLOCK_SIZE;
     const int devCap = (cap < ctx->stageCap) ? cap : ctx->stageCap; // what a stage buffer slot can hold
+    {
+        const int rcb = ensure_bwt(ctx, &type, 1);
+        if (rcb != KNZ_OK)
+            return rcb;
+    }
     cudaSetDevice(ctx->device);
     cudaStream_t s = ctx->stream;
     CK(cudaMemcpyAsync(ctx->dStageIn, in, (size_t)n, cudaMemcpyHostToDevice, s));
@@ -1495,11 +1550,16 @@ extern "C" int knz_entropy_encode(knz_ctx* ctx, int type, const uint8_t* in, int
     if (!ctx || !in || !out || !outBits || n <= 0)
         return KNZ_ERR_INVALID_PARAM;
     std::lock_guard<std::recursive_mutex> lock_(ctx->mtx);
-    if (type != E_RAW && type != E_ANS0 && type != E_HUF)
+    if (!entropy_supported(type))
         return KNZ_ERR_INVALID_CODEC;
     if ((i64)n + 64 > ctx->bstride)
         return KNZ_ERR_BLOCK_SIZE;
     cudaSetDevice(ctx->device);
+    {
+        const int rc1 = ensure_ans1(ctx, type);
+        if (rc1 != KNZ_OK)
+            return rc1;
+    }
     cudaStream_t s = ctx->stream;
     CK(cudaMemcpyAsync(ctx->dStageIn, in, (size_t)n, cudaMemcpyHostToDevice, s));
     ctx->h_st[0].len = n;
@@ -1528,6 +1588,7 @@ extern "C" int knz_entropy_encode(knz_ctx* ctx, int type, const uint8_t* in, int
     E.outStride = ctx->outStride;
     E.errFlag = ctx->errFlag;
     E.evK0 = E.evK1 = NULL;
+    E.a1 = &ctx->a1;
     launch_entropy_encode(E, s, &ctx->launches);
     CK(cudaMemcpyAsync(ctx->h_err, ctx->errFlag, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(ctx->h_bits, ctx->blockBits, sizeof(u64), cudaMemcpyDeviceToHost, s));
@@ -1553,12 +1614,17 @@ extern "C" int knz_entropy_decode(knz_ctx* ctx, int type, const uint8_t* in, int
     if (!ctx || !in || !out || n <= 0 || inBits < 0)
         return KNZ_ERR_INVALID_PARAM;
     std::lock_guard<std::recursive_mutex> lock_(ctx->mtx);
-    if (type != E_RAW && type != E_ANS0 && type != E_HUF)
+    if (!entropy_supported(type))
         return KNZ_ERR_INVALID_CODEC;
     const i64 nbytes = (inBits + 7) >> 3;
     if ((i64)n + 64 > ctx->bstride || nbytes + 16 > ctx->outStride)
         return KNZ_ERR_BLOCK_SIZE;
     cudaSetDevice(ctx->device);
+    {
+        const int rc1 = ensure_ans1(ctx, type);
+        if (rc1 != KNZ_OK)
+            return rc1;
+    }
     cudaStream_t s = ctx->stream;
     CK(cudaMemsetAsync(ctx->dOut + (nbytes & ~(i64)15), 0, 32, s));
     CK(cudaMemcpyAsync(ctx->dOut, in, (size_t)nbytes, cudaMemcpyHostToDevice, s));
@@ -1583,6 +1649,7 @@ extern "C" int knz_entropy_decode(knz_ctx* ctx, int type, const uint8_t* in, int
     D.dstStride = ctx->bstride;
     D.errFlag = ctx->errFlag;
     D.evK0 = D.evK1 = NULL;
+    D.a1 = &ctx->a1;
     launch_entropy_decode(D, s, &ctx->launches);
     CK(cudaMemcpyAsync(ctx->h_err, ctx->errFlag, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(out, ctx->bufA, (size_t)n, cudaMemcpyDeviceToHost, s));

@@ -1999,15 +1999,27 @@ bool workspace_alloc(Workspace& ws, int maxBlocks, int capN)
     ws.maxBlocks = maxBlocks;
     ws.capN = capN;
     const i64 nb = maxBlocks;
-    const i64 elems = nb * capN;
     const i64 zTiles = (capN + 4095) / 4096 + 1;
-    const i64 sTiles = (capN + RS_TILE - 1) / RS_TILE + 1;
     bool ok = true;
     ws.tileWords = nb * zTiles * 8;
     ok = ok && wsalloc(&ws.tileA, ws.tileWords);
     ok = ok && wsalloc(&ws.tileB, ws.tileWords);
     ws.occWords = nb * zTiles * 512;
     ok = ok && wsalloc(&ws.occ, ws.occWords);
+    ok = ok && wsalloc(&ws.zlen, nb);
+    return ok;
+}
+
+// The suffix sorter's arrays (56 bytes per input byte of a batch) are only allocated by contexts
+// that run a BWT stage: entropy-only pipelines on small blocks keep large batches cheap.
+bool workspace_alloc_bwt(Workspace& ws)
+{
+    if (ws.bwtReady)
+        return true;
+    const i64 nb = ws.maxBlocks;
+    const i64 elems = nb * ws.capN;
+    const i64 sTiles = (ws.capN + RS_TILE - 1) / RS_TILE + 1;
+    bool ok = true;
     ok = ok && wsalloc(&ws.keyA, elems);
     ok = ok && wsalloc(&ws.keyB, elems);
     ok = ok && wsalloc(&ws.valA, elems);
@@ -2032,12 +2044,13 @@ bool workspace_alloc(Workspace& ws, int maxBlocks, int capN)
     ok = ok && wsalloc(&ws.pidx, nb * 8);
     ok = ok && wsalloc(&ws.bwtOk, nb);
     ok = ok && (cudaMallocHost((void**)&ws.h_cnt, sizeof(int) * (size_t)nb) == cudaSuccess);
+    ws.bwtReady = ok;
     return ok;
 }
 
 void workspace_free(Workspace& ws)
 {
-    void* d[] = { ws.tileA, ws.tileB, ws.occ, ws.keyA, ws.keyB, ws.valA, ws.valB, ws.grpA, ws.isa, ws.hist,
+    void* d[] = { ws.tileA, ws.tileB, ws.occ, ws.zlen, ws.keyA, ws.keyB, ws.valA, ws.valB, ws.grpA, ws.isa, ws.hist,
                   ws.digitBase, ws.totals, ws.which, ws.trivial, ws.cnt, ws.cntNext, ws.scanA, ws.pidx, ws.bwtOk,
                   ws.scanB, ws.xkeyA, ws.xkeyB, ws.xvalA, ws.xvalB, ws.whichX, ws.cntX };
     for (size_t i = 0; i < sizeof(d) / sizeof(d[0]); i++)

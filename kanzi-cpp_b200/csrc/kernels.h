@@ -13,6 +13,11 @@
 #define E_RAW 0
 #define E_HUF 1
 #define E_ANS0 5
+#define E_ANS1 8
+
+// order-1 rANS: chunk = 16384 << 8 bytes, logRange 11 (entropy/ANSRangeEncoder.cpp:59-67)
+#define ANS1_CHUNK (16384 << 8)
+#define ANS1_LR 11
 
 #define T_NONE 0
 #define T_BWT 1
@@ -26,6 +31,24 @@
 #define KERR_UNSUPPORTED 3
 #define KERR_INTERNAL 4
 
+// Scratch of the order-1 rANS coder (ans1.cu), allocated on first use of ANS1 by a context.
+struct Ans1Work {
+    int maxBlocks, stageCap, cpb; // cpb = order-1 chunks per block
+    i64 payRegion, payStride, recStride;
+    u32* freq;     // [blocks*cpb][256][256] pair counts (decode: per-context symbol lists)
+    u64* tenc;     // [blocks*cpb][256][256] packed encoder entries
+    u64* rec;      // [blocks][recStride]    every position's encoder entry (pre-mapped records)
+    u8* hdr;       // [blocks*cpb][256][512] context header bit strings
+    u32* hbits;    // [blocks*cpb][256]      their lengths (decode: alphabet sizes)
+    u8* pay;       // [blocks][cpb][payRegion] renormalisation words (backwards) + tail bytes
+    void* trailer; // [blocks*cpb] payload size + final states
+    u64* pieceOff; // [blocks*cpb][258] bit offsets of the pieces of a chunk
+    u32* tdec;     // [blocks*cpb][256][2048] decoder slot tables
+    void* dmeta;   // [blocks*cpb] decoder: payload position, size, initial states
+};
+bool ans1_work_alloc(Ans1Work& W, int maxBlocks, int stageCap);
+void ans1_work_free(Ans1Work& W);
+
 struct EncodeLaunch {
     BufTable bt;
     const BlkState* st; // state after the last transform stage
@@ -37,8 +60,12 @@ struct EncodeLaunch {
     i64 outStride;
     int* errFlag;
     cudaEvent_t evK0, evK1; // optional: bracket the rANS kernel alone (NULL = off)
+    Ans1Work* a1;           // ANS1 only
 };
 void launch_entropy_encode(const EncodeLaunch& L, cudaStream_t s, u64* launches);
+void launch_ans1_encode(const EncodeLaunch& L, cudaStream_t s, u64* launches);
+// zero the output words of every block and write the block headers (shared by all entropy coders)
+void launch_out_prepare_and_header(const EncodeLaunch& L, cudaStream_t s, u64* launches);
 // startBit / endBit are device scalars (may alias): batches chain without a host round trip.
 void launch_stream_assemble(const u8* blockOut, i64 outStride, const u64* blockBits, int nBlocks,
                             const u64* startBit, u64* blockOff, u64* endBit, u8* stream, cudaStream_t s,
@@ -58,8 +85,10 @@ struct DecodeLaunch {
     i64 dstStride;
     int* errFlag;
     cudaEvent_t evK0, evK1; // optional: bracket the rANS decode kernel alone
+    Ans1Work* a1;           // ANS1 only
 };
 void launch_entropy_decode(const DecodeLaunch& L, cudaStream_t s, u64* launches);
+void launch_ans1_decode(const DecodeLaunch& L, cudaStream_t s, u64* launches);
 void launch_huffman_encode_chunks(const EncodeLaunch& L, cudaStream_t s, u64* launches);
 void launch_huffman_decode(const DecodeLaunch& L, cudaStream_t s, u64* launches);
 
@@ -97,6 +126,7 @@ struct Workspace {
     // SBRT per-tile last-two-occurrence tables: [maxBlocks][tiles][256][2]
     u32* occ;
     i64 occWords;
+    u32* zlen;       // [maxBlocks] ZRLT: output length per block (or "refused")
     // suffix sorting
     u64 *keyA, *keyB;   // [maxBlocks * capN]
     u32 *valA, *valB;
@@ -118,9 +148,11 @@ struct Workspace {
     int* cntX;          // [maxBlocks]
     int* pidx;          // [maxBlocks * 8] primary indexes
     int* bwtOk;         // [maxBlocks]
+    bool bwtReady;      // suffix-sort arrays allocated (workspace_alloc_bwt)
 };
 
 bool workspace_alloc(Workspace& ws, int maxBlocks, int capN);
+bool workspace_alloc_bwt(Workspace& ws); // on the first BWT stage of a context
 void workspace_free(Workspace& ws);
 // Copies each block's final bytes to out + b*outStride; a block longer than outCap is not copied
 // and raises KERR_OUT_OVERFLOW (a crafted stream may not write past its destination slot).

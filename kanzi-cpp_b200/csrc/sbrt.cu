@@ -212,7 +212,8 @@ sbrt_rank_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkState*
         return (MODE == 1) ? (int)i : (MODE == 2) ? (int)((i + pc) >> 1) : (int)pc;
     };
     __shared__ u64 s_keys[R_WARPS][256];
-    __shared__ u64 s_ent[R_WARPS][256]; // (q << 32 | pb) by rank, only while the list is built
+    __shared__ u64 s_ent[R_WARPS][256];  // pb = (last access time << 8) | symbol, by rank, while the list is built
+    __shared__ u32 s_entq[R_WARPS][256]; // key q by rank (kept apart: pb needs more than 32 bits from 16 MiB on)
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int b = blockIdx.y;
     const int t = blockIdx.x * R_WARPS + w;
@@ -231,6 +232,7 @@ sbrt_rank_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkState*
     // ---- build the sorted list for this tile: rank(s) = #{u : key_u > key_s}
     u64* keys = s_keys[w];
     u64* ent = s_ent[w];
+    u32* entq = s_entq[w];
     const uint2* o = occ + ((i64)b * maxTiles + t) * 256;
     u64 myKey[8];
     u32 myQ[8], myP[8];
@@ -252,15 +254,16 @@ sbrt_rank_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkState*
             rk[k] += (ku > myKey[k]) ? 1 : 0;
     }
 #pragma unroll
-    for (int k = 0; k < 8; k++)
-        ent[rk[k]] = ((u64)myQ[k] << 32) | ((u64)myP[k] << 8) | (u64)(32 * k + lane);
+    for (int k = 0; k < 8; k++) {
+        ent[rk[k]] = ((u64)myP[k] << 8) | (u64)(32 * k + lane);
+        entq[rk[k]] = myQ[k];
+    }
     __syncwarp();
     RankList<PB> L;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        const u64 e = ent[32 * k + lane];
-        L.q[k] = (int)(e >> 32);
-        L.pb[k] = (PB)(e & 0xFFFFFFFFull);
+        L.q[k] = (int)entq[32 * k + lane];
+        L.pb[k] = (PB)ent[32 * k + lane];
     }
     // ---- replay
     const int end = min(base + S_TILE, n);

@@ -452,7 +452,7 @@ void launch_zrlt_forward(const StageLaunch& L, Workspace& ws, cudaStream_t s, u6
     const int tiles = (L.maxLen + Z_TILE - 1) / Z_TILE;
     ZSum* tileSum = reinterpret_cast<ZSum*>(ws.tileA);
     ZEntry* tileEntry = reinterpret_cast<ZEntry*>(ws.tileB);
-    u32* zlen = ws.scanA;
+    u32* zlen = ws.zlen;
     KLAUNCH(zrlt_fwd_sum_kernel, dim3(tiles, L.nBlocks), Z_THREADS, s, L.bt, L.stIn, maxTiles, tileSum);
     KLAUNCH(zrlt_fold_kernel<false>, (L.nBlocks + 31) / 32, 32, s, L, maxTiles, tileSum, tileEntry, zlen);
     KLAUNCH(zrlt_fwd_emit_kernel, dim3(tiles, L.nBlocks), Z_THREADS, s, L.bt, L.stIn, maxTiles, tileEntry, zlen);
@@ -465,7 +465,7 @@ void launch_zrlt_inverse(const StageLaunch& L, Workspace& ws, cudaStream_t s, u6
     const int tiles = (L.maxLen + Z_TILE - 1) / Z_TILE;
     ZSum* tileSum = reinterpret_cast<ZSum*>(ws.tileA) + (i64)L.wsBlock0 * maxTiles;
     ZEntry* tileEntry = reinterpret_cast<ZEntry*>(ws.tileB) + (i64)L.wsBlock0 * maxTiles;
-    u32* zlen = ws.scanA + L.wsBlock0;
+    u32* zlen = ws.zlen + L.wsBlock0;
     const int bit = 1 << (7 - L.stageIdx);
     KLAUNCH(zrlt_inv_sum_kernel, dim3(tiles, L.nBlocks), Z_THREADS, s, L.bt, L.stIn, bit, maxTiles, tileSum, L.errFlag);
     KLAUNCH(zrlt_fold_kernel<true>, (L.nBlocks + 31) / 32, 32, s, L, maxTiles, tileSum, tileEntry, zlen);

@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "libknzgpu.so")
 
 T_IDS = {"NONE": 0, "BWT": 1, "ZRLT": 6, "MTFT": 7, "RANK": 8}
-E_IDS = {"NONE": 0, "HUFFMAN": 1, "ANS0": 5}
+E_IDS = {"NONE": 0, "HUFFMAN": 1, "ANS0": 5, "ANS1": 8}
 
 
 class KanziGpuError(RuntimeError):
@@ -119,6 +119,8 @@ class Context:
     def compress(self, data, transform="BWT+RANK+ZRLT", entropy="ANS0", block_size=4 << 20, out=None):
         data = np.ascontiguousarray(data, dtype=np.uint8)
         cap = data.size + data.size // 4 + 16 * (data.size // block_size + 1) + 65536
+        if entropy == "ANS1":  # up to 256 context headers (~100 KiB) per order-1 chunk of incompressible data
+            cap += 131072 * (data.size // min(block_size, 4 << 20) + 1)
         if out is None:
             out = np.empty(cap, dtype=np.uint8)
         n = ctypes.c_int64(0)
@@ -144,7 +146,7 @@ class Context:
         for i, b in enumerate(blocks):
             inp[i * stride: i * stride + b.size] = b
             lens[i] = b.size
-        ostride = (block_size + block_size // 4 + 4096 + 255) // 256 * 256
+        ostride = (block_size + block_size // 4 + 4096 + 131072 * (block_size // (4 << 20) + 1) + 255) // 256 * 256
         out = np.zeros(nb * ostride, dtype=np.uint8)
         bits = np.zeros(nb, dtype=np.uint64)
         flags = np.zeros(nb, dtype=np.uint8)
@@ -194,7 +196,7 @@ class Context:
 
     def entropy_encode(self, name, data):
         data = np.ascontiguousarray(data, dtype=np.uint8)
-        out = np.zeros(data.size + data.size // 4 + 8192, dtype=np.uint8)
+        out = np.zeros(data.size + data.size // 4 + 8192 + (140000 if name == "ANS1" else 0), dtype=np.uint8)
         bits = ctypes.c_int64(0)
         self._check(self.lib.knz_entropy_encode(self.h, E_IDS[name], _ptr(data), data.size, _ptr(out), out.size,
                                                 ctypes.byref(bits)))

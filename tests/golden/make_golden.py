@@ -39,6 +39,12 @@ STREAMS = [
     ("text", 1, 16 << 20, "NONE", "HUFFMAN", 4 << 20),  # BASELINE.json configs[0]
     ("compressible", 5, 200000, "BWT+RANK+ZRLT", "HUFFMAN", 65536),
     ("compressible", 2, 64 << 20, "BWT+RANK+ZRLT", "ANS0", 4 << 20),
+    # order-1 rANS (BASELINE.json configs[3])
+    ("text", 1, 70000, "NONE", "ANS1", 65536),
+    ("compressible", 2, 300000, "BWT+RANK+ZRLT", "ANS1", 65536),
+    ("incompressible", 9, 100000, "NONE", "ANS1", 65536),
+    ("compressible", 4, 9 << 20, "NONE", "ANS1", 4 << 20),
+    ("compressible", 4, (9 << 20) + 3, "NONE", "ANS1", 8 << 20),  # two order-1 chunks per block
 ]
 
 
@@ -69,6 +75,9 @@ def main():
         enc, bits = ref.entropy_encode("ANS0", data)
         rec["ans0_hex"] = enc.tobytes().hex()
         rec["ans0_bits"] = int(bits)
+        enc1, bits1 = ref.entropy_encode("ANS1", data)
+        rec["ans1_hex"] = enc1.tobytes().hex()
+        rec["ans1_bits"] = int(bits1)
         for t in ("ZRLT", "RANK", "MTFT"):
             o, fl, ok = ref.sequence_forward(t, data, data.size + 64, data.size + 64)
             rec[t.lower() + "_hex"] = o.tobytes().hex() if fl != 0xFF else None

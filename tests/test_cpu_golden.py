@@ -50,6 +50,8 @@ def test_oracle_stage_vectors(oracle):
             assert pidx[: len(rec["primary"])] == rec["primary"], rec["case"]
         enc, bits = oracle.entropy_encode("ANS0", data)
         assert bits == rec["ans0_bits"] and enc.tobytes().hex() == rec["ans0_hex"], rec["case"]
+        enc, bits = oracle.entropy_encode("ANS1", data)
+        assert bits == rec["ans1_bits"] and enc.tobytes().hex() == rec["ans1_hex"], rec["case"]
         for t in ("ZRLT", "RANK", "MTFT"):
             o, fl = oracle.sequence_forward(t, data, data.size + 64, data.size + 64)
             want = rec[t.lower() + "_hex"]

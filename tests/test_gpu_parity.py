@@ -38,7 +38,7 @@ def _first_diff(a, b):
 @pytest.mark.parametrize("idx", range(len(GOLD["streams"])))
 def test_gpu_stream_matches_golden(gpu, idx):
     rec = GOLD["streams"][idx]
-    if rec["entropy"] not in ("ANS0", "NONE", "HUFFMAN"):
+    if rec["entropy"] not in ("ANS0", "NONE", "HUFFMAN", "ANS1"):
         pytest.skip("entropy codec not on the GPU path yet (covered by the CPU oracle suite)")
     data = synth.GENERATORS[rec["gen"]](rec["size"], rec["seed"])
     assert synth.sha256(data) == rec["input_sha256"]
@@ -52,7 +52,7 @@ def test_gpu_stream_matches_golden(gpu, idx):
     assert back.size == data.size and np.array_equal(back, data)
 
 
-@pytest.mark.parametrize("ename", ["ANS0", "HUFFMAN"])
+@pytest.mark.parametrize("ename", ["ANS0", "HUFFMAN", "ANS1"])
 def test_gpu_entropy_vs_oracle(gpu, oracle, ename):
     for name, data in CASES.items():
         a, abits = gpu.entropy_encode(ename, data)
@@ -95,6 +95,8 @@ def test_gpu_stage_golden_vectors(gpu):
                 assert v == (p - 1) % (1 << (8 * pisz)), (rec["case"], k)
         enc, bits = gpu.entropy_encode("ANS0", data)
         assert bits == rec["ans0_bits"] and enc.tobytes().hex() == rec["ans0_hex"], rec["case"]
+        enc, bits = gpu.entropy_encode("ANS1", data)
+        assert bits == rec["ans1_bits"] and enc.tobytes().hex() == rec["ans1_hex"], rec["case"]
         for t in ("ZRLT", "RANK", "MTFT"):
             want = rec[t.lower() + "_hex"]
             o, applied = gpu.transform_forward(t, data, data.size + 64)
@@ -107,7 +109,7 @@ def test_gpu_stage_golden_vectors(gpu):
 @pytest.mark.parametrize("tname,ename", [("NONE", "ANS0"), ("BWT+RANK+ZRLT", "ANS0"), ("NONE", "NONE"),
                                          ("ZRLT", "ANS0"), ("BWT+MTFT+ZRLT", "ANS0"), ("BWT", "NONE"),
                                          ("RANK+ZRLT", "ANS0"), ("NONE", "HUFFMAN"),
-                                         ("BWT+RANK+ZRLT", "HUFFMAN")])
+                                         ("BWT+RANK+ZRLT", "HUFFMAN"), ("NONE", "ANS1"), ("BWT+RANK+ZRLT", "ANS1")])
 def test_gpu_stream_vs_oracle(gpu, oracle, tname, ename):
     inputs = {
         "comp_600k": synth.synth_compressible(600000, 21),
@@ -220,7 +222,7 @@ def gpu_big():
 
 @pytest.mark.parametrize("bs_mib", [16, 32])
 @pytest.mark.parametrize("tname,ename", [("BWT+RANK+ZRLT", "ANS0"), ("NONE", "HUFFMAN"), ("NONE", "ANS0"),
-                                         ("BWT+MTFT+ZRLT", "HUFFMAN")])
+                                         ("BWT+MTFT+ZRLT", "HUFFMAN"), ("NONE", "ANS1")])
 def test_gpu_large_blocks_vs_reference(gpu_big, tname, ename, bs_mib):
     """16 MiB and 32 MiB blocks against the unmodified reference (prebuilt oracle/_ref)."""
     from oracle.oracle import Ref

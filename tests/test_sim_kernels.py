@@ -26,7 +26,7 @@ def sim():
 CASES = small_cases()
 
 
-@pytest.mark.parametrize("ename", ["ANS0", "HUFFMAN"])
+@pytest.mark.parametrize("ename", ["ANS0", "HUFFMAN", "ANS1"])
 def test_sim_entropy(sim, oracle, ename):
     for name, data in CASES.items():
         a, abits = sim.entropy_encode(ename, data)
@@ -60,7 +60,8 @@ def test_sim_stage_forward_inverse(sim, oracle, tname):
 
 @pytest.mark.parametrize("tname,ename", [("NONE", "ANS0"), ("BWT+RANK+ZRLT", "ANS0"), ("NONE", "NONE"),
                                          ("ZRLT", "ANS0"), ("BWT+MTFT+ZRLT", "ANS0"), ("BWT", "NONE"),
-                                         ("NONE", "HUFFMAN"), ("BWT+RANK+ZRLT", "HUFFMAN")])
+                                         ("NONE", "HUFFMAN"), ("BWT+RANK+ZRLT", "HUFFMAN"), ("NONE", "ANS1"),
+                                         ("ZRLT", "ANS1")])
 def test_sim_stream(sim, oracle, tname, ename):
     inputs = {
         "comp_150k": synth.synth_compressible(150000, 21),

@@ -1,6 +1,6 @@
 """Experiment (not a test): wall-clock of knz_compress / knz_decompress on pinned host buffers."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "kanzi-cpp_b200")]
 import numpy as np, torch
 import synth

@@ -1,7 +1,7 @@
 """Timing probe (not a test): entropy kernels alone on the raw workload (BASELINE config 4
 shape: -t NONE -e {ANS0,HUFFMAN}, 4 MiB blocks) and on the post-transform bytes of config 2."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "kanzi-cpp_b200")]
 import numpy as np, torch
 import synth

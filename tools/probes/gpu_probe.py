@@ -1,6 +1,6 @@
 """Ad-hoc GPU probe (not a test): stage timings of the headline pipeline."""
 import sys, os, time, json
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "kanzi-cpp_b200")]
 import numpy as np
 import synth

@@ -1,7 +1,7 @@
 """Profiling target for ncu (not a test): one warm-up + one measured encode/decode of
 64 x 4 MiB blocks of the headline workload through the device-resident block API."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "kanzi-cpp_b200")]
 import numpy as np, torch
 import synth

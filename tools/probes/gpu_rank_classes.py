@@ -1,6 +1,6 @@
 """Experiment (not a test): RANK-inverse cycles per step by rank class, one 4 MiB block."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "kanzi-cpp_b200")]
 import numpy as np
 from kanzi_b200 import Context

@@ -1,6 +1,6 @@
 """compute-sanitizer target (not a test): small round trips through every kernel family."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "kanzi-cpp_b200")]
 import numpy as np
 import synth

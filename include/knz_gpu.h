@@ -41,9 +41,11 @@ extern "C" {
 #define KNZ_T_ZRLT 6
 #define KNZ_T_MTFT 7
 #define KNZ_T_RANK 8
+#define KNZ_T_SRT 13
 /* Entropy ids: entropy/EntropyEncoderFactory.hpp:37-52 */
 #define KNZ_E_NONE 0
 #define KNZ_E_HUFFMAN 1
+#define KNZ_E_FPAQ 2
 #define KNZ_E_ANS0 5
 #define KNZ_E_ANS1 8
 

@@ -764,6 +764,10 @@ void launch_entropy_encode(const EncodeLaunch& L, cudaStream_t s, u64* launches)
         launch_ans1_encode(L, s, launches);
         return;
     }
+    if (L.eType == E_FPAQ) {
+        launch_fpaq_encode(L, s, launches);
+        return;
+    }
     if (L.eType == E_RAW) {
         KLAUNCH(raw_meta_kernel, (nB + 127) / 128, 128, s, L.st, nB, L.maxChunks, L.hdrBits, L.payBytes, L.payOff);
     } else if (L.eType == E_HUF) {
@@ -1285,6 +1289,10 @@ void launch_entropy_decode(const DecodeLaunch& L, cudaStream_t s, u64* launches)
     }
     if (L.eType == E_ANS1) {
         launch_ans1_decode(L, s, launches);
+        return;
+    }
+    if (L.eType == E_FPAQ) {
+        launch_fpaq_decode(L, s, launches);
         return;
     }
     KLAUNCH(ans0_dec_scan_kernel, L.nBlocks, 32, s, L);

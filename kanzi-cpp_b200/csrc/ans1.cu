@@ -954,8 +954,14 @@ ans1_decode_kernel(DecodeLaunch L, int cpb, const A1DecMeta* __restrict__ meta, 
                 oc[count4 + t] = (u8)a1_rd_bits(p, M.payPos + 16ull * cnt + 8ull * t, 8);
         }
     }
+    // A payload that does not match its tables is reported through the second flag word: the other
+    // chunks of the batch still decode (the header walk's flag, word 0, stops everything because chunk
+    // positions derived from a bad header are not trustworthy).  The reference produces such streams
+    // itself: when EntropyUtils::normalizeFrequencies leaves a residual (EntropyUtils.cpp:243) the
+    // decoder infers a different first frequency than the encoder used (ANSRangeDecoder.cpp:150-158)
+    // and ANSRangeDecoder::decodeChunk returns false -- reproduced here, block for block.
     if (bad)
-        atomicExch(L.errFlag, KERR_BAD_STREAM);
+        atomicExch(L.errFlag + 1, KERR_BAD_STREAM);
 }
 
 void launch_ans1_decode(const DecodeLaunch& L, cudaStream_t s, u64* launches)

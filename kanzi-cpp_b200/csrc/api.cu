@@ -56,6 +56,8 @@ struct knz_ctx {
     Workspace ws;
     Ans1Work a1; // order-1 rANS scratch, allocated on the first use of ANS1
     bool a1Ready;
+    SrtWork srt; // SRT scratch, allocated on the first SRT stage
+    bool srtReady;
     // pinned host mirrors
     BlkState* h_st;
     int *h_capEven, *h_capOdd, *h_err, *h_preLen;
@@ -85,11 +87,18 @@ static int split_types(u64 tType, int* types)
     return n;
 }
 
-static bool entropy_supported(int e) { return e == E_RAW || e == E_ANS0 || e == E_HUF || e == E_ANS1; }
+static bool entropy_supported(int e)
+{
+    return e == E_RAW || e == E_ANS0 || e == E_HUF || e == E_ANS1 || e == E_FPAQ;
+}
 
-static bool type_supported(int t) { return t == T_NONE || t == T_BWT || t == T_ZRLT || t == T_MTFT || t == T_RANK; }
+static bool type_supported(int t)
+{
+    return t == T_NONE || t == T_BWT || t == T_ZRLT || t == T_MTFT || t == T_RANK || t == T_SRT;
+}
 
-static int stage_max_len(int t, int n) { return (t == T_BWT) ? n + 33 : n; }
+// Transform<T>::getMaxEncodedLength: BWTBlockCodec n + 33, SRT n + 1024 (transform/SRT.hpp:38)
+static int stage_max_len(int t, int n) { return (t == T_BWT) ? n + 33 : (t == T_SRT) ? n + 1024 : n; }
 
 static int required_size(const int* types, int nt, int n)
 {
@@ -123,6 +132,8 @@ extern "C" uint64_t knz_transform_type(const char* name)
             t = T_MTFT;
         else if (len == 4 && !strncmp(p, "RANK", 4))
             t = T_RANK;
+        else if (len == 3 && !strncmp(p, "SRT", 3))
+            t = T_SRT;
         if (t < 0 || ++n > 8)
             return (uint64_t)-1;
         if (t != T_NONE) {
@@ -148,6 +159,8 @@ extern "C" int knz_entropy_type(const char* name)
         return E_HUF;
     if (!strcmp(name, "ANS1"))
         return E_ANS1;
+    if (!strcmp(name, "FPAQ"))
+        return E_FPAQ;
     return -1;
 }
 
@@ -190,9 +203,9 @@ extern "C" int knz_create(int device, int maxBlockSize, int maxBatchBlocks, knz_
         const char* g = getenv("KNZ_DEC_GROUPS");
         ctx->decBwtGroups = (g && atoi(g) > 0) ? atoi(g) : 2; // 2: the per-launch latency of the node ranking outweighs more overlap
     }
-    // a block's output: the block, 25 % expansion room, and the 256 context headers of every order-1
+    // a block's output: the largest post-transform block, 25 % expansion room, and the 256 context headers of every order-1
     // rANS chunk (<= 401 bytes each) -- incompressible data under ANS1 costs up to ~100 KiB per chunk
-    ctx->outStride = round_up((i64)maxBlockSize + (maxBlockSize >> 2) + 4096 + 131072 * (i64)((maxBlockSize >> 22) + 1), 256);
+    ctx->outStride = round_up(refCap + (refCap >> 2) + 4096 + 131072 * (i64)((maxBlockSize >> 22) + 1), 256);
     ctx->maxChunks = (int)((ctx->bstride + ANS_CHUNK - 1) / ANS_CHUNK);
     bool ok = true;
 #define A(call) ok = ok && ((call) == cudaSuccess)
@@ -268,6 +281,8 @@ extern "C" void knz_destroy(knz_ctx* ctx)
     workspace_free(ctx->ws);
     if (ctx->a1Ready)
         ans1_work_free(ctx->a1);
+    if (ctx->srtReady)
+        srt_work_free(ctx->srt);
     void* dev[] = { ctx->bufA, ctx->bufB, ctx->dStageIn, ctx->dOut, ctx->st, ctx->capEven, ctx->capOdd, ctx->slots,
                     ctx->hdrBits, ctx->payBytes, ctx->payOff, ctx->chunkOff, ctx->chunkPos, ctx->blockBits,
                     ctx->blockOff, ctx->streamPos, ctx->dInBits, ctx->dPayStart, ctx->dPreLen, ctx->errFlag,
@@ -339,7 +354,7 @@ static int map_kerr(knz_ctx* ctx, int kerr)
 
 static void add_stage_time(knz_ctx* ctx, int t, float ms)
 {
-    const int slot = (t == T_BWT) ? 0 : (t == T_RANK || t == T_MTFT) ? 1 : (t == T_ZRLT) ? 2 : 5;
+    const int slot = (t == T_BWT) ? 0 : (t == T_RANK || t == T_MTFT || t == T_SRT) ? 1 : (t == T_ZRLT) ? 2 : 5;
     if (slot < 5)
         ctx->ms[slot] += ms;
 }
@@ -360,11 +375,19 @@ static int ensure_ans1(knz_ctx* ctx, int eType)
 
 static int ensure_bwt(knz_ctx* ctx, const int* types, int nt)
 {
-    for (int i = 0; i < nt; i++)
+    for (int i = 0; i < nt; i++) {
         if (types[i] == T_BWT && !ctx->ws.bwtReady && !workspace_alloc_bwt(ctx->ws)) {
             snprintf(ctx->err, sizeof(ctx->err), "out of device memory for the suffix-sort workspace");
             return KNZ_ERR_CREATE_COMPRESSOR;
         }
+        if (types[i] == T_SRT && !ctx->srtReady) {
+            if (!srt_work_alloc(ctx->srt, ctx->maxBatch, (int)ctx->bstride)) {
+                snprintf(ctx->err, sizeof(ctx->err), "out of device memory for the SRT workspace");
+                return KNZ_ERR_CREATE_COMPRESSOR;
+            }
+            ctx->srtReady = true;
+        }
+    }
     return KNZ_OK;
 }
 
@@ -386,6 +409,9 @@ static void launch_forward_stage(knz_ctx* ctx, int type, const StageLaunch& L, c
     case T_RANK:
         launch_sbrt_forward(L, 2, ctx->ws, s, &ctx->launches);
         break;
+    case T_SRT:
+        launch_srt_forward(L, ctx->ws, ctx->srt, s, &ctx->launches);
+        break;
     }
 }
 
@@ -406,6 +432,9 @@ static void launch_inverse_stage(knz_ctx* ctx, int type, const StageLaunch& L, c
         break;
     case T_RANK:
         launch_sbrt_inverse(L, 2, ctx->ws, s, &ctx->launches);
+        break;
+    case T_SRT:
+        launch_srt_inverse(L, s, &ctx->launches);
         break;
     }
 }
@@ -528,14 +557,14 @@ static int encode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const
     ctx->ms[3] = ms;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]);
     ctx->ms[5] = ms;
-    if (eType == E_ANS0 || eType == E_HUF || eType == E_ANS1) {
+    if (eType != E_RAW) {
         cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]);
         ctx->ms[6] = ms;
     }
     if (h_flags)
         for (int b = 0; b < nB; b++)
             h_flags[b] = (u8)ctx->h_st[b].flags;
-    return map_kerr(ctx, ctx->h_err[0]);
+    return map_kerr(ctx, ctx->h_err[0] ? ctx->h_err[0] : ctx->h_err[1]);
 }
 
 extern "C" int knz_encode_blocks_dev(knz_ctx* ctx, uint64_t tType, int eType, int blockSize, const uint8_t* d_in,
@@ -763,7 +792,13 @@ extern "C" int knz_compress(knz_ctx* ctx, const char* transform, const char* ent
     u8 hdr[32];
     const int hdrBytes = knz_stream_header(tType, eType, blockSize, n, hdr);
     const i64 nBlocks = (n + blockSize - 1) / blockSize;
-    const i64 streamCap = round_up(n + (n >> 2) + 16 * nBlocks + 65536 + ((eType == E_ANS1) ? 131072 * (n / ((blockSize < ANS1_CHUNK) ? blockSize : ANS1_CHUNK) + 1) : 0), 256);
+    // Worst case per block: a transform sequence may legally expand a block up to the reference's task
+    // buffer, max(bs + bs/8, 256 KiB) (ZRLT at odd swap parity on 0xFF-heavy data); the entropy stage adds at
+    // most 25 % plus, under ANS1, the context headers of every order-1 chunk.
+    const i64 refCapBlk = ((i64)blockSize + (blockSize >> 3) > 262144) ? (i64)blockSize + (blockSize >> 3) : 262144;
+    const i64 worstBlk = ((2 * (i64)blockSize < refCapBlk) ? 2 * (i64)blockSize : refCapBlk);
+    const i64 perBlk = worstBlk + (worstBlk >> 2) + 1024 + ((eType == E_ANS1) ? 131072 * (i64)((blockSize >> 22) + 1) : 0);
+    const i64 streamCap = round_up(nBlocks * perBlk + 65536, 256);
     int rc = grow(ctx, &ctx->dStream, &ctx->dStreamCap, streamCap);
     if (rc != KNZ_OK)
         return rc;
@@ -1051,7 +1086,7 @@ static int decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const
         ctx->ms[5] = msT; // per-stage times are not separable when the groups overlap
         for (int b = 0; b < nB; b++)
             h_outLens[b] = ctx->h_st[b].len;
-        return map_kerr(ctx, ctx->h_err[0]);
+        return map_kerr(ctx, ctx->h_err[0] ? ctx->h_err[0] : ctx->h_err[1]);
     }
 
     launch_entropy_decode(D, s, &ctx->launches);
@@ -1119,13 +1154,13 @@ static int decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const
     ctx->ms[3] = ms;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]);
     ctx->ms[5] = ms;
-    if (eType == E_ANS0 || eType == E_HUF || eType == E_ANS1) {
+    if (eType != E_RAW) {
         cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]);
         ctx->ms[7] = ms;
     }
     for (int b = 0; b < nB; b++)
         h_outLens[b] = ctx->h_st[b].len;
-    return map_kerr(ctx, ctx->h_err[0]);
+    return map_kerr(ctx, ctx->h_err[0] ? ctx->h_err[0] : ctx->h_err[1]);
 }
 
 // Parse one block's private header (mode byte, [skip flags], length) at r.pos.
@@ -1484,23 +1519,10 @@ static int run_single_stage(knz_ctx* ctx, int type, bool inverse, const u8* in, 
     L.errFlag = ctx->errFlag;
     L.wsBlock0 = 0;
     CK(cudaEventRecord(ctx->ev[1], s));
-    switch (type) {
-    case T_NONE:
-        launch_none_forward(L, s, &ctx->launches);
-        break;
-    case T_BWT:
-        inverse ? launch_bwt_inverse(L, ctx->ws, s, &ctx->launches) : launch_bwt_forward(L, ctx->ws, s, &ctx->launches);
-        break;
-    case T_ZRLT:
-        inverse ? launch_zrlt_inverse(L, ctx->ws, s, &ctx->launches)
-                : launch_zrlt_forward(L, ctx->ws, s, &ctx->launches);
-        break;
-    case T_MTFT:
-    case T_RANK:
-        inverse ? launch_sbrt_inverse(L, type == T_MTFT ? 1 : 2, ctx->ws, s, &ctx->launches)
-                : launch_sbrt_forward(L, type == T_MTFT ? 1 : 2, ctx->ws, s, &ctx->launches);
-        break;
-    }
+    if (inverse)
+        launch_inverse_stage(ctx, type, L, s);
+    else
+        launch_forward_stage(ctx, type, L, s);
     CK(cudaEventRecord(ctx->ev[2], s));
     CK(cudaMemcpyAsync(ctx->h_err, ctx->errFlag, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(ctx->h_st, L.stOut, sizeof(BlkState), cudaMemcpyDeviceToHost, s));
@@ -1517,7 +1539,7 @@ static int run_single_stage(knz_ctx* ctx, int type, bool inverse, const u8* in, 
     if (ctx->h_err[0] != 0) {
         if (inverse && ctx->h_err[0] == KERR_BAD_STREAM)
             return KNZ_OK; // inverse() returns false on malformed input: applied stays 0
-        return map_kerr(ctx, ctx->h_err[0]);
+        return map_kerr(ctx, ctx->h_err[0] ? ctx->h_err[0] : ctx->h_err[1]);
     }
     const BlkState r = ctx->h_st[0];
     if (r.swaps == 0)
@@ -1595,7 +1617,7 @@ extern "C" int knz_entropy_encode(knz_ctx* ctx, int type, const uint8_t* in, int
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
     if (ctx->h_err[0])
-        return map_kerr(ctx, ctx->h_err[0]);
+        return map_kerr(ctx, ctx->h_err[0] ? ctx->h_err[0] : ctx->h_err[1]);
     // strip the block header the block-level path put in front (mode + length bytes)
     const int dataSize = (n < 256) ? 1 : (ilog2_u32((u32)n) >> 3) + 1;
     const int hdr = 1 + dataSize;
@@ -1655,5 +1677,5 @@ extern "C" int knz_entropy_decode(knz_ctx* ctx, int type, const uint8_t* in, int
     CK(cudaMemcpyAsync(out, ctx->bufA, (size_t)n, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
-    return map_kerr(ctx, ctx->h_err[0]);
+    return map_kerr(ctx, ctx->h_err[0] ? ctx->h_err[0] : ctx->h_err[1]);
 }

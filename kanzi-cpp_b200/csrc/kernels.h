@@ -12,6 +12,7 @@
 
 #define E_RAW 0
 #define E_HUF 1
+#define E_FPAQ 2
 #define E_ANS0 5
 #define E_ANS1 8
 
@@ -24,6 +25,7 @@
 #define T_ZRLT 6
 #define T_MTFT 7
 #define T_RANK 8
+#define T_SRT 13
 
 // device-side error flags (first one wins)
 #define KERR_OUT_OVERFLOW 1
@@ -64,6 +66,7 @@ struct EncodeLaunch {
 };
 void launch_entropy_encode(const EncodeLaunch& L, cudaStream_t s, u64* launches);
 void launch_ans1_encode(const EncodeLaunch& L, cudaStream_t s, u64* launches);
+void launch_fpaq_encode(const EncodeLaunch& L, cudaStream_t s, u64* launches);
 // zero the output words of every block and write the block headers (shared by all entropy coders)
 void launch_out_prepare_and_header(const EncodeLaunch& L, cudaStream_t s, u64* launches);
 // startBit / endBit are device scalars (may alias): batches chain without a host round trip.
@@ -89,6 +92,7 @@ struct DecodeLaunch {
 };
 void launch_entropy_decode(const DecodeLaunch& L, cudaStream_t s, u64* launches);
 void launch_ans1_decode(const DecodeLaunch& L, cudaStream_t s, u64* launches);
+void launch_fpaq_decode(const DecodeLaunch& L, cudaStream_t s, u64* launches);
 void launch_huffman_encode_chunks(const EncodeLaunch& L, cudaStream_t s, u64* launches);
 void launch_huffman_decode(const DecodeLaunch& L, cudaStream_t s, u64* launches);
 
@@ -112,6 +116,25 @@ void launch_zrlt_forward(const StageLaunch& L, Workspace& ws, cudaStream_t s, u6
 void launch_zrlt_inverse(const StageLaunch& L, Workspace& ws, cudaStream_t s, u64* launches);
 void launch_sbrt_forward(const StageLaunch& L, int mode, Workspace& ws, cudaStream_t s, u64* launches);
 void launch_sbrt_inverse(const StageLaunch& L, int mode, Workspace& ws, cudaStream_t s, u64* launches);
+// MTFT / RANK ranks of nBlocks buffers without the stage bookkeeping (stIn[b].len bytes from
+// bt.base[0] to bt.base[1]; blocks with stOut[b].swaps == stIn[b].swaps are left alone): SRT's ranks
+// are the MTFT ranks of the block relabelled by first appearance.
+void launch_sbrt_rank_only(const BufTable& bt, const BlkState* stIn, const BlkState* stOut, int nBlocks, int maxLen,
+                           int mode, Workspace& ws, cudaStream_t s, u64* launches);
+// Sorted Rank Transform scratch (srt.cu), allocated on the first SRT stage of a context.
+struct SrtWork {
+    u32* cntT;       // [blocks][tiles][256] per-tile symbol counts -> exclusive prefix over tiles
+    u32* firstT;     // [blocks][tiles][256] first position of each symbol in the tile
+    u8* relabel;     // [blocks][256] symbol -> first-appearance index
+    u32* bucketBase; // [blocks][256] header size + bucket start of each symbol
+    BlkState *fakeIn, *fakeOut; // states handed to the rank kernels
+    u8 *tmp1, *tmp2; // relabelled block, its MTFT ranks
+    i64 tmpStride;
+};
+bool srt_work_alloc(SrtWork& W, int maxBlocks, int capN);
+void srt_work_free(SrtWork& W);
+void launch_srt_forward(const StageLaunch& L, Workspace& ws, SrtWork& W, cudaStream_t s, u64* launches);
+void launch_srt_inverse(const StageLaunch& L, cudaStream_t s, u64* launches);
 void launch_bwt_forward(const StageLaunch& L, Workspace& ws, cudaStream_t s, u64* launches);
 void launch_bwt_inverse(const StageLaunch& L, Workspace& ws, cudaStream_t s, u64* launches);
 

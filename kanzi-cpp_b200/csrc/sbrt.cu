@@ -839,28 +839,35 @@ sbrt_rank_fast_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkS
     }
 }
 
-void launch_sbrt_forward(const StageLaunch& L, int mode, Workspace& ws, cudaStream_t s, u64* launches)
+void launch_sbrt_rank_only(const BufTable& bt, const BlkState* stIn, const BlkState* stOut, int nBlocks, int maxLen,
+                           int mode, Workspace& ws, cudaStream_t s, u64* launches)
 {
     const int maxTiles = (ws.capN + S_TILE - 1) / S_TILE;
-    const int tiles = (L.maxLen + S_TILE - 1) / S_TILE;
+    const int tiles = (maxLen + S_TILE - 1) / S_TILE;
     uint2* occ = reinterpret_cast<uint2*>(ws.occ);
-    KLAUNCH(sbrt_decide_kernel, (L.nBlocks + 31) / 32, 32, s, L, 0);
-    KLAUNCH(sbrt_occ_kernel, dim3(tiles, L.nBlocks), 256, s, L.bt, L.stIn, L.stOut, maxTiles, occ);
-    KLAUNCH(sbrt_fold_kernel, L.nBlocks, 256, s, L.stIn, L.stOut, maxTiles, occ);
-    const dim3 rg((tiles + R_WARPS - 1) / R_WARPS, L.nBlocks);
-    const bool small = L.maxLen < (1 << 24);
+    KLAUNCH(sbrt_occ_kernel, dim3(tiles, nBlocks), 256, s, bt, stIn, stOut, maxTiles, occ);
+    KLAUNCH(sbrt_fold_kernel, nBlocks, 256, s, stIn, stOut, maxTiles, occ);
+    const dim3 rg((tiles + R_WARPS - 1) / R_WARPS, nBlocks);
+    const bool small = maxLen < (1 << 24);
     if (mode == 1) {
         if (small)
-            KLAUNCH((sbrt_rank_fast_kernel<1>), rg, R_WARPS * 32, s, L.bt, L.stIn, L.stOut, maxTiles, occ);
+            KLAUNCH((sbrt_rank_fast_kernel<1>), rg, R_WARPS * 32, s, bt, stIn, stOut, maxTiles, occ);
         else
-            KLAUNCH((sbrt_rank_kernel<u64, 1>), rg, R_WARPS * 32, s, L.bt, L.stIn, L.stOut, maxTiles, occ);
+            KLAUNCH((sbrt_rank_kernel<u64, 1>), rg, R_WARPS * 32, s, bt, stIn, stOut, maxTiles, occ);
     } else {
         if (small)
-            KLAUNCH((sbrt_rank_fast_kernel<2>), rg, R_WARPS * 32, s, L.bt, L.stIn, L.stOut, maxTiles, occ);
+            KLAUNCH((sbrt_rank_fast_kernel<2>), rg, R_WARPS * 32, s, bt, stIn, stOut, maxTiles, occ);
         else
-            KLAUNCH((sbrt_rank_kernel<u64, 2>), rg, R_WARPS * 32, s, L.bt, L.stIn, L.stOut, maxTiles, occ);
+            KLAUNCH((sbrt_rank_kernel<u64, 2>), rg, R_WARPS * 32, s, bt, stIn, stOut, maxTiles, occ);
     }
-    *launches += 4;
+    *launches += 3;
+}
+
+void launch_sbrt_forward(const StageLaunch& L, int mode, Workspace& ws, cudaStream_t s, u64* launches)
+{
+    KLAUNCH(sbrt_decide_kernel, (L.nBlocks + 31) / 32, 32, s, L, 0);
+    *launches += 1;
+    launch_sbrt_rank_only(L.bt, L.stIn, L.stOut, L.nBlocks, L.maxLen, mode, ws, s, launches);
 }
 
 void launch_sbrt_inverse(const StageLaunch& L, int mode, Workspace& ws, cudaStream_t s, u64* launches)

@@ -16,8 +16,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "libknzgpu.so")
 
-T_IDS = {"NONE": 0, "BWT": 1, "ZRLT": 6, "MTFT": 7, "RANK": 8}
-E_IDS = {"NONE": 0, "HUFFMAN": 1, "ANS0": 5, "ANS1": 8}
+T_IDS = {"NONE": 0, "BWT": 1, "ZRLT": 6, "MTFT": 7, "RANK": 8, "SRT": 13}
+E_IDS = {"NONE": 0, "HUFFMAN": 1, "FPAQ": 2, "ANS0": 5, "ANS1": 8}
 
 
 class KanziGpuError(RuntimeError):
@@ -118,9 +118,10 @@ class Context:
     # ---- stream level (CompressedOutputStream write+close / CompressedInputStream read)
     def compress(self, data, transform="BWT+RANK+ZRLT", entropy="ANS0", block_size=4 << 20, out=None):
         data = np.ascontiguousarray(data, dtype=np.uint8)
-        cap = data.size + data.size // 4 + 16 * (data.size // block_size + 1) + 65536
-        if entropy == "ANS1":  # up to 256 context headers (~100 KiB) per order-1 chunk of incompressible data
-            cap += 131072 * (data.size // min(block_size, 4 << 20) + 1)
+        # worst case: every block expanded 2x by a transform stage, 25 % by the entropy stage, plus the
+        # ANS1 context headers (see knz_compress); untouched pages of the buffer cost nothing
+        nblk = data.size // block_size + 1
+        cap = 2 * data.size + data.size // 2 + nblk * (1024 + (131072 * (block_size // (4 << 20) + 1) if entropy == "ANS1" else 0)) + 65536
         if out is None:
             out = np.empty(cap, dtype=np.uint8)
         n = ctypes.c_int64(0)
@@ -179,7 +180,7 @@ class Context:
     # ---- stage level (Transform<byte>::forward/inverse, EntropyEncoder::encode, EntropyDecoder::decode)
     def transform_forward(self, name, data, cap=None):
         data = np.ascontiguousarray(data, dtype=np.uint8)
-        cap = data.size + 64 if cap is None else cap
+        cap = data.size + (1088 if name == "SRT" else 64) if cap is None else cap
         out = np.zeros(cap + 64, dtype=np.uint8)
         ol, ap = ctypes.c_int(0), ctypes.c_int(0)
         self._check(self.lib.knz_transform_forward(self.h, T_IDS[name], _ptr(data), data.size, _ptr(out), cap,

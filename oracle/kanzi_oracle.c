@@ -20,6 +20,7 @@
 #include <string.h>
 
 typedef uint8_t u8;
+typedef uint16_t u16;
 typedef uint32_t u32;
 typedef uint64_t u64;
 typedef int64_t i64;
@@ -1405,13 +1406,172 @@ static int bwtcodec_inverse(const u8* in, int n, u8* out, int cap, int* outLen)
     return 1;
 }
 
+
+/* ------------------------------------------------------------------ SRT
+ * transform/SRT.cpp:22-109 forward, :111-204 inverse, :206-244 preprocess,
+ * :246-277 encodeHeader, :279-305 decodeHeader.  Sorted Rank Transform: classic
+ * move-to-front whose list starts in order of first appearance, every rank written
+ * into the bucket of its own symbol (buckets: frequency descending, symbol
+ * ascending), behind a header of 256 varint frequencies.                       */
+static int srt_preprocess(const u32* freqs, u8* symbols)
+{
+    int nb = 0;
+    for (int i = 0; i < 256; i++)
+        if (freqs[i] != 0)
+            symbols[nb++] = (u8)i;
+    int h = 4;
+    while (h < nb)
+        h = h * 3 + 1;
+    do {
+        h /= 3;
+        for (int i = h; i < nb; i++) {
+            const u8 t = symbols[i];
+            int b;
+            for (b = i - h; b >= 0; b -= h) {
+                const int val = (int)(freqs[symbols[b]] - freqs[t]);
+                if ((val >= 0) && ((val != 0) || (t >= symbols[b])))
+                    break;
+                symbols[b + h] = symbols[b];
+            }
+            symbols[b + h] = t;
+        }
+    } while (h != 1);
+    return nb;
+}
+
+static int srt_forward(const u8* src, int length, u8* out, int cap, int* outLen)
+{
+    if (cap < length + 1024) /* getMaxEncodedLength, SRT.hpp:38 */
+        return 0;
+    u32 freqs[256] = { 0 };
+    u8 s2r[256] = { 0 }, r2s[256] = { 0 };
+    for (int i = 0, b = 0; i < length;) {
+        const u8 c = src[i];
+        int j = i + 1;
+        while ((j < length) && (src[j] == c))
+            j++;
+        if (freqs[c] == 0) {
+            r2s[b] = c;
+            s2r[c] = (u8)b;
+            b++;
+        }
+        freqs[c] += (u32)(j - i);
+        i = j;
+    }
+    u8 symbols[256];
+    int buckets[256] = { 0 };
+    const int nb = srt_preprocess(freqs, symbols);
+    for (int i = 0, pos = 0; i < nb; i++) {
+        buckets[symbols[i]] = pos;
+        pos += (int)freqs[symbols[i]];
+    }
+    int hdr = 0;
+    for (int i = 0; i < 256; i++) {
+        u32 f = freqs[i];
+        for (int k = 0; k < 4 && f >= 128; k++) {
+            out[hdr++] = (u8)(0x80 | f);
+            f >>= 7;
+        }
+        out[hdr++] = (u8)f;
+    }
+    u8* dst = out + hdr;
+    for (int i = 0; i < length;) {
+        const u8 c = src[i];
+        int r = s2r[c];
+        int p = buckets[c];
+        dst[p++] = (u8)r;
+        if (r != 0) {
+            do {
+                const u8 t = r2s[r - 1];
+                r2s[r] = t;
+                s2r[t] = (u8)r;
+                r--;
+            } while (r != 0);
+            r2s[0] = c;
+            s2r[c] = 0;
+        }
+        i++;
+        while ((i < length) && (src[i] == c)) {
+            dst[p++] = 0;
+            i++;
+        }
+        buckets[c] = p;
+    }
+    *outLen = length + hdr;
+    return 1;
+}
+
+static int srt_inverse(const u8* in, int length, u8* dst, int cap, int* outLen)
+{
+    if (length < 256)
+        return 0;
+    u32 freqs[256] = { 0 };
+    int hdr = 0;
+    for (int i = 0; i < 256; i++) {
+        u32 res = 0;
+        int shift = 0;
+        for (int j = 0; j < 5; j++) {
+            if (hdr >= length)
+                return 0;
+            const u32 val = in[hdr++];
+            res |= (val & 0x7F) << shift;
+            if ((val & 0x80) == 0)
+                break;
+            if (j == 4)
+                return 0;
+            shift += 7;
+        }
+        freqs[i] = res;
+    }
+    length -= hdr;
+    if (length < 0 || length > cap)
+        return 0;
+    const u8* src = in + hdr;
+    u8 symbols[256] = { 0 };
+    int nb = srt_preprocess(freqs, symbols);
+    int buckets[256] = { 0 }, ends[256] = { 0 };
+    u8 r2s[256] = { 0 };
+    for (int i = 0, pos = 0; i < nb; i++) {
+        const u8 c = symbols[i];
+        if (pos < 0 || pos >= length)
+            return 0;
+        r2s[src[pos]] = c;
+        buckets[c] = pos + 1;
+        pos += (int)freqs[c];
+        ends[c] = pos;
+    }
+    u8 c = r2s[0];
+    for (int i = 0; i < length; i++) {
+        dst[i] = c;
+        if (buckets[c] < ends[c]) {
+            if (buckets[c] >= length)
+                return 0; /* the reference would read past the block here */
+            const u8 r = src[buckets[c]++];
+            if (r == 0)
+                continue;
+            memmove(&r2s[0], &r2s[1], r);
+            r2s[r] = c;
+            c = r2s[0];
+        } else {
+            if (nb == 1)
+                continue;
+            nb--;
+            memmove(&r2s[0], &r2s[1], (size_t)nb);
+            c = r2s[0];
+        }
+    }
+    *outLen = length;
+    return 1;
+}
+
 /* ------------------------------------------------------------------ sequence
  * transform ids: transform/TransformFactory.hpp:49-73.                       */
-enum { T_NONE = 0, T_BWT = 1, T_ZRLT = 6, T_MTFT = 7, T_RANK = 8 };
+enum { T_NONE = 0, T_BWT = 1, T_ZRLT = 6, T_MTFT = 7, T_RANK = 8, T_SRT = 13 };
 
 static int stage_max_len(int t, int n) /* getMaxEncodedLength of each stage */
 {
-    return (t == T_BWT) ? n + 33 : n; /* BWTBlockCodec.hpp:47-50; others srcLen */
+    /* BWTBlockCodec.hpp:47-50 n + 33; SRT.hpp:38 n + 1024; others srcLen */
+    return (t == T_BWT) ? n + 33 : (t == T_SRT) ? n + 1024 : n;
 }
 
 static int stage_forward(int t, const u8* in, int n, u8* out, int cap, int* outLen)
@@ -1434,6 +1594,8 @@ static int stage_forward(int t, const u8* in, int n, u8* out, int cap, int* outL
         sbrt_forward(in, n, out, (t == T_MTFT) ? 1 : 2);
         *outLen = n;
         return 1;
+    case T_SRT:
+        return srt_forward(in, n, out, cap, outLen);
     default:
         return -1;
     }
@@ -1459,6 +1621,8 @@ static int stage_inverse(int t, const u8* in, int n, u8* out, int cap, int* outL
         sbrt_inverse(in, n, out, (t == T_MTFT) ? 1 : 2);
         *outLen = n;
         return 1;
+    case T_SRT:
+        return srt_inverse(in, n, out, cap, outLen);
     default:
         return -1;
     }
@@ -1591,9 +1755,134 @@ static int sequence_inverse(u64 ttype, int skipFlags, const u8* in, int n, u8* o
     return ok;
 }
 
+
+/* ------------------------------------------------------------------ FPAQ
+ * entropy/FPAQEncoder.cpp:58-103 encode, FPAQEncoder.hpp:72-94 encodeBit/flush,
+ * entropy/FPAQDecoder.cpp:61-120 decode, FPAQDecoder.hpp:74-118 decodeBit/read.
+ * Binary arithmetic coder, 56-bit interval, 4 x 256 adaptive 16-bit probabilities
+ * (row = top two bits of the previous byte, restarted at 0 for every 4 MiB chunk;
+ * probabilities and the interval persist across the chunks of a block).  Per
+ * chunk: varint byte count, the flushed 32-bit words, then (between chunks and at
+ * dispose) 56 bits of low | 0xFFFFFF.                                           */
+#define FPAQ_TOP 0x00FFFFFFFFFFFFFFull
+#define FPAQ_CHUNK (4u << 20)
+static void fpaq_encode(BitW* w, const u8* block, u32 count)
+{
+    u64 low = 0, high = FPAQ_TOP;
+    u16 probs[4][256];
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 256; j++)
+            probs[i][j] = 32768;
+    u8* buf = (u8*)malloc((size_t)FPAQ_CHUNK + (FPAQ_CHUNK >> 3) + 1024);
+    u32 start = 0;
+    while (start < count) {
+        const u32 chunk = (FPAQ_CHUNK < count - start) ? FPAQ_CHUNK : count - start;
+        u32 idx = 0;
+        u16* p = probs[0];
+        for (u32 i = start; i < start + chunk; i++) {
+            const int val = block[i];
+            const int bits = val + 256;
+            for (int k = 7; k >= 0; k--) {
+                u16* pr = &p[(k == 7) ? 1 : (bits >> (k + 1))];
+                const int bit = (val >> k) & 1;
+                const u64 split = (((high - low) >> 8) * (u64)(*pr)) >> 8;
+                if (bit == 0) {
+                    low = low + split + 1;
+                    *pr -= (u16)(*pr >> 6);
+                } else {
+                    high = low + split;
+                    *pr -= (u16)(((int)*pr - 65536 + 64) >> 6);
+                }
+                if (((low ^ high) >> 24) == 0) {
+                    const u32 v = (u32)(high >> 24);
+                    buf[idx++] = (u8)(v >> 24);
+                    buf[idx++] = (u8)(v >> 16);
+                    buf[idx++] = (u8)(v >> 8);
+                    buf[idx++] = (u8)v;
+                    low <<= 32;
+                    high = (high << 32) | 0xFFFFFFFFull;
+                }
+            }
+            p = probs[val >> 6];
+        }
+        put_varint(w, idx);
+        bw_put_bytes(w, buf, 8 * (i64)idx);
+        start += chunk;
+        if (start < count)
+            bw_put(w, (low | 0xFFFFFFull) & FPAQ_TOP, 56);
+    }
+    bw_put(w, (low | 0xFFFFFFull) & FPAQ_TOP, 56); /* dispose() */
+    free(buf);
+}
+
+static int fpaq_decode(BitR* r, u8* block, u32 count)
+{
+    u64 low = 0, high = FPAQ_TOP, current = 0;
+    u16 probs[4][256];
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 256; j++)
+            probs[i][j] = 32768;
+    u32 start = 0;
+    u8* buf = NULL;
+    while (start < count) {
+        u32 sz = 0;
+        if (get_varint(r, &sz) < 0) {
+            free(buf);
+            return 0;
+        }
+        if (sz >= 2 * count) {
+            free(buf);
+            return 0;
+        }
+        free(buf);
+        buf = (u8*)calloc((size_t)sz + (sz >> 3) + 8192, 1);
+        current = br_get(r, 56);
+        br_get_bytes(r, buf, sz);
+        u32 idx = 0;
+        const u32 chunk = (FPAQ_CHUNK < count - start) ? FPAQ_CHUNK : count - start;
+        u16* p = probs[0];
+        for (u32 i = start; i < start + chunk; i++) {
+            int ctx = 1;
+            for (int k = 0; k < 8; k++) {
+                const u64 split = ((((high - low) >> 8) * (u64)p[ctx]) >> 8) + low;
+                if (split >= current) {
+                    high = split;
+                    p[ctx] -= (u16)(((int)p[ctx] - 65536 + 64) >> 6);
+                    ctx += ctx + 1;
+                } else {
+                    low = split + 1;
+                    p[ctx] -= (u16)(p[ctx] >> 6);
+                    ctx += ctx;
+                }
+                if (((low ^ high) >> 24) == 0) {
+                    low = (low << 32) & FPAQ_TOP;
+                    high = ((high << 32) | 0xFFFFFFFFull) & FPAQ_TOP;
+                    if (idx + 4 > sz) {
+                        current = (current << 32) & FPAQ_TOP;
+                        idx = sz + 1;
+                    } else {
+                        const u64 val = ((u64)buf[idx] << 24) | ((u64)buf[idx + 1] << 16) | ((u64)buf[idx + 2] << 8) | buf[idx + 3];
+                        current = ((current << 32) | val) & FPAQ_TOP;
+                        idx += 4;
+                    }
+                }
+            }
+            block[i] = (u8)ctx;
+            if (idx > sz) {
+                free(buf);
+                return 0;
+            }
+            p = probs[(ctx & 0xFF) >> 6];
+        }
+        start += chunk;
+    }
+    free(buf);
+    return (int)count;
+}
+
 /* ------------------------------------------------------------------ blocks
  * entropy ids: entropy/EntropyEncoderFactory.hpp:37-52.                      */
-enum { E_NONE = 0, E_HUFFMAN = 1, E_ANS0 = 5, E_ANS1 = 8 };
+enum { E_NONE = 0, E_HUFFMAN = 1, E_FPAQ = 2, E_ANS0 = 5, E_ANS1 = 8 };
 
 static int entropy_encode(BitW* w, int etype, const u8* p, u32 n)
 {
@@ -1609,6 +1898,9 @@ static int entropy_encode(BitW* w, int etype, const u8* p, u32 n)
         return 0;
     case E_HUFFMAN:
         huf_encode(w, p, n);
+        return 0;
+    case E_FPAQ:
+        fpaq_encode(w, p, n);
         return 0;
     default:
         return -1;
@@ -1627,6 +1919,8 @@ static int entropy_decode(BitR* r, int etype, u8* p, u32 n)
         return ans_decode(r, p, n, 1);
     case E_HUFFMAN:
         return huf_decode(r, p, n);
+    case E_FPAQ:
+        return fpaq_decode(r, p, n);
     default:
         return -1;
     }

@@ -14,8 +14,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
-T_IDS = {"NONE": 0, "BWT": 1, "ZRLT": 6, "MTFT": 7, "RANK": 8}
-E_IDS = {"NONE": 0, "HUFFMAN": 1, "ANS0": 5, "ANS1": 8}
+T_IDS = {"NONE": 0, "BWT": 1, "ZRLT": 6, "MTFT": 7, "RANK": 8, "SRT": 13}
+E_IDS = {"NONE": 0, "HUFFMAN": 1, "FPAQ": 2, "ANS0": 5, "ANS1": 8}
 
 
 def transform_word(name):

@@ -45,6 +45,12 @@ STREAMS = [
     ("incompressible", 9, 100000, "NONE", "ANS1", 65536),
     ("compressible", 4, 9 << 20, "NONE", "ANS1", 4 << 20),
     ("compressible", 4, (9 << 20) + 3, "NONE", "ANS1", 8 << 20),  # two order-1 chunks per block
+    # BASELINE.json configs[4] shape: BWT+SRT+ZRLT / FPAQ
+    ("compressible", 5, 300000, "BWT+SRT+ZRLT", "FPAQ", 65536),
+    ("text", 1, 70000, "SRT", "ANS0", 65536),
+    ("incompressible", 9, 100000, "NONE", "FPAQ", 65536),
+    ("compressible", 5, 9 << 20, "BWT+SRT+ZRLT", "FPAQ", 4 << 20),
+    ("compressible", 5, (40 << 20) + 5, "BWT+SRT+ZRLT", "FPAQ", 32 << 20),
 ]
 
 
@@ -78,9 +84,14 @@ def main():
         enc1, bits1 = ref.entropy_encode("ANS1", data)
         rec["ans1_hex"] = enc1.tobytes().hex()
         rec["ans1_bits"] = int(bits1)
+        encf, bitsf = ref.entropy_encode("FPAQ", data)
+        rec["fpaq_hex"] = encf.tobytes().hex()
+        rec["fpaq_bits"] = int(bitsf)
         for t in ("ZRLT", "RANK", "MTFT"):
             o, fl, ok = ref.sequence_forward(t, data, data.size + 64, data.size + 64)
             rec[t.lower() + "_hex"] = o.tobytes().hex() if fl != 0xFF else None
+        o, fl, ok = ref.sequence_forward("SRT", data, data.size + 1152, data.size + 1152)
+        rec["srt_hex"] = o.tobytes().hex() if fl != 0xFF else None
         out["stages"].append(rec)
     with open(os.path.join(HERE, "golden.json"), "w") as f:
         json.dump(out, f)

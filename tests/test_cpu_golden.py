@@ -52,6 +52,10 @@ def test_oracle_stage_vectors(oracle):
         assert bits == rec["ans0_bits"] and enc.tobytes().hex() == rec["ans0_hex"], rec["case"]
         enc, bits = oracle.entropy_encode("ANS1", data)
         assert bits == rec["ans1_bits"] and enc.tobytes().hex() == rec["ans1_hex"], rec["case"]
+        enc, bits = oracle.entropy_encode("FPAQ", data)
+        assert bits == rec["fpaq_bits"] and enc.tobytes().hex() == rec["fpaq_hex"], rec["case"]
+        o, fl = oracle.sequence_forward("SRT", data, data.size + 1152, data.size + 1152)
+        assert (o.tobytes().hex() if fl != 0xFF else None) == rec["srt_hex"], rec["case"]
         for t in ("ZRLT", "RANK", "MTFT"):
             o, fl = oracle.sequence_forward(t, data, data.size + 64, data.size + 64)
             want = rec[t.lower() + "_hex"]
@@ -92,10 +96,11 @@ def test_type_words():
     lib = ctypes.CDLL(os.path.join(ROOT, "kanzi-cpp_b200", "libknzgpu.so"))
     lib.knz_transform_type.restype = ctypes.c_uint64
     from oracle.oracle import transform_word
-    for name in ("NONE", "BWT", "BWT+RANK+ZRLT", "BWT+MTFT+ZRLT", "ZRLT", "RANK+ZRLT"):
+    for name in ("NONE", "BWT", "BWT+RANK+ZRLT", "BWT+MTFT+ZRLT", "ZRLT", "RANK+ZRLT", "BWT+SRT+ZRLT", "SRT"):
         assert lib.knz_transform_type(name.encode()) == transform_word(name)
     assert lib.knz_transform_type(b"LZX") == 0xFFFFFFFFFFFFFFFF
-    assert lib.knz_entropy_type(b"ANS0") == 5 and lib.knz_entropy_type(b"FPAQ") == -1
+    assert lib.knz_entropy_type(b"ANS0") == 5 and lib.knz_entropy_type(b"ANS1") == 8
+    assert lib.knz_entropy_type(b"FPAQ") == 2 and lib.knz_entropy_type(b"TPAQ") == -1
     hdr = (ctypes.c_uint8 * 32)()
     n = lib.knz_stream_header(ctypes.c_uint64(transform_word("BWT+RANK+ZRLT")), 5, 4 << 20, ctypes.c_int64(1 << 30), hdr)
     assert n == 24 and bytes(hdr[:4]) == b"KANZ"

@@ -29,6 +29,19 @@ def gpu():
     ctx.close()
 
 
+@pytest.fixture(scope="module")
+def gpu_big():
+    """A context provisioned for the large-block configurations (BASELINE configs 4 and 5): the
+    > 4 MiB suffix-sort path (bwt_init_keys), the 64-bit SBRT kernels (>= 16 MiB) and large
+    chunk counts only run here."""
+    import torch
+    assert torch.cuda.is_available()
+    from kanzi_b200 import Context
+    ctx = Context(0, 32 << 20, 4)
+    yield ctx
+    ctx.close()
+
+
 def _first_diff(a, b):
     n = min(a.size, b.size)
     d = np.nonzero(a[:n] != b[:n])[0]
@@ -36,9 +49,11 @@ def _first_diff(a, b):
 
 
 @pytest.mark.parametrize("idx", range(len(GOLD["streams"])))
-def test_gpu_stream_matches_golden(gpu, idx):
+def test_gpu_stream_matches_golden(gpu, gpu_big, idx):
     rec = GOLD["streams"][idx]
-    if rec["entropy"] not in ("ANS0", "NONE", "HUFFMAN", "ANS1"):
+    if rec["block"] > (4 << 20):
+        gpu = gpu_big
+    if rec["entropy"] not in ("ANS0", "NONE", "HUFFMAN", "ANS1", "FPAQ"):
         pytest.skip("entropy codec not on the GPU path yet (covered by the CPU oracle suite)")
     data = synth.GENERATORS[rec["gen"]](rec["size"], rec["seed"])
     assert synth.sha256(data) == rec["input_sha256"]
@@ -52,7 +67,7 @@ def test_gpu_stream_matches_golden(gpu, idx):
     assert back.size == data.size and np.array_equal(back, data)
 
 
-@pytest.mark.parametrize("ename", ["ANS0", "HUFFMAN", "ANS1"])
+@pytest.mark.parametrize("ename", ["ANS0", "HUFFMAN", "ANS1", "FPAQ"])
 def test_gpu_entropy_vs_oracle(gpu, oracle, ename):
     for name, data in CASES.items():
         a, abits = gpu.entropy_encode(ename, data)
@@ -63,11 +78,11 @@ def test_gpu_entropy_vs_oracle(gpu, oracle, ename):
         assert np.array_equal(dec, data), name
 
 
-@pytest.mark.parametrize("tname", ["ZRLT", "RANK", "MTFT", "BWT"])
+@pytest.mark.parametrize("tname", ["ZRLT", "RANK", "MTFT", "BWT", "SRT"])
 def test_gpu_stage_vs_oracle(gpu, oracle, tname):
     for name, data in CASES.items():
         n = data.size
-        for cap in (n + 64, n):
+        for cap in ((n + 1088,) if tname == "SRT" else (n + 64, n)):
             if tname == "BWT" and cap < n + 33:
                 continue
             a, applied = gpu.transform_forward(tname, data, cap)
@@ -77,6 +92,9 @@ def test_gpu_stage_vs_oracle(gpu, oracle, tname):
                 assert a.size == b.size and np.array_equal(a, b), (name, tname, cap, _first_diff(a, b))
                 back, ok = gpu.transform_inverse(tname, b, n + 64)
                 assert ok and np.array_equal(back, data), (name, tname, cap)
+        if tname == "SRT":  # SRT refuses a destination smaller than n + 1024 (transform/SRT.cpp:33-34)
+            _, applied = gpu.transform_forward("SRT", data, n + 64)
+            assert not applied, name
 
 
 def test_gpu_stage_golden_vectors(gpu):
@@ -97,6 +115,10 @@ def test_gpu_stage_golden_vectors(gpu):
         assert bits == rec["ans0_bits"] and enc.tobytes().hex() == rec["ans0_hex"], rec["case"]
         enc, bits = gpu.entropy_encode("ANS1", data)
         assert bits == rec["ans1_bits"] and enc.tobytes().hex() == rec["ans1_hex"], rec["case"]
+        enc, bits = gpu.entropy_encode("FPAQ", data)
+        assert bits == rec["fpaq_bits"] and enc.tobytes().hex() == rec["fpaq_hex"], rec["case"]
+        o, applied = gpu.transform_forward("SRT", data, data.size + 1152)
+        assert (o.tobytes().hex() if applied else None) == rec["srt_hex"], rec["case"]
         for t in ("ZRLT", "RANK", "MTFT"):
             want = rec[t.lower() + "_hex"]
             o, applied = gpu.transform_forward(t, data, data.size + 64)
@@ -109,7 +131,8 @@ def test_gpu_stage_golden_vectors(gpu):
 @pytest.mark.parametrize("tname,ename", [("NONE", "ANS0"), ("BWT+RANK+ZRLT", "ANS0"), ("NONE", "NONE"),
                                          ("ZRLT", "ANS0"), ("BWT+MTFT+ZRLT", "ANS0"), ("BWT", "NONE"),
                                          ("RANK+ZRLT", "ANS0"), ("NONE", "HUFFMAN"),
-                                         ("BWT+RANK+ZRLT", "HUFFMAN"), ("NONE", "ANS1"), ("BWT+RANK+ZRLT", "ANS1")])
+                                         ("BWT+RANK+ZRLT", "HUFFMAN"), ("NONE", "ANS1"), ("BWT+RANK+ZRLT", "ANS1"),
+                                         ("BWT+SRT+ZRLT", "FPAQ"), ("SRT", "ANS0"), ("NONE", "FPAQ")])
 def test_gpu_stream_vs_oracle(gpu, oracle, tname, ename):
     inputs = {
         "comp_600k": synth.synth_compressible(600000, 21),
@@ -207,22 +230,9 @@ def test_gpu_decode_groups(gpu, oracle, groups):
         gpu.set_decode_groups(1)
 
 
-@pytest.fixture(scope="module")
-def gpu_big():
-    """A context provisioned for the large-block configurations (BASELINE configs 4 and 5): the
-    > 4 MiB suffix-sort path (bwt_init_keys), the 64-bit SBRT kernels (>= 16 MiB) and large
-    chunk counts only run here."""
-    import torch
-    assert torch.cuda.is_available()
-    from kanzi_b200 import Context
-    ctx = Context(0, 32 << 20, 4)
-    yield ctx
-    ctx.close()
-
-
 @pytest.mark.parametrize("bs_mib", [16, 32])
 @pytest.mark.parametrize("tname,ename", [("BWT+RANK+ZRLT", "ANS0"), ("NONE", "HUFFMAN"), ("NONE", "ANS0"),
-                                         ("BWT+MTFT+ZRLT", "HUFFMAN"), ("NONE", "ANS1")])
+                                         ("BWT+MTFT+ZRLT", "HUFFMAN"), ("NONE", "ANS1"), ("BWT+SRT+ZRLT", "FPAQ")])
 def test_gpu_large_blocks_vs_reference(gpu_big, tname, ename, bs_mib):
     """16 MiB and 32 MiB blocks against the unmodified reference (prebuilt oracle/_ref)."""
     from oracle.oracle import Ref

@@ -10,7 +10,7 @@ from cases import small_cases, rng_bytes
 CASES = small_cases()
 
 
-@pytest.mark.parametrize("ename", ["ANS0", "ANS1", "NONE", "HUFFMAN"])
+@pytest.mark.parametrize("ename", ["ANS0", "ANS1", "NONE", "HUFFMAN", "FPAQ"])
 def test_entropy_encode_matches_ref(oracle, ref, ename):
     for name, data in CASES.items():
         if data.size == 0:
@@ -41,6 +41,23 @@ def test_sequence_forward_matches_ref(oracle, ref, tname):
                 assert ok3 == 1 and np.array_equal(back2, data), (name, tname)
 
 
+def test_srt_matches_ref(oracle, ref):
+    """SRT (transform/SRT.cpp): getMaxEncodedLength is n + 1024, so the buffers are sized for it."""
+    for tname in ("SRT", "BWT+SRT+ZRLT"):
+        for name, data in CASES.items():
+            n = data.size
+            cap = n + 1088 + 64
+            a, af = oracle.sequence_forward(tname, data, cap, cap)
+            b, bf, ok = ref.sequence_forward(tname, data, cap, cap)
+            assert af == bf, (name, tname, af, bf)
+            if af != 0xFF:
+                assert np.array_equal(a, b), (name, tname)
+                back, ok2 = oracle.sequence_inverse(tname, bf, b, cap)
+                assert ok2 == 1 and np.array_equal(back, data), (name, tname)
+                back2, ok3 = ref.sequence_inverse(tname, bf, b, cap)
+                assert ok3 == 1 and np.array_equal(back2, data), (name, tname)
+
+
 def test_bwt_matches_ref(oracle, ref):
     for name, data in CASES.items():
         if data.size < 2:
@@ -54,7 +71,8 @@ def test_bwt_matches_ref(oracle, ref):
 
 @pytest.mark.parametrize("tname,ename", [("NONE", "ANS0"), ("BWT+RANK+ZRLT", "ANS0"), ("NONE", "NONE"),
                                          ("BWT", "ANS1"), ("ZRLT", "ANS0"), ("BWT+MTFT+ZRLT", "ANS0"),
-                                         ("NONE", "HUFFMAN"), ("BWT+RANK+ZRLT", "HUFFMAN")])
+                                         ("NONE", "HUFFMAN"), ("BWT+RANK+ZRLT", "HUFFMAN"),
+                                         ("BWT+SRT+ZRLT", "FPAQ"), ("SRT", "ANS0"), ("NONE", "FPAQ")])
 def test_stream_matches_ref(oracle, ref, tname, ename):
     inputs = {
         "comp_300k": synth.synth_compressible(300000, 21),

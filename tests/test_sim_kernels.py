@@ -26,7 +26,7 @@ def sim():
 CASES = small_cases()
 
 
-@pytest.mark.parametrize("ename", ["ANS0", "HUFFMAN", "ANS1"])
+@pytest.mark.parametrize("ename", ["ANS0", "HUFFMAN", "ANS1", "FPAQ"])
 def test_sim_entropy(sim, oracle, ename):
     for name, data in CASES.items():
         a, abits = sim.entropy_encode(ename, data)
@@ -58,10 +58,27 @@ def test_sim_stage_forward_inverse(sim, oracle, tname):
                 assert ok and np.array_equal(back, data), (name, tname, cap)
 
 
+def test_sim_srt(sim, oracle):
+    """SRT forward (tile tables + relabelled MTFT ranks + stable scatter) and the serial inverse."""
+    for name, data in CASES.items():
+        n = data.size
+        if n > 70001:
+            continue
+        a, applied = sim.transform_forward("SRT", data, n + 1088)
+        b, flags = oracle.sequence_forward("SRT", data, n + 1088, n + 1088)
+        assert applied == (flags != 0xFF), (name, applied, flags)
+        if applied:
+            assert a.size == b.size and np.array_equal(a, b), name
+            back, ok = sim.transform_inverse("SRT", b, n + 64)
+            assert ok and np.array_equal(back, data), name
+        _, applied = sim.transform_forward("SRT", data, n + 64)  # destination < n + 1024: refused
+        assert not applied, name
+
+
 @pytest.mark.parametrize("tname,ename", [("NONE", "ANS0"), ("BWT+RANK+ZRLT", "ANS0"), ("NONE", "NONE"),
                                          ("ZRLT", "ANS0"), ("BWT+MTFT+ZRLT", "ANS0"), ("BWT", "NONE"),
                                          ("NONE", "HUFFMAN"), ("BWT+RANK+ZRLT", "HUFFMAN"), ("NONE", "ANS1"),
-                                         ("ZRLT", "ANS1")])
+                                         ("ZRLT", "ANS1"), ("BWT+SRT+ZRLT", "FPAQ")])
 def test_sim_stream(sim, oracle, tname, ename):
     inputs = {
         "comp_150k": synth.synth_compressible(150000, 21),

@@ -138,6 +138,41 @@ int knz_entropy_encode(knz_ctx* ctx, int type, const uint8_t* in, int n, uint8_t
 /* EntropyDecoder::decode (src/EntropyDecoder.hpp:30): n = number of bytes to produce. */
 int knz_entropy_decode(knz_ctx* ctx, int type, const uint8_t* in, int64_t inBits, uint8_t* out, int n);
 
+/* ---- Multi-GPU: one process per GPU, blocks sharded round-robin (block i -> rank i % world).
+ * Replaces the task pool of CompressedOutputStream / CompressedInputStream across devices: the ordered
+ * append to the shared bitstream (io/CompressedOutputStream.cpp:836-868) becomes an all-gather of the
+ * per-block bit counts, a gather of the block payloads to rank 0 over NCCL and one bit-concatenation
+ * kernel there; on decode the host walks the length prefixes (io/CompressedInputStream.cpp:823-856)
+ * and ships only its own blocks' bit ranges to its GPU.
+ *   knz_dist_unique_id   rank 0 creates the NCCL id, the launcher hands it to every rank
+ *   knz_dist_init        collective: joins the context to an NCCL communicator of `world` ranks
+ *   knz_dist_init_transport   same with caller-supplied collectives over device buffers (tests; gloo)  */
+typedef int (*knz_allgather_fn)(void* user, const void* d_send, int64_t bytes, void* d_recv);  /* recv: world * bytes, rank order */
+typedef int (*knz_gather_fn)(void* user, const void* d_send, int64_t bytes, void* d_recv);     /* recv used on rank 0 only */
+typedef int (*knz_bcast_fn)(void* user, void* d_buf, int64_t bytes);                            /* from rank 0 */
+int knz_dist_unique_id(uint8_t id[128]);
+int knz_dist_init(knz_ctx* ctx, int rank, int world, const uint8_t id[128]);
+int knz_dist_init_transport(knz_ctx* ctx, int rank, int world, knz_allgather_fn allgather, knz_gather_fn gather,
+                            knz_bcast_fn bcast, void* user);
+/* Stream level, host buffers, collective.  compress: every rank passes the whole input, encodes the
+ * blocks it owns, rank 0 receives the stream (*outLen = 0 elsewhere); byte-identical to knz_compress.
+ * decompress: every rank passes the whole stream and a buffer for the whole original and fills the
+ * blocks it owns (block i at out + i * blockSize; pass a shared mapping to collect them in one place).  */
+int knz_compress_dist(knz_ctx* ctx, const char* transform, const char* entropy, int blockSize, const uint8_t* in,
+                      int64_t n, uint8_t* out, int64_t cap, int64_t* outLen);
+int knz_decompress_dist(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_t* out, int64_t cap, int64_t* outLen);
+/* Same with the data resident in device memory.  encode: this rank's nbOwn blocks (block k of the rank is
+ * block rank + k * world of the stream) -> stream body assembled in d_stream on rank 0 from bit `startBit`;
+ * h_allBits (every rank, may be NULL) receives the bit count of all nBlocks blocks in stream order.
+ * decode: d_stream holds the stream on rank 0 and is a receive buffer elsewhere (broadcast inside); the
+ * rank's blocks are decoded to d_out + k * outStride.                                                    */
+int knz_dist_encode_dev(knz_ctx* ctx, uint64_t tType, int eType, int blockSize, const uint8_t* d_in, int64_t inStride,
+                        const int32_t* lens, int nbOwn, int nBlocks, int firstBlockLen, uint8_t* d_stream,
+                        int64_t streamCap, uint64_t startBit, uint64_t* h_allBits, uint64_t* endBit);
+int knz_dist_decode_dev(knz_ctx* ctx, uint64_t tType, int eType, int blockSize, uint8_t* d_stream, int64_t streamBytes,
+                        uint64_t startBit, const uint64_t* h_allBits, int nBlocks, uint8_t* d_out, int64_t outStride,
+                        int32_t* h_outLens);
+
 /* Instrumentation for bench.py: kernels launched by this context since creation,
  * and the CUDA stream (cudaStream_t) the library launches on.                    */
 uint64_t knz_launch_count(const knz_ctx* ctx);

@@ -713,7 +713,7 @@ stream_scan_kernel(const u64* __restrict__ blockBits, int nBlocks, const u64* st
 
 __global__ void __launch_bounds__(256)
 stream_concat_kernel(const u8* __restrict__ blockOut, i64 outStride, const u64* __restrict__ blockBits,
-                     const u64* __restrict__ blockOff, u8* __restrict__ stream)
+                     const u64* __restrict__ blockOff, u8* __restrict__ stream, const int* __restrict__ srcIndex)
 {
     const int b = blockIdx.y;
     u32* dst = reinterpret_cast<u32*>(stream);
@@ -731,7 +731,9 @@ stream_concat_kernel(const u8* __restrict__ blockOut, i64 outStride, const u64* 
         }
     }
     off += 5 + lw;
-    const u8* src = blockOut + (i64)b * outStride;
+    // srcIndex: where block b's bytes sit in blockOut (blocks gathered from several GPUs arrive grouped
+    // by rank, not in stream order); NULL = in order
+    const u8* src = blockOut + (i64)(srcIndex ? srcIndex[b] : b) * outStride;
     const i64 nbits = (i64)w;
     if (nbits <= 0)
         return;
@@ -803,10 +805,11 @@ void launch_entropy_encode(const EncodeLaunch& L, cudaStream_t s, u64* launches)
 
 void launch_stream_assemble(const u8* blockOut, i64 outStride, const u64* blockBits, int nBlocks,
                             const u64* startBit, u64* blockOff, u64* endBit, u8* stream, cudaStream_t s,
-                            u64* launches)
+                            u64* launches, const int* srcIndex)
 {
     KLAUNCH(stream_scan_kernel, 1, 256, s, blockBits, nBlocks, startBit, blockOff, endBit);
-    KLAUNCH(stream_concat_kernel, dim3(32, nBlocks), 256, s, blockOut, outStride, blockBits, blockOff, stream);
+    KLAUNCH(stream_concat_kernel, dim3(32, nBlocks), 256, s, blockOut, outStride, blockBits, blockOff, stream,
+            srcIndex);
     *launches += 2;
 }
 

@@ -4,77 +4,10 @@
 //   transforms (BWT -> RANK/MTFT -> ZRLT)  ->  rANS  ->  bit assembly.
 // The reference's equivalents are CompressedOutputStream / EncodingTask and
 // CompressedInputStream / DecodingTask (io/Compressed{Output,Input}Stream.cpp).
-#include <stdio.h>
-#include <stdlib.h>
-#include <string.h>
-#include <mutex>
+#include "ctx.h"
 
-#include "../../include/knz_gpu.h"
-#include "kernels.h"
-
-#define CK(call)                                                                                   \
-    do {                                                                                           \
-        cudaError_t e_ = (call);                                                                   \
-        if (e_ != cudaSuccess) {                                                                   \
-            snprintf(ctx->err, sizeof(ctx->err), "%s:%d CUDA error %d: %s", __FILE__, __LINE__,    \
-                     (int)e_, cudaGetErrorString(e_));                                             \
-            return KNZ_ERR_PROCESS_BLOCK;                                                          \
-        }                                                                                          \
-    } while (0)
-
-#define KNZ_MAX_GROUPS 8
-
-struct knz_ctx {
-    int device, maxBlockSize, maxBatch;
-    cudaStream_t stream;
-    cudaStream_t copyStream; // host->device staging of the stream-level API (overlaps with compute)
-    cudaStream_t d2hStream;  // device->host copies of finished output (second DMA direction)
-    cudaEvent_t evCopy[2], evDone[2];
-    cudaEvent_t ev[10];
-    cudaEvent_t evStage[16]; // per-stage brackets: recorded during a batch, read once after it (no mid-batch sync)
-    std::recursive_mutex mtx; // every C-ABI entry point locks its context (reference worker threads share one)
-    int stageCap;             // bytes a stage buffer slot can hold (bstride - 64)
-    int encSched[3];          // knz_compress sub-batch schedule (env KNZ_ENC_BATCH)
-    int decBwtGroups;         // knz_decompress: groups of the last inverse-BWT stage (env KNZ_DEC_GROUPS)
-    cudaStream_t gStream[KNZ_MAX_GROUPS]; // decode: one stream per block group (stages of different groups overlap)
-    cudaEvent_t gEv[KNZ_MAX_GROUPS + 1];
-    int decGroups;                        // 1 = one group, per-stage timings valid
-    i64 bstride;     // stride of the ping-pong stage buffers
-    u8 *bufA, *bufB; // [maxBatch * bstride]
-    u8* dStageIn;    // host API: staged input blocks [maxBatch * bstride]
-    u8* dOut;        // per-block output bit strings [maxBatch * outStride]
-    i64 outStride;
-    BlkState* st;    // [10][maxBatch]
-    int *capEven, *capOdd;
-    int maxChunks;
-    u8* slots;
-    u32 *hdrBits, *payBytes, *payOff;
-    u64 *chunkOff, *blockBits, *blockOff, *streamPos;
-    u64 *chunkPos, *dInBits, *dPayStart;
-    int* dPreLen;
-    int* errFlag;
-    Workspace ws;
-    Ans1Work a1; // order-1 rANS scratch, allocated on the first use of ANS1
-    bool a1Ready;
-    SrtWork srt; // SRT scratch, allocated on the first SRT stage
-    bool srtReady;
-    // pinned host mirrors
-    BlkState* h_st;
-    int *h_capEven, *h_capOdd, *h_err, *h_preLen;
-    u64 *h_bits, *h_payStart, *h_pos;
-    // stream-level buffers (grown on demand)
-    u8* dStream;
-    i64 dStreamCap;
-    u8* dPlain;
-    i64 dPlainCap;
-    u8* dPlain2;
-    i64 dPlain2Cap;
-    u64 launches;
-    float ms[8];
-    char err[256];
-};
-
-static i64 round_up(i64 v, i64 a) { return (v + a - 1) / a * a; }
+i64 knz_round_up(i64 v, i64 a) { return (v + a - 1) / a * a; }
+static i64 round_up(i64 v, i64 a) { return knz_round_up(v, a); }
 
 static int split_types(u64 tType, int* types)
 {
@@ -278,6 +211,7 @@ extern "C" void knz_destroy(knz_ctx* ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream)
         cudaStreamSynchronize(ctx->stream);
+    knz_dist_destroy(ctx);
     workspace_free(ctx->ws);
     if (ctx->a1Ready)
         ans1_work_free(ctx->a1);
@@ -441,7 +375,7 @@ static void launch_inverse_stage(knz_ctx* ctx, int type, const StageLaunch& L, c
 
 // Forward transforms + entropy for one batch of blocks resident on the device.
 // All lens[i] must be > 15 (small blocks are framed on the host).
-static int encode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8* d_in, i64 inStride,
+int knz_encode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8* d_in, i64 inStride,
                         const int32_t* lens, int nB, int firstBlockLen, u8* d_out, i64 outStride, u64* d_bits,
                         u8* h_flags)
 {
@@ -579,7 +513,7 @@ extern "C" int knz_encode_blocks_dev(knz_ctx* ctx, uint64_t tType, int eType, in
     float acc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
     for (int off = 0; off < nBlocks; off += ctx->maxBatch) {
         const int nb = (nBlocks - off < ctx->maxBatch) ? nBlocks - off : ctx->maxBatch;
-        const int rc = encode_batch(ctx, tType, eType, blockSize, d_in + (i64)off * inStride, inStride, lens + off, nb,
+        const int rc = knz_encode_batch(ctx, tType, eType, blockSize, d_in + (i64)off * inStride, inStride, lens + off, nb,
                                     firstBlockLen, d_blockOut + (i64)off * outStride, outStride, d_outBits + off,
                                     h_skipFlags ? h_skipFlags + off : NULL);
         if (rc != KNZ_OK)
@@ -595,7 +529,7 @@ extern "C" int knz_encode_blocks_dev(knz_ctx* ctx, uint64_t tType, int eType, in
 // Small blocks (<= 15 bytes) are always copy blocks: mode 0x80 | skipFlags>>4
 // with the single NullTransform applied (flags 0x7F), one length byte, raw bytes
 // (io/CompressedOutputStream.cpp:38,691-695).
-static u64 frame_small_block(const u8* in, int len, u8* out)
+u64 knz_frame_small_block(const u8* in, int len, u8* out)
 {
     out[0] = 0x87;
     out[1] = (u8)len;
@@ -628,7 +562,7 @@ extern "C" int knz_encode_blocks(knz_ctx* ctx, uint64_t tType, int eType, int bl
                 return KNZ_ERR_BLOCK_SIZE;
             }
             if (len <= 15) {
-                outBits[off + b] = frame_small_block(in + (i64)(off + b) * inStride, len, out + (i64)(off + b) * outStride);
+                outBits[off + b] = knz_frame_small_block(in + (i64)(off + b) * inStride, len, out + (i64)(off + b) * outStride);
                 if (skipFlags)
                     skipFlags[off + b] = 0x7F;
             } else {
@@ -642,7 +576,7 @@ extern "C" int knz_encode_blocks(knz_ctx* ctx, uint64_t tType, int eType, int bl
         int rc = KNZ_OK;
         u8* fl = (u8*)malloc((size_t)nb + 1);
         if (ng > 0)
-            rc = encode_batch(ctx, tType, eType, blockSize, ctx->dStageIn, ctx->bstride, dl, ng, firstBlockLen, ctx->dOut,
+            rc = knz_encode_batch(ctx, tType, eType, blockSize, ctx->dStageIn, ctx->bstride, dl, ng, firstBlockLen, ctx->dOut,
                               ctx->outStride, ctx->blockBits, fl);
         if (rc == KNZ_OK && ng > 0) {
             cudaMemcpyAsync(ctx->h_bits, ctx->blockBits, sizeof(u64) * ng, cudaMemcpyDeviceToHost, s);
@@ -759,7 +693,7 @@ extern "C" int knz_stream_header(uint64_t tType, int eType, int blockSize, int64
     return (int)(w.pos >> 3);
 }
 
-static int grow(knz_ctx* ctx, u8** buf, i64* cap, i64 need)
+int knz_grow(knz_ctx* ctx, u8** buf, i64* cap, i64 need)
 {
     if (*cap >= need)
         return KNZ_OK;
@@ -799,7 +733,7 @@ extern "C" int knz_compress(knz_ctx* ctx, const char* transform, const char* ent
     const i64 worstBlk = ((2 * (i64)blockSize < refCapBlk) ? 2 * (i64)blockSize : refCapBlk);
     const i64 perBlk = worstBlk + (worstBlk >> 2) + 1024 + ((eType == E_ANS1) ? 131072 * (i64)((blockSize >> 22) + 1) : 0);
     const i64 streamCap = round_up(nBlocks * perBlk + 65536, 256);
-    int rc = grow(ctx, &ctx->dStream, &ctx->dStreamCap, streamCap);
+    int rc = knz_grow(ctx, &ctx->dStream, &ctx->dStreamCap, streamCap);
     if (rc != KNZ_OK)
         return rc;
     // Encode in sub-batches: the pinned-host -> device copy of sub-batch i+1 runs on the copy
@@ -815,10 +749,10 @@ extern "C" int knz_compress(knz_ctx* ctx, const char* transform, const char* ent
     const int ebWant = (sched[1] > sched[2]) ? (sched[1] > sched[0] ? sched[1] : sched[0]) : (sched[2] > sched[0] ? sched[2] : sched[0]);
     const int eb = (ctx->maxBatch < ebWant) ? ctx->maxBatch : ebWant;
     const i64 plainBytes = round_up((i64)eb * blockSize + 256, 256);
-    rc = grow(ctx, &ctx->dPlain, &ctx->dPlainCap, plainBytes);
+    rc = knz_grow(ctx, &ctx->dPlain, &ctx->dPlainCap, plainBytes);
     if (rc != KNZ_OK)
         return rc;
-    rc = grow(ctx, &ctx->dPlain2, &ctx->dPlain2Cap, plainBytes);
+    rc = knz_grow(ctx, &ctx->dPlain2, &ctx->dPlain2Cap, plainBytes);
     if (rc != KNZ_OK)
         return rc;
     u8* plain[2] = { ctx->dPlain, ctx->dPlain2 };
@@ -860,7 +794,7 @@ extern "C" int knz_compress(knz_ctx* ctx, const char* transform, const char* ent
         if (lens[nb - 1] <= 15)
             ng = nb - 1; // only the last block of a stream can be that small
         if (ng > 0) {
-            rc = encode_batch(ctx, tType, eType, blockSize, plain[slot], blockSize, lens, ng, firstLen, ctx->dOut,
+            rc = knz_encode_batch(ctx, tType, eType, blockSize, plain[slot], blockSize, lens, ng, firstLen, ctx->dOut,
                               ctx->outStride, ctx->blockBits, NULL);
             for (int i = 0; i < 8; i++)
                 acc[i] += ctx->ms[i];
@@ -868,7 +802,7 @@ extern "C" int knz_compress(knz_ctx* ctx, const char* transform, const char* ent
         if (rc == KNZ_OK && ng < nb) {
             u8 tmp[32];
             memset(tmp, 0, sizeof(tmp));
-            ctx->h_bits[0] = frame_small_block(in + off + (i64)ng * blockSize, lens[ng], tmp);
+            ctx->h_bits[0] = knz_frame_small_block(in + off + (i64)ng * blockSize, lens[ng], tmp);
             CK(cudaMemcpyAsync(ctx->dOut + (i64)ng * ctx->outStride, tmp, 32, cudaMemcpyHostToDevice, s));
             CK(cudaMemcpyAsync(ctx->blockBits + ng, ctx->h_bits, sizeof(u64), cudaMemcpyHostToDevice, s));
             CK(cudaStreamSynchronize(s));
@@ -918,32 +852,13 @@ extern "C" int knz_compress(knz_ctx* ctx, const char* transform, const char* ent
 }
 
 // ------------------------------------------------------------------ decode
-struct HostBitReader {
-    const u8* p;
-    u64 nbits, pos;
-    bool bad;
-    u64 get(int n)
-    {
-        u64 v = 0;
-        for (int k = 0; k < n; k++) {
-            u64 b = 0;
-            if (pos < nbits)
-                b = (p[pos >> 3] >> (7 - (pos & 7))) & 1;
-            else
-                bad = true;
-            v = (v << 1) | b;
-            pos++;
-        }
-        return v;
-    }
-};
 
 // Inverse transforms + entropy decode for a batch.  Block b's bit string starts
 // at bit h_start[b] of d_in (+ b*inStride) and holds h_bits[b] bits.
-static int decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8* d_in, i64 inStride,
+int knz_decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8* d_in, i64 inStride,
                         const u64* h_payStart, const u64* h_endBit, const int* h_preLen, const u8* h_flags, int nB,
                         u8* d_out, i64 outStride, int32_t* h_outLens,
-                        u8* h_sink = NULL, int* h_sinkBlocks = NULL)
+                        u8* h_sink, int* h_sinkBlocks)
 {
     int types[8];
     const int nt = split_types(tType, types);
@@ -1165,7 +1080,7 @@ static int decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const
 
 // Parse one block's private header (mode byte, [skip flags], length) at r.pos.
 // Returns 0 ok, 1 copy block, <0 error.
-static int parse_block_header(HostBitReader& r, int blkLen, u8* flags, int* preLen)
+int knz_parse_block_header(HostBitReader& r, int blockSize, u8* flags, int* preLen)
 {
     const int mode = (int)r.get(8);
     int fl = 0;
@@ -1178,7 +1093,7 @@ static int parse_block_header(HostBitReader& r, int blkLen, u8* flags, int* preL
         fl = ((mode << 4) | 0x0F) & 0xFF;
     const int dataSize = 1 + ((mode >> 5) & 3);
     const int pre = (int)r.get(8 * dataSize);
-    int maxT = blkLen + blkLen / 2;
+    int maxT = blockSize + blockSize / 2; // io/CompressedInputStream.cpp:893-894 (maxTransformSize)
     if (maxT < 2048)
         maxT = 2048;
     if (r.bad || pre <= 0 || pre > maxT)
@@ -1213,14 +1128,14 @@ extern "C" int knz_decode_blocks_dev(knz_ctx* ctx, uint64_t tType, int eType, in
         int rc = KNZ_OK;
         for (int b = 0; b < nb && rc == KNZ_OK; b++) {
             HostBitReader r = { heads + 8 * b, 64, 0, false };
-            const int k = parse_block_header(r, blkLen, &fl[b], &pre[b]);
+            const int k = knz_parse_block_header(r, blockSize, &fl[b], &pre[b]);
             if (k != 0)
                 rc = (k < 0) ? KNZ_ERR_INVALID_FILE : KNZ_ERR_INVALID_CODEC; // device path: no copy blocks
             pay[b] = r.pos;
             endb[b] = h_inBits[off + b];
         }
         if (rc == KNZ_OK)
-            rc = decode_batch(ctx, tType, eType, blockSize, d_in + (i64)off * inStride, inStride, pay, endb, pre, fl, nb,
+            rc = knz_decode_batch(ctx, tType, eType, blockSize, d_in + (i64)off * inStride, inStride, pay, endb, pre, fl, nb,
                               d_out + (i64)off * outStride, outStride, h_outLens + off);
         free(heads);
         free(pay);
@@ -1261,7 +1176,7 @@ extern "C" int knz_decode_blocks(knz_ctx* ctx, uint64_t tType, int eType, int bl
             HostBitReader r = { p, inBits[off + b], 0, false };
             u8 f = 0;
             int pl = 0;
-            const int k = parse_block_header(r, blkLen, &f, &pl);
+            const int k = knz_parse_block_header(r, blockSize, &f, &pl);
             if (k < 0 || nbytes + 16 > ctx->outStride) {
                 rc = KNZ_ERR_INVALID_FILE;
             } else if (k == 1) { // copy block: raw bytes follow
@@ -1283,7 +1198,7 @@ extern "C" int knz_decode_blocks(knz_ctx* ctx, uint64_t tType, int eType, int bl
         }
         int32_t* ol = (int32_t*)malloc(sizeof(int32_t) * (size_t)nb);
         if (rc == KNZ_OK && ng > 0)
-            rc = decode_batch(ctx, tType, eType, blockSize, ctx->dOut, ctx->outStride, pay, endb, pre, fl, ng,
+            rc = knz_decode_batch(ctx, tType, eType, blockSize, ctx->dOut, ctx->outStride, pay, endb, pre, fl, ng,
                               ctx->dStageIn, ctx->bstride, ol);
         if (rc == KNZ_OK) {
             for (int g = 0; g < ng; g++) {
@@ -1309,14 +1224,10 @@ extern "C" int knz_decode_blocks(knz_ctx* ctx, uint64_t tType, int eType, int bl
     return KNZ_OK;
 }
 
-extern "C" int knz_decompress(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_t* out, int64_t cap, int64_t* outLen)
+// Stream header: magic, version 6, checksum size, entropy id, transform word, block size, optional
+// original size, padding, header checksum (io/CompressedInputStream.cpp:511-663).
+int knz_parse_stream_header(knz_ctx* ctx, HostBitReader& r, KnzStreamInfo* info)
 {
-    if (!ctx || !in || !out || !outLen || n < 20)
-        return KNZ_ERR_INVALID_PARAM;
-    std::lock_guard<std::recursive_mutex> lock_(ctx->mtx);
-    cudaSetDevice(ctx->device);
-    cudaStream_t s = ctx->stream;
-    HostBitReader r = { in, 8ull * (u64)n, 0, false };
     if (r.get(32) != 0x4B414E5A)
         return KNZ_ERR_INVALID_FILE;
     if (r.get(4) != 6)
@@ -1357,12 +1268,36 @@ extern "C" int knz_decompress(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_
     }
     if (blockSize < 1024 || blockSize > ctx->maxBlockSize)
         return KNZ_ERR_BLOCK_SIZE;
+    info->eType = eType;
+    info->tType = tType;
+    info->blockSize = blockSize;
+    info->origSize = szMask ? (i64)origSize : -1;
+    return KNZ_OK;
+}
+
+extern "C" int knz_decompress(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_t* out, int64_t cap, int64_t* outLen)
+{
+    if (!ctx || !in || !out || !outLen || n < 20)
+        return KNZ_ERR_INVALID_PARAM;
+    std::lock_guard<std::recursive_mutex> lock_(ctx->mtx);
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    HostBitReader r = { in, 8ull * (u64)n, 0, false };
+    KnzStreamInfo info;
+    {
+        const int rch = knz_parse_stream_header(ctx, r, &info);
+        if (rch != KNZ_OK)
+            return rch;
+    }
+    const int eType = info.eType;
+    const u64 tType = info.tType;
+    const int blockSize = info.blockSize;
     const int blkLen = blockSize + ((blockSize >> 4) > 512 ? (blockSize >> 4) : 512);
     // whole compressed stream to the device; kernels read at bit offsets
-    int rc = grow(ctx, &ctx->dStream, &ctx->dStreamCap, round_up(n + 256, 256));
+    int rc = knz_grow(ctx, &ctx->dStream, &ctx->dStreamCap, round_up(n + 256, 256));
     if (rc != KNZ_OK)
         return rc;
-    rc = grow(ctx, &ctx->dPlain, &ctx->dPlainCap, round_up((i64)ctx->maxBatch * blockSize + 256, 256));
+    rc = knz_grow(ctx, &ctx->dPlain, &ctx->dPlainCap, round_up((i64)ctx->maxBatch * blockSize + 256, 256));
     if (rc != KNZ_OK)
         return rc;
     CK(cudaMemsetAsync(ctx->dStream + (n & ~(i64)255), 0, (size_t)(round_up(n + 256, 256) - (n & ~(i64)255)), s));
@@ -1395,7 +1330,7 @@ extern "C" int knz_decompress(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_
             HostBitReader hb = { in, start + bits, start, false };
             u8 f = 0;
             int pl = 0;
-            const int k = parse_block_header(hb, blkLen, &f, &pl);
+            const int k = knz_parse_block_header(hb, blockSize, &f, &pl);
             if (k < 0 || start + bits > r.nbits) {
                 rc = KNZ_ERR_INVALID_FILE;
                 break;
@@ -1428,7 +1363,7 @@ extern "C" int knz_decompress(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_
         // blocks the batch already sent to the host (full-size blocks, overlapped with the last stage)
         int sunk = 0;
         const bool roomy = batchOut + (i64)ng * blockSize <= cap;
-        rc = decode_batch(ctx, tType, eType, blockSize, ctx->dStream, 0, pay, endb, pre, fl, ng, ctx->dPlain, blockSize,
+        rc = knz_decode_batch(ctx, tType, eType, blockSize, ctx->dStream, 0, pay, endb, pre, fl, ng, ctx->dPlain, blockSize,
                           ol, roomy ? out + batchOut : NULL, &sunk);
         if (rc != KNZ_OK) {
             cudaStreamSynchronize(ctx->d2hStream);

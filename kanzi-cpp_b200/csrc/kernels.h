@@ -72,7 +72,7 @@ void launch_out_prepare_and_header(const EncodeLaunch& L, cudaStream_t s, u64* l
 // startBit / endBit are device scalars (may alias): batches chain without a host round trip.
 void launch_stream_assemble(const u8* blockOut, i64 outStride, const u64* blockBits, int nBlocks,
                             const u64* startBit, u64* blockOff, u64* endBit, u8* stream, cudaStream_t s,
-                            u64* launches);
+                            u64* launches, const int* srcIndex = NULL);
 
 // Entropy decode: block b's bit string is at in + b*inStride; its entropy payload
 // starts at bit payStart[b] and must yield preLen[b] bytes into dst (buffer A).

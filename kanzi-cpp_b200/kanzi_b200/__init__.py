@@ -62,6 +62,14 @@ def _load(path):
     L.knz_transform_inverse.argtypes = [vp, i32, vp, i32, vp, i32, ctypes.POINTER(i32), ctypes.POINTER(i32)]
     L.knz_entropy_encode.argtypes = [vp, i32, vp, i32, vp, i64, ctypes.POINTER(i64)]
     L.knz_entropy_decode.argtypes = [vp, i32, vp, i64, vp, i32]
+    L.knz_dist_unique_id.argtypes = [vp]
+    L.knz_dist_init.argtypes = [vp, i32, i32, vp]
+    L.knz_dist_init_transport.argtypes = [vp, i32, i32, vp, vp, vp, vp]
+    L.knz_compress_dist.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p, i32, vp, i64, vp, i64, ctypes.POINTER(i64)]
+    L.knz_decompress_dist.argtypes = [vp, vp, i64, vp, i64, ctypes.POINTER(i64)]
+    L.knz_dist_encode_dev.argtypes = [vp, u64, i32, i32, vp, i64, vp, i32, i32, i32, vp, i64, u64, vp,
+                                      ctypes.POINTER(u64)]
+    L.knz_dist_decode_dev.argtypes = [vp, u64, i32, i32, vp, i64, u64, vp, i32, vp, i64, vp]
     return L
 
 
@@ -135,6 +143,81 @@ class Context:
             out = np.empty(max(cap, 1), dtype=np.uint8)
         n = ctypes.c_int64(0)
         self._check(self.lib.knz_decompress(self.h, _ptr(comp), comp.size, _ptr(out), cap, ctypes.byref(n)))
+        return out[: n.value]
+
+    # ---- multi-GPU: one process per GPU, blocks sharded round-robin (see include/knz_gpu.h)
+    def dist_init(self, rank, world):
+        """Collective.  With the NCCL backend the library opens its own communicator (the 128-byte
+        unique id travels over torch.distributed); with gloo (CPU tests on the emulator build) the
+        three collectives the library needs are served by torch.distributed through callbacks."""
+        self.rank, self.world = rank, world
+        buf = np.zeros(128, dtype=np.uint8)
+        if world == 1:
+            self._check(self.lib.knz_dist_init(self.h, 0, 1, _ptr(buf)))
+            return
+        import torch
+        import torch.distributed as dist
+        if dist.get_backend() == "nccl":
+            if rank == 0:
+                self._check(self.lib.knz_dist_unique_id(_ptr(buf)))
+            t = torch.from_numpy(buf).cuda()
+            dist.broadcast(t, 0)
+            buf = t.cpu().numpy()
+            self._check(self.lib.knz_dist_init(self.h, rank, world, _ptr(buf)))
+            return
+
+        def view(ptr, n):
+            return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint8)), shape=(max(int(n), 1),))[: int(n)]
+
+        def allgather(user, send, nbytes, recv):
+            ts = torch.from_numpy(view(send, nbytes).copy())
+            outs = [torch.empty_like(ts) for _ in range(world)]
+            dist.all_gather(outs, ts)
+            view(recv, world * nbytes)[:] = torch.cat(outs).numpy()
+            return 0
+
+        def gather(user, send, nbytes, recv):
+            ts = torch.from_numpy(view(send, nbytes).copy())
+            if rank == 0:
+                outs = [torch.empty_like(ts) for _ in range(world)]
+                dist.gather(ts, outs, dst=0)
+                view(recv, world * nbytes)[:] = torch.cat(outs).numpy()
+            else:
+                dist.gather(ts, None, dst=0)
+            return 0
+
+        def bcast(user, buf_, nbytes):
+            ts = torch.from_numpy(view(buf_, nbytes).copy())
+            dist.broadcast(ts, 0)
+            view(buf_, nbytes)[:] = ts.numpy()
+            return 0
+
+        ft = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p)
+        fb = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64)
+        self._cbs = (ft(allgather), ft(gather), fb(bcast))  # keep the trampolines alive
+        self._check(self.lib.knz_dist_init_transport(self.h, rank, world, ctypes.cast(self._cbs[0], ctypes.c_void_p),
+                                                     ctypes.cast(self._cbs[1], ctypes.c_void_p),
+                                                     ctypes.cast(self._cbs[2], ctypes.c_void_p), None))
+
+    def compress_dist(self, data, transform="BWT+RANK+ZRLT", entropy="ANS0", block_size=4 << 20, out=None):
+        """Collective: every rank passes the whole input; rank 0 gets the stream (others an empty array)."""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        nblk = data.size // block_size + 1
+        cap = 2 * data.size + data.size // 2 + nblk * (1024 + (131072 * (block_size // (4 << 20) + 1) if entropy == "ANS1" else 0)) + 65536
+        if out is None:
+            out = np.empty(cap if getattr(self, "rank", 0) == 0 else 16, dtype=np.uint8)
+        n = ctypes.c_int64(0)
+        self._check(self.lib.knz_compress_dist(self.h, transform.encode(), entropy.encode(), block_size, _ptr(data),
+                                               data.size, _ptr(out), out.size, ctypes.byref(n)))
+        return out[: n.value]
+
+    def decompress_dist(self, comp, cap, out=None):
+        """Collective: every rank passes the whole stream; each rank fills the blocks it owns in `out`."""
+        comp = np.ascontiguousarray(comp, dtype=np.uint8)
+        if out is None:
+            out = np.zeros(max(cap, 1), dtype=np.uint8)
+        n = ctypes.c_int64(0)
+        self._check(self.lib.knz_decompress_dist(self.h, _ptr(comp), comp.size, _ptr(out), cap, ctypes.byref(n)))
         return out[: n.value]
 
     # ---- block level (EncodingTask::run / DecodingTask::run bodies)

@@ -350,6 +350,8 @@ inline cudaError_t cudaGetLastError() { return 0; }
 inline cudaError_t cudaPeekAtLastError() { return 0; }
 inline const char* cudaGetErrorString(cudaError_t) { return "cusim"; }
 inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = nullptr; return 0; }
+#define cudaEventDisableTiming 2
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = nullptr; return 0; }
 inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
 inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }

@@ -252,6 +252,7 @@ def test_gpu_zrlt_odd_parity_expansion(gpu):
     """ZRLT at odd swap parity on 0xFE/0xFF-heavy input expands a block up to the reference's
     max(bs + bs/8, 256 KiB) task buffer: the stage buffers must hold that (the neighbours of the
     block in the batch stay intact) and the stream must decode."""
+    from kanzi_b200 import KanziGpuError
     bs = 65536
     heavy = (rng_bytes(6 * bs, 77, 4) + 252).astype(np.uint8)
     plain = synth.synth_text(2 * bs, 78)
@@ -260,9 +261,18 @@ def test_gpu_zrlt_odd_parity_expansion(gpu):
         comp = gpu.compress(data, tname, "ANS0", bs)
         back = gpu.decompress(comp, data.size)
         assert back.size == data.size and np.array_equal(back, data), tname
-        comp = gpu.compress(np.full(3 * bs + 17, 0xFF, dtype=np.uint8), tname, "NONE", bs)
-        back = gpu.decompress(comp, 3 * bs + 17)
-        assert np.array_equal(back, np.full(3 * bs + 17, 0xFF, dtype=np.uint8)), tname
+        # all-0xFF blocks double in size: the encoder must survive it; like the reference's, the stream is
+        # then refused by the decoder (post-transform length > 1.5 x block size,
+        # io/CompressedInputStream.cpp:893-903) unless the expansion stayed below that limit
+        ff = np.full(3 * bs + 17, 0xFF, dtype=np.uint8)
+        comp = gpu.compress(ff, tname, "NONE", bs)
+        try:
+            back = gpu.decompress(comp, ff.size)
+            assert np.array_equal(back, ff), tname
+        except KanziGpuError as e:
+            assert e.code == 15, e
+        back = gpu.decompress(gpu.compress(data, tname, "ANS0", bs), data.size)
+        assert np.array_equal(back, data), tname  # the context is still healthy
 
 
 def test_gpu_rejects_oversized_parameters(gpu):

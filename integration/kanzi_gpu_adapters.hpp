@@ -2,9 +2,10 @@
 //
 // This header is what a kanzi maintainer adds to the reference tree: three adapter
 // classes deriving from the reference's own plugin interfaces and forwarding to the
-// C ABI (include/knz_gpu.h).  It is compile-checked against the unmodified reference
-// headers by __graft_entry__.build() when /root/reference is present; it is not part
-// of the product library (the reference headers do not travel to the GPU box).
+// C ABI (include/knz_gpu.h).  It is compiled against the unmodified reference headers
+// by oracle/Makefile (target refgpu: the reference's stream classes rebuilt with the
+// three factory switches routed here, integration/knz_reference_hooks.hpp) and executed
+// on the GPU box by tests/test_gpu_adapters.py; it is not part of the product library.
 //
 //   GpuTransform      : kanzi::Transform<byte>   (src/Transform.hpp:31-48)
 //   GpuEntropyEncoder : kanzi::EntropyEncoder    (src/EntropyEncoder.hpp:25-40)
@@ -18,6 +19,7 @@
 // DecodingTask<T>::run call knz_encode_blocks / knz_decode_blocks for a batch of
 // blocks instead of building a TransformSequence + codec per block.
 #pragma once
+#include <mutex>
 #include <stdexcept>
 #include <vector>
 
@@ -31,24 +33,43 @@
 
 namespace kanzi {
 
-// One process-wide context per device; the C ABI serialises calls per context.
+// One process-wide context per device, shared by every worker thread of the stream classes
+// (up to 64 tasks, io/CompressedOutputStream.cpp:40,512-525): every C-ABI entry point locks its
+// context, so concurrent stage calls serialise on the device.  Stage-level calls handle one
+// block at a time: a batch capacity of 2 is enough.  Provisioned for the largest block size seen.
 inline knz_ctx* knzSharedContext(int maxBlockSize = 4 * 1024 * 1024)
 {
+    static std::mutex mtx;
     static knz_ctx* ctx = nullptr;
-    if (ctx == nullptr && knz_create(0, maxBlockSize, 64, &ctx) != KNZ_OK)
-        throw std::runtime_error("knz_create failed: no usable CUDA device (there is no CPU fallback)");
+    static int provisioned = 0;
+    std::lock_guard<std::mutex> lock(mtx);
+    maxBlockSize = (maxBlockSize + 15) & ~15;
+    if (maxBlockSize < 65536)
+        maxBlockSize = 65536;
+    if (ctx != nullptr && maxBlockSize > provisioned) {
+        knz_destroy(ctx); // nobody holds a stage call across block sizes: streams are created one after another
+        ctx = nullptr;
+    }
+    if (ctx == nullptr) {
+        if (knz_create(0, maxBlockSize, 2, &ctx) != KNZ_OK)
+            throw std::runtime_error("knz_create failed: no usable CUDA device (there is no CPU fallback)");
+        provisioned = maxBlockSize;
+    }
     return ctx;
 }
 
 class GpuTransform FINAL : public Transform<byte> {
 public:
-    // type = wire id (TransformFactory.hpp:49-73): BWT_TYPE, RANK_TYPE, MTFT_TYPE, ZRLT_TYPE
+    // type = wire id (TransformFactory.hpp:49-73): BWT_TYPE, RANK_TYPE, MTFT_TYPE, ZRLT_TYPE, SRT_TYPE
     GpuTransform(int type, knz_ctx* ctx) : _type(type), _ctx(ctx) {}
     ~GpuTransform() {}
 
     bool forward(SliceArray<byte>& src, SliceArray<byte>& dst, int length) { return run(src, dst, length, false); }
     bool inverse(SliceArray<byte>& src, SliceArray<byte>& dst, int length) { return run(src, dst, length, true); }
-    int getMaxEncodedLength(int srcLen) const { return (_type == KNZ_T_BWT) ? srcLen + 33 : srcLen; }
+    int getMaxEncodedLength(int srcLen) const
+    {
+        return (_type == KNZ_T_BWT) ? srcLen + 33 : (_type == KNZ_T_SRT) ? srcLen + 1024 : srcLen;
+    }
 
 private:
     int _type;
@@ -89,7 +110,7 @@ public:
     {
         if (len == 0)
             return 0;
-        _buf.resize(size_t(len) + (len >> 2) + 8192);
+        _buf.resize(size_t(len) + (len >> 2) + 8192 + 140000 * size_t((len >> 22) + 1));
         int64_t bits = 0;
         if (knz_entropy_encode(_ctx, _type, reinterpret_cast<const uint8_t*>(&block[blkptr]), int(len), _buf.data(),
                                int64_t(_buf.size()), &bits) != KNZ_OK)
@@ -109,9 +130,13 @@ private:
 
 class GpuEntropyDecoder FINAL : public EntropyDecoder {
 public:
-    // `availableBits`: bits left in the task's private stream (DecodingTask copies each
-    // block into its own buffer first: io/CompressedInputStream.cpp:843-856).
-    GpuEntropyDecoder(InputBitStream& ibs, int type, knz_ctx* ctx, uint64 availableBits)
+    // The device decodes a whole block payload at once, so the adapter hands it every bit the block
+    // has left.  `availableBits` > 0: that many bits are read (a one-line patch in DecodingTask::run can
+    // publish them through the Context).  availableBits == 0: the stream is the
+    // task's PRIVATE per-block stream (DecodingTask copies each block into its own buffer when jobs > 1:
+    // io/CompressedInputStream.cpp:843-856,870-872) and is read to its end; trailing padding bits are
+    // harmless because every codec knows its own lengths.
+    GpuEntropyDecoder(InputBitStream& ibs, int type, knz_ctx* ctx, uint64 availableBits = 0)
         : _ibs(ibs), _type(type), _ctx(ctx), _avail(availableBits)
     {
     }
@@ -121,10 +146,18 @@ public:
     {
         if (len == 0)
             return 0;
-        const size_t nbytes = size_t((_avail + 7) >> 3);
-        _buf.assign(nbytes + 16, 0);
-        _ibs.readBits(reinterpret_cast<byte*>(_buf.data()), uint(_avail));
-        if (knz_entropy_decode(_ctx, _type, _buf.data(), int64_t(_avail), reinterpret_cast<uint8_t*>(&block[blkptr]),
+        uint64 bits = _avail;
+        if (bits > 0) {
+            _buf.assign(size_t((bits + 7) >> 3) + 16, 0);
+            _ibs.readBits(reinterpret_cast<byte*>(_buf.data()), uint(bits));
+        } else {
+            _buf.clear();
+            while (_ibs.hasMoreToRead())
+                _buf.push_back(uint8_t(_ibs.readBits(8)));
+            bits = uint64(_buf.size()) * 8;
+            _buf.resize(_buf.size() + 16, 0);
+        }
+        if (knz_entropy_decode(_ctx, _type, _buf.data(), int64_t(bits), reinterpret_cast<uint8_t*>(&block[blkptr]),
                                int(len)) != KNZ_OK)
             return -1;
         return int(len);

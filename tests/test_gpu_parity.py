@@ -254,7 +254,9 @@ def test_gpu_zrlt_odd_parity_expansion(gpu):
     block in the batch stay intact) and the stream must decode."""
     from kanzi_b200 import KanziGpuError
     bs = 65536
-    heavy = (rng_bytes(6 * bs, 77, 4) + 252).astype(np.uint8)
+    # 2 of 6 byte values (0xFE, 0xFF) cost two bytes under ZRLT: blocks grow by a third -- beyond the old
+    # stage-buffer slot (bs + bs/16) but below the decoder's 1.5 x block-size limit
+    heavy = (rng_bytes(6 * bs, 77, 6) + 250).astype(np.uint8)
     plain = synth.synth_text(2 * bs, 78)
     data = np.concatenate([plain[:bs], heavy[: 3 * bs], plain[bs:], heavy[3 * bs:]])
     for tname in ("BWT+ZRLT", "RANK+ZRLT", "MTFT+ZRLT"):

@@ -440,6 +440,12 @@ def run_ours(args, rank, world, local_rank):
            "api": ("knz_compress + knz_decompress" if world == 1 else "knz_compress_dist + knz_decompress_dist")
                   + " (host pinned buffers; at N > 1 every rank uploads its own blocks / its own blocks' bit ranges)"}
 
+    # the library's communicator is torn down while every rank is still here (communicator teardown
+    # synchronises the ranks; interleaving it with torch's own teardown on another rank can deadlock)
+    launch_count_total = launches
+    barrier()
+    ctx.close()
+    barrier()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -488,7 +494,6 @@ def run_ours(args, rank, world, local_rank):
         "decode_pipeline": rl(my_bytes + comp_share, d_ms["total"]),
     }
     # BASELINE config 4: -t NONE -e {HUFFMAN, ANS0, ANS1} x block size, device-resident, kernel-only GB/s
-    ctx.close()
     del d_in, d_dec, d_stream
     torch.cuda.empty_cache()
     sweep = {}

@@ -839,6 +839,265 @@ sbrt_rank_fast_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkS
     }
 }
 
+// ---- forward replay, four lanes per tile ------------------------------------------------
+// The warp-per-tile replays above spend a whole warp instruction on every step of ONE tile
+// (36 warp instructions per symbol: issue-bound).  Here a quad owns a tile: lane q keeps ranks
+// 8q..8q+7 in registers (the 32 ranks that post-BWT data touches almost all the time), ranks
+// 32..255 stay in shared memory, and the eight quads of a warp replay eight tiles in lockstep:
+// the same instruction stream now advances eight symbols.  A step is
+//   find    each lane compares its 8 symbols with c; one ballot tells the quad who holds it
+//   key     y = i + t1 (RANK) / i (MTFT), broadcast from the holder by two quad shuffles
+//   update  every register entry decides locally whether it keeps its value, takes the entry of
+//           the rank above or receives the new entry (the list is sorted by key, so "key <= y and
+//           rank <= r" is exactly the range that moves); the only cross-lane traffic is the last
+//           entry of the lane above
+// A symbol that is not among the top 32 takes a rare, warp-uniform slow path over the shared list.
+#define RQ_WARPS 2
+template <int MODE>
+__global__ void __launch_bounds__(RQ_WARPS * 32)
+sbrt_rank_quad_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkState* __restrict__ stOut, int maxTiles,
+                      const uint2* __restrict__ occ)
+{
+    __shared__ u64 s_keys[RQ_WARPS][256];
+    __shared__ u32 s_lK[RQ_WARPS][8][256]; // per tile: stored keys by rank (ranks 32.. = the deep list)
+    __shared__ u32 s_lP[RQ_WARPS][8][256]; // per tile: (last access time << 8) | symbol by rank
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    const int tile0 = (blockIdx.x * RQ_WARPS + w) * 8;
+    const BlkState bs = stIn[b];
+    if (stOut[b].swaps == bs.swaps)
+        return;
+    const int n = bs.len;
+    if ((i64)tile0 * S_TILE >= n)
+        return;
+    u32 m1, m2;
+    int sh;
+    sbrt_masks(MODE, m1, m2, sh);
+    const u8* __restrict__ src = blk_src(bt, bs, b);
+    u8* __restrict__ dst = blk_dst(bt, bs, b);
+    // ---- sorted lists at the first position of the warp's eight tiles (whole warp per tile)
+    for (int jt = 0; jt < 8; jt++) {
+        const int t = tile0 + jt;
+        if ((i64)t * S_TILE >= n)
+            break;
+        u64* keys = s_keys[w];
+        const uint2* o = occ + ((i64)b * maxTiles + t) * 256;
+        u64 myKey[8];
+        u32 myP[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int sym = 32 * k + lane;
+            const uint2 e = o[sym];
+            myKey[k] = sbrt_key(e.x, e.y, sym, m1, m2, sh);
+            keys[sym] = myKey[k];
+            myP[k] = e.x ? e.x - 1 : 0u;
+        }
+        __syncwarp();
+        int rk[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+        for (int u = 0; u < 256; u++) {
+            const u64 ku = keys[u];
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                rk[k] += (ku > myKey[k]) ? 1 : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) { // stored key = q << sh (even in RANK mode), see InvList
+            s_lK[w][jt][rk[k]] = (u32)(myKey[k] >> 32) << sh;
+            s_lP[w][jt][rk[k]] = (myP[k] << 8) | (u32)(32 * k + lane);
+        }
+        __syncwarp();
+    }
+    const int q = lane & 3, jq = lane >> 2, qbase = lane & ~3;
+    const int base = (tile0 + jq) * S_TILE;
+    const bool active = base < n;
+    const int end = active ? min(base + S_TILE, n) : 0;
+    u32 K[8], P[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        K[k] = s_lK[w][jq][8 * q + k];
+        P[k] = s_lP[w][jq][8 * q + k];
+    }
+    u32* dK = &s_lK[w][jq][32];
+    u32* dP = &s_lP[w][jq][32];
+
+    // Register-list update of one access that comes from rank R (entry: stored key yn, payload ne,
+    // compare value y); LIVE masks quads without a step.  The lane's entries are sorted by key, so the
+    // ones with key <= y are a suffix starting at gq = #(K > y): entries gq+1 .. min(R - 8q, 7) take the
+    // entry above them, entry gq receives the new entry -- or, when the lane above ends with a key <= y,
+    // that lane's last entry.  Written with one move mask so that the compiler emits predicated moves.
+#define RQ_UPDATE(R, LIVE)                                                                      \
+    {                                                                                           \
+        u32 upK = __shfl_up_sync(FULL_MASK, K[7], 1);                                           \
+        const u32 upP = __shfl_up_sync(FULL_MASK, P[7], 1);                                     \
+        if (q == 0)                                                                             \
+            upK = 0xFFFFFFFFu;                                                                  \
+        int gq = 0;                                                                             \
+        _Pragma("unroll") for (int k = 0; k < 8; k++) gq += (K[k] > y) ? 1 : 0;                 \
+        const int hi_ = min((R) - 8 * q, 7);                                                    \
+        /* bits gq .. hi_ (empty when hi_ < gq or the quad is not live) */                      \
+        u32 mv = ((LIVE) && hi_ >= gq) ? ((2u << hi_) - (1u << gq)) : 0u;                       \
+        const bool fromUp = upK <= y;                                                           \
+        const u32 k0 = fromUp ? upK : yn, p0 = fromUp ? upP : ne;                               \
+        _Pragma("unroll") for (int k = 7; k >= 1; k--)                                          \
+        {                                                                                       \
+            if (mv & (1u << k)) {                                                               \
+                const bool first = (k == gq);                                                   \
+                K[k] = first ? yn : K[k - 1];                                                   \
+                P[k] = first ? ne : P[k - 1];                                                   \
+            }                                                                                   \
+        }                                                                                       \
+        if (mv & 1u) {                                                                          \
+            K[0] = k0;                                                                          \
+            P[0] = p0;                                                                          \
+        }                                                                                       \
+    }
+
+    for (int g = 0; g < S_TILE; g += 64) {
+        const int pos0 = base + g;
+        if (!__any_sync(FULL_MASK, active && pos0 < end))
+            break;
+        uint4 in = make_uint4(0, 0, 0, 0);
+        {
+            const int p = pos0 + 16 * q;
+            if (active && p < end) {
+                if (p + 16 <= n) {
+                    in = *reinterpret_cast<const uint4*>(src + p); // buffers and tiles are 16-byte aligned
+                } else {
+                    u32 wv[4] = { 0, 0, 0, 0 };
+                    for (int k = 0; k < 16; k++)
+                        if (p + k < n)
+                            wv[k >> 2] |= (u32)src[p + k] << (8 * (k & 3));
+                    in = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+                }
+            }
+        }
+        uint4 outv = make_uint4(0, 0, 0, 0);
+#pragma unroll 1
+        for (int tt = 0; tt < 4; tt++) {
+            const int sl = qbase + tt;
+            u32 ov0 = 0, ov1 = 0, ov2 = 0, ov3 = 0;
+#pragma unroll 1
+            for (int wi = 0; wi < 4; wi++) { // four steps unrolled per trip (the step body is large: keep it in the I-cache)
+            const u32 wsel = (wi == 0) ? in.x : (wi == 1) ? in.y : (wi == 2) ? in.z : in.w;
+            const u32 w4 = __shfl_sync(FULL_MASK, wsel, sl);
+            u32 o4 = 0;
+#pragma unroll
+            for (int xb = 0; xb < 4; xb++) {
+                const int x = 4 * wi + xb;
+                const u32 i = (u32)(pos0 + 16 * tt + x);
+                const bool live = active && ((int)i < end);
+                const u32 c = (w4 >> (8 * xb)) & 0xFF;
+                // find c among the lane's eight entries
+                u32 sel = 0;
+                int kk = -1;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const bool m = (P[k] & 0xFF) == c;
+                    sel = m ? P[k] : sel;
+                    kk = m ? k : kk;
+                }
+                const u32 bal = (__ballot_sync(FULL_MASK, live && kk >= 0) >> qbase) & 0xFu;
+                const bool miss = live && bal == 0;
+                int r = 0, rsrc = 0;
+                u32 y = 0, yn = 0, ne = 0;
+                bool upd = false;
+                if (__any_sync(FULL_MASK, miss)) {
+                    // ---- rare: c sits below rank 31 (warp-uniform branch; quads without a miss idle)
+                    int found = 1 << 20;
+                    if (miss)
+                        for (int d = q; d < 224; d += 4)
+                            if ((dP[d] & 0xFF) == c) {
+                                found = d;
+                                break;
+                            }
+                    found = min(found, __shfl_xor_sync(FULL_MASK, found, 1));
+                    found = min(found, __shfl_xor_sync(FULL_MASK, found, 2));
+                    const int d = miss ? min(found, 223) : 0;
+                    const u32 ph = miss ? dP[d] : 0u;
+                    const u32 yd = InvList<MODE>::key_raw(i, ph >> 8);
+                    int cg = 0; // register entries with a larger key
+#pragma unroll
+                    for (int k = 0; k < 8; k++)
+                        cg += (K[k] > yd) ? 1 : 0;
+                    cg += __shfl_xor_sync(FULL_MASK, cg, 1);
+                    cg += __shfl_xor_sync(FULL_MASK, cg, 2);
+                    const u32 evK = __shfl_sync(FULL_MASK, K[7], qbase + 3);
+                    const u32 evP = __shfl_sync(FULL_MASK, P[7], qbase + 3);
+                    __syncwarp();
+                    if (miss && q == 0) {
+                        const u32 ynd = InvList<MODE>::key_store(yd);
+                        const u32 ned = (i << 8) | c;
+                        if (cg >= 32) { // stays in the deep list: new deep position = entries above with a larger key
+                            int pd = d;
+                            while (pd > 0 && dK[pd - 1] <= yd)
+                                pd--;
+                            for (int e = d; e > pd; e--) {
+                                dK[e] = dK[e - 1];
+                                dP[e] = dP[e - 1];
+                            }
+                            dK[pd] = ynd;
+                            dP[pd] = ned;
+                        } else { // enters the registers: rank 31 drops to the top of the deep list
+                            for (int e = d; e > 0; e--) {
+                                dK[e] = dK[e - 1];
+                                dP[e] = dP[e - 1];
+                            }
+                            dK[0] = evK;
+                            dP[0] = evP;
+                        }
+                    }
+                    __syncwarp();
+                    if (miss) {
+                        r = 32 + d;
+                        rsrc = 32; // the register list sees the entry arrive from "rank 32"
+                        y = yd;
+                        yn = InvList<MODE>::key_store(yd);
+                        ne = (i << 8) | c;
+                        upd = cg < 32;
+                    }
+                }
+                // ---- common: c is among the top 32
+                {
+                    const int hl = qbase + __ffs((int)bal) - 1;
+                    const int rr = __shfl_sync(FULL_MASK, 8 * q + kk, hl & 31);
+                    const u32 ph = __shfl_sync(FULL_MASK, sel, hl & 31);
+                    if (live && bal != 0) {
+                        r = rr;
+                        rsrc = rr;
+                        y = InvList<MODE>::key_raw(i, ph >> 8);
+                        yn = InvList<MODE>::key_store(y);
+                        ne = (i << 8) | c;
+                        upd = true;
+                    }
+                }
+                RQ_UPDATE(rsrc, upd)
+                o4 |= (u32)r << (8 * xb);
+            }
+            ov0 = (wi == 0) ? o4 : ov0;
+            ov1 = (wi == 1) ? o4 : ov1;
+            ov2 = (wi == 2) ? o4 : ov2;
+            ov3 = (wi == 3) ? o4 : ov3;
+            }
+            if (q == tt)
+                outv = make_uint4(ov0, ov1, ov2, ov3);
+        }
+        {
+            const int p = pos0 + 16 * q;
+            if (active && p < end) {
+                if (p + 16 <= end) {
+                    *reinterpret_cast<uint4*>(dst + p) = outv;
+                } else {
+                    const u32 wv[4] = { outv.x, outv.y, outv.z, outv.w };
+                    for (int k = 0; k < 16; k++)
+                        if (p + k < end)
+                            dst[p + k] = (u8)(wv[k >> 2] >> (8 * (k & 3)));
+                }
+            }
+        }
+    }
+#undef RQ_UPDATE
+}
+
 void launch_sbrt_rank_only(const BufTable& bt, const BlkState* stIn, const BlkState* stOut, int nBlocks, int maxLen,
                            int mode, Workspace& ws, cudaStream_t s, u64* launches)
 {
@@ -849,13 +1108,23 @@ void launch_sbrt_rank_only(const BufTable& bt, const BlkState* stIn, const BlkSt
     KLAUNCH(sbrt_fold_kernel, nBlocks, 256, s, stIn, stOut, maxTiles, occ);
     const dim3 rg((tiles + R_WARPS - 1) / R_WARPS, nBlocks);
     const bool small = maxLen < (1 << 24);
+    static int variant = -1; // KNZ_SBRT_FWD=0 selects the warp-per-tile replay (experiments)
+    if (variant < 0) {
+        const char* e = getenv("KNZ_SBRT_FWD");
+        variant = e ? atoi(e) : 1;
+    }
+    const dim3 qg((tiles + 8 * RQ_WARPS - 1) / (8 * RQ_WARPS), nBlocks);
     if (mode == 1) {
-        if (small)
+        if (small && variant == 1)
+            KLAUNCH((sbrt_rank_quad_kernel<1>), qg, RQ_WARPS * 32, s, bt, stIn, stOut, maxTiles, occ);
+        else if (small)
             KLAUNCH((sbrt_rank_fast_kernel<1>), rg, R_WARPS * 32, s, bt, stIn, stOut, maxTiles, occ);
         else
             KLAUNCH((sbrt_rank_kernel<u64, 1>), rg, R_WARPS * 32, s, bt, stIn, stOut, maxTiles, occ);
     } else {
-        if (small)
+        if (small && variant == 1)
+            KLAUNCH((sbrt_rank_quad_kernel<2>), qg, RQ_WARPS * 32, s, bt, stIn, stOut, maxTiles, occ);
+        else if (small)
             KLAUNCH((sbrt_rank_fast_kernel<2>), rg, R_WARPS * 32, s, bt, stIn, stOut, maxTiles, occ);
         else
             KLAUNCH((sbrt_rank_kernel<u64, 2>), rg, R_WARPS * 32, s, bt, stIn, stOut, maxTiles, occ);

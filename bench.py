@@ -251,6 +251,11 @@ def entropy_sweep(dev, peak, total):
     return out
 
 
+def progress(rank, *a):
+    """Progress notes on stderr (stdout carries the one JSON line)."""
+    print(f"[bench rank {rank}] {time.strftime('%H:%M:%S')}", *a, file=sys.stderr, flush=True)
+
+
 def run_ours(args, rank, world, local_rank):
     import ctypes
     import hashlib
@@ -271,6 +276,7 @@ def run_ours(args, rank, world, local_rank):
     batch = max(1, min(args.batch, nb))
     ctx = Context(local_rank, BLOCK, batch)
     ctx.dist_init(rank, world)  # the library opens its own NCCL communicator (csrc/dist.cu)
+    progress(rank, "context + communicator ready")
     L = ctx.lib
     host_in = torch.from_numpy(data).view(nblocks, BLOCK)[my].contiguous().pin_memory()
     d_in = torch.empty((max(nb, 1), BLOCK), dtype=torch.uint8, device=dev)
@@ -333,6 +339,7 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(max(1, args.warmup)):
         comp_bytes, _ = step_dev()
     barrier()
+    progress(rank, "warm-up done")
     assert bool((d_dec[:nb] == d_in[:nb]).all().item()), "decode(encode(x)) != x"
     if rank == 0:
         stream = d_stream[:comp_bytes].cpu().numpy()
@@ -373,6 +380,7 @@ def run_ours(args, rank, world, local_rank):
         launches = int(lt.item())
     total_s, enc_s, dec_s = [float(x) for x in t_local.tolist()]
     per_step = total_s / args.steps
+    progress(rank, f"device-resident leg done: {per_step * 1e3:.1f} ms/step")
 
     # ---- e2e through the public API with HOST buffers (pinned): knz_compress / knz_decompress at N = 1,
     # knz_compress_dist / knz_decompress_dist at N > 1 -- every rank holds the input (compress) and the
@@ -434,6 +442,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e_enc, e_dec = [float(x) / args.steps for x in t_e.tolist()]
+    progress(rank, f"e2e leg done: {(e_enc + e_dec) * 1e3:.1f} ms/step")
     e2e = {"value": size / (e_enc + e_dec) / 1e6, "unit": "MB/s",
            "h2d_bytes_per_step": int(size + comp.size), "d2h_bytes_per_step": int(comp.size + size),
            "encode_MBps": size / e_enc / 1e6, "decode_MBps": size / e_dec / 1e6,

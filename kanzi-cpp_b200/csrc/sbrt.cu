@@ -844,14 +844,20 @@ sbrt_rank_fast_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkS
 // (36 warp instructions per symbol: issue-bound).  Here a quad owns a tile: lane q keeps ranks
 // 8q..8q+7 in registers (the 32 ranks that post-BWT data touches almost all the time), ranks
 // 32..255 stay in shared memory, and the eight quads of a warp replay eight tiles in lockstep:
-// the same instruction stream now advances eight symbols.  A step is
-//   find    each lane compares its 8 symbols with c; one ballot tells the quad who holds it
-//   key     y = i + t1 (RANK) / i (MTFT), broadcast from the holder by two quad shuffles
-//   update  every register entry decides locally whether it keeps its value, takes the entry of
-//           the rank above or receives the new entry (the list is sorted by key, so "key <= y and
-//           rank <= r" is exactly the range that moves); the only cross-lane traffic is the last
-//           entry of the lane above
-// A symbol that is not among the top 32 takes a rare, warp-uniform slow path over the shared list.
+// the same instruction stream now advances eight symbols.  An entry is ONE register,
+// (stored key << 8) | symbol -- keys stay below 2^24 for blocks under 8 MiB -- and the last
+// access time of every symbol lives in a per-tile shared-memory table, so a step is
+//   find    each lane compares the low bytes of its 8 entries with c; one ballot tells the quad
+//           who holds it, one quad shuffle broadcasts the rank
+//   key     y = i + lastT[c] (RANK) / i (MTFT): a shared-memory read, no cross-lane traffic
+//   update  the lane's entries are sorted, so the ones with key <= y are a suffix starting at
+//           gq = #(E > Y); entries gq+1 .. min(r - 8q, 7) take the entry above them and entry gq
+//           receives the new entry (or the last entry of the lane above): one move mask, predicated
+//           moves, one shuffle-up
+// ncu (profiles/r02_ncu_rank_quad_*.md): the two-register version of this kernel was bound by the
+// integer ALU pipe (81 % busy, 24 warp instructions per symbol); halving the registers an entry
+// occupies halves the selects.  A symbol below rank 31 takes a rare slow path in which the whole
+// warp searches, re-ranks and shifts the shared list of that tile (7 entries per lane).
 #define RQ_WARPS 2
 template <int MODE>
 __global__ void __launch_bounds__(RQ_WARPS * 32)
@@ -859,8 +865,8 @@ sbrt_rank_quad_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkS
                       const uint2* __restrict__ occ)
 {
     __shared__ u64 s_keys[RQ_WARPS][256];
-    __shared__ u32 s_lK[RQ_WARPS][8][256]; // per tile: stored keys by rank (ranks 32.. = the deep list)
-    __shared__ u32 s_lP[RQ_WARPS][8][256]; // per tile: (last access time << 8) | symbol by rank
+    __shared__ u32 s_lE[RQ_WARPS][8][256]; // per tile: (stored key << 8) | symbol by rank (ranks 32.. = the deep list)
+    __shared__ u32 s_lT[RQ_WARPS][8][256]; // per tile: last access time of every symbol
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int b = blockIdx.y;
     const int tile0 = (blockIdx.x * RQ_WARPS + w) * 8;
@@ -883,14 +889,13 @@ sbrt_rank_quad_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkS
         u64* keys = s_keys[w];
         const uint2* o = occ + ((i64)b * maxTiles + t) * 256;
         u64 myKey[8];
-        u32 myP[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             const int sym = 32 * k + lane;
             const uint2 e = o[sym];
             myKey[k] = sbrt_key(e.x, e.y, sym, m1, m2, sh);
             keys[sym] = myKey[k];
-            myP[k] = e.x ? e.x - 1 : 0u;
+            s_lT[w][jt][sym] = e.x ? e.x - 1 : 0u;
         }
         __syncwarp();
         int rk[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
@@ -901,56 +906,19 @@ sbrt_rank_quad_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkS
                 rk[k] += (ku > myKey[k]) ? 1 : 0;
         }
 #pragma unroll
-        for (int k = 0; k < 8; k++) { // stored key = q << sh (even in RANK mode), see InvList
-            s_lK[w][jt][rk[k]] = (u32)(myKey[k] >> 32) << sh;
-            s_lP[w][jt][rk[k]] = (myP[k] << 8) | (u32)(32 * k + lane);
-        }
+        for (int k = 0; k < 8; k++) // stored key = q << sh (even in RANK mode), see InvList
+            s_lE[w][jt][rk[k]] = (((u32)(myKey[k] >> 32) << sh) << 8) | (u32)(32 * k + lane);
         __syncwarp();
     }
     const int q = lane & 3, jq = lane >> 2, qbase = lane & ~3;
     const int base = (tile0 + jq) * S_TILE;
     const bool active = base < n;
     const int end = active ? min(base + S_TILE, n) : 0;
-    u32 K[8], P[8];
+    u32 E[8];
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        K[k] = s_lK[w][jq][8 * q + k];
-        P[k] = s_lP[w][jq][8 * q + k];
-    }
-    u32* dK = &s_lK[w][jq][32];
-    u32* dP = &s_lP[w][jq][32];
-
-    // Register-list update of one access that comes from rank R (entry: stored key yn, payload ne,
-    // compare value y); LIVE masks quads without a step.  The lane's entries are sorted by key, so the
-    // ones with key <= y are a suffix starting at gq = #(K > y): entries gq+1 .. min(R - 8q, 7) take the
-    // entry above them, entry gq receives the new entry -- or, when the lane above ends with a key <= y,
-    // that lane's last entry.  Written with one move mask so that the compiler emits predicated moves.
-#define RQ_UPDATE(R, LIVE)                                                                      \
-    {                                                                                           \
-        u32 upK = __shfl_up_sync(FULL_MASK, K[7], 1);                                           \
-        const u32 upP = __shfl_up_sync(FULL_MASK, P[7], 1);                                     \
-        if (q == 0)                                                                             \
-            upK = 0xFFFFFFFFu;                                                                  \
-        int gq = 0;                                                                             \
-        _Pragma("unroll") for (int k = 0; k < 8; k++) gq += (K[k] > y) ? 1 : 0;                 \
-        const int hi_ = min((R) - 8 * q, 7);                                                    \
-        /* bits gq .. hi_ (empty when hi_ < gq or the quad is not live) */                      \
-        u32 mv = ((LIVE) && hi_ >= gq) ? ((2u << hi_) - (1u << gq)) : 0u;                       \
-        const bool fromUp = upK <= y;                                                           \
-        const u32 k0 = fromUp ? upK : yn, p0 = fromUp ? upP : ne;                               \
-        _Pragma("unroll") for (int k = 7; k >= 1; k--)                                          \
-        {                                                                                       \
-            if (mv & (1u << k)) {                                                               \
-                const bool first = (k == gq);                                                   \
-                K[k] = first ? yn : K[k - 1];                                                   \
-                P[k] = first ? ne : P[k - 1];                                                   \
-            }                                                                                   \
-        }                                                                                       \
-        if (mv & 1u) {                                                                          \
-            K[0] = k0;                                                                          \
-            P[0] = p0;                                                                          \
-        }                                                                                       \
-    }
+    for (int k = 0; k < 8; k++)
+        E[k] = s_lE[w][jq][8 * q + k];
+    u32* lastT = s_lT[w][jq];
 
     for (int g = 0; g < S_TILE; g += 64) {
         const int pos0 = base + g;
@@ -978,105 +946,131 @@ sbrt_rank_quad_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkS
             u32 ov0 = 0, ov1 = 0, ov2 = 0, ov3 = 0;
 #pragma unroll 1
             for (int wi = 0; wi < 4; wi++) { // four steps unrolled per trip (the step body is large: keep it in the I-cache)
-            const u32 wsel = (wi == 0) ? in.x : (wi == 1) ? in.y : (wi == 2) ? in.z : in.w;
-            const u32 w4 = __shfl_sync(FULL_MASK, wsel, sl);
-            u32 o4 = 0;
+                const u32 wsel = (wi == 0) ? in.x : (wi == 1) ? in.y : (wi == 2) ? in.z : in.w;
+                const u32 w4 = __shfl_sync(FULL_MASK, wsel, sl);
+                u32 o4 = 0;
 #pragma unroll
-            for (int xb = 0; xb < 4; xb++) {
-                const int x = 4 * wi + xb;
-                const u32 i = (u32)(pos0 + 16 * tt + x);
-                const bool live = active && ((int)i < end);
-                const u32 c = (w4 >> (8 * xb)) & 0xFF;
-                // find c among the lane's eight entries
-                u32 sel = 0;
-                int kk = -1;
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const bool m = (P[k] & 0xFF) == c;
-                    sel = m ? P[k] : sel;
-                    kk = m ? k : kk;
-                }
-                const u32 bal = (__ballot_sync(FULL_MASK, live && kk >= 0) >> qbase) & 0xFu;
-                const bool miss = live && bal == 0;
-                int r = 0, rsrc = 0;
-                u32 y = 0, yn = 0, ne = 0;
-                bool upd = false;
-                if (__any_sync(FULL_MASK, miss)) {
-                    // ---- rare: c sits below rank 31 (warp-uniform branch; quads without a miss idle)
-                    int found = 1 << 20;
-                    if (miss)
-                        for (int d = q; d < 224; d += 4)
-                            if ((dP[d] & 0xFF) == c) {
-                                found = d;
-                                break;
-                            }
-                    found = min(found, __shfl_xor_sync(FULL_MASK, found, 1));
-                    found = min(found, __shfl_xor_sync(FULL_MASK, found, 2));
-                    const int d = miss ? min(found, 223) : 0;
-                    const u32 ph = miss ? dP[d] : 0u;
-                    const u32 yd = InvList<MODE>::key_raw(i, ph >> 8);
-                    int cg = 0; // register entries with a larger key
+                for (int xb = 0; xb < 4; xb++) {
+                    const u32 i = (u32)(pos0 + 16 * tt + 4 * wi + xb);
+                    const bool live = active && ((int)i < end);
+                    const u32 c = (w4 >> (8 * xb)) & 0xFF;
+                    // find c among the lane's eight entries
+                    int kk = -1;
 #pragma unroll
                     for (int k = 0; k < 8; k++)
-                        cg += (K[k] > yd) ? 1 : 0;
-                    cg += __shfl_xor_sync(FULL_MASK, cg, 1);
-                    cg += __shfl_xor_sync(FULL_MASK, cg, 2);
-                    const u32 evK = __shfl_sync(FULL_MASK, K[7], qbase + 3);
-                    const u32 evP = __shfl_sync(FULL_MASK, P[7], qbase + 3);
-                    __syncwarp();
-                    if (miss && q == 0) {
-                        const u32 ynd = InvList<MODE>::key_store(yd);
-                        const u32 ned = (i << 8) | c;
-                        if (cg >= 32) { // stays in the deep list: new deep position = entries above with a larger key
-                            int pd = d;
-                            while (pd > 0 && dK[pd - 1] <= yd)
-                                pd--;
-                            for (int e = d; e > pd; e--) {
-                                dK[e] = dK[e - 1];
-                                dP[e] = dP[e - 1];
-                            }
-                            dK[pd] = ynd;
-                            dP[pd] = ned;
-                        } else { // enters the registers: rank 31 drops to the top of the deep list
-                            for (int e = d; e > 0; e--) {
-                                dK[e] = dK[e - 1];
-                                dP[e] = dP[e - 1];
-                            }
-                            dK[0] = evK;
-                            dP[0] = evP;
+                        kk = (((E[k] ^ c) & 0xFF) == 0) ? k : kk;
+                    const u32 bal = (__ballot_sync(FULL_MASK, live && kk >= 0) >> qbase) & 0xFu;
+                    const bool miss = live && bal == 0;
+                    // key of the access: the symbol's last access time sits in shared memory
+                    const u32 t1 = live ? lastT[c] : 0u;
+                    const u32 y = InvList<MODE>::key_raw(i, t1);
+                    const u32 Y = (y << 8) | 0xFFu;                         // E <= Y  <=>  key <= y
+                    const u32 ne = (InvList<MODE>::key_store(y) << 8) | c; // the entry after the access
+                    __syncwarp(); // every lane of the quad has read lastT[c] before it is overwritten
+                    if (live && q == 0)
+                        lastT[c] = i;
+                    int r = 0, rsrc = 0;
+                    bool upd = false;
+                    u32 mm = __ballot_sync(FULL_MASK, miss);
+                    while (mm) {
+                        // ---- rare: c sits below rank 31.  One missing quad at a time, the WHOLE warp works
+                        // on its shared list (224 entries = 7 per lane): search, new position and the shift
+                        // are parallel (a serial walk by one lane cost ~14000 cycles on blocks whose symbols
+                        // come back from the bottom of the list, e.g. byte counters).
+                        const int ml = __ffs((int)mm) - 1; // lane 0 of the quad
+                        const int jm = ml >> 2;
+                        mm &= ~(0xFu << ml);
+                        const u32 cm = __shfl_sync(FULL_MASK, c, ml);
+                        const u32 Ym = __shfl_sync(FULL_MASK, Y, ml);
+                        const u32 nem = __shfl_sync(FULL_MASK, ne, ml);
+                        u32* mE = &s_lE[w][jm][32];
+                        u32 vE[7];
+                        int myd = -1;
+#pragma unroll
+                        for (int t = 0; t < 7; t++) {
+                            vE[t] = mE[lane + 32 * t];
+                            if ((vE[t] & 0xFF) == cm)
+                                myd = lane + 32 * t;
+                        }
+                        const u32 fb = __ballot_sync(FULL_MASK, myd >= 0);
+                        const int d = fb ? __shfl_sync(FULL_MASK, myd, __ffs((int)fb) - 1) : 223;
+                        int cg = 0; // register entries of that quad with a larger key
+                        if (jq == jm) {
+#pragma unroll
+                            for (int k = 0; k < 8; k++)
+                                cg += (E[k] > Ym) ? 1 : 0;
+                        }
+                        cg = __shfl_sync(FULL_MASK, cg, ml) + __shfl_sync(FULL_MASK, cg, ml + 1) +
+                             __shfl_sync(FULL_MASK, cg, ml + 2) + __shfl_sync(FULL_MASK, cg, ml + 3);
+                        const u32 evE = __shfl_sync(FULL_MASK, E[7], ml + 3);
+                        // new position inside the deep list (when the entry stays there): the deep entries
+                        // above d with a larger key; the list is sorted, so they are a prefix
+                        int pd = 0;
+#pragma unroll
+                        for (int t = 0; t < 7; t++)
+                            pd += (lane + 32 * t < d && vE[t] > Ym) ? 1 : 0;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1)
+                            pd += __shfl_xor_sync(FULL_MASK, pd, o);
+                        const bool stays = cg >= 32;
+                        const int lo = stays ? pd : 0; // entries lo .. d-1 move down by one, entry lo is rewritten
+                        __syncwarp();
+                        // every entry takes the old value of the entry above it: lane - 1 of the same round,
+                        // or lane 31 of the previous round (values come from the register snapshot vE)
+#pragma unroll
+                        for (int t = 0; t < 7; t++) {
+                            const int e = lane + 32 * t;
+                            u32 pe = __shfl_up_sync(FULL_MASK, vE[t], 1);
+                            const u32 we = (t > 0) ? __shfl_sync(FULL_MASK, vE[t > 0 ? t - 1 : 0], 31) : 0u;
+                            if (lane == 0 && t > 0)
+                                pe = we;
+                            if (e > lo && e <= d)
+                                mE[e] = pe;
+                        }
+                        if (lane == 0)
+                            mE[lo] = stays ? nem : evE;
+                        __syncwarp();
+                        if (jq == jm) {
+                            r = 32 + d;
+                            rsrc = 32; // the register list sees the entry arrive from "rank 32"
+                            upd = !stays;
                         }
                     }
-                    __syncwarp();
-                    if (miss) {
-                        r = 32 + d;
-                        rsrc = 32; // the register list sees the entry arrive from "rank 32"
-                        y = yd;
-                        yn = InvList<MODE>::key_store(yd);
-                        ne = (i << 8) | c;
-                        upd = cg < 32;
+                    // ---- common: c is among the top 32
+                    {
+                        const int hl = qbase + __ffs((int)bal) - 1;
+                        const int rr = __shfl_sync(FULL_MASK, 8 * q + kk, hl & 31);
+                        if (live && bal != 0) {
+                            r = rr;
+                            rsrc = rr;
+                            upd = true;
+                        }
                     }
-                }
-                // ---- common: c is among the top 32
-                {
-                    const int hl = qbase + __ffs((int)bal) - 1;
-                    const int rr = __shfl_sync(FULL_MASK, 8 * q + kk, hl & 31);
-                    const u32 ph = __shfl_sync(FULL_MASK, sel, hl & 31);
-                    if (live && bal != 0) {
-                        r = rr;
-                        rsrc = rr;
-                        y = InvList<MODE>::key_raw(i, ph >> 8);
-                        yn = InvList<MODE>::key_store(y);
-                        ne = (i << 8) | c;
-                        upd = true;
+                    // ---- register-list update (entry arrives from rank rsrc)
+                    {
+                        u32 upE = __shfl_up_sync(FULL_MASK, E[7], 1);
+                        if (q == 0)
+                            upE = 0xFFFFFFFFu;
+                        int gq = 0; // entries and Y stay below 2^31: the sign of Y - E says E > Y
+#pragma unroll
+                        for (int k = 0; k < 8; k++)
+                            gq += (int)((Y - E[k]) >> 31);
+                        const int hi = min(rsrc - 8 * q, 7);
+                        const u32 mv = (upd && hi >= gq) ? ((2u << hi) - (1u << gq)) : 0u; // bits gq .. hi
+                        const u32 e0 = (upE <= Y) ? upE : ne;
+#pragma unroll
+                        for (int k = 7; k >= 1; k--)
+                            if (mv & (1u << k))
+                                E[k] = (k == gq) ? ne : E[k - 1];
+                        if (mv & 1u)
+                            E[0] = e0;
                     }
+                    o4 |= (u32)r << (8 * xb);
                 }
-                RQ_UPDATE(rsrc, upd)
-                o4 |= (u32)r << (8 * xb);
-            }
-            ov0 = (wi == 0) ? o4 : ov0;
-            ov1 = (wi == 1) ? o4 : ov1;
-            ov2 = (wi == 2) ? o4 : ov2;
-            ov3 = (wi == 3) ? o4 : ov3;
+                ov0 = (wi == 0) ? o4 : ov0;
+                ov1 = (wi == 1) ? o4 : ov1;
+                ov2 = (wi == 2) ? o4 : ov2;
+                ov3 = (wi == 3) ? o4 : ov3;
             }
             if (q == tt)
                 outv = make_uint4(ov0, ov1, ov2, ov3);
@@ -1095,7 +1089,6 @@ sbrt_rank_quad_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkS
             }
         }
     }
-#undef RQ_UPDATE
 }
 
 void launch_sbrt_rank_only(const BufTable& bt, const BlkState* stIn, const BlkState* stOut, int nBlocks, int maxLen,
@@ -1114,15 +1107,16 @@ void launch_sbrt_rank_only(const BufTable& bt, const BlkState* stIn, const BlkSt
         variant = e ? atoi(e) : 1;
     }
     const dim3 qg((tiles + 8 * RQ_WARPS - 1) / (8 * RQ_WARPS), nBlocks);
+    const bool quad = variant == 1 && maxLen < (1 << 23); // keys (up to 2 * length) must fit 24 bits
     if (mode == 1) {
-        if (small && variant == 1)
+        if (quad)
             KLAUNCH((sbrt_rank_quad_kernel<1>), qg, RQ_WARPS * 32, s, bt, stIn, stOut, maxTiles, occ);
         else if (small)
             KLAUNCH((sbrt_rank_fast_kernel<1>), rg, R_WARPS * 32, s, bt, stIn, stOut, maxTiles, occ);
         else
             KLAUNCH((sbrt_rank_kernel<u64, 1>), rg, R_WARPS * 32, s, bt, stIn, stOut, maxTiles, occ);
     } else {
-        if (small && variant == 1)
+        if (quad)
             KLAUNCH((sbrt_rank_quad_kernel<2>), qg, RQ_WARPS * 32, s, bt, stIn, stOut, maxTiles, occ);
         else if (small)
             KLAUNCH((sbrt_rank_fast_kernel<2>), rg, R_WARPS * 32, s, bt, stIn, stOut, maxTiles, occ);

@@ -397,10 +397,9 @@ struct A1Trailer {
         const u32 xmax_ = 0x80000000u - (cmpl_ << xsh); /* freq << (31 - lr) */                \
         const bool did_ = (LIVE) && (state >= xmax_);                                          \
         const u32 bal_ = __ballot_sync(FULL_MASK, did_);                                       \
-        if (did_) {                                                                            \
-            const u32 idx_ = cnt + (u32)__popc(bal_ & mBelow);                                 \
-            if (idx_ < maxWords)                                                               \
-                wlast[-(i64)idx_] = (u16)__byte_perm(state, 0, 0x4401);                        \
+        if (did_) { /* an overflowing payload keeps rewriting the last slot; cnt reports it afterwards */ \
+            const u32 idx_ = min(cnt + (u32)__popc(bal_ & mBelow), maxWords - 1);             \
+            wlast[-(i64)idx_] = (u16)__byte_perm(state, 0, 0x4401);                            \
             state >>= 16;                                                                      \
         }                                                                                      \
         cnt += (u32)__popc(bal_ & mQuad);                                                      \
@@ -409,22 +408,24 @@ struct A1Trailer {
             state = state + (hi_ & 0x1FFFu) + q_ * cmpl_;                                      \
     }
 
-#define A1_CODE_WARPS 2
+#define A1_CODE_WARPS 1
 // One quad per chunk, lane k owns state k = quarter k of the chunk, walked from its last symbol
 // to its first (ANSRangeEncoder.cpp:216-245).  Words are stored backwards from the top of the
 // chunk's payload region so that they land in decode order; the raw tail bytes sit above them.
 __global__ void __launch_bounds__(A1_CODE_WARPS * 32)
 ans1_code_kernel(BufTable bt, const BlkState* __restrict__ st, int nBlocks, int cpb, int lr,
                  const u64* __restrict__ rec, i64 recStride, u8* __restrict__ pay, i64 payStride, i64 payRegion,
-                 A1Trailer* __restrict__ trailer, int* __restrict__ errFlag)
+                 A1Trailer* __restrict__ trailer, int* __restrict__ errFlag, int qpw)
 {
+    // qpw = quads (chunks) per warp: 8 when there are many chunks (throughput), 1 when there are few, so
+    // that every serial chain gets an SM -- and its L1 / L2 slice -- to itself
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int j = lane >> 2, k = lane & 3;
-    const i64 g = ((i64)blockIdx.x * A1_CODE_WARPS + wib) * 8 + j;
+    const i64 g = ((i64)blockIdx.x * A1_CODE_WARPS + wib) * qpw + j;
     const int b = (int)(g / cpb), c = (int)(g - (i64)b * cpb);
     int m = 0;
     bool valid = false;
-    if (b < nBlocks) {
+    if (j < qpw && b < nBlocks) {
         m = st[b].len;
         valid = c < a1_chunks(m);
     }
@@ -447,23 +448,20 @@ ans1_code_kernel(BufTable bt, const BlkState* __restrict__ st, int nBlocks, int 
     const int qsh = lane & ~3;
     const u32 mQuad = 0xFu << qsh;
     const u32 mBelow = ((1u << k) - 1u) << qsh;
-    u64 ring[8];
+    // the records of the next 24 steps are in flight while a step runs (they stream from HBM once)
+    u64 ring[24];
 #pragma unroll
-    for (int x = 0; x < 8; x++)
+    for (int x = 0; x < 24; x++)
         ring[x] = (x < steps) ? __ldg(rp - x) : 0ull;
     int s = 0;
-    for (; s + 8 <= maxSteps; s += 8) {
+    for (; s < maxSteps; s += 24) { // the last trip runs past the end with its steps masked off
 #pragma unroll
-        for (int x = 0; x < 8; x++) {
+        for (int x = 0; x < 24; x++) {
             const u64 e = ring[x];
-            const int sn = s + 8 + x;
+            const int sn = s + 24 + x;
             ring[x] = (sn < steps) ? __ldg(rp - sn) : 0ull;
             A1_STEP(e, (s + x) < steps)
         }
-    }
-    for (int x = 0; s < maxSteps; s++, x++) {
-        const u64 e = ring[x];
-        A1_STEP(e, s < steps)
     }
     const u32 s1 = __shfl_sync(FULL_MASK, state, (lane & ~3) + 1);
     const u32 s2 = __shfl_sync(FULL_MASK, state, (lane & ~3) + 2);
@@ -615,9 +613,11 @@ void launch_ans1_encode(const EncodeLaunch& L, cudaStream_t s, u64* launches)
     KLAUNCH(ans1_map_kernel, dim3(tiles4, nB), 256, s, L.bt, L.st, cpb, W.tenc, W.rec, W.recStride);
     if (L.evK0)
         cudaEventRecord(L.evK0, s);
-    const int quadsPerCta = A1_CODE_WARPS * 8;
+    const int qpwE = (nch <= 2048) ? 1 : 8;
+    const int quadsPerCta = A1_CODE_WARPS * qpwE;
     KLAUNCH(ans1_code_kernel, (unsigned)((nch + quadsPerCta - 1) / quadsPerCta), A1_CODE_WARPS * 32, s, L.bt, L.st, nB,
-            cpb, ANS1_LR, W.rec, W.recStride, W.pay, W.payStride, W.payRegion, (A1Trailer*)W.trailer, L.errFlag);
+            cpb, ANS1_LR, W.rec, W.recStride, W.pay, W.payStride, W.payRegion, (A1Trailer*)W.trailer, L.errFlag,
+            qpwE);
     if (L.evK1)
         cudaEventRecord(L.evK1, s);
     KLAUNCH(ans1_scan_kernel, nB, 256, s, L.st, cpb, L.nTransforms, W.hbits, (const A1Trailer*)W.trailer, W.pieceOff,
@@ -867,20 +867,22 @@ ans1_dec_tables_kernel(DecodeLaunch L, int cpb, const u32* __restrict__ dlist, c
     }
 }
 
-#define A1_DEC_WARPS 2
+#define A1_DEC_WARPS 1
 // Pass 3, one quad per chunk, lane k = state k = quarter k (ANSRangeDecoder.cpp:259-285).
 __global__ void __launch_bounds__(A1_DEC_WARPS * 32)
-ans1_decode_kernel(DecodeLaunch L, int cpb, const A1DecMeta* __restrict__ meta, const u32* __restrict__ tdec)
+ans1_decode_kernel(DecodeLaunch L, int cpb, const A1DecMeta* __restrict__ meta, const u32* __restrict__ tdec, int qpw)
 {
+    // qpw = quads (chunks) per warp: with few chunks every chain gets an SM of its own, whose L1 then
+    // holds the slot tables of the contexts the chunk keeps returning to
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int j = lane >> 2, k = lane & 3;
-    const i64 g = ((i64)blockIdx.x * A1_DEC_WARPS + wib) * 8 + j;
+    const i64 g = ((i64)blockIdx.x * A1_DEC_WARPS + wib) * qpw + j;
     const int b = (int)(g / cpb), c = (int)(g - (i64)b * cpb);
     if (*L.errFlag != 0)
         return;
     int m = 0;
     bool valid = false;
-    if (b < L.nBlocks) {
+    if (j < qpw && b < L.nBlocks) {
         m = L.preLen[b];
         valid = c < a1_chunks(m);
         if (m <= 32 && c == 0) { // raw block: this quad copies it
@@ -911,6 +913,8 @@ ans1_decode_kernel(DecodeLaunch L, int cpb, const A1DecMeta* __restrict__ meta, 
     const u8* __restrict__ p = L.in + (i64)(valid ? b : 0) * L.inStride;
     u8* __restrict__ o = L.dst + (i64)(valid ? b : 0) * L.dstStride + (i64)c * A1_CH + (i64)k * quarter;
     const u32* __restrict__ T = tdec + (valid ? g : 0) * 256 * 2048;
+    const u32* __restrict__ pw32 = reinterpret_cast<const u32*>(p);
+    const bool aligned4 = (((size_t)p) & 3) == 0;
     const u32 maxWords = M.psz >> 1;
     const int qsh = lane & ~3;
     const u32 mQuad = 0xFu << qsh;
@@ -932,10 +936,18 @@ ans1_decode_kernel(DecodeLaunch L, int cpb, const A1DecMeta* __restrict__ meta, 
         if (need) {
             const u32 idx = cnt + (u32)__popc(bal & mAbove);
             u32 w = 0;
-            if (idx < maxWords)
-                w = a1_rd_bits(p, M.payPos + 16ull * idx, 16);
-            else
+            if (idx < maxWords) {
+                const u64 bp = M.payPos + 16ull * idx;
+                if (aligned4) { // two aligned 32-bit loads + funnel shift instead of five byte loads
+                    const u64 wi = bp >> 5;
+                    const u32 hi = bswap32(__ldg(pw32 + wi)), lo = bswap32(__ldg(pw32 + wi + 1));
+                    w = __funnelshift_l(lo, hi, (u32)(bp & 31)) >> 16;
+                } else {
+                    w = a1_rd_bits(p, bp, 16);
+                }
+            } else {
                 bad = true;
+            }
             state = (state << 16) | w;
         }
         cnt += (u32)__popc(bal & mQuad);
@@ -978,9 +990,10 @@ void launch_ans1_decode(const DecodeLaunch& L, cudaStream_t s, u64* launches)
             (const A1DecMeta*)W.dmeta, W.tdec);
     if (L.evK0)
         cudaEventRecord(L.evK0, s);
-    const int quadsPerCta = A1_DEC_WARPS * 8;
+    const int qpwD = (nch <= 2048) ? 1 : 8;
+    const int quadsPerCta = A1_DEC_WARPS * qpwD;
     KLAUNCH(ans1_decode_kernel, (unsigned)((nch + quadsPerCta - 1) / quadsPerCta), A1_DEC_WARPS * 32, s, L, cpb,
-            (const A1DecMeta*)W.dmeta, W.tdec);
+            (const A1DecMeta*)W.dmeta, W.tdec, qpwD);
     if (L.evK1)
         cudaEventRecord(L.evK1, s);
     *launches += 3;

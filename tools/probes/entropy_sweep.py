@@ -16,7 +16,7 @@ d_all = torch.from_numpy(data).to(dev)
 for bs in (64 << 10, 256 << 10, 1 << 20, 4 << 20, 16 << 20, 32 << 20):
     nblocks = total // bs
     batch = min(nblocks, max(1, (64 << 20) // bs * 4))
-    for ename in ("HUFFMAN", "ANS0", "ANS1"):
+    for ename in (sys.argv[2].split(",") if len(sys.argv) > 2 else ("HUFFMAN", "ANS0", "ANS1")):
         ctx = Context(0, bs, batch)
         ostride = (bs + bs // 4 + 4096 + 131072 * (bs // (4 << 20) + 1) + 255) // 256 * 256
         d_in = d_all[: nblocks * bs].view(nblocks, bs)
@@ -28,7 +28,10 @@ for bs in (64 << 10, 256 << 10, 1 << 20, 4 << 20, 16 << 20, 32 << 20):
         for rep in range(2):
             sharded.encode_shard(ctx, tt, et, bs, d_in, lens, bs, d_blk, d_bits)
             te = ctx.timings()
-            sharded.decode_shard(ctx, tt, et, bs, d_blk, d_bits.cpu().numpy().astype(np.uint64), d_dec)
+            try:
+                sharded.decode_shard(ctx, tt, et, bs, d_blk, d_bits.cpu().numpy().astype(np.uint64), d_dec)
+            except RuntimeError as ex:  # ANS1: blocks the reference cannot decode either
+                print("   decode:", str(ex)[:80])
             td = ctx.timings()
         ok = bool(torch.equal(d_dec, d_in))
         e = int((d_bits.sum().item() + 7) // 8)

@@ -121,6 +121,14 @@ int knz_assemble_stream_dev(knz_ctx* ctx, const uint8_t* d_blockOut, int64_t out
                             uint64_t* endBit);
 /* Stream header bytes (io/CompressedOutputStream.cpp:277-342); returns byte count (20..26). */
 int knz_stream_header(uint64_t tType, int eType, int blockSize, int64_t inputSize, uint8_t out[32]);
+int knz_stream_header_ex(uint64_t tType, int eType, int blockSize, int64_t inputSize, int checksumBits, uint8_t out[32]);
+/* Block checksums (the `checksum` parameter of CompressedOutputStream, io/CompressedOutputStream.cpp:99-117):
+ * bits = 0, 32 or 64.  Encoders of this context then hash every block with kanzi's XXHash32 / XXHash64
+ * (util/XXHash.hpp, seed "KANZ") before the transforms and write the value behind the block length (:674-682,
+ * :804-807); the block-level decoders expect it there.  knz_decompress / knz_decompress_dist read the
+ * checksum size from the stream header and verify every decoded block (io/CompressedInputStream.cpp:
+ * 1003-1022), failing with KNZ_ERR_CRC_CHECK.                                                            */
+int knz_set_checksum(knz_ctx* ctx, int bits);
 
 /* ---- Stage level (what the Transform<byte> / EntropyEncoder adapters call).
  * knz_transform_forward == Transform<byte>::forward (src/Transform.hpp:38):

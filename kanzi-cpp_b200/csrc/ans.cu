@@ -568,8 +568,7 @@ ans_scan_kernel(const BlkState* __restrict__ st, int nBlocks, int maxChunks, int
     const BlkState bs = st[b];
     const int m = bs.len;
     const int nChunks = (eType == E_RAW || m <= 32) ? 1 : ((m + ANS_CHUNK - 1) >> 14);
-    const int dataSize = (m < 256) ? 1 : (ilog2_u32((u32)m) >> 3) + 1;
-    const int hdrBytes = 1 + ((nTransforms > 4) ? 1 : 0) + dataSize;
+    const int hdrBytes = knz_hdr_bytes(m, nTransforms);
     if (threadIdx.x == 0)
         s_carry = (u64)hdrBytes * 8;
     __syncthreads();
@@ -610,9 +609,10 @@ out_prepare_kernel(const BlkState* __restrict__ st, int nTransforms, const u64* 
         ow[i] = 0;
 }
 
-__global__ void block_header_kernel(const BlkState* __restrict__ st, int nBlocks, int nTransforms,
-                                    u8* __restrict__ out, i64 outStride)
+__global__ void block_header_kernel(const BlkState* __restrict__ st, int nBlocks, int hdrInfo,
+                                    const u64* __restrict__ blockHash, u8* __restrict__ out, i64 outStride)
 {
+    const int nTransforms = hdrInfo & 0xFF, ckBytes = hdrInfo >> 8;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nBlocks)
         return;
@@ -632,6 +632,11 @@ __global__ void block_header_kernel(const BlkState* __restrict__ st, int nBlocks
     }
     for (int sh = 8 * (dataSize - 1); sh >= 0; sh -= 8)
         o[p++] = (u8)(m >> sh);
+    if (ckBytes) { // XXHash of the block before the transforms, 32 or 64 bits, MSB first (:804-807)
+        const u64 h = blockHash[b];
+        for (int sh = 8 * (ckBytes - 1); sh >= 0; sh -= 8)
+            o[p++] = (u8)(h >> sh);
+    }
 }
 
 // One CTA per (chunk, block): shift-merge the chunk's header bit string and its
@@ -755,7 +760,7 @@ void launch_out_prepare_and_header(const EncodeLaunch& L, cudaStream_t s, u64* l
     i64 zx64 = (L.outStride / 4 + 255) / 256;
     const int zx = (int)(zx64 < 64 ? zx64 : 64);
     KLAUNCH(out_prepare_kernel, dim3(zx, nB), 256, s, L.st, L.nTransforms, L.blockBits, L.out, L.outStride);
-    KLAUNCH(block_header_kernel, (nB + 127) / 128, 128, s, L.st, nB, L.nTransforms, L.out, L.outStride);
+    KLAUNCH(block_header_kernel, (nB + 127) / 128, 128, s, L.st, nB, L.nTransforms, L.blockHash, L.out, L.outStride);
     *launches += 2;
 }
 

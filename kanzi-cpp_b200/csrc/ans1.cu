@@ -503,8 +503,7 @@ ans1_scan_kernel(const BlkState* __restrict__ st, int cpb, int nTransforms, cons
     __shared__ u32 s_w[8];
     const int b = blockIdx.x;
     const int m = st[b].len;
-    const int dataSize = (m < 256) ? 1 : (ilog2_u32((u32)m) >> 3) + 1;
-    const int hdrBytes = 1 + ((nTransforms > 4) ? 1 : 0) + dataSize;
+    const int hdrBytes = knz_hdr_bytes(m, nTransforms);
     u64 base = (u64)hdrBytes * 8;
     const int nch = a1_chunks(m);
     if (nch == 0) { // stored raw (ANSRangeEncoder.cpp:160-163)

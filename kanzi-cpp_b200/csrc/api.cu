@@ -186,6 +186,9 @@ extern "C" int knz_create(int device, int maxBlockSize, int maxBatchBlocks, knz_
     A(dalloc(&ctx->dPayStart, nb));
     A(dalloc(&ctx->dPreLen, nb));
     A(dalloc(&ctx->errFlag, 4));
+    A(dalloc(&ctx->blockHash, nb));
+    A(dalloc(&ctx->expectHash, nb));
+    A(cudaMallocHost((void**)&ctx->h_hash, sizeof(u64) * nb));
     A(cudaMallocHost((void**)&ctx->h_st, sizeof(BlkState) * nb));
     A(cudaMallocHost((void**)&ctx->h_capEven, sizeof(int) * nb));
     A(cudaMallocHost((void**)&ctx->h_capOdd, sizeof(int) * nb));
@@ -220,12 +223,12 @@ extern "C" void knz_destroy(knz_ctx* ctx)
     void* dev[] = { ctx->bufA, ctx->bufB, ctx->dStageIn, ctx->dOut, ctx->st, ctx->capEven, ctx->capOdd, ctx->slots,
                     ctx->hdrBits, ctx->payBytes, ctx->payOff, ctx->chunkOff, ctx->chunkPos, ctx->blockBits,
                     ctx->blockOff, ctx->streamPos, ctx->dInBits, ctx->dPayStart, ctx->dPreLen, ctx->errFlag,
-                    ctx->dStream, ctx->dPlain, ctx->dPlain2 };
+                    ctx->dStream, ctx->dPlain, ctx->dPlain2, ctx->blockHash, ctx->expectHash };
     for (size_t i = 0; i < sizeof(dev) / sizeof(dev[0]); i++)
         if (dev[i])
             cudaFree(dev[i]);
     void* hst[] = { ctx->h_st, ctx->h_capEven, ctx->h_capOdd, ctx->h_err, ctx->h_preLen, ctx->h_bits,
-                    ctx->h_payStart, ctx->h_pos };
+                    ctx->h_payStart, ctx->h_pos, ctx->h_hash };
     for (size_t i = 0; i < sizeof(hst) / sizeof(hst[0]); i++)
         if (hst[i])
             cudaFreeHost(hst[i]);
@@ -265,6 +268,15 @@ extern "C" int knz_set_decode_groups(knz_ctx* ctx, int groups)
     return KNZ_OK;
 }
 
+extern "C" int knz_set_checksum(knz_ctx* ctx, int bits)
+{
+    if (ctx == NULL || (bits != 0 && bits != 32 && bits != 64))
+        return KNZ_ERR_INVALID_PARAM;
+    std::lock_guard<std::recursive_mutex> lock_(ctx->mtx);
+    ctx->checksumBits = bits;
+    return KNZ_OK;
+}
+
 extern "C" const char* knz_last_error(const knz_ctx* ctx) { return ctx ? ctx->err : "null context"; }
 extern "C" uint64_t knz_launch_count(const knz_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" void* knz_stream(const knz_ctx* ctx) { return ctx ? (void*)ctx->stream : NULL; }
@@ -282,8 +294,9 @@ static int map_kerr(knz_ctx* ctx, int kerr)
              kerr == KERR_OUT_OVERFLOW  ? "output buffer overflow"
              : kerr == KERR_BAD_STREAM  ? "invalid bitstream"
              : kerr == KERR_UNSUPPORTED ? "unsupported stream feature"
+             : kerr == KERR_CRC         ? "block checksum mismatch"
                                         : "internal");
-    return (kerr == KERR_BAD_STREAM) ? KNZ_ERR_INVALID_FILE : KNZ_ERR_PROCESS_BLOCK;
+    return (kerr == KERR_BAD_STREAM) ? KNZ_ERR_INVALID_FILE : (kerr == KERR_CRC) ? KNZ_ERR_CRC_CHECK : KNZ_ERR_PROCESS_BLOCK;
 }
 
 static void add_stage_time(knz_ctx* ctx, int t, float ms)
@@ -439,6 +452,8 @@ int knz_encode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8
     for (int i = 0; i < 8; i++)
         ctx->ms[i] = 0.f;
     CK(cudaEventRecord(ctx->ev[0], s));
+    if (ctx->checksumBits) // XXHash of every block before the transforms (io/CompressedOutputStream.cpp:674-682)
+        launch_xxhash(bt, ctx->st, nB, ctx->checksumBits, ctx->blockHash, NULL, ctx->errFlag, s, &ctx->launches);
     for (int i = 0; i < nt; i++) {
         StageLaunch L;
         L.bt = bt;
@@ -463,7 +478,8 @@ int knz_encode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8
     E.nBlocks = nB;
     E.maxChunks = ctx->maxChunks;
     E.eType = eType;
-    E.nTransforms = nt;
+    E.nTransforms = nt | ((ctx->checksumBits >> 3) << 8);
+    E.blockHash = ctx->blockHash;
     E.slots = ctx->slots;
     E.hdrBits = ctx->hdrBits;
     E.payBytes = ctx->payBytes;
@@ -498,7 +514,7 @@ int knz_encode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8
     if (h_flags)
         for (int b = 0; b < nB; b++)
             h_flags[b] = (u8)ctx->h_st[b].flags;
-    return map_kerr(ctx, ctx->h_err[0] ? ctx->h_err[0] : ctx->h_err[1]);
+    return map_kerr(ctx, ctx->h_err[0] ? ctx->h_err[0] : ctx->h_err[1] ? ctx->h_err[1] : ctx->h_err[2]);
 }
 
 extern "C" int knz_encode_blocks_dev(knz_ctx* ctx, uint64_t tType, int eType, int blockSize, const uint8_t* d_in,
@@ -529,12 +545,18 @@ extern "C" int knz_encode_blocks_dev(knz_ctx* ctx, uint64_t tType, int eType, in
 // Small blocks (<= 15 bytes) are always copy blocks: mode 0x80 | skipFlags>>4
 // with the single NullTransform applied (flags 0x7F), one length byte, raw bytes
 // (io/CompressedOutputStream.cpp:38,691-695).
-u64 knz_frame_small_block(const u8* in, int len, u8* out)
+u64 knz_frame_small_block(const u8* in, int len, u8* out, int ckBits)
 {
     out[0] = 0x87;
     out[1] = (u8)len;
-    memcpy(out + 2, in, (size_t)len);
-    return 8ull * (u64)(2 + len);
+    int p = 2;
+    if (ckBits) {
+        const u64 h = knz_xxhash_host(in, len, ckBits);
+        for (int sh = ckBits - 8; sh >= 0; sh -= 8)
+            out[p++] = (u8)(h >> sh);
+    }
+    memcpy(out + p, in, (size_t)len);
+    return 8ull * (u64)(p + len);
 }
 
 extern "C" int knz_encode_blocks(knz_ctx* ctx, uint64_t tType, int eType, int blockSize, const uint8_t* in,
@@ -562,7 +584,8 @@ extern "C" int knz_encode_blocks(knz_ctx* ctx, uint64_t tType, int eType, int bl
                 return KNZ_ERR_BLOCK_SIZE;
             }
             if (len <= 15) {
-                outBits[off + b] = knz_frame_small_block(in + (i64)(off + b) * inStride, len, out + (i64)(off + b) * outStride);
+                outBits[off + b] = knz_frame_small_block(in + (i64)(off + b) * inStride, len, out + (i64)(off + b) * outStride,
+                                                         ctx->checksumBits);
                 if (skipFlags)
                     skipFlags[off + b] = 0x7F;
             } else {
@@ -656,13 +679,15 @@ struct HostBits {
     }
 };
 
-extern "C" int knz_stream_header(uint64_t tType, int eType, int blockSize, int64_t inputSize, uint8_t out[32])
+extern "C" int knz_stream_header_ex(uint64_t tType, int eType, int blockSize, int64_t inputSize, int checksumBits,
+                                    uint8_t out[32])
 {
+    const u32 ckSize = (checksumBits == 32) ? 1u : (checksumBits == 64) ? 2u : 0u; // :290-296
     memset(out, 0, 32);
     HostBits w = { out, 0 };
     w.put(0x4B414E5A, 32);
     w.put(6, 4);
-    w.put(0, 2);
+    w.put(ckSize, 2);
     w.put((u64)eType, 5);
     w.put(tType, 48);
     w.put((u64)(blockSize >> 4), 28);
@@ -679,7 +704,7 @@ extern "C" int knz_stream_header(uint64_t tType, int eType, int blockSize, int64
     w.put(0, 15);
     const u32 HASH = 0x1E35A7BDu;
     u32 ck = HASH * (0x01030507u * 6u);
-    ck ^= HASH * (u32)~0u;
+    ck ^= HASH * (u32)~ckSize;
     ck ^= HASH * (u32)~(u32)eType;
     ck ^= HASH * (u32)((~tType) >> 32);
     ck ^= HASH * (u32)(~tType);
@@ -691,6 +716,11 @@ extern "C" int knz_stream_header(uint64_t tType, int eType, int blockSize, int64
     ck = (ck >> 23) ^ (ck >> 3);
     w.put(ck & 0xFFFFFFu, 24);
     return (int)(w.pos >> 3);
+}
+
+extern "C" int knz_stream_header(uint64_t tType, int eType, int blockSize, int64_t inputSize, uint8_t out[32])
+{
+    return knz_stream_header_ex(tType, eType, blockSize, inputSize, 0, out);
 }
 
 int knz_grow(knz_ctx* ctx, u8** buf, i64* cap, i64 need)
@@ -724,7 +754,7 @@ extern "C" int knz_compress(knz_ctx* ctx, const char* transform, const char* ent
     cudaSetDevice(ctx->device);
     cudaStream_t s = ctx->stream;
     u8 hdr[32];
-    const int hdrBytes = knz_stream_header(tType, eType, blockSize, n, hdr);
+    const int hdrBytes = knz_stream_header_ex(tType, eType, blockSize, n, ctx->checksumBits, hdr);
     const i64 nBlocks = (n + blockSize - 1) / blockSize;
     // Worst case per block: a transform sequence may legally expand a block up to the reference's task
     // buffer, max(bs + bs/8, 256 KiB) (ZRLT at odd swap parity on 0xFF-heavy data); the entropy stage adds at
@@ -802,7 +832,7 @@ extern "C" int knz_compress(knz_ctx* ctx, const char* transform, const char* ent
         if (rc == KNZ_OK && ng < nb) {
             u8 tmp[32];
             memset(tmp, 0, sizeof(tmp));
-            ctx->h_bits[0] = knz_frame_small_block(in + off + (i64)ng * blockSize, lens[ng], tmp);
+            ctx->h_bits[0] = knz_frame_small_block(in + off + (i64)ng * blockSize, lens[ng], tmp, ctx->checksumBits);
             CK(cudaMemcpyAsync(ctx->dOut + (i64)ng * ctx->outStride, tmp, 32, cudaMemcpyHostToDevice, s));
             CK(cudaMemcpyAsync(ctx->blockBits + ng, ctx->h_bits, sizeof(u64), cudaMemcpyHostToDevice, s));
             CK(cudaStreamSynchronize(s));
@@ -858,7 +888,7 @@ extern "C" int knz_compress(knz_ctx* ctx, const char* transform, const char* ent
 int knz_decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8* d_in, i64 inStride,
                         const u64* h_payStart, const u64* h_endBit, const int* h_preLen, const u8* h_flags, int nB,
                         u8* d_out, i64 outStride, int32_t* h_outLens,
-                        u8* h_sink, int* h_sinkBlocks)
+                        u8* h_sink, int* h_sinkBlocks, const u64* h_expectHash, int ckBits)
 {
     int types[8];
     const int nt = split_types(tType, types);
@@ -991,6 +1021,11 @@ int knz_decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8
         if (sink)
             *h_sinkBlocks = nB - 1;
         const BlkState* stF = ctx->st + (i64)nt * ctx->maxBatch;
+        if (ckBits && h_expectHash) { // DecodingTask::run verifies the hash of the decoded block (:1003-1022)
+            memcpy(ctx->h_hash, h_expectHash, sizeof(u64) * (size_t)nB);
+            CK(cudaMemcpyAsync(ctx->expectHash, ctx->h_hash, sizeof(u64) * nB, cudaMemcpyHostToDevice, s));
+            launch_xxhash(bt, stF, nB, ckBits, NULL, ctx->expectHash, ctx->errFlag, s, &ctx->launches);
+        }
         CK(cudaEventRecord(ctx->ev[4], s));
         CK(cudaMemcpyAsync(ctx->h_err, ctx->errFlag, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(ctx->h_st, stF, sizeof(BlkState) * nB, cudaMemcpyDeviceToHost, s));
@@ -1001,7 +1036,7 @@ int knz_decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8
         ctx->ms[5] = msT; // per-stage times are not separable when the groups overlap
         for (int b = 0; b < nB; b++)
             h_outLens[b] = ctx->h_st[b].len;
-        return map_kerr(ctx, ctx->h_err[0] ? ctx->h_err[0] : ctx->h_err[1]);
+        return map_kerr(ctx, ctx->h_err[0] ? ctx->h_err[0] : ctx->h_err[1] ? ctx->h_err[1] : ctx->h_err[2]);
     }
 
     launch_entropy_decode(D, s, &ctx->launches);
@@ -1053,6 +1088,11 @@ int knz_decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8
         CK(cudaEventRecord(ctx->evStage[2 * step + 1], s));
     }
     const BlkState* stFinal = ctx->st + (i64)nt * ctx->maxBatch;
+    if (ckBits && h_expectHash) { // DecodingTask::run verifies the hash of the decoded block (:1003-1022)
+        memcpy(ctx->h_hash, h_expectHash, sizeof(u64) * (size_t)nB);
+        CK(cudaMemcpyAsync(ctx->expectHash, ctx->h_hash, sizeof(u64) * nB, cudaMemcpyHostToDevice, s));
+        launch_xxhash(bt, stFinal, nB, ckBits, NULL, ctx->expectHash, ctx->errFlag, s, &ctx->launches);
+    }
     if (!(h_sinkBlocks && *h_sinkBlocks > 0))
         launch_copy_out(bt, stFinal, nB, d_out, outStride, outCap, ctx->errFlag, s, &ctx->launches);
     CK(cudaEventRecord(ctx->ev[4], s));
@@ -1075,12 +1115,12 @@ int knz_decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8
     }
     for (int b = 0; b < nB; b++)
         h_outLens[b] = ctx->h_st[b].len;
-    return map_kerr(ctx, ctx->h_err[0] ? ctx->h_err[0] : ctx->h_err[1]);
+    return map_kerr(ctx, ctx->h_err[0] ? ctx->h_err[0] : ctx->h_err[1] ? ctx->h_err[1] : ctx->h_err[2]);
 }
 
 // Parse one block's private header (mode byte, [skip flags], length) at r.pos.
 // Returns 0 ok, 1 copy block, <0 error.
-int knz_parse_block_header(HostBitReader& r, int blockSize, u8* flags, int* preLen)
+int knz_parse_block_header(HostBitReader& r, int blockSize, u8* flags, int* preLen, int ckBits, u64* checksum)
 {
     const int mode = (int)r.get(8);
     int fl = 0;
@@ -1098,6 +1138,13 @@ int knz_parse_block_header(HostBitReader& r, int blockSize, u8* flags, int* preL
         maxT = 2048;
     if (r.bad || pre <= 0 || pre > maxT)
         return -1;
+    if (ckBits) { // io/CompressedInputStream.cpp:913-921
+        const u64 ck = (ckBits == 32) ? r.get(32) : ((r.get(32) << 32) | r.get(32));
+        if (checksum)
+            *checksum = ck;
+        if (r.bad)
+            return -1;
+    }
     *flags = (u8)fl;
     *preLen = pre;
     return copy;
@@ -1113,12 +1160,12 @@ extern "C" int knz_decode_blocks_dev(knz_ctx* ctx, uint64_t tType, int eType, in
     std::lock_guard<std::recursive_mutex> lock_(ctx->mtx);
     cudaSetDevice(ctx->device);
     cudaStream_t s = ctx->stream;
-    const int blkLen = blockSize + ((blockSize >> 4) > 512 ? (blockSize >> 4) : 512);
     float acc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
     for (int off = 0; off < nBlocks; off += ctx->maxBatch) {
         const int nb = (nBlocks - off < ctx->maxBatch) ? nBlocks - off : ctx->maxBatch;
-        u8* heads = (u8*)malloc((size_t)nb * 8);
-        CK(cudaMemcpy2DAsync(heads, 8, d_in + (i64)off * inStride, (size_t)inStride, 8, (size_t)nb,
+        u8* heads = (u8*)malloc((size_t)nb * 16);
+        u64* cks = (u64*)malloc(sizeof(u64) * (size_t)nb);
+        CK(cudaMemcpy2DAsync(heads, 16, d_in + (i64)off * inStride, (size_t)inStride, 16, (size_t)nb,
                              cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         u64* pay = (u64*)malloc(sizeof(u64) * (size_t)nb);
@@ -1127,8 +1174,8 @@ extern "C" int knz_decode_blocks_dev(knz_ctx* ctx, uint64_t tType, int eType, in
         u8* fl = (u8*)malloc((size_t)nb);
         int rc = KNZ_OK;
         for (int b = 0; b < nb && rc == KNZ_OK; b++) {
-            HostBitReader r = { heads + 8 * b, 64, 0, false };
-            const int k = knz_parse_block_header(r, blockSize, &fl[b], &pre[b]);
+            HostBitReader r = { heads + 16 * b, 128, 0, false };
+            const int k = knz_parse_block_header(r, blockSize, &fl[b], &pre[b], ctx->checksumBits, &cks[b]);
             if (k != 0)
                 rc = (k < 0) ? KNZ_ERR_INVALID_FILE : KNZ_ERR_INVALID_CODEC; // device path: no copy blocks
             pay[b] = r.pos;
@@ -1136,8 +1183,10 @@ extern "C" int knz_decode_blocks_dev(knz_ctx* ctx, uint64_t tType, int eType, in
         }
         if (rc == KNZ_OK)
             rc = knz_decode_batch(ctx, tType, eType, blockSize, d_in + (i64)off * inStride, inStride, pay, endb, pre, fl, nb,
-                              d_out + (i64)off * outStride, outStride, h_outLens + off);
+                              d_out + (i64)off * outStride, outStride, h_outLens + off, NULL, NULL, cks,
+                              ctx->checksumBits);
         free(heads);
+        free(cks);
         free(pay);
         free(endb);
         free(pre);
@@ -1161,7 +1210,6 @@ extern "C" int knz_decode_blocks(knz_ctx* ctx, uint64_t tType, int eType, int bl
     std::lock_guard<std::recursive_mutex> lock_(ctx->mtx);
     cudaSetDevice(ctx->device);
     cudaStream_t s = ctx->stream;
-    const int blkLen = blockSize + ((blockSize >> 4) > 512 ? (blockSize >> 4) : 512);
     for (int off = 0; off < nBlocks; off += ctx->maxBatch) {
         const int nb = (nBlocks - off < ctx->maxBatch) ? nBlocks - off : ctx->maxBatch;
         u64* pay = (u64*)malloc(sizeof(u64) * (size_t)nb);
@@ -1169,6 +1217,8 @@ extern "C" int knz_decode_blocks(knz_ctx* ctx, uint64_t tType, int eType, int bl
         int* pre = (int*)malloc(sizeof(int) * (size_t)nb);
         u8* fl = (u8*)malloc((size_t)nb);
         int* map = (int*)malloc(sizeof(int) * (size_t)nb);
+        u64* cks = (u64*)malloc(sizeof(u64) * (size_t)nb);
+        const int ckBits = ctx->checksumBits;
         int ng = 0, rc = KNZ_OK;
         for (int b = 0; b < nb && rc == KNZ_OK; b++) {
             const u8* p = in + (i64)(off + b) * inStride;
@@ -1176,7 +1226,8 @@ extern "C" int knz_decode_blocks(knz_ctx* ctx, uint64_t tType, int eType, int bl
             HostBitReader r = { p, inBits[off + b], 0, false };
             u8 f = 0;
             int pl = 0;
-            const int k = knz_parse_block_header(r, blockSize, &f, &pl);
+            u64 ck = 0;
+            const int k = knz_parse_block_header(r, blockSize, &f, &pl, ckBits, &ck);
             if (k < 0 || nbytes + 16 > ctx->outStride) {
                 rc = KNZ_ERR_INVALID_FILE;
             } else if (k == 1) { // copy block: raw bytes follow
@@ -1185,6 +1236,8 @@ extern "C" int knz_decode_blocks(knz_ctx* ctx, uint64_t tType, int eType, int bl
                 } else {
                     memcpy(out + (i64)(off + b) * outStride, p + (r.pos >> 3), (size_t)pl);
                     outLens[off + b] = pl;
+                    if (ckBits && knz_xxhash_host(out + (i64)(off + b) * outStride, pl, ckBits) != ck)
+                        rc = KNZ_ERR_CRC_CHECK;
                 }
             } else {
                 CK(cudaMemcpyAsync(ctx->dOut + (i64)ng * ctx->outStride, p, (size_t)nbytes, cudaMemcpyHostToDevice, s));
@@ -1192,6 +1245,7 @@ extern "C" int knz_decode_blocks(knz_ctx* ctx, uint64_t tType, int eType, int bl
                 endb[ng] = inBits[off + b];
                 pre[ng] = pl;
                 fl[ng] = f;
+                cks[ng] = ck;
                 map[ng] = off + b;
                 ng++;
             }
@@ -1199,7 +1253,7 @@ extern "C" int knz_decode_blocks(knz_ctx* ctx, uint64_t tType, int eType, int bl
         int32_t* ol = (int32_t*)malloc(sizeof(int32_t) * (size_t)nb);
         if (rc == KNZ_OK && ng > 0)
             rc = knz_decode_batch(ctx, tType, eType, blockSize, ctx->dOut, ctx->outStride, pay, endb, pre, fl, ng,
-                              ctx->dStageIn, ctx->bstride, ol);
+                              ctx->dStageIn, ctx->bstride, ol, NULL, NULL, cks, ckBits);
         if (rc == KNZ_OK) {
             for (int g = 0; g < ng; g++) {
                 if (ol[g] > outStride) {
@@ -1218,6 +1272,7 @@ extern "C" int knz_decode_blocks(knz_ctx* ctx, uint64_t tType, int eType, int bl
         free(pre);
         free(fl);
         free(map);
+        free(cks);
         if (rc != KNZ_OK)
             return rc;
     }
@@ -1262,12 +1317,11 @@ int knz_parse_stream_header(knz_ctx* ctx, HostBitReader& r, KnzStreamInfo* info)
             return KNZ_ERR_CRC_CHECK;
         }
     }
-    if (ckSize != 0) {
-        snprintf(ctx->err, sizeof(ctx->err), "block checksums not implemented");
-        return KNZ_ERR_INVALID_CODEC;
-    }
+    if (ckSize > 2)
+        return KNZ_ERR_INVALID_FILE;
     if (blockSize < 1024 || blockSize > ctx->maxBlockSize)
         return KNZ_ERR_BLOCK_SIZE;
+    info->ckBits = (int)ckSize * 32;
     info->eType = eType;
     info->tType = tType;
     info->blockSize = blockSize;
@@ -1292,7 +1346,6 @@ extern "C" int knz_decompress(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_
     const int eType = info.eType;
     const u64 tType = info.tType;
     const int blockSize = info.blockSize;
-    const int blkLen = blockSize + ((blockSize >> 4) > 512 ? (blockSize >> 4) : 512);
     // whole compressed stream to the device; kernels read at bit offsets
     int rc = knz_grow(ctx, &ctx->dStream, &ctx->dStreamCap, round_up(n + 256, 256));
     if (rc != KNZ_OK)
@@ -1308,6 +1361,8 @@ extern "C" int knz_decompress(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_
     int* pre = (int*)malloc(sizeof(int) * (size_t)mb);
     u8* fl = (u8*)malloc((size_t)mb);
     int32_t* ol = (int32_t*)malloc(sizeof(int32_t) * (size_t)mb);
+    u64* cks = (u64*)malloc(sizeof(u64) * (size_t)mb);
+    const int ckBits = info.ckBits;
     i64 produced = 0;
     bool done = false;
     float acc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
@@ -1330,7 +1385,8 @@ extern "C" int knz_decompress(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_
             HostBitReader hb = { in, start + bits, start, false };
             u8 f = 0;
             int pl = 0;
-            const int k = knz_parse_block_header(hb, blockSize, &f, &pl);
+            u64 ck = 0;
+            const int k = knz_parse_block_header(hb, blockSize, &f, &pl, ckBits, &ck);
             if (k < 0 || start + bits > r.nbits) {
                 rc = KNZ_ERR_INVALID_FILE;
                 break;
@@ -1346,6 +1402,11 @@ extern "C" int knz_decompress(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_
                 }
                 for (int i = 0; i < pl; i++)
                     out[produced + i] = (u8)hb.get(8);
+                if (ckBits && knz_xxhash_host(out + produced, pl, ckBits) != ck) {
+                    snprintf(ctx->err, sizeof(ctx->err), "corrupted bitstream: block checksum mismatch");
+                    rc = KNZ_ERR_CRC_CHECK;
+                    break;
+                }
                 produced += pl;
                 batchOut = produced;
                 r.pos = start + bits;
@@ -1355,6 +1416,7 @@ extern "C" int knz_decompress(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_
             endb[ng] = start + bits;
             pre[ng] = pl;
             fl[ng] = f;
+            cks[ng] = ck;
             ng++;
             r.pos = start + bits;
         }
@@ -1364,7 +1426,7 @@ extern "C" int knz_decompress(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_
         int sunk = 0;
         const bool roomy = batchOut + (i64)ng * blockSize <= cap;
         rc = knz_decode_batch(ctx, tType, eType, blockSize, ctx->dStream, 0, pay, endb, pre, fl, ng, ctx->dPlain, blockSize,
-                          ol, roomy ? out + batchOut : NULL, &sunk);
+                          ol, roomy ? out + batchOut : NULL, &sunk, cks, ckBits);
         if (rc != KNZ_OK) {
             cudaStreamSynchronize(ctx->d2hStream);
             break;
@@ -1390,6 +1452,7 @@ extern "C" int knz_decompress(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_
         cudaStreamSynchronize(ctx->d2hStream);
         produced = batchOut;
     }
+    free(cks);
     free(pay);
     free(endb);
     free(pre);
@@ -1474,7 +1537,7 @@ static int run_single_stage(knz_ctx* ctx, int type, bool inverse, const u8* in, 
     if (ctx->h_err[0] != 0) {
         if (inverse && ctx->h_err[0] == KERR_BAD_STREAM)
             return KNZ_OK; // inverse() returns false on malformed input: applied stays 0
-        return map_kerr(ctx, ctx->h_err[0] ? ctx->h_err[0] : ctx->h_err[1]);
+        return map_kerr(ctx, ctx->h_err[0] ? ctx->h_err[0] : ctx->h_err[1] ? ctx->h_err[1] : ctx->h_err[2]);
     }
     const BlkState r = ctx->h_st[0];
     if (r.swaps == 0)
@@ -1552,7 +1615,7 @@ extern "C" int knz_entropy_encode(knz_ctx* ctx, int type, const uint8_t* in, int
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
     if (ctx->h_err[0])
-        return map_kerr(ctx, ctx->h_err[0] ? ctx->h_err[0] : ctx->h_err[1]);
+        return map_kerr(ctx, ctx->h_err[0] ? ctx->h_err[0] : ctx->h_err[1] ? ctx->h_err[1] : ctx->h_err[2]);
     // strip the block header the block-level path put in front (mode + length bytes)
     const int dataSize = (n < 256) ? 1 : (ilog2_u32((u32)n) >> 3) + 1;
     const int hdr = 1 + dataSize;
@@ -1612,5 +1675,5 @@ extern "C" int knz_entropy_decode(knz_ctx* ctx, int type, const uint8_t* in, int
     CK(cudaMemcpyAsync(out, ctx->bufA, (size_t)n, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
-    return map_kerr(ctx, ctx->h_err[0] ? ctx->h_err[0] : ctx->h_err[1]);
+    return map_kerr(ctx, ctx->h_err[0] ? ctx->h_err[0] : ctx->h_err[1] ? ctx->h_err[1] : ctx->h_err[2]);
 }

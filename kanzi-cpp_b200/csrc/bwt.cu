@@ -1252,7 +1252,6 @@ bwt_extract_kernel(XCtx X, int writeBack)
     const int w = X.which0[b];
     u64* __restrict__ K = X.key[w] + (i64)b * X.capN;
     u32* __restrict__ V = X.val[w] + (i64)b * X.capN;
-    const u32* __restrict__ G = X.grp + (i64)b * X.capN;
     const int tend = min(tbase + RS_TILE, cnt);
     const int tiles = (cnt + RS_TILE - 1) / RS_TILE;
     const u32* xc = X.xcnt + ((i64)b * X.maxTiles + blockIdx.x) * 2;

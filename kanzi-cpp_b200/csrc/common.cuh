@@ -47,6 +47,21 @@ __device__ __forceinline__ u8* blk_dst(const BufTable& t, const BlkState& s, int
 
 __host__ __device__ __forceinline__ int next_cur(int cur) { return (cur == 0) ? 1 : 0; }
 
+// Block header written by EncodingTask::run (io/CompressedOutputStream.cpp:757-807): mode byte,
+// [skip-flag byte when the sequence has more than 4 transforms], the post-transform length on 1..4
+// bytes, [the block checksum on 4 or 8 bytes].  hdrInfo = nTransforms | (checksumBytes << 8).
+__host__ __device__ __forceinline__ int knz_len_bytes(int m)
+{
+    int r = 1;
+    for (unsigned v = (unsigned)m; v >= 256; v >>= 8)
+        r++;
+    return r;
+}
+__host__ __device__ __forceinline__ int knz_hdr_bytes(int m, int hdrInfo)
+{
+    return 1 + (((hdrInfo & 0xFF) > 4) ? 1 : 0) + knz_len_bytes(m) + (hdrInfo >> 8);
+}
+
 __host__ __device__ __forceinline__ int ilog2_u32(u32 x) // floor(log2 x), x >= 1
 {
 #ifdef __CUDA_ARCH__

@@ -68,6 +68,9 @@ struct knz_ctx {
     i64 dPlainCap;
     u8* dPlain2;
     i64 dPlain2Cap;
+    int checksumBits;  // 0, 32 or 64: block checksums written by the encoders of this context (knz_set_checksum)
+    u64 *blockHash, *expectHash; // [maxBatch] device: hashes of a batch / values read from the block headers
+    u64* h_hash;       // pinned mirror
     KnzDist* dist; // multi-process sharding state (dist.cu), NULL until knz_dist_init*
     u64 launches;
     float ms[8];
@@ -102,15 +105,18 @@ int knz_grow(knz_ctx* ctx, u8** buf, i64* cap, i64 need);
 int knz_encode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8* d_in, i64 inStride,
                      const int32_t* lens, int nB, int firstBlockLen, u8* d_out, i64 outStride, u64* d_bits,
                      u8* h_flags);
+// h_expectHash (may be NULL): the checksums read from the block headers, verified after the inverse transforms
 int knz_decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8* d_in, i64 inStride,
                      const u64* h_payStart, const u64* h_endBit, const int* h_preLen, const u8* h_flags, int nB,
-                     u8* d_out, i64 outStride, int32_t* h_outLens, u8* h_sink = NULL, int* h_sinkBlocks = NULL);
-// Parse one block's private header (mode byte, [skip flags], length) at r.pos: 0 ok, 1 copy block, <0 error.
-int knz_parse_block_header(HostBitReader& r, int blockSize, u8* flags, int* preLen);
-u64 knz_frame_small_block(const u8* in, int len, u8* out);
+                     u8* d_out, i64 outStride, int32_t* h_outLens, u8* h_sink = NULL, int* h_sinkBlocks = NULL,
+                     const u64* h_expectHash = NULL, int ckBits = 0);
+// Parse one block's private header (mode byte, [skip flags], length, [checksum of ckBits bits]) at r.pos:
+// 0 ok, 1 copy block, <0 error.
+int knz_parse_block_header(HostBitReader& r, int blockSize, u8* flags, int* preLen, int ckBits = 0, u64* checksum = NULL);
+u64 knz_frame_small_block(const u8* in, int len, u8* out, int ckBits = 0);
 // Stream header fields (io/CompressedInputStream.cpp:511-663); returns KNZ_OK and leaves r behind the header.
 struct KnzStreamInfo {
-    int eType, blockSize;
+    int eType, blockSize, ckBits;
     u64 tType;
     i64 origSize; // -1 when the header does not carry it
 };

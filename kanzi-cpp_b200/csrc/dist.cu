@@ -18,7 +18,55 @@
 #include "ctx.h"
 
 #ifndef KNZ_SIM
+#include <dlfcn.h>
 #include <nccl.h>
+
+// NCCL is bound at knz_dist_init time, not at link time: a process that also runs torch.distributed must
+// use the ONE libnccl.so.2 already mapped (the torch-bundled build), whichever library was loaded first;
+// a plain C++ host gets the system library.  Only the eight entry points below are used.
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*GroupStart)();
+    ncclResult_t (*GroupEnd)();
+    bool ok;
+};
+
+static const NcclApi* nccl_api()
+{
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL); // already mapped (torch): share it
+        if (h == NULL)
+            h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (h == NULL)
+            h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (h == NULL)
+            return;
+        bool ok = true;
+#define NCCL_SYM(field, name)                                  \
+    *(void**)(&api.field) = dlsym(h, name);                    \
+    ok = ok && (*(void**)(&api.field) != NULL)
+        NCCL_SYM(GetUniqueId, "ncclGetUniqueId");
+        NCCL_SYM(CommInitRank, "ncclCommInitRank");
+        NCCL_SYM(CommDestroy, "ncclCommDestroy");
+        NCCL_SYM(AllGather, "ncclAllGather");
+        NCCL_SYM(Broadcast, "ncclBroadcast");
+        NCCL_SYM(Send, "ncclSend");
+        NCCL_SYM(Recv, "ncclRecv");
+        NCCL_SYM(GroupStart, "ncclGroupStart");
+        NCCL_SYM(GroupEnd, "ncclGroupEnd");
+#undef NCCL_SYM
+        api.ok = ok;
+    });
+    return api.ok ? &api : NULL;
+}
 #endif
 
 struct KnzDist {
@@ -70,7 +118,7 @@ void knz_dist_destroy(knz_ctx* ctx)
         cudaEventDestroy(D->evBatch[i]);
 #ifndef KNZ_SIM
     if (D->useNccl)
-        ncclCommDestroy(D->comm);
+        nccl_api()->CommDestroy(D->comm);
 #endif
     delete D;
     ctx->dist = NULL;
@@ -97,7 +145,8 @@ extern "C" int knz_dist_unique_id(uint8_t id[128])
     memset(id, 0, 128);
 #ifndef KNZ_SIM
     ncclUniqueId u;
-    if (ncclGetUniqueId(&u) != ncclSuccess)
+    const NcclApi* N = nccl_api();
+    if (N == NULL || N->GetUniqueId(&u) != ncclSuccess)
         return KNZ_ERR_CREATE_COMPRESSOR;
     static_assert(sizeof(ncclUniqueId) <= 128, "unique id does not fit");
     memcpy(id, &u, sizeof(u));
@@ -120,8 +169,9 @@ extern "C" int knz_dist_init(knz_ctx* ctx, int rank, int world, const uint8_t id
         cudaSetDevice(ctx->device);
         ncclUniqueId u;
         memcpy(&u, id, sizeof(u));
-        if (ncclCommInitRank(&ctx->dist->comm, world, u, rank) != ncclSuccess) {
-            snprintf(ctx->err, sizeof(ctx->err), "ncclCommInitRank failed");
+        const NcclApi* N = nccl_api();
+        if (N == NULL || N->CommInitRank(&ctx->dist->comm, world, u, rank) != ncclSuccess) {
+            snprintf(ctx->err, sizeof(ctx->err), N ? "ncclCommInitRank failed" : "libnccl.so.2 not found");
             delete ctx->dist;
             ctx->dist = NULL;
             return KNZ_ERR_CREATE_COMPRESSOR;
@@ -161,7 +211,7 @@ static int t_allgather(knz_ctx* ctx, const void* send, i64 bytes, void* recv)
     }
 #ifndef KNZ_SIM
     if (D->useNccl) {
-        if (ncclAllGather(send, recv, (size_t)bytes, ncclUint8, D->comm, s) != ncclSuccess)
+        if (nccl_api()->AllGather(send, recv, (size_t)bytes, ncclUint8, D->comm, s) != ncclSuccess)
             return KNZ_ERR_PROCESS_BLOCK;
         return KNZ_OK;
     }
@@ -180,12 +230,13 @@ static int t_gather(knz_ctx* ctx, const void* send, i64 bytes, void* recv)
     }
 #ifndef KNZ_SIM
     if (D->useNccl) {
-        bool ok = ncclGroupStart() == ncclSuccess;
+        const NcclApi* N = nccl_api();
+        bool ok = N->GroupStart() == ncclSuccess;
         if (D->rank == 0)
             for (int r = 0; r < D->world; r++)
-                ok = ok && ncclRecv((u8*)recv + (i64)r * bytes, (size_t)bytes, ncclUint8, r, D->comm, s) == ncclSuccess;
-        ok = ok && ncclSend(send, (size_t)bytes, ncclUint8, 0, D->comm, s) == ncclSuccess;
-        ok = (ncclGroupEnd() == ncclSuccess) && ok;
+                ok = ok && N->Recv((u8*)recv + (i64)r * bytes, (size_t)bytes, ncclUint8, r, D->comm, s) == ncclSuccess;
+        ok = ok && N->Send(send, (size_t)bytes, ncclUint8, 0, D->comm, s) == ncclSuccess;
+        ok = (N->GroupEnd() == ncclSuccess) && ok;
         return ok ? KNZ_OK : KNZ_ERR_PROCESS_BLOCK;
     }
 #endif
@@ -201,7 +252,7 @@ static int t_bcast(knz_ctx* ctx, void* buf, i64 bytes)
         return KNZ_OK;
 #ifndef KNZ_SIM
     if (D->useNccl)
-        return ncclBroadcast(buf, buf, (size_t)bytes, ncclUint8, 0, D->comm, s) == ncclSuccess ? KNZ_OK
+        return nccl_api()->Broadcast(buf, buf, (size_t)bytes, ncclUint8, 0, D->comm, s) == ncclSuccess ? KNZ_OK
                                                                                                 : KNZ_ERR_PROCESS_BLOCK;
 #endif
     DCK(cudaStreamSynchronize(s));
@@ -289,7 +340,7 @@ static int dist_encode_dev(knz_ctx* ctx, u64 tType, int eType, int blockSize, co
             const int len = lens[off + ng];
             DCK(cudaMemcpyAsync(raw, d_in + (i64)(off + ng) * inStride, (size_t)len, cudaMemcpyDeviceToHost, s));
             DCK(cudaStreamSynchronize(s));
-            const u64 bits = knz_frame_small_block(raw, len, tmp);
+            const u64 bits = knz_frame_small_block(raw, len, tmp, ctx->checksumBits);
             DCK(cudaMemcpyAsync(D->dBlk + (i64)(off + ng) * ctx->outStride, tmp, 32, cudaMemcpyHostToDevice, s));
             DCK(cudaMemcpyAsync(dOwnBits + off + ng, &bits, sizeof(u64), cudaMemcpyHostToDevice, s));
             DCK(cudaStreamSynchronize(s));
@@ -421,6 +472,8 @@ extern "C" int knz_dist_decode_dev(knz_ctx* ctx, uint64_t tType, int eType, int 
     int* pre = (int*)malloc(sizeof(int) * (size_t)nbOwn);
     u8* fl = (u8*)malloc((size_t)nbOwn);
     u8* heads = (u8*)malloc((size_t)nbOwn * 16);
+    u64* cks = (u64*)malloc(sizeof(u64) * (size_t)nbOwn);
+    const int ckBits = ctx->checksumBits;
     u64 pos = startBit;
     for (int i = 0, k = 0; i < nBlocks; i++) {
         const u64 st = pos + 5 + prefix_bits(h_allBits[i]);
@@ -454,7 +507,7 @@ extern "C" int knz_dist_decode_dev(knz_ctx* ctx, uint64_t tType, int eType, int 
             const int g = off + b;
             const u64 rel = start[g] & 7;
             HostBitReader hb = { heads + 16 * g, 128, rel, false };
-            const int k = knz_parse_block_header(hb, blockSize, &fl[g], &pre[g]);
+            const int k = knz_parse_block_header(hb, blockSize, &fl[g], &pre[g], ckBits, &cks[g]);
             if (k < 0) {
                 rc = KNZ_ERR_INVALID_FILE;
             } else if (k == 1) { // copy block (only the last, short block of a stream): raw bytes follow
@@ -472,7 +525,7 @@ extern "C" int knz_dist_decode_dev(knz_ctx* ctx, uint64_t tType, int eType, int 
         }
         if (rc == KNZ_OK && ng > 0) {
             rc = knz_decode_batch(ctx, tType, eType, blockSize, d_stream, 0, pay + off, endb + off, pre + off, fl + off, ng,
-                                  d_out + (i64)off * outStride, outStride, h_outLens + off);
+                                  d_out + (i64)off * outStride, outStride, h_outLens + off, NULL, NULL, cks + off, ckBits);
             for (int i = 0; i < 8; i++)
                 acc[i] += ctx->ms[i];
         }
@@ -489,6 +542,7 @@ extern "C" int knz_dist_decode_dev(knz_ctx* ctx, uint64_t tType, int eType, int 
     free(pre);
     free(fl);
     free(heads);
+    free(cks);
     return rc;
 }
 
@@ -528,7 +582,7 @@ extern "C" int knz_compress_dist(knz_ctx* ctx, const char* transform, const char
     const int nbOwn = own_count(nBlocks, R, W);
     const int nbMax = (nBlocks + W - 1) / W;
     u8 hdr[32];
-    const int hdrBytes = knz_stream_header(tType, eType, blockSize, n, hdr);
+    const int hdrBytes = knz_stream_header_ex(tType, eType, blockSize, n, ctx->checksumBits, hdr);
     // own blocks -> device, all copies queued up front on the copy stream, one event per sub-batch
     int rc = knz_grow(ctx, &D->dIn, &D->dInCap, (i64)(nbMax > 0 ? nbMax : 1) * blockSize + 256);
     if (rc != KNZ_OK)
@@ -602,7 +656,7 @@ extern "C" int knz_decompress_dist(knz_ctx* ctx, const uint8_t* in, int64_t n, u
     const int blockSize = info.blockSize;
     // ---- walk the length prefixes of the whole stream, keep the ranges of the blocks this rank owns
     struct Own {
-        u64 start, bits, pay;
+        u64 start, bits, pay, ck;
         int pre, index;
         u8 flags;
     };
@@ -627,7 +681,8 @@ extern "C" int knz_decompress_dist(knz_ctx* ctx, const uint8_t* in, int64_t n, u
             HostBitReader hb = { in, start + bits, start, false };
             u8 f = 0;
             int pl = 0;
-            const int k = knz_parse_block_header(hb, blockSize, &f, &pl);
+            u64 ck = 0;
+            const int k = knz_parse_block_header(hb, blockSize, &f, &pl, info.ckBits, &ck);
             const i64 dstOff = (i64)nBlocks * blockSize;
             if (k < 0) {
                 rc = KNZ_ERR_INVALID_FILE;
@@ -640,6 +695,10 @@ extern "C" int knz_decompress_dist(knz_ctx* ctx, const uint8_t* in, int64_t n, u
                 }
                 for (int i = 0; i < pl; i++)
                     out[dstOff + i] = (u8)hb.get(8);
+                if (info.ckBits && knz_xxhash_host(out + dstOff, pl, info.ckBits) != ck) {
+                    rc = KNZ_ERR_CRC_CHECK;
+                    break;
+                }
                 if (dstOff + pl > lastEnd)
                     lastEnd = dstOff + pl;
             } else {
@@ -648,7 +707,7 @@ extern "C" int knz_decompress_dist(knz_ctx* ctx, const uint8_t* in, int64_t n, u
                     own = (Own*)realloc(own, sizeof(Own) * (size_t)capOwn);
                 }
                 Own o;
-                o.start = start, o.bits = bits, o.pay = hb.pos, o.pre = pl, o.index = nBlocks, o.flags = f;
+                o.start = start, o.bits = bits, o.pay = hb.pos, o.pre = pl, o.index = nBlocks, o.flags = f, o.ck = ck;
                 own[nOwn++] = o;
             }
         }
@@ -674,6 +733,9 @@ extern "C" int knz_decompress_dist(knz_ctx* ctx, const uint8_t* in, int64_t n, u
     int* pre = (int*)malloc(sizeof(int) * (size_t)(nOwn + 1));
     u8* fl = (u8*)malloc((size_t)nOwn + 1);
     int32_t* ol = (int32_t*)malloc(sizeof(int32_t) * (size_t)(nOwn + 1));
+    u64* cks = (u64*)malloc(sizeof(u64) * (size_t)(nOwn + 1));
+    for (int k = 0; k < nOwn; k++)
+        cks[k] = own[k].ck;
     if (rc == KNZ_OK && nOwn > 0) {
         if (cudaMemsetAsync(D->dIn, 0, (size_t)((i64)nOwn * istride), ctx->copyStream) != cudaSuccess)
             rc = KNZ_ERR_PROCESS_BLOCK;
@@ -699,7 +761,8 @@ extern "C" int knz_decompress_dist(knz_ctx* ctx, const uint8_t* in, int64_t n, u
             break;
         }
         rc = knz_decode_batch(ctx, info.tType, info.eType, blockSize, D->dIn + (i64)off * istride, istride, pay + off,
-                              endb + off, pre + off, fl + off, nb, D->dPlain + (i64)off * blockSize, blockSize, ol + off);
+                              endb + off, pre + off, fl + off, nb, D->dPlain + (i64)off * blockSize, blockSize, ol + off,
+                              NULL, NULL, cks + off, info.ckBits);
         if (rc != KNZ_OK)
             break;
         for (int i = 0; i < 8; i++)
@@ -730,6 +793,7 @@ extern "C" int knz_decompress_dist(knz_ctx* ctx, const uint8_t* in, int64_t n, u
     free(pre);
     free(fl);
     free(ol);
+    free(cks);
     free(own);
     if (rc != KNZ_OK)
         return rc;

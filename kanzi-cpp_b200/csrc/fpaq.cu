@@ -133,8 +133,7 @@ __global__ void fpaq_bits_kernel(const BlkState* __restrict__ st, int nBlocks, i
     if (b >= nBlocks)
         return;
     const int m = st[b].len;
-    const int dataSize = (m < 256) ? 1 : (ilog2_u32((u32)m) >> 3) + 1;
-    const int hdrBytes = 1 + ((nTransforms > 4) ? 1 : 0) + dataSize;
+    const int hdrBytes = knz_hdr_bytes(m, nTransforms);
     const u64 total = 8ull * ((u64)hdrBytes + stageLen[b]);
     blockBits[b] = total;
     if ((i64)(total >> 3) + 8 > outStride)
@@ -147,8 +146,7 @@ fpaq_copy_kernel(const BlkState* __restrict__ st, int nTransforms, const u8* __r
 {
     const int b = blockIdx.y;
     const int m = st[b].len;
-    const int dataSize = (m < 256) ? 1 : (ilog2_u32((u32)m) >> 3) + 1;
-    const int hdrBytes = 1 + ((nTransforms > 4) ? 1 : 0) + dataSize;
+    const int hdrBytes = knz_hdr_bytes(m, nTransforms);
     const u32 n = stageLen[b];
     if ((i64)hdrBytes + n + 8 > outStride)
         return;

@@ -32,6 +32,7 @@
 #define KERR_BAD_STREAM 2
 #define KERR_UNSUPPORTED 3
 #define KERR_INTERNAL 4
+#define KERR_CRC 5 // block checksum mismatch (reported in errFlag[2])
 
 // Scratch of the order-1 rANS coder (ans1.cu), allocated on first use of ANS1 by a context.
 struct Ans1Work {
@@ -54,7 +55,9 @@ void ans1_work_free(Ans1Work& W);
 struct EncodeLaunch {
     BufTable bt;
     const BlkState* st; // state after the last transform stage
-    int nBlocks, maxChunks, eType, nTransforms;
+    int nBlocks, maxChunks, eType;
+    int nTransforms;      // number of transforms of the sequence | (block checksum bytes << 8), see knz_hdr_bytes
+    const u64* blockHash; // per block XXHash (when checksum bytes != 0)
     u8* slots;
     u32 *hdrBits, *payBytes, *payOff;
     u64 *chunkOff, *blockBits;
@@ -179,5 +182,10 @@ bool workspace_alloc_bwt(Workspace& ws); // on the first BWT stage of a context
 void workspace_free(Workspace& ws);
 // Copies each block's final bytes to out + b*outStride; a block longer than outCap is not copied
 // and raises KERR_OUT_OVERFLOW (a crafted stream may not write past its destination slot).
+// Block checksums (xxhash.cu): hash of st[b].len bytes of every block; expect == NULL stores it,
+// else compares and raises KERR_CRC in errFlag[2].  bits = 32 or 64.
+void launch_xxhash(const BufTable& bt, const BlkState* st, int nBlocks, int bits, u64* hash, const u64* expect,
+                   int* errFlag, cudaStream_t s, u64* launches);
+u64 knz_xxhash_host(const u8* data, int length, int bits);
 void launch_copy_out(const BufTable& bt, const BlkState* st, int nBlocks, u8* out, i64 outStride, int outCap,
                      int* errFlag, cudaStream_t s, u64* launches);

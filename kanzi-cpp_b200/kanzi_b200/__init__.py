@@ -42,6 +42,7 @@ def _load(path):
     L.knz_transform_type.restype = ctypes.c_uint64
     L.knz_transform_type.argtypes = [ctypes.c_char_p]
     L.knz_entropy_type.argtypes = [ctypes.c_char_p]
+    L.knz_set_checksum.argtypes = [ctypes.c_void_p, ctypes.c_int]
     L.knz_set_decode_groups.restype = ctypes.c_int
     L.knz_set_decode_groups.argtypes = [ctypes.c_void_p, ctypes.c_int]
     L.knz_launch_count.restype = ctypes.c_uint64
@@ -109,6 +110,10 @@ class Context:
     @property
     def cuda_stream(self):
         return int(self.lib.knz_stream(self.h) or 0)
+
+    def set_checksum(self, bits):
+        """Block checksums written by the encoders of this context: 0, 32 (XXHash32) or 64 (XXHash64)."""
+        self._check(self.lib.knz_set_checksum(self.h, int(bits)))
 
     def set_decode_groups(self, groups):
         """Block groups decoded concurrently (1 = serial stages with per-stage timings)."""

@@ -1926,12 +1926,109 @@ static int entropy_decode(BitR* r, int etype, u8* p, u32 n)
     }
 }
 
+/* ================================================================== block checksums
+ * util/XXHash.hpp:61-121 (XXHash32::hash) and :151-231 (XXHash64::hash), seed = BITSTREAM_TYPE
+ * (io/CompressedOutputStream.cpp:99-110).  The 64-bit variant's first merge rotates by
+ * (1, 7, 12, 18) with 32-bit complements on 64-bit values -- written here as the reference has it. */
+static u32 xx_le32(const u8* p) { return (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16) | ((u32)p[3] << 24); }
+static u64 xx_le64(const u8* p) { return (u64)xx_le32(p) | ((u64)xx_le32(p + 4) << 32); }
+static u32 xx32_round(u32 acc, u32 val)
+{
+    acc += val * 0x85EBCA77u;
+    return ((acc << 13) | (acc >> 19)) * 0x9E3779B1u;
+}
+static u32 xxhash32(const u8* data, int length)
+{
+    const u32 P1 = 0x9E3779B1u, P2 = 0x85EBCA77u, P3 = 0xC2B2AE3Du, P4 = 0x27D4EB2Fu, P5 = 0x165667B1u;
+    const u32 seed = 0x4B414E5Au;
+    u32 h;
+    int idx = 0;
+    if (length >= 16) {
+        u32 v1 = seed + P1 + P2, v2 = seed + P2, v3 = seed, v4 = seed - P1;
+        do {
+            v1 = xx32_round(v1, xx_le32(data + idx));
+            v2 = xx32_round(v2, xx_le32(data + idx + 4));
+            v3 = xx32_round(v3, xx_le32(data + idx + 8));
+            v4 = xx32_round(v4, xx_le32(data + idx + 12));
+            idx += 16;
+        } while (idx <= length - 16);
+        h = ((v1 << 1) | (v1 >> 31)) + ((v2 << 7) | (v2 >> 25)) + ((v3 << 12) | (v3 >> 20)) + ((v4 << 18) | (v4 >> 14));
+    } else {
+        h = seed + P5;
+    }
+    h += (u32)length;
+    for (; idx <= length - 4; idx += 4) {
+        h += xx_le32(data + idx) * P3;
+        h = ((h << 17) | (h >> 15)) * P4;
+    }
+    for (; idx < length; idx++) {
+        h += (u32)data[idx] * P5;
+        h = ((h << 11) | (h >> 21)) * P1;
+    }
+    h ^= h >> 15;
+    h *= P2;
+    h ^= h >> 13;
+    h *= P3;
+    return h ^ (h >> 16);
+}
+static u64 xx64_round(u64 acc, u64 val)
+{
+    acc += val * 0xC2B2AE3D27D4EB4Full;
+    return ((acc << 31) | (acc >> 33)) * 0x9E3779B185EBCA87ull;
+}
+static u64 xx64_merge(u64 acc, u64 val) { return (acc ^ xx64_round(0, val)) * 0x9E3779B185EBCA87ull + 0x85EBCA77C2B2AE63ull; }
+static u64 xxhash64(const u8* data, int length)
+{
+    const u64 P1 = 0x9E3779B185EBCA87ull, P2 = 0xC2B2AE3D27D4EB4Full, P3 = 0x165667B19E3779F9ull,
+              P4 = 0x85EBCA77C2B2AE63ull, P5 = 0x27D4EB2F165667C5ull;
+    const u64 seed = 0x4B414E5Aull;
+    u64 h;
+    int idx = 0;
+    if (length >= 32) {
+        u64 v1 = seed + P1 + P2, v2 = seed + P2, v3 = seed, v4 = seed - P1;
+        do {
+            v1 = xx64_round(v1, xx_le64(data + idx));
+            v2 = xx64_round(v2, xx_le64(data + idx + 8));
+            v3 = xx64_round(v3, xx_le64(data + idx + 16));
+            v4 = xx64_round(v4, xx_le64(data + idx + 24));
+            idx += 32;
+        } while (idx <= length - 32);
+        h = ((v1 << 1) | (v1 >> 31)) + ((v2 << 7) | (v2 >> 25)) + ((v3 << 12) | (v3 >> 20)) + ((v4 << 18) | (v4 >> 14));
+        h = xx64_merge(h, v1);
+        h = xx64_merge(h, v2);
+        h = xx64_merge(h, v3);
+        h = xx64_merge(h, v4);
+    } else {
+        h = seed + P5;
+    }
+    h += (u64)length;
+    for (; idx + 8 <= length; idx += 8) {
+        h ^= xx64_round(0, xx_le64(data + idx));
+        h = ((h << 27) | (h >> 37)) * P1 + P4;
+    }
+    for (; idx + 4 <= length; idx += 4) {
+        h ^= (u64)xx_le32(data + idx) * P1;
+        h = ((h << 23) | (h >> 41)) * P2 + P3;
+    }
+    for (; idx < length; idx++) {
+        h ^= (u64)data[idx] * P5;
+        h = ((h << 11) | (h >> 53)) * P1;
+    }
+    h ^= h >> 33;
+    h *= P2;
+    h ^= h >> 29;
+    h *= P3;
+    return h ^ (h >> 32);
+}
+static u64 block_hash(const u8* data, int length, int ckBits) { return (ckBits == 32) ? (u64)xxhash32(data, length) : xxhash64(data, length); }
+
 /* One block exactly as EncodingTask::run builds it in its private buffer
- * (io/CompressedOutputStream.cpp:652-898, checksum off, skipBlocks off):
- * mode byte, [skip-flag byte], post-transform length, entropy payload.
+ * (io/CompressedOutputStream.cpp:652-898, skipBlocks off):
+ * mode byte, [skip-flag byte], post-transform length, [block checksum], entropy payload.
  * dataCap / bufCap model _data->_length / _buffer->_length (the two ping-pong
  * capacities handed to TransformSequence::forward).  Returns bit count.       */
-static i64 encode_block(const u8* in, int n, u64 ttype, int etype, int dataCap, int bufCap, u8* out, i64 outCap)
+static i64 encode_block_ck(const u8* in, int n, u64 ttype, int etype, int dataCap, int bufCap, u8* out, i64 outCap,
+                           int ckBits)
 {
     BitW w;
     bw_init(&w, out, outCap);
@@ -1969,13 +2066,20 @@ static i64 encode_block(const u8* in, int n, u64 ttype, int etype, int dataCap, 
         bw_put(&w, (u64)flags, 8);
     }
     bw_put(&w, (u64)post, 8 * dataSize);
+    if (ckBits) /* :674-682 (hash of the block before the transforms), :804-807 */
+        bw_put(&w, block_hash(in, n, ckBits), ckBits);
     entropy_encode(&w, etype, payload, (u32)post);
     free(tbuf);
     return w.overflow ? -1 : w.bits;
 }
 
+static i64 encode_block(const u8* in, int n, u64 ttype, int etype, int dataCap, int bufCap, u8* out, i64 outCap)
+{
+    return encode_block_ck(in, n, ttype, etype, dataCap, bufCap, out, outCap, 0);
+}
+
 /* io/CompressedInputStream.cpp:791-1041 DecodingTask::run (payload part) */
-static int decode_block(const u8* in, i64 nbits, u64 ttype, int etype, int blockSize, u8* out, int outCap)
+static int decode_block_ck(const u8* in, i64 nbits, u64 ttype, int etype, int blockSize, u8* out, int outCap, int ckBits)
 {
     BitR r;
     br_init(&r, in, nbits);
@@ -1991,6 +2095,7 @@ static int decode_block(const u8* in, i64 nbits, u64 ttype, int etype, int block
     }
     const int dataSize = 1 + ((mode >> 5) & 3);
     const int pre = (int)br_get(&r, 8 * dataSize);
+    const u64 ck = ckBits ? br_get(&r, ckBits) : 0; /* :895-900 */
     /* DecodingTask's _blockLength = blockSize + max(512, blockSize/16)
      * (CompressedInputStream.cpp:275): capacity of the task's data buffer.     */
     const int blkLen = blockSize + ((blockSize >> 4) > 512 ? (blockSize >> 4) : 512);
@@ -2008,6 +2113,8 @@ static int decode_block(const u8* in, i64 nbits, u64 ttype, int etype, int block
         if (sequence_inverse(ttype, flags, tmp, pre, data, blkLen, &produced) && produced <= outCap) {
             memcpy(out, data, (size_t)produced);
             rc = produced;
+            if (ckBits && block_hash(data, produced, ckBits) != ck) /* :1003-1022 */
+                rc = -2;
         }
     }
     free(data);
@@ -2015,12 +2122,18 @@ static int decode_block(const u8* in, i64 nbits, u64 ttype, int etype, int block
     return rc;
 }
 
-/* Stream header, io/CompressedOutputStream.cpp:277-342 */
-static void put_stream_header(BitW* w, u64 ttype, int etype, int blockSize, i64 inputSize)
+static int decode_block(const u8* in, i64 nbits, u64 ttype, int etype, int blockSize, u8* out, int outCap)
 {
+    return decode_block_ck(in, nbits, ttype, etype, blockSize, out, outCap, 0);
+}
+
+/* Stream header, io/CompressedOutputStream.cpp:277-342 */
+static void put_stream_header(BitW* w, u64 ttype, int etype, int blockSize, i64 inputSize, int ckBits)
+{
+    const u32 ckSize = (u32)(ckBits >> 5); /* 0, 1 (32 bits), 2 (64 bits) */
     bw_put(w, 0x4B414E5A, 32);
     bw_put(w, 6, 4);
-    bw_put(w, 0, 2); /* checksum size */
+    bw_put(w, ckSize, 2);
     bw_put(w, (u64)etype, 5);
     bw_put(w, ttype, 48);
     bw_put(w, (u64)(blockSize >> 4), 28);
@@ -2040,7 +2153,7 @@ static void put_stream_header(BitW* w, u64 ttype, int etype, int blockSize, i64 
     bw_put(w, 0, 15);
     const u32 HASH = 0x1E35A7BDu;
     u32 ck = HASH * (0x01030507u * 6u);
-    ck ^= HASH * (u32)~0u; /* ~ckSize with ckSize = 0 */
+    ck ^= HASH * (u32)~ckSize;
     ck ^= HASH * (u32)~(u32)etype;
     ck ^= HASH * (u32)((~ttype) >> 32);
     ck ^= HASH * (u32)(~ttype);
@@ -2102,11 +2215,11 @@ API int ko_decode_block(const u8* in, i64 nbits, u64 ttype, int etype, int block
 /* Whole stream with the jobs=1 buffer model of CompressedOutputStream
  * (:138-146, :447-474): _buffers[0] = max(bs + bs/8, 256 KiB) is the data buffer
  * of every block; the transform buffer keeps the largest `required` seen.     */
-API i64 ko_stream_compress(const u8* in, i64 n, u64 ttype, int etype, int blockSize, u8* out, i64 cap)
+API i64 ko_stream_compress_ck(const u8* in, i64 n, u64 ttype, int etype, int blockSize, int ckBits, u8* out, i64 cap)
 {
     BitW w;
     bw_init(&w, out, cap);
-    put_stream_header(&w, ttype, etype, blockSize, n);
+    put_stream_header(&w, ttype, etype, blockSize, n, ckBits);
     const int dataCap = (blockSize + (blockSize >> 3) > 262144) ? blockSize + (blockSize >> 3) : 262144;
     int bufCap = 0;
     const i64 tmpCap = (i64)blockSize + (blockSize >> 1) + 65536;
@@ -2125,7 +2238,7 @@ API i64 ko_stream_compress(const u8* in, i64 n, u64 ttype, int etype, int blockS
         }
         if (bufCap < required)
             bufCap = required;
-        const i64 bits = encode_block(in + off, len, ttype, etype, dataCap, bufCap, tmp, tmpCap);
+        const i64 bits = encode_block_ck(in + off, len, ttype, etype, dataCap, bufCap, tmp, tmpCap, ckBits);
         if (bits < 0) {
             free(tmp);
             return -1;
@@ -2143,7 +2256,14 @@ API i64 ko_stream_compress(const u8* in, i64 n, u64 ttype, int etype, int blockS
     return (w.bits + 7) >> 3;
 }
 
-/* io/CompressedInputStream.cpp:511-663 readHeader (+ block loop) */
+API i64 ko_stream_compress(const u8* in, i64 n, u64 ttype, int etype, int blockSize, u8* out, i64 cap)
+{
+    return ko_stream_compress_ck(in, n, ttype, etype, blockSize, 0, out, cap);
+}
+
+API u64 ko_block_hash(const u8* in, int n, int ckBits) { return block_hash(in, n, ckBits); }
+
+/* io/CompressedInputStream.cpp:511-663 readHeader (+ block loop); -5 = block checksum mismatch */
 API i64 ko_stream_decompress(const u8* in, i64 n, u8* out, i64 cap)
 {
     BitR r;
@@ -2152,8 +2272,9 @@ API i64 ko_stream_decompress(const u8* in, i64 n, u8* out, i64 cap)
         return -1;
     if (br_get(&r, 4) != 6)
         return -2;
-    if (br_get(&r, 2) != 0)
-        return -3; /* checksums: not restated */
+    const int ckBits = 32 * (int)br_get(&r, 2);
+    if (ckBits > 64)
+        return -3;
     const int etype = (int)br_get(&r, 5);
     const u64 ttype = br_get(&r, 48);
     const int blockSize = (int)br_get(&r, 28) << 4;
@@ -2182,11 +2303,11 @@ API i64 ko_stream_decompress(const u8* in, i64 n, u8* out, i64 cap)
                 tmp[k >> 3] |= (u8)(0x80 >> (k & 7));
         }
         const i64 room = cap - produced;
-        const int rc = decode_block(tmp, (i64)bits, ttype, etype, blockSize, out + produced,
-            (int)((room < blockSize) ? room : blockSize));
+        const int rc = decode_block_ck(tmp, (i64)bits, ttype, etype, blockSize, out + produced,
+            (int)((room < blockSize) ? room : blockSize), ckBits);
         if (rc < 0) {
             free(tmp);
-            return -4;
+            return (rc == -2) ? -5 : -4;
         }
         produced += rc;
     }

@@ -42,6 +42,7 @@ class Oracle:
         L.ko_entropy_encode.restype = ctypes.c_int64
         L.ko_encode_block.restype = ctypes.c_int64
         L.ko_stream_compress.restype = ctypes.c_int64
+        L.ko_stream_compress_ck.restype = ctypes.c_int64
         L.ko_stream_decompress.restype = ctypes.c_int64
 
     def entropy_encode(self, name, data):
@@ -97,11 +98,16 @@ class Oracle:
         assert bits >= 0
         return out[: (bits + 7) // 8].copy(), bits
 
-    def stream_compress(self, data, tname, ename, block_size):
+    def block_hash(self, data, bits):
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        self.lib.ko_block_hash.restype = ctypes.c_uint64
+        return int(self.lib.ko_block_hash(_ptr(data), data.size, bits))
+
+    def stream_compress(self, data, tname, ename, block_size, checksum=0):
         data = np.ascontiguousarray(data, dtype=np.uint8)
         out = np.zeros(data.size + data.size // 2 + 65536, dtype=np.uint8)
-        n = self.lib.ko_stream_compress(_ptr(data), ctypes.c_int64(data.size), ctypes.c_uint64(transform_word(tname)),
-                                        E_IDS[ename], block_size, _ptr(out), ctypes.c_int64(out.size))
+        n = self.lib.ko_stream_compress_ck(_ptr(data), ctypes.c_int64(data.size), ctypes.c_uint64(transform_word(tname)),
+                                           E_IDS[ename], block_size, checksum, _ptr(out), ctypes.c_int64(out.size))
         assert n >= 0, n
         return out[:n].copy()
 
@@ -123,12 +129,12 @@ class Ref:
     def __init__(self, path):
         self.lib = ctypes.CDLL(path)
 
-    def stream_compress(self, data, tname, ename, block_size, jobs=1):
+    def stream_compress(self, data, tname, ename, block_size, jobs=1, checksum=0):
         data = np.ascontiguousarray(data, dtype=np.uint8)
         out = np.empty(data.size + data.size // 2 + 65536, dtype=np.uint8)
         ol = ctypes.c_int64(0)
         rc = self.lib.kref_stream_compress(_ptr(data), ctypes.c_int64(data.size), tname.encode(), ename.encode(),
-                                           block_size, jobs, 0, _ptr(out), ctypes.c_int64(out.size), ctypes.byref(ol))
+                                           block_size, jobs, checksum, _ptr(out), ctypes.c_int64(out.size), ctypes.byref(ol))
         assert rc == 0, rc
         return out[: ol.value].copy()
 

@@ -51,6 +51,12 @@ STREAMS = [
     ("incompressible", 9, 100000, "NONE", "FPAQ", 65536),
     ("compressible", 5, 9 << 20, "BWT+SRT+ZRLT", "FPAQ", 4 << 20),
     ("compressible", 5, (40 << 20) + 5, "BWT+SRT+ZRLT", "FPAQ", 32 << 20),
+    # block checksums (7th field: 32 = XXHash32, 64 = XXHash64)
+    ("text", 1, 70000, "BWT+RANK+ZRLT", "ANS0", 65536, 32),
+    ("text", 1, 70000, "BWT+RANK+ZRLT", "ANS0", 65536, 64),
+    ("compressible", 2, (9 << 20) + 11, "BWT+RANK+ZRLT", "ANS0", 4 << 20, 32),
+    ("compressible", 2, (9 << 20) + 11, "NONE", "HUFFMAN", 4 << 20, 64),
+    ("incompressible", 9, 100000, "NONE", "NONE", 65536, 64),
 ]
 
 
@@ -58,10 +64,12 @@ def main():
     ref = Ref.load()
     assert ref is not None, "oracle/_ref missing: run `make -C oracle ref` where /root/reference exists"
     out = {"streams": [], "stages": []}
-    for gen, seed, size, tname, ename, bs in STREAMS:
+    for gen, seed, size, tname, ename, bs, *rest in STREAMS:
+        ck = rest[0] if rest else 0
         data = synth.GENERATORS[gen](size, seed)
-        comp = ref.stream_compress(data, tname, ename, bs, jobs=1)  # jobs=1: the buffer model the GPU path reproduces
-        rec = {"gen": gen, "seed": seed, "size": size, "transform": tname, "entropy": ename, "block": bs,
+        # jobs=1: the buffer model the GPU path reproduces
+        comp = ref.stream_compress(data, tname, ename, bs, jobs=1, checksum=ck)
+        rec = {"gen": gen, "seed": seed, "size": size, "transform": tname, "entropy": ename, "block": bs, "checksum": ck,
                "input_sha256": synth.sha256(data), "len": int(comp.size),
                "sha256": hashlib.sha256(comp.tobytes()).hexdigest()}
         if comp.size <= 50000:

@@ -29,7 +29,7 @@ def test_oracle_stream_matches_golden(oracle, idx):
     if rec["size"] > (10 << 20) and "BWT" in rec["transform"]:
         pytest.skip("oracle suffix sorter is too slow for this size on CPU; covered by the GPU suite")
     data = _input(rec)
-    comp = oracle.stream_compress(data, rec["transform"], rec["entropy"], rec["block"])
+    comp = oracle.stream_compress(data, rec["transform"], rec["entropy"], rec["block"], checksum=rec.get("checksum", 0))
     assert comp.size == rec["len"]
     assert hashlib.sha256(comp.tobytes()).hexdigest() == rec["sha256"]
     if "hex" in rec:

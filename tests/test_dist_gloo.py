@@ -73,6 +73,20 @@ for nbytes, tname, ename in ((7 * BS + 1234, "BWT+RANK+ZRLT", "ANS0"), (5 * BS +
     assert rc == 0, (rc, ctx.lib.knz_last_error(ctx.h))
     for k, i in enumerate(my):
         assert ol[k] == lens[k] and np.array_equal(d_out[k, : lens[k]], d_in[k, : lens[k]]), (tname, ename, "dev block", i)
+# ---- block checksums (XXHash32 / XXHash64) through the sharded path
+for ck in (32, 64):
+    nbytes = 5 * BS + 77
+    data = synth.synth_compressible(nbytes, 43)
+    ctx.set_checksum(ck)
+    comp = ctx.compress_dist(data, "BWT+RANK+ZRLT", "ANS0", BS)
+    want = oracle.stream_compress(data, "BWT+RANK+ZRLT", "ANS0", BS, checksum=ck)
+    if rank == 0:
+        assert comp.size == want.size and np.array_equal(comp, want), ("checksum", ck)
+    ctx.set_checksum(0)  # the stream header says which checksum to verify
+    out = np.zeros(nbytes, dtype=np.uint8)
+    ctx.decompress_dist(want, nbytes, out=out)
+    for i in range(rank, (nbytes + BS - 1) // BS, world):
+        assert np.array_equal(out[i * BS: (i + 1) * BS], data[i * BS: (i + 1) * BS]), ("checksum", ck, i)
 dist.barrier()
 if rank == 0:
     print("GLOO_OK")

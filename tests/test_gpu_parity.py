@@ -57,7 +57,11 @@ def test_gpu_stream_matches_golden(gpu, gpu_big, idx):
         pytest.skip("entropy codec not on the GPU path yet (covered by the CPU oracle suite)")
     data = synth.GENERATORS[rec["gen"]](rec["size"], rec["seed"])
     assert synth.sha256(data) == rec["input_sha256"]
-    comp = gpu.compress(data, rec["transform"], rec["entropy"], rec["block"])
+    gpu.set_checksum(rec.get("checksum", 0))
+    try:
+        comp = gpu.compress(data, rec["transform"], rec["entropy"], rec["block"])
+    finally:
+        gpu.set_checksum(0)
     if "hex" in rec:
         want = np.frombuffer(bytes.fromhex(rec["hex"]), dtype=np.uint8)
         assert np.array_equal(comp, want), _first_diff(comp, want)
@@ -160,6 +164,52 @@ def test_gpu_stream_vs_oracle(gpu, oracle, tname, ename):
             assert a.size == b.size and np.array_equal(a, b), (name, tname, ename, bs, _first_diff(a, b))
             dec = gpu.decompress(b, data.size)
             assert dec.size == data.size and np.array_equal(dec, data), (name, tname, ename, bs)
+
+
+@pytest.mark.parametrize("ck", [32, 64])
+def test_gpu_block_checksums(gpu, oracle, ck):
+    """XXHash32 / XXHash64 block checksums: streams equal the oracle's, decoded blocks are
+    verified on the device, a flipped bit is reported as CRC (19) or invalid bitstream (15)."""
+    from kanzi_b200 import KanziGpuError
+    inputs = [np.concatenate([synth.synth_compressible(3 << 20, 21), synth.synth_incompressible(70000, 3),
+                              np.zeros(10, np.uint8)]), rng_bytes(31, 5), rng_bytes(15, 6), synth.synth_text(65536 + 17, 7)]
+    for data in inputs:
+        for tname, ename in (("NONE", "ANS0"), ("BWT+RANK+ZRLT", "ANS0"), ("NONE", "NONE"), ("ZRLT", "HUFFMAN"),
+                             ("NONE", "ANS1"), ("BWT+SRT+ZRLT", "FPAQ")):
+            for bs in (65536, 1 << 20):
+                d = data[: 6 * bs]
+                want = oracle.stream_compress(d, tname, ename, bs, checksum=ck)
+                gpu.set_checksum(ck)
+                try:
+                    got = gpu.compress(d, tname, ename, bs)
+                finally:
+                    gpu.set_checksum(0)
+                assert got.size == want.size and np.array_equal(got, want), (d.size, tname, ename, bs, _first_diff(got, want))
+                assert np.array_equal(gpu.decompress(want, d.size), d), (d.size, tname, ename, bs)
+                if want.size > 1000:
+                    bad = want.copy()
+                    bad[bad.size - 40] ^= 0x04
+                    with pytest.raises(KanziGpuError) as ei:
+                        gpu.decompress(bad, d.size)
+                    assert ei.value.code in (15, 19), ei.value.code
+    # a wrong stored checksum alone (payload intact) is exactly KNZ_ERR_CRC_CHECK
+    bs = 1 << 18
+    data = synth.synth_compressible(2 * bs, 9)
+    blocks = [data[:bs], data[bs:]]
+    gpu.set_checksum(ck)
+    try:
+        enc = gpu.encode_blocks(blocks, "BWT+RANK+ZRLT", "ANS0", bs)
+        stored = int.from_bytes(bytes(enc[1][0][4: 4 + ck // 8]), "big")  # mode byte + 3 length bytes
+        assert stored == oracle.block_hash(blocks[1], ck)
+        dec = gpu.decode_blocks([(e[0], e[1]) for e in enc], "BWT+RANK+ZRLT", "ANS0", bs)
+        assert all(np.array_equal(dec[i], blocks[i]) for i in range(2))
+        broken = enc[1][0].copy()
+        broken[5] ^= 0x80
+        with pytest.raises(KanziGpuError) as ei:
+            gpu.decode_blocks([(enc[0][0], enc[0][1]), (broken, enc[1][1])], "BWT+RANK+ZRLT", "ANS0", bs)
+        assert ei.value.code == 19, ei.value.code
+    finally:
+        gpu.set_checksum(0)
 
 
 def test_gpu_blocks_vs_oracle(gpu, oracle):

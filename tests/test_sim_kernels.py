@@ -117,6 +117,52 @@ def test_sim_blocks(sim, oracle):
         assert np.array_equal(dec[i], blk), i
 
 
+@pytest.mark.parametrize("ck", [32, 64])
+def test_sim_block_checksums(oracle, ck):
+    """XXHash32 / XXHash64 block checksums: written by the encoders (csrc/xxhash.cu + the block header kernel),
+    verified on the device after the inverse transforms; a flipped payload bit is a CRC or bitstream error."""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "sim"), "-j8"], stdout=subprocess.DEVNULL)
+    from kanzi_b200 import Context, KanziGpuError
+    ctx = Context(0, 1 << 16, 4, lib_path=SIM)
+    inputs = [np.concatenate([synth.synth_compressible(150000, 21), synth.synth_incompressible(70000, 3),
+                              np.zeros(10, np.uint8)]), rng_bytes(31, 5), rng_bytes(15, 6), synth.synth_text(65536 + 17, 7)]
+    for data in inputs:
+        for tname, ename in (("NONE", "ANS0"), ("BWT+RANK+ZRLT", "ANS0"), ("NONE", "NONE"), ("ZRLT", "HUFFMAN"),
+                             ("NONE", "ANS1"), ("BWT+SRT+ZRLT", "FPAQ")):
+            chain = ("RANK" in tname) or ("SRT" in tname)
+            d = data[:40000] if chain else data
+            bs = 16384 if chain else 65536
+            want = oracle.stream_compress(d, tname, ename, bs, checksum=ck)
+            ctx.set_checksum(ck)
+            got = ctx.compress(d, tname, ename, bs)
+            assert got.size == want.size and np.array_equal(got, want), (d.size, tname, ename, ck)
+            ctx.set_checksum(0)  # decompress takes the checksum size from the stream header
+            assert np.array_equal(ctx.decompress(want, d.size), d), (d.size, tname, ename, ck)
+            if want.size > 1000:
+                bad = want.copy()
+                bad[bad.size - 40] ^= 0x04
+                with pytest.raises(KanziGpuError) as ei:
+                    ctx.decompress(bad, d.size)
+                assert ei.value.code in (15, 19), ei.value.code
+    # block-level entry points: the checksum follows the block length
+    bs = 65536
+    data = synth.synth_compressible(2 * bs + 100, 9)
+    blocks = [data[i: i + bs] for i in range(0, data.size, bs)]
+    ctx.set_checksum(ck)
+    enc = ctx.encode_blocks(blocks, "ZRLT", "ANS0", bs)
+    dec = ctx.decode_blocks([(e[0], e[1]) for e in enc], "ZRLT", "ANS0", bs)
+    for i, blk in enumerate(blocks):
+        assert np.array_equal(dec[i], blk), i
+    hdr = 1 + 3  # mode byte + 3 length bytes for a 64 KiB block (len 65536 needs 3 bytes)
+    stored = int.from_bytes(bytes(enc[0][0][hdr: hdr + ck // 8]), "big")
+    assert stored == oracle.block_hash(blocks[0], ck)
+    broken = enc[0][0].copy()
+    broken[broken.size - 9] ^= 1
+    with pytest.raises(KanziGpuError):
+        ctx.decode_blocks([(broken, enc[0][1])], "ZRLT", "ANS0", bs)
+    ctx.close()
+
+
 def test_sim_decode_groups(oracle):
     """Block groups decoded on separate streams over disjoint workspace slices (knz_set_decode_groups)."""
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "sim"), "-j8"], stdout=subprocess.DEVNULL)

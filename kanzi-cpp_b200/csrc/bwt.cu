@@ -1263,7 +1263,6 @@ bwt_extract_kernel(XCtx X, int writeBack)
     const int wx = writeBack ? X.whichX8[b] : 0;
     u64* __restrict__ xk = (wx ? X.xkeyAlt : X.xkey) + (i64)b * X.capN;
     u32* __restrict__ xv = (wx ? X.xvalAlt : X.xval) + (i64)b * X.capN;
-    (void)G;
     for (u32 i = threadIdx.x; i < npre + nsuf; i += RS_THREADS) {
         const int j = (i < npre) ? (tbase + (int)i) : (tend - (int)nsuf + (int)(i - npre));
         const u32 x = (i < npre) ? (offPre + i) : (offSuf + (i - npre));

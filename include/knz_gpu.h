@@ -42,6 +42,9 @@ extern "C" {
 #define KNZ_T_MTFT 7
 #define KNZ_T_RANK 8
 #define KNZ_T_SRT 13
+#define KNZ_T_LZ 3
+#define KNZ_T_LZP 14
+#define KNZ_T_LZX 16
 /* Entropy ids: entropy/EntropyEncoderFactory.hpp:37-52 */
 #define KNZ_E_NONE 0
 #define KNZ_E_HUFFMAN 1

@@ -27,11 +27,19 @@ static bool entropy_supported(int e)
 
 static bool type_supported(int t)
 {
-    return t == T_NONE || t == T_BWT || t == T_ZRLT || t == T_MTFT || t == T_RANK || t == T_SRT;
+    return t == T_NONE || t == T_BWT || t == T_ZRLT || t == T_MTFT || t == T_RANK || t == T_SRT || t == T_LZ ||
+           t == T_LZX || t == T_LZP;
 }
+static bool is_lz(int t) { return t == T_LZ || t == T_LZX || t == T_LZP; }
 
-// Transform<T>::getMaxEncodedLength: BWTBlockCodec n + 33, SRT n + 1024 (transform/SRT.hpp:38)
-static int stage_max_len(int t, int n) { return (t == T_BWT) ? n + 33 : (t == T_SRT) ? n + 1024 : n; }
+// Transform<T>::getMaxEncodedLength: BWTBlockCodec n + 33, SRT n + 1024 (transform/SRT.hpp:38),
+// LZ / LZX n + max(16, n/64) + 2 and LZP without the + 2 (transform/LZCodec.hpp:91-95, :158-161)
+static int stage_max_len(int t, int n)
+{
+    if (is_lz(t))
+        return ((n <= 1024) ? n + 16 : n + n / 64) + ((t == T_LZP) ? 0 : 2);
+    return (t == T_BWT) ? n + 33 : (t == T_SRT) ? n + 1024 : n;
+}
 
 static int required_size(const int* types, int nt, int n)
 {
@@ -67,6 +75,12 @@ extern "C" uint64_t knz_transform_type(const char* name)
             t = T_RANK;
         else if (len == 3 && !strncmp(p, "SRT", 3))
             t = T_SRT;
+        else if (len == 2 && !strncmp(p, "LZ", 2))
+            t = T_LZ;
+        else if (len == 3 && !strncmp(p, "LZX", 3))
+            t = T_LZX;
+        else if (len == 3 && !strncmp(p, "LZP", 3))
+            t = T_LZP;
         if (t < 0 || ++n > 8)
             return (uint64_t)-1;
         if (t != T_NONE) {
@@ -220,6 +234,8 @@ extern "C" void knz_destroy(knz_ctx* ctx)
         ans1_work_free(ctx->a1);
     if (ctx->srtReady)
         srt_work_free(ctx->srt);
+    if (ctx->lzReady)
+        lz_work_free(ctx->lz);
     void* dev[] = { ctx->bufA, ctx->bufB, ctx->dStageIn, ctx->dOut, ctx->st, ctx->capEven, ctx->capOdd, ctx->slots,
                     ctx->hdrBits, ctx->payBytes, ctx->payOff, ctx->chunkOff, ctx->chunkPos, ctx->blockBits,
                     ctx->blockOff, ctx->streamPos, ctx->dInBits, ctx->dPayStart, ctx->dPreLen, ctx->errFlag,
@@ -301,7 +317,7 @@ static int map_kerr(knz_ctx* ctx, int kerr)
 
 static void add_stage_time(knz_ctx* ctx, int t, float ms)
 {
-    const int slot = (t == T_BWT) ? 0 : (t == T_RANK || t == T_MTFT || t == T_SRT) ? 1 : (t == T_ZRLT) ? 2 : 5;
+    const int slot = (t == T_BWT) ? 0 : (t == T_RANK || t == T_MTFT || t == T_SRT || is_lz(t)) ? 1 : (t == T_ZRLT) ? 2 : 5;
     if (slot < 5)
         ctx->ms[slot] += ms;
 }
@@ -334,6 +350,13 @@ static int ensure_bwt(knz_ctx* ctx, const int* types, int nt)
             }
             ctx->srtReady = true;
         }
+        if (is_lz(types[i]) && !ctx->lzReady) {
+            if (!lz_work_alloc(ctx->lz, ctx->maxBatch, ctx->bstride)) {
+                snprintf(ctx->err, sizeof(ctx->err), "out of device memory for the LZ workspace");
+                return KNZ_ERR_CREATE_COMPRESSOR;
+            }
+            ctx->lzReady = true;
+        }
     }
     return KNZ_OK;
 }
@@ -359,6 +382,11 @@ static void launch_forward_stage(knz_ctx* ctx, int type, const StageLaunch& L, c
     case T_SRT:
         launch_srt_forward(L, ctx->ws, ctx->srt, s, &ctx->launches);
         break;
+    case T_LZ:
+    case T_LZX:
+    case T_LZP:
+        launch_lz_forward(L, type, ctx->lz, s, &ctx->launches);
+        break;
     }
 }
 
@@ -382,6 +410,11 @@ static void launch_inverse_stage(knz_ctx* ctx, int type, const StageLaunch& L, c
         break;
     case T_SRT:
         launch_srt_inverse(L, s, &ctx->launches);
+        break;
+    case T_LZ:
+    case T_LZX:
+    case T_LZP:
+        launch_lz_inverse(L, type, ctx->lz, s, &ctx->launches);
         break;
     }
 }

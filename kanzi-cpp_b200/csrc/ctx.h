@@ -57,6 +57,8 @@ struct knz_ctx {
     bool a1Ready;
     SrtWork srt; // SRT scratch, allocated on the first SRT stage
     bool srtReady;
+    LzWork lz; // LZ / LZX / LZP scratch, allocated on the first stage of that family
+    bool lzReady;
     // pinned host mirrors
     BlkState* h_st;
     int *h_capEven, *h_capOdd, *h_err, *h_preLen;

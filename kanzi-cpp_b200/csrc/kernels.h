@@ -26,6 +26,9 @@
 #define T_MTFT 7
 #define T_RANK 8
 #define T_SRT 13
+#define T_LZ 3
+#define T_LZP 14
+#define T_LZX 16
 
 // device-side error flags (first one wins)
 #define KERR_OUT_OVERFLOW 1
@@ -138,6 +141,17 @@ bool srt_work_alloc(SrtWork& W, int maxBlocks, int capN);
 void srt_work_free(SrtWork& W);
 void launch_srt_forward(const StageLaunch& L, Workspace& ws, SrtWork& W, cudaStream_t s, u64* launches);
 void launch_srt_inverse(const StageLaunch& L, cudaStream_t s, u64* launches);
+// LZ / LZX / LZP scratch (lz.cu), allocated on the first LZ-family stage of a context.
+struct LzWork {
+    int* hashes;    // [blocks][2^19] last position of every hash (LZ and LZP use the first 2^16)
+    i64 hashStride; // ints per block
+    u8* side;       // [blocks][2][sideStride] tokens + match lengths | distances
+    i64 sideStride;
+};
+bool lz_work_alloc(LzWork& W, int maxBlocks, i64 stageStride);
+void lz_work_free(LzWork& W);
+void launch_lz_forward(const StageLaunch& L, int type, LzWork& W, cudaStream_t s, u64* launches);
+void launch_lz_inverse(const StageLaunch& L, int type, LzWork& W, cudaStream_t s, u64* launches);
 void launch_bwt_forward(const StageLaunch& L, Workspace& ws, cudaStream_t s, u64* launches);
 void launch_bwt_inverse(const StageLaunch& L, Workspace& ws, cudaStream_t s, u64* launches);
 

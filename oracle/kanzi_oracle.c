@@ -1566,11 +1566,466 @@ static int srt_inverse(const u8* in, int length, u8* dst, int cap, int* outLen)
 
 /* ------------------------------------------------------------------ sequence
  * transform ids: transform/TransformFactory.hpp:49-73.                       */
-enum { T_NONE = 0, T_BWT = 1, T_ZRLT = 6, T_MTFT = 7, T_RANK = 8, T_SRT = 13 };
+/* ------------------------------------------------------------------ LZ / LZX / LZP
+ * transform/LZCodec.cpp:118-455 (LZXCodec<T>::forward), :470-610 (inverseV6),
+ * :771-992 (LZPCodec), helpers transform/LZCodec.hpp:178-248.
+ * LZ (extra = 0, 2^16 hash slots) and LZX (extra = 1, 2^19 slots, one more lazy position) share
+ * the format: 13-byte header (end of literals, token count, distance bytes as LE int32, flag byte
+ * 0000MMMD), then literals (with their long lengths inline) | tokens | distances | match lengths. */
+static u64 lz_le64(const u8* p)
+{
+    u64 v = 0;
+    for (int i = 7; i >= 0; i--)
+        v = (v << 8) | p[i];
+    return v;
+}
+static u32 lz_le32(const u8* p) { return (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16) | ((u32)p[3] << 24); }
+static void lz_put_le32(u8* p, u32 v)
+{
+    p[0] = (u8)v, p[1] = (u8)(v >> 8), p[2] = (u8)(v >> 16), p[3] = (u8)(v >> 24);
+}
+#define LZ_MAX_MATCH (65535 + 254 + 4)
+#define LZ_MAXD1 ((1 << 16) - 2)
+#define LZ_MAXD2 ((1 << 24) - 2)
+static int lz_max_len(int n, int lzp) { return ((n <= 1024) ? n + 16 : n + n / 64) + (lzp ? 0 : 2); }
+static u32 lz_hash(const u8* p, int hashLog) /* LZCodec.hpp:188-191 */
+{
+    return (u32)(((lz_le64(p) << 24) * (u64)0x1E35A7BDu) >> (64 - hashLog));
+}
+static int lz_match(const u8* src, int a, int b, int maxMatch) /* LZCodec.hpp:229-246 */
+{
+    int n = 0;
+    while (n + 8 <= maxMatch) {
+        const u64 diff = lz_le64(src + a + n) ^ lz_le64(src + b + n);
+        if (diff) {
+            n += __builtin_ctzll(diff) >> 3;
+            break;
+        }
+        n += 8;
+    }
+    return n;
+}
+static int lz_emit_len(u8* p, int length) /* LZCodec.hpp:194-210 */
+{
+    if (length < 254) {
+        p[0] = (u8)length;
+        return 1;
+    }
+    if (length < 65536 + 254) {
+        const u32 l = (u32)(length - 254);
+        p[0] = 0xFE, p[1] = (u8)(l >> 8), p[2] = (u8)l;
+        return 3;
+    }
+    const u32 l = (u32)(length - 255);
+    p[0] = 0xFF, p[1] = (u8)(l >> 16), p[2] = (u8)(l >> 8), p[3] = (u8)l;
+    return 4;
+}
+static u32 lz_read_len(const u8* p, int* pos) /* LZCodec.hpp:212-227 */
+{
+    u32 res = p[(*pos)++];
+    if (res < 254)
+        return res;
+    if (res == 254) {
+        res += ((u32)p[*pos] << 8) | p[*pos + 1];
+        *pos += 2;
+        return res;
+    }
+    res += ((u32)p[*pos] << 16) | ((u32)p[*pos + 1] << 8) | p[*pos + 2];
+    *pos += 3;
+    return res;
+}
+
+static int lzx_forward(const u8* src, int count, u8* dst, int cap, int* outLen, int extra)
+{
+    if (count == 0) {
+        *outLen = 0;
+        return 1;
+    }
+    if (cap < lz_max_len(count, 0) || count < 24)
+        return 0;
+    const int hashLog = extra ? 19 : 16;
+    int* hashes = (int*)calloc((size_t)1 << hashLog, sizeof(int));
+    /* the three side streams; the sum of everything emitted stays below count or the stage fails */
+    u8* tk = (u8*)malloc((size_t)count + 64);
+    u8* mb = (u8*)malloc((size_t)count + 64);
+    u8* ml = (u8*)malloc((size_t)count + 64);
+    const int srcEnd = count - 16 - 2;
+    const int maxDist = (srcEnd < 4 * LZ_MAXD1) ? LZ_MAXD1 : LZ_MAXD2;
+    const int minMatch = 4; /* dataType DNA / SMALL_ALPHABET come from pre-transforms that are out of scope */
+    dst[12] = (u8)(((maxDist == LZ_MAXD1) ? 0 : 1) | (((minMatch - 2) & 7) << 1));
+    int srcIdx = 0, dstIdx = 13, anchor = 0, mIdx = 0, mLenIdx = 0, tkIdx = 0;
+    int repd[2] = { count, count };
+    int repIdx = 0, srcInc = 0, ok = 1;
+    while (srcIdx < srcEnd) {
+        int bestLen = 0;
+        const u32 h0 = lz_hash(src + srcIdx, hashLog);
+        const int ref0 = hashes[h0];
+        hashes[h0] = srcIdx;
+        const int srcIdx1 = srcIdx + 1;
+        int ref = srcIdx1 - repd[repIdx];
+        const int minRef = (srcIdx - maxDist > 0) ? srcIdx - maxDist : 0;
+        const int lim1 = (srcEnd - srcIdx1 < LZ_MAX_MATCH) ? srcEnd - srcIdx1 : LZ_MAX_MATCH;
+        if (ref > minRef && lz_le32(src + srcIdx1) == lz_le32(src + ref)) {
+            bestLen = lz_match(src, srcIdx1, ref, lim1); /* most recent repeat distance first */
+        } else {
+            ref = srcIdx1 - repd[repIdx ^ 1];
+            if (ref > minRef && lz_le32(src + srcIdx1) == lz_le32(src + ref))
+                bestLen = lz_match(src, srcIdx1, ref, lim1);
+        }
+        if (bestLen < minMatch) {
+            ref = ref0; /* the hash table's candidate */
+            if (ref > minRef && lz_le32(src + srcIdx) == lz_le32(src + ref)) {
+                const int lim0 = (srcEnd - srcIdx < LZ_MAX_MATCH) ? srcEnd - srcIdx : LZ_MAX_MATCH;
+                bestLen = lz_match(src, srcIdx, ref, lim0);
+            }
+            if (bestLen < minMatch) { /* no match: skip faster and faster through incompressible data */
+                srcIdx = srcIdx1 + (srcInc >> 6);
+                srcInc++;
+                repIdx = 0;
+                continue;
+            }
+            if (srcIdx - ref != repd[0] && srcIdx - ref != repd[1]) {
+                /* lazy evaluation: one (LZ) or two (LZX) positions further */
+                const u32 h1 = lz_hash(src + srcIdx1, hashLog);
+                const int ref1 = hashes[h1];
+                hashes[h1] = srcIdx1;
+                if (ref1 > minRef + 1 && lz_le32(src + srcIdx1 + bestLen - 3) == lz_le32(src + ref1 + bestLen - 3)) {
+                    const int bl1 = lz_match(src, srcIdx1, ref1, lim1);
+                    if (bl1 >= bestLen) {
+                        ref = ref1;
+                        bestLen = bl1;
+                        srcIdx = srcIdx1;
+                    }
+                }
+                if (extra) {
+                    const int srcIdx2 = srcIdx1 + 1;
+                    const u32 h2 = lz_hash(src + srcIdx2, hashLog);
+                    const int ref2 = hashes[h2];
+                    hashes[h2] = srcIdx2;
+                    if (ref2 > minRef + 2 && lz_le32(src + srcIdx2 + bestLen - 3) == lz_le32(src + ref2 + bestLen - 3)) {
+                        const int lim2 = (srcEnd - srcIdx2 < LZ_MAX_MATCH) ? srcEnd - srcIdx2 : LZ_MAX_MATCH;
+                        const int bl2 = lz_match(src, srcIdx2, ref2, lim2);
+                        if (bl2 >= bestLen) {
+                            ref = ref2;
+                            bestLen = bl2;
+                            srcIdx = srcIdx2;
+                        }
+                    }
+                }
+            }
+            while (srcIdx > anchor && ref > minRef && src[srcIdx - 1] == src[ref - 1]) { /* extend backwards */
+                bestLen++;
+                ref--;
+                srcIdx--;
+            }
+            if (bestLen > LZ_MAX_MATCH) {
+                ref += bestLen - LZ_MAX_MATCH;
+                srcIdx += bestLen - LZ_MAX_MATCH;
+                bestLen = LZ_MAX_MATCH;
+            }
+        } else { /* repeat-distance match found at srcIdx + 1 */
+            if (bestLen >= LZ_MAX_MATCH || src[srcIdx] != src[ref - 1]) {
+                srcIdx++;
+                hashes[lz_hash(src + srcIdx, hashLog)] = srcIdx;
+            } else {
+                bestLen++;
+                ref--;
+            }
+        }
+        srcInc = 0;
+        /* token LLLFFMMM (new distance on FF = 1..3 bytes) or LLLFFFMM (FFF = 000 / 001: repeat distance 0 / 1) */
+        const int dist = srcIdx - ref;
+        int token, mLenTh;
+        if (dist == repd[0]) {
+            token = 0x00;
+            mLenTh = 3;
+        } else if (dist == repd[1]) {
+            token = 0x04;
+            mLenTh = 3;
+        } else {
+            int nb = 1;
+            if (dist >= 65536)
+                mb[mIdx++] = (u8)(dist >> 16), nb++;
+            if (dist >= 256)
+                mb[mIdx++] = (u8)(dist >> 8), nb++;
+            mb[mIdx++] = (u8)dist;
+            token = nb << 3;
+            mLenTh = 7;
+        }
+        const int mLen = bestLen - minMatch;
+        if (mLen >= mLenTh) {
+            token += mLenTh;
+            mLenIdx += lz_emit_len(ml + mLenIdx, mLen - mLenTh);
+        } else {
+            token += mLen;
+        }
+        repd[1] = repd[0];
+        repd[0] = dist;
+        repIdx = 1;
+        const int litLen = srcIdx - anchor;
+        if (litLen == 0) {
+            tk[tkIdx++] = (u8)token;
+        } else {
+            if (litLen >= 7) {
+                if (litLen >= (1 << 24)) {
+                    ok = 0;
+                    break;
+                }
+                tk[tkIdx++] = (u8)((7 << 5) | token);
+                dstIdx += lz_emit_len(dst + dstIdx, litLen - 7);
+            } else {
+                tk[tkIdx++] = (u8)((litLen << 5) | token);
+            }
+            memcpy(dst + dstIdx, src + anchor, (size_t)litLen);
+            dstIdx += litLen;
+        }
+        if (dstIdx + tkIdx + mIdx + mLenIdx >= count) { /* every term only grows: the final test (:421) must fail */
+            ok = 0;
+            break;
+        }
+        anchor = srcIdx + bestLen;
+        while (++srcIdx < anchor) /* index the positions the match covers */
+            hashes[lz_hash(src + srcIdx, hashLog)] = srcIdx;
+    }
+    int produced = 0;
+    if (ok) {
+        const int litLen = count - anchor;
+        if (dstIdx + litLen + tkIdx + mIdx + mLenIdx >= count) {
+            ok = 0;
+        } else {
+            if (litLen >= 7) {
+                tk[tkIdx++] = (u8)(7 << 5);
+                dstIdx += lz_emit_len(dst + dstIdx, litLen - 7);
+            } else {
+                tk[tkIdx++] = (u8)(litLen << 5);
+            }
+            memcpy(dst + dstIdx, src + anchor, (size_t)litLen);
+            dstIdx += litLen;
+            lz_put_le32(dst, (u32)dstIdx);
+            lz_put_le32(dst + 4, (u32)tkIdx);
+            lz_put_le32(dst + 8, (u32)mIdx);
+            memcpy(dst + dstIdx, tk, (size_t)tkIdx);
+            dstIdx += tkIdx;
+            memcpy(dst + dstIdx, mb, (size_t)mIdx);
+            dstIdx += mIdx;
+            memcpy(dst + dstIdx, ml, (size_t)mLenIdx);
+            dstIdx += mLenIdx;
+            produced = dstIdx;
+            ok = dstIdx <= count - count / 100; /* :455 */
+        }
+    }
+    free(hashes);
+    free(tk);
+    free(mb);
+    free(ml);
+    *outLen = produced;
+    return ok;
+}
+
+static int lzx_inverse(const u8* src, int count, u8* dst, int dstEnd, int* outLen)
+{
+    *outLen = 0;
+    if (count == 0)
+        return 1;
+    if (count < 13)
+        return 0;
+    int tkIdx = (int)lz_le32(src), mIdx = (int)lz_le32(src + 4), mLenIdx = (int)lz_le32(src + 8);
+    if (tkIdx < 0 || mIdx < 0 || mLenIdx < 0)
+        return 0;
+    if (tkIdx < 13 || tkIdx > count || mIdx > count - tkIdx || mLenIdx > count - tkIdx - mIdx)
+        return 0;
+    mIdx += tkIdx;
+    mLenIdx += mIdx;
+    const int srcEnd = tkIdx - 13, litEnd = tkIdx;
+    const int maxDist = ((src[12] & 1) == 0) ? LZ_MAXD1 : LZ_MAXD2;
+    const int minMatch = ((src[12] >> 1) & 7) + 2;
+    int srcIdx = 13, dstIdx = 0, repd0 = count, repd1 = count, ok = 1;
+    for (;;) {
+        /* (the reference reads past `count` on truncated input; refuse instead) */
+        if (tkIdx >= count + 2 || mIdx > count + 2 || mLenIdx > count + 2) {
+            ok = 0;
+            break;
+        }
+        const int token = src[tkIdx++];
+        int mLen, dist;
+        if ((token & 0x18) == 0) {
+            mLen = token & 3;
+            mLen += (mLen == 3) ? minMatch + (int)lz_read_len(src, &mLenIdx) : minMatch;
+            dist = (token & 4) ? repd1 : repd0;
+        } else {
+            mLen = token & 7;
+            mLen += (mLen == 7) ? minMatch + (int)lz_read_len(src, &mLenIdx) : minMatch;
+            dist = src[mIdx++];
+            if (token & 0x10) {
+                dist = (dist << 8) | src[mIdx++];
+                if (token & 0x08)
+                    dist = (dist << 8) | src[mIdx++];
+            }
+        }
+        if (token >= 32) {
+            const u32 litLen = (token >= 0xE0) ? 7u + lz_read_len(src, &srcIdx) : (u32)(token >> 5);
+            if (litLen > (u32)(dstEnd - dstIdx) || litLen > (u32)(litEnd - srcIdx)) {
+                ok = 0;
+                break;
+            }
+            memcpy(dst + dstIdx, src + srcIdx, litLen);
+            srcIdx += (int)litLen;
+            dstIdx += (int)litLen;
+            if (srcIdx >= srcEnd)
+                break;
+        }
+        repd1 = repd0;
+        repd0 = dist;
+        const int mEnd = dstIdx + mLen;
+        int ref = dstIdx - dist;
+        if (ref < 0 || dist > maxDist || mEnd > dstEnd) {
+            ok = 0;
+            break;
+        }
+        while (dstIdx < mEnd)
+            dst[dstIdx++] = dst[ref++];
+    }
+    *outLen = dstIdx;
+    return ok && (srcIdx == srcEnd + 13);
+}
+
+static int lzp_forward(const u8* src, int count, u8* dst, int cap, int* outLen)
+{
+    *outLen = 0;
+    if (count == 0)
+        return 1;
+    if (count < 4 || cap < lz_max_len(count, 1) || count < 128)
+        return 0;
+    const int srcEnd = count, dstEnd = count - (count >> 6);
+    int* hashes = (int*)calloc(1 << 16, sizeof(int));
+    memcpy(dst, src, 4);
+    u32 ctx = lz_le32(src);
+    int srcIdx = 4, dstIdx = 4, ok = 1;
+    while (srcIdx < srcEnd - 64 && dstIdx < dstEnd) {
+        const u32 h = (0x7FEB352Du * ctx) >> 16;
+        const int ref = hashes[h];
+        hashes[h] = srcIdx;
+        int bestLen = 0;
+        if (ref != 0 && lz_le64(src + ref + 56) == lz_le64(src + srcIdx + 56))
+            bestLen = lz_match(src, srcIdx, ref, srcEnd - srcIdx);
+        if (bestLen < 64) {
+            const u32 val = src[srcIdx];
+            ctx = (ctx << 8) | val;
+            dst[dstIdx++] = src[srcIdx++];
+            if (ref != 0 && val == 0xFC) { /* a literal that looks like the match flag is escaped */
+                if (dstIdx >= dstEnd) {
+                    ok = 0;
+                    break;
+                }
+                dst[dstIdx++] = 0xFF;
+            }
+            continue;
+        }
+        srcIdx += bestLen;
+        ctx = lz_le32(src + srcIdx - 4);
+        dst[dstIdx++] = 0xFC;
+        bestLen -= 64;
+        while (bestLen >= 254 && dstIdx < dstEnd) {
+            bestLen -= 254;
+            dst[dstIdx++] = 0xFE;
+        }
+        if (dstIdx >= dstEnd) {
+            ok = 0;
+            break;
+        }
+        dst[dstIdx++] = (u8)bestLen;
+    }
+    while (ok && srcIdx < srcEnd && dstIdx < dstEnd) {
+        const u32 h = (0x7FEB352Du * ctx) >> 16;
+        const int ref = hashes[h];
+        hashes[h] = srcIdx;
+        const u32 val = src[srcIdx];
+        ctx = (ctx << 8) | val;
+        dst[dstIdx++] = src[srcIdx++];
+        if (ref != 0 && val == 0xFC) {
+            if (dstIdx >= dstEnd) {
+                ok = 0;
+                break;
+            }
+            dst[dstIdx++] = 0xFF;
+        }
+    }
+    free(hashes);
+    *outLen = dstIdx;
+    return ok && srcIdx == count && dstIdx < dstEnd;
+}
+
+static int lzp_inverse(const u8* src, int count, u8* dst, int dstEnd, int* outLen)
+{
+    *outLen = 0;
+    if (count == 0)
+        return 1;
+    if (count < 4 || dstEnd < count)
+        return 0;
+    int* hashes = (int*)calloc(1 << 16, sizeof(int));
+    memcpy(dst, src, 4);
+    u32 ctx = lz_le32(dst);
+    int srcIdx = 4, dstIdx = 4, ok = 1;
+    const int srcEnd = count;
+    while (srcIdx < srcEnd) {
+        const u32 h = (0x7FEB352Du * ctx) >> 16;
+        int ref = hashes[h];
+        hashes[h] = dstIdx;
+        if (src[srcIdx] != 0xFC || ref == 0) {
+            if (dstIdx >= dstEnd) {
+                ok = 0;
+                break;
+            }
+            ctx = (ctx << 8) | src[srcIdx];
+            dst[dstIdx++] = src[srcIdx++];
+            continue;
+        }
+        srcIdx++;
+        if (srcIdx >= srcEnd) {
+            ok = 0;
+            break;
+        }
+        if (src[srcIdx] == 0xFF) {
+            if (dstIdx >= dstEnd) {
+                ok = 0;
+                break;
+            }
+            ctx = (ctx << 8) | 0xFC;
+            dst[dstIdx++] = 0xFC;
+            srcIdx++;
+            continue;
+        }
+        int mLen = 64;
+        while (srcIdx < srcEnd && src[srcIdx] == 0xFE) {
+            srcIdx++;
+            mLen += 254;
+        }
+        if (srcIdx >= srcEnd) {
+            ok = 0;
+            break;
+        }
+        mLen += src[srcIdx++];
+        if (dstIdx + mLen > dstEnd) {
+            ok = 0;
+            break;
+        }
+        for (int i = 0; i < mLen; i++)
+            dst[dstIdx + i] = dst[ref + i];
+        dstIdx += mLen;
+        ctx = lz_le32(dst + dstIdx - 4);
+    }
+    free(hashes);
+    *outLen = dstIdx;
+    return ok && srcIdx == srcEnd;
+}
+
+enum { T_NONE = 0, T_BWT = 1, T_LZ = 3, T_ZRLT = 6, T_MTFT = 7, T_RANK = 8, T_SRT = 13, T_LZP = 14, T_LZX = 16 };
 
 static int stage_max_len(int t, int n) /* getMaxEncodedLength of each stage */
 {
-    /* BWTBlockCodec.hpp:47-50 n + 33; SRT.hpp:38 n + 1024; others srcLen */
+    /* BWTBlockCodec.hpp:47-50 n + 33; SRT.hpp:38 n + 1024; LZCodec.hpp:91-95,158-161; others srcLen */
+    if (t == T_LZ || t == T_LZX || t == T_LZP)
+        return lz_max_len(n, t == T_LZP);
     return (t == T_BWT) ? n + 33 : (t == T_SRT) ? n + 1024 : n;
 }
 
@@ -1596,6 +2051,12 @@ static int stage_forward(int t, const u8* in, int n, u8* out, int cap, int* outL
         return 1;
     case T_SRT:
         return srt_forward(in, n, out, cap, outLen);
+    case T_LZ:
+        return lzx_forward(in, n, out, cap, outLen, 0);
+    case T_LZX:
+        return lzx_forward(in, n, out, cap, outLen, 1);
+    case T_LZP:
+        return lzp_forward(in, n, out, cap, outLen);
     default:
         return -1;
     }
@@ -1623,6 +2084,11 @@ static int stage_inverse(int t, const u8* in, int n, u8* out, int cap, int* outL
         return 1;
     case T_SRT:
         return srt_inverse(in, n, out, cap, outLen);
+    case T_LZ:
+    case T_LZX:
+        return lzx_inverse(in, n, out, cap, outLen);
+    case T_LZP:
+        return lzp_inverse(in, n, out, cap, outLen);
     default:
         return -1;
     }

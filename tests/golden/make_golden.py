@@ -51,6 +51,13 @@ STREAMS = [
     ("incompressible", 9, 100000, "NONE", "FPAQ", 65536),
     ("compressible", 5, 9 << 20, "BWT+SRT+ZRLT", "FPAQ", 4 << 20),
     ("compressible", 5, (40 << 20) + 5, "BWT+SRT+ZRLT", "FPAQ", 32 << 20),
+    # LZ family
+    ("compressible", 6, 300000, "LZ", "HUFFMAN", 65536),
+    ("text", 1, 70000, "LZX", "ANS0", 65536),
+    ("compressible", 6, 300000, "LZP", "NONE", 65536),
+    ("compressible", 6, (9 << 20) + 7, "LZ", "HUFFMAN", 4 << 20),
+    ("compressible", 6, (9 << 20) + 7, "LZX", "HUFFMAN", 4 << 20),
+    ("compressible", 6, (9 << 20) + 7, "LZP+LZX", "ANS0", 4 << 20),
     # block checksums (7th field: 32 = XXHash32, 64 = XXHash64)
     ("text", 1, 70000, "BWT+RANK+ZRLT", "ANS0", 65536, 32),
     ("text", 1, 70000, "BWT+RANK+ZRLT", "ANS0", 65536, 64),

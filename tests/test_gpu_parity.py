@@ -166,6 +166,29 @@ def test_gpu_stream_vs_oracle(gpu, oracle, tname, ename):
             assert dec.size == data.size and np.array_equal(dec, data), (name, tname, ename, bs)
 
 
+@pytest.mark.parametrize("tname,ename", [("LZ", "NONE"), ("LZX", "ANS0"), ("LZP", "NONE"), ("LZP+LZX", "HUFFMAN"),
+                                         ("LZ+ZRLT", "ANS0"), ("LZ", "HUFFMAN")])
+def test_gpu_lz_family_vs_oracle(gpu, oracle, tname, ename):
+    """LZ / LZX / LZP: streams byte-identical to the oracle's, decode restores the input."""
+    inputs = {
+        "comp_5m": synth.synth_compressible(5 << 20, 21),
+        "text_1m": synth.synth_text(1 << 20, 22),
+        "incomp_300k": synth.synth_incompressible(300000, 23),
+        "zeros_1m": np.zeros(1 << 20, dtype=np.uint8),
+        "period_1000": np.tile(rng_bytes(1000, 3), 1500),
+        "flag_bytes": np.tile(np.array([0xFC, 1, 2, 3, 0xFC, 0xFC, 7] * 40, dtype=np.uint8), 2000),
+        "twice_70k": np.concatenate([rng_bytes(70000, 9), rng_bytes(70000, 9), rng_bytes(5, 1)]),
+        "tiny_20": rng_bytes(20, 1),
+    }
+    for name, data in inputs.items():
+        for bs in (65536, 1 << 20, 4 << 20):
+            want = oracle.stream_compress(data, tname, ename, bs)
+            got = gpu.compress(data, tname, ename, bs)
+            assert got.size == want.size and np.array_equal(got, want), (name, tname, ename, bs, _first_diff(got, want))
+            dec = gpu.decompress(want, data.size)
+            assert dec.size == data.size and np.array_equal(dec, data), (name, tname, ename, bs)
+
+
 @pytest.mark.parametrize("ck", [32, 64])
 def test_gpu_block_checksums(gpu, oracle, ck):
     """XXHash32 / XXHash64 block checksums: streams equal the oracle's, decoded blocks are

@@ -110,3 +110,42 @@ def test_block_checksums_match_ref(oracle, ref, ck):
                 _, n = oracle.stream_decompress(bad, data.size)
                 # (the reference library is not asked: its CRC-mismatch exit crashes in this build)
                 assert n < 0, (data.size, tname, ename, ck, n)
+
+
+@pytest.mark.parametrize("tname", ["LZ", "LZX", "LZP", "LZ+ZRLT"])
+def test_lz_family_matches_ref(oracle, ref, tname):
+    """transform/LZCodec.cpp: LZ, LZX (two lazy positions, 2^19 hash slots) and LZP against the reference,
+    stage level with the capacities EncodingTask hands over, then whole streams."""
+    cases = dict(CASES)
+    cases.update({
+        "comp_300k": synth.synth_compressible(300000, 21), "text_70k": synth.synth_text(70000, 22),
+        "incomp": synth.synth_incompressible(100000, 23), "zeros": np.zeros(100000, np.uint8),
+        "comp_3m": synth.synth_compressible(3 << 20, 5), "period": np.tile(rng_bytes(1000, 3), 300),
+        "flag_bytes": np.tile(np.array([0xFC, 1, 2, 3, 0xFC, 0xFC, 7] * 40, dtype=np.uint8), 200),
+        "twice": np.concatenate([rng_bytes(70000, 9), rng_bytes(70000, 9), rng_bytes(5, 1)]),
+    })
+    applied = 0
+    for name, data in cases.items():
+        n = data.size
+        m = n + 16 if n <= 1024 else n + n // 64
+        for in_cap, out_cap in ((n + n // 8 + 64, m + 2), (m + 2, m + 2), (max(n + n // 8, 262144), m + 40)):
+            a, af = oracle.sequence_forward(tname, data, in_cap, out_cap)
+            b, bf, ok = ref.sequence_forward(tname, data, in_cap, out_cap)
+            assert af == bf, (tname, name, in_cap, out_cap, af, bf)
+            if af != 0xFF:
+                applied += 1
+                assert np.array_equal(a, b), (tname, name, a.size, b.size)
+                back, ok2 = oracle.sequence_inverse(tname, bf, b, n + n // 8 + 1200)
+                assert ok2 == 1 and np.array_equal(back, data), (tname, name)
+                back2, ok3 = ref.sequence_inverse(tname, bf, a, n + n // 8 + 1200)
+                assert ok3 == 1 and np.array_equal(back2, data), (tname, name)
+    assert applied > 20
+    for ename in ("HUFFMAN", "NONE"):
+        for name in ("comp_300k", "text_70k", "incomp", "zeros", "comp_3m"):
+            data = cases[name]
+            for bs in (65536, 1 << 20):
+                a = oracle.stream_compress(data, tname, ename, bs)
+                b = ref.stream_compress(data, tname, ename, bs, jobs=1)
+                assert a.size == b.size and np.array_equal(a, b), (tname, ename, name, bs, a.size, b.size)
+                dec, n = oracle.stream_decompress(b, data.size)
+                assert n == data.size and np.array_equal(dec, data), (tname, ename, name, bs)

@@ -117,6 +117,43 @@ def test_sim_blocks(sim, oracle):
         assert np.array_equal(dec[i], blk), i
 
 
+@pytest.mark.parametrize("tname,ename", [("LZ", "NONE"), ("LZX", "ANS0"), ("LZP", "NONE"), ("LZP+LZX", "HUFFMAN"),
+                                         ("LZ+ZRLT", "ANS0")])
+def test_sim_lz_family(sim, oracle, tname, ename):
+    """LZ / LZX / LZP (csrc/lz.cu): the warp-per-block parse reproduces the reference's token, distance and
+    length streams byte for byte; the decoders restore the input."""
+    inputs = {
+        "comp_200k": synth.synth_compressible(200000, 21),
+        "text_70k": synth.synth_text(70000, 22),
+        "incomp_80k": synth.synth_incompressible(80000, 23),          # stage refuses: skip flag
+        "zeros_100k": np.zeros(100000, dtype=np.uint8),               # matches longer than 65535 + 254
+        "period_1000": np.tile(rng_bytes(1000, 3), 150),
+        "flag_bytes": np.tile(np.array([0xFC, 1, 2, 3, 0xFC, 0xFC, 7] * 40, dtype=np.uint8), 200),  # LZP escapes
+        "twice_70k": np.concatenate([rng_bytes(70000, 9), rng_bytes(70000, 9), rng_bytes(5, 1)]),   # 3-byte distances
+        "tiny_20": rng_bytes(20, 1),
+        "text_100": synth.synth_text(100, 3),
+    }
+    for name, data in inputs.items():
+        for bs in (65536, 1 << 18):
+            want = oracle.stream_compress(data, tname, ename, bs)
+            got = sim.compress(data, tname, ename, bs)
+            assert got.size == want.size and np.array_equal(got, want), (name, tname, ename, bs, got.size, want.size)
+            dec = sim.decompress(want, data.size)
+            assert dec.size == data.size and np.array_equal(dec, data), (name, tname, ename, bs)
+    # stage level: Transform<byte>::forward / inverse with the exact getMaxEncodedLength capacity
+    first = tname.split("+")[0]
+    data = inputs["comp_200k"][:65536]
+    cap = data.size + data.size // 64 + (0 if first == "LZP" else 2)
+    fwd, applied = sim.transform_forward(first, data, cap=cap)
+    ref_out, flags = oracle.sequence_forward(first, data, data.size + 64, cap)
+    assert applied == (flags != 0xFF) and (not applied or np.array_equal(fwd, ref_out))
+    _, refused = sim.transform_forward(first, data, cap=cap - 1)  # one byte short: forward() returns false
+    assert not refused
+    if applied:
+        back, ok = sim.transform_inverse(first, fwd, data.size + 4096)
+        assert ok and np.array_equal(back, data)
+
+
 @pytest.mark.parametrize("ck", [32, 64])
 def test_sim_block_checksums(oracle, ck):
     """XXHash32 / XXHash64 block checksums: written by the encoders (csrc/xxhash.cu + the block header kernel),
@@ -188,7 +225,8 @@ def test_sim_corrupt_streams():
     ctx = Context(0, bs, 8, lib_path=SIM)
     data = synth.synth_compressible(3 * bs + 500, 9)
     rng = np.random.RandomState(1)
-    for tname, ename in (("NONE", "ANS0"), ("NONE", "HUFFMAN"), ("ZRLT", "ANS0")):
+    for tname, ename in (("NONE", "ANS0"), ("NONE", "HUFFMAN"), ("ZRLT", "ANS0"), ("LZ", "NONE"), ("LZP", "NONE"),
+                         ("LZX", "HUFFMAN")):
         comp = ctx.compress(data, tname, ename, bs)
         outcomes = {"error": 0, "bytes": 0}
         for t in range(8):

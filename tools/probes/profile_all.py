@@ -2,6 +2,7 @@
   python tools/probes/profile_all.py headline [nblocks]   BWT+RANK+ZRLT / ANS0, 4 MiB blocks, encode + decode
   python tools/probes/profile_all.py entropy  [nblocks]   -t NONE -e HUFFMAN / ANS0 / ANS1 on 4 MiB blocks, ANS1 on 64 KiB blocks
   python tools/probes/profile_all.py config5  [nblocks]   BWT+SRT+ZRLT / FPAQ, 4 MiB blocks
+  python tools/probes/profile_all.py lz       [nblocks]   LZ / LZX / LZP with HUFFMAN, 4 MiB blocks (+ the reference's time)
 """
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -47,3 +48,19 @@ elif what == "entropy":
     run("NONE", "ANS1", 64 << 10, nb * 16, 4)
 elif what == "config5":
     run("BWT+SRT+ZRLT", "FPAQ", 4 << 20, nb, 5)
+elif what == "lz":
+    import time
+    from oracle.oracle import Ref
+    ref = Ref.load()
+    for tn in ("LZ", "LZX", "LZP"):
+        run(tn, "HUFFMAN", 4 << 20, nb, 6, reps=2)
+        if ref is not None:
+            data = synth.synth_compressible(nb * (4 << 20), 6)
+            jobs = min(16, os.cpu_count() or 1)
+            t0 = time.time()
+            comp = ref.stream_compress(data, tn, "HUFFMAN", 4 << 20, jobs=jobs)
+            t1 = time.time()
+            ref.stream_decompress(comp, data.size, jobs=jobs)
+            t2 = time.time()
+            print(" reference jobs=%d: encode %.0f ms decode %.0f ms ratio %.3f" % (jobs, 1e3 * (t1 - t0), 1e3 * (t2 - t1),
+                                                                                  comp.size / data.size))

@@ -96,9 +96,10 @@ def test_type_words():
     lib = ctypes.CDLL(os.path.join(ROOT, "kanzi-cpp_b200", "libknzgpu.so"))
     lib.knz_transform_type.restype = ctypes.c_uint64
     from oracle.oracle import transform_word
-    for name in ("NONE", "BWT", "BWT+RANK+ZRLT", "BWT+MTFT+ZRLT", "ZRLT", "RANK+ZRLT", "BWT+SRT+ZRLT", "SRT"):
+    for name in ("NONE", "BWT", "BWT+RANK+ZRLT", "BWT+MTFT+ZRLT", "ZRLT", "RANK+ZRLT", "BWT+SRT+ZRLT", "SRT", "LZ", "LZX", "LZP",
+                 "LZP+LZX", "LZ+ZRLT"):
         assert lib.knz_transform_type(name.encode()) == transform_word(name)
-    assert lib.knz_transform_type(b"LZX") == 0xFFFFFFFFFFFFFFFF
+    assert lib.knz_transform_type(b"ROLZ") == 0xFFFFFFFFFFFFFFFF
     assert lib.knz_entropy_type(b"ANS0") == 5 and lib.knz_entropy_type(b"ANS1") == 8
     assert lib.knz_entropy_type(b"FPAQ") == 2 and lib.knz_entropy_type(b"TPAQ") == -1
     hdr = (ctypes.c_uint8 * 32)()

@@ -975,6 +975,191 @@ ans1_decode_kernel(DecodeLaunch L, int cpb, const A1DecMeta* __restrict__ meta, 
         atomicExch(L.errFlag + 1, KERR_BAD_STREAM);
 }
 
+// Pass 3 for FEW LONG chunks (blocks of 1 MiB and more: at most a few hundred chains, each up to 2^20
+// steps).  ans1_decode_kernel's step is two dependent trips to L2 / HBM (the 2 MiB slot table of the
+// chunk, then the renormalisation word): ~1100 cycles.  Here ONE warp owns a chunk and keeps the
+// chunk's model in its SM's shared memory instead of a slot table:
+//   cum[ctx][i]   u16  cumulative frequency of the i-th present symbol of the context   129 KiB
+//   sym[ctx][i]   u8   that symbol                                                        64 KiB
+//   idx[ctx][k]   u8   last i with cum <= k * 2^(lr-6): entry point of the search          16 KiB
+//   ring          the next 128 renormalisation words, realigned, refilled by all lanes behind the chain
+// State k is replicated in the eight lanes 8k..8k+7: they look up eight consecutive cumulative
+// frequencies at once and a ballot counts how many are <= the slot (one round for symbols within
+// eight places of the bucket's entry point, which the 64 buckets make the common case), then all
+// eight advance the same state -- no broadcast on the chain.  A step is four shared-memory reads, two
+// ballots and the multiply-add: ~200 cycles.
+#define A1S_CUM_STRIDE 258
+#define A1S_RING 128
+#define A1S_SMEM (256 * A1S_CUM_STRIDE * 2 + 256 * 256 + 256 * 64 + 256 * 2 + 256 * 2 + A1S_RING * 4)
+__global__ void __launch_bounds__(32)
+ans1_decode_smem_kernel(DecodeLaunch L, int cpb, const A1DecMeta* __restrict__ meta, const u32* __restrict__ dlist,
+                        const u32* __restrict__ dasz)
+{
+    KNZ_DYN_SMEM(a1s_smem);
+    u16* s_cum = reinterpret_cast<u16*>(a1s_smem);                             // [256][258]
+    u8* s_sym = a1s_smem + 256 * A1S_CUM_STRIDE * 2;                           // [256][256]
+    u8* s_idx = s_sym + 256 * 256;                                             // [256][64]
+    u16* s_tot = reinterpret_cast<u16*>(s_idx + 256 * 64);                     // [256] sum of frequencies
+    u16* s_asz = s_tot + 256;                                                  // [256]
+    u32* s_ring = reinterpret_cast<u32*>(s_asz + 256);                         // [128]
+    const int lane = threadIdx.x;
+    const i64 g = blockIdx.x;
+    const int b = (int)(g / cpb), c = (int)(g - (i64)b * cpb);
+    if (*L.errFlag != 0 || b >= L.nBlocks)
+        return;
+    const int m = L.preLen[b];
+    const u8* __restrict__ p = L.in + (i64)b * L.inStride;
+    if (m <= 32) { // raw block
+        if (c == 0) {
+            u8* __restrict__ out = L.dst + (i64)b * L.dstStride;
+            const u64 pos = meta[(i64)b * cpb].payPos;
+            for (int i = lane; i < m; i += 32)
+                out[i] = (u8)a1_rd_bits(p, pos + 8ull * i, 8);
+        }
+        return;
+    }
+    if (c >= a1_chunks(m))
+        return;
+    const A1DecMeta M = meta[g];
+    const int lr = (int)M.lr;
+    const u32 scale = 1u << lr, mask = scale - 1;
+    const int bsh = lr - 6; // 64 buckets per context
+    // ---- model of the chunk
+    for (int ctx = 0; ctx < 256; ctx++) {
+        const int asz = min((int)dasz[g * 256 + ctx], 256);
+        const u32* __restrict__ dl = dlist + g * 65536 + ctx * 256;
+        u32 run = 0;
+        for (int i0 = 0; i0 < asz; i0 += 32) {
+            const int i = i0 + lane;
+            const u32 e = (i < asz) ? dl[i] : 0u;
+            const u32 fq = e >> 8;
+            const u32 inc = warp_incl_sum(fq, lane);
+            if (i < asz) {
+                s_cum[ctx * A1S_CUM_STRIDE + i] = (u16)min(run + inc - fq, 0xFFFFu);
+                s_sym[ctx * 256 + i] = (u8)e;
+            }
+            run += __shfl_sync(FULL_MASK, inc, 31);
+        }
+        if (lane == 0) {
+            s_tot[ctx] = (u16)min(run, 0xFFFFu);
+            s_asz[ctx] = (u16)max(asz, 0);
+        }
+    }
+    __syncwarp();
+    for (int q = lane; q < 256 * 64; q += 32) {
+        const int ctx = q >> 6;
+        const u32 lim = (u32)(q & 63) << bsh;
+        const int asz = s_asz[ctx];
+        int lo = 0, hi = asz - 1; // last i with cum[i] <= lim (cum[0] = 0)
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if ((u32)s_cum[ctx * A1S_CUM_STRIDE + mid] <= lim)
+                lo = mid;
+            else
+                hi = mid - 1;
+        }
+        s_idx[q] = (u8)max(lo, 0);
+    }
+    // ---- renormalisation words: ring entry j = bits [payPos + 32 j, + 32) of the block's bit string
+    const u32* __restrict__ pw32 = reinterpret_cast<const u32*>(p);
+    const bool aligned4 = (((size_t)p) & 3) == 0;
+    const u64 wiEnd = (L.inBits[b] + 31) >> 5; // 32-bit words of the block's bit string
+    auto load_word = [&](u32 j) -> u32 {
+        const u64 bp = M.payPos + 32ull * j;
+        const u64 wi = bp >> 5;
+        if (aligned4) {
+            const u32 hi = (wi < wiEnd) ? bswap32(__ldg(pw32 + wi)) : 0u;
+            const u32 lo = (wi + 1 < wiEnd) ? bswap32(__ldg(pw32 + wi + 1)) : 0u;
+            return __funnelshift_l(lo, hi, (u32)(bp & 31));
+        }
+        if ((bp >> 3) + 5 > ((L.inBits[b] + 7) >> 3) + 4)
+            return 0u;
+        return a1_rd_bits(p, bp, 32);
+    };
+    u32 filled = 0; // ring entries loaded so far
+    for (; filled < A1S_RING; filled += 32)
+        s_ring[(filled + lane) & (A1S_RING - 1)] = load_word(filled + (u32)lane);
+    __syncwarp();
+    const int sz = min(A1_CH, m - c * A1_CH);
+    const int quarter = sz >> 2;
+    const int k = lane >> 3, t = lane & 7;
+    const u32 grp = 0xFFu << (8 * k);
+    const u32 heads = 0x01010101u;
+    const u32 headsAbove = heads & ~((2u << (8 * k)) - 1u); // states consumed before state k in a step: 3, 2, 1, 0
+    u32 state = M.st[k];
+    u8* __restrict__ o = L.dst + (i64)b * L.dstStride + (i64)c * A1_CH + (i64)k * quarter;
+    const u32 maxWords = M.psz >> 1;
+    u32 cnt = 0, prv = 0, pend = 0;
+    int pendAge = -1;
+    bool bad = false;
+    for (int s = 0; s < quarter; s++) {
+        // refill behind the chain: the load is issued now and stored three steps later, when it has landed
+        if (pendAge >= 0) {
+            if (++pendAge == 3) {
+                s_ring[(filled + lane) & (A1S_RING - 1)] = pend;
+                filled += 32;
+                pendAge = -1;
+                __syncwarp();
+            }
+        } else if (2 * filled - cnt < 2 * A1S_RING - 64 - 8) { // room for 32 more entries
+            pend = load_word(filled + (u32)lane);
+            pendAge = 0;
+        }
+        const u32 slot = state & mask;
+        const int asz = s_asz[prv];
+        const u16* __restrict__ cr = s_cum + prv * A1S_CUM_STRIDE;
+        int i0 = s_idx[prv * 64 + (slot >> bsh)];
+        int i;
+        for (;;) {
+            const int it = i0 + t;
+            const bool le = (it < asz) && ((u32)cr[it] <= slot);
+            const u32 v = __ballot_sync(FULL_MASK, le) & grp;
+            const int n = __popc(v);
+            const bool more = (n == 8);
+            i = i0 + n - 1;
+            if (!__any_sync(FULL_MASK, more))
+                break;
+            if (more)
+                i0 += 8; // the symbol lies further down the context's list (entry i0 + 7 is still <= slot)
+            else
+                i0 = i; // settled: cum[i] <= slot < cum[i + 1]; the next round finds it again in place 0
+        }
+        i = max(i, 0);
+        const u32 sym = s_sym[prv * 256 + i];
+        const u32 cumi = cr[i];
+        const u32 cnext = (i + 1 < asz) ? (u32)cr[i + 1] : (u32)s_tot[prv];
+        const u32 fq = min(cnext - cumi, scale - 1); // ANSDecSymbol::reset clamps like the encoder
+        state = fq * (state >> lr) + slot - cumi;
+        const bool need = state < (1u << 15);
+        const u32 bal = __ballot_sync(FULL_MASK, need) & heads;
+        if (need) {
+            const u32 wix = cnt + (u32)__popc(bal & headsAbove);
+            u32 w = 0;
+            if (wix < maxWords)
+                w = (s_ring[(wix >> 1) & (A1S_RING - 1)] >> (16 * (1 - (wix & 1)))) & 0xFFFFu;
+            else
+                bad = true;
+            state = (state << 16) | w;
+        }
+        cnt += (u32)__popc(bal);
+        if (t == 0)
+            o[s] = (u8)sym;
+        prv = sym;
+    }
+    if (lane == 0) {
+        const int count4 = quarter << 2, tail = sz - count4;
+        u8* __restrict__ oc = L.dst + (i64)b * L.dstStride + (i64)c * A1_CH;
+        if (2 * cnt + (u32)tail != M.psz) {
+            bad = true;
+        } else {
+            for (int x = 0; x < tail; x++)
+                oc[count4 + x] = (u8)a1_rd_bits(p, M.payPos + 16ull * cnt + 8ull * x, 8);
+        }
+    }
+    if (bad)
+        atomicExch(L.errFlag + 1, KERR_BAD_STREAM); // soft: the other chunks still decode (see ans1_decode_kernel)
+}
+
 void launch_ans1_decode(const DecodeLaunch& L, cudaStream_t s, u64* launches)
 {
     Ans1Work& W = *L.a1;
@@ -985,14 +1170,27 @@ void launch_ans1_decode(const DecodeLaunch& L, cudaStream_t s, u64* launches)
     u32* dasz = W.hbits;
     cudaMemsetAsync(dasz, 0, (size_t)nch * 256 * sizeof(u32), s);
     KLAUNCH(ans1_dec_scan_kernel, L.nBlocks, 32, s, L, cpb, dlist, dasz, (A1DecMeta*)W.dmeta);
-    KLAUNCH(ans1_dec_tables_kernel, dim3(256 / A1_TAB_WARPS, (unsigned)nch), A1_TAB_WARPS * 32, s, L, cpb, dlist, dasz,
-            (const A1DecMeta*)W.dmeta, W.tdec);
     if (L.evK0)
         cudaEventRecord(L.evK0, s);
-    const int qpwD = (nch <= 2048) ? 1 : 8;
-    const int quadsPerCta = A1_DEC_WARPS * qpwD;
-    KLAUNCH(ans1_decode_kernel, (unsigned)((nch + quadsPerCta - 1) / quadsPerCta), A1_DEC_WARPS * 32, s, L, cpb,
-            (const A1DecMeta*)W.dmeta, W.tdec, qpwD);
+    // few long chains: model in shared memory, one warp (= one SM's worth of shared memory) per chunk
+    static int smemMax = -1;
+    if (smemMax < 0) {
+        const char* e = getenv("KNZ_ANS1_SMEM_CHUNKS");
+        smemMax = e ? atoi(e) : 600;
+#ifndef KNZ_SIM
+        cudaFuncSetAttribute(ans1_decode_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A1S_SMEM);
+#endif
+    }
+    if (nch <= smemMax) {
+        KLAUNCH_DYN(ans1_decode_smem_kernel, (unsigned)nch, 32, A1S_SMEM, s, L, cpb, (const A1DecMeta*)W.dmeta, dlist, dasz);
+    } else {
+        KLAUNCH(ans1_dec_tables_kernel, dim3(256 / A1_TAB_WARPS, (unsigned)nch), A1_TAB_WARPS * 32, s, L, cpb, dlist, dasz,
+                (const A1DecMeta*)W.dmeta, W.tdec);
+        const int qpwD = (nch <= 2048) ? 1 : 8;
+        const int quadsPerCta = A1_DEC_WARPS * qpwD;
+        KLAUNCH(ans1_decode_kernel, (unsigned)((nch + quadsPerCta - 1) / quadsPerCta), A1_DEC_WARPS * 32, s, L, cpb,
+                (const A1DecMeta*)W.dmeta, W.tdec, qpwD);
+    }
     if (L.evK1)
         cudaEventRecord(L.evK1, s);
     *launches += 3;

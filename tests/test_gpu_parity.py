@@ -214,7 +214,7 @@ def test_gpu_block_checksums(gpu, oracle, ck):
                     bad[bad.size - 40] ^= 0x04
                     with pytest.raises(KanziGpuError) as ei:
                         gpu.decompress(bad, d.size)
-                    assert ei.value.code in (15, 19), ei.value.code
+                    assert ei.value.code in (13, 15, 19), ei.value.code  # decode overflow, invalid bitstream or CRC
     # a wrong stored checksum alone (payload intact) is exactly KNZ_ERR_CRC_CHECK
     bs = 1 << 18
     data = synth.synth_compressible(2 * bs, 9)

@@ -68,6 +68,8 @@ public:
     bool inverse(SliceArray<byte>& src, SliceArray<byte>& dst, int length) { return run(src, dst, length, true); }
     int getMaxEncodedLength(int srcLen) const
     {
+        if (_type == KNZ_T_LZ || _type == KNZ_T_LZX || _type == KNZ_T_LZP) // transform/LZCodec.hpp:91-95, :158-161
+            return ((srcLen <= 1024) ? srcLen + 16 : srcLen + (srcLen / 64)) + ((_type == KNZ_T_LZP) ? 0 : 2);
         return (_type == KNZ_T_BWT) ? srcLen + 33 : (_type == KNZ_T_SRT) ? srcLen + 1024 : srcLen;
     }
 

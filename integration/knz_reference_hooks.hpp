@@ -24,7 +24,8 @@ namespace kanzi {
 
 inline bool knzGpuTransformId(uint64 t)
 {
-    return t == KNZ_T_BWT || t == KNZ_T_RANK || t == KNZ_T_MTFT || t == KNZ_T_ZRLT || t == KNZ_T_SRT;
+    return t == KNZ_T_BWT || t == KNZ_T_RANK || t == KNZ_T_MTFT || t == KNZ_T_ZRLT || t == KNZ_T_SRT || t == KNZ_T_LZ ||
+           t == KNZ_T_LZX || t == KNZ_T_LZP;
 }
 
 inline bool knzGpuEntropyId(short e)

@@ -1176,7 +1176,7 @@ void launch_ans1_decode(const DecodeLaunch& L, cudaStream_t s, u64* launches)
     static int smemMax = -1;
     if (smemMax < 0) {
         const char* e = getenv("KNZ_ANS1_SMEM_CHUNKS");
-        smemMax = e ? atoi(e) : 600;
+        smemMax = e ? atoi(e) : 300; // two waves of one-CTA-per-SM chunks still beat the slot-table kernel
 #ifndef KNZ_SIM
         cudaFuncSetAttribute(ans1_decode_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A1S_SMEM);
 #endif

@@ -122,6 +122,15 @@ __device__ __forceinline__ void lz_store(int* slot, int v)
     *slot = v;
 }
 
+__device__ __forceinline__ void lz_prefetch(const void* p)
+{
+#ifndef KNZ_SIM
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 // n bytes, non-overlapping, spread over the warp
 __device__ __forceinline__ void lz_warp_copy(u8* dst, const u8* src, int n, int lane)
 {
@@ -193,7 +202,21 @@ lzx_forward_kernel(StageLaunch L, LzWork W)
     int repd0 = count, repd1 = count; // repd[0], repd[1]
     int repIdx = 0, srcInc = 0;
     bool ok = true;
+    int winEnd = 0; // positions below winEnd had their hash slot and their candidate's bytes pulled into L1
     while (srcIdx < srcEnd) {
+        // A step of the parse is a chain of three dependent loads (text -> hash slot -> candidate text), each a
+        // trip to L2 or HBM when taken cold.  Every 30 positions the lanes run that chain for the next 32
+        // positions side by side; the values are hints only (the parse re-reads the table in order).
+        if (srcIdx + 2 >= winEnd) {
+            const int pw = srcIdx + lane;
+            if (pw < srcEnd) {
+                const int cand = hashes[lz_hash(src + pw, lim, HLOG)];
+                if (cand > 0)
+                    lz_prefetch(src + cand);
+            }
+            winEnd = srcIdx + 32;
+            __syncwarp();
+        }
         int bestLen = 0;
         const u32 h0 = lz_hash(src + srcIdx, lim, HLOG);
         const int ref0 = lz_xchg(&hashes[h0], srcIdx);
@@ -479,7 +502,18 @@ lzp_forward_kernel(StageLaunch L, LzWork W)
     u32 ctx = lz_ld32(src, lim);
     int srcIdx = 4, dstIdx = 4;
     bool ok = true;
+    int winEnd = 0;
     while (srcIdx < srcEnd - LZP_MIN_MATCH && dstIdx < dstEnd) {
+        if (srcIdx >= winEnd) { // same look-ahead as the LZ parse: slot and candidate of the next 32 positions
+            const int pw = srcIdx + lane;
+            if (pw < srcEnd - LZP_MIN_MATCH) {
+                const int cand = hashes[(LZP_SEED * lz_ld32(src + pw - 4, lim)) >> 16];
+                if (cand > 0)
+                    lz_prefetch(src + cand + LZP_MIN_MATCH - 8);
+            }
+            winEnd = srcIdx + 32;
+            __syncwarp();
+        }
         const u32 h = (LZP_SEED * ctx) >> 16;
         const int ref = lz_xchg(&hashes[h], srcIdx);
         int bestLen = 0;
@@ -557,8 +591,14 @@ lzp_inverse_kernel(StageLaunch L, LzWork W)
         const int srcEnd = count;
         while (srcIdx < srcEnd) {
             const u32 h = (LZP_SEED * ctx) >> 16;
-            const int ref = lz_xchg(&hashes[h], dstIdx);
             const u32 v = src[srcIdx];
+            // the slot's old value matters only behind a flag byte: literals just overwrite it (a store
+            // nobody waits for) instead of a load on the critical path of every byte
+            int ref = 0;
+            if (v == LZP_FLAG)
+                ref = lz_xchg(&hashes[h], dstIdx);
+            else
+                lz_store(&hashes[h], dstIdx);
             if (v != LZP_FLAG || ref == 0) {
                 if (dstIdx >= dstEnd) {
                     ok = false;

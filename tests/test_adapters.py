@@ -51,7 +51,7 @@ def test_adapters_on_emulator():
     inputs = {"comp_90k": synth.synth_compressible(90000, 21), "text_40k": synth.synth_text(40000, 22),
               "tiny_10": small_cases()["rnd256_9"]}
     _check_streams(gpuref, ref, inputs, [("BWT+RANK+ZRLT", "ANS0"), ("NONE", "HUFFMAN"), ("BWT+SRT+ZRLT", "FPAQ"),
-                                         ("ZRLT", "ANS1")], (65536,), jobs=3)
+                                         ("ZRLT", "ANS1"), ("LZ", "HUFFMAN"), ("LZP+LZX", "ANS0")], (65536,), jobs=3)
     # stage level through the shim (TransformSequence built by the routed factory)
     data = inputs["text_40k"]
     for t in ("BWT", "RANK", "ZRLT", "BWT+RANK+ZRLT"):
@@ -66,6 +66,7 @@ def test_adapters_on_gpu():
     inputs = {"comp_3m": synth.synth_compressible(3 * (1 << 20) + 777, 31), "text_70k": synth.synth_text(70000, 22),
               "incomp_300k": synth.synth_incompressible(300000, 23), "tiny_10": small_cases()["rnd256_9"]}
     _check_streams(gpuref, ref, inputs, [("BWT+RANK+ZRLT", "ANS0"), ("BWT+MTFT+ZRLT", "HUFFMAN"), ("NONE", "ANS1"),
-                                         ("BWT+SRT+ZRLT", "FPAQ"), ("ZRLT", "NONE")], (65536, 1 << 20), jobs=8)
+                                         ("BWT+SRT+ZRLT", "FPAQ"), ("ZRLT", "NONE"), ("LZ", "HUFFMAN"), ("LZX", "ANS0"),
+                                         ("LZP", "NONE")], (65536, 1 << 20), jobs=8)
     big = synth.synth_compressible(20 << 20, 2)
     _check_streams(gpuref, ref, {"comp_20m": big}, [("BWT+RANK+ZRLT", "ANS0")], (4 << 20,), jobs=4)

@@ -52,9 +52,10 @@ elif what == "lz":
     import time
     from oracle.oracle import Ref
     ref = Ref.load()
-    for tn in ("LZ", "LZX", "LZP"):
-        run(tn, "HUFFMAN", 4 << 20, nb, 6, reps=2)
-        if ref is not None:
+    only = sys.argv[3].split(",") if len(sys.argv) > 3 else ("LZ", "LZX", "LZP")
+    for tn in only:
+        run(tn, "HUFFMAN", 4 << 20, nb, 6, reps=(1 if len(sys.argv) > 3 else 2))
+        if ref is not None and len(sys.argv) <= 3:
             data = synth.synth_compressible(nb * (4 << 20), 6)
             jobs = min(16, os.cpu_count() or 1)
             t0 = time.time()

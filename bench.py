@@ -513,18 +513,18 @@ def run_ours(args, rank, world, local_rank):
                 stages["config4_" + k] = v
         except Exception as ex:
             stages["config4_error"] = repr(ex)
-    # DRAM traffic per launch from the committed `ncu --set full` captures (profiles/r01_ncu_*.md),
-    # scaled to this rank's blocks: dram__bytes_read.sum + dram__bytes_write.sum
+    # DRAM traffic from the committed ncu captures, scaled to this rank's blocks:
+    # dram__bytes_read.sum + dram__bytes_write.sum
     NCU_TRAFFIC_PER_BLOCK = {
-        # profiles/r01_ncu_traffic_64blocks_v6.md (stage sums of one encode+decode of 64 blocks) / 64
-        "bwt_forward": 64.38e9 / 64,
-        "rank_forward": 1.23e9 / 64,
-        "zrlt_forward": 0.70e9 / 64,
-        "ans0_encode_kernel": 0.46e9 / 64,
-        "ans0_decode_kernel": 0.26e9 / 64,
-        "zrlt_inverse": 1.07e9 / 64,
-        "bwt_inverse": 24.17e9 / 64,
-        "rank_inverse": (1.088619e9 + 1.040149e9) / 256,      # r01_ncu_rank_inverse_256blocks.md (--set full)
+        # profiles/r02_traffic_64blocks.md (stage sums of one encode+decode pass over 64 blocks) / 64
+        "bwt_forward": 64.568e9 / 64,
+        "rank_forward": 1.230e9 / 64,
+        "zrlt_forward": 0.704e9 / 64,
+        "ans0_encode_kernel": 0.458e9 / 64,
+        "ans0_decode_kernel": 0.248e9 / 64,
+        "zrlt_inverse": 1.068e9 / 64,
+        "bwt_inverse": 24.261e9 / 64,
+        "rank_inverse": (1.096665e9 + 1.040414e9) / 256,      # profiles/r02_ncu_rank_256blocks.md (--set full)
     }
     for k, per_block in NCU_TRAFFIC_PER_BLOCK.items():
         if stages.get(k):

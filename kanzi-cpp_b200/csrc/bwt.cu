@@ -987,7 +987,10 @@ bwt_grp_apply_kernel(GrpCtx G)
         const u32 old = G.initial ? 0u : oldHi[x];
         const u32 rank = old + (H - Gm);
         const u32 sfx = s_v[GRP_PAD(threadIdx.x * RS_ITEMS + x)];
-        isa[sfx] = rank;
+        // a survivor whose group did not split keeps the rank the round before wrote: skip the scattered
+        // store (one 32 B sector each; in the late rounds, which only serve long repeats, that is most of them)
+        if (G.initial || H != Gm)
+            isa[sfx] = rank;
         if (!res[x]) {
             vout[U] = sfx;
             gout[U] = rank;
@@ -1862,6 +1865,47 @@ __global__ void bwt_inv_rank_kernel(InvCtx C)
         atomicExch(C.errFlag, KERR_BAD_STREAM);
 }
 
+// Same ranking with the chunk chains walked in shared memory: one CTA per block stages (next, length)
+// of its ~n/256 nodes (8 B each, 128 KiB for a 4 MiB block), then eight threads follow their chains
+// at shared-memory latency (the global version pays a DRAM round trip per node: 4 ms per GiB).
+#define INV_RANK_SMEM_MAX (200 * 1024)
+__global__ void __launch_bounds__(256)
+bwt_inv_rank_smem_kernel(InvCtx C)
+{
+    KNZ_DYN_SMEM(ir_smem);
+    uint2* s_nd = reinterpret_cast<uint2*>(ir_smem);
+    const int b = blockIdx.x;
+    if (b >= C.nBlocks || !C.bwtOk[b])
+        return;
+    const BlkState bs = C.stIn[b];
+    const u8* __restrict__ src = blk_src(C.bt, bs, b);
+    const InvBlk B = inv_blk(C, b, src, bs.len);
+    u32* nodes = C.node + (i64)b * C.nodeStride * 4;
+    const int total = B.S + 8;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const uint2 v = *reinterpret_cast<const uint2*>(nodes + (i64)i * 4);
+        s_nd[i] = v; // x = next node, y = symbols in this node's segment
+    }
+    __syncthreads();
+    const int k = threadIdx.x;
+    if (k >= 8 || B.anchor[k] == 0xFFFFFFFEu)
+        return;
+    u32 off = (u32)((i64)k * B.step);
+    const u32 endOff = (u32)min((i64)(k + 1) * B.step, (i64)B.m);
+    int id = B.S + k;
+    int guard = B.S + 16;
+    while (guard-- > 0) {
+        const uint2 nd = s_nd[id];
+        nodes[(i64)id * 4 + 2] = off;
+        off += nd.y;
+        if (nd.x == 0xFFFFFFFFu || (int)nd.x >= B.S) // text end or the next chunk's anchor
+            break;
+        id = (int)nd.x;
+    }
+    if (off != endOff)
+        atomicExch(C.errFlag, KERR_BAD_STREAM);
+}
+
 void launch_bwt_inverse(const StageLaunch& L, Workspace& wsAll, cudaStream_t s, u64* launches)
 {
     const int nB = L.nBlocks;
@@ -1920,7 +1964,22 @@ void launch_bwt_inverse(const StageLaunch& L, Workspace& wsAll, cudaStream_t s, 
         C.slot = (int)(fit < INV_SLOT ? fit : INV_SLOT);
     }
     KLAUNCH(bwt_inv_walk_kernel, dim3((nodes + 127) / 128, nB), 128, s, C);
-    KLAUNCH(bwt_inv_rank_kernel, (nB * 8 + 63) / 64, 64, s, C);
+    {
+        static bool attr = false;
+        const size_t need = (size_t)(nodes + 8) * sizeof(uint2);
+        if (need <= INV_RANK_SMEM_MAX) {
+#ifndef KNZ_SIM
+            if (!attr) {
+                cudaFuncSetAttribute(bwt_inv_rank_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, INV_RANK_SMEM_MAX);
+                attr = true;
+            }
+#endif
+            KLAUNCH_DYN(bwt_inv_rank_smem_kernel, nB, 256, need, s, C);
+        } else {
+            KLAUNCH(bwt_inv_rank_kernel, (nB * 8 + 63) / 64, 64, s, C);
+        }
+        (void)attr;
+    }
     KLAUNCH(bwt_inv_copy_kernel, dim3(min((nodes + 7) / 8, 1024), nB), 256, s, C);
     *launches += 3;
 }

@@ -361,7 +361,7 @@ def test_gpu_rejects_oversized_parameters(gpu):
         gpu.encode_blocks(blocks, "ZRLT", "ANS0", 8 << 20)
     comp = gpu.compress(data, "NONE", "ANS0", 1 << 16)
     bad = comp.copy()
-    bad[19] ^= 0x5A  # stream header checksum byte
+    bad[8] ^= 0x5A  # inside the 48-bit transform word: the 24-bit header checksum no longer matches
     with pytest.raises(KanziGpuError) as e:
         gpu.decompress(bad, data.size)
     assert e.value.code == 19  # ERR_CRC_CHECK

@@ -341,8 +341,14 @@ rs_text_hist_kernel(SortArrays A, TextSort T)
     __syncthreads();
     const u8* __restrict__ text = blk_src(T.bt, T.st[b], b);
     const int end = min(cnt, base + RS_TILE * 4);
-    for (int j = base + threadIdx.x; j < end; j += RS_THREADS)
-        atomicAdd(&s_h[text[j]], 1u);
+    const int lane = threadIdx.x & 31;
+    for (int j0 = base + (threadIdx.x & ~31); j0 < end; j0 += RS_THREADS) { // one atomic per distinct byte per warp row
+        const int j = j0 + lane;
+        const u32 c = (j < end) ? (u32)text[j] : (256u + (u32)lane);
+        const u32 peers = __match_any_sync(FULL_MASK, c);
+        if (j < end && (peers >> lane) == 1u)
+            atomicAdd(&s_h[c], (u32)__popc(peers));
+    }
     __syncthreads();
     const u32 v = s_h[threadIdx.x];
     if (v)

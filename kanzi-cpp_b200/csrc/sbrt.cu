@@ -69,12 +69,26 @@ sbrt_occ_kernel(BufTable bt, const BlkState* __restrict__ stIn, const BlkState* 
     s_t2[threadIdx.x] = 0;
     __syncthreads();
     const int end = min(base + S_TILE, n);
-    for (int i = base + threadIdx.x; i < end; i += 256)
-        atomicMax(&s_t1[src[i]], (u32)(i + 1));
+    // Post-BWT data is long runs of one symbol: 32 lanes hitting one shared-memory word serialise.
+    // Positions grow with the lane, so of the lanes that hold the same symbol only the highest one
+    // (match_any) can win the max: one atomic per distinct symbol per warp row.
+    const int lane = threadIdx.x & 31;
+    for (int i0 = base + (threadIdx.x & ~31); i0 < end; i0 += 256) {
+        const int i = i0 + lane;
+        const u32 c = (i < end) ? (u32)src[i] : (256u + (u32)lane);
+        const u32 peers = __match_any_sync(FULL_MASK, c);
+        if (i < end && (peers >> lane) == 1u)
+            atomicMax(&s_t1[c], (u32)(i + 1));
+    }
     __syncthreads();
-    for (int i = base + threadIdx.x; i < end; i += 256) {
-        const u32 c = src[i];
-        if ((u32)(i + 1) != s_t1[c])
+    for (int i0 = base + (threadIdx.x & ~31); i0 < end; i0 += 256) {
+        const int i = i0 + lane;
+        const bool in = i < end;
+        const u32 c = in ? (u32)src[i] : (256u + (u32)lane);
+        const u32 peers = __match_any_sync(FULL_MASK, c);
+        const bool cand = in && ((u32)(i + 1) != s_t1[c]);
+        const u32 cm = __ballot_sync(FULL_MASK, cand) & peers; // same-symbol lanes that are not the last occurrence
+        if (cand && (cm >> lane) == 1u)
             atomicMax(&s_t2[c], (u32)(i + 1));
     }
     __syncthreads();

@@ -155,6 +155,25 @@ __device__ __forceinline__ ZEntry zapply(const ZEntry& e, const ZSum& S)
     return r;
 }
 
+// A thread's 16-byte segment in four registers: one 128-bit load when the segment is whole and
+// aligned (stage buffers always are; a caller's input may not be), else byte by byte.  Returns the
+// number of valid bytes.
+__device__ __forceinline__ int zload16(const u8* __restrict__ src, int pos, int n, u32 w[4])
+{
+    const int cnt = min(16, n - pos);
+    const u8* p = src + pos;
+    if (cnt == 16 && (reinterpret_cast<size_t>(p) & 15) == 0) {
+        const uint4 v = *reinterpret_cast<const uint4*>(p);
+        w[0] = v.x, w[1] = v.y, w[2] = v.z, w[3] = v.w;
+    } else {
+        w[0] = w[1] = w[2] = w[3] = 0;
+        for (int k = 0; k < cnt; k++)
+            w[k >> 2] |= (u32)p[k] << (8 * (k & 3));
+    }
+    return cnt;
+}
+#define ZBYTE(w, k) (((w)[(k) >> 2] >> (8 * ((k)&3))) & 0xFFu)
+
 // ---- forward: per-thread walk over <= 16 bytes
 __device__ __forceinline__ ZSum zfwd_summary(const u8* __restrict__ src, int pos, int n)
 {
@@ -162,9 +181,13 @@ __device__ __forceinline__ ZSum zfwd_summary(const u8* __restrict__ src, int pos
     S.allz = 1;
     u32 run = 0;
     bool seen = false;
-    const int end = min(pos + 16, n);
-    for (int i = pos; i < end; i++) {
-        const u32 v = src[i];
+    u32 w[4];
+    const int cnt = zload16(src, pos, n, w);
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        if (k >= cnt)
+            break;
+        const u32 v = ZBYTE(w, k);
         if (v == 0) {
             run++;
             continue;
@@ -287,8 +310,13 @@ zrlt_fwd_emit_kernel(BufTable bt, const BlkState* __restrict__ st, int maxTiles,
     const ZEntry e = zapply<false>(tileEntry[(i64)b * maxTiles + t], pre);
     u32 out = e.out, run = e.cnt;
     const int end = min(pos + 16, n);
-    for (int i = pos; i < end; i++) {
-        const u32 v = src[i];
+    u32 w[4];
+    const int cnt = zload16(src, pos, n, w);
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        if (k >= cnt)
+            break;
+        const u32 v = ZBYTE(w, k);
         if (v == 0) {
             run++;
             continue;
@@ -325,9 +353,13 @@ __device__ __forceinline__ ZSum zinv_summary(const u8* __restrict__ src, int pos
     u32 cnt = 0, bits = 0;
     bool seen = false;
     bool payload = zinv_first_is_payload(src, pos);
-    const int end = min(pos + 16, n);
-    for (int i = pos; i < end; i++) {
-        const u32 v = src[i];
+    u32 w[4];
+    const int nb = zload16(src, pos, n, w);
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        if (k >= nb)
+            break;
+        const u32 v = ZBYTE(w, k);
         if (!payload && v <= 1) {
             bits = (bits << 1) | v;
             cnt = (cnt < 64) ? cnt + 1 : cnt;
@@ -425,9 +457,13 @@ zrlt_inv_emit_kernel(BufTable bt, const BlkState* __restrict__ st, int maxTiles,
     const ZEntry e = zapply<true>(tileEntry[(i64)b * maxTiles + t], pre);
     u32 out = e.out, cnt = e.cnt, bits = e.bits;
     bool payload = zinv_first_is_payload(src, pos);
-    const int end = min(pos + 16, n);
-    for (int i = pos; i < end; i++) {
-        const u32 v = src[i];
+    u32 w[4];
+    const int nb = zload16(src, pos, n, w);
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        if (k >= nb)
+            break;
+        const u32 v = ZBYTE(w, k);
         if (!payload && v <= 1) {
             bits = (bits << 1) | v;
             cnt++;

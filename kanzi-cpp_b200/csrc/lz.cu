@@ -209,20 +209,62 @@ lzx_forward_kernel(StageLaunch L, LzWork W)
     int repd0 = count, repd1 = count; // repd[0], repd[1]
     int repIdx = 0, srcInc = 0;
     bool ok = true;
-    int winEnd = 0; // positions below winEnd had their hash slot and their candidate's bytes pulled into L1
+    // Most positions of a block match nothing (2.6 M of the 4 M positions of a compressible 4 MiB block), and
+    // for those the sequential step -- hash, table exchange, three candidate tests, each a chain of dependent
+    // loads -- only advances by one.  While no match is pending the state is simple (repeat distances fixed,
+    // skip growing by the book), so the lanes test the next 32 VISITED positions side by side: lane j hashes
+    // position p_j, takes its candidate from the latest earlier lane with the same hash or else from the table,
+    // and applies the three 4-byte tests that gate findMatch in the reference.  The first lane that passes any
+    // of them is the next position the sequential step has to look at; all lanes before it are misses and are
+    // committed at once (table insertions, last one wins; skip counter).  The tests are the reference's own
+    // gates, so the scan can stop early (the sequential step then decides) but never skips a match.
+    bool scan = true;
     while (srcIdx < srcEnd) {
-        // A step of the parse is a chain of three dependent loads (text -> hash slot -> candidate text), each a
-        // trip to L2 or HBM when taken cold.  Every 30 positions the lanes run that chain for the next 32
-        // positions side by side; the values are hints only (the parse re-reads the table in order).
-        if (srcIdx + 2 >= winEnd) {
-            const int pw = srcIdx + lane;
-            if (pw < srcEnd) {
-                const int cand = hashes[lz_hash(src + pw, lim, HLOG)];
-                if (cand > 0)
-                    lz_prefetch(src + cand);
+        if (scan) {
+            int pj = srcIdx + lane;
+            if (srcInc + 31 >= 64) { // the skip has started to grow: p_(j+1) = p_j + 1 + ((srcInc + j) >> 6)
+                pj = srcIdx;
+                for (int i = 0; i < lane; i++)
+                    pj += 1 + ((srcInc + i) >> 6);
             }
-            winEnd = srcIdx + 32;
+            const bool act = pj < srcEnd;
+            const u32 h = act ? lz_hash(src + pj, lim, HLOG) : (0x80000000u | (u32)lane);
+            const u32 peers = __match_any_sync(FULL_MASK, h);
+            const u32 lower = peers & ((1u << lane) - 1u);
+            const int fromLane = lower ? (31 - __clz((int)lower)) : lane;
+            const int inWin = __shfl_sync(FULL_MASK, pj, fromLane);
+            __syncwarp(); // every earlier insertion is visible
+            const int cand = lower ? inWin : (act ? hashes[h] : 0);
+            bool ev = false;
+            if (act) {
+                const int minRefJ = max(pj - maxDist, 0);
+                const u64 t = lz_ld64(src + pj, lim);
+                const u32 w0 = (u32)t, w1n = (u32)(t >> 8);
+                int r = pj + 1 - repd0;
+                if (r > minRefJ && w1n == lz_ld32(src + r, lim))
+                    ev = true;
+                r = pj + 1 - repd1;
+                if (r > minRefJ && w1n == lz_ld32(src + r, lim))
+                    ev = true;
+                if (cand > minRefJ && w0 == lz_ld32(src + cand, lim))
+                    ev = true;
+            }
+            const u32 evm = __ballot_sync(FULL_MASK, ev);
+            const int nact = __popc(__ballot_sync(FULL_MASK, act)); // active lanes are a prefix
+            const int f = evm ? (__ffs((int)evm) - 1) : nact;      // lanes below f are misses
+            const u32 below = (f >= 32) ? 0xFFFFFFFFu : ((1u << f) - 1u);
+            if (lane < f && ((peers & below) >> lane) == 1u)
+                hashes[h] = pj;
             __syncwarp();
+            if (f > 0) {
+                const int last = __shfl_sync(FULL_MASK, pj, f - 1);
+                srcIdx = (f < nact) ? __shfl_sync(FULL_MASK, pj, f & 31) : last + 1 + ((srcInc + f - 1) >> 6);
+                srcInc += f;
+                repIdx = 0;
+            }
+            if (evm == 0)
+                continue;
+            scan = false; // a candidate is pending at srcIdx: the sequential step decides
         }
         int bestLen = 0;
         const u32 h0 = lz_hash(src + srcIdx, lim, HLOG);
@@ -247,6 +289,7 @@ lzx_forward_kernel(StageLaunch L, LzWork W)
                 srcIdx = srcIdx1 + (srcInc >> 6);
                 srcInc++;
                 repIdx = 0;
+                scan = true;
                 continue;
             }
             if (srcIdx - ref != repd0 && srcIdx - ref != repd1) {
@@ -509,17 +552,53 @@ lzp_forward_kernel(StageLaunch L, LzWork W)
     u32 ctx = lz_ld32(src, lim);
     int srcIdx = 4, dstIdx = 4;
     bool ok = true;
-    int winEnd = 0;
+    // Matches are rare (>= 64 bytes): nearly every position is a literal.  As in the LZ parse the lanes test the
+    // next 32 positions side by side -- context hash, candidate from the latest earlier lane with that hash or from
+    // the table, the reference's 8-byte gate at offset 56 -- and commit all literals before the first candidate
+    // at once (bytes and escapes at scanned offsets, table insertions with the last one winning).  The context is
+    // history dependent: little-endian read after a match, then shifted a byte at a time (LZCodec.cpp:813,842).
     while (srcIdx < srcEnd - LZP_MIN_MATCH && dstIdx < dstEnd) {
-        if (srcIdx >= winEnd) { // same look-ahead as the LZ parse: slot and candidate of the next 32 positions
-            const int pw = srcIdx + lane;
-            if (pw < srcEnd - LZP_MIN_MATCH) {
-                const int cand = hashes[(LZP_SEED * lz_ld32(src + pw - 4, lim)) >> 16];
-                if (cand > 0)
-                    lz_prefetch(src + cand + LZP_MIN_MATCH - 8);
+        if (dstIdx + 80 < dstEnd) {
+            const int pj = srcIdx + lane;
+            const bool act = pj < srcEnd - LZP_MIN_MATCH;
+            u32 cj = ctx;
+            if (lane >= 4) {
+                cj = __byte_perm(lz_ld32(src + pj - 4, lim), 0, 0x0123); // the last four bytes, oldest on top
+            } else {
+                for (int i = 0; i < lane; i++)
+                    cj = (cj << 8) | src[srcIdx + i];
             }
-            winEnd = srcIdx + 32;
+            const u32 h = act ? ((LZP_SEED * cj) >> 16) : (0x80000000u | (u32)lane);
+            const u32 peers = __match_any_sync(FULL_MASK, h);
+            const u32 lower = peers & ((1u << lane) - 1u);
+            const int inWin = __shfl_sync(FULL_MASK, pj, lower ? (31 - __clz((int)lower)) : lane);
             __syncwarp();
+            const int cand = lower ? inWin : (act ? hashes[h] : 0);
+            const bool ev = act && cand != 0 &&
+                            lz_ld64(src + cand + LZP_MIN_MATCH - 8, lim) == lz_ld64(src + pj + LZP_MIN_MATCH - 8, lim);
+            const u32 evm = __ballot_sync(FULL_MASK, ev);
+            const int nact = __popc(__ballot_sync(FULL_MASK, act));
+            const int f = evm ? (__ffs((int)evm) - 1) : nact;
+            const u32 val = act ? (u32)src[pj] : 0u;
+            const u32 nb = (lane < f) ? (1u + ((cand != 0 && val == LZP_FLAG) ? 1u : 0u)) : 0u;
+            const u32 incl = warp_incl_sum(nb, lane);
+            const u32 below = (f >= 32) ? 0xFFFFFFFFu : ((1u << f) - 1u);
+            if (lane < f) {
+                const u32 o = (u32)dstIdx + incl - nb;
+                dst[o] = (u8)val;
+                if (nb == 2)
+                    dst[o + 1] = 0xFF;
+                if (((peers & below) >> lane) == 1u)
+                    hashes[h] = pj;
+            }
+            __syncwarp();
+            if (f > 0) {
+                dstIdx += (int)__shfl_sync(FULL_MASK, incl, f - 1);
+                ctx = __shfl_sync(FULL_MASK, (cj << 8) | val, f - 1);
+                srcIdx += f;
+            }
+            if (evm == 0)
+                continue;
         }
         const u32 h = (LZP_SEED * ctx) >> 16;
         const int ref = lz_xchg(&hashes[h], srcIdx);
@@ -597,6 +676,37 @@ lzp_inverse_kernel(StageLaunch L, LzWork W)
         u32 ctx = lz_ld32(src, lim);
         const int srcEnd = count;
         while (srcIdx < srcEnd) {
+            // literal runs, 32 bytes per trip: everything up to the next flag byte is copied, its context
+            // hashes inserted (last one wins); only a flag byte needs the table's old value
+            if (dstIdx + 40 < dstEnd) {
+                const int sj = srcIdx + lane;
+                const bool act = sj < srcEnd;
+                const u32 vj = act ? (u32)src[sj] : (u32)LZP_FLAG;
+                const u32 stop = __ballot_sync(FULL_MASK, vj == LZP_FLAG);
+                const int f = stop ? (__ffs((int)stop) - 1) : 32;
+                if (f > 0) {
+                    u32 cj = ctx;
+                    if (lane >= 4) {
+                        cj = __byte_perm(lz_ld32(src + sj - 4, lim), 0, 0x0123);
+                    } else {
+                        for (int i = 0; i < lane; i++)
+                            cj = (cj << 8) | src[srcIdx + i];
+                    }
+                    const u32 hj = (lane < f) ? ((LZP_SEED * cj) >> 16) : (0x80000000u | (u32)lane);
+                    const u32 peers = __match_any_sync(FULL_MASK, hj);
+                    __syncwarp();
+                    if (lane < f) {
+                        dst[dstIdx + lane] = (u8)vj;
+                        if ((peers >> lane) == 1u)
+                            hashes[hj] = dstIdx + lane;
+                    }
+                    __syncwarp();
+                    ctx = __shfl_sync(FULL_MASK, (cj << 8) | vj, f - 1);
+                    dstIdx += f;
+                    srcIdx += f;
+                    continue;
+                }
+            }
             const u32 h = (LZP_SEED * ctx) >> 16;
             const u32 v = src[srcIdx];
             // the slot's old value matters only behind a flag byte: literals just overwrite it (a store

@@ -9,6 +9,10 @@
 //   alphabet       entropy/EntropyUtils.cpp:57-89
 //   chunk header   entropy/ANSRangeEncoder.cpp:83-155
 //   symbol reset   entropy/ANSRangeEncoder.hpp:92-116
+// NOTE: the slow error-spreading path of the normaliser (normalize_spread / normalize_counts) restates
+// EntropyUtils::normalizeFrequencies decision for decision -- which symbol gives up or receives a unit of
+// frequency decides the header bytes and every later state -- so these lines have no freedom of design.
+// The fast path is warp-parallel (ans.cu) and original.
 #pragma once
 #include <stdint.h>
 

@@ -7,6 +7,10 @@
 //   entropy/ExpGolombEncoder.hpp:51-62 signed exp-Golomb of the length deltas
 // The caller provides the (freq << 8 | symbol) keys already SORTED increasingly
 // (the warp sorts them in parallel); everything else is small serial integer work.
+// NOTE: huf_inplace_lengths and huf_limit_fast necessarily restate the reference's serial heuristics
+// (computeInPlaceSizesPhase1/2, limitCodeLengths) decision for decision: every tie-break and every unit of
+// "debt" moved changes code lengths and therefore the bitstream, so there is no freedom of design in these
+// ~150 lines; the parallel work around them (histogram, sort, emit) is this repo's own.
 #pragma once
 #include "ans_tables.cuh"
 

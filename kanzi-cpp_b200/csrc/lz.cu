@@ -16,6 +16,11 @@
 //     by letting only the highest lane of a match_any group store), the final concatenation of
 //     the four streams, and in the decoders the literal and match copies (a match closer than 32
 //     bytes is a periodic pattern of bytes that already exist, farther ones go 32 bytes per round)
+// NOTE: the sequential step of lzx_forward / lzp_forward (which candidate is tried first, the lazy
+// positions, the backward extension, the token layout) restates the reference's parse decision for
+// decision -- any deviation changes the tokens and therefore the bitstream.  What is this repo's own is
+// the execution model around it: warp-uniform execution, the lane-parallel scan over positions that
+// match nothing, cooperative literal / match copies and table insertions.
 // LZ/LZX keep their three side streams (tokens, distances, match lengths) in per-block scratch: the
 // stage fails as soon as literals + side streams reach the input length (LZCodec.cpp:421 tests the
 // same sum once at the end; every term only grows), so one input length of scratch bounds them.
@@ -218,9 +223,8 @@ lzx_forward_kernel(StageLaunch L, LzWork W)
     // of them is the next position the sequential step has to look at; all lanes before it are misses and are
     // committed at once (table insertions, last one wins; skip counter).  The tests are the reference's own
     // gates, so the scan can stop early (the sequential step then decides) but never skips a match.
-    bool scan = true;
     while (srcIdx < srcEnd) {
-        if (scan) {
+        { // (a scan whose first lane already passes costs less than a sequential miss, so it always runs)
             int pj = srcIdx + lane;
             if (srcInc + 31 >= 64) { // the skip has started to grow: p_(j+1) = p_j + 1 + ((srcInc + j) >> 6)
                 pj = srcIdx;
@@ -263,8 +267,7 @@ lzx_forward_kernel(StageLaunch L, LzWork W)
                 repIdx = 0;
             }
             if (evm == 0)
-                continue;
-            scan = false; // a candidate is pending at srcIdx: the sequential step decides
+                continue; // else a candidate is pending at srcIdx: the sequential step decides
         }
         int bestLen = 0;
         const u32 h0 = lz_hash(src + srcIdx, lim, HLOG);
@@ -289,7 +292,6 @@ lzx_forward_kernel(StageLaunch L, LzWork W)
                 srcIdx = srcIdx1 + (srcInc >> 6);
                 srcInc++;
                 repIdx = 0;
-                scan = true;
                 continue;
             }
             if (srcIdx - ref != repd0 && srcIdx - ref != repd1) {

@@ -98,7 +98,7 @@ int knz_decode_blocks(knz_ctx* ctx, uint64_t tType, int eType, int blockSize, co
  * prefixes :852-864, end marker :416-417) and CompressedInputStream::read
  * (io/CompressedInputStream.cpp:428-510, readHeader :511-663), host buffers.
  * Output is byte-identical to the reference's stream for the same parameters
- * (checksum 0, skipBlocks off).                                                  */
+ * (block checksums: knz_set_checksum; skipBlocks: knz_set_skip_blocks).           */
 int knz_compress(knz_ctx* ctx, const char* transform, const char* entropy, int blockSize, const uint8_t* in,
                  int64_t n, uint8_t* out, int64_t cap, int64_t* outLen);
 int knz_decompress(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_t* out, int64_t cap, int64_t* outLen);
@@ -132,6 +132,43 @@ int knz_stream_header_ex(uint64_t tType, int eType, int blockSize, int64_t input
  * checksum size from the stream header and verify every decoded block (io/CompressedInputStream.cpp:
  * 1003-1022), failing with KNZ_ERR_CRC_CHECK.                                                            */
 int knz_set_checksum(knz_ctx* ctx, int bits);
+
+/* `skipBlocks` of the reference's context (io/CompressedOutputStream.cpp:697-715): when on, a block whose
+ * first four bytes are the signature of an already compressed format (Magic.hpp:69-131) or whose order-0
+ * entropy reaches EntropyUtils::INCOMPRESSIBLE_THRESHOLD (973/1024 bits per byte, Global.cpp:313-329) is
+ * written as a copy block (mode 0x80, no transform, no entropy coding).  Applies to every encoder of the
+ * context; the decoders need nothing (copy blocks are part of the format).                               */
+int knz_set_skip_blocks(knz_ctx* ctx, int on);
+
+/* Block range of CompressedInputStream (context entries "from" / "to", io/CompressedInputStream.cpp:836-837,
+ * :864-869): block ids are 1-based; blocks with fromBlock <= id < toBlock are decoded and concatenated in
+ * `out`, the others are stepped over through their length prefixes (only the bytes of the stream that
+ * hold the wanted blocks are sent to the device).  knz_decompress == range [1, INT_MAX).                */
+int knz_decompress_range(knz_ctx* ctx, const uint8_t* in, int64_t n, int fromBlock, int toBlock, uint8_t* out,
+                         int64_t cap, int64_t* outLen);
+
+/* Listener events (Event.hpp:28-88).  The reference's tasks notify their listeners around every stage of
+ * every block (io/CompressedOutputStream.cpp:685-689, :768-772, :810-814, :871-881;
+ * io/CompressedInputStream.cpp:380, :924-932, :973-983); here a batch of blocks goes through the device
+ * as one unit, so knz_compress / knz_decompress re-emit the same events, with the same ids, sizes, hashes,
+ * bit offsets and skip flags, when the batch has completed -- per block in the reference's order, blocks
+ * in stream order, on the calling thread.  type values are those of Event::Type.                         */
+#define KNZ_EVT_BEFORE_TRANSFORM 2
+#define KNZ_EVT_AFTER_TRANSFORM 3
+#define KNZ_EVT_BEFORE_ENTROPY 4
+#define KNZ_EVT_AFTER_ENTROPY 5
+#define KNZ_EVT_BLOCK_INFO 9
+typedef struct knz_event {
+    int type;          /* KNZ_EVT_* */
+    int blockId;       /* 1-based */
+    int64_t size;      /* bytes: block / post-transform / coded size as in the reference's event */
+    uint64_t hash;     /* block checksum when hashBits != 0 */
+    int hashBits;      /* 0, 32 or 64 (Event::HashType) */
+    int64_t offset;    /* BLOCK_INFO: bit position of the block in the stream, else -1 */
+    uint8_t skipFlags; /* BLOCK_INFO: TransformSequence skip flags */
+} knz_event;
+typedef void (*knz_event_fn)(void* user, const knz_event* evt);
+int knz_set_listener(knz_ctx* ctx, knz_event_fn fn, void* user); /* fn == NULL: off */
 
 /* ---- Stage level (what the Transform<byte> / EntropyEncoder adapters call).
  * knz_transform_forward == Transform<byte>::forward (src/Transform.hpp:38):

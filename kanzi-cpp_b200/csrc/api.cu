@@ -4,6 +4,8 @@
 //   transforms (BWT -> RANK/MTFT -> ZRLT)  ->  rANS  ->  bit assembly.
 // The reference's equivalents are CompressedOutputStream / EncodingTask and
 // CompressedInputStream / DecodingTask (io/Compressed{Output,Input}Stream.cpp).
+#include <math.h>
+
 #include "ctx.h"
 
 i64 knz_round_up(i64 v, i64 a) { return (v + a - 1) / a * a; }
@@ -203,6 +205,16 @@ extern "C" int knz_create(int device, int maxBlockSize, int maxBatchBlocks, knz_
     A(dalloc(&ctx->blockHash, nb));
     A(dalloc(&ctx->expectHash, nb));
     A(cudaMallocHost((void**)&ctx->h_hash, sizeof(u64) * nb));
+    A(dalloc(&ctx->dSkip, nb));
+    A(dalloc(&ctx->dLog2Tab, 257));
+    A(cudaMallocHost((void**)&ctx->h_skip, sizeof(int) * nb));
+    if (ok) { // Global::LOG2_4096 (Global.cpp:47-74) is round(4096 * log2(i)); tests compare all 257 entries
+        int tab[257];
+        tab[0] = 0;
+        for (int i = 1; i <= 256; i++)
+            tab[i] = (int)floor(4096.0 * log2((double)i) + 0.5);
+        A(cudaMemcpy(ctx->dLog2Tab, tab, sizeof(tab), cudaMemcpyHostToDevice));
+    }
     A(cudaMallocHost((void**)&ctx->h_st, sizeof(BlkState) * nb));
     A(cudaMallocHost((void**)&ctx->h_capEven, sizeof(int) * nb));
     A(cudaMallocHost((void**)&ctx->h_capOdd, sizeof(int) * nb));
@@ -239,12 +251,13 @@ extern "C" void knz_destroy(knz_ctx* ctx)
     void* dev[] = { ctx->bufA, ctx->bufB, ctx->dStageIn, ctx->dOut, ctx->st, ctx->capEven, ctx->capOdd, ctx->slots,
                     ctx->hdrBits, ctx->payBytes, ctx->payOff, ctx->chunkOff, ctx->chunkPos, ctx->blockBits,
                     ctx->blockOff, ctx->streamPos, ctx->dInBits, ctx->dPayStart, ctx->dPreLen, ctx->errFlag,
-                    ctx->dStream, ctx->dPlain, ctx->dPlain2, ctx->blockHash, ctx->expectHash };
+                    ctx->dStream, ctx->dPlain, ctx->dPlain2, ctx->blockHash, ctx->expectHash, ctx->dSkip,
+                    ctx->dLog2Tab };
     for (size_t i = 0; i < sizeof(dev) / sizeof(dev[0]); i++)
         if (dev[i])
             cudaFree(dev[i]);
     void* hst[] = { ctx->h_st, ctx->h_capEven, ctx->h_capOdd, ctx->h_err, ctx->h_preLen, ctx->h_bits,
-                    ctx->h_payStart, ctx->h_pos, ctx->h_hash };
+                    ctx->h_payStart, ctx->h_pos, ctx->h_hash, ctx->h_skip };
     for (size_t i = 0; i < sizeof(hst) / sizeof(hst[0]); i++)
         if (hst[i])
             cudaFreeHost(hst[i]);
@@ -291,6 +304,38 @@ extern "C" int knz_set_checksum(knz_ctx* ctx, int bits)
     std::lock_guard<std::recursive_mutex> lock_(ctx->mtx);
     ctx->checksumBits = bits;
     return KNZ_OK;
+}
+
+extern "C" int knz_set_skip_blocks(knz_ctx* ctx, int on)
+{
+    if (ctx == NULL)
+        return KNZ_ERR_INVALID_PARAM;
+    std::lock_guard<std::recursive_mutex> lock_(ctx->mtx);
+    ctx->skipBlocks = on ? 1 : 0;
+    return KNZ_OK;
+}
+
+extern "C" int knz_set_listener(knz_ctx* ctx, knz_event_fn fn, void* user)
+{
+    if (ctx == NULL)
+        return KNZ_ERR_INVALID_PARAM;
+    std::lock_guard<std::recursive_mutex> lock_(ctx->mtx);
+    ctx->listener = fn;
+    ctx->listenerUser = user;
+    return KNZ_OK;
+}
+
+static void emit_event(knz_ctx* ctx, int type, int blockId, i64 size, u64 hash, int hashBits, i64 offset, int skipFlags)
+{
+    knz_event e;
+    e.type = type;
+    e.blockId = blockId;
+    e.size = size;
+    e.hash = hashBits ? hash : 0;
+    e.hashBits = hashBits;
+    e.offset = offset;
+    e.skipFlags = (uint8_t)skipFlags;
+    ctx->listener(ctx->listenerUser, &e);
 }
 
 extern "C" const char* knz_last_error(const knz_ctx* ctx) { return ctx ? ctx->err : "null context"; }
@@ -487,6 +532,8 @@ int knz_encode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8
     CK(cudaEventRecord(ctx->ev[0], s));
     if (ctx->checksumBits) // XXHash of every block before the transforms (io/CompressedOutputStream.cpp:674-682)
         launch_xxhash(bt, ctx->st, nB, ctx->checksumBits, ctx->blockHash, NULL, ctx->errFlag, s, &ctx->launches);
+    if (ctx->skipBlocks) // entropy / signature test (io/CompressedOutputStream.cpp:697-715)
+        launch_skip_decide(bt, ctx->st, nB, ctx->dLog2Tab, ctx->dSkip, s, &ctx->launches);
     for (int i = 0; i < nt; i++) {
         StageLaunch L;
         L.bt = bt;
@@ -526,11 +573,29 @@ int knz_encode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8
     E.evK1 = ctx->ev[9];
     E.a1 = &ctx->a1;
     launch_entropy_encode(E, s, &ctx->launches);
+    if (ctx->skipBlocks) { // flagged blocks: their private buffer becomes the copy block
+        launch_copy_frame(bt, ctx->st, nB, ctx->dSkip, ctx->checksumBits >> 3, ctx->blockHash, d_out, outStride, d_bits, s,
+                          &ctx->launches);
+        CK(cudaMemcpyAsync(ctx->h_skip, ctx->dSkip, sizeof(int) * nB, cudaMemcpyDeviceToHost, s));
+    }
     CK(cudaEventRecord(ctx->ev[4], s));
     CK(cudaMemcpyAsync(ctx->h_err, ctx->errFlag, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(ctx->h_st, stFinal, sizeof(BlkState) * nB, cudaMemcpyDeviceToHost, s));
+    if (ctx->listener) {
+        CK(cudaMemcpyAsync(ctx->h_bits, d_bits, sizeof(u64) * nB, cudaMemcpyDeviceToHost, s));
+        if (ctx->checksumBits)
+            CK(cudaMemcpyAsync(ctx->h_hash, ctx->blockHash, sizeof(u64) * nB, cudaMemcpyDeviceToHost, s));
+    }
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
+    for (int b = 0; b < nB; b++) {
+        if (!ctx->skipBlocks)
+            ctx->h_skip[b] = 0;
+        if (ctx->h_skip[b]) { // what the reference reports for a copy block: one NullTransform, applied
+            ctx->h_st[b].len = lens[b];
+            ctx->h_st[b].flags = 0x7F;
+        }
+    }
     float ms = 0.f;
     for (int i = 0; i < nt; i++) { // stage brackets were recorded without stalling the stream
         cudaEventElapsedTime(&ms, ctx->evStage[2 * i], ctx->evStage[2 * i + 1]);
@@ -865,10 +930,33 @@ extern "C" int knz_compress(knz_ctx* ctx, const char* transform, const char* ent
         if (rc == KNZ_OK && ng < nb) {
             u8 tmp[32];
             memset(tmp, 0, sizeof(tmp));
-            ctx->h_bits[0] = knz_frame_small_block(in + off + (i64)ng * blockSize, lens[ng], tmp, ctx->checksumBits);
+            ctx->h_bits[ng] = knz_frame_small_block(in + off + (i64)ng * blockSize, lens[ng], tmp, ctx->checksumBits);
             CK(cudaMemcpyAsync(ctx->dOut + (i64)ng * ctx->outStride, tmp, 32, cudaMemcpyHostToDevice, s));
-            CK(cudaMemcpyAsync(ctx->blockBits + ng, ctx->h_bits, sizeof(u64), cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(ctx->blockBits + ng, ctx->h_bits + ng, sizeof(u64), cudaMemcpyHostToDevice, s));
             CK(cudaStreamSynchronize(s));
+            ctx->h_st[ng].len = lens[ng];
+            ctx->h_st[ng].flags = 0x7F;
+            if (ctx->checksumBits)
+                ctx->h_hash[ng] = knz_xxhash_host(in + off + (i64)ng * blockSize, lens[ng], ctx->checksumBits);
+        }
+        if (rc == KNZ_OK && ctx->listener) {
+            // Event re-emission (io/CompressedOutputStream.cpp:685-689, :768-772, :810-814, :871-881): the batch
+            // has completed, so the events of a block come out together, blocks in stream order
+            u64 pos = ctx->h_pos[0]; // bit position of the batch in the stream (OutputBitStream::tell)
+            for (int g = 0; g < nb; g++) {
+                const int id = (int)(b0 + g) + 1;
+                const u64 wr = ctx->h_bits[g];
+                const int post = ctx->h_st[g].len;
+                const u64 hsh = ctx->checksumBits ? ctx->h_hash[g] : 0;
+                emit_event(ctx, KNZ_EVT_BEFORE_TRANSFORM, id, lens[g], hsh, ctx->checksumBits, -1, 0);
+                emit_event(ctx, KNZ_EVT_AFTER_TRANSFORM, id, post, hsh, ctx->checksumBits, -1, 0);
+                emit_event(ctx, KNZ_EVT_BEFORE_ENTROPY, id, post, hsh, ctx->checksumBits, -1, 0);
+                emit_event(ctx, KNZ_EVT_AFTER_ENTROPY, id, (i64)((wr + 7) >> 3), hsh, ctx->checksumBits, -1, 0);
+                emit_event(ctx, KNZ_EVT_BLOCK_INFO, id, (i64)((wr + 7) >> 3), hsh, ctx->checksumBits, (i64)pos,
+                           ctx->h_st[g].flags & 0xFF);
+                const u32 lw = (wr < 8) ? 3u : (u32)ilog2_u32((u32)(wr >> 3)) + 4u;
+                pos += 5 + lw + wr;
+            }
         }
         free(lens);
         if (rc != KNZ_OK) {
@@ -1362,9 +1450,22 @@ int knz_parse_stream_header(knz_ctx* ctx, HostBitReader& r, KnzStreamInfo* info)
     return KNZ_OK;
 }
 
-extern "C" int knz_decompress(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_t* out, int64_t cap, int64_t* outLen)
+// Events of one decoded block (io/CompressedInputStream.cpp:924-932, :973-983, :380), in the order the
+// reference's task and its consumer emit them.
+static void emit_decode_events(knz_ctx* ctx, int id, i64 offset, i64 rBytes, int preLen, int decoded, u64 ck, int ckBits,
+                               int flags)
 {
-    if (!ctx || !in || !out || !outLen || n < 20)
+    emit_event(ctx, KNZ_EVT_BLOCK_INFO, id, rBytes, ck, ckBits, offset, flags);
+    emit_event(ctx, KNZ_EVT_BEFORE_ENTROPY, id, rBytes, ck, ckBits, -1, 0);
+    emit_event(ctx, KNZ_EVT_AFTER_ENTROPY, id, preLen, ck, ckBits, -1, 0);
+    emit_event(ctx, KNZ_EVT_BEFORE_TRANSFORM, id, preLen, ck, ckBits, -1, 0);
+    emit_event(ctx, KNZ_EVT_AFTER_TRANSFORM, id, decoded, ck, ckBits, -1, 0);
+}
+
+static int decompress_impl(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_t* out, int64_t cap, int64_t* outLen,
+                           int fromBlock, int toBlock)
+{
+    if (!ctx || !in || !out || !outLen || n < 20 || fromBlock < 1 || toBlock < fromBlock)
         return KNZ_ERR_INVALID_PARAM;
     std::lock_guard<std::recursive_mutex> lock_(ctx->mtx);
     cudaSetDevice(ctx->device);
@@ -1387,8 +1488,41 @@ extern "C" int knz_decompress(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_
     if (rc != KNZ_OK)
         return rc;
     CK(cudaMemsetAsync(ctx->dStream + (n & ~(i64)255), 0, (size_t)(round_up(n + 256, 256) - (n & ~(i64)255)), s));
-    CK(cudaMemcpyAsync(ctx->dStream, in, (size_t)n, cudaMemcpyHostToDevice, s));
+    // Block range (the `from` / `to` entries of the reference's context, io/CompressedInputStream.cpp:836-837,
+    // :864-869: ids are 1-based, blocks with from <= id < to are decoded): only the bytes that hold those blocks
+    // go to the device, found by walking the length prefixes first.
+    i64 upLo = 0, upHi = n;
+    if (fromBlock > 1 || toBlock != 0x7FFFFFFF) {
+        HostBitReader w = r;
+        u64 firstBit = ~0ull, lastBit = 0;
+        for (int id = 1; id < toBlock; id++) {
+            const int lr = 3 + (int)w.get(5);
+            const u64 bits = w.get(lr);
+            if (w.bad || bits == 0)
+                break;
+            if (id >= fromBlock) {
+                if (firstBit == ~0ull)
+                    firstBit = w.pos;
+                lastBit = w.pos + bits;
+            }
+            w.pos += bits;
+        }
+        if (firstBit == ~0ull) {
+            upLo = upHi = 0;
+        } else {
+            upLo = (i64)(firstBit >> 3) & ~(i64)255;
+            upHi = (i64)((lastBit + 7) >> 3);
+            if (upHi > n)
+                upHi = n;
+        }
+    }
+    if (upHi > upLo)
+        CK(cudaMemcpyAsync(ctx->dStream + upLo, in + upLo, (size_t)(upHi - upLo), cudaMemcpyHostToDevice, s));
     const int mb = ctx->maxBatch;
+    i64* evOff = (i64*)malloc(sizeof(i64) * (size_t)mb); // listener: bit position and byte size of each block
+    i64* evBytes = (i64*)malloc(sizeof(i64) * (size_t)mb);
+    int* evId = (int*)malloc(sizeof(int) * (size_t)mb);
+    int nextId = 1; // id of the next block of the stream
     u64* pay = (u64*)malloc(sizeof(u64) * (size_t)mb);
     u64* endb = (u64*)malloc(sizeof(u64) * (size_t)mb);
     int* pre = (int*)malloc(sizeof(int) * (size_t)mb);
@@ -1410,11 +1544,20 @@ extern "C" int knz_decompress(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_
                 rc = KNZ_ERR_INVALID_FILE;
                 break;
             }
-            if (bits == 0) {
+            if (bits == 0 || nextId >= toBlock) {
                 done = true;
                 break;
             }
             const u64 start = r.pos;
+            if (start + bits > r.nbits) {
+                rc = KNZ_ERR_INVALID_FILE;
+                break;
+            }
+            if (nextId < fromBlock) { // skipped: its bits are consumed, nothing is decoded (:864-866)
+                r.pos = start + bits;
+                nextId++;
+                continue;
+            }
             HostBitReader hb = { in, start + bits, start, false };
             u8 f = 0;
             int pl = 0;
@@ -1440,9 +1583,12 @@ extern "C" int knz_decompress(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_
                     rc = KNZ_ERR_CRC_CHECK;
                     break;
                 }
+                if (ctx->listener)
+                    emit_decode_events(ctx, nextId, (i64)start - (5 + lr), (i64)((bits + 7) >> 3), pl, pl, ck, ckBits, 0);
                 produced += pl;
                 batchOut = produced;
                 r.pos = start + bits;
+                nextId++;
                 continue;
             }
             pay[ng] = hb.pos;
@@ -1450,8 +1596,12 @@ extern "C" int knz_decompress(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_
             pre[ng] = pl;
             fl[ng] = f;
             cks[ng] = ck;
+            evOff[ng] = (i64)start - (5 + lr);
+            evBytes[ng] = (i64)((bits + 7) >> 3);
+            evId[ng] = nextId;
             ng++;
             r.pos = start + bits;
+            nextId++;
         }
         if (rc != KNZ_OK || ng == 0)
             continue;
@@ -1484,7 +1634,13 @@ extern "C" int knz_decompress(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_
         cudaStreamSynchronize(s);
         cudaStreamSynchronize(ctx->d2hStream);
         produced = batchOut;
+        if (rc == KNZ_OK && ctx->listener)
+            for (int g = 0; g < ng; g++)
+                emit_decode_events(ctx, evId[g], evOff[g], evBytes[g], pre[g], ol[g], cks[g], ckBits, fl[g]);
     }
+    free(evOff);
+    free(evBytes);
+    free(evId);
     free(cks);
     free(pay);
     free(endb);
@@ -1497,6 +1653,17 @@ extern "C" int knz_decompress(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_
     for (int i = 0; i < 8; i++)
         ctx->ms[i] = acc[i];
     return KNZ_OK;
+}
+
+extern "C" int knz_decompress(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_t* out, int64_t cap, int64_t* outLen)
+{
+    return decompress_impl(ctx, in, n, out, cap, outLen, 1, 0x7FFFFFFF);
+}
+
+extern "C" int knz_decompress_range(knz_ctx* ctx, const uint8_t* in, int64_t n, int fromBlock, int toBlock, uint8_t* out,
+                                    int64_t cap, int64_t* outLen)
+{
+    return decompress_impl(ctx, in, n, out, cap, outLen, fromBlock, toBlock);
 }
 
 // ------------------------------------------------------------------ stage-level API

@@ -73,6 +73,11 @@ struct knz_ctx {
     int checksumBits;  // 0, 32 or 64: block checksums written by the encoders of this context (knz_set_checksum)
     u64 *blockHash, *expectHash; // [maxBatch] device: hashes of a batch / values read from the block headers
     u64* h_hash;       // pinned mirror
+    int skipBlocks;    // knz_set_skip_blocks: store incompressible blocks as copy blocks
+    int *dSkip, *h_skip, *dLog2Tab; // [maxBatch] decisions of a batch (device, pinned mirror); log2 table
+    knz_event_fn listener; // knz_set_listener: per-block events re-emitted after each batch
+    void* listenerUser;
+    int evBlockBase;       // stream-level calls: id of the first block of the current batch minus one
     KnzDist* dist; // multi-process sharding state (dist.cu), NULL until knz_dist_init*
     u64 launches;
     float ms[8];

@@ -201,5 +201,11 @@ void workspace_free(Workspace& ws);
 void launch_xxhash(const BufTable& bt, const BlkState* st, int nBlocks, int bits, u64* hash, const u64* expect,
                    int* errFlag, cudaStream_t s, u64* launches);
 u64 knz_xxhash_host(const u8* data, int length, int bits);
+// skipBlocks (blockscan.cu): entropy / signature test of every block, and the copy-block framing that
+// overrides the private buffer of the flagged ones.  log2tab: 257 ints, round(4096 * log2(i)).
+void launch_skip_decide(const BufTable& bt, const BlkState* st, int nBlocks, const int* log2tab, int* skip,
+                        cudaStream_t s, u64* launches);
+void launch_copy_frame(const BufTable& bt, const BlkState* st0, int nBlocks, const int* skip, int ckBytes,
+                       const u64* blockHash, u8* out, i64 outStride, u64* blockBits, cudaStream_t s, u64* launches);
 void launch_copy_out(const BufTable& bt, const BlkState* st, int nBlocks, u8* out, i64 outStride, int outCap,
                      int* errFlag, cudaStream_t s, u64* launches);

@@ -20,6 +20,15 @@ T_IDS = {"NONE": 0, "BWT": 1, "LZ": 3, "ZRLT": 6, "MTFT": 7, "RANK": 8, "SRT": 1
 E_IDS = {"NONE": 0, "HUFFMAN": 1, "FPAQ": 2, "ANS0": 5, "ANS1": 8}
 
 
+class _Event(ctypes.Structure):
+    _fields_ = [("type", ctypes.c_int), ("blockId", ctypes.c_int), ("size", ctypes.c_int64), ("hash", ctypes.c_uint64),
+                ("hashBits", ctypes.c_int), ("offset", ctypes.c_int64), ("skipFlags", ctypes.c_uint8)]
+
+
+_EVENT_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.POINTER(_Event))
+EVENT_NAMES = {2: "BEFORE_TRANSFORM", 3: "AFTER_TRANSFORM", 4: "BEFORE_ENTROPY", 5: "AFTER_ENTROPY", 9: "BLOCK_INFO"}
+
+
 class KanziGpuError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"knz error {code}: {msg}")
@@ -53,6 +62,9 @@ def _load(path):
     vp, i32, i64, u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint64
     L.knz_compress.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p, i32, vp, i64, vp, i64, ctypes.POINTER(i64)]
     L.knz_decompress.argtypes = [vp, vp, i64, vp, i64, ctypes.POINTER(i64)]
+    L.knz_decompress_range.argtypes = [vp, vp, i64, i32, i32, vp, i64, ctypes.POINTER(i64)]
+    L.knz_set_skip_blocks.argtypes = [vp, i32]
+    L.knz_set_listener.argtypes = [vp, vp, vp]
     L.knz_encode_blocks.argtypes = [vp, u64, i32, i32, vp, i64, vp, i32, i32, vp, i64, vp, vp]
     L.knz_decode_blocks.argtypes = [vp, u64, i32, i32, vp, i64, vp, i32, vp, i64, vp]
     L.knz_encode_blocks_dev.argtypes = [vp, u64, i32, i32, vp, i64, vp, i32, i32, vp, i64, vp, vp]
@@ -115,6 +127,26 @@ class Context:
         """Block checksums written by the encoders of this context: 0, 32 (XXHash32) or 64 (XXHash64)."""
         self._check(self.lib.knz_set_checksum(self.h, int(bits)))
 
+    def set_skip_blocks(self, on):
+        """`skipBlocks` of the reference's context: incompressible blocks are stored as copy blocks."""
+        self._check(self.lib.knz_set_skip_blocks(self.h, 1 if on else 0))
+
+    def set_listener(self, fn):
+        """fn(dict) is called with every per-block event (type, blockId, size, hash, hashBits, offset,
+        skipFlags) after each device batch; None switches the events off."""
+        if fn is None:
+            self._listener = None
+            self._check(self.lib.knz_set_listener(self.h, None, None))
+            return
+
+        def tramp(_user, evt):
+            e = evt.contents
+            fn({"type": EVENT_NAMES.get(e.type, e.type), "blockId": e.blockId, "size": e.size, "hash": e.hash,
+                "hashBits": e.hashBits, "offset": e.offset, "skipFlags": e.skipFlags})
+
+        self._listener = _EVENT_FN(tramp)  # keep the trampoline alive
+        self._check(self.lib.knz_set_listener(self.h, ctypes.cast(self._listener, ctypes.c_void_p), None))
+
     def set_decode_groups(self, groups):
         """Block groups decoded concurrently (1 = serial stages with per-stage timings)."""
         self._check(self.lib.knz_set_decode_groups(self.h, int(groups)))
@@ -148,6 +180,16 @@ class Context:
             out = np.empty(max(cap, 1), dtype=np.uint8)
         n = ctypes.c_int64(0)
         self._check(self.lib.knz_decompress(self.h, _ptr(comp), comp.size, _ptr(out), cap, ctypes.byref(n)))
+        return out[: n.value]
+
+    def decompress_range(self, comp, from_block, to_block, cap, out=None):
+        """Blocks with from_block <= id < to_block (1-based ids), like the reference's `from` / `to`."""
+        comp = np.ascontiguousarray(comp, dtype=np.uint8)
+        if out is None:
+            out = np.empty(max(cap, 1), dtype=np.uint8)
+        n = ctypes.c_int64(0)
+        self._check(self.lib.knz_decompress_range(self.h, _ptr(comp), comp.size, int(from_block), int(to_block),
+                                                  _ptr(out), cap, ctypes.byref(n)))
         return out[: n.value]
 
     # ---- multi-GPU: one process per GPU, blocks sharded round-robin (see include/knz_gpu.h)

@@ -146,6 +146,35 @@ class Ref:
                                              ctypes.c_int64(cap), ctypes.byref(ol))
         return out[: ol.value], rc
 
+    EVT_FIELDS = ("type", "blockId", "size", "hash", "hashType", "offset", "skipFlags")
+
+    def stream_compress_ctx(self, data, tname, ename, block_size, jobs=1, checksum=0, skip_blocks=0, events=False):
+        """Through the reference's Context constructor (skipBlocks, listeners).  Returns (stream, events)."""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        out = np.empty(data.size + data.size // 2 + 65536, dtype=np.uint8)
+        ol = ctypes.c_int64(0)
+        ev_cap = 8 * (data.size // block_size + 2)
+        ev = np.zeros((ev_cap, 7), dtype=np.int64)
+        ec = ctypes.c_int(0)
+        rc = self.lib.kref_stream_compress_ctx(_ptr(data), ctypes.c_int64(data.size), tname.encode(), ename.encode(),
+                                               block_size, jobs, checksum, int(skip_blocks), _ptr(out),
+                                               ctypes.c_int64(out.size), ctypes.byref(ol),
+                                               _ptr(ev) if events else None, ev_cap, ctypes.byref(ec))
+        assert rc == 0, rc
+        return out[: ol.value].copy(), [dict(zip(self.EVT_FIELDS, (int(x) for x in row))) for row in ev[: ec.value]]
+
+    def stream_decompress_ctx(self, comp, cap, jobs=1, from_block=0, to_block=0, events=False):
+        comp = np.ascontiguousarray(comp, dtype=np.uint8)
+        out = np.empty(max(cap, 1), dtype=np.uint8)
+        ol = ctypes.c_int64(0)
+        ev_cap = 65536
+        ev = np.zeros((ev_cap, 7), dtype=np.int64)
+        ec = ctypes.c_int(0)
+        rc = self.lib.kref_stream_decompress_ctx(_ptr(comp), ctypes.c_int64(comp.size), jobs, from_block, to_block,
+                                                 _ptr(out), ctypes.c_int64(cap), ctypes.byref(ol),
+                                                 _ptr(ev) if events else None, ev_cap, ctypes.byref(ec))
+        return out[: ol.value], rc, [dict(zip(self.EVT_FIELDS, (int(x) for x in row))) for row in ev[: ec.value]]
+
     def sequence_forward(self, name, data, in_cap=None, out_cap=None):
         data = np.ascontiguousarray(data, dtype=np.uint8)
         n = data.size

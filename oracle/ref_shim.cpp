@@ -23,8 +23,19 @@
 #include <vector>
 #include <streambuf>
 #include <cstdio>
+#include <mutex>
+
+#include <chrono>
+#include <map>
+#include <iomanip>
 
 #include "types.hpp"
+#include "util/WallTimer.hpp"
+// Event::_skipFlags has no accessor (it only appears in Event::toString()); the shim reads the member
+// itself.  Access control does not change the layout of the unmodified class.
+#define private public
+#include "Event.hpp"
+#undef private
 #include "Context.hpp"
 #include "SliceArray.hpp"
 #include "io/CompressedOutputStream.hpp"
@@ -45,6 +56,13 @@ class FixedOut : public std::streambuf {
 public:
     FixedOut(char* p, size_t n) { setp(p, p + n); }
     size_t count() const { return size_t(pptr() - pbase()); }
+
+protected:
+    // tellp(): the reference reports bit offsets of blocks through OutputBitStream::tell()
+    pos_type seekoff(off_type off, std::ios_base::seekdir dir, std::ios_base::openmode) override
+    {
+        return (dir == std::ios_base::cur && off == 0) ? pos_type(pptr() - pbase()) : pos_type(off_type(-1));
+    }
 };
 
 class FixedIn : public std::streambuf {
@@ -53,6 +71,12 @@ public:
     {
         char* q = const_cast<char*>(p);
         setg(q, q, q + n);
+    }
+
+protected:
+    pos_type seekoff(off_type off, std::ios_base::seekdir dir, std::ios_base::openmode) override
+    {
+        return (dir == std::ios_base::cur && off == 0) ? pos_type(gptr() - eback()) : pos_type(off_type(-1));
     }
 };
 
@@ -113,6 +137,120 @@ int kref_stream_decompress(const uint8_t* in, int64_t n, int jobs, uint8_t* out,
 
         cis.close();
         *outLen = off;
+        return 0;
+    }
+    catch (const std::exception& e) {
+        fprintf(stderr, "[ref_shim] %s\n", e.what());
+        return -1;
+    }
+}
+
+// The same two calls through the Context constructors, which is how the reference's application sets
+// `skipBlocks`, `from` / `to` and attaches listeners (app/BlockCompressor.cpp, app/BlockDecompressor.cpp).
+// Every event a listener receives is recorded as seven int64: type, id, size, hash, hash type, offset; the
+// skip flags of BLOCK_INFO events are the seventh.
+struct RecListener : public Listener<Event> {
+    int64_t* buf;
+    int cap, n;
+    std::mutex m;
+    RecListener(int64_t* b, int c) : buf(b), cap(c), n(0) {}
+    void processEvent(const Event& e)
+    {
+        std::lock_guard<std::mutex> g(m);
+        if (buf == nullptr || n >= cap)
+            return;
+        int64_t* r = buf + 7 * n++;
+        r[0] = int64_t(e.getType());
+        r[1] = e.getId();
+        r[2] = e.getSize();
+        r[3] = int64_t(e.getHash());
+        r[4] = int64_t(e.getHashType());
+        r[5] = e.getOffset();
+        r[6] = 0;
+        if (e.getType() == Event::BLOCK_INFO)
+            r[6] = int64_t(e._skipFlags);
+    }
+};
+
+int kref_stream_compress_ctx(const uint8_t* in, int64_t n, const char* transform, const char* entropy, int blockSize,
+                             int jobs, int checksum, int skipBlocks, uint8_t* out, int64_t cap, int64_t* outLen,
+                             int64_t* events, int evCap, int* evCount)
+{
+    try {
+        FixedOut ob(reinterpret_cast<char*>(out), size_t(cap));
+        std::ostream os(&ob);
+        RecListener rec(events, evCap);
+        {
+            Context ctx;
+            ctx.putInt("jobs", jobs);
+            ctx.putInt("blockSize", blockSize);
+            ctx.putInt("checksum", checksum);
+            ctx.putInt("skipBlocks", skipBlocks);
+            ctx.putInt("verbosity", 5); // BLOCK_INFO events are only built above 4
+            ctx.putLong("fileSize", n);
+            ctx.putString("entropy", entropy);
+            ctx.putString("transform", transform);
+            CompressedOutputStream cos(os, ctx);
+            if (events != nullptr)
+                cos.addListener(rec);
+            int64_t off = 0;
+
+            while (off < n) {
+                const int64_t len = (n - off < (int64_t(1) << 24)) ? (n - off) : (int64_t(1) << 24);
+                cos.write(reinterpret_cast<const char*>(in + off), std::streamsize(len));
+                off += len;
+            }
+
+            cos.close();
+        }
+
+        if (os.fail())
+            return -2;
+
+        *outLen = int64_t(ob.count());
+        if (evCount)
+            *evCount = rec.n;
+        return 0;
+    }
+    catch (const std::exception& e) {
+        fprintf(stderr, "[ref_shim] %s\n", e.what());
+        return -1;
+    }
+}
+
+int kref_stream_decompress_ctx(const uint8_t* in, int64_t n, int jobs, int from, int to, uint8_t* out, int64_t cap,
+                               int64_t* outLen, int64_t* events, int evCap, int* evCount)
+{
+    try {
+        FixedIn ib(reinterpret_cast<const char*>(in), size_t(n));
+        std::istream is(&ib);
+        RecListener rec(events, evCap);
+        Context ctx;
+        ctx.putInt("jobs", jobs);
+        ctx.putInt("verbosity", 5);
+        if (from > 0)
+            ctx.putInt("from", from);
+        if (to > 0)
+            ctx.putInt("to", to);
+        CompressedInputStream cis(is, ctx);
+        if (events != nullptr)
+            cis.addListener(rec);
+        int64_t off = 0;
+
+        while (off < cap) {
+            const int64_t want = (cap - off < (int64_t(1) << 24)) ? (cap - off) : (int64_t(1) << 24);
+            cis.read(reinterpret_cast<char*>(out + off), std::streamsize(want));
+            const int64_t got = int64_t(cis.gcount());
+            off += got;
+
+            if (got < want)
+                break;
+        }
+
+        cis.close();
+        *outLen = off;
+        if (evCount)
+            *evCount = rec.n;
         return 0;
     }
     catch (const std::exception& e) {

@@ -7,6 +7,7 @@
 #include <math.h>
 
 #include "ctx.h"
+#include "pre.h"
 
 i64 knz_round_up(i64 v, i64 a) { return (v + a - 1) / a * a; }
 static i64 round_up(i64 v, i64 a) { return knz_round_up(v, a); }
@@ -40,6 +41,8 @@ static int stage_max_len(int t, int n)
 {
     if (is_lz(t))
         return ((n <= 1024) ? n + 16 : n + n / 64) + ((t == T_LZP) ? 0 : 2);
+    if (knz_is_host_stage(t))
+        return knz_pre_max_len(t, n);
     return (t == T_BWT) ? n + 33 : (t == T_SRT) ? n + 1024 : n;
 }
 
@@ -83,6 +86,14 @@ extern "C" uint64_t knz_transform_type(const char* name)
             t = T_LZX;
         else if (len == 3 && !strncmp(p, "LZP", 3))
             t = T_LZP;
+        else if (len == 4 && !strncmp(p, "PACK", 4)) // host stages (pre.cu): a prefix of the sequence
+            t = KNZ_T_PACK;
+        else if (len == 3 && !strncmp(p, "DNA", 3))
+            t = KNZ_T_DNA;
+        else if (len == 2 && !strncmp(p, "MM", 2))
+            t = KNZ_T_MM;
+        else if (len == 3 && !strncmp(p, "UTF", 3))
+            t = KNZ_T_UTF;
         if (t < 0 || ++n > 8)
             return (uint64_t)-1;
         if (t != T_NONE) {
@@ -1677,6 +1688,18 @@ static int run_single_stage(knz_ctx* ctx, int type, bool inverse, const u8* in, 
     *outLen = 0;
     if (n == 0) {
         *applied = 1;
+        return KNZ_OK;
+    }
+    if (knz_is_host_stage(type)) { // host stage (pre.cu): nothing for the device to do
+        if (cap < 0)
+            return KNZ_ERR_BLOCK_SIZE;
+        KnzPreCtx pc = { KDT_UNDEFINED, ctx->maxBlockSize, E_ANS0 };
+        int len = 0;
+        const bool ok = inverse ? knz_pre_inverse(type, in, n, out, cap, &len) : knz_pre_forward(type, in, n, out, cap, &len, &pc);
+        if (ok) {
+            *outLen = len;
+            *applied = 1;
+        }
         return KNZ_OK;
     }
     if (!type_supported(type))

@@ -1,0 +1,107 @@
+"""Host stages of the block pipeline: PACK / DNA (AliasCodec), MM (FSDCodec), UTF (UTFCodec),
+stage by stage and inside whole streams, byte for byte against the unmodified reference (oracle/_ref).
+CPU tests use the emulator build of the library (the host stages are the same code in both builds)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import synth
+from cases import rng_bytes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SIM = os.path.join(ROOT, "tests", "sim", "libknzsim.so")
+
+
+@pytest.fixture(scope="module")
+def sim():
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "sim"), "-j8"], stdout=subprocess.DEVNULL)
+    from kanzi_b200 import Context
+    ctx = Context(0, 1 << 18, 4, lib_path=SIM)
+    yield ctx
+    ctx.close()
+
+
+def utf8_text(n, seed, alphabets=("абвгдежзиклмнопрстуфхцчшщъыьэюя", "αβγδεζηθικλμνξοπρστυφχψω", "日本語中文字漢", "😀😁😂🤣")):
+    r = np.random.RandomState(seed)
+    words, size = [], 0
+    while size < n + 16:
+        a = alphabets[r.randint(0, len(alphabets))] if r.randint(0, 4) else "abcdefghij"
+        w = "".join(a[r.randint(0, len(a))] for _ in range(r.randint(2, 9)))
+        words.append(w)
+        size += len(w.encode()) + 1
+    b = (" ".join(words)).encode()
+    return np.frombuffer(b[:n], dtype=np.uint8).copy()
+
+
+def smooth16(n, seed):
+    r = np.random.RandomState(seed)
+    x = np.cumsum(r.randint(-40, 41, size=n // 2)).astype(np.int64) + 20000
+    return (x & 0xFFFF).astype("<u2").view(np.uint8).copy()
+
+
+def walk8(n, seed, step=4):
+    r = np.random.RandomState(seed)
+    out = np.zeros(n, dtype=np.uint8)
+    for c in range(step):
+        m = len(out[c::step])
+        out[c::step] = (np.cumsum(r.randint(-3, 4, size=m)) + 128 + 17 * c) & 0xFF
+    return out
+
+
+def dna(n, seed):
+    r = np.random.RandomState(seed)
+    return np.frombuffer(b"ACGT", dtype=np.uint8)[r.randint(0, 4, size=n)].copy()
+
+
+def stage_inputs():
+    c = {}
+    c["text_60000"] = synth.synth_text(60000, 3)
+    c["text_5000"] = synth.synth_text(5000, 4)
+    c["comp_200k"] = synth.synth_compressible(200000, 6)
+    c["rnd4_9001"] = rng_bytes(9001, 5, 4) + 65
+    c["rnd3_9002"] = rng_bytes(9002, 6, 3) + 48
+    c["rnd16_9003"] = rng_bytes(9003, 7, 16) * 3
+    c["rnd13_9000"] = rng_bytes(9000, 8, 13) + 100
+    c["const_4000"] = np.full(4000, 0x41, dtype=np.uint8)
+    c["two_sym_5001"] = rng_bytes(5001, 9, 2) * 255
+    c["rnd200_30000"] = rng_bytes(30000, 10, 200)
+    c["rnd256_30000"] = rng_bytes(30000, 11, 256)
+    c["dna_40000"] = dna(40000, 12)
+    c["dna_n_40001"] = np.where(rng_bytes(40001, 13, 50) == 0, ord("N"), dna(40001, 14)).astype(np.uint8)
+    c["digits_20000"] = np.frombuffer(b"0123456789,.", dtype=np.uint8)[rng_bytes(20000, 15, 12)].copy()
+    c["smooth16_100k"] = smooth16(100000, 16)
+    c["walk8_step1"] = walk8(50000, 17, 1)
+    c["walk8_step3"] = walk8(60000, 18, 3)
+    c["walk8_step4"] = walk8(64000, 19, 4)
+    c["walk8_step8"] = walk8(80000, 20, 8)
+    c["utf8_50000"] = utf8_text(50000, 21)
+    c["utf8_cyr_30000"] = utf8_text(30000, 22, ("абвгдежзиклмнопрстуфхцчшщъыьэюя",))
+    c["utf8_bom"] = np.concatenate([np.frombuffer(b"\xef\xbb\xbf", dtype=np.uint8), utf8_text(20000, 23)])
+    c["utf8_cut"] = utf8_text(40000, 24)[1:]  # may start in the middle of a sequence
+    c["short_1000"] = synth.synth_text(1000, 25)
+    bad = utf8_text(30000, 26)
+    bad[15000] = 0xC0
+    c["utf8_bad"] = bad
+    return c
+
+
+STAGES = ["PACK", "DNA", "MM", "UTF"]
+
+
+@pytest.mark.parametrize("tname", STAGES)
+def test_sim_pre_stage_vs_reference(sim, ref, tname):
+    applied_some = False
+    for name, data in stage_inputs().items():
+        n = data.size
+        cap = n + max(n // 16, 8192) + 1024  # >= getMaxEncodedLength of every stage, as EncodingTask sizes it
+        want, flags, _ = ref.sequence_forward(tname, data, cap, cap)
+        got, applied = sim.transform_forward(tname, data, cap)
+        assert applied == (flags != 0xFF), (tname, name, applied, flags)
+        if applied:
+            applied_some = True
+            assert got.size == want.size and np.array_equal(got, want), (tname, name)
+            back, ok = sim.transform_inverse(tname, want, n + 64)
+            assert ok and np.array_equal(back, data), (tname, name)
+    assert applied_some, tname

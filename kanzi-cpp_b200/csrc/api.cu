@@ -5,6 +5,9 @@
 // The reference's equivalents are CompressedOutputStream / EncodingTask and
 // CompressedInputStream / DecodingTask (io/Compressed{Output,Input}Stream.cpp).
 #include <math.h>
+#include <atomic>
+#include <thread>
+#include <vector>
 
 #include "ctx.h"
 #include "pre.h"
@@ -219,6 +222,9 @@ extern "C" int knz_create(int device, int maxBlockSize, int maxBatchBlocks, knz_
     A(dalloc(&ctx->dSkip, nb));
     A(dalloc(&ctx->dLog2Tab, 257));
     A(cudaMallocHost((void**)&ctx->h_skip, sizeof(int) * nb));
+    A(dalloc(&ctx->dDtype, nb));
+    A(cudaMallocHost((void**)&ctx->h_dtype, sizeof(int) * nb));
+    A(cudaMallocHost((void**)&ctx->h_init, sizeof(BlkState) * nb));
     if (ok) { // Global::LOG2_4096 (Global.cpp:47-74) is round(4096 * log2(i)); tests compare all 257 entries
         int tab[257];
         tab[0] = 0;
@@ -263,12 +269,12 @@ extern "C" void knz_destroy(knz_ctx* ctx)
                     ctx->hdrBits, ctx->payBytes, ctx->payOff, ctx->chunkOff, ctx->chunkPos, ctx->blockBits,
                     ctx->blockOff, ctx->streamPos, ctx->dInBits, ctx->dPayStart, ctx->dPreLen, ctx->errFlag,
                     ctx->dStream, ctx->dPlain, ctx->dPlain2, ctx->blockHash, ctx->expectHash, ctx->dSkip,
-                    ctx->dLog2Tab };
+                    ctx->dLog2Tab, ctx->dDtype };
     for (size_t i = 0; i < sizeof(dev) / sizeof(dev[0]); i++)
         if (dev[i])
             cudaFree(dev[i]);
     void* hst[] = { ctx->h_st, ctx->h_capEven, ctx->h_capOdd, ctx->h_err, ctx->h_preLen, ctx->h_bits,
-                    ctx->h_payStart, ctx->h_pos, ctx->h_hash, ctx->h_skip };
+                    ctx->h_payStart, ctx->h_pos, ctx->h_hash, ctx->h_skip, ctx->h_dtype, ctx->h_init, ctx->h_pre };
     for (size_t i = 0; i < sizeof(hst) / sizeof(hst[0]); i++)
         if (hst[i])
             cudaFreeHost(hst[i]);
@@ -483,19 +489,23 @@ int knz_encode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8
 {
     int types[8];
     const int nt = split_types(tType, types);
+    const int hs = ctx->nHost; // leading stages the caller has applied on the host already (pre.cu)
     for (int i = 0; i < nt; i++)
-        if (!type_supported(types[i])) {
-            snprintf(ctx->err, sizeof(ctx->err), "transform id %d not implemented", types[i]);
+        if (!(type_supported(types[i]) || (i < hs && knz_is_host_stage(types[i])))) {
+            snprintf(ctx->err, sizeof(ctx->err), "transform id %d not implemented%s", types[i],
+                     knz_is_host_stage(types[i]) ? " here (host stages: leading stages of knz_compress / knz_decompress only)" : "");
             return KNZ_ERR_INVALID_CODEC;
         }
     if (!entropy_supported(eType)) {
         snprintf(ctx->err, sizeof(ctx->err), "entropy id %d not implemented", eType);
         return KNZ_ERR_INVALID_CODEC;
     }
+    if (hs > 0 && ctx->skipBlocks)
+        return KNZ_ERR_INVALID_PARAM; // the entropy test belongs to the original block, which the device does not see
     {
         int rc1 = ensure_ans1(ctx, eType);
         if (rc1 == KNZ_OK)
-            rc1 = ensure_bwt(ctx, types, nt);
+            rc1 = ensure_bwt(ctx, types + hs, nt - hs);
         if (rc1 != KNZ_OK)
             return rc1;
     }
@@ -516,6 +526,12 @@ int knz_encode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8
         ctx->h_st[b].cur = 2;
         ctx->h_st[b].swaps = 0;
         ctx->h_st[b].flags = 0xFF;
+        if (hs > 0) { // length, ping-pong parity and skip flags as the host stages left them
+            ctx->h_st[b] = ctx->h_init[b];
+            ctx->h_st[b].cur = 2;
+            if (ctx->h_st[b].len < 1 || ctx->h_st[b].len > ctx->stageCap)
+                return KNZ_ERR_BLOCK_SIZE;
+        }
         ctx->h_capEven[b] = (reqFirst > req) ? reqFirst : req;
         ctx->h_capOdd[b] = (dataCap >= req) ? dataCap : req;
         // never beyond what a stage buffer slot holds (cannot bind for blockSize <= maxBlockSize)
@@ -523,10 +539,14 @@ int knz_encode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8
             ctx->h_capEven[b] = ctx->stageCap;
         if (ctx->h_capOdd[b] > ctx->stageCap)
             ctx->h_capOdd[b] = ctx->stageCap;
+        if (ctx->h_st[b].len > maxLen)
+            maxLen = ctx->h_st[b].len;
         if (lens[b] > maxLen)
             maxLen = lens[b];
     }
     CK(cudaMemcpyAsync(ctx->st, ctx->h_st, sizeof(BlkState) * nB, cudaMemcpyHostToDevice, s));
+    if (hs > 0)
+        CK(cudaMemcpyAsync(ctx->dDtype, ctx->h_dtype, sizeof(int) * nB, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->capEven, ctx->h_capEven, sizeof(int) * nB, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->capOdd, ctx->h_capOdd, sizeof(int) * nB, cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync(ctx->errFlag, 0, sizeof(int) * 4, s));
@@ -541,15 +561,18 @@ int knz_encode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8
     for (int i = 0; i < 8; i++)
         ctx->ms[i] = 0.f;
     CK(cudaEventRecord(ctx->ev[0], s));
-    if (ctx->checksumBits) // XXHash of every block before the transforms (io/CompressedOutputStream.cpp:674-682)
+    if (ctx->checksumBits && hs > 0) // hashed by the caller before the host stages ran (ctx->h_hash)
+        CK(cudaMemcpyAsync(ctx->blockHash, ctx->h_hash, sizeof(u64) * nB, cudaMemcpyHostToDevice, s));
+    else if (ctx->checksumBits) // XXHash of every block before the transforms (io/CompressedOutputStream.cpp:674-682)
         launch_xxhash(bt, ctx->st, nB, ctx->checksumBits, ctx->blockHash, NULL, ctx->errFlag, s, &ctx->launches);
     if (ctx->skipBlocks) // entropy / signature test (io/CompressedOutputStream.cpp:697-715)
         launch_skip_decide(bt, ctx->st, nB, ctx->dLog2Tab, ctx->dSkip, s, &ctx->launches);
-    for (int i = 0; i < nt; i++) {
+    for (int i = hs; i < nt; i++) {
         StageLaunch L;
         L.bt = bt;
-        L.stIn = ctx->st + (i64)i * ctx->maxBatch;
-        L.stOut = ctx->st + (i64)(i + 1) * ctx->maxBatch;
+        L.stIn = ctx->st + (i64)(i - hs) * ctx->maxBatch;
+        L.stOut = ctx->st + (i64)(i - hs + 1) * ctx->maxBatch;
+        L.dtype = (hs > 0) ? ctx->dDtype : NULL;
         L.stageIdx = i;
         L.nBlocks = nB;
         L.maxLen = maxLen + 33 * (i + 1);
@@ -561,7 +584,7 @@ int knz_encode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8
         launch_forward_stage(ctx, types[i], L, s);
         CK(cudaEventRecord(ctx->evStage[2 * i + 1], s));
     }
-    const BlkState* stFinal = ctx->st + (i64)nt * ctx->maxBatch;
+    const BlkState* stFinal = ctx->st + (i64)(nt - hs) * ctx->maxBatch;
     CK(cudaEventRecord(ctx->ev[3], s));
     EncodeLaunch E;
     E.bt = bt;
@@ -608,7 +631,7 @@ int knz_encode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8
         }
     }
     float ms = 0.f;
-    for (int i = 0; i < nt; i++) { // stage brackets were recorded without stalling the stream
+    for (int i = hs; i < nt; i++) { // stage brackets were recorded without stalling the stream
         cudaEventElapsedTime(&ms, ctx->evStage[2 * i], ctx->evStage[2 * i + 1]);
         add_stage_time(ctx, types[i], ms);
     }
@@ -845,6 +868,123 @@ int knz_grow(knz_ctx* ctx, u8** buf, i64* cap, i64 need)
     return KNZ_OK;
 }
 
+// ---- host stages in front of / behind the device stages (pre.cu) ------------------------------------
+// Leading host stages of a sequence; -1 when a host stage follows a device stage (not supported: the
+// reference's levels put them first).
+static int host_prefix_len(const int* types, int nt)
+{
+    int hs = 0;
+    while (hs < nt && knz_is_host_stage(types[hs]))
+        hs++;
+    for (int i = hs; i < nt; i++)
+        if (knz_is_host_stage(types[i]))
+            return -1;
+    return hs;
+}
+
+template <class F>
+static void host_parallel_for(int n, F&& body)
+{
+    int nt = (int)std::thread::hardware_concurrency();
+    nt = (nt < 1) ? 1 : (nt > 64 ? 64 : nt);
+    if (nt > n)
+        nt = n;
+    std::atomic<int> next(0);
+    auto run = [&]() {
+        for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1))
+            body(i);
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; t++)
+        pool.emplace_back(run);
+    run();
+    for (std::thread& t : pool)
+        t.join();
+}
+
+static int ensure_h_pre(knz_ctx* ctx)
+{
+    if (ctx->h_pre == NULL && cudaMallocHost((void**)&ctx->h_pre, (size_t)ctx->maxBatch * (size_t)ctx->bstride) != cudaSuccess) {
+        ctx->h_pre = NULL;
+        snprintf(ctx->err, sizeof(ctx->err), "cannot allocate the host staging buffer");
+        return KNZ_ERR_PROCESS_BLOCK;
+    }
+    return KNZ_OK;
+}
+
+// Forward: every block of a batch through the leading host stages, one block per task (what the reference's
+// worker threads do in TransformSequence::forward, transform/TransformSequence.hpp:88-162, for those stages).
+// Leaves the bytes in ctx->h_pre (bstride apart) and the state of every block in ctx->h_init / h_dtype / h_hash.
+static int host_prefix_forward(knz_ctx* ctx, const int* types, int hs, int eType, int blockSize, const u8* in,
+                               const int32_t* lens, int nb)
+{
+    if (ensure_h_pre(ctx) != KNZ_OK)
+        return KNZ_ERR_PROCESS_BLOCK;
+    const int cap = ctx->stageCap;
+    host_parallel_for(nb, [&](int b) {
+        std::vector<u8> tmp[2];
+        const u8* cur = in + (i64)b * blockSize;
+        int len = lens[b], swaps = 0, flags = 0xFF, w = 0;
+        // what EncodingTask leaves in the Context before the sequence runs (io/CompressedOutputStream.cpp:722-731)
+        KnzPreCtx pc = { knz_magic_data_type(cur, len), blockSize, eType };
+        if (ctx->checksumBits)
+            ctx->h_hash[b] = knz_xxhash_host(cur, len, ctx->checksumBits);
+        for (int i = 0; i < hs; i++) {
+            if (tmp[w].empty())
+                tmp[w].resize((size_t)cap + 64);
+            int ol = 0;
+            if (knz_pre_forward(types[i], cur, len, tmp[w].data(), cap, &ol, &pc)) {
+                cur = tmp[w].data();
+                w ^= 1;
+                len = ol;
+                swaps++;
+                flags &= ~(1 << (7 - i));
+            }
+        }
+        memcpy(ctx->h_pre + (i64)b * ctx->bstride, cur, (size_t)len);
+        ctx->h_init[b].len = len;
+        ctx->h_init[b].cur = 2;
+        ctx->h_init[b].swaps = swaps;
+        ctx->h_init[b].flags = flags;
+        ctx->h_dtype[b] = pc.dataType;
+    });
+    return KNZ_OK;
+}
+
+// Inverse: block b of a batch arrives from the device in ctx->h_pre (len[b] bytes) with the leading `hs` stages
+// still to undo, last one first (TransformSequence::inverse, transform/TransformSequence.hpp:165-247);
+// the result goes to out[b].  Returns false in ok[b] when a stage rejects its input.
+static void host_prefix_inverse(knz_ctx* ctx, const int* types, int hs, const u8* flags, const int* lens, int nb,
+                                u8* const* out, const int* outCap, int* outLen, u8* ok)
+{
+    const int cap = ctx->stageCap;
+    host_parallel_for(nb, [&](int b) {
+        std::vector<u8> tmp[2];
+        const u8* cur = ctx->h_pre + (i64)b * ctx->bstride;
+        int len = lens[b], w = 0;
+        ok[b] = 1;
+        for (int i = hs - 1; i >= 0 && ok[b]; i--) {
+            if (flags[b] & (1 << (7 - i)))
+                continue; // skipped by the encoder
+            if (tmp[w].empty())
+                tmp[w].resize((size_t)cap + 64);
+            int ol = 0;
+            if (!knz_pre_inverse(types[i], cur, len, tmp[w].data(), cap, &ol)) {
+                ok[b] = 0;
+                break;
+            }
+            cur = tmp[w].data();
+            w ^= 1;
+            len = ol;
+        }
+        if (ok[b] && len > outCap[b])
+            ok[b] = 0;
+        if (ok[b])
+            memcpy(out[b], cur, (size_t)len);
+        outLen[b] = len;
+    });
+}
+
 extern "C" int knz_compress(knz_ctx* ctx, const char* transform, const char* entropy, int blockSize,
                             const uint8_t* in, int64_t n, uint8_t* out, int64_t cap, int64_t* outLen)
 {
@@ -860,6 +1000,13 @@ extern "C" int knz_compress(knz_ctx* ctx, const char* transform, const char* ent
     }
     if (blockSize < 1024 || blockSize > ctx->maxBlockSize || (blockSize & 15))
         return KNZ_ERR_BLOCK_SIZE;
+    int types[8];
+    const int ntAll = split_types(tType, types);
+    const int hs = host_prefix_len(types, ntAll);
+    if (hs < 0 || (hs > 0 && ctx->skipBlocks)) {
+        snprintf(ctx->err, sizeof(ctx->err), "host stages (PACK, DNA, MM, UTF) must lead the sequence and do not combine with skipBlocks");
+        return KNZ_ERR_INVALID_CODEC;
+    }
     cudaSetDevice(ctx->device);
     cudaStream_t s = ctx->stream;
     u8 hdr[32];
@@ -910,7 +1057,7 @@ extern "C" int knz_compress(knz_ctx* ctx, const char* transform, const char* ent
         return e;
     };
     int nbCur = batchSize(0, nBlocks);
-    if (nBlocks > 0)
+    if (nBlocks > 0 && hs == 0)
         CK(issueCopy(0, nbCur, 0));
     int slot = 0;
     i64 sentBytes = 0; // bytes of the stream already on their way to the host
@@ -921,9 +1068,11 @@ extern "C" int knz_compress(knz_ctx* ctx, const char* transform, const char* ent
         // the other staging buffer is free: encode_batch of the previous sub-batch has completed
         if (bNext < nBlocks) {
             nbCur = batchSize((int)k + 1, nBlocks - bNext);
-            CK(issueCopy(bNext, nbCur, slot ^ 1));
+            if (hs == 0)
+                CK(issueCopy(bNext, nbCur, slot ^ 1));
         }
-        CK(cudaStreamWaitEvent(s, ctx->evCopy[slot], 0));
+        if (hs == 0)
+            CK(cudaStreamWaitEvent(s, ctx->evCopy[slot], 0));
         int32_t* lens = (int32_t*)malloc(sizeof(int32_t) * (size_t)nb);
         for (int i = 0; i < nb; i++) {
             const i64 rem = n - (off + (i64)i * blockSize);
@@ -932,7 +1081,22 @@ extern "C" int knz_compress(knz_ctx* ctx, const char* transform, const char* ent
         int ng = nb;
         if (lens[nb - 1] <= 15)
             ng = nb - 1; // only the last block of a stream can be that small
-        if (ng > 0) {
+        if (ng > 0 && hs > 0) {
+            // leading host stages on the host threads, then what they left goes to the device in one copy per block
+            rc = host_prefix_forward(ctx, types, hs, eType, blockSize, in + off, lens, ng);
+            for (int b = 0; b < ng && rc == KNZ_OK; b++)
+                if (cudaMemcpyAsync(ctx->dStageIn + (i64)b * ctx->bstride, ctx->h_pre + (i64)b * ctx->bstride,
+                                    (size_t)ctx->h_init[b].len, cudaMemcpyHostToDevice, s) != cudaSuccess)
+                    rc = KNZ_ERR_PROCESS_BLOCK;
+            if (rc == KNZ_OK) {
+                ctx->nHost = hs;
+                rc = knz_encode_batch(ctx, tType, eType, blockSize, ctx->dStageIn, ctx->bstride, lens, ng, firstLen, ctx->dOut,
+                                      ctx->outStride, ctx->blockBits, NULL);
+                ctx->nHost = 0;
+            }
+            for (int i = 0; i < 8; i++)
+                acc[i] += ctx->ms[i];
+        } else if (ng > 0) {
             rc = knz_encode_batch(ctx, tType, eType, blockSize, plain[slot], blockSize, lens, ng, firstLen, ctx->dOut,
                               ctx->outStride, ctx->blockBits, NULL);
             for (int i = 0; i < 8; i++)
@@ -1024,15 +1188,19 @@ int knz_decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8
 {
     int types[8];
     const int nt = split_types(tType, types);
+    const int hs = ctx->nHost; // leading stages the caller undoes on the host afterwards (pre.cu)
     for (int i = 0; i < nt; i++)
-        if (!type_supported(types[i]))
+        if (!(type_supported(types[i]) || (i < hs && knz_is_host_stage(types[i])))) {
+            snprintf(ctx->err, sizeof(ctx->err), "transform id %d not implemented%s", types[i],
+                     knz_is_host_stage(types[i]) ? " here (host stages: leading stages of knz_compress / knz_decompress only)" : "");
             return KNZ_ERR_INVALID_CODEC;
+        }
     if (!entropy_supported(eType))
         return KNZ_ERR_INVALID_CODEC;
     {
         int rc1 = ensure_ans1(ctx, eType);
         if (rc1 == KNZ_OK)
-            rc1 = ensure_bwt(ctx, types, nt);
+            rc1 = ensure_bwt(ctx, types + hs, nt - hs);
         if (rc1 != KNZ_OK)
             return rc1;
     }
@@ -1041,8 +1209,10 @@ int knz_decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8
     if (blockSize < 1 || blockSize > ctx->maxBlockSize)
         return KNZ_ERR_BLOCK_SIZE;
     cudaStream_t s = ctx->stream;
-    // a decoded block may not exceed its destination slot nor the stream's block size
-    const int outCap = (int)((outStride > 0 && outStride < blockSize) ? outStride : blockSize);
+    // a decoded block may not exceed its destination slot nor the stream's block size (what the host stages
+    // still have to undo may be as large as a stage buffer)
+    const int outCap = (hs > 0) ? (int)((outStride < ctx->stageCap) ? outStride : ctx->stageCap)
+                                : (int)((outStride > 0 && outStride < blockSize) ? outStride : blockSize);
     // capacity of the reference's task buffers on the decode side (io/CompressedInputStream.cpp:275)
     const int blkLen = blockSize + ((blockSize >> 4) > 512 ? (blockSize >> 4) : 512);
     int maxLen = 0;
@@ -1098,7 +1268,7 @@ int knz_decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8
     // its own stream over its own slice of the scratch arrays.  The inverse RANK/MTFT stage is one
     // dependency chain per block (one warp per block, ~140 ms for 4 MiB whatever the batch size):
     // while one group sits in it the SMs run the entropy / ZRLT / BWT stages of the other groups.
-    const int G = (ctx->decGroups > 1 && nB >= 4 * ctx->decGroups) ? ctx->decGroups : 1;
+    const int G = (hs == 0 && ctx->decGroups > 1 && nB >= 4 * ctx->decGroups) ? ctx->decGroups : 1;
     if (G > 1) {
         const bool sink = (h_sink != NULL) && (outStride == blockSize);
         CK(cudaEventRecord(ctx->gEv[KNZ_MAX_GROUPS], s));
@@ -1174,7 +1344,7 @@ int knz_decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8
     launch_entropy_decode(D, s, &ctx->launches);
     CK(cudaEventRecord(ctx->ev[1], s));
     int step = 0;
-    for (int i = nt - 1; i >= 0; i--, step++) {
+    for (int i = nt - 1; i >= hs; i--, step++) {
         StageLaunch L;
         L.bt = bt;
         L.stIn = ctx->st + (i64)step * ctx->maxBatch;
@@ -1219,7 +1389,7 @@ int knz_decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8
         launch_inverse_stage(ctx, types[i], L, s);
         CK(cudaEventRecord(ctx->evStage[2 * step + 1], s));
     }
-    const BlkState* stFinal = ctx->st + (i64)nt * ctx->maxBatch;
+    const BlkState* stFinal = ctx->st + (i64)(nt - hs) * ctx->maxBatch;
     if (ckBits && h_expectHash) { // DecodingTask::run verifies the hash of the decoded block (:1003-1022)
         memcpy(ctx->h_hash, h_expectHash, sizeof(u64) * (size_t)nB);
         CK(cudaMemcpyAsync(ctx->expectHash, ctx->h_hash, sizeof(u64) * nB, cudaMemcpyHostToDevice, s));
@@ -1233,7 +1403,7 @@ int knz_decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
     float ms = 0.f;
-    for (int k = 0; k < nt; k++) { // stage brackets were recorded without stalling the stream
+    for (int k = 0; k < nt - hs; k++) { // stage brackets were recorded without stalling the stream
         cudaEventElapsedTime(&ms, ctx->evStage[2 * k], ctx->evStage[2 * k + 1]);
         add_stage_time(ctx, types[nt - 1 - k], ms);
     }
@@ -1491,6 +1661,15 @@ static int decompress_impl(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_t* 
     const int eType = info.eType;
     const u64 tType = info.tType;
     const int blockSize = info.blockSize;
+    int types[8];
+    const int ntAll = split_types(tType, types);
+    const int hs = host_prefix_len(types, ntAll);
+    if (hs < 0) {
+        snprintf(ctx->err, sizeof(ctx->err), "host stages behind device stages are not supported");
+        return KNZ_ERR_INVALID_CODEC;
+    }
+    if (hs > 0 && ensure_h_pre(ctx) != KNZ_OK)
+        return KNZ_ERR_PROCESS_BLOCK;
     // whole compressed stream to the device; kernels read at bit offsets
     int rc = knz_grow(ctx, &ctx->dStream, &ctx->dStreamCap, round_up(n + 256, 256));
     if (rc != KNZ_OK)
@@ -1616,6 +1795,55 @@ static int decompress_impl(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_t* 
         }
         if (rc != KNZ_OK || ng == 0)
             continue;
+        if (hs > 0) {
+            // Device stages first (into stage-sized slots), then the leading host stages are undone on host threads
+            // (TransformSequence::inverse walks the sequence backwards, transform/TransformSequence.hpp:165-247).
+            ctx->nHost = hs;
+            rc = knz_decode_batch(ctx, tType, eType, blockSize, ctx->dStream, 0, pay, endb, pre, fl, ng, ctx->dStageIn,
+                                  ctx->bstride, ol, NULL, NULL, NULL, 0);
+            ctx->nHost = 0;
+            if (rc != KNZ_OK)
+                break;
+            for (int i = 0; i < 8; i++)
+                acc[i] += ctx->ms[i];
+            for (int g = 0; g < ng; g++)
+                cudaMemcpyAsync(ctx->h_pre + (i64)g * ctx->bstride, ctx->dStageIn + (i64)g * ctx->bstride, (size_t)ol[g],
+                                cudaMemcpyDeviceToHost, s);
+            CK(cudaStreamSynchronize(s));
+            std::vector<u8*> dstp((size_t)ng);
+            std::vector<int> dcap((size_t)ng), dlen((size_t)ng), ilen(ol, ol + ng);
+            std::vector<u8> good((size_t)ng);
+            for (int g = 0; g < ng; g++) { // every block but the last of a stream is full: decode in place
+                const i64 at = batchOut + (i64)g * blockSize;
+                dstp[g] = out + ((at < cap) ? at : cap);
+                const i64 room = cap - at;
+                dcap[g] = (int)((room < 0) ? 0 : (room < blockSize ? room : blockSize));
+            }
+            host_prefix_inverse(ctx, types, hs, fl, ilen.data(), ng, dstp.data(), dcap.data(), dlen.data(), good.data());
+            for (int g = 0; g < ng && rc == KNZ_OK; g++) {
+                if (!good[g]) {
+                    snprintf(ctx->err, sizeof(ctx->err), "transform inverse failed (host stage) in block %d", evId[g]);
+                    rc = (dlen[g] > dcap[g]) ? KNZ_ERR_OUTPUT_TOO_SMALL : KNZ_ERR_PROCESS_BLOCK;
+                    break;
+                }
+                if (dstp[g] != out + batchOut) // a short block in the middle of the batch: close the gap
+                    memmove(out + batchOut, dstp[g], (size_t)dlen[g]);
+                if (ckBits && knz_xxhash_host(out + batchOut, dlen[g], ckBits) != cks[g]) {
+                    snprintf(ctx->err, sizeof(ctx->err), "corrupted bitstream: block checksum mismatch");
+                    rc = KNZ_ERR_CRC_CHECK;
+                    break;
+                }
+                ol[g] = dlen[g];
+                batchOut += dlen[g];
+            }
+            if (rc != KNZ_OK)
+                break;
+            produced = batchOut;
+            if (ctx->listener)
+                for (int g = 0; g < ng; g++)
+                    emit_decode_events(ctx, evId[g], evOff[g], evBytes[g], pre[g], ol[g], cks[g], ckBits, fl[g]);
+            continue;
+        }
         // blocks the batch already sent to the host (full-size blocks, overlapped with the last stage)
         int sunk = 0;
         const bool roomy = batchOut + (i64)ng * blockSize <= cap;

@@ -78,6 +78,11 @@ struct knz_ctx {
     knz_event_fn listener; // knz_set_listener: per-block events re-emitted after each batch
     void* listenerUser;
     int evBlockBase;       // stream-level calls: id of the first block of the current batch minus one
+    // host stages in front of the device stages (pre.cu): set by the stream-level entry points around a batch
+    int nHost;             // leading stages of the sequence already applied on the host (0: none)
+    BlkState* h_init;      // [maxBatch] state of every block behind the host stages (length, swaps, skip flags)
+    int *h_dtype, *dDtype; // [maxBatch] Global::DataType of every block as the host stages left it
+    u8* h_pre;             // pinned staging of the blocks behind the host stages [maxBatch * bstride], on demand
     KnzDist* dist; // multi-process sharding state (dist.cu), NULL until knz_dist_init*
     u64 launches;
     float ms[8];

@@ -115,6 +115,7 @@ struct StageLaunch {
     int* errFlag;
     int wsBlock0;       // first workspace slot of this launch (block groups decoded concurrently on
                         // separate streams use disjoint slices of the per-block scratch arrays)
+    const int* dtype = nullptr; // per block Global::DataType left by the host stages (NULL: undefined); read by LZ / LZX
 };
 struct Workspace;
 void launch_none_forward(const StageLaunch& L, cudaStream_t s, u64* launches);

@@ -191,7 +191,10 @@ lzx_forward_kernel(StageLaunch L, LzWork W)
     const BlkState bs = L.stIn[b];
     const int count = bs.len;
     const int cap = (bs.swaps & 1) ? L.capOdd[b] : L.capEven[b];
-    if (count < 24 || cap < lz_max_len(count, false)) { // MIN_BLOCK_LENGTH, LZCodec.cpp:131-136
+    // data type left in the reference's Context by an earlier stage (LZCodec.cpp:181-191): DNA asks for a longer
+    // minimum match (6), a small alphabet makes the codec refuse
+    const int dt = L.dtype ? L.dtype[b] : 0;
+    if (count < 24 || cap < lz_max_len(count, false) || dt == 9 /* SMALL_ALPHABET */) { // MIN_BLOCK_LENGTH, LZCodec.cpp:131-136
         lz_finish_forward(L, b, bs, false, 0, lane);
         return;
     }
@@ -207,7 +210,7 @@ lzx_forward_kernel(StageLaunch L, LzWork W)
     const int mlTop = (int)W.sideStride - 8; // match-length byte k lives at tk[mlTop - k]
     const int srcEnd = count - 16 - 2;
     const int maxDist = (srcEnd < 4 * LZ_MAXD1) ? LZ_MAXD1 : LZ_MAXD2;
-    const int minMatch = 4;
+    const int minMatch = (dt == 6 /* DNA */) ? 6 : 4;
     if (lane == 0)
         dst[12] = (u8)(((maxDist == LZ_MAXD1) ? 0 : 1) | (((minMatch - 2) & 7) << 1));
     int srcIdx = 0, dstIdx = 13, anchor = 0, mIdx = 0, mLenIdx = 0, tkIdx = 0;

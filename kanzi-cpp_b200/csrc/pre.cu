@@ -73,29 +73,36 @@ const int* log2_table()
     return tab;
 }
 
-// Magic.hpp:69-106, reduced to the classes the host stages ask about
-enum { MG_NONE = 0, MG_BMP, MG_RIFF, MG_PNM, MG_OTHER };
+// Magic.hpp:69-166 (getType, isCompressed, isMultimedia, isExecutable) as one classification
+enum { MG_NONE = 0, MG_BMP, MG_RIFF, MG_PNM, MG_EXE, MG_COMPRESSED, MG_OTHER };
 int magic_class(const u8* p)
 {
     const u32 key = ((u32)p[0] << 24) | ((u32)p[1] << 16) | ((u32)p[2] << 8) | p[3];
-    if ((key & ~0x0Fu) == 0xFFD8FFE0u)
-        return MG_OTHER;
+    if ((key & ~0x0Fu) == 0xFFD8FFE0u) // JPG
+        return (key == 0xFFD8FFE0u) ? MG_COMPRESSED : MG_OTHER; // isCompressed compares the full key
     const u32 k24 = key >> 8;
-    if (k24 == 0x425A68u || k24 == 0x494433u)
-        return MG_OTHER;
-    static const u32 k32[] = { 0x47494638u, 0x25504446u, 0x504B0304u, 0x377ABCAFu, 0x89504E47u, 0x7F454C46u,
-                               0xFEEDFACEu, 0xCEFAEDFEu, 0xFEEDFACFu, 0xCFFAEDFEu, 0x28B52FFDu, 0x81CFB2CEu,
-                               0x4D534346u, 0x664C6143u, 0xFD377A58u, 0x4B414E5Au, 0x52617221u };
-    if (key == 0x52494646u)
+    if (k24 == 0x425A68u || k24 == 0x494433u) // BZIP2, MP3 / ID3
+        return MG_COMPRESSED;
+    switch (key) {
+    case 0x47494638u: case 0x504B0304u: case 0x377ABCAFu: case 0x89504E47u: case 0x28B52FFDu: case 0x81CFB2CEu:
+    case 0x4D534346u: case 0x664C6143u: case 0xFD377A58u: case 0x4B414E5Au: case 0x52617221u:
+        return MG_COMPRESSED; // GIF ZIP 7z PNG ZSTD BROTLI CAB FLAC XZ KNZ RAR
+    case 0x7F454C46u: case 0xFEEDFACEu: case 0xCEFAEDFEu: case 0xFEEDFACFu: case 0xCFFAEDFEu:
+        return MG_EXE; // ELF, Mach-O
+    case 0x25504446u:
+        return MG_OTHER; // PDF: known, in no class
+    case 0x52494646u:
         return MG_RIFF;
-    for (u32 k : k32)
-        if (key == k)
-            return MG_OTHER;
+    default:
+        break;
+    }
     const u32 k16 = key >> 16;
+    if (k16 == 0x1F8Bu)
+        return MG_COMPRESSED; // GZIP
     if (k16 == 0x424Du)
         return MG_BMP;
-    if (k16 == 0x1F8Bu || k16 == 0x4D5Au)
-        return MG_OTHER;
+    if (k16 == 0x4D5Au)
+        return MG_EXE; // MZ
     if (k16 == 0x5034u || k16 == 0x5035u || k16 == 0x5036u) {
         const u32 sub = (key >> 8) & 0xFF;
         if (sub == 0x07 || sub == 0x0A || sub == 0x0D || sub == 0x20)
@@ -307,8 +314,11 @@ bool fsd_forward(const u8* src, int n, u8* dst, int cap, int* outLen, KnzPreCtx*
         return false;
     if (pc->dataType != KDT_UNDEFINED && pc->dataType != KDT_MULTIMEDIA && pc->dataType != KDT_BIN)
         return false;
-    if (magic_class(src) == MG_OTHER) // detection only runs on image / audio containers and on unknown data
-        return false;
+    {
+        const int mg = magic_class(src); // detection only runs on image / audio containers and on unknown data
+        if (mg != MG_NONE && mg != MG_BMP && mg != MG_RIFF && mg != MG_PNM)
+            return false;
+    }
     const int* tab = log2_table();
     const int tenth = n / 10, fifth = 2 * tenth;
     static const int steps[7] = { 0, 1, 2, 3, 4, 8, 16 };
@@ -670,6 +680,25 @@ int knz_detect_simple_type(int n, const u32 f[256])
     if (distinct == 256)
         return KDT_BIN;
     return (distinct <= 4) ? KDT_SMALL_ALPHABET : KDT_UNDEFINED;
+}
+
+// What EncodingTask puts into the Context before the transforms run (io/CompressedOutputStream.cpp:722-731)
+int knz_magic_data_type(const u8* block, int n)
+{
+    if (n < 4)
+        return KDT_UNDEFINED;
+    switch (magic_class(block)) {
+    case MG_COMPRESSED:
+        return KDT_BIN;
+    case MG_BMP:
+    case MG_RIFF:
+    case MG_PNM:
+        return KDT_MULTIMEDIA;
+    case MG_EXE:
+        return KDT_EXE;
+    default:
+        return KDT_UNDEFINED;
+    }
 }
 
 bool knz_is_host_stage(int type)

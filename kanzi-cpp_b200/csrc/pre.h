@@ -29,3 +29,4 @@ bool knz_pre_inverse(int type, const u8* src, int n, u8* dst, int cap, int* outL
 int knz_detect_simple_type(int n, const u32 f[256]);
 bool knz_utf8_plausible(const u32 f0[256], const u32* f1, int n);
 void knz_log2_table(int tab[257]);
+int knz_magic_data_type(const u8* block, int n);

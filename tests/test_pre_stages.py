@@ -105,3 +105,58 @@ def test_sim_pre_stage_vs_reference(sim, ref, tname):
             back, ok = sim.transform_inverse(tname, want, n + 64)
             assert ok and np.array_equal(back, data), (tname, name)
     assert applied_some, tname
+
+
+def mixed_stream(bs, seed=31):
+    """One block of each kind the host stages tell apart, and a short tail."""
+    parts = [synth.synth_text(bs, seed), utf8_text(bs, seed + 1), smooth16(bs, seed + 2), dna(bs, seed + 3),
+             rng_bytes(bs, seed + 4), (rng_bytes(bs, seed + 5, 3) + 48).astype(np.uint8), walk8(bs, seed + 6, 3),
+             synth.synth_compressible(bs, seed + 7), np.full(bs, 7, dtype=np.uint8), utf8_text(bs // 3 + 11, seed + 8)]
+    parts[4][:4] = np.frombuffer(b"RIFF", dtype=np.uint8)  # a container signature sets the data type up front
+    return np.concatenate(parts)
+
+
+PIPELINES = [("PACK+LZX", "HUFFMAN", 0), ("DNA+LZ", "HUFFMAN", 0), ("MM+LZ", "ANS0", 32),
+             ("UTF+PACK+MM+LZX", "HUFFMAN", 0), ("UTF+BWT+RANK+ZRLT", "ANS0", 64), ("PACK+MM", "NONE", 0),
+             ("MM", "ANS1", 0)]
+
+
+def check_streams(ctx, ref, bs, pipelines):
+    data = mixed_stream(bs)
+    for tname, ename, ck in pipelines:
+        ctx.set_checksum(ck)
+        got = ctx.compress(data, tname, ename, bs)
+        ctx.set_checksum(0)
+        want = ref.stream_compress(data, tname, ename, bs, 1, ck)
+        assert got.size == want.size and np.array_equal(got, want), (tname, ename, ck)
+        back = ctx.decompress(got, data.size)
+        assert back.size == data.size and np.array_equal(back, data), (tname, ename, ck)
+        r, rc = ref.stream_decompress(got, data.size)
+        assert rc == 0 and np.array_equal(r, data), ("reference decoder", tname, ename)
+
+
+def test_sim_pre_streams_vs_reference(sim, ref):
+    check_streams(sim, ref, 1 << 16, PIPELINES)
+
+
+def test_sim_pre_stage_misplaced(sim):
+    """A host stage behind a device stage is refused (the reference's levels put them first)."""
+    from kanzi_b200 import KanziGpuError
+    with pytest.raises(KanziGpuError):
+        sim.compress(synth.synth_text(100000, 1), "LZX+PACK", "HUFFMAN", 1 << 16)
+
+
+@pytest.mark.gpu
+def test_gpu_pre_streams_vs_reference():
+    import torch
+    assert torch.cuda.is_available()
+    from kanzi_b200 import Context
+    from oracle.oracle import Ref
+    r = Ref.load()
+    if r is None:
+        pytest.skip("oracle/_ref/libkanzi_ref.so not present")
+    ctx = Context(0, 1 << 20, 16)
+    try:
+        check_streams(ctx, r, 1 << 20, PIPELINES)
+    finally:
+        ctx.close()

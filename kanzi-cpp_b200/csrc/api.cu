@@ -97,6 +97,8 @@ extern "C" uint64_t knz_transform_type(const char* name)
             t = KNZ_T_MM;
         else if (len == 3 && !strncmp(p, "UTF", 3))
             t = KNZ_T_UTF;
+        else if (len == 4 && !strncmp(p, "TEXT", 4))
+            t = KNZ_T_TEXT;
         if (t < 0 || ++n > 8)
             return (uint64_t)-1;
         if (t != T_NONE) {
@@ -954,10 +956,11 @@ static int host_prefix_forward(knz_ctx* ctx, const int* types, int hs, int eType
 // Inverse: block b of a batch arrives from the device in ctx->h_pre (len[b] bytes) with the leading `hs` stages
 // still to undo, last one first (TransformSequence::inverse, transform/TransformSequence.hpp:165-247);
 // the result goes to out[b].  Returns false in ok[b] when a stage rejects its input.
-static void host_prefix_inverse(knz_ctx* ctx, const int* types, int hs, const u8* flags, const int* lens, int nb,
-                                u8* const* out, const int* outCap, int* outLen, u8* ok)
+static void host_prefix_inverse(knz_ctx* ctx, const int* types, int hs, int eType, int blockSize, const u8* flags,
+                                const int* lens, int nb, u8* const* out, const int* outCap, int* outLen, u8* ok)
 {
     const int cap = ctx->stageCap;
+    const KnzPreCtx pc = { KDT_UNDEFINED, blockSize, eType };
     host_parallel_for(nb, [&](int b) {
         std::vector<u8> tmp[2];
         const u8* cur = ctx->h_pre + (i64)b * ctx->bstride;
@@ -969,7 +972,7 @@ static void host_prefix_inverse(knz_ctx* ctx, const int* types, int hs, const u8
             if (tmp[w].empty())
                 tmp[w].resize((size_t)cap + 64);
             int ol = 0;
-            if (!knz_pre_inverse(types[i], cur, len, tmp[w].data(), cap, &ol)) {
+            if (!knz_pre_inverse(types[i], cur, len, tmp[w].data(), cap, &ol, &pc)) {
                 ok[b] = 0;
                 break;
             }
@@ -1819,7 +1822,8 @@ static int decompress_impl(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_t* 
                 const i64 room = cap - at;
                 dcap[g] = (int)((room < 0) ? 0 : (room < blockSize ? room : blockSize));
             }
-            host_prefix_inverse(ctx, types, hs, fl, ilen.data(), ng, dstp.data(), dcap.data(), dlen.data(), good.data());
+            host_prefix_inverse(ctx, types, hs, eType, blockSize, fl, ilen.data(), ng, dstp.data(), dcap.data(), dlen.data(),
+                                good.data());
             for (int g = 0; g < ng && rc == KNZ_OK; g++) {
                 if (!good[g]) {
                     snprintf(ctx->err, sizeof(ctx->err), "transform inverse failed (host stage) in block %d", evId[g]);
@@ -1921,9 +1925,11 @@ static int run_single_stage(knz_ctx* ctx, int type, bool inverse, const u8* in, 
     if (knz_is_host_stage(type)) { // host stage (pre.cu): nothing for the device to do
         if (cap < 0)
             return KNZ_ERR_BLOCK_SIZE;
-        KnzPreCtx pc = { KDT_UNDEFINED, ctx->maxBlockSize, E_ANS0 };
+        // a stage on its own sees an empty Context: no data type, no "blockSize"; the text codec variant is the
+        // one of an ANS0 stream (what the reference-side shim of the tests sets)
+        KnzPreCtx pc = { KDT_UNDEFINED, 0, E_ANS0 };
         int len = 0;
-        const bool ok = inverse ? knz_pre_inverse(type, in, n, out, cap, &len) : knz_pre_forward(type, in, n, out, cap, &len, &pc);
+        const bool ok = inverse ? knz_pre_inverse(type, in, n, out, cap, &len, &pc) : knz_pre_forward(type, in, n, out, cap, &len, &pc);
         if (ok) {
             *outLen = len;
             *applied = 1;

@@ -7,6 +7,7 @@
 //   PACK / DNA   AliasCodec   transform/AliasCodec.cpp:37-229 (forward), :232-425 (inverse)
 //   MM           FSDCodec     transform/FSDCodec.cpp:103-277 (forward), :279-386 (inverse)
 //   UTF          UTFCodec     transform/UTFCodec.cpp:49-226 (forward), :228-326 (inverse), validate :331-422
+//   TEXT         TextCodec    pretext.cu
 //
 // Byte-exact with the reference (tests/test_pre_stages.py pins every stage and whole streams against
 // oracle/_ref).  This file holds host code only; it is compiled with the rest of the library.
@@ -701,9 +702,11 @@ int knz_magic_data_type(const u8* block, int n)
     }
 }
 
+bool knz_magic_known(const u8* block) { return magic_class(block) != MG_NONE; }
+
 bool knz_is_host_stage(int type)
 {
-    return type == KNZ_T_PACK || type == KNZ_T_DNA || type == KNZ_T_MM || type == KNZ_T_UTF;
+    return type == KNZ_T_TEXT || type == KNZ_T_PACK || type == KNZ_T_DNA || type == KNZ_T_MM || type == KNZ_T_UTF;
 }
 
 int knz_pre_max_len(int type, int n)
@@ -736,12 +739,14 @@ bool knz_pre_forward(int type, const u8* src, int n, u8* dst, int cap, int* outL
         return fsd_forward(src, n, dst, cap, outLen, pc);
     case KNZ_T_UTF:
         return utf_forward(src, n, dst, cap, outLen, pc);
+    case KNZ_T_TEXT:
+        return knz_text_forward(src, n, dst, cap, outLen, pc);
     default:
         return false;
     }
 }
 
-bool knz_pre_inverse(int type, const u8* src, int n, u8* dst, int cap, int* outLen)
+bool knz_pre_inverse(int type, const u8* src, int n, u8* dst, int cap, int* outLen, const KnzPreCtx* pc)
 {
     if (n == 0) {
         *outLen = 0;
@@ -755,6 +760,8 @@ bool knz_pre_inverse(int type, const u8* src, int n, u8* dst, int cap, int* outL
         return fsd_inverse(src, n, dst, cap, outLen);
     case KNZ_T_UTF:
         return utf_inverse(src, n, dst, cap, outLen);
+    case KNZ_T_TEXT:
+        return knz_text_inverse(src, n, dst, cap, outLen, pc->blockSize, pc->eType);
     default:
         return false;
     }

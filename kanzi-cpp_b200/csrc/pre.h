@@ -25,8 +25,18 @@ bool knz_is_host_stage(int type);
 int knz_pre_max_len(int type, int n); // Transform::getMaxEncodedLength
 // Transform<byte>::forward / inverse of one stage: true = applied (*outLen bytes in dst), false = refused
 bool knz_pre_forward(int type, const u8* src, int n, u8* dst, int cap, int* outLen, KnzPreCtx* pc);
-bool knz_pre_inverse(int type, const u8* src, int n, u8* dst, int cap, int* outLen);
+bool knz_pre_inverse(int type, const u8* src, int n, u8* dst, int cap, int* outLen, const KnzPreCtx* pc);
 int knz_detect_simple_type(int n, const u32 f[256]);
 bool knz_utf8_plausible(const u32 f0[256], const u32* f1, int n);
 void knz_log2_table(int tab[257]);
 int knz_magic_data_type(const u8* block, int n);
+bool knz_magic_known(const u8* block); // Magic::getType(block) != NO_MAGIC (4 readable bytes)
+// pretext.cu
+bool knz_text_forward(const u8* src, int n, u8* dst, int cap, int* outLen, KnzPreCtx* pc);
+bool knz_text_inverse(const u8* src, int n, u8* dst, int cap, int* outLen, int blockSize, int eType);
+// entropy ids as the stages need them
+#ifndef E_RAW
+#define E_RAW 0
+#define E_HUF 1
+#define E_ANS0 5
+#endif

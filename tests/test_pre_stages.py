@@ -18,7 +18,7 @@ SIM = os.path.join(ROOT, "tests", "sim", "libknzsim.so")
 def sim():
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "sim"), "-j8"], stdout=subprocess.DEVNULL)
     from kanzi_b200 import Context
-    ctx = Context(0, 1 << 18, 4, lib_path=SIM)
+    ctx = Context(0, 1 << 20, 4, lib_path=SIM)
     yield ctx
     ctx.close()
 
@@ -87,13 +87,75 @@ def stage_inputs():
     return c
 
 
-STAGES = ["PACK", "DNA", "MM", "UTF"]
+def english(n, seed, crlf=False, xml=False, odd=False):
+    """Prose with capitalised sentence starts, static-dictionary words, repeated invented words, numbers;
+    optionally CR+LF line ends, mark-up, and the bytes the text codec has to escape (0x0E, 0x0F, >= 0x80)."""
+    r = np.random.RandomState(seed)
+    common = ("the be and of in to with it that for you he have on said say at but we by had they as would who or can "
+              "may do this was is much any from not she what their which people because through different between "
+              "information everything government development organization").split()
+    made = ["".join(chr(97 + r.randint(0, 26)) for _ in range(r.randint(3, 12))) for _ in range(400)]
+    out, size, start = [], 0, True
+    while size < n + 64:
+        k = r.randint(0, 10)
+        w = common[r.randint(0, len(common))] if k < 6 else made[int(r.randint(0, 400) ** 2 / 400)]
+        if k == 9:
+            w = str(r.randint(0, 100000))
+        if start:
+            w = w.capitalize()
+        if xml and r.randint(0, 12) == 0:
+            w = "<%s>%s&amp;</%s>" % (w, w, w)
+        if odd and r.randint(0, 40) == 0:
+            w += ["\x0f", "\x0e", "é", "ü\x0f"][r.randint(0, 4)]
+        sep = " "
+        start = False
+        if r.randint(0, 12) == 0:
+            sep = ". "
+            start = True
+        if r.randint(0, 30) == 0:
+            sep = ("\r\n" if crlf else "\n")
+        out.append(w + sep)
+        size += len(w) + len(sep)
+    b = "".join(out).encode("latin-1", "replace")
+    return np.frombuffer(b[:n], dtype=np.uint8).copy()
+
+
+def text_inputs():
+    c = {}
+    c["english_80000"] = english(80000, 41)
+    c["english_crlf"] = english(50000, 42, crlf=True)
+    c["english_xml"] = english(60000, 43, xml=True)
+    c["english_odd"] = english(70000, 44, odd=True)
+    c["english_all"] = english(120000, 45, crlf=True, xml=True, odd=True)
+    c["spaces_first"] = np.concatenate([np.full(37, 32, dtype=np.uint8), english(30000, 46)])
+    c["upper"] = np.frombuffer(bytes(english(40000, 47)).upper(), dtype=np.uint8).copy()
+    c["grow"] = distinct_words(60000, 48)    # more distinct words than the initial list holds: it doubles
+    c["wrap"] = distinct_words(700000, 49)   # more than 2^19: the oldest learnt words are replaced
+    return c
+
+
+def distinct_words(count, seed):
+    r = np.random.RandomState(seed)
+    letters = r.randint(0, 26, size=(count, 9)).astype(np.uint8) + 97
+    letters[:, 8] = 32
+    idx = np.arange(count)
+    for k in range(4):  # four letters spell the word's number: all distinct
+        letters[:, k] = 97 + (idx // (26 ** k)) % 26
+    flat = letters.reshape(-1).copy()
+    # repeat a slice so that learnt words are referenced again, old and recent ones
+    return np.concatenate([flat, flat[: 9 * 5000], flat[-9 * 5000:]])
+
+
+STAGES = ["PACK", "DNA", "MM", "UTF", "TEXT"]
 
 
 @pytest.mark.parametrize("tname", STAGES)
 def test_sim_pre_stage_vs_reference(sim, ref, tname):
     applied_some = False
-    for name, data in stage_inputs().items():
+    inputs = stage_inputs()
+    if tname == "TEXT":
+        inputs.update(text_inputs())
+    for name, data in inputs.items():
         n = data.size
         cap = n + max(n // 16, 8192) + 1024  # >= getMaxEncodedLength of every stage, as EncodingTask sizes it
         want, flags, _ = ref.sequence_forward(tname, data, cap, cap)
@@ -111,12 +173,17 @@ def mixed_stream(bs, seed=31):
     """One block of each kind the host stages tell apart, and a short tail."""
     parts = [synth.synth_text(bs, seed), utf8_text(bs, seed + 1), smooth16(bs, seed + 2), dna(bs, seed + 3),
              rng_bytes(bs, seed + 4), (rng_bytes(bs, seed + 5, 3) + 48).astype(np.uint8), walk8(bs, seed + 6, 3),
-             synth.synth_compressible(bs, seed + 7), np.full(bs, 7, dtype=np.uint8), utf8_text(bs // 3 + 11, seed + 8)]
+             synth.synth_compressible(bs, seed + 7), np.full(bs, 7, dtype=np.uint8), english(bs, seed + 9),
+             english(bs, seed + 10, crlf=True, xml=True, odd=True), utf8_text(bs // 3 + 11, seed + 8)]
     parts[4][:4] = np.frombuffer(b"RIFF", dtype=np.uint8)  # a container signature sets the data type up front
     return np.concatenate(parts)
 
 
-PIPELINES = [("PACK+LZX", "HUFFMAN", 0), ("DNA+LZ", "HUFFMAN", 0), ("MM+LZ", "ANS0", 32),
+PIPELINES = [("TEXT+UTF+PACK+MM+LZX", "HUFFMAN", 0),      # -l 3
+             ("TEXT+UTF+BWT+RANK+ZRLT", "ANS0", 32),      # -l 5
+             ("TEXT+UTF+BWT+SRT+ZRLT", "FPAQ", 0),        # -l 6 (text codec variant 1)
+             ("TEXT", "ANS1", 64), ("TEXT+LZ", "NONE", 0),
+             ("PACK+LZX", "HUFFMAN", 0), ("DNA+LZ", "HUFFMAN", 0), ("MM+LZ", "ANS0", 32),
              ("UTF+PACK+MM+LZX", "HUFFMAN", 0), ("UTF+BWT+RANK+ZRLT", "ANS0", 64), ("PACK+MM", "NONE", 0),
              ("MM", "ANS1", 0)]
 

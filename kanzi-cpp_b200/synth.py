@@ -9,6 +9,8 @@ SHA-256 of each generated buffer is recorded next to the results.
                                 walk in [64 KiB, 1 MiB) segments + a 4 KiB copy from
                                 ~1 MiB earlier every 64 KiB (configs 2, 4, 5)
   synth_incompressible(n, seed) uniform random bytes (skipped-stage edge cases)
+  synth_silesia(n, seed)        45 % text / mark-up, 25 % executable-like, 12 % records, 18 % smooth
+                                16-bit samples in [256 KiB, 2 MiB) segments (config 3, the `-l N` levels)
 """
 import ctypes
 import hashlib
@@ -50,6 +52,10 @@ def synth_incompressible(n, seed=9):
     return _gen("knz_synth_incompressible", n, seed)
 
 
+def synth_silesia(n, seed=3):
+    return _gen("knz_synth_silesia", n, seed)
+
+
 def sha256(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
@@ -58,4 +64,5 @@ GENERATORS = {
     "text": synth_text,
     "compressible": synth_compressible,
     "incompressible": synth_incompressible,
+    "silesia": synth_silesia,
 }

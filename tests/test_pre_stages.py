@@ -227,3 +227,29 @@ def test_gpu_pre_streams_vs_reference():
         check_streams(ctx, r, 1 << 20, PIPELINES)
     finally:
         ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_config3_levels_vs_reference():
+    """BASELINE config 3 (`-l 3` = TEXT+UTF+PACK+MM+LZX / HUFFMAN, 4 MiB blocks, silesia-shaped input) and the
+    level built on the headline pipeline (`-l 5` = TEXT+UTF+BWT+RANK+ZRLT / ANS0): streams identical to the
+    reference's, round trip through both decoders."""
+    import torch
+    assert torch.cuda.is_available()
+    from kanzi_b200 import Context
+    from oracle.oracle import Ref
+    r = Ref.load()
+    if r is None:
+        pytest.skip("oracle/_ref/libkanzi_ref.so not present")
+    bs = 4 << 20
+    data = synth.synth_silesia(48 * (1 << 20) + 12345, 3)
+    ctx = Context(0, bs, 16)
+    try:
+        for tname, ename in [("TEXT+UTF+PACK+MM+LZX", "HUFFMAN"), ("TEXT+UTF+BWT+RANK+ZRLT", "ANS0"), ("DNA+LZ", "HUFFMAN")]:
+            got = ctx.compress(data, tname, ename, bs)
+            want = r.stream_compress(data, tname, ename, bs, 1, 0)
+            assert got.size == want.size and np.array_equal(got, want), (tname, ename)
+            back = ctx.decompress(got, data.size)
+            assert np.array_equal(back, data), (tname, ename)
+    finally:
+        ctx.close()

@@ -203,7 +203,9 @@ def check_streams(ctx, ref, bs, pipelines):
 
 
 def test_sim_pre_streams_vs_reference(sim, ref):
-    check_streams(sim, ref, 1 << 16, PIPELINES)
+    # the emulator runs the device stages of every block on the CPU: the levels and one pipeline per host stage
+    # (the GPU test runs the whole list at 1 MiB blocks)
+    check_streams(sim, ref, 1 << 16, PIPELINES[:4] + [("DNA+LZ", "HUFFMAN", 0), ("UTF+PACK+MM+LZX", "HUFFMAN", 0), ("MM", "ANS1", 0)])
 
 
 def test_sim_pre_stage_misplaced(sim):

@@ -15,7 +15,7 @@
 i64 knz_round_up(i64 v, i64 a) { return (v + a - 1) / a * a; }
 static i64 round_up(i64 v, i64 a) { return knz_round_up(v, a); }
 
-static int split_types(u64 tType, int* types)
+int knz_split_types(u64 tType, int* types)
 {
     int n = 0;
     for (int i = 0; i < 8; i++) {
@@ -490,7 +490,7 @@ int knz_encode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8
                         u8* h_flags)
 {
     int types[8];
-    const int nt = split_types(tType, types);
+    const int nt = knz_split_types(tType, types);
     const int hs = ctx->nHost; // leading stages the caller has applied on the host already (pre.cu)
     for (int i = 0; i < nt; i++)
         if (!(type_supported(types[i]) || (i < hs && knz_is_host_stage(types[i])))) {
@@ -873,7 +873,7 @@ int knz_grow(knz_ctx* ctx, u8** buf, i64* cap, i64 need)
 // ---- host stages in front of / behind the device stages (pre.cu) ------------------------------------
 // Leading host stages of a sequence; -1 when a host stage follows a device stage (not supported: the
 // reference's levels put them first).
-static int host_prefix_len(const int* types, int nt)
+int knz_host_prefix_len(const int* types, int nt)
 {
     int hs = 0;
     while (hs < nt && knz_is_host_stage(types[hs]))
@@ -904,7 +904,7 @@ static void host_parallel_for(int n, F&& body)
         t.join();
 }
 
-static int ensure_h_pre(knz_ctx* ctx)
+int knz_ensure_h_pre(knz_ctx* ctx)
 {
     if (ctx->h_pre == NULL && cudaMallocHost((void**)&ctx->h_pre, (size_t)ctx->maxBatch * (size_t)ctx->bstride) != cudaSuccess) {
         ctx->h_pre = NULL;
@@ -917,15 +917,15 @@ static int ensure_h_pre(knz_ctx* ctx)
 // Forward: every block of a batch through the leading host stages, one block per task (what the reference's
 // worker threads do in TransformSequence::forward, transform/TransformSequence.hpp:88-162, for those stages).
 // Leaves the bytes in ctx->h_pre (bstride apart) and the state of every block in ctx->h_init / h_dtype / h_hash.
-static int host_prefix_forward(knz_ctx* ctx, const int* types, int hs, int eType, int blockSize, const u8* in,
-                               const int32_t* lens, int nb)
+int knz_host_prefix_forward(knz_ctx* ctx, const int* types, int hs, int eType, int blockSize, const u8* in, i64 inStride,
+                            const int32_t* lens, int nb)
 {
-    if (ensure_h_pre(ctx) != KNZ_OK)
+    if (knz_ensure_h_pre(ctx) != KNZ_OK)
         return KNZ_ERR_PROCESS_BLOCK;
     const int cap = ctx->stageCap;
     host_parallel_for(nb, [&](int b) {
         std::vector<u8> tmp[2];
-        const u8* cur = in + (i64)b * blockSize;
+        const u8* cur = in + (i64)b * inStride;
         int len = lens[b], swaps = 0, flags = 0xFF, w = 0;
         // what EncodingTask leaves in the Context before the sequence runs (io/CompressedOutputStream.cpp:722-731)
         KnzPreCtx pc = { knz_magic_data_type(cur, len), blockSize, eType };
@@ -956,8 +956,8 @@ static int host_prefix_forward(knz_ctx* ctx, const int* types, int hs, int eType
 // Inverse: block b of a batch arrives from the device in ctx->h_pre (len[b] bytes) with the leading `hs` stages
 // still to undo, last one first (TransformSequence::inverse, transform/TransformSequence.hpp:165-247);
 // the result goes to out[b].  Returns false in ok[b] when a stage rejects its input.
-static void host_prefix_inverse(knz_ctx* ctx, const int* types, int hs, int eType, int blockSize, const u8* flags,
-                                const int* lens, int nb, u8* const* out, const int* outCap, int* outLen, u8* ok)
+void knz_host_prefix_inverse(knz_ctx* ctx, const int* types, int hs, int eType, int blockSize, const u8* flags,
+                             const int* lens, int nb, u8* const* out, const int* outCap, int* outLen, u8* ok)
 {
     const int cap = ctx->stageCap;
     const KnzPreCtx pc = { KDT_UNDEFINED, blockSize, eType };
@@ -1004,8 +1004,8 @@ extern "C" int knz_compress(knz_ctx* ctx, const char* transform, const char* ent
     if (blockSize < 1024 || blockSize > ctx->maxBlockSize || (blockSize & 15))
         return KNZ_ERR_BLOCK_SIZE;
     int types[8];
-    const int ntAll = split_types(tType, types);
-    const int hs = host_prefix_len(types, ntAll);
+    const int ntAll = knz_split_types(tType, types);
+    const int hs = knz_host_prefix_len(types, ntAll);
     if (hs < 0 || (hs > 0 && ctx->skipBlocks)) {
         snprintf(ctx->err, sizeof(ctx->err), "host stages (PACK, DNA, MM, UTF) must lead the sequence and do not combine with skipBlocks");
         return KNZ_ERR_INVALID_CODEC;
@@ -1086,7 +1086,7 @@ extern "C" int knz_compress(knz_ctx* ctx, const char* transform, const char* ent
             ng = nb - 1; // only the last block of a stream can be that small
         if (ng > 0 && hs > 0) {
             // leading host stages on the host threads, then what they left goes to the device in one copy per block
-            rc = host_prefix_forward(ctx, types, hs, eType, blockSize, in + off, lens, ng);
+            rc = knz_host_prefix_forward(ctx, types, hs, eType, blockSize, in + off, blockSize, lens, ng);
             for (int b = 0; b < ng && rc == KNZ_OK; b++)
                 if (cudaMemcpyAsync(ctx->dStageIn + (i64)b * ctx->bstride, ctx->h_pre + (i64)b * ctx->bstride,
                                     (size_t)ctx->h_init[b].len, cudaMemcpyHostToDevice, s) != cudaSuccess)
@@ -1190,7 +1190,7 @@ int knz_decode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8
                         u8* h_sink, int* h_sinkBlocks, const u64* h_expectHash, int ckBits)
 {
     int types[8];
-    const int nt = split_types(tType, types);
+    const int nt = knz_split_types(tType, types);
     const int hs = ctx->nHost; // leading stages the caller undoes on the host afterwards (pre.cu)
     for (int i = 0; i < nt; i++)
         if (!(type_supported(types[i]) || (i < hs && knz_is_host_stage(types[i])))) {
@@ -1665,13 +1665,13 @@ static int decompress_impl(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_t* 
     const u64 tType = info.tType;
     const int blockSize = info.blockSize;
     int types[8];
-    const int ntAll = split_types(tType, types);
-    const int hs = host_prefix_len(types, ntAll);
+    const int ntAll = knz_split_types(tType, types);
+    const int hs = knz_host_prefix_len(types, ntAll);
     if (hs < 0) {
         snprintf(ctx->err, sizeof(ctx->err), "host stages behind device stages are not supported");
         return KNZ_ERR_INVALID_CODEC;
     }
-    if (hs > 0 && ensure_h_pre(ctx) != KNZ_OK)
+    if (hs > 0 && knz_ensure_h_pre(ctx) != KNZ_OK)
         return KNZ_ERR_PROCESS_BLOCK;
     // whole compressed stream to the device; kernels read at bit offsets
     int rc = knz_grow(ctx, &ctx->dStream, &ctx->dStreamCap, round_up(n + 256, 256));
@@ -1822,8 +1822,8 @@ static int decompress_impl(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_t* 
                 const i64 room = cap - at;
                 dcap[g] = (int)((room < 0) ? 0 : (room < blockSize ? room : blockSize));
             }
-            host_prefix_inverse(ctx, types, hs, eType, blockSize, fl, ilen.data(), ng, dstp.data(), dcap.data(), dlen.data(),
-                                good.data());
+            knz_host_prefix_inverse(ctx, types, hs, eType, blockSize, fl, ilen.data(), ng, dstp.data(), dcap.data(),
+                                    dlen.data(), good.data());
             for (int g = 0; g < ng && rc == KNZ_OK; g++) {
                 if (!good[g]) {
                     snprintf(ctx->err, sizeof(ctx->err), "transform inverse failed (host stage) in block %d", evId[g]);

@@ -134,3 +134,11 @@ struct KnzStreamInfo {
 };
 int knz_parse_stream_header(knz_ctx* ctx, HostBitReader& r, KnzStreamInfo* info);
 void knz_dist_destroy(knz_ctx* ctx);
+// host stages around a device batch (api.cu; pre.cu holds the stages)
+int knz_split_types(u64 tType, int* types);
+int knz_host_prefix_len(const int* types, int nt); // leading host stages, -1 if one follows a device stage
+int knz_ensure_h_pre(knz_ctx* ctx);
+int knz_host_prefix_forward(knz_ctx* ctx, const int* types, int hs, int eType, int blockSize, const u8* in, i64 inStride,
+                            const int32_t* lens, int nb);
+void knz_host_prefix_inverse(knz_ctx* ctx, const int* types, int hs, int eType, int blockSize, const u8* flags,
+                             const int* lens, int nb, u8* const* out, const int* outCap, int* outLen, u8* ok);

@@ -291,10 +291,20 @@ __global__ void dist_heads_kernel(const u8* __restrict__ stream, const u64* __re
 
 // Encode this rank's blocks (device resident), gather every rank's blocks on rank 0 and assemble
 // the stream body there.  h_allBits (optional, every rank): bit count of every block in stream order.
+// Leading host stages of the sequence (pre.cu) for the stream-level entry point: the rank's blocks are still in
+// host memory, block k of the rank at base + k * stride; each sub-batch goes through the host stages and is
+// uploaded just before it is encoded.
+struct HostPrefix {
+    const u8* base;
+    i64 stride;
+    int hs;
+    int types[8];
+};
+
 static int dist_encode_dev(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8* d_in, i64 inStride,
                            const int32_t* lens, int nbOwn, int nBlocks, int firstBlockLen, u8* d_stream,
                            i64 streamCap, u64 startBit, u64* h_allBits, u64* endBit, const cudaEvent_t* batchReady,
-                           int batchBlocks)
+                           int batchBlocks, const HostPrefix* hp = NULL)
 {
     KnzDist* D = ctx->dist;
     cudaStream_t s = ctx->stream;
@@ -325,10 +335,21 @@ static int dist_encode_dev(knz_ctx* ctx, u64 tType, int eType, int blockSize, co
         int ng = nb;
         if (lens[off + nb - 1] <= 15)
             ng = nb - 1; // only the last block of a stream can be that small: framed on the host
+        if (ng > 0 && hp) {
+            rc = knz_host_prefix_forward(ctx, hp->types, hp->hs, eType, blockSize, hp->base + (i64)off * hp->stride, hp->stride,
+                                         lens + off, ng);
+            if (rc != KNZ_OK)
+                return rc;
+            for (int b = 0; b < ng; b++)
+                DCK(cudaMemcpyAsync(const_cast<u8*>(d_in) + (i64)(off + b) * inStride, ctx->h_pre + (i64)b * ctx->bstride,
+                                    (size_t)ctx->h_init[b].len, cudaMemcpyHostToDevice, s));
+            ctx->nHost = hp->hs;
+        }
         if (ng > 0) {
             rc = knz_encode_batch(ctx, tType, eType, blockSize, d_in + (i64)off * inStride, inStride, lens + off, ng,
                                   firstBlockLen, D->dBlk + (i64)off * ctx->outStride, ctx->outStride, dOwnBits + off,
                                   NULL);
+            ctx->nHost = 0;
             if (rc != KNZ_OK)
                 return rc;
             for (int i = 0; i < 8; i++)
@@ -338,7 +359,10 @@ static int dist_encode_dev(knz_ctx* ctx, u64 tType, int eType, int blockSize, co
             u8 raw[16], tmp[32];
             memset(tmp, 0, sizeof(tmp));
             const int len = lens[off + ng];
-            DCK(cudaMemcpyAsync(raw, d_in + (i64)(off + ng) * inStride, (size_t)len, cudaMemcpyDeviceToHost, s));
+            if (hp)
+                memcpy(raw, hp->base + (i64)(off + ng) * hp->stride, (size_t)len);
+            else
+                DCK(cudaMemcpyAsync(raw, d_in + (i64)(off + ng) * inStride, (size_t)len, cudaMemcpyDeviceToHost, s));
             DCK(cudaStreamSynchronize(s));
             const u64 bits = knz_frame_small_block(raw, len, tmp, ctx->checksumBits);
             DCK(cudaMemcpyAsync(D->dBlk + (i64)(off + ng) * ctx->outStride, tmp, 32, cudaMemcpyHostToDevice, s));
@@ -583,8 +607,15 @@ extern "C" int knz_compress_dist(knz_ctx* ctx, const char* transform, const char
     const int nbMax = (nBlocks + W - 1) / W;
     u8 hdr[32];
     const int hdrBytes = knz_stream_header_ex(tType, eType, blockSize, n, ctx->checksumBits, hdr);
+    HostPrefix hp;
+    hp.hs = knz_host_prefix_len(hp.types, knz_split_types(tType, hp.types));
+    if (hp.hs < 0 || (hp.hs > 0 && ctx->skipBlocks))
+        return KNZ_ERR_INVALID_CODEC;
+    hp.base = in + (i64)R * blockSize;
+    hp.stride = (i64)W * blockSize;
+    const i64 inSlot = (hp.hs > 0) ? ctx->bstride : (i64)blockSize; // host stages may expand a block
     // own blocks -> device, all copies queued up front on the copy stream, one event per sub-batch
-    int rc = knz_grow(ctx, &D->dIn, &D->dInCap, (i64)(nbMax > 0 ? nbMax : 1) * blockSize + 256);
+    int rc = knz_grow(ctx, &D->dIn, &D->dInCap, (i64)(nbMax > 0 ? nbMax : 1) * inSlot + 256);
     if (rc != KNZ_OK)
         return rc;
     const int step = ctx->maxBatch;
@@ -597,6 +628,8 @@ extern "C" int knz_compress_dist(knz_ctx* ctx, const char* transform, const char
         const i64 i = (i64)R + (i64)k * W;
         const i64 rem = n - i * blockSize;
         lens[k] = (int)((rem < blockSize) ? rem : blockSize);
+        if (hp.hs > 0)
+            continue; // uploaded per sub-batch, behind the host stages
         cudaMemcpyAsync(D->dIn + (i64)k * blockSize, in + i * blockSize, (size_t)lens[k], cudaMemcpyHostToDevice,
                         ctx->copyStream);
         if ((k + 1) % step == 0 || k == nbOwn - 1)
@@ -616,8 +649,9 @@ extern "C" int knz_compress_dist(knz_ctx* ctx, const char* transform, const char
     const int firstLen = (int)((n < blockSize) ? n : blockSize);
     // (a rank that failed locally still has to take part in the exchange: dist_encode_dev returns its own rc)
     if (rc == KNZ_OK)
-        rc = dist_encode_dev(ctx, tType, eType, blockSize, D->dIn, blockSize, lens, nbOwn, nBlocks, firstLen, ctx->dStream,
-                             streamCap, 8ull * (u64)hdrBytes, NULL, &endBit, D->evBatch, step);
+        rc = dist_encode_dev(ctx, tType, eType, blockSize, D->dIn, inSlot, lens, nbOwn, nBlocks, firstLen, ctx->dStream,
+                             streamCap, 8ull * (u64)hdrBytes, NULL, &endBit, (hp.hs > 0) ? NULL : D->evBatch, step,
+                             (hp.hs > 0) ? &hp : NULL);
     free(lens);
     if (rc != KNZ_OK)
         return rc;
@@ -654,6 +688,12 @@ extern "C" int knz_decompress_dist(knz_ctx* ctx, const uint8_t* in, int64_t n, u
     if (rc != KNZ_OK)
         return rc;
     const int blockSize = info.blockSize;
+    int types[8];
+    const int hs = knz_host_prefix_len(types, knz_split_types(info.tType, types));
+    if (hs < 0)
+        return KNZ_ERR_INVALID_CODEC;
+    if (hs > 0 && knz_ensure_h_pre(ctx) != KNZ_OK)
+        return KNZ_ERR_PROCESS_BLOCK;
     // ---- walk the length prefixes of the whole stream, keep the ranges of the blocks this rank owns
     struct Own {
         u64 start, bits, pay, ck;
@@ -759,6 +799,50 @@ extern "C" int knz_decompress_dist(knz_ctx* ctx, const uint8_t* in, int64_t n, u
         if (cudaStreamWaitEvent(s, D->evBatch[kb], 0) != cudaSuccess) {
             rc = KNZ_ERR_PROCESS_BLOCK;
             break;
+        }
+        if (hs > 0) {
+            // device stages into stage-sized slots, then the leading host stages are undone on the host threads and
+            // the blocks land at their place in the output
+            ctx->nHost = hs;
+            rc = knz_decode_batch(ctx, info.tType, info.eType, blockSize, D->dIn + (i64)off * istride, istride, pay + off,
+                                  endb + off, pre + off, fl + off, nb, ctx->dStageIn, ctx->bstride, ol + off, NULL, NULL, NULL, 0);
+            ctx->nHost = 0;
+            if (rc != KNZ_OK)
+                break;
+            for (int i = 0; i < 8; i++)
+                acc[i] += ctx->ms[i];
+            for (int b = 0; b < nb; b++)
+                cudaMemcpyAsync(ctx->h_pre + (i64)b * ctx->bstride, ctx->dStageIn + (i64)b * ctx->bstride, (size_t)ol[off + b],
+                                cudaMemcpyDeviceToHost, s);
+            if (cudaStreamSynchronize(s) != cudaSuccess) {
+                rc = KNZ_ERR_PROCESS_BLOCK;
+                break;
+            }
+            u8** dstp = (u8**)malloc(sizeof(u8*) * (size_t)nb);
+            int* dcap = (int*)malloc(sizeof(int) * (size_t)nb * 3);
+            int *dlen = dcap + nb, *ilen = dcap + 2 * nb;
+            u8* good = (u8*)malloc((size_t)nb);
+            for (int b = 0; b < nb; b++) {
+                const i64 dstOff = (i64)own[off + b].index * blockSize;
+                dstp[b] = out + ((dstOff < cap) ? dstOff : cap);
+                const i64 room = cap - dstOff;
+                dcap[b] = (int)((room < 0) ? 0 : (room < blockSize ? room : blockSize));
+                ilen[b] = ol[off + b];
+            }
+            knz_host_prefix_inverse(ctx, types, hs, info.eType, blockSize, fl + off, ilen, nb, dstp, dcap, dlen, good);
+            for (int b = 0; b < nb && rc == KNZ_OK; b++) {
+                const i64 dstOff = (i64)own[off + b].index * blockSize;
+                if (!good[b])
+                    rc = (dlen[b] > dcap[b]) ? KNZ_ERR_OUTPUT_TOO_SMALL : KNZ_ERR_PROCESS_BLOCK;
+                else if (info.ckBits && knz_xxhash_host(out + dstOff, dlen[b], info.ckBits) != cks[off + b])
+                    rc = KNZ_ERR_CRC_CHECK;
+                else if (dstOff + dlen[b] > lastEnd)
+                    lastEnd = dstOff + dlen[b];
+            }
+            free(dstp);
+            free(dcap);
+            free(good);
+            continue;
         }
         rc = knz_decode_batch(ctx, info.tType, info.eType, blockSize, D->dIn + (i64)off * istride, istride, pay + off,
                               endb + off, pre + off, fl + off, nb, D->dPlain + (i64)off * blockSize, blockSize, ol + off,

@@ -87,6 +87,28 @@ for ck in (32, 64):
     ctx.decompress_dist(want, nbytes, out=out)
     for i in range(rank, (nbytes + BS - 1) // BS, world):
         assert np.array_equal(out[i * BS: (i + 1) * BS], data[i * BS: (i + 1) * BS]), ("checksum", ck, i)
+# ---- sequences with leading host stages (levels 3 and 5 of the reference): pinned against the reference itself
+from oracle.oracle import Ref
+ref = Ref.load()
+if ref is not None:
+    from test_pre_stages import mixed_stream
+    data = mixed_stream(BS)
+    nbytes = data.size
+    for tname, ename, ck in (("TEXT+UTF+PACK+MM+LZX", "HUFFMAN", 0), ("TEXT+UTF+BWT+RANK+ZRLT", "ANS0", 32)):
+        ctx.set_checksum(ck)
+        comp = ctx.compress_dist(data, tname, ename, BS)
+        ctx.set_checksum(0)
+        want = ref.stream_compress(data, tname, ename, BS, 1, ck)
+        if rank == 0:
+            assert comp.size == want.size and np.array_equal(comp, want), ("host stages", tname, ename)
+        out = np.full(nbytes, 0xEE, dtype=np.uint8)
+        ctx.decompress_dist(want, nbytes, out=out)
+        for i in range((nbytes + BS - 1) // BS):
+            lo, hi = i * BS, min((i + 1) * BS, nbytes)
+            if i % world == rank:
+                assert np.array_equal(out[lo:hi], data[lo:hi]), ("host stages", tname, "own block", i)
+            else:
+                assert (out[lo:hi] == 0xEE).all(), ("host stages", tname, "foreign block touched", i)
 dist.barrier()
 if rank == 0:
     print("GLOO_OK")

@@ -624,8 +624,11 @@ bool utf_inverse(const u8* src, int n, u8* dst, int cap, int* outLen)
         dst[d++] = src[s++];
     while (s < end) {
         u32 a = src[s++];
-        if (a >= 128)
+        if (a >= 128) {
+            if (s >= n)
+                return false;
             a = ((u32)src[s++] << 7) + (a & 0x7F);
+        }
         if (a >= (u32)cnt)
             return false;
         const Sym& m = map[a];

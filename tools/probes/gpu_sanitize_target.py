@@ -12,6 +12,8 @@ PIPES = {
     "round1": (("BWT+RANK+ZRLT", "ANS0"), ("BWT+MTFT+ZRLT", "HUFFMAN"), ("NONE", "ANS0"), ("ZRLT", "HUFFMAN")),
     "round2": (("NONE", "ANS1"), ("BWT+SRT+ZRLT", "FPAQ"), ("LZ", "HUFFMAN"), ("LZX", "ANS0"), ("LZP", "NONE"),
                ("LZP+LZX", "ANS1")),
+    # round 2, second half: leading host stages (device stages start from the state they leave), skipBlocks
+    "round2b": (("TEXT+UTF+PACK+MM+LZX", "HUFFMAN"), ("TEXT+UTF+BWT+RANK+ZRLT", "ANS0"), ("DNA+LZ", "HUFFMAN"), ("MM", "ANS1")),
 }
 pipes = sum(PIPES.values(), ()) if what == "all" else PIPES[what]
 for name, data in (("comp", synth.synth_compressible(700000, 3)), ("inc", synth.synth_incompressible(300001, 4)),
@@ -32,4 +34,18 @@ for name, data in (("comp", synth.synth_compressible(700000, 3)), ("inc", synth.
                             ctx.decompress(bad, data.size)
                         except KanziGpuError:
                             pass
+if what in ("all", "round2b"):
+    mixed = np.concatenate([synth.synth_silesia(600000, 3), synth.synth_incompressible(200000, 5), synth.synth_text(100000, 6)])
+    for tr, en in (("BWT+RANK+ZRLT", "ANS0"), ("LZ", "HUFFMAN"), ("NONE", "NONE")):
+        for ck in (0, 32, 64):
+            ctx.set_checksum(ck)
+            ctx.set_skip_blocks(True)
+            c = ctx.compress(mixed, tr, en, 65536)
+            ctx.set_skip_blocks(False)
+            ctx.set_checksum(0)
+            assert np.array_equal(ctx.decompress(c, mixed.size), mixed), ("skipBlocks", tr, en, ck)
+            assert np.array_equal(ctx.decompress_range(c, 3, 9, mixed.size), mixed[2 * 65536: 8 * 65536]), ("range", tr, en, ck)
+    for tr, en in PIPES["round2b"]:
+        c = ctx.compress(mixed, tr, en, 65536)
+        assert np.array_equal(ctx.decompress(c, mixed.size), mixed), ("levels", tr, en)
 print("sanitize target ok")

@@ -147,6 +147,12 @@ int knz_set_skip_blocks(knz_ctx* ctx, int on);
 int knz_decompress_range(knz_ctx* ctx, const uint8_t* in, int64_t n, int fromBlock, int toBlock, uint8_t* out,
                          int64_t cap, int64_t* outLen);
 
+/* CompressedInputStream::seek (io/CompressedInputStream.hpp:329-375): restart decoding at a block boundary given
+ * as a BIT position of the stream -- the `offset` of a BLOCK_INFO event -- and decode up to nBlocks blocks from
+ * there.  The stream header is still read (it carries the pipeline and the block size).                  */
+int knz_decompress_seek(knz_ctx* ctx, const uint8_t* in, int64_t n, int64_t bitPos, int nBlocks, uint8_t* out,
+                        int64_t cap, int64_t* outLen);
+
 /* Listener events (Event.hpp:28-88).  The reference's tasks notify their listeners around every stage of
  * every block (io/CompressedOutputStream.cpp:685-689, :768-772, :810-814, :871-881;
  * io/CompressedInputStream.cpp:380, :924-932, :973-983); here a batch of blocks goes through the device

@@ -1647,9 +1647,9 @@ static void emit_decode_events(knz_ctx* ctx, int id, i64 offset, i64 rBytes, int
 }
 
 static int decompress_impl(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_t* out, int64_t cap, int64_t* outLen,
-                           int fromBlock, int toBlock)
+                           int fromBlock, int toBlock, int64_t seekBit = -1)
 {
-    if (!ctx || !in || !out || !outLen || n < 20 || fromBlock < 1 || toBlock < fromBlock)
+    if (!ctx || !in || !out || !outLen || n < 20 || fromBlock < 1 || toBlock < fromBlock || seekBit >= 8 * n)
         return KNZ_ERR_INVALID_PARAM;
     std::lock_guard<std::recursive_mutex> lock_(ctx->mtx);
     cudaSetDevice(ctx->device);
@@ -1664,6 +1664,13 @@ static int decompress_impl(knz_ctx* ctx, const uint8_t* in, int64_t n, uint8_t* 
     const int eType = info.eType;
     const u64 tType = info.tType;
     const int blockSize = info.blockSize;
+    if (seekBit >= 0) {
+        // CompressedInputStream::seek (io/CompressedInputStream.hpp:329-375): decoding restarts at a block boundary
+        // given as a bit position of the stream (what BLOCK_INFO events report); block ids count from there
+        if ((u64)seekBit < r.pos)
+            return KNZ_ERR_INVALID_PARAM;
+        r.pos = (u64)seekBit;
+    }
     int types[8];
     const int ntAll = knz_split_types(tType, types);
     const int hs = knz_host_prefix_len(types, ntAll);
@@ -1907,6 +1914,14 @@ extern "C" int knz_decompress_range(knz_ctx* ctx, const uint8_t* in, int64_t n, 
                                     int64_t cap, int64_t* outLen)
 {
     return decompress_impl(ctx, in, n, out, cap, outLen, fromBlock, toBlock);
+}
+
+extern "C" int knz_decompress_seek(knz_ctx* ctx, const uint8_t* in, int64_t n, int64_t bitPos, int nBlocks, uint8_t* out,
+                                   int64_t cap, int64_t* outLen)
+{
+    if (bitPos < 0 || nBlocks < 1)
+        return KNZ_ERR_INVALID_PARAM;
+    return decompress_impl(ctx, in, n, out, cap, outLen, 1, (nBlocks >= 0x7FFFFFFE) ? 0x7FFFFFFF : nBlocks + 1, bitPos);
 }
 
 // ------------------------------------------------------------------ stage-level API

@@ -63,6 +63,7 @@ def _load(path):
     L.knz_compress.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p, i32, vp, i64, vp, i64, ctypes.POINTER(i64)]
     L.knz_decompress.argtypes = [vp, vp, i64, vp, i64, ctypes.POINTER(i64)]
     L.knz_decompress_range.argtypes = [vp, vp, i64, i32, i32, vp, i64, ctypes.POINTER(i64)]
+    L.knz_decompress_seek.argtypes = [vp, vp, i64, i64, i32, vp, i64, ctypes.POINTER(i64)]
     L.knz_set_skip_blocks.argtypes = [vp, i32]
     L.knz_set_listener.argtypes = [vp, vp, vp]
     L.knz_encode_blocks.argtypes = [vp, u64, i32, i32, vp, i64, vp, i32, i32, vp, i64, vp, vp]
@@ -190,6 +191,16 @@ class Context:
         n = ctypes.c_int64(0)
         self._check(self.lib.knz_decompress_range(self.h, _ptr(comp), comp.size, int(from_block), int(to_block),
                                                   _ptr(out), cap, ctypes.byref(n)))
+        return out[: n.value]
+
+    def decompress_seek(self, comp, bit_pos, n_blocks, cap, out=None):
+        """Up to n_blocks blocks starting at the block boundary at bit `bit_pos` (the offset of a BLOCK_INFO event)."""
+        comp = np.ascontiguousarray(comp, dtype=np.uint8)
+        if out is None:
+            out = np.empty(max(cap, 1), dtype=np.uint8)
+        n = ctypes.c_int64(0)
+        self._check(self.lib.knz_decompress_seek(self.h, _ptr(comp), comp.size, int(bit_pos), int(n_blocks), _ptr(out), cap,
+                                                 ctypes.byref(n)))
         return out[: n.value]
 
     # ---- multi-GPU: one process per GPU, blocks sharded round-robin (see include/knz_gpu.h)

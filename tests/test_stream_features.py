@@ -78,6 +78,25 @@ def check_ranges(ctx, ref, bs):
             assert rc == 0 and r.size == want.size and np.array_equal(r, want), ("reference", lo, hi)
 
 
+def check_seek(ctx, bs):
+    """Block offsets reported by the listener are valid seek positions (CompressedInputStream::seek)."""
+    data = mixed_input(bs)
+    evs = []
+    ctx.set_listener(evs.append)
+    comp = ctx.compress(data, "ZRLT", "ANS0", bs)
+    ctx.set_listener(None)
+    offs = {e["blockId"]: e["offset"] for e in evs if e["type"] == "BLOCK_INFO"}
+    nblk = (data.size + bs - 1) // bs
+    assert sorted(offs) == list(range(1, nblk + 1))
+    for first, count in [(1, 1), (3, 2), (nblk, 1), (2, nblk)]:
+        got = ctx.decompress_seek(comp, offs[first], count, data.size)
+        want = data[(first - 1) * bs: min((first - 1 + count) * bs, data.size)]
+        assert got.size == want.size and np.array_equal(got, want), (first, count)
+    from kanzi_b200 import KanziGpuError
+    with pytest.raises(KanziGpuError):
+        ctx.decompress_seek(comp, offs[2] + 3, 1, data.size)  # not a block boundary
+
+
 def norm_events(evs, decode):
     """Per block, the reference's order; BLOCK_INFO is compared apart (it is emitted at a different point of
     the interleaving in a threaded run, but with the same content)."""
@@ -133,6 +152,10 @@ def test_sim_events(sim, ref):
     check_events(sim, ref, 1 << 16)
 
 
+def test_sim_seek(sim):
+    check_seek(sim, 1 << 16)
+
+
 # ---------------------------------------------------------------- on the B200
 @pytest.fixture(scope="module")
 def gpu():
@@ -160,6 +183,11 @@ def test_gpu_skip_blocks(gpu):
 @pytest.mark.gpu
 def test_gpu_block_ranges(gpu):
     check_ranges(gpu, maybe_ref(), 1 << 20)
+
+
+@pytest.mark.gpu
+def test_gpu_seek(gpu):
+    check_seek(gpu, 1 << 20)
 
 
 @pytest.mark.gpu

@@ -8,6 +8,11 @@
 // bytes, trailing run), CTA tiles are reduced, one thread per block folds the
 // tile summaries into tile entry states, and the emit pass re-walks each segment
 // from its exact entry state.  Algorithmic traffic: n read twice + z written.
+// Whole 16-byte segments are summarised and walked through 16-bit byte-class MASKS
+// (zero / non-zero, >= 0xFE, digit, escape lead, payload): run lengths come from
+// ffs / clz / popc and the walks visit tokens, not bytes, so lanes do not each follow
+// their own per-byte branch pattern.  KNZ_ZRLT_BYTEWALK=1 selects the byte walks
+// (kept for the ragged last segment of a block).
 #include "common.cuh"
 #include "kernels.h"
 
@@ -83,15 +88,20 @@ __device__ __forceinline__ ZSum zcombine(const ZSum& X, const ZSum& Y)
     return R;
 }
 
+template <bool INV>
 __device__ __forceinline__ ZSum zshfl_up(const ZSum& v, int o)
 {
     ZSum r;
     r.leadCnt = __shfl_up_sync(FULL_MASK, v.leadCnt, o);
-    r.leadBits = __shfl_up_sync(FULL_MASK, v.leadBits, o);
     r.trailCnt = __shfl_up_sync(FULL_MASK, v.trailCnt, o);
-    r.trailBits = __shfl_up_sync(FULL_MASK, v.trailBits, o);
     r.inter = __shfl_up_sync(FULL_MASK, v.inter, o);
     r.allz = __shfl_up_sync(FULL_MASK, v.allz, o);
+    if (INV) { // the forward direction carries plain counts: the digit fields stay zero
+        r.leadBits = __shfl_up_sync(FULL_MASK, v.leadBits, o);
+        r.trailBits = __shfl_up_sync(FULL_MASK, v.trailBits, o);
+    } else {
+        r.leadBits = r.trailBits = 0;
+    }
     return r;
 }
 
@@ -104,32 +114,46 @@ __device__ __forceinline__ ZSum zidentity()
 }
 
 // CTA-wide exclusive scan (Z_THREADS threads).  Returns the exclusive prefix of
-// `mine`; *total = combination of all threads (valid in every thread).
+// `mine`; *total = combination of all threads (valid in every thread).  The warp totals are
+// scanned by warp 0 (s_warp holds Z_THREADS / 32 + 1 elements: the exclusive warp prefixes, then
+// the CTA total).
 template <bool INV>
-__device__ ZSum zblock_scan(const ZSum& mine, ZSum* s_warp /*[8]*/, ZSum* total)
+__device__ ZSum zblock_scan(const ZSum& mine, ZSum* s_warp /*[Z_THREADS / 32 + 1]*/, ZSum* total)
 {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     ZSum inc = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const ZSum t = zshfl_up(inc, o);
+        const ZSum t = zshfl_up<INV>(inc, o);
         if (lane >= o)
             inc = zcombine<INV>(t, inc);
     }
-    ZSum exc = zshfl_up(inc, 1);
+    ZSum exc = zshfl_up<INV>(inc, 1);
     if (lane == 0)
         exc = zidentity();
     if (lane == 31)
         s_warp[w] = inc;
     __syncthreads();
-    ZSum base = zidentity(), tot = zidentity();
-    for (int i = 0; i < Z_THREADS / 32; i++) {
-        if (i == w)
-            base = tot;
-        tot = zcombine<INV>(tot, s_warp[i]);
+    if (w == 0) {
+        ZSum wi = (lane < Z_THREADS / 32) ? s_warp[lane] : zidentity();
+#pragma unroll
+        for (int o = 1; o < Z_THREADS / 32; o <<= 1) {
+            const ZSum t = zshfl_up<INV>(wi, o);
+            if (lane >= o)
+                wi = zcombine<INV>(t, wi);
+        }
+        ZSum we = zshfl_up<INV>(wi, 1);
+        if (lane == 0)
+            we = zidentity();
+        if (lane < Z_THREADS / 32)
+            s_warp[lane] = we;
+        if (lane == Z_THREADS / 32 - 1)
+            s_warp[Z_THREADS / 32] = wi;
     }
     __syncthreads();
-    *total = tot;
+    const ZSum base = s_warp[w];
+    *total = s_warp[Z_THREADS / 32];
+    __syncthreads();
     return zcombine<INV>(base, exc);
 }
 
@@ -174,15 +198,38 @@ __device__ __forceinline__ int zload16(const u8* __restrict__ src, int pos, int 
 }
 #define ZBYTE(w, k) (((w)[(k) >> 2] >> (8 * ((k)&3))) & 0xFFu)
 
+// ---- byte-class masks of a whole 16-byte segment (bit k <-> byte k)
+__device__ __forceinline__ u32 znz4(u32 w) // bit k set iff byte k of w is non-zero
+{
+    const u32 y = ((((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w) >> 7) & 0x01010101u;
+    return (y * 0x01020408u) >> 24;
+}
+
+__device__ __forceinline__ u32 znz16(u32 a, u32 b, u32 c, u32 d)
+{
+    return znz4(a) | (znz4(b) << 4) | (znz4(c) << 8) | (znz4(d) << 12);
+}
+
+__device__ __forceinline__ u32 zbyte_at(const u32 w[4], int k) // byte k, k not a compile-time constant
+{
+    const u32 a = (k & 8) ? w[2] : w[0];
+    const u32 b = (k & 8) ? w[3] : w[1];
+    return __byte_perm(a, b, (u32)(k & 7)) & 0xFFu;
+}
+
+// the `len` mask bits from bit `s` on, read as a binary number whose first bit is the most significant
+__device__ __forceinline__ u32 zdigits(u32 vm, int s, int len) // 1 <= len <= 16
+{
+    return __brev((vm >> s) & ((1u << len) - 1u)) >> (32 - len);
+}
+
 // ---- forward: per-thread walk over <= 16 bytes
-__device__ __forceinline__ ZSum zfwd_summary(const u8* __restrict__ src, int pos, int n)
+__device__ __forceinline__ ZSum zfwd_summary_bytes(const u32 w[4], int cnt)
 {
     ZSum S = zidentity();
     S.allz = 1;
     u32 run = 0;
     bool seen = false;
-    u32 w[4];
-    const int cnt = zload16(src, pos, n, w);
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         if (k >= cnt)
@@ -210,10 +257,47 @@ __device__ __forceinline__ ZSum zfwd_summary(const u8* __restrict__ src, int pos
     return S;
 }
 
+// Whole segment from masks.  An interior zero run (non-zero bytes on both sides) is at most 14 long,
+// so its digit count ilog2(len + 1) is [len >= 1] + [len >= 3] + [len >= 7]: three popcounts over the
+// run starts.  *nzOut = mask of the non-zero bytes.
+__device__ __forceinline__ ZSum zfwd_summary16(const u32 w[4], u32* nzOut)
+{
+    ZSum S = zidentity();
+    const u32 nz = znz16(w[0], w[1], w[2], w[3]);
+    *nzOut = nz;
+    if (nz == 0) {
+        S.leadCnt = S.trailCnt = 16;
+        return S;
+    }
+    // v >= 0xFE  <=>  (~v & 0xFE) == 0
+    const u32 fe = ~znz16(~w[0] & 0xFEFEFEFEu, ~w[1] & 0xFEFEFEFEu, ~w[2] & 0xFEFEFEFEu, ~w[3] & 0xFEFEFEFEu) & 0xFFFFu;
+    const int lead = __ffs((int)nz) - 1;
+    const int trail = __clz((int)nz) - 16;
+    const u32 zi = ~nz & ~((1u << lead) - 1u) & (0xFFFFu >> trail); // zero bytes of the interior runs
+    const u32 starts = zi & ~(zi << 1);
+    const u32 a3 = zi & (zi >> 1) & (zi >> 2);
+    const u32 a7 = a3 & (a3 >> 3) & (zi >> 6);
+    S.inter = (u32)(__popc(nz) + __popc(fe) + __popc(starts) + __popc(starts & a3) + __popc(starts & a7));
+    S.leadCnt = (u32)lead;
+    S.trailCnt = (u32)trail;
+    S.allz = 0;
+    return S;
+}
+
+template <bool LEAN>
+__device__ __forceinline__ ZSum zfwd_summary(const u32 w[4], int cnt, u32* nz)
+{
+    if (LEAN && cnt == 16)
+        return zfwd_summary16(w, nz);
+    *nz = 0;
+    return zfwd_summary_bytes(w, cnt);
+}
+
+template <bool LEAN>
 __global__ void __launch_bounds__(Z_THREADS)
 zrlt_fwd_sum_kernel(BufTable bt, const BlkState* __restrict__ st, int maxTiles, ZSum* __restrict__ tileSum)
 {
-    __shared__ ZSum s_warp[Z_THREADS / 32];
+    __shared__ ZSum s_warp[Z_THREADS / 32 + 1];
     const int b = blockIdx.y, t = blockIdx.x;
     const BlkState bs = st[b];
     const int n = bs.len;
@@ -221,7 +305,12 @@ zrlt_fwd_sum_kernel(BufTable bt, const BlkState* __restrict__ st, int maxTiles, 
         return;
     const u8* __restrict__ src = blk_src(bt, bs, b);
     const int pos = t * Z_TILE + threadIdx.x * 16;
-    const ZSum mine = (pos < n) ? zfwd_summary(src, pos, n) : zidentity();
+    ZSum mine = zidentity();
+    if (pos < n) {
+        u32 w[4], nz;
+        const int cnt = zload16(src, pos, n, w);
+        mine = zfwd_summary<LEAN>(w, cnt, &nz);
+    }
     ZSum total;
     zblock_scan<false>(mine, s_warp, &total);
     if (threadIdx.x == 0)
@@ -287,11 +376,12 @@ __device__ __forceinline__ u32 zemit_run(u8* __restrict__ dst, u32 out, u32 run)
     return out;
 }
 
+template <bool LEAN>
 __global__ void __launch_bounds__(Z_THREADS)
 zrlt_fwd_emit_kernel(BufTable bt, const BlkState* __restrict__ st, int maxTiles,
                      const ZEntry* __restrict__ tileEntry, const u32* __restrict__ zlen)
 {
-    __shared__ ZSum s_warp[Z_THREADS / 32];
+    __shared__ ZSum s_warp[Z_THREADS / 32 + 1];
     const int b = blockIdx.y, t = blockIdx.x;
     if (zlen[b] == 0xFFFFFFFFu)
         return;
@@ -302,7 +392,14 @@ zrlt_fwd_emit_kernel(BufTable bt, const BlkState* __restrict__ st, int maxTiles,
     const u8* __restrict__ src = blk_src(bt, bs, b);
     u8* __restrict__ dst = blk_dst(bt, bs, b);
     const int pos = t * Z_TILE + threadIdx.x * 16;
-    const ZSum mine = (pos < n) ? zfwd_summary(src, pos, n) : zidentity();
+    u32 w[4] = { 0, 0, 0, 0 };
+    u32 nz = 0;
+    int cnt = 0;
+    ZSum mine = zidentity();
+    if (pos < n) {
+        cnt = zload16(src, pos, n, w);
+        mine = zfwd_summary<LEAN>(w, cnt, &nz);
+    }
     ZSum total;
     const ZSum pre = zblock_scan<false>(mine, s_warp, &total);
     if (pos >= n)
@@ -310,26 +407,56 @@ zrlt_fwd_emit_kernel(BufTable bt, const BlkState* __restrict__ st, int maxTiles,
     const ZEntry e = zapply<false>(tileEntry[(i64)b * maxTiles + t], pre);
     u32 out = e.out, run = e.cnt;
     const int end = min(pos + 16, n);
-    u32 w[4];
-    const int cnt = zload16(src, pos, n, w);
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-        if (k >= cnt)
-            break;
-        const u32 v = ZBYTE(w, k);
-        if (v == 0) {
-            run++;
-            continue;
-        }
-        if (run) {
-            out = zemit_run(dst, out, run);
+    if (LEAN && cnt == 16) {
+        // one trip per non-zero byte; the zeros in front of it are a difference of bit positions
+        u32 m = nz;
+        int prev = 0;
+        while (m) {
+            const int k = __ffs((int)m) - 1;
+            m &= m - 1;
+            const u32 v = zbyte_at(w, k);
+            run += (u32)(k - prev);
+            prev = k + 1;
+            const u32 r = run + 1;
+            if (r >= 16) { // a run that came in from the segments before: any number of digits
+                out = zemit_run(dst, out, run);
+            } else if (r > 1) { // at most three digits, most significant first
+                const int nd = ilog2_u32(r);
+                if (nd > 2)
+                    dst[out + nd - 3] = (u8)((r >> 2) & 1);
+                if (nd > 1)
+                    dst[out + nd - 2] = (u8)((r >> 1) & 1);
+                dst[out + nd - 1] = (u8)(r & 1);
+                out += (u32)nd;
+            }
             run = 0;
+            const bool big = v >= 0xFE;
+            dst[out] = big ? (u8)0xFF : (u8)(v + 1);
+            if (big)
+                dst[out + 1] = (u8)(v - 0xFE);
+            out += big ? 2u : 1u;
         }
-        if (v >= 0xFE) {
-            dst[out++] = 0xFF;
-            dst[out++] = (u8)(v - 0xFE);
-        } else {
-            dst[out++] = (u8)(v + 1);
+        run += (u32)(16 - prev);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            if (k >= cnt)
+                break;
+            const u32 v = ZBYTE(w, k);
+            if (v == 0) {
+                run++;
+                continue;
+            }
+            if (run) {
+                out = zemit_run(dst, out, run);
+                run = 0;
+            }
+            if (v >= 0xFE) {
+                dst[out++] = 0xFF;
+                dst[out++] = (u8)(v - 0xFE);
+            } else {
+                dst[out++] = (u8)(v + 1);
+            }
         }
     }
     if (end == n && run)
@@ -347,14 +474,11 @@ __device__ __forceinline__ bool zinv_first_is_payload(const u8* __restrict__ src
     return (k & 1) != 0;
 }
 
-__device__ __forceinline__ ZSum zinv_summary(const u8* __restrict__ src, int pos, int n)
+__device__ __forceinline__ ZSum zinv_summary_bytes(const u32 w[4], int nb, bool payload)
 {
     ZSum S = zidentity();
     u32 cnt = 0, bits = 0;
     bool seen = false;
-    bool payload = zinv_first_is_payload(src, pos);
-    u32 w[4];
-    const int nb = zload16(src, pos, n, w);
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         if (k >= nb)
@@ -393,11 +517,69 @@ __device__ __forceinline__ ZSum zinv_summary(const u8* __restrict__ src, int pos
     return S;
 }
 
+// Byte classes of a whole segment: dig = digit bytes (0 / 1, not a payload), lead = escape leads,
+// pay = payloads, vm = bit 0 of every byte (the digit values).
+struct ZInvMasks {
+    u32 dig, lead, pay, vm;
+};
+
+__device__ __forceinline__ ZInvMasks zinv_masks16(const u32 w[4], bool payload0)
+{
+    ZInvMasks M;
+    const u32 le1 = ~znz16(w[0] & 0xFEFEFEFEu, w[1] & 0xFEFEFEFEu, w[2] & 0xFEFEFEFEu, w[3] & 0xFEFEFEFEu) & 0xFFFFu;
+    const u32 ff = ~znz16(~w[0], ~w[1], ~w[2], ~w[3]) & 0xFFFFu;
+    M.vm = znz16(w[0] & 0x01010101u, w[1] & 0x01010101u, w[2] & 0x01010101u, w[3] & 0x01010101u);
+    u32 pm = 0;
+    if (ff | (u32)payload0) {
+        // a 0xFF is a lead unless it is itself the payload of the lead before it: inside a run of
+        // 0xFF bytes the classes alternate, starting from the state the segment is entered in
+        u32 p = payload0 ? 1u : 0u;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            pm |= p << k;
+            p = ((ff >> k) & 1u) & (p ^ 1u);
+        }
+    }
+    M.pay = pm;
+    M.dig = le1 & ~pm;
+    M.lead = ff & ~pm;
+    return M;
+}
+
+__device__ __forceinline__ ZSum zinv_summary16(const ZInvMasks& M)
+{
+    ZSum S = zidentity();
+    const u32 nd = ~M.dig & 0xFFFFu; // tokens that end a digit run
+    if (nd == 0) {
+        S.leadCnt = S.trailCnt = 16;
+        S.leadBits = S.trailBits = __brev(M.vm) >> 16;
+        return S;
+    }
+    const int lead = __ffs((int)nd) - 1;
+    const int trail = __clz((int)nd) - 16;
+    S.allz = 0;
+    S.leadCnt = (u32)lead;
+    S.leadBits = lead ? zdigits(M.vm, 0, lead) : 0u;
+    S.trailCnt = (u32)trail;
+    S.trailBits = trail ? zdigits(M.vm, 16 - trail, trail) : 0u;
+    u32 inter = (u32)__popc(nd & ~M.lead); // literals and payloads: one output byte each
+    u32 di = M.dig & ~((1u << lead) - 1u) & (0xFFFFu >> trail); // digits of the interior runs (<= 14 long)
+    while (di) {
+        const int s = __ffs((int)di) - 1;
+        const int len = __ffs((int)~(di >> s)) - 1;
+        inter += ((1u << len) | zdigits(M.vm, s, len)) - 1u;
+        di &= ~(((1u << len) - 1u) << s);
+    }
+    S.inter = inter;
+    return S;
+}
+
+template <bool LEAN>
 __global__ void __launch_bounds__(Z_THREADS)
 zrlt_inv_sum_kernel(BufTable bt, const BlkState* __restrict__ st, int stageBit, int maxTiles,
                     ZSum* __restrict__ tileSum, int* __restrict__ errFlag)
 {
-    __shared__ ZSum s_warp[Z_THREADS / 32];
+    __shared__ ZSum s_warp[Z_THREADS / 32 + 1];
     const int b = blockIdx.y, t = blockIdx.x;
     const BlkState bs = st[b];
     if (bs.flags & stageBit)
@@ -407,7 +589,13 @@ zrlt_inv_sum_kernel(BufTable bt, const BlkState* __restrict__ st, int stageBit, 
         return;
     const u8* __restrict__ src = blk_src(bt, bs, b);
     const int pos = t * Z_TILE + threadIdx.x * 16;
-    const ZSum mine = (pos < n) ? zinv_summary(src, pos, n) : zidentity();
+    ZSum mine = zidentity();
+    if (pos < n) {
+        u32 w[4];
+        const int nb = zload16(src, pos, n, w);
+        const bool payload0 = zinv_first_is_payload(src, pos);
+        mine = (LEAN && nb == 16) ? zinv_summary16(zinv_masks16(w, payload0)) : zinv_summary_bytes(w, nb, payload0);
+    }
     ZSum total;
     zblock_scan<true>(mine, s_warp, &total);
     if (threadIdx.x == 0) {
@@ -434,11 +622,12 @@ zrlt_inv_zero_kernel(BufTable bt, const BlkState* __restrict__ st, const u32* __
         d4[i] = zero;
 }
 
+template <bool LEAN>
 __global__ void __launch_bounds__(Z_THREADS)
 zrlt_inv_emit_kernel(BufTable bt, const BlkState* __restrict__ st, int maxTiles,
                      const ZEntry* __restrict__ tileEntry, const u32* __restrict__ zlen)
 {
-    __shared__ ZSum s_warp[Z_THREADS / 32];
+    __shared__ ZSum s_warp[Z_THREADS / 32 + 1];
     const int b = blockIdx.y, t = blockIdx.x;
     if (zlen[b] == 0xFFFFFFFFu)
         return;
@@ -449,16 +638,51 @@ zrlt_inv_emit_kernel(BufTable bt, const BlkState* __restrict__ st, int maxTiles,
     const u8* __restrict__ src = blk_src(bt, bs, b);
     u8* __restrict__ dst = blk_dst(bt, bs, b);
     const int pos = t * Z_TILE + threadIdx.x * 16;
-    const ZSum mine = (pos < n) ? zinv_summary(src, pos, n) : zidentity();
+    u32 w[4] = { 0, 0, 0, 0 };
+    int nb = 0;
+    bool payload = false;
+    ZInvMasks M;
+    M.dig = M.lead = M.pay = M.vm = 0;
+    ZSum mine = zidentity();
+    if (pos < n) {
+        nb = zload16(src, pos, n, w);
+        payload = zinv_first_is_payload(src, pos);
+        if (LEAN && nb == 16) {
+            M = zinv_masks16(w, payload);
+            mine = zinv_summary16(M);
+        } else {
+            mine = zinv_summary_bytes(w, nb, payload);
+        }
+    }
     ZSum total;
     const ZSum pre = zblock_scan<true>(mine, s_warp, &total);
     if (pos >= n)
         return;
     const ZEntry e = zapply<true>(tileEntry[(i64)b * maxTiles + t], pre);
     u32 out = e.out, cnt = e.cnt, bits = e.bits;
-    bool payload = zinv_first_is_payload(src, pos);
-    u32 w[4];
-    const int nb = zload16(src, pos, n, w);
+    if (LEAN && nb == 16) {
+        // one trip per token that is not a digit; the digits in front of it come out of the masks
+        u32 m = ~M.dig & 0xFFFFu;
+        int prev = 0;
+        while (m) {
+            const int k = __ffs((int)m) - 1;
+            m &= m - 1;
+            const int gap = k - prev;
+            if (gap) {
+                bits = (bits << gap) | zdigits(M.vm, prev, gap);
+                cnt += (u32)gap;
+            }
+            prev = k + 1;
+            out += run_cost<true>(cnt, bits); // zeros are already in place (pre-zeroed output)
+            cnt = bits = 0;
+            const u32 v = zbyte_at(w, k);
+            if ((M.pay >> k) & 1u)
+                dst[out++] = (u8)(0xFE + v);
+            else if (!((M.lead >> k) & 1u))
+                dst[out++] = (u8)(v - 1);
+        }
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         if (k >= nb)
@@ -482,6 +706,16 @@ zrlt_inv_emit_kernel(BufTable bt, const BlkState* __restrict__ st, int maxTiles,
     }
 }
 
+// KNZ_ZRLT_BYTEWALK=1: the byte-by-byte walks for every segment (the form the masks replaced)
+static bool zrlt_lean()
+{
+    static const bool lean = [] {
+        const char* e = getenv("KNZ_ZRLT_BYTEWALK");
+        return !(e && e[0] == '1');
+    }();
+    return lean;
+}
+
 void launch_zrlt_forward(const StageLaunch& L, Workspace& ws, cudaStream_t s, u64* launches)
 {
     const int maxTiles = (ws.capN + Z_TILE - 1) / Z_TILE;
@@ -489,9 +723,16 @@ void launch_zrlt_forward(const StageLaunch& L, Workspace& ws, cudaStream_t s, u6
     ZSum* tileSum = reinterpret_cast<ZSum*>(ws.tileA);
     ZEntry* tileEntry = reinterpret_cast<ZEntry*>(ws.tileB);
     u32* zlen = ws.zlen;
-    KLAUNCH(zrlt_fwd_sum_kernel, dim3(tiles, L.nBlocks), Z_THREADS, s, L.bt, L.stIn, maxTiles, tileSum);
+    const bool lean = zrlt_lean();
+    if (lean)
+        KLAUNCH(zrlt_fwd_sum_kernel<true>, dim3(tiles, L.nBlocks), Z_THREADS, s, L.bt, L.stIn, maxTiles, tileSum);
+    else
+        KLAUNCH(zrlt_fwd_sum_kernel<false>, dim3(tiles, L.nBlocks), Z_THREADS, s, L.bt, L.stIn, maxTiles, tileSum);
     KLAUNCH(zrlt_fold_kernel<false>, (L.nBlocks + 31) / 32, 32, s, L, maxTiles, tileSum, tileEntry, zlen);
-    KLAUNCH(zrlt_fwd_emit_kernel, dim3(tiles, L.nBlocks), Z_THREADS, s, L.bt, L.stIn, maxTiles, tileEntry, zlen);
+    if (lean)
+        KLAUNCH(zrlt_fwd_emit_kernel<true>, dim3(tiles, L.nBlocks), Z_THREADS, s, L.bt, L.stIn, maxTiles, tileEntry, zlen);
+    else
+        KLAUNCH(zrlt_fwd_emit_kernel<false>, dim3(tiles, L.nBlocks), Z_THREADS, s, L.bt, L.stIn, maxTiles, tileEntry, zlen);
     *launches += 3;
 }
 
@@ -503,9 +744,16 @@ void launch_zrlt_inverse(const StageLaunch& L, Workspace& ws, cudaStream_t s, u6
     ZEntry* tileEntry = reinterpret_cast<ZEntry*>(ws.tileB) + (i64)L.wsBlock0 * maxTiles;
     u32* zlen = ws.zlen + L.wsBlock0;
     const int bit = 1 << (7 - L.stageIdx);
-    KLAUNCH(zrlt_inv_sum_kernel, dim3(tiles, L.nBlocks), Z_THREADS, s, L.bt, L.stIn, bit, maxTiles, tileSum, L.errFlag);
+    const bool lean = zrlt_lean();
+    if (lean)
+        KLAUNCH(zrlt_inv_sum_kernel<true>, dim3(tiles, L.nBlocks), Z_THREADS, s, L.bt, L.stIn, bit, maxTiles, tileSum, L.errFlag);
+    else
+        KLAUNCH(zrlt_inv_sum_kernel<false>, dim3(tiles, L.nBlocks), Z_THREADS, s, L.bt, L.stIn, bit, maxTiles, tileSum, L.errFlag);
     KLAUNCH(zrlt_fold_kernel<true>, (L.nBlocks + 31) / 32, 32, s, L, maxTiles, tileSum, tileEntry, zlen);
     KLAUNCH(zrlt_inv_zero_kernel, dim3(32, L.nBlocks), 256, s, L.bt, L.stIn, zlen);
-    KLAUNCH(zrlt_inv_emit_kernel, dim3(tiles, L.nBlocks), Z_THREADS, s, L.bt, L.stIn, maxTiles, tileEntry, zlen);
+    if (lean)
+        KLAUNCH(zrlt_inv_emit_kernel<true>, dim3(tiles, L.nBlocks), Z_THREADS, s, L.bt, L.stIn, maxTiles, tileEntry, zlen);
+    else
+        KLAUNCH(zrlt_inv_emit_kernel<false>, dim3(tiles, L.nBlocks), Z_THREADS, s, L.bt, L.stIn, maxTiles, tileEntry, zlen);
     *launches += 4;
 }

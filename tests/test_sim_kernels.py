@@ -273,3 +273,63 @@ def test_sim_corrupt_streams():
         assert outcomes["error"] + outcomes["bytes"] == 8
         assert np.array_equal(ctx.decompress(comp, data.size), data), (tname, ename, outcomes)
     ctx.close()
+
+
+def _zrlt_inputs():
+    """Inputs aimed at the mask forms of the ZRLT walks: zero runs of every length class inside a 16-byte
+    segment, across segments and across 4 KiB tiles, dense 0xFE / 0xFF, ragged lengths."""
+    rng = np.random.default_rng(20261017)
+    out = {}
+    for i, (n, pz, pbig) in enumerate([(16, 0.5, 0.1), (17, 0.5, 0.1), (31, 0.9, 0.0), (4096, 0.5, 0.02), (4097, 0.7, 0.2),
+                                       (12301, 0.3, 0.5), (20011, 0.95, 0.01), (33333, 0.6, 0.05), (8192 + 15, 0.0, 1.0)]):
+        a = rng.integers(1, 254, n, dtype=np.uint8)
+        a[rng.random(n) < pbig] = rng.choice(np.array([0xFE, 0xFF], dtype=np.uint8), 1)[0]
+        big = rng.random(n) < pbig
+        a[big] = rng.choice(np.array([0xFE, 0xFF], dtype=np.uint8), int(big.sum()))
+        a[rng.random(n) < pz] = 0
+        out[f"rnd{i}_{n}"] = a
+    # runs of exactly 1..40 zeros separated by one literal, then long runs that span tiles
+    parts = []
+    for L in list(range(1, 41)) + [62, 63, 64, 65, 126, 127, 128, 4095, 4096, 4097, 9000]:
+        parts.append(np.zeros(L, dtype=np.uint8))
+        parts.append(np.array([L & 0xFF or 7], dtype=np.uint8))
+    out["run_ladder"] = np.concatenate(parts)
+    out["run_ladder_shifted"] = np.concatenate([np.array([9, 0, 0], dtype=np.uint8), out["run_ladder"], np.zeros(21, dtype=np.uint8)])
+    z = np.zeros(30000, dtype=np.uint8)
+    z[::4099] = 0xFF
+    out["sparse_ff"] = z
+    return out
+
+
+def test_sim_zrlt_masks(sim, oracle):
+    for name, data in _zrlt_inputs().items():
+        n = data.size
+        cap = 2 * n + 64
+        a, applied = sim.transform_forward("ZRLT", data, cap)
+        b, flags = oracle.sequence_forward("ZRLT", data, n, cap)
+        assert applied == (flags != 0xFF), (name, applied, flags)
+        if applied:
+            assert a.size == b.size and np.array_equal(a, b), name
+            back, ok = sim.transform_inverse("ZRLT", b, n + 64)
+            assert ok and np.array_equal(back, data), name
+
+
+def test_sim_zrlt_inverse_token_classes(sim, oracle):
+    """Inverse on arbitrary token streams (runs of 0xFF: lead / payload alternate; digits behind a lead are payloads)."""
+    from kanzi_b200 import KanziGpuError
+    rng = np.random.default_rng(7)
+    alphabet = np.array([0, 1, 0xFF, 0xFF, 2, 3, 0x80, 0xFE], dtype=np.uint8)
+    for n in (16, 33, 4096, 5000, 12345):
+        for trial in range(3):
+            src = alphabet[rng.integers(0, alphabet.size, n)]
+            if trial == 2:
+                src[rng.random(n) < 0.5] = 0xFF
+            want, ok = oracle.sequence_inverse("ZRLT", 0, src, 1 << 17)
+            try:
+                got, applied = sim.transform_inverse("ZRLT", src, 1 << 17)
+            except KanziGpuError:
+                assert not ok, (n, trial)
+                continue
+            assert bool(ok) == applied, (n, trial)
+            if ok:
+                assert got.size == want.size and np.array_equal(got, want), (n, trial)

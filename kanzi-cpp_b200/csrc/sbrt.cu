@@ -519,13 +519,17 @@ struct InvList {
         return c;
     }
 
-    // any r: generic 8-slot update
+    // any r.  Entries below rank r keep keys <= the accessed entry's old key <= its new one, so only slots
+    // 0..r/32 can hold a larger key, and only slots rp/32..r/32 change (r, rp are warp uniform).  One rotate
+    // per array and slot: lane l takes lane l-1, and lane 0 receives lane 31 of the same slot, which is what
+    // lane 0 of the NEXT slot needs -- it is carried there in a register instead of a second shuffle.
     __device__ __forceinline__ u32 step_deep(int r, u32 i, int lane)
     {
+        const int kr = r >> 5;
         u32 sel = 0;
 #pragma unroll
         for (int k = 0; k < 8; k++)
-            sel |= dP[k] & (0u - (u32)((r >> 5) == k));
+            sel |= dP[k] & (0u - (u32)(kr == k));
         const u32 e = __shfl_sync(FULL_MASK, sel, r & 31);
         const u32 c = e & 0xFF;
         const u32 y = key_raw(i, e >> 8);
@@ -534,24 +538,26 @@ struct InvList {
         int rp = 0;
 #pragma unroll
         for (int k = 0; k < 8; k++)
-            rp += __popc(__ballot_sync(FULL_MASK, dK[k] > y));
+            if (k <= kr)
+                rp += __popc(__ballot_sync(FULL_MASK, dK[k] > y));
+        const int kp = rp >> 5;
+        const int from = (lane + 31) & 31;
+        u32 carryK = 0, carryP = 0; // lane 0: lane 31 of the slot before (never used in slot kp: 32 kp <= rp)
 #pragma unroll
-        for (int k = 7; k >= 0; k--) {
-            u32 nK = __shfl_up_sync(FULL_MASK, dK[k], 1);
-            u32 nP = __shfl_up_sync(FULL_MASK, dP[k], 1);
-            if (k > 0) {
-                const u32 sK = __shfl_sync(FULL_MASK, dK[k - 1], 31);
-                const u32 sP = __shfl_sync(FULL_MASK, dP[k - 1], 31);
-                if (lane == 0) {
-                    nK = sK;
-                    nP = sP;
-                }
+        for (int k = 0; k < 8; k++) {
+            if (k >= kp && k <= kr) {
+                const u32 rK = __shfl_sync(FULL_MASK, dK[k], from);
+                const u32 rP = __shfl_sync(FULL_MASK, dP[k], from);
+                const u32 nK = (lane == 0) ? carryK : rK;
+                const u32 nP = (lane == 0) ? carryP : rP;
+                carryK = rK;
+                carryP = rP;
+                const int g = 32 * k + lane;
+                const bool mv = (g > rp) && (g <= r);
+                const bool ins = g == rp;
+                dK[k] = ins ? yn : (mv ? nK : dK[k]);
+                dP[k] = ins ? ne : (mv ? nP : dP[k]);
             }
-            const int g = 32 * k + lane;
-            const bool mv = (g > rp) && (g <= r);
-            const bool ins = g == rp;
-            dK[k] = ins ? yn : (mv ? nK : dK[k]);
-            dP[k] = ins ? ne : (mv ? nP : dP[k]);
         }
         return c;
     }

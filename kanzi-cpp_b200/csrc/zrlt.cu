@@ -317,32 +317,61 @@ zrlt_fwd_sum_kernel(BufTable bt, const BlkState* __restrict__ st, int maxTiles, 
         tileSum[(i64)b * maxTiles + t] = total;
 }
 
-// One thread per block: fold tile summaries, decide accept/refuse, publish next state.
+// One warp per block: fold the tile summaries into tile entry states (32 tiles per trip: warp scan of the
+// summaries, applied to the state the trip is entered in), decide accept/refuse, publish the next state.
 template <bool INV>
-__global__ void zrlt_fold_kernel(StageLaunch L, int maxTiles, const ZSum* __restrict__ tileSum,
-                                 ZEntry* __restrict__ tileEntry, u32* __restrict__ zlen)
+__global__ void __launch_bounds__(32)
+zrlt_fold_kernel(StageLaunch L, int maxTiles, const ZSum* __restrict__ tileSum,
+                 ZEntry* __restrict__ tileEntry, u32* __restrict__ zlen)
 {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.x;
+    const int lane = threadIdx.x;
     if (b >= L.nBlocks)
         return;
     const BlkState bs = L.stIn[b];
     BlkState ns = bs;
     const int bit = 1 << (7 - L.stageIdx);
     if (INV && (bs.flags & bit)) { // stage was skipped by the encoder
-        L.stOut[b] = ns;
-        zlen[b] = 0xFFFFFFFFu;
+        if (lane == 0) {
+            L.stOut[b] = ns;
+            zlen[b] = 0xFFFFFFFFu;
+        }
         return;
     }
     const int n = bs.len;
     const int tiles = (n + Z_TILE - 1) / Z_TILE;
+    const ZSum* __restrict__ ts = tileSum + (i64)b * maxTiles;
+    ZEntry* __restrict__ te = tileEntry + (i64)b * maxTiles;
     ZEntry e;
     e.out = e.cnt = e.bits = e.pad = 0;
     bool overflow = false;
-    for (int t = 0; t < tiles; t++) {
-        tileEntry[(i64)b * maxTiles + t] = e;
-        const ZSum S = tileSum[(i64)b * maxTiles + t];
-        e = zapply<INV>(e, S);
+    ZSum nxt = (lane < tiles) ? ts[lane] : zidentity();
+    for (int t0 = 0; t0 < tiles; t0 += 32) {
+        const int t = t0 + lane;
+        ZSum inc = nxt;
+        nxt = (t + 32 < tiles) ? ts[t + 32] : zidentity(); // the next trip's summaries are in flight during the scan
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const ZSum up = zshfl_up<INV>(inc, o);
+            if (lane >= o)
+                inc = zcombine<INV>(up, inc);
+        }
+        ZSum exc = zshfl_up<INV>(inc, 1);
+        if (lane == 0)
+            exc = zidentity();
+        if (t < tiles)
+            te[t] = zapply<INV>(e, exc);
+        ZSum tot;
+        tot.leadCnt = __shfl_sync(FULL_MASK, inc.leadCnt, 31);
+        tot.leadBits = __shfl_sync(FULL_MASK, inc.leadBits, 31);
+        tot.trailCnt = __shfl_sync(FULL_MASK, inc.trailCnt, 31);
+        tot.trailBits = __shfl_sync(FULL_MASK, inc.trailBits, 31);
+        tot.inter = __shfl_sync(FULL_MASK, inc.inter, 31);
+        tot.allz = __shfl_sync(FULL_MASK, inc.allz, 31);
+        e = zapply<INV>(e, tot);
     }
+    if (lane != 0)
+        return;
     const u32 tailCost = run_cost<INV>(e.cnt, e.bits);
     const u32 z = sadd(e.out, tailCost);
     if (z >= 0x7FFFFFFFu)
@@ -376,14 +405,41 @@ __device__ __forceinline__ u32 zemit_run(u8* __restrict__ dst, u32 out, u32 run)
     return out;
 }
 
+// Output bytes of one tile staged in shared memory: 2 bytes per input byte at most, plus the digits of the run
+// that was open when the tile started, plus the 16-byte alignment slack of the destination.
+#define Z_STAGE_BYTES (2 * Z_TILE + 64)
+
+// Copies the staged bytes [a0, a0 + len) of s_out to g0 + a0 .. (g0 is 16-byte aligned): whole 16-byte
+// vectors inside, single bytes on the two ragged ends (their neighbours belong to other tiles).
+__device__ __forceinline__ void zstage_flush(const u8* s_out, u8* __restrict__ g0, u32 a0, u32 len)
+{
+    const u32 tot = a0 + len;
+    const u32 nvec = (tot + 15) >> 4;
+    for (u32 v = threadIdx.x; v < nvec; v += Z_THREADS) {
+        const u32 lo = v << 4, hi = lo + 16;
+        if (lo >= a0 && hi <= tot) {
+            *reinterpret_cast<uint4*>(g0 + lo) = *reinterpret_cast<const uint4*>(s_out + lo);
+        } else {
+            const u32 k1 = (hi < tot) ? hi : tot;
+            for (u32 k = (lo > a0) ? lo : a0; k < k1; k++)
+                g0[k] = s_out[k];
+        }
+    }
+}
+
+// LEAN: mask walks, and the tile's output goes through shared memory (it is one contiguous range,
+// [entry(t).out, entry(t + 1).out) or up to the block's output length for the last tile) and leaves as
+// aligned 128-bit stores; otherwise byte walks that store straight to global memory.
 template <bool LEAN>
 __global__ void __launch_bounds__(Z_THREADS)
 zrlt_fwd_emit_kernel(BufTable bt, const BlkState* __restrict__ st, int maxTiles,
                      const ZEntry* __restrict__ tileEntry, const u32* __restrict__ zlen)
 {
     __shared__ ZSum s_warp[Z_THREADS / 32 + 1];
+    __shared__ __align__(16) u8 s_out[LEAN ? Z_STAGE_BYTES : 16];
     const int b = blockIdx.y, t = blockIdx.x;
-    if (zlen[b] == 0xFFFFFFFFu)
+    const u32 z = zlen[b];
+    if (z == 0xFFFFFFFFu)
         return;
     const BlkState bs = st[b];
     const int n = bs.len;
@@ -402,65 +458,76 @@ zrlt_fwd_emit_kernel(BufTable bt, const BlkState* __restrict__ st, int maxTiles,
     }
     ZSum total;
     const ZSum pre = zblock_scan<false>(mine, s_warp, &total);
-    if (pos >= n)
-        return;
-    const ZEntry e = zapply<false>(tileEntry[(i64)b * maxTiles + t], pre);
-    u32 out = e.out, run = e.cnt;
-    const int end = min(pos + 16, n);
-    if (LEAN && cnt == 16) {
-        // one trip per non-zero byte; the zeros in front of it are a difference of bit positions
-        u32 m = nz;
-        int prev = 0;
-        while (m) {
-            const int k = __ffs((int)m) - 1;
-            m &= m - 1;
-            const u32 v = zbyte_at(w, k);
-            run += (u32)(k - prev);
-            prev = k + 1;
-            const u32 r = run + 1;
-            if (r >= 16) { // a run that came in from the segments before: any number of digits
-                out = zemit_run(dst, out, run);
-            } else if (r > 1) { // at most three digits, most significant first
-                const int nd = ilog2_u32(r);
-                if (nd > 2)
-                    dst[out + nd - 3] = (u8)((r >> 2) & 1);
-                if (nd > 1)
-                    dst[out + nd - 2] = (u8)((r >> 1) & 1);
-                dst[out + nd - 1] = (u8)(r & 1);
-                out += (u32)nd;
-            }
-            run = 0;
-            const bool big = v >= 0xFE;
-            dst[out] = big ? (u8)0xFF : (u8)(v + 1);
-            if (big)
-                dst[out + 1] = (u8)(v - 0xFE);
-            out += big ? 2u : 1u;
-        }
-        run += (u32)(16 - prev);
-    } else {
-#pragma unroll
-        for (int k = 0; k < 16; k++) {
-            if (k >= cnt)
-                break;
-            const u32 v = ZBYTE(w, k);
-            if (v == 0) {
-                run++;
-                continue;
-            }
-            if (run) {
-                out = zemit_run(dst, out, run);
+    const ZEntry te = tileEntry[(i64)b * maxTiles + t];
+    // where this tile's bytes are written: wdst[k - wbase] is output byte k of the block
+    const u32 wbase = LEAN ? te.out : 0u;
+    const u32 a0 = LEAN ? (u32)(reinterpret_cast<size_t>(dst + te.out) & 15) : 0u;
+    u8* __restrict__ wdst = LEAN ? (s_out + a0) : dst;
+    if (pos < n) {
+        const ZEntry e = zapply<false>(te, pre);
+        u32 out = e.out - wbase, run = e.cnt;
+        const int end = min(pos + 16, n);
+        if (LEAN && cnt == 16) {
+            // one trip per non-zero byte; the zeros in front of it are a difference of bit positions
+            u32 m = nz;
+            int prev = 0;
+            while (m) {
+                const int k = __ffs((int)m) - 1;
+                m &= m - 1;
+                const u32 v = zbyte_at(w, k);
+                run += (u32)(k - prev);
+                prev = k + 1;
+                const u32 r = run + 1;
+                if (r >= 16) { // a run that came in from the segments before: any number of digits
+                    out = zemit_run(wdst, out, run);
+                } else if (r > 1) { // at most three digits, most significant first
+                    const int nd = ilog2_u32(r);
+                    if (nd > 2)
+                        wdst[out + nd - 3] = (u8)((r >> 2) & 1);
+                    if (nd > 1)
+                        wdst[out + nd - 2] = (u8)((r >> 1) & 1);
+                    wdst[out + nd - 1] = (u8)(r & 1);
+                    out += (u32)nd;
+                }
                 run = 0;
+                const bool big = v >= 0xFE;
+                wdst[out] = big ? (u8)0xFF : (u8)(v + 1);
+                if (big)
+                    wdst[out + 1] = (u8)(v - 0xFE);
+                out += big ? 2u : 1u;
             }
-            if (v >= 0xFE) {
-                dst[out++] = 0xFF;
-                dst[out++] = (u8)(v - 0xFE);
-            } else {
-                dst[out++] = (u8)(v + 1);
+            run += (u32)(16 - prev);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                if (k >= cnt)
+                    break;
+                const u32 v = ZBYTE(w, k);
+                if (v == 0) {
+                    run++;
+                    continue;
+                }
+                if (run) {
+                    out = zemit_run(wdst, out, run);
+                    run = 0;
+                }
+                if (v >= 0xFE) {
+                    wdst[out++] = 0xFF;
+                    wdst[out++] = (u8)(v - 0xFE);
+                } else {
+                    wdst[out++] = (u8)(v + 1);
+                }
             }
         }
+        if (end == n && run)
+            zemit_run(wdst, out, run);
     }
-    if (end == n && run)
-        zemit_run(dst, out, run);
+    if (LEAN) {
+        const bool lastTile = (i64)(t + 1) * Z_TILE >= n;
+        const u32 endOut = lastTile ? z : tileEntry[(i64)b * maxTiles + t + 1].out;
+        __syncthreads();
+        zstage_flush(s_out, dst + te.out - a0, a0, endOut - te.out);
+    }
 }
 
 // ---- inverse
@@ -622,14 +689,20 @@ zrlt_inv_zero_kernel(BufTable bt, const BlkState* __restrict__ st, const u32* __
         d4[i] = zero;
 }
 
+// A tile's output range, zeros included, staged in shared memory when it is at most this long (a tile
+// whose runs expand further stores its literals straight into the pre-zeroed output).
+#define Z_INV_STAGE_BYTES 16384
+
 template <bool LEAN>
 __global__ void __launch_bounds__(Z_THREADS)
 zrlt_inv_emit_kernel(BufTable bt, const BlkState* __restrict__ st, int maxTiles,
                      const ZEntry* __restrict__ tileEntry, const u32* __restrict__ zlen)
 {
     __shared__ ZSum s_warp[Z_THREADS / 32 + 1];
+    __shared__ __align__(16) u8 s_out[LEAN ? Z_INV_STAGE_BYTES : 16];
     const int b = blockIdx.y, t = blockIdx.x;
-    if (zlen[b] == 0xFFFFFFFFu)
+    const u32 z = zlen[b];
+    if (z == 0xFFFFFFFFu)
         return;
     const BlkState bs = st[b];
     const int n = bs.len;
@@ -637,6 +710,22 @@ zrlt_inv_emit_kernel(BufTable bt, const BlkState* __restrict__ st, int maxTiles,
         return;
     const u8* __restrict__ src = blk_src(bt, bs, b);
     u8* __restrict__ dst = blk_dst(bt, bs, b);
+    const ZEntry te = tileEntry[(i64)b * maxTiles + t];
+    // the tile's output range [te.out, endOut): literals of its tokens and the zeros of the runs they end
+    const bool lastTile = (i64)(t + 1) * Z_TILE >= n;
+    const u32 endOut = lastTile ? z : tileEntry[(i64)b * maxTiles + t + 1].out;
+    const u32 span = endOut - te.out;
+    const u32 a0 = (u32)(reinterpret_cast<size_t>(dst + te.out) & 15);
+    const bool staged = LEAN && (a0 + span <= (u32)Z_INV_STAGE_BYTES); // uniform over the CTA
+    if (staged) {
+        const u32 nvec = (a0 + span + 15) >> 4;
+        const uint4 zero = make_uint4(0, 0, 0, 0);
+        for (u32 v = threadIdx.x; v < nvec; v += Z_THREADS)
+            reinterpret_cast<uint4*>(s_out)[v] = zero;
+        __syncthreads();
+    }
+    const u32 wbase = staged ? te.out : 0u;
+    u8* __restrict__ wdst = staged ? (s_out + a0) : dst;
     const int pos = t * Z_TILE + threadIdx.x * 16;
     u32 w[4] = { 0, 0, 0, 0 };
     int nb = 0;
@@ -656,53 +745,57 @@ zrlt_inv_emit_kernel(BufTable bt, const BlkState* __restrict__ st, int maxTiles,
     }
     ZSum total;
     const ZSum pre = zblock_scan<true>(mine, s_warp, &total);
-    if (pos >= n)
-        return;
-    const ZEntry e = zapply<true>(tileEntry[(i64)b * maxTiles + t], pre);
-    u32 out = e.out, cnt = e.cnt, bits = e.bits;
-    if (LEAN && nb == 16) {
-        // one trip per token that is not a digit; the digits in front of it come out of the masks
-        u32 m = ~M.dig & 0xFFFFu;
-        int prev = 0;
-        while (m) {
-            const int k = __ffs((int)m) - 1;
-            m &= m - 1;
-            const int gap = k - prev;
-            if (gap) {
-                bits = (bits << gap) | zdigits(M.vm, prev, gap);
-                cnt += (u32)gap;
+    if (pos < n) {
+        const ZEntry e = zapply<true>(te, pre);
+        u32 out = e.out - wbase, cnt = e.cnt, bits = e.bits;
+        if (LEAN && nb == 16) {
+            // one trip per token that is not a digit; the digits in front of it come out of the masks
+            u32 m = ~M.dig & 0xFFFFu;
+            int prev = 0;
+            while (m) {
+                const int k = __ffs((int)m) - 1;
+                m &= m - 1;
+                const int gap = k - prev;
+                if (gap) {
+                    bits = (bits << gap) | zdigits(M.vm, prev, gap);
+                    cnt += (u32)gap;
+                }
+                prev = k + 1;
+                out += run_cost<true>(cnt, bits); // the zeros are already in place
+                cnt = bits = 0;
+                const u32 v = zbyte_at(w, k);
+                if ((M.pay >> k) & 1u)
+                    wdst[out++] = (u8)(0xFE + v);
+                else if (!((M.lead >> k) & 1u))
+                    wdst[out++] = (u8)(v - 1);
             }
-            prev = k + 1;
-            out += run_cost<true>(cnt, bits); // zeros are already in place (pre-zeroed output)
-            cnt = bits = 0;
-            const u32 v = zbyte_at(w, k);
-            if ((M.pay >> k) & 1u)
-                dst[out++] = (u8)(0xFE + v);
-            else if (!((M.lead >> k) & 1u))
-                dst[out++] = (u8)(v - 1);
-        }
-        return;
-    }
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-        if (k >= nb)
-            break;
-        const u32 v = ZBYTE(w, k);
-        if (!payload && v <= 1) {
-            bits = (bits << 1) | v;
-            cnt++;
-            continue;
-        }
-        out += run_cost<true>(cnt, bits); // zeros are already in place (pre-zeroed output)
-        cnt = bits = 0;
-        if (payload) {
-            dst[out++] = (u8)(0xFE + v);
-            payload = false;
-        } else if (v == 0xFF) {
-            payload = true;
         } else {
-            dst[out++] = (u8)(v - 1);
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                if (k >= nb)
+                    break;
+                const u32 v = ZBYTE(w, k);
+                if (!payload && v <= 1) {
+                    bits = (bits << 1) | v;
+                    cnt++;
+                    continue;
+                }
+                out += run_cost<true>(cnt, bits); // the zeros are already in place
+                cnt = bits = 0;
+                if (payload) {
+                    wdst[out++] = (u8)(0xFE + v);
+                    payload = false;
+                } else if (v == 0xFF) {
+                    payload = true;
+                } else {
+                    wdst[out++] = (u8)(v - 1);
+                }
+            }
         }
+    }
+    if (staged) {
+        __syncthreads();
+        zstage_flush(s_out, dst + te.out - a0, a0, span);
     }
 }
 
@@ -728,7 +821,7 @@ void launch_zrlt_forward(const StageLaunch& L, Workspace& ws, cudaStream_t s, u6
         KLAUNCH(zrlt_fwd_sum_kernel<true>, dim3(tiles, L.nBlocks), Z_THREADS, s, L.bt, L.stIn, maxTiles, tileSum);
     else
         KLAUNCH(zrlt_fwd_sum_kernel<false>, dim3(tiles, L.nBlocks), Z_THREADS, s, L.bt, L.stIn, maxTiles, tileSum);
-    KLAUNCH(zrlt_fold_kernel<false>, (L.nBlocks + 31) / 32, 32, s, L, maxTiles, tileSum, tileEntry, zlen);
+    KLAUNCH(zrlt_fold_kernel<false>, L.nBlocks, 32, s, L, maxTiles, tileSum, tileEntry, zlen);
     if (lean)
         KLAUNCH(zrlt_fwd_emit_kernel<true>, dim3(tiles, L.nBlocks), Z_THREADS, s, L.bt, L.stIn, maxTiles, tileEntry, zlen);
     else
@@ -749,7 +842,7 @@ void launch_zrlt_inverse(const StageLaunch& L, Workspace& ws, cudaStream_t s, u6
         KLAUNCH(zrlt_inv_sum_kernel<true>, dim3(tiles, L.nBlocks), Z_THREADS, s, L.bt, L.stIn, bit, maxTiles, tileSum, L.errFlag);
     else
         KLAUNCH(zrlt_inv_sum_kernel<false>, dim3(tiles, L.nBlocks), Z_THREADS, s, L.bt, L.stIn, bit, maxTiles, tileSum, L.errFlag);
-    KLAUNCH(zrlt_fold_kernel<true>, (L.nBlocks + 31) / 32, 32, s, L, maxTiles, tileSum, tileEntry, zlen);
+    KLAUNCH(zrlt_fold_kernel<true>, L.nBlocks, 32, s, L, maxTiles, tileSum, tileEntry, zlen);
     KLAUNCH(zrlt_inv_zero_kernel, dim3(32, L.nBlocks), 256, s, L.bt, L.stIn, zlen);
     if (lean)
         KLAUNCH(zrlt_inv_emit_kernel<true>, dim3(tiles, L.nBlocks), Z_THREADS, s, L.bt, L.stIn, maxTiles, tileEntry, zlen);

@@ -519,10 +519,10 @@ def run_ours(args, rank, world, local_rank):
         # profiles/r02_traffic_64blocks.md (stage sums of one encode+decode pass over 64 blocks) / 64
         "bwt_forward": 64.568e9 / 64,
         "rank_forward": 1.230e9 / 64,
-        "zrlt_forward": 0.704e9 / 64,
+        "zrlt_forward": 0.721e9 / 64,                         # profiles/r02e_zrlt_launches.md (mask walks, staged stores)
         "ans0_encode_kernel": 0.458e9 / 64,
         "ans0_decode_kernel": 0.248e9 / 64,
-        "zrlt_inverse": 1.068e9 / 64,
+        "zrlt_inverse": 0.825e9 / 64,                         # profiles/r02e_zrlt_launches.md
         "bwt_inverse": 24.261e9 / 64,
         "rank_inverse": (1.096665e9 + 1.040414e9) / 256,      # profiles/r02_ncu_rank_256blocks.md (--set full)
     }

@@ -365,3 +365,62 @@ def test_gpu_rejects_oversized_parameters(gpu):
     with pytest.raises(KanziGpuError) as e:
         gpu.decompress(bad, data.size)
     assert e.value.code == 19  # ERR_CRC_CHECK
+
+
+def test_gpu_zrlt_mask_walks(gpu, oracle):
+    """ZRLT's mask-form summaries / walks, the staged tile output and the warp fold: zero runs of every length class
+    inside a segment, across segments and tiles, dense 0xFE / 0xFF, ragged lengths (inputs shared with the emulator test)."""
+    from test_sim_kernels import _zrlt_inputs
+    cases = dict(_zrlt_inputs())
+    big = synth.synth_compressible(2 << 20, 11).copy()
+    big[np.random.default_rng(5).random(big.size) < 0.6] = 0
+    cases["sparse_2m"] = big
+    for name, data in cases.items():
+        n = data.size
+        cap = 2 * n + 64
+        a, applied = gpu.transform_forward("ZRLT", data, cap)
+        b, flags = oracle.sequence_forward("ZRLT", data, n, cap)
+        assert applied == (flags != 0xFF), (name, applied, flags)
+        if applied:
+            assert a.size == b.size and np.array_equal(a, b), (name, _first_diff(a, b))
+            back, ok = gpu.transform_inverse("ZRLT", b, n + 64)
+            assert ok and np.array_equal(back, data), name
+
+
+def test_gpu_zrlt_inverse_token_classes(gpu, oracle):
+    """Inverse ZRLT on arbitrary token streams (runs of 0xFF: lead / payload alternate) against the oracle."""
+    from kanzi_b200 import KanziGpuError
+    rng = np.random.default_rng(7)
+    alphabet = np.array([0, 1, 0xFF, 0xFF, 2, 3, 0x80, 0xFE], dtype=np.uint8)
+    for n in (16, 33, 4096, 5000, 12345, 300001):
+        for trial in range(3):
+            src = alphabet[rng.integers(0, alphabet.size, n)]
+            if trial == 2:
+                src[rng.random(n) < 0.5] = 0xFF
+            want, ok = oracle.sequence_inverse("ZRLT", 0, src, 1 << 21)
+            try:
+                got, applied = gpu.transform_inverse("ZRLT", src, 1 << 21)
+            except KanziGpuError:
+                assert not ok, (n, trial)
+                continue
+            assert bool(ok) == applied, (n, trial)
+            if ok:
+                assert got.size == want.size and np.array_equal(got, want), (n, trial)
+
+
+def test_gpu_rank_deep_steps(gpu, oracle):
+    """RANK / MTFT on inputs whose ranks are mostly >= 32 (uniform bytes, a byte random walk, sparse symbols): the deep
+    step of the inverse chain and of the forward replay."""
+    rng = np.random.default_rng(5)
+    inputs = {"random": rng.integers(0, 256, 1 << 18, dtype=np.uint8),
+              "walk": np.cumsum(rng.integers(-3, 4, 1 << 18)).astype(np.uint8),
+              "cycle": (np.arange(1 << 17) * 37 % 251).astype(np.uint8)}
+    for tname in ("RANK", "MTFT"):
+        for name, data in inputs.items():
+            n = data.size
+            a, applied = gpu.transform_forward(tname, data, n + 64)
+            b, flags = oracle.sequence_forward(tname, data, n, n + 64)
+            assert applied == (flags != 0xFF), (name, tname)
+            assert a.size == b.size and np.array_equal(a, b), (name, tname, _first_diff(a, b))
+            back, ok = gpu.transform_inverse(tname, b, n + 64)
+            assert ok and np.array_equal(back, data), (name, tname)

@@ -5,9 +5,11 @@
 // digit per byte (0/1); v -> v+1; 0xFE/0xFF -> 0xFF, v-0xFE.
 // The sequential scanner is replaced by a three-step scan: each 16-byte thread
 // segment is summarised by an associative element (leading run, interior output
-// bytes, trailing run), CTA tiles are reduced, one thread per block folds the
+// bytes, trailing run), CTA tiles are reduced, one warp per block folds the
 // tile summaries into tile entry states, and the emit pass re-walks each segment
-// from its exact entry state.  Algorithmic traffic: n read twice + z written.
+// from its exact entry state; a tile's output is one contiguous range, staged in
+// shared memory and written as aligned 128-bit stores.  Traffic: n read twice +
+// z written (forward); the inverse also zero-fills its output first.
 // Whole 16-byte segments are summarised and walked through 16-bit byte-class MASKS
 // (zero / non-zero, >= 0xFE, digit, escape lead, payload): run lengths come from
 // ffs / clz / popc and the walks visit tokens, not bytes, so lanes do not each follow

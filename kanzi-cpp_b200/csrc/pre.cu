@@ -287,6 +287,16 @@ bool alias_inverse(const u8* src, int n, u8* dst, int cap, int* outLen)
             return false;
         for (int i = 0; i < k; i++, s += 3)
             expand[src[s + 2]] = 0x20000u | src[s] | ((u32)src[s + 1] << 8);
+        // 256 input bytes at a time while even 256 digrams fit the destination: two bytes stored per input
+        // byte without a check (the second one is overwritten by the next store when the entry is a single byte)
+        while (end - s >= 256 && d + 512 <= cap) {
+            for (const int stop = s + 256; s < stop; s++) {
+                const u32 e = expand[src[s]];
+                dst[d] = (u8)e;
+                dst[d + 1] = (u8)(e >> 8);
+                d += (int)(e >> 16);
+            }
+        }
         for (; s < end; s++) {
             const u32 e = expand[src[s]];
             const int len = (int)(e >> 16);

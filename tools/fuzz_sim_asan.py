@@ -25,7 +25,7 @@ if mode == "stages":
         x = a[rng.integers(0, a.size, n)]
         if rng.random() < 0.3:  # plausible headers: small little-endian / varint fields up front
             x[: min(n, 16)] = rng.integers(0, 4, min(n, 16))
-        for t in ("ZRLT", "RANK", "MTFT", "BWT", "SRT", "LZ", "LZX", "LZP"):
+        for t in ("ZRLT", "RANK", "MTFT", "BWT", "SRT", "LZ", "LZX", "LZP", "PACK", "DNA", "MM", "UTF", "TEXT"):
             try:
                 sim.transform_inverse(t, x, int(rng.integers(1, 70000)))
             except KanziGpuError:

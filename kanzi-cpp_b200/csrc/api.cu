@@ -569,6 +569,12 @@ int knz_encode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8
         launch_xxhash(bt, ctx->st, nB, ctx->checksumBits, ctx->blockHash, NULL, ctx->errFlag, s, &ctx->launches);
     if (ctx->skipBlocks) // entropy / signature test (io/CompressedOutputStream.cpp:697-715)
         launch_skip_decide(bt, ctx->st, nB, ctx->dLog2Tab, ctx->dSkip, s, &ctx->launches);
+    // Upper bound of the block lengths a stage may meet (its launches size their grids with it): 33 bytes per
+    // stage so far (the BWT header; bwt.cu subtracts exactly that to recover its input bound), the SRT header
+    // (up to 1024 bytes, transform/SRT.hpp:38) once an SRT stage is involved, and whatever a slot can hold behind a
+    // ZRLT stage, which may legally expand a block at odd swap parity (reference quirk 2).
+    int grown = 0;
+    bool afterZrlt = false;
     for (int i = hs; i < nt; i++) {
         StageLaunch L;
         L.bt = bt;
@@ -577,7 +583,13 @@ int knz_encode_batch(knz_ctx* ctx, u64 tType, int eType, int blockSize, const u8
         L.dtype = (hs > 0) ? ctx->dDtype : NULL;
         L.stageIdx = i;
         L.nBlocks = nB;
-        L.maxLen = maxLen + 33 * (i + 1);
+        if (types[i] == T_SRT)
+            grown += 1024 - 33;
+        L.maxLen = maxLen + 33 * (i + 1) + grown;
+        if (afterZrlt || L.maxLen > ctx->stageCap)
+            L.maxLen = ctx->stageCap;
+        if (types[i] == T_ZRLT)
+            afterZrlt = true;
         L.capEven = ctx->capEven;
         L.capOdd = ctx->capOdd;
         L.errFlag = ctx->errFlag;

@@ -424,3 +424,8 @@ def test_gpu_rank_deep_steps(gpu, oracle):
             assert a.size == b.size and np.array_equal(a, b), (name, tname, _first_diff(a, b))
             back, ok = gpu.transform_inverse(tname, b, n + 64)
             assert ok and np.array_equal(back, data), (name, tname)
+
+
+def test_gpu_srt_header_across_tile_edge(gpu, oracle):
+    from test_sim_kernels import check_srt_header_across_tile_edge
+    check_srt_header_across_tile_edge(gpu, oracle)

@@ -333,3 +333,22 @@ def test_sim_zrlt_inverse_token_classes(sim, oracle):
             assert bool(ok) == applied, (n, trial)
             if ok:
                 assert got.size == want.size and np.array_equal(got, want), (n, trial)
+
+
+SRT_EDGE_SIZES = (40760, 4096 * 3 - 200, 4096 * 5 - 150)
+
+
+def check_srt_header_across_tile_edge(ctx, oracle):
+    """A ragged block whose SRT header (256 .. 1024 bytes) carries the length over a 4 KiB tile edge that the
+    33-bytes-per-stage bound does not reach: the stage behind SRT must still see every byte (found by tools/fuzz_sim.py)."""
+    for n in SRT_EDGE_SIZES:
+        data = synth.synth_text(n, 1)
+        for tname, ename in (("BWT+SRT+ZRLT", "ANS0"), ("SRT+ZRLT", "NONE")):
+            got = ctx.compress(data, tname, ename, 65536)
+            want = oracle.stream_compress(data, tname, ename, 65536)
+            assert got.size == want.size and np.array_equal(got, want), (n, tname, ename)
+            assert np.array_equal(ctx.decompress(got, n), data), (n, tname, ename)
+
+
+def test_sim_srt_header_across_tile_edge(sim, oracle):
+    check_srt_header_across_tile_edge(sim, oracle)

@@ -17,7 +17,9 @@ assert ref is not None, "needs oracle/_ref (make -C oracle ref)"
 sim = Context(0, 1 << 18, 4, lib_path=os.path.join(ROOT, "tests", "sim", "libknzsim.so"))
 PIPES = [("BWT+RANK+ZRLT", "ANS0"), ("BWT+MTFT+ZRLT", "HUFFMAN"), ("ZRLT", "ANS0"), ("RANK", "NONE"), ("ZRLT", "NONE"),
          ("BWT+SRT+ZRLT", "ANS0"), ("NONE", "ANS1"), ("LZ+ZRLT", "HUFFMAN"), ("LZX", "ANS0"), ("LZP", "NONE"),
-         ("TEXT+UTF+BWT+RANK+ZRLT", "ANS0"), ("MTFT+ZRLT", "ANS0")]
+         ("TEXT+UTF+BWT+RANK+ZRLT", "ANS0"), ("MTFT+ZRLT", "ANS0"), ("BWT+SRT+ZRLT", "FPAQ"), ("LZP+LZX", "HUFFMAN"),
+         ("TEXT+UTF+PACK+MM+LZX", "HUFFMAN"), ("DNA+LZ", "HUFFMAN"), ("SRT", "ANS1"), ("BWT", "NONE"), ("NONE", "HUFFMAN"),
+         ("SRT+ZRLT", "NONE"), ("BWT+SRT", "ANS0"), ("PACK+LZX", "ANS0"), ("MM+LZ", "NONE"), ("UTF+BWT+RANK+ZRLT", "HUFFMAN")]
 
 
 def gen(n):
